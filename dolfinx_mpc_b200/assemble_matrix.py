@@ -1,0 +1,155 @@
+"""``assemble_matrix`` / ``create_sparsity_pattern`` / ``create_matrix`` -- the reference's Python surface
+(``python/src/dolfinx_mpc/assemble_matrix.py:21-146``) in front of the device kernels."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from collections.abc import Sequence
+from typing import Optional, Union
+
+import numpy as np
+
+from . import _lib
+from . import device as _dev
+from .fem import DirichletBC, Form
+from .la import Matrix
+from .multipointconstraint import MultiPointConstraint
+
+
+def _pair(constraint):
+    if isinstance(constraint, Sequence):
+        assert len(constraint) == 2
+        return tuple(constraint)
+    return (constraint, constraint)
+
+
+def _mpc_host(mpc: MultiPointConstraint):
+    keep = (np.ascontiguousarray(mpc.masters.array), np.ascontiguousarray(mpc.masters.offsets),
+            np.ascontiguousarray(mpc.cell_to_slaves.array), np.ascontiguousarray(mpc.cell_to_slaves.offsets))
+    return _lib.MpcHostS(*[k.ctypes.data for k in keep]), keep
+
+
+def create_sparsity_pattern(form: Form, mpc: Union[MultiPointConstraint, Sequence[MultiPointConstraint]],
+                            num_threads: int = 0):
+    """Sparsity pattern with the MPC additions (``assemble_matrix.py:68-88`` -> ``cpp/utils.h:381-496``).
+
+    Returns ``(row_ptr int64, col int32)`` of the scalar CSR over the local (owned + ghost) rows of the
+    constraints' function spaces.
+    """
+    mpc0, mpc1 = _pair(mpc)
+    for m in (mpc0, mpc1):
+        m._not_finalized()
+    if form.rank != 2:
+        raise RuntimeError("Cannot create sparsity pattern. Form is not a bilinear form")
+    lib = _lib.load()
+    V0, V1 = form.function_spaces
+    nrows_b = mpc0.function_space.num_blocks
+    h0, k0 = _mpc_host(mpc0)
+    h1, k1 = _mpc_host(mpc1)
+    rp = C.POINTER(C.c_int64)()
+    cl = C.POINTER(C.c_int32)()
+    nnz = C.c_int64(0)
+    nc = form.mesh.num_cells_local
+    _lib.check(lib.mpcx_create_pattern_host(V0.dofmap.ctypes.data, V0.nd, V0.bs, V1.dofmap.ctypes.data, V1.nd, V1.bs,
+                                            nc, nrows_b, C.byref(h0), C.byref(h1),
+                                            num_threads or (os.cpu_count() or 1), C.byref(rp), C.byref(cl),
+                                            C.byref(nnz)))
+    nrows = nrows_b * V0.bs
+    row_ptr = np.ctypeslib.as_array(rp, shape=(nrows + 1,)).copy()
+    col = np.ctypeslib.as_array(cl, shape=(max(1, nnz.value),))[: nnz.value].copy()
+    lib.mpcx_free_host(rp)
+    lib.mpcx_free_host(cl)
+    return row_ptr, col
+
+
+def create_matrix(form: Form, mpc0: MultiPointConstraint, mpc1: Optional[MultiPointConstraint] = None) -> Matrix:
+    """``cpp.mpc.create_matrix`` (``cpp/utils.h:140-173``): pattern + zeroed device CSR."""
+    mpc1 = mpc0 if mpc1 is None else mpc1
+    row_ptr, col = create_sparsity_pattern(form, (mpc0, mpc1))
+    shape = (mpc0.function_space.num_dofs, mpc1.function_space.num_dofs)
+    bs = (form.function_spaces[0].bs, form.function_spaces[1].bs)
+    return Matrix(row_ptr, col, shape, bs)
+
+
+def _bc_markers(V, bcs, n: int):
+    """int8 marker over the unrolled dofs of ``V`` or None when no bc lives on it
+    (``cpp/assemble_matrix.cpp:687-705``)."""
+    mine = [bc for bc in bcs if bc.function_space is V or bc.function_space.dofmap is V.dofmap]
+    if not mine:
+        return None
+    m = np.zeros(n, dtype=np.int8)
+    for bc in mine:
+        bc.mark_dofs(m)
+    return m
+
+
+def assemble_matrix(form: Form, constraint: Union[MultiPointConstraint, Sequence[MultiPointConstraint]],
+                    bcs: Optional[Sequence[DirichletBC]] = None, diagval: float = 1.0, A: Optional[Matrix] = None,
+                    num_threads: Optional[int] = 1) -> Matrix:
+    """Assemble a bilinear form into a device CSR matrix with multi point constraints and Dirichlet
+    conditions; same arguments as the reference (``python/src/dolfinx_mpc/assemble_matrix.py:21-65``).
+    ``num_threads`` is accepted and ignored."""
+    bcs = [] if bcs is None else list(bcs)
+    if not isinstance(constraint, Sequence):
+        assert form.function_spaces[0] is form.function_spaces[1]
+    mpc0, mpc1 = _pair(constraint)
+    lib = _lib.load()
+    if A is None:
+        A = create_matrix(form, mpc0, mpc1)
+    A.zeroEntries()
+    V0, V1 = form.function_spaces
+    st = _dev.stream_ptr()
+    bc0 = _bc_markers(V0, bcs, A.shape[0])
+    bc1 = _bc_markers(V1, bcs, A.shape[1])
+    bc0_d = None if bc0 is None else _dev.to_dev(bc0)
+    bc1_d = bc0_d if (bc1 is not None and bc0 is not None and V0 is V1) else (None if bc1 is None else _dev.to_dev(bc1))
+    mesh_s = _dev.mesh_dev(form.mesh)["struct"]
+    d0 = _dev.dofmap_struct(V0, A.shape[0])
+    d1 = _dev.dofmap_struct(V1, A.shape[1])
+    m0 = _dev.mpc_dev(mpc0)["struct"]
+    m1 = _dev.mpc_dev(mpc1)["struct"]
+    As = A.struct()
+    keep = []
+    for it in form.integrals:
+        if it.integral_type != "cell":
+            raise RuntimeError(f"{it.integral_type} integrals have no device kernel yet")
+        s = _dev.integral_struct(form, it, (mpc0, mpc1), keep)
+        plan = A.plan(form, it)
+        _lib.check(lib.mpcx_assemble_matrix_f64(C.byref(s), C.byref(mesh_s), C.byref(d0), C.byref(d1),
+                                                _dev.ptr(bc0_d), _dev.ptr(bc1_d), C.byref(m0), C.byref(m1),
+                                                C.byref(As), None if plan is None else C.byref(plan), st))
+    # slave diagonal for owned slaves when both sides share the constraint space (cpp/assemble_matrix.cpp:711-724)
+    if mpc0.function_space is mpc1.function_space and mpc0.num_local_slaves > 0:
+        sl = _dev.mpc_dev(mpc0)["slaves"]
+        _lib.check(lib.mpcx_add_diagonal_f64(C.byref(As), _dev.ptr(sl), mpc0.num_local_slaves, float(diagval), st))
+    # Dirichlet diagonal (assemble_matrix.py:59-62 -> dolfinx insert_diagonal: owned dofs of every bc)
+    if V0 is V1:
+        n_owned = V0.index_map.size_local * V0.bs
+        for bc in bcs:
+            if bc.function_space is V0 or bc.function_space.dofmap is V0.dofmap:
+                dofs = bc.dofs[bc.dofs < n_owned]
+                if len(dofs):
+                    t = _dev.to_dev(dofs)
+                    keep.append(t)
+                    _lib.check(lib.mpcx_add_diagonal_f64(C.byref(As), _dev.ptr(t), len(dofs), float(diagval), st))
+    _lib.check(lib.mpcx_device_error(st))
+    A.assemble()
+    return A
+
+
+def create_matrix_nest(a: Sequence[Sequence[Optional[Form]]], constraints: Sequence[MultiPointConstraint]):
+    """Block list of matrices with MPC sparsity (``assemble_matrix.py:91-115``); a nested list stands in for
+    the PETSc "nest" Mat."""
+    assert len(constraints) == len(a)
+    return [[None if a[i][j] is None else create_matrix(a[i][j], constraints[i], constraints[j])
+             for j in range(len(a[0]))] for i in range(len(a))]
+
+
+def assemble_matrix_nest(A, a: Sequence[Sequence[Optional[Form]]], constraints: Sequence[MultiPointConstraint],
+                         bcs: Sequence[DirichletBC] = (), diagval: float = 1.0, num_threads: Optional[int] = 1):
+    """``assemble_matrix.py:118-146``."""
+    for i, a_row in enumerate(a):
+        for j, a_block in enumerate(a_row):
+            if a_block is not None:
+                assemble_matrix(a_block, (constraints[i], constraints[j]), bcs=bcs, diagval=diagval, A=A[i][j],
+                                num_threads=num_threads)

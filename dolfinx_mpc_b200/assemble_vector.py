@@ -1,0 +1,113 @@
+"""``assemble_vector`` / ``apply_lifting`` -- the reference's Python surface
+(``python/src/dolfinx_mpc/assemble_vector.py:25-147``) in front of the device kernels."""
+from __future__ import annotations
+
+import ctypes as C
+from collections.abc import Sequence
+from typing import Optional
+
+import numpy as np
+
+from . import _lib
+from . import device as _dev
+from .fem import DirichletBC, Form
+from .la import Vector
+from .multipointconstraint import MultiPointConstraint
+
+
+def create_vector(constraint: MultiPointConstraint) -> Vector:
+    return Vector(constraint.function_space.num_dofs)
+
+
+def assemble_vector(form: Form, constraint: MultiPointConstraint, b: Optional[Vector] = None,
+                    num_threads: Optional[int] = 1) -> Vector:
+    """Assemble a linear form into ``b`` with the multi point constraint applied (``K^T b``);
+    ``b`` is zeroed first, as the reference's wrapper does (``assemble_vector.py:79-104``)."""
+    lib = _lib.load()
+    constraint._not_finalized()
+    if b is None:
+        b = create_vector(constraint)
+    b.set(0.0)
+    V = form.function_spaces[0]
+    st = _dev.stream_ptr()
+    mesh_s = _dev.mesh_dev(form.mesh)["struct"]
+    dm = _dev.dofmap_struct(V, constraint.function_space.num_dofs)
+    m = _dev.mpc_dev(constraint)["struct"]
+    keep = []
+    for it in form.integrals:
+        if it.integral_type != "cell":
+            raise RuntimeError(f"{it.integral_type} integrals have no device kernel yet")
+        s = _dev.integral_struct(form, it, (constraint,), keep)
+        _lib.check(lib.mpcx_assemble_vector_f64(C.byref(s), C.byref(mesh_s), C.byref(dm), C.byref(m),
+                                                _dev.ptr(b.data), st))
+    return b
+
+
+def apply_lifting(b: Vector, form: Sequence[Form], bcs: Sequence[Sequence[DirichletBC]],
+                  constraint: MultiPointConstraint, x0: Optional[Sequence] = None, scale: float = 1.0,
+                  num_threads: Optional[int] = 1):
+    """``b <- b - scale * K^T A_j (g_j - x0_j)`` (``assemble_vector.py:25-76`` -> ``cpp/lifting.h:441-670``)."""
+    lib = _lib.load()
+    constraint._not_finalized()
+    x0 = [] if x0 is None else list(x0)
+    # argument checks of cpp/lifting.h:452-465
+    if len(x0) and len(x0) != len(form):
+        raise RuntimeError("Mismatch in size between x0 and bilinear form in assembler.")
+    if len(form) != len(bcs):
+        raise RuntimeError("Mismatch in size between a and bcs in assembler.")
+    st = _dev.stream_ptr()
+    keep = []
+    for j, a in enumerate(form):
+        if a is None:
+            continue
+        V0, V1 = a.function_spaces
+        n1 = V1.num_dofs
+        markers = np.zeros(n1, dtype=np.int8)  # cpp/lifting.h:166-180
+        values = np.zeros(n1, dtype=np.float64)
+        for bc in bcs[j]:
+            bc.mark_dofs(markers)
+            bc.set(values)
+        if not markers.any():
+            continue
+        mk, vl = _dev.to_dev(markers), _dev.to_dev(values)
+        x0_d = None
+        if len(x0):
+            x0_d = x0[j].data if isinstance(x0[j], Vector) else _dev.to_dev(np.asarray(x0[j], dtype=np.float64))
+        keep += [mk, vl, x0_d]
+        mesh_s = _dev.mesh_dev(a.mesh)["struct"]
+        d0 = _dev.dofmap_struct(V0, constraint.function_space.num_dofs)
+        d1 = _dev.dofmap_struct(V1, n1)
+        m0 = _dev.mpc_dev(constraint)["struct"]
+        for it in a.integrals:
+            if it.integral_type != "cell":
+                raise RuntimeError(f"{it.integral_type} integrals have no device kernel yet")
+            s = _dev.integral_struct(a, it, (constraint,), keep)
+            _lib.check(lib.mpcx_apply_lifting_f64(C.byref(s), C.byref(mesh_s), C.byref(d0), C.byref(d1),
+                                                  _dev.ptr(mk), _dev.ptr(vl), _dev.ptr(x0_d), float(scale),
+                                                  C.byref(m0), _dev.ptr(b.data), st))
+
+
+def set_bc(b: Vector, bcs: Sequence[DirichletBC], x0=None, scale: float = 1.0):
+    """``dolfinx.fem.petsc.set_bc``: b[dofs] = scale * (g - x0) on owned bc dofs (host-side index write)."""
+    import torch
+
+    for bc in bcs:
+        vals = np.zeros(b.data.numel())
+        bc.set(vals)
+        n_owned = bc.function_space.index_map.size_local * bc.function_space.bs
+        dofs = bc.dofs[bc.dofs < n_owned]
+        g = vals[dofs] - (0.0 if x0 is None else np.asarray(x0)[dofs])
+        b.data[torch.from_numpy(dofs.astype(np.int64)).to(b.data.device)] = torch.from_numpy(scale * g).to(b.data.device)
+
+
+def create_vector_nest(L: Sequence[Form], constraints: Sequence[MultiPointConstraint]):
+    assert len(constraints) == len(L)
+    return [create_vector(c) for c in constraints]
+
+
+def assemble_vector_nest(b, L: Sequence[Form], constraints: Sequence[MultiPointConstraint],
+                         num_threads: Optional[int] = 1):
+    """``assemble_vector.py:130-147``."""
+    assert len(constraints) == len(L)
+    for i, L_row in enumerate(L):
+        assemble_vector(L_row, constraints[i], b=b[i], num_threads=num_threads)

@@ -1,0 +1,897 @@
+// mpcx_kernels.cu -- sm_100a kernels and C ABI of the MPC-constrained assembly engine.
+//
+// Replaces the per-cell loops of the reference (cpp/assemble_matrix.cpp:417-548 and
+// 99-268, cpp/assemble_vector.cpp:34-91, cpp/assemble_vector.h:35-69, cpp/lifting.h:
+// 45-134,250-301, cpp/assemble_utils.cpp:10-28).  Not a port: the reference walks cells
+// serially, copies A_e twice per slave cell and issues one PETSc insertion call per
+// master row/column/pair.  Here the elimination is expressed as
+//      G[t_p, t_q] += w_p * w_q * A_e[p, q]
+// over per-dof target lists (a free dof targets itself with weight 1, a slave targets
+// its masters with weights alpha), which is K^T A_e K written entry-wise, so one pass
+// over A_e feeds the device CSR directly with red.global.add.f64.
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "mpcx.h"
+
+namespace
+{
+thread_local char g_err[512] = "";
+__device__ int g_dev_err = 0;
+
+int fail(int code, const char* fmt, const char* a = "")
+{
+  snprintf(g_err, sizeof(g_err), fmt, a);
+  return code;
+}
+int cuda_check(cudaError_t e, const char* where)
+{
+  if (e == cudaSuccess) return MPCX_OK;
+  snprintf(g_err, sizeof(g_err), "CUDA error in %s: %s", where, cudaGetErrorString(e));
+  return MPCX_ERR_CUDA;
+}
+
+// ------------------------------------------------------------------ device structs
+struct Tab
+{
+  int tdim, gdim, nd, ng, nq, bs;
+  const double *w, *phi, *dphi, *gdphi;
+};
+struct MeshD
+{
+  const double* x;
+  const int* xd;
+  int ng, xs;
+};
+struct MpcD
+{
+  const int8_t* is_slave;
+  const int* masters;
+  const double* coeffs;
+  const int* offsets;
+  const int* c2s_off;
+};
+struct CsrD
+{
+  const long long* rp;
+  const int* col;
+  double* val;
+};
+struct IntD
+{
+  int kernel;
+  const int* cells;
+  long long ncells;
+  const double* coeffs;
+  int cstride;
+  const double* wnodal;
+  const int* wmap;
+  int wnd, wbs;
+  double c[MPCX_MAX_CONSTANTS];
+  const int* slave_cells;
+  long long nslave_cells;
+};
+
+__device__ __forceinline__ long long csr_find(const CsrD& A, int row, int c)
+{
+  long long lo = A.rp[row], hi = A.rp[row + 1];
+  const long long end = hi;
+  while (lo < hi)
+  {
+    const long long mid = (lo + hi) >> 1;
+    if (__ldg(A.col + mid) < c) lo = mid + 1; else hi = mid;
+  }
+  return (lo < end && __ldg(A.col + lo) == c) ? lo : -1;
+}
+
+__device__ __forceinline__ void csr_add(const CsrD& A, int row, int c, double v)
+{
+  const long long p = csr_find(A, row, c);
+  if (p >= 0) atomicAdd(A.val + p, v);
+  else g_dev_err = MPCX_ERR_PATTERN;
+}
+
+// Geometry at quadrature point q (all lanes redundantly): K = J^-1 as K[a*3+k], detJ.
+__device__ __forceinline__ void jacobian(const Tab& t, int q, const double* X, double* K, double& detJ)
+{
+  double J[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+  for (int a = 0; a < t.tdim; ++a)
+    for (int g = 0; g < t.ng; ++g)
+    {
+      const double d = __ldg(t.gdphi + (q * t.tdim + a) * t.ng + g);
+      for (int k = 0; k < t.gdim; ++k) J[k * 3 + a] += X[3 * g + k] * d;
+    }
+  if (t.tdim == 2)
+  {
+    const double det = J[0] * J[4] - J[1] * J[3];
+    detJ = det;
+    K[0] = J[4] / det; K[1] = -J[1] / det; K[3] = -J[3] / det; K[4] = J[0] / det;
+    K[2] = K[5] = K[6] = K[7] = K[8] = 0.0;
+  }
+  else
+  {
+    const double c00 = J[4] * J[8] - J[5] * J[7];
+    const double c01 = J[5] * J[6] - J[3] * J[8];
+    const double c02 = J[3] * J[7] - J[4] * J[6];
+    const double det = J[0] * c00 + J[1] * c01 + J[2] * c02;
+    detJ = det;
+    K[0] = c00 / det;
+    K[1] = (J[2] * J[7] - J[1] * J[8]) / det;
+    K[2] = (J[1] * J[5] - J[2] * J[4]) / det;
+    K[3] = c01 / det;
+    K[4] = (J[0] * J[8] - J[2] * J[6]) / det;
+    K[5] = (J[2] * J[3] - J[0] * J[5]) / det;
+    K[6] = c02 / det;
+    K[7] = (J[1] * J[6] - J[0] * J[7]) / det;
+    K[8] = (J[0] * J[4] - J[1] * J[3]) / det;
+  }
+}
+
+// Warp-cooperative tabulated-quadrature element tensor into shared memory.
+// out: [n][n] (bilinear) or [n] (SOURCE); g: scratch [nd][3]; w: packed coefficients.
+__device__ void tabulate_warp(const Tab& t, int kernel, const double* c, const double* X,
+                              const double* w, double* out, double* g, int lane)
+{
+  const int nd = t.nd, bs = t.bs, n = nd * bs;
+  const int nout = (kernel == MPCX_KERNEL_SOURCE) ? n : n * n;
+  for (int e = lane; e < nout; e += 32) out[e] = 0.0;
+  __syncwarp();
+  for (int q = 0; q < t.nq; ++q)
+  {
+    double K[9], detJ;
+    jacobian(t, q, X, K, detJ);
+    const double s = __ldg(t.w + q) * fabs(detJ);
+    const double* phi = t.phi + q * nd;
+    if (kernel == MPCX_KERNEL_MASS)
+    {
+      const double sc = c[0] * s;
+      for (int pr = lane; pr < nd * nd; pr += 32)
+      {
+        const int i = pr / nd, j = pr - i * nd;
+        const double d = sc * __ldg(phi + i) * __ldg(phi + j);
+        for (int b = 0; b < bs; ++b) out[(i * bs + b) * n + j * bs + b] += d;
+      }
+    }
+    else if (kernel == MPCX_KERNEL_SOURCE)
+    {
+      const double sc = c[0] * s;
+      for (int e = lane; e < n; e += 32)
+      {
+        const int i = e / bs, a = e - i * bs;
+        double fq = 0.0;
+        for (int j = 0; j < nd; ++j) fq += __ldg(phi + j) * w[j * bs + a];
+        out[e] += sc * fq * __ldg(phi + i);
+      }
+    }
+    else
+    {
+      for (int e = lane; e < nd * t.gdim; e += 32)
+      {
+        const int i = e / t.gdim, k = e - i * t.gdim;
+        double sum = 0.0;
+        for (int a = 0; a < t.tdim; ++a) sum += K[a * 3 + k] * __ldg(t.dphi + (q * t.tdim + a) * nd + i);
+        g[i * 3 + k] = sum;
+      }
+      __syncwarp();
+      if (kernel == MPCX_KERNEL_ELASTICITY)
+      {
+        const double mu = c[0], lmbda = c[1];
+        for (int pr = lane; pr < nd * nd; pr += 32)
+        {
+          const int i = pr / nd, j = pr - i * nd;
+          double dot = 0.0;
+          for (int k = 0; k < t.gdim; ++k) dot += g[i * 3 + k] * g[j * 3 + k];
+          for (int a = 0; a < bs; ++a)
+            for (int b = 0; b < bs; ++b)
+            {
+              double v = mu * g[i * 3 + b] * g[j * 3 + a] + lmbda * g[i * 3 + a] * g[j * 3 + b];
+              if (a == b) v += mu * dot;
+              out[(i * bs + a) * n + j * bs + b] += s * v;
+            }
+        }
+      }
+      else
+      {
+        double sc = c[0] * s;
+        if (kernel == MPCX_KERNEL_LAPLACE_VARCOEF)
+        {
+          double kap = 0.0;
+          for (int k = 0; k < nd; ++k) kap += __ldg(phi + k) * w[k];
+          sc *= kap;
+        }
+        for (int pr = lane; pr < nd * nd; pr += 32)
+        {
+          const int i = pr / nd, j = pr - i * nd;
+          double d = 0.0;
+          for (int k = 0; k < t.gdim; ++k) d += g[i * 3 + k] * g[j * 3 + k];
+          d *= sc;
+          for (int b = 0; b < bs; ++b) out[(i * bs + b) * n + j * bs + b] += d;
+        }
+      }
+      __syncwarp();
+    }
+  }
+  __syncwarp();
+}
+
+// Loads geometry, dofs and coefficients of one cell into the warp's shared memory.
+__device__ __forceinline__ void load_cell(const MeshD& m, const IntD& in, long long index, int cell,
+                                          double* X, double* w, int lane)
+{
+  for (int e = lane; e < m.ng * 3; e += 32)
+  {
+    const int gi = e / 3, k = e - gi * 3;
+    X[e] = __ldg(m.x + (long long)__ldg(m.xd + (long long)cell * m.ng + gi) * m.xs + k);
+  }
+  if (in.coeffs)
+    for (int e = lane; e < in.cstride; e += 32) w[e] = __ldg(in.coeffs + index * in.cstride + e);
+  else if (in.wnodal)
+    for (int e = lane; e < in.wnd * in.wbs; e += 32)
+    {
+      const int j = e / in.wbs, a = e - j * in.wbs;
+      w[e] = __ldg(in.wnodal + (long long)__ldg(in.wmap + (long long)cell * in.wnd + j) * in.wbs + a);
+    }
+}
+
+// ------------------------------------------------------------------ generic kernels
+// One warp per cell; A_e in shared memory; handles every element, BCs and slaves.
+// mode 0: all active cells.  mode 1: only the listed slave cells (positions in the
+// active list).  When a plan is given, cells without slaves use the precomputed offsets.
+template <typename PosT>
+__global__ void __launch_bounds__(128)
+k_matrix_generic(Tab t, IntD in, MeshD mesh, const int* __restrict__ dm0, const int* __restrict__ dm1,
+                 int nd0, int nd1, int bs0, int bs1, const int8_t* __restrict__ bc0,
+                 const int8_t* __restrict__ bc1, MpcD m0, MpcD m1, CsrD A, const PosT* __restrict__ lpos,
+                 int mode, int smem_per_warp)
+{
+  extern __shared__ double smem[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int n0 = nd0 * bs0, n1 = nd1 * bs1;
+  double* base = smem + (size_t)warp * smem_per_warp;
+  double* X = base;
+  double* Ae = X + 3 * mesh.ng;
+  double* g = Ae + n0 * n1;
+  double* w = g + 3 * t.nd;
+  int* d0 = (int*)(w + (in.cstride > 0 ? in.cstride : 1));
+  int* d1 = d0 + nd0;
+  const long long nwork = mode == 1 ? in.nslave_cells : in.ncells;
+  const long long wstride = (long long)gridDim.x * (blockDim.x >> 5);
+  for (long long it = (long long)blockIdx.x * (blockDim.x >> 5) + warp; it < nwork; it += wstride)
+  {
+    const long long index = mode == 1 ? (long long)__ldg(in.slave_cells + it) : it;
+    const int cell = in.cells ? __ldg(in.cells + index) : (int)index;
+    const bool has_slaves = (__ldg(m0.c2s_off + cell + 1) > __ldg(m0.c2s_off + cell))
+                            || (__ldg(m1.c2s_off + cell + 1) > __ldg(m1.c2s_off + cell));
+    if (mode == 2 && has_slaves) continue;  // bulk pass of a split launch
+    __syncwarp();
+    load_cell(mesh, in, index, cell, X, w, lane);
+    for (int e = lane; e < nd0; e += 32) d0[e] = __ldg(dm0 + (long long)cell * nd0 + e);
+    for (int e = lane; e < nd1; e += 32) d1[e] = __ldg(dm1 + (long long)cell * nd1 + e);
+    __syncwarp();
+    tabulate_warp(t, in.kernel, in.c, X, w, Ae, g, lane);
+    for (int e = lane; e < n0 * n1; e += 32)
+    {
+      const int p = e / n1, q = e - p * n1;
+      const int ib = p / bs0, ia = p - ib * bs0, jb = q / bs1, ja = q - jb * bs1;
+      const int r = d0[ib] * bs0 + ia, cc = d1[jb] * bs1 + ja;
+      // BC zeroing precedes elimination (cpp/assemble_matrix.cpp:513-545); a zeroed entry
+      // contributes nothing anywhere, so it is skipped.
+      if ((bc0 && bc0[r]) || (bc1 && bc1[cc])) continue;
+      const double v = Ae[e];
+      if (!has_slaves)
+      {
+        if (lpos)
+        {
+          const long long pos = A.rp[r] + (long long)lpos[index * (nd0 * nd1) + ib * nd1 + jb] * bs1 + ja;
+          atomicAdd(A.val + pos, v);
+        }
+        else
+          csr_add(A, r, cc, v);
+        continue;
+      }
+      // K^T A_e K entry-wise (cpp/assemble_matrix.cpp:214-267): target lists of row and column dof
+      const bool sr = m0.is_slave[r], sc = m1.is_slave[cc];
+      const int r0 = sr ? m0.offsets[r] : 0, r1 = sr ? m0.offsets[r + 1] : 1;
+      const int c0 = sc ? m1.offsets[cc] : 0, c1 = sc ? m1.offsets[cc + 1] : 1;
+      for (int a = r0; a < r1; ++a)
+      {
+        const int tr = sr ? m0.masters[a] : r;
+        const double wr = sr ? m0.coeffs[a] : 1.0;
+        for (int b = c0; b < c1; ++b)
+        {
+          const int tc = sc ? m1.masters[b] : cc;
+          const double wc = sc ? m1.coeffs[b] : 1.0;
+          csr_add(A, tr, tc, wr * wc * v);
+        }
+      }
+    }
+  }
+}
+
+__global__ void __launch_bounds__(128)
+k_vector_generic(Tab t, IntD in, MeshD mesh, const int* __restrict__ dm, int nd, int bs, MpcD m,
+                 double* __restrict__ b, int smem_per_warp)
+{
+  extern __shared__ double smem[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int n = nd * bs;
+  double* base = smem + (size_t)warp * smem_per_warp;
+  double* X = base;
+  double* be = X + 3 * mesh.ng;
+  double* g = be + n;
+  double* w = g + 3 * t.nd;
+  const long long wstride = (long long)gridDim.x * (blockDim.x >> 5);
+  for (long long index = (long long)blockIdx.x * (blockDim.x >> 5) + warp; index < in.ncells; index += wstride)
+  {
+    const int cell = in.cells ? __ldg(in.cells + index) : (int)index;
+    __syncwarp();
+    load_cell(mesh, in, index, cell, X, w, lane);
+    __syncwarp();
+    tabulate_warp(t, in.kernel, in.c, X, w, be, g, lane);
+    for (int e = lane; e < n; e += 32)
+    {
+      const int ib = e / bs, ia = e - ib * bs;
+      const int r = __ldg(dm + (long long)cell * nd + ib) * bs + ia;
+      const double v = be[e];
+      // cpp/assemble_vector.h:52-68: the slave entry is zeroed inside the master loop, so a
+      // slave without masters keeps its own entry.
+      const int o0 = m.is_slave[r] ? m.offsets[r] : 0, o1 = m.is_slave[r] ? m.offsets[r + 1] : 0;
+      if (o1 > o0)
+        for (int a = o0; a < o1; ++a) atomicAdd(b + m.masters[a], m.coeffs[a] * v);
+      else
+        atomicAdd(b + r, v);
+    }
+  }
+}
+
+__global__ void __launch_bounds__(128)
+k_lifting_generic(Tab t, IntD in, MeshD mesh, const int* __restrict__ dm0, const int* __restrict__ dm1,
+                  int nd0, int nd1, int bs0, int bs1, const int8_t* __restrict__ bcm,
+                  const double* __restrict__ bcv, const double* __restrict__ x0, double scale, MpcD m0,
+                  double* __restrict__ b, int smem_per_warp)
+{
+  extern __shared__ double smem[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int n0 = nd0 * bs0, n1 = nd1 * bs1;
+  double* base = smem + (size_t)warp * smem_per_warp;
+  double* X = base;
+  double* Ae = X + 3 * mesh.ng;
+  double* g = Ae + n0 * n1;
+  double* w = g + 3 * t.nd;
+  double* gx = w + (in.cstride > 0 ? in.cstride : 1);  // scale*(g - x0) per column, 0 where no bc
+  const long long wstride = (long long)gridDim.x * (blockDim.x >> 5);
+  for (long long index = (long long)blockIdx.x * (blockDim.x >> 5) + warp; index < in.ncells; index += wstride)
+  {
+    const int cell = in.cells ? __ldg(in.cells + index) : (int)index;
+    __syncwarp();
+    bool any = false;  // cpp/lifting.h:93-109
+    for (int q = lane; q < n1; q += 32)
+    {
+      const int jb = q / bs1, ja = q - jb * bs1;
+      const int cc = __ldg(dm1 + (long long)cell * nd1 + jb) * bs1 + ja;
+      const bool isbc = bcm[cc];
+      gx[q] = isbc ? scale * (bcv[cc] - (x0 ? x0[cc] : 0.0)) : 0.0;
+      any |= isbc;
+    }
+    if (!__any_sync(0xffffffffu, any)) continue;
+    load_cell(mesh, in, index, cell, X, w, lane);
+    __syncwarp();
+    tabulate_warp(t, in.kernel, in.c, X, w, Ae, g, lane);  // un-zeroed A_e (cpp/lifting.h:266-299)
+    for (int p = lane; p < n0; p += 32)
+    {
+      double v = 0.0;
+      for (int q = 0; q < n1; ++q) v -= Ae[p * n1 + q] * gx[q];
+      const int ib = p / bs0, ia = p - ib * bs0;
+      const int r = __ldg(dm0 + (long long)cell * nd0 + ib) * bs0 + ia;
+      const int o0 = m0.is_slave[r] ? m0.offsets[r] : 0, o1 = m0.is_slave[r] ? m0.offsets[r + 1] : 0;
+      if (o1 > o0)
+        for (int a = o0; a < o1; ++a) atomicAdd(b + m0.masters[a], m0.coeffs[a] * v);
+      else
+        atomicAdd(b + r, v);
+    }
+  }
+}
+
+// ------------------------------------------------------------------ plan / small kernels
+template <typename PosT>
+__global__ void k_build_plan(const int* __restrict__ dm0, const int* __restrict__ dm1, int nd0, int nd1,
+                             int bs0, int bs1, const int* __restrict__ cells, long long ncells, CsrD A,
+                             PosT* __restrict__ lpos)
+{
+  const long long tot = ncells * nd0 * nd1;
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < tot;
+       e += (long long)gridDim.x * blockDim.x)
+  {
+    const long long index = e / (nd0 * nd1);
+    const int ij = (int)(e - index * (nd0 * nd1));
+    const int i = ij / nd1, j = ij - i * nd1;
+    const int cell = cells ? cells[index] : (int)index;
+    const int r = dm0[(long long)cell * nd0 + i] * bs0, c = dm1[(long long)cell * nd1 + j] * bs1;
+    const long long p = csr_find(A, r, c);
+    if (p < 0) { g_dev_err = MPCX_ERR_PATTERN; lpos[e] = 0; continue; }
+    const long long off = p - A.rp[r];
+    const long long blk = off / bs1;
+    // the scalar CSR must be the bs0 x bs1 expansion of a block pattern
+    bool ok = (off % bs1 == 0) && (blk <= (long long)((PosT)~(PosT)0));
+    for (int a = 0; a < bs0 && ok; ++a)
+      for (int bb = 0; bb < bs1 && ok; ++bb) ok = A.col[A.rp[r + a] + off + bb] == c + bb;
+    if (!ok) g_dev_err = MPCX_ERR_PATTERN;
+    lpos[e] = (PosT)blk;
+  }
+}
+
+__global__ void k_add_diag(CsrD A, const int* __restrict__ dofs, long long n, double v)
+{
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) csr_add(A, dofs[i], dofs[i], v);
+}
+
+__global__ void k_backsub(MpcD m, const int* __restrict__ slaves, int ns, double* __restrict__ u, int homogenize)
+{
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= ns) return;
+  const int s = slaves[i];
+  double acc = 0.0;
+  if (!homogenize)
+    for (int k = m.offsets[s]; k < m.offsets[s + 1]; ++k) acc += m.coeffs[k] * u[m.masters[k]];
+  u[s] = acc;  // masters are never slaves, so there is no read/write hazard between threads
+}
+
+__global__ void k_gather(const double* __restrict__ src, const long long* __restrict__ idx, long long n,
+                         double* __restrict__ dst)
+{
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    dst[i] = src[idx[i]];
+}
+__global__ void k_scatter_add(double* __restrict__ dst, const long long* __restrict__ idx, long long n,
+                              const double* __restrict__ src)
+{
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    atomicAdd(dst + idx[i], src[i]);
+}
+
+// ------------------------------------------------------------------ P1 simplex fast path
+// Affine P1 simplex: gradients of the barycentric coordinates are the rows of J^-1.
+template <int TD>
+struct P1Geom
+{
+  double g[TD + 1][TD];  // physical gradients
+  double vol;            // |detJ| / TD!
+};
+
+template <int TD>
+__device__ __forceinline__ void load_vertices(const MeshD& m, const int* xd, double (*X)[3])
+{
+#pragma unroll
+  for (int v = 0; v <= TD; ++v)
+  {
+    const double* p = m.x + (long long)xd[v] * m.xs;
+    if (m.xs == 4)
+    {
+      const double2 a = __ldg(reinterpret_cast<const double2*>(p));
+      X[v][0] = a.x; X[v][1] = a.y;
+      X[v][2] = TD == 3 ? __ldg(p + 2) : 0.0;
+    }
+    else
+    {
+      X[v][0] = __ldg(p); X[v][1] = __ldg(p + 1);
+      X[v][2] = TD == 3 ? __ldg(p + 2) : 0.0;
+    }
+  }
+}
+
+template <int TD>
+__device__ __forceinline__ void p1_geometry(const double (*X)[3], P1Geom<TD>& G)
+{
+  if (TD == 2)
+  {
+    const double j00 = X[1][0] - X[0][0], j01 = X[2][0] - X[0][0];
+    const double j10 = X[1][1] - X[0][1], j11 = X[2][1] - X[0][1];
+    const double det = j00 * j11 - j01 * j10;
+    const double inv = 1.0 / det;
+    G.g[1][0] = j11 * inv; G.g[1][1] = -j01 * inv;
+    G.g[2][0] = -j10 * inv; G.g[2][1] = j00 * inv;
+    G.g[0][0] = -(G.g[1][0] + G.g[2][0]); G.g[0][1] = -(G.g[1][1] + G.g[2][1]);
+    G.vol = 0.5 * fabs(det);
+  }
+  else
+  {
+    double J[3][3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k)
+#pragma unroll
+      for (int a = 0; a < 3; ++a) J[k][a] = X[a + 1][k] - X[0][k];
+    const double c00 = J[1][1] * J[2][2] - J[1][2] * J[2][1];
+    const double c01 = J[1][2] * J[2][0] - J[1][0] * J[2][2];
+    const double c02 = J[1][0] * J[2][1] - J[1][1] * J[2][0];
+    const double det = J[0][0] * c00 + J[0][1] * c01 + J[0][2] * c02;
+    const double inv = 1.0 / det;
+    G.g[1][0] = c00 * inv;
+    G.g[1][1] = (J[0][2] * J[2][1] - J[0][1] * J[2][2]) * inv;
+    G.g[1][2] = (J[0][1] * J[1][2] - J[0][2] * J[1][1]) * inv;
+    G.g[2][0] = c01 * inv;
+    G.g[2][1] = (J[0][0] * J[2][2] - J[0][2] * J[2][0]) * inv;
+    G.g[2][2] = (J[0][2] * J[1][0] - J[0][0] * J[1][2]) * inv;
+    G.g[3][0] = c02 * inv;
+    G.g[3][1] = (J[0][1] * J[2][0] - J[0][0] * J[2][1]) * inv;
+    G.g[3][2] = (J[0][0] * J[1][1] - J[0][1] * J[1][0]) * inv;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) G.g[0][k] = -(G.g[1][k] + G.g[2][k] + G.g[3][k]);
+    G.vol = fabs(det) * (1.0 / 6.0);
+  }
+}
+
+// Thread per cell, scalar P1 Laplace, cells without slaves only (slave cells go through
+// k_matrix_generic in mode 1).  Scatter through the precomputed plan.
+template <int TD, typename PosT>
+__global__ void __launch_bounds__(256)
+k_matrix_p1_laplace(IntD in, MeshD mesh, const int* __restrict__ dm0, const int* __restrict__ dm1,
+                    const int8_t* __restrict__ bc0, const int8_t* __restrict__ bc1,
+                    const int* __restrict__ c2s0, const int* __restrict__ c2s1, CsrD A,
+                    const PosT* __restrict__ lpos)
+{
+  constexpr int NV = TD + 1;
+  const long long index = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (index >= in.ncells) return;
+  const int cell = in.cells ? __ldg(in.cells + index) : (int)index;
+  if (__ldg(c2s0 + cell + 1) > __ldg(c2s0 + cell) || __ldg(c2s1 + cell + 1) > __ldg(c2s1 + cell)) return;
+  int xd[NV], r[NV], c[NV];
+#pragma unroll
+  for (int v = 0; v < NV; ++v)
+  {
+    xd[v] = __ldg(mesh.xd + (long long)cell * NV + v);
+    r[v] = __ldg(dm0 + (long long)cell * NV + v);
+    c[v] = __ldg(dm1 + (long long)cell * NV + v);
+  }
+  double X[NV][3];
+  load_vertices<TD>(mesh, xd, X);
+  P1Geom<TD> G;
+  p1_geometry<TD>(X, G);
+  const double s = in.c[0] * G.vol;
+  bool zr[NV], zc[NV];
+#pragma unroll
+  for (int v = 0; v < NV; ++v)
+  {
+    zr[v] = bc0 ? bc0[r[v]] : false;
+    zc[v] = bc1 ? bc1[c[v]] : false;
+  }
+  const PosT* lp = lpos + index * (NV * NV);
+#pragma unroll
+  for (int i = 0; i < NV; ++i)
+  {
+    const long long rp = __ldg(A.rp + r[i]);
+#pragma unroll
+    for (int j = 0; j < NV; ++j)
+    {
+      double d = 0.0;
+#pragma unroll
+      for (int k = 0; k < TD; ++k) d += G.g[i][k] * G.g[j][k];
+      if (!(zr[i] || zc[j])) atomicAdd(A.val + rp + lp[i * NV + j], s * d);
+    }
+  }
+}
+
+// Thread per cell, P1 source vector b_i = c0 * vol/((d+1)(d+2)) * (f_i + sum_j f_j), scalar.
+template <int TD>
+__global__ void __launch_bounds__(256)
+k_vector_p1_source(IntD in, MeshD mesh, const int* __restrict__ dm, const int* __restrict__ c2s,
+                   MpcD m, double* __restrict__ b)
+{
+  constexpr int NV = TD + 1;
+  const long long index = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (index >= in.ncells) return;
+  const int cell = in.cells ? __ldg(in.cells + index) : (int)index;
+  int xd[NV], r[NV];
+#pragma unroll
+  for (int v = 0; v < NV; ++v)
+  {
+    xd[v] = __ldg(mesh.xd + (long long)cell * NV + v);
+    r[v] = __ldg(dm + (long long)cell * NV + v);
+  }
+  double X[NV][3];
+  load_vertices<TD>(mesh, xd, X);
+  P1Geom<TD> G;
+  p1_geometry<TD>(X, G);
+  double f[NV], fs = 0.0;
+#pragma unroll
+  for (int v = 0; v < NV; ++v)
+  {
+    f[v] = in.coeffs ? __ldg(in.coeffs + index * in.cstride + v)
+                     : __ldg(in.wnodal + __ldg(in.wmap + (long long)cell * NV + v));
+    fs += f[v];
+  }
+  const double s = in.c[0] * G.vol / double((TD + 1) * (TD + 2));
+  const bool has_slaves = __ldg(c2s + cell + 1) > __ldg(c2s + cell);
+#pragma unroll
+  for (int v = 0; v < NV; ++v)
+  {
+    const double val = s * (f[v] + fs);
+    int o0 = 0, o1 = 0;
+    if (has_slaves && m.is_slave[r[v]]) { o0 = m.offsets[r[v]]; o1 = m.offsets[r[v] + 1]; }
+    if (o1 > o0)
+      for (int a = o0; a < o1; ++a) atomicAdd(b + m.masters[a], m.coeffs[a] * val);
+    else
+      atomicAdd(b + r[v], val);
+  }
+}
+
+// ------------------------------------------------------------------ host helpers
+Tab make_tab(const mpcx_tables* t)
+{
+  return Tab{t->tdim, t->gdim, t->nd, t->ng, t->nq, t->bs, t->weights, t->phi, t->dphi, t->gdphi};
+}
+MpcD make_mpc(const mpcx_mpc* m)
+{
+  return MpcD{m->is_slave, m->masters, m->coeffs, m->offsets, m->cell_to_slaves_offsets};
+}
+IntD make_int(const mpcx_integral* in)
+{
+  IntD d;
+  d.kernel = in->kernel; d.cells = in->cells; d.ncells = in->num_cells;
+  d.coeffs = in->coeffs; d.cstride = in->cstride;
+  d.wnodal = in->coeff_nodal; d.wmap = in->coeff_dofmap; d.wnd = in->coeff_nd; d.wbs = in->coeff_bs;
+  if (!d.coeffs && d.wnodal) d.cstride = d.wnd * d.wbs;
+  for (int i = 0; i < MPCX_MAX_CONSTANTS; ++i) d.c[i] = i < in->num_constants ? in->constants[i] : 0.0;
+  d.slave_cells = in->slave_cells; d.nslave_cells = in->num_slave_cells;
+  return d;
+}
+
+int check_integral(const mpcx_integral* in, bool bilinear)
+{
+  if (!in || !in->tables) return fail(MPCX_ERR_ARG, "null integral/tables");
+  if (in->num_cells < 0 || in->num_constants > MPCX_MAX_CONSTANTS) return fail(MPCX_ERR_ARG, "bad sizes");
+  const int k = in->kernel;
+  const bool is_bilinear = k == MPCX_KERNEL_LAPLACE || k == MPCX_KERNEL_MASS || k == MPCX_KERNEL_ELASTICITY
+                           || k == MPCX_KERNEL_LAPLACE_VARCOEF;
+  if (k < 0 || k > MPCX_KERNEL_LAPLACE_VARCOEF) return fail(MPCX_ERR_UNSUPPORTED, "unknown kernel id");
+  if (bilinear != is_bilinear)
+    return fail(MPCX_ERR_UNSUPPORTED, "kernel rank does not match the assembly routine");
+  const mpcx_tables* t = in->tables;
+  if (t->tdim != t->gdim || (t->tdim != 2 && t->tdim != 3))
+    return fail(MPCX_ERR_UNSUPPORTED, "only tdim == gdim in {2, 3} has device kernels");
+  if (k == MPCX_KERNEL_ELASTICITY && t->bs != t->gdim) return fail(MPCX_ERR_ARG, "elasticity needs bs == gdim");
+  const bool needs_w = k == MPCX_KERNEL_SOURCE || k == MPCX_KERNEL_LAPLACE_VARCOEF;
+  if (needs_w && !in->coeffs && !in->coeff_nodal) return fail(MPCX_ERR_ARG, "kernel needs coefficients");
+  return MPCX_OK;
+}
+
+int grid_for_warps(long long nwork, int warps_per_block)
+{
+  long long blocks = (nwork + warps_per_block - 1) / warps_per_block;
+  const long long cap = 148LL * 16 * 4;  // persistent-ish: a few waves of 148 SMs
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  return (int)blocks;
+}
+}  // namespace
+
+// ====================================================================== C ABI
+extern "C" {
+
+const char* mpcx_last_error(void) { return g_err; }
+int mpcx_abi_version(void) { return MPCX_ABI_VERSION; }
+
+int mpcx_device_error(void* stream)
+{
+  int h = 0, zero = 0;
+  cudaStream_t s = (cudaStream_t)stream;
+  int rc = cuda_check(cudaMemcpyFromSymbolAsync(&h, g_dev_err, sizeof(int), 0, cudaMemcpyDeviceToHost, s), "device_error");
+  if (rc) return rc;
+  rc = cuda_check(cudaStreamSynchronize(s), "device_error sync");
+  if (rc) return rc;
+  if (h)
+  {
+    cudaMemcpyToSymbolAsync(g_dev_err, &zero, sizeof(int), 0, cudaMemcpyHostToDevice, s);
+    cudaStreamSynchronize(s);
+    return fail(h, "device reported an insertion outside the sparsity pattern");
+  }
+  return MPCX_OK;
+}
+
+int mpcx_assemble_matrix_f64(const mpcx_integral* integral, const mpcx_mesh* mesh,
+                             const mpcx_dofmap* dofmap0, const mpcx_dofmap* dofmap1,
+                             const int8_t* bc0, const int8_t* bc1, const mpcx_mpc* mpc0,
+                             const mpcx_mpc* mpc1, const mpcx_csr* A, const mpcx_plan* plan, void* stream)
+{
+  int rc = check_integral(integral, true);
+  if (rc) return rc;
+  if (!mesh || !dofmap0 || !dofmap1 || !mpc0 || !mpc1 || !A) return fail(MPCX_ERR_ARG, "null argument");
+  const mpcx_tables* t = integral->tables;
+  if (dofmap0->nd != t->nd || dofmap1->nd != t->nd || dofmap0->bs != t->bs || dofmap1->bs != t->bs)
+    return fail(MPCX_ERR_UNSUPPORTED, "test/trial dofmaps must match the tabulated element");
+  if (mesh->ng != t->ng) return fail(MPCX_ERR_ARG, "geometry dofmap width does not match the tables");
+  if (plan && plan->lpos && plan->width != 1 && plan->width != 2) return fail(MPCX_ERR_ARG, "plan width must be 1 or 2");
+  if (integral->num_cells == 0) return MPCX_OK;
+  cudaStream_t s = (cudaStream_t)stream;
+  const Tab tab = make_tab(t);
+  IntD in = make_int(integral);
+  const MeshD md{mesh->x, mesh->x_dofmap, mesh->ng, mesh->x_stride};
+  const MpcD m0 = make_mpc(mpc0), m1 = make_mpc(mpc1);
+  const CsrD Ad{(const long long*)A->row_ptr, A->col, A->val};
+  const void* lpos = plan ? plan->lpos : nullptr;
+  const int width = plan ? plan->width : 0;
+  const int nd = t->nd, bs = t->bs, n = nd * bs;
+
+  const bool p1_simplex = t->nd == t->tdim + 1 && t->ng == t->tdim + 1 && t->nq == 1;
+  // the bulk/elimination split needs the list of slave cells (or a constraint without slaves)
+  const bool have_split = integral->slave_cells != nullptr || (mpc0->num_slaves == 0 && mpc1->num_slaves == 0);
+  const bool fast = lpos && have_split && integral->kernel == MPCX_KERNEL_LAPLACE && bs == 1 && p1_simplex;
+  // generic kernel resources
+  const int wcount = in.cstride > 0 ? in.cstride : 1;
+  int spw = 3 * mesh->ng + n * n + 3 * nd + wcount + (2 * nd + 1) / 2 + 1;
+  const size_t smem = (size_t)spw * 4 * sizeof(double);
+  if (smem > 48 * 1024)
+  {
+    rc = cuda_check(cudaFuncSetAttribute(k_matrix_generic<uint8_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "smem attr");
+    if (rc) return rc;
+    rc = cuda_check(cudaFuncSetAttribute(k_matrix_generic<uint16_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "smem attr");
+    if (rc) return rc;
+  }
+  auto launch_generic = [&](int mode, long long nwork) {
+    if (nwork <= 0) return;
+    const int grid = grid_for_warps(nwork, 4);
+    if (width == 2)
+      k_matrix_generic<uint16_t><<<grid, 128, smem, s>>>(tab, in, md, dofmap0->map, dofmap1->map, nd, nd, bs, bs, bc0, bc1,
+                                                         m0, m1, Ad, (const uint16_t*)lpos, mode, spw);
+    else
+      k_matrix_generic<uint8_t><<<grid, 128, smem, s>>>(tab, in, md, dofmap0->map, dofmap1->map, nd, nd, bs, bs, bc0, bc1,
+                                                        m0, m1, Ad, (const uint8_t*)lpos, mode, spw);
+  };
+  if (fast)
+  {
+    const long long nb = (in.ncells + 255) / 256;
+    if (t->tdim == 3)
+    {
+      if (width == 1)
+        k_matrix_p1_laplace<3, uint8_t><<<(unsigned)nb, 256, 0, s>>>(in, md, dofmap0->map, dofmap1->map, bc0, bc1, m0.c2s_off, m1.c2s_off, Ad, (const uint8_t*)lpos);
+      else
+        k_matrix_p1_laplace<3, uint16_t><<<(unsigned)nb, 256, 0, s>>>(in, md, dofmap0->map, dofmap1->map, bc0, bc1, m0.c2s_off, m1.c2s_off, Ad, (const uint16_t*)lpos);
+    }
+    else
+    {
+      if (width == 1)
+        k_matrix_p1_laplace<2, uint8_t><<<(unsigned)nb, 256, 0, s>>>(in, md, dofmap0->map, dofmap1->map, bc0, bc1, m0.c2s_off, m1.c2s_off, Ad, (const uint8_t*)lpos);
+      else
+        k_matrix_p1_laplace<2, uint16_t><<<(unsigned)nb, 256, 0, s>>>(in, md, dofmap0->map, dofmap1->map, bc0, bc1, m0.c2s_off, m1.c2s_off, Ad, (const uint16_t*)lpos);
+    }
+    launch_generic(1, in.nslave_cells);
+  }
+  else if (have_split && lpos)
+  {
+    launch_generic(2, in.ncells);         // bulk cells, planned scatter
+    launch_generic(1, in.nslave_cells);   // slave cells, elimination
+  }
+  else
+    launch_generic(0, in.ncells);
+  return cuda_check(cudaGetLastError(), "assemble_matrix launch");
+}
+
+int mpcx_add_diagonal_f64(const mpcx_csr* A, const int32_t* dofs, int64_t n, double diagval, void* stream)
+{
+  if (!A || (n > 0 && !dofs)) return fail(MPCX_ERR_ARG, "null argument");
+  if (n <= 0) return MPCX_OK;
+  const CsrD Ad{(const long long*)A->row_ptr, A->col, A->val};
+  k_add_diag<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(Ad, dofs, n, diagval);
+  return cuda_check(cudaGetLastError(), "add_diagonal launch");
+}
+
+int mpcx_build_plan(const mpcx_dofmap* dofmap0, const mpcx_dofmap* dofmap1, const int32_t* cells,
+                    int64_t num_cells, const mpcx_csr* A, void* lpos_out, int32_t width, void* stream)
+{
+  if (!dofmap0 || !dofmap1 || !A || !lpos_out) return fail(MPCX_ERR_ARG, "null argument");
+  if (width != 1 && width != 2) return fail(MPCX_ERR_ARG, "plan width must be 1 or 2");
+  if (num_cells <= 0) return MPCX_OK;
+  const CsrD Ad{(const long long*)A->row_ptr, A->col, A->val};
+  const long long tot = (long long)num_cells * dofmap0->nd * dofmap1->nd;
+  long long nb = (tot + 255) / 256;
+  if (nb > 148LL * 64) nb = 148LL * 64;
+  if (width == 1)
+    k_build_plan<uint8_t><<<(unsigned)nb, 256, 0, (cudaStream_t)stream>>>(dofmap0->map, dofmap1->map, dofmap0->nd, dofmap1->nd,
+                                                                          dofmap0->bs, dofmap1->bs, cells, num_cells, Ad, (uint8_t*)lpos_out);
+  else
+    k_build_plan<uint16_t><<<(unsigned)nb, 256, 0, (cudaStream_t)stream>>>(dofmap0->map, dofmap1->map, dofmap0->nd, dofmap1->nd,
+                                                                           dofmap0->bs, dofmap1->bs, cells, num_cells, Ad, (uint16_t*)lpos_out);
+  return cuda_check(cudaGetLastError(), "build_plan launch");
+}
+
+int mpcx_assemble_vector_f64(const mpcx_integral* integral, const mpcx_mesh* mesh, const mpcx_dofmap* dofmap,
+                             const mpcx_mpc* mpc, double* b, void* stream)
+{
+  int rc = check_integral(integral, false);
+  if (rc) return rc;
+  if (!mesh || !dofmap || !mpc || !b) return fail(MPCX_ERR_ARG, "null argument");
+  const mpcx_tables* t = integral->tables;
+  if (dofmap->nd != t->nd || dofmap->bs != t->bs) return fail(MPCX_ERR_UNSUPPORTED, "dofmap must match the tabulated element");
+  if (mesh->ng != t->ng) return fail(MPCX_ERR_ARG, "geometry dofmap width does not match the tables");
+  if (integral->num_cells == 0) return MPCX_OK;
+  cudaStream_t s = (cudaStream_t)stream;
+  const Tab tab = make_tab(t);
+  IntD in = make_int(integral);
+  const MeshD md{mesh->x, mesh->x_dofmap, mesh->ng, mesh->x_stride};
+  const MpcD m = make_mpc(mpc);
+  const int nd = t->nd, bs = t->bs, n = nd * bs;
+  const bool p1_simplex = t->nd == t->tdim + 1 && t->ng == t->tdim + 1;
+  const bool w_ok = in.coeffs ? in.cstride == nd : (in.wnd == nd && in.wbs == 1);
+  if (integral->kernel == MPCX_KERNEL_SOURCE && bs == 1 && p1_simplex && w_ok)
+  {
+    const long long nb = (in.ncells + 255) / 256;
+    if (t->tdim == 3) k_vector_p1_source<3><<<(unsigned)nb, 256, 0, s>>>(in, md, dofmap->map, m.c2s_off, m, b);
+    else k_vector_p1_source<2><<<(unsigned)nb, 256, 0, s>>>(in, md, dofmap->map, m.c2s_off, m, b);
+  }
+  else
+  {
+    const int wcount = in.cstride > 0 ? in.cstride : 1;
+    const int spw = 3 * mesh->ng + n + 3 * nd + wcount + 1;
+    const size_t smem = (size_t)spw * 4 * sizeof(double);
+    k_vector_generic<<<grid_for_warps(in.ncells, 4), 128, smem, s>>>(tab, in, md, dofmap->map, nd, bs, m, b, spw);
+  }
+  return cuda_check(cudaGetLastError(), "assemble_vector launch");
+}
+
+int mpcx_apply_lifting_f64(const mpcx_integral* integral, const mpcx_mesh* mesh, const mpcx_dofmap* dofmap0,
+                           const mpcx_dofmap* dofmap1, const int8_t* bc_markers1, const double* bc_values1,
+                           const double* x0, double scale, const mpcx_mpc* mpc0, double* b, void* stream)
+{
+  int rc = check_integral(integral, true);
+  if (rc) return rc;
+  if (!mesh || !dofmap0 || !dofmap1 || !mpc0 || !b || !bc_markers1 || !bc_values1) return fail(MPCX_ERR_ARG, "null argument");
+  const mpcx_tables* t = integral->tables;
+  if (dofmap0->nd != t->nd || dofmap1->nd != t->nd || dofmap0->bs != t->bs || dofmap1->bs != t->bs)
+    return fail(MPCX_ERR_UNSUPPORTED, "test/trial dofmaps must match the tabulated element");
+  if (integral->num_cells == 0) return MPCX_OK;
+  const Tab tab = make_tab(t);
+  IntD in = make_int(integral);
+  const MeshD md{mesh->x, mesh->x_dofmap, mesh->ng, mesh->x_stride};
+  const int nd = t->nd, bs = t->bs, n = nd * bs;
+  const int wcount = in.cstride > 0 ? in.cstride : 1;
+  const int spw = 3 * mesh->ng + n * n + 3 * nd + wcount + n + 1;
+  const size_t smem = (size_t)spw * 4 * sizeof(double);
+  if (smem > 48 * 1024)
+  {
+    rc = cuda_check(cudaFuncSetAttribute(k_lifting_generic, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "smem attr");
+    if (rc) return rc;
+  }
+  k_lifting_generic<<<grid_for_warps(in.ncells, 4), 128, smem, (cudaStream_t)stream>>>(
+      tab, in, md, dofmap0->map, dofmap1->map, nd, nd, bs, bs, bc_markers1, bc_values1, x0, scale, make_mpc(mpc0), b, spw);
+  return cuda_check(cudaGetLastError(), "apply_lifting launch");
+}
+
+int mpcx_backsubstitution_f64(const mpcx_mpc* mpc, double* u, void* stream)
+{
+  if (!mpc || !u) return fail(MPCX_ERR_ARG, "null argument");
+  if (mpc->num_slaves <= 0) return MPCX_OK;
+  k_backsub<<<(mpc->num_slaves + 255) / 256, 256, 0, (cudaStream_t)stream>>>(make_mpc(mpc), mpc->slaves, mpc->num_slaves, u, 0);
+  return cuda_check(cudaGetLastError(), "backsubstitution launch");
+}
+
+int mpcx_homogenize_f64(const mpcx_mpc* mpc, double* u, void* stream)
+{
+  if (!mpc || !u) return fail(MPCX_ERR_ARG, "null argument");
+  if (mpc->num_slaves <= 0) return MPCX_OK;
+  k_backsub<<<(mpc->num_slaves + 255) / 256, 256, 0, (cudaStream_t)stream>>>(make_mpc(mpc), mpc->slaves, mpc->num_slaves, u, 1);
+  return cuda_check(cudaGetLastError(), "homogenize launch");
+}
+
+int mpcx_gather_f64(const double* src, const int64_t* idx, int64_t n, double* dst, void* stream)
+{
+  if (n <= 0) return MPCX_OK;
+  if (!src || !idx || !dst) return fail(MPCX_ERR_ARG, "null argument");
+  long long nb = (n + 255) / 256;
+  if (nb > 148LL * 32) nb = 148LL * 32;
+  k_gather<<<(unsigned)nb, 256, 0, (cudaStream_t)stream>>>(src, (const long long*)idx, n, dst);
+  return cuda_check(cudaGetLastError(), "gather launch");
+}
+
+int mpcx_scatter_add_f64(double* dst, const int64_t* idx, int64_t n, const double* src, void* stream)
+{
+  if (n <= 0) return MPCX_OK;
+  if (!src || !idx || !dst) return fail(MPCX_ERR_ARG, "null argument");
+  long long nb = (n + 255) / 256;
+  if (nb > 148LL * 32) nb = 148LL * 32;
+  k_scatter_add<<<(unsigned)nb, 256, 0, (cudaStream_t)stream>>>(dst, (const long long*)idx, n, src);
+  return cuda_check(cudaGetLastError(), "scatter_add launch");
+}
+
+}  // extern "C"

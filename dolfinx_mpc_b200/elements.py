@@ -1,0 +1,168 @@
+"""Tabulated Lagrange elements and quadrature rules (host side, numpy).
+
+The reference receives its element kernel as an opaque FFCx-generated
+``tabulate_tensor`` whose basis tables are baked into the generated C source
+(call site ``cpp/assemble_matrix.cpp:438-439,505-506``).  FFCx/Basix are not in
+this image, so the tables are produced here and handed, as plain arrays, to the
+device kernels (and to the CPU oracle): quadrature weights, basis values and
+reference derivatives at the quadrature points, and the reference derivatives of
+the geometry map.
+
+Node ordering follows the Basix/DOLFINx convention: vertices first, then edge
+midpoints with edges ordered by (tet) (2,3),(1,3),(1,2),(0,3),(0,2),(0,1) and
+(triangle) (1,2),(0,2),(0,1); tensor-product cells number vertices with x
+fastest.
+"""
+from __future__ import annotations
+
+import dataclasses
+import functools
+
+import numpy as np
+from scipy.special import roots_jacobi
+
+CELL_TDIM = {"interval": 1, "triangle": 2, "tetrahedron": 3, "quadrilateral": 2, "hexahedron": 3}
+_TRI_EDGES = ((1, 2), (0, 2), (0, 1))
+_TET_EDGES = ((2, 3), (1, 3), (1, 2), (0, 3), (0, 2), (0, 1))
+
+
+def is_simplex(cell_type: str) -> bool:
+    return cell_type in ("interval", "triangle", "tetrahedron")
+
+
+def _gauss_jacobi_01(m: int, alpha: int):
+    """m-point Gauss-Jacobi rule for weight (1-x)^alpha on [0, 1]."""
+    x, w = roots_jacobi(m, alpha, 0)
+    return 0.5 * (x + 1.0), w / 2.0 ** (alpha + 1)
+
+
+@functools.lru_cache(maxsize=None)
+def make_quadrature(cell_type: str, degree: int):
+    """Quadrature exact for polynomials of total ``degree`` on the reference cell.
+
+    Simplices use the collapsed (Stroud conical product) Gauss-Jacobi rule,
+    tensor cells a Gauss-Legendre product rule.
+    """
+    m = max(1, (degree + 2) // 2)
+    tdim = CELL_TDIM[cell_type]
+    if cell_type == "interval":
+        x, w = _gauss_jacobi_01(m, 0)
+        return x[:, None].copy(), w.copy()
+    if cell_type == "triangle":
+        if degree <= 1:
+            return np.array([[1 / 3, 1 / 3]]), np.array([0.5])
+        r, wr = _gauss_jacobi_01(m, 1)
+        s, ws = _gauss_jacobi_01(m, 0)
+        pts = np.array([[ri, sj * (1 - ri)] for ri in r for sj in s])
+        wts = np.array([wi * wj for wi in wr for wj in ws])
+        return pts, wts
+    if cell_type == "tetrahedron":
+        if degree <= 1:
+            return np.array([[0.25, 0.25, 0.25]]), np.array([1 / 6])
+        r, wr = _gauss_jacobi_01(m, 2)
+        s, ws = _gauss_jacobi_01(m, 1)
+        t, wt = _gauss_jacobi_01(m, 0)
+        pts = np.array([[ri, sj * (1 - ri), tk * (1 - ri) * (1 - sj)] for ri in r for sj in s for tk in t])
+        wts = np.array([wi * wj * wk for wi in wr for wj in ws for wk in wt])
+        return pts, wts
+    x, w = _gauss_jacobi_01(m, 0)
+    if tdim == 2:
+        pts = np.array([[xi, yj] for yj in x for xi in x])
+        wts = np.array([wi * wj for wj in w for wi in w])
+    else:
+        pts = np.array([[xi, yj, zk] for zk in x for yj in x for xi in x])
+        wts = np.array([wi * wj * wk for wk in w for wj in w for wi in w])
+    return pts, wts
+
+
+def _simplex_barycentric(pts: np.ndarray):
+    tdim = pts.shape[1]
+    lam = np.concatenate([1.0 - pts.sum(axis=1, keepdims=True), pts], axis=1)  # (nq, tdim+1)
+    dlam = np.zeros((tdim, tdim + 1))
+    dlam[:, 0] = -1.0
+    for a in range(tdim):
+        dlam[a, a + 1] = 1.0
+    return lam, dlam
+
+
+def _lagrange_1d(degree: int, x: np.ndarray):
+    """Equispaced 1-D Lagrange basis, Basix ordering (end points first)."""
+    if degree == 1:
+        return np.stack([1 - x, x], 1), np.stack([-np.ones_like(x), np.ones_like(x)], 1)
+    if degree == 2:
+        phi = np.stack([(1 - x) * (1 - 2 * x), x * (2 * x - 1), 4 * x * (1 - x)], 1)
+        dphi = np.stack([4 * x - 3, 4 * x - 1, 4 - 8 * x], 1)
+        return phi, dphi
+    raise NotImplementedError(f"degree {degree}")
+
+
+def tabulate(cell_type: str, degree: int, pts: np.ndarray):
+    """Basis values (nq, nd) and reference derivatives (nq, tdim, nd)."""
+    pts = np.atleast_2d(np.asarray(pts, dtype=np.float64))
+    tdim = CELL_TDIM[cell_type]
+    nq = pts.shape[0]
+    if is_simplex(cell_type):
+        lam, dlam = _simplex_barycentric(pts)
+        nv = tdim + 1
+        if degree == 1:
+            return lam.copy(), np.broadcast_to(dlam[None], (nq, tdim, nv)).copy()
+        if degree == 2:
+            edges = {1: ((0, 1),), 2: _TRI_EDGES, 3: _TET_EDGES}[tdim]
+            nd = nv + len(edges)
+            phi = np.zeros((nq, nd))
+            dphi = np.zeros((nq, tdim, nd))
+            for v in range(nv):
+                phi[:, v] = lam[:, v] * (2 * lam[:, v] - 1)
+                dphi[:, :, v] = (4 * lam[:, v, None] - 1) * dlam[None, :, v]
+            for e, (a, b) in enumerate(edges):
+                phi[:, nv + e] = 4 * lam[:, a] * lam[:, b]
+                dphi[:, :, nv + e] = 4 * (lam[:, a, None] * dlam[None, :, b] + lam[:, b, None] * dlam[None, :, a])
+            return phi, dphi
+        raise NotImplementedError(f"Lagrange degree {degree} on {cell_type}")
+    if degree != 1:
+        raise NotImplementedError(f"Lagrange degree {degree} on {cell_type}")
+    p1 = [_lagrange_1d(1, pts[:, a]) for a in range(tdim)]
+    nd = 2**tdim
+    phi = np.ones((nq, nd))
+    dphi = np.ones((nq, tdim, nd))
+    for v in range(nd):
+        for a in range(tdim):
+            bit = (v >> a) & 1
+            phi[:, v] *= p1[a][0][:, bit]
+            for b in range(tdim):
+                dphi[:, b, v] *= p1[a][1][:, bit] if a == b else p1[a][0][:, bit]
+    return phi, dphi
+
+
+def num_element_dofs(cell_type: str, degree: int) -> int:
+    return tabulate(cell_type, degree, np.zeros((1, CELL_TDIM[cell_type]))).__getitem__(0).shape[1]
+
+
+@dataclasses.dataclass(frozen=True)
+class ElementTables:
+    """Arrays a tabulated kernel consumes; layout matches ``mpcx_tables`` (include/mpcx.h)."""
+
+    cell_type: str
+    degree: int
+    tdim: int
+    gdim: int
+    nd: int
+    ng: int
+    nq: int
+    weights: np.ndarray  # (nq,)
+    phi: np.ndarray  # (nq, nd)
+    dphi: np.ndarray  # (nq, tdim, nd)
+    gdphi: np.ndarray  # (nq, tdim, ng)
+
+
+@functools.lru_cache(maxsize=None)
+def element_tables(cell_type: str, degree: int, qdegree: int) -> ElementTables:
+    pts, wts = make_quadrature(cell_type, qdegree)
+    phi, dphi = tabulate(cell_type, degree, pts)
+    _, gdphi = tabulate(cell_type, 1, pts)
+    tdim = CELL_TDIM[cell_type]
+    return ElementTables(
+        cell_type, degree, tdim, tdim, phi.shape[1], gdphi.shape[2], len(wts),
+        np.ascontiguousarray(wts), np.ascontiguousarray(phi), np.ascontiguousarray(dphi),
+        np.ascontiguousarray(gdphi),
+    )

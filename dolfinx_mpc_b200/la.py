@@ -1,0 +1,104 @@
+"""Device-resident linear-algebra containers the assembly routines fill.
+
+``Matrix`` is a scalar CSR (int64 ``row_ptr``, int32 ``col`` ascending per row,
+float64 ``val``) in HBM -- what replaces the PETSc ``Mat`` behind
+``mat_add_block_values`` / ``mat_add_values`` (``python/src/dolfinx_mpc/mpc.cpp:284-287``).
+``Vector`` is the local (owned + ghost) array of a PETSc ``Vec``'s local form
+(``python/src/dolfinx_mpc/assemble_vector.py:100-102``).  Both are handed back to
+SciPy / numpy on the host only for checking.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional
+
+import numpy as np
+import torch
+
+from . import _lib
+from . import device as _dev
+
+
+class Matrix:
+    def __init__(self, row_ptr: np.ndarray, col: np.ndarray, shape, bs=(1, 1), max_block_row: Optional[int] = None):
+        self.shape = tuple(int(s) for s in shape)
+        self.bs = tuple(bs)
+        self.row_ptr_host = np.ascontiguousarray(row_ptr, dtype=np.int64)
+        self.col_host = np.ascontiguousarray(col, dtype=np.int32)
+        self.nnz = int(self.row_ptr_host[-1])
+        self.row_ptr = _dev.to_dev(self.row_ptr_host)
+        self.col = _dev.to_dev(self.col_host)
+        self.val = torch.zeros(self.nnz, dtype=torch.float64, device=_dev.device())
+        if max_block_row is None:
+            max_block_row = int(np.diff(self.row_ptr_host).max(initial=0)) // max(1, self.bs[1])
+        self.max_block_row = max_block_row
+        self._plans = {}
+        self.ghost_exchange = None  # set by distributed.attach_ghost_exchange
+
+    def struct(self) -> _lib.CsrS:
+        return _lib.CsrS(_dev.ptr(self.row_ptr), _dev.ptr(self.col), _dev.ptr(self.val), self.shape[0], self.nnz)
+
+    def zeroEntries(self):
+        self.val.zero_()
+
+    def plan(self, form, integral) -> Optional[_lib.PlanS]:
+        """Scatter plan for one integral of ``form`` into this pattern (built on first use, then cached)."""
+        width = 1 if self.max_block_row <= 256 else (2 if self.max_block_row <= 65536 else 0)
+        if width == 0:
+            return None
+        key = (id(form.function_spaces[0]), id(form.function_spaces[1]), id(integral))
+        if key not in self._plans:
+            V0, V1 = form.function_spaces
+            ncells = form.mesh.num_cells_local if integral.cells is None else len(integral.cells)
+            lpos = torch.empty(ncells * V0.nd * V1.nd, dtype=torch.uint8 if width == 1 else torch.int16,
+                               device=_dev.device())
+            d0 = _dev.dofmap_struct(V0, self.shape[0])
+            d1 = _dev.dofmap_struct(V1, self.shape[1])
+            if integral.cells is not None and "cells" not in integral._dev:
+                integral._dev["cells"] = _dev.to_dev(integral.cells)
+            lib = _lib.load()
+            A = self.struct()
+            _lib.check(lib.mpcx_build_plan(C.byref(d0), C.byref(d1), _dev.ptr(integral._dev.get("cells")), ncells,
+                                           C.byref(A), _dev.ptr(lpos), width, _dev.stream_ptr()))
+            _lib.check(lib.mpcx_device_error(_dev.stream_ptr()))
+            self._plans[key] = (lpos, _lib.PlanS(_dev.ptr(lpos), width))
+        return self._plans[key][1]
+
+    def assemble(self):
+        """Finish assembly: with several ranks, send ghost-row values to their owners and add
+        (PETSc ``MatAssemblyBegin/End`` in ``python/src/dolfinx_mpc/assemble_matrix.py:64``)."""
+        if self.ghost_exchange is not None:
+            self.ghost_exchange.reduce_matrix(self)
+
+    # -- hand-off to the host, for checks only ---------------------------------------------------------------
+    def getValuesCSR(self):
+        return self.row_ptr_host, self.col_host, self.val.cpu().numpy()
+
+    def to_scipy(self):
+        import scipy.sparse as sp
+
+        return sp.csr_matrix((self.val.cpu().numpy(), self.col_host, self.row_ptr_host), shape=self.shape)
+
+    def norm(self) -> float:
+        return float(torch.linalg.vector_norm(self.val))
+
+
+class Vector:
+    def __init__(self, n: int, data: Optional[torch.Tensor] = None):
+        self.data = torch.zeros(n, dtype=torch.float64, device=_dev.device()) if data is None else data
+        self.ghost_exchange = None
+
+    def set(self, v: float):
+        self.data.fill_(v)
+
+    @property
+    def array(self) -> np.ndarray:
+        return self.data.cpu().numpy()
+
+    def ghostUpdate(self):
+        """``VecGhostUpdate(ADD_VALUES, SCATTER_REVERSE)`` (e.g. ``python/tests/test_vector_assembly.py:51``)."""
+        if self.ghost_exchange is not None:
+            self.ghost_exchange.reduce_vector(self)
+
+    def norm(self) -> float:
+        return float(torch.linalg.vector_norm(self.data))

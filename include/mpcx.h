@@ -1,0 +1,219 @@
+/*
+ * mpcx.h -- C ABI of the B200-native MPC-constrained assembly engine (libmpcx.so).
+ *
+ * This is the drop-in boundary for the hot path of jorgensd/dolfinx_mpc: the
+ * entry points below are what the reference's FFI layer for this path
+ * (nanobind module dolfinx_mpc.cpp.mpc, python/src/dolfinx_mpc/mpc.cpp:261-345)
+ * would bind instead of its own C++ loops.  Plain pointers and sizes only; no
+ * torch / DOLFINx / PETSc types.  The array layouts are the ones the reference
+ * states explicitly in its numba path (python/src/dolfinx_mpc/numba/
+ * assemble_matrix.py:58-104): blocked int32 dofmaps, 3-padded float64 geometry,
+ * dof-indexed master/coefficient adjacency lists, int8 slave / bc markers.
+ *
+ * Conventions
+ *  - every function returns 0 (MPCX_OK) or an mpcx_status; mpcx_last_error()
+ *    gives the message (thread-local).  Reference: C++ std::runtime_error
+ *    surfaced by nanobind (cpp/assemble_matrix.cpp:315,464,605,659).
+ *  - pointers inside the structs are DEVICE pointers unless the name ends in
+ *    _host.  They are borrowed for the call.  Outputs are written in place.
+ *  - `stream` is a cudaStream_t passed as void*; kernels are asynchronous.
+ *  - a slave/entry outside the sparsity pattern raises a device-side flag read
+ *    back by mpcx_device_error() (one 4-byte copy + stream sync).
+ *  - T = float64 (suffix _f64).  Integer maps int32, row_ptr int64.
+ */
+#ifndef MPCX_H
+#define MPCX_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MPCX_ABI_VERSION 1
+#define MPCX_MAX_CONSTANTS 8
+
+typedef enum mpcx_status
+{
+  MPCX_OK = 0,
+  MPCX_ERR_ARG = 1,          /* bad argument (null pointer, negative size ...) */
+  MPCX_ERR_UNSUPPORTED = 2,  /* kernel/element combination without a device kernel */
+  MPCX_ERR_CUDA = 3,         /* CUDA runtime error */
+  MPCX_ERR_PATTERN = 4,      /* an insertion fell outside the sparsity pattern */
+  MPCX_ERR_ALLOC = 5
+} mpcx_status;
+
+/* Element kernels: replace the opaque FFCx tabulate_tensor function pointer
+ * (cpp/assemble_matrix.cpp:438-439,505-506; numba/assemble_matrix.py:138-145). */
+typedef enum mpcx_kernel
+{
+  MPCX_KERNEL_LAPLACE = 0,         /* c[0] * inner(grad u, grad v) dx, block-diagonal for bs > 1 */
+  MPCX_KERNEL_MASS = 1,            /* c[0] * inner(u, v) dx */
+  MPCX_KERNEL_ELASTICITY = 2,      /* inner(sigma(u), grad v) dx; c = {mu, lambda}; bs == gdim */
+  MPCX_KERNEL_SOURCE = 3,          /* c[0] * inner(f, v) dx (linear form); w = f at the cell dofs */
+  MPCX_KERNEL_LAPLACE_VARCOEF = 4  /* c[0] * w * inner(grad u, grad v) dx; w scalar, same element */
+} mpcx_kernel;
+
+/* Tabulated element (what FFCx bakes into the generated kernel). */
+typedef struct mpcx_tables
+{
+  int32_t tdim, gdim, nd, ng, nq, bs;
+  const double* weights; /* [nq] */
+  const double* phi;     /* [nq][nd] */
+  const double* dphi;    /* [nq][tdim][nd] */
+  const double* gdphi;   /* [nq][tdim][ng] */
+} mpcx_tables;
+
+/* Geometry: mesh.geometry().x() / dofmaps().front() (cpp/assemble_matrix.cpp:465-470).
+ * x_stride is 3 (the reference layout) or 4 (padded device mirror, 32-byte rows). */
+typedef struct mpcx_mesh
+{
+  const double* x;
+  const int32_t* x_dofmap; /* [num_cells][ng] */
+  int64_t num_nodes;
+  int32_t ng;
+  int32_t x_stride;
+} mpcx_mesh;
+
+/* dofmap.map() / bs() (cpp/assemble_matrix.cpp:474-478). */
+typedef struct mpcx_dofmap
+{
+  const int32_t* map; /* [num_cells][nd], blocked */
+  int32_t nd, bs;
+  int64_t num_dofs; /* unrolled, owned + ghost */
+} mpcx_dofmap;
+
+/* MultiPointConstraint data (cpp/MultiPointConstraint.h:201-223; tuple `mpc_data`
+ * of numba/assemble_matrix.py:60-74). */
+typedef struct mpcx_mpc
+{
+  const int8_t* is_slave;          /* [num_dofs] */
+  const int32_t* masters;          /* adjacency values, local (extended-map) dof ids */
+  const double* coeffs;            /* same offsets */
+  const int32_t* offsets;          /* [num_dofs + 1] */
+  const int32_t* cell_to_slaves;   /* adjacency values (ascending slave dofs per cell) */
+  const int32_t* cell_to_slaves_offsets; /* [num_cells + 1] */
+  const int32_t* slaves;           /* sorted, first num_local_slaves are owned */
+  int32_t num_slaves, num_local_slaves;
+  int64_t num_dofs;
+} mpcx_mpc;
+
+/* Device CSR the element tensors accumulate into (replaces the PETSc Mat behind
+ * mat_add_block_values / mat_add_values, python/src/dolfinx_mpc/mpc.cpp:284-287). */
+typedef struct mpcx_csr
+{
+  const int64_t* row_ptr; /* [num_rows + 1] */
+  const int32_t* col;     /* ascending within a row */
+  double* val;
+  int64_t num_rows, nnz;
+} mpcx_csr;
+
+/* One cell integral: kernel, integration domain, packed coefficients, constants
+ * (cpp/assemble_matrix.cpp:620-636). */
+typedef struct mpcx_integral
+{
+  int32_t kernel;
+  const mpcx_tables* tables;  /* host struct holding device pointers */
+  const int32_t* cells;       /* active cells or NULL for 0..num_cells-1 */
+  int64_t num_cells;
+  const double* coeffs;       /* packed [num_cells][cstride], by position (:505), or NULL */
+  int32_t cstride;
+  /* alternative to `coeffs`: gather w from a nodal array through a dofmap inside the
+   * kernel (device-side pack_coefficients, cpp/assemble_matrix.cpp:587-589) */
+  const double* coeff_nodal;
+  const int32_t* coeff_dofmap; /* [num_cells][coeff_nd] */
+  int32_t coeff_nd, coeff_bs;
+  int32_t num_constants;
+  double constants[MPCX_MAX_CONSTANTS];
+  /* optional: compacted list of the active cells that hold a slave dof (row or column
+   * side).  When given together with a scatter plan the bulk kernel skips those cells
+   * and the elimination kernel runs on this list only. */
+  const int32_t* slave_cells;      /* values are POSITIONS into the active list */
+  int64_t num_slave_cells;
+} mpcx_integral;
+
+/* Scatter plan: for every active cell and local entry (p, q) the offset of column
+ * d1(q) inside CSR row d0(p) (blocked: offset of the block).  Built once per
+ * (pattern, dofmaps) pair -- the role PETSc's per-call row search plays in the
+ * reference, hoisted out of the assembly loop. */
+typedef struct mpcx_plan
+{
+  const void* lpos;     /* [num_cells][nd0*nd1] uint8 or uint16 */
+  int32_t width;        /* 1 or 2 bytes per entry */
+} mpcx_plan;
+
+const char* mpcx_last_error(void);
+int mpcx_abi_version(void);
+
+/* Reads and clears the device-side error flag (syncs `stream`). 0 = none,
+ * MPCX_ERR_PATTERN = an insertion missed the pattern. */
+int mpcx_device_error(void* stream);
+
+/* A += integral, with BC row/column zeroing and MPC elimination K^T A_e K.
+ * Replaces assemble_cells_impl + modify_mpc_cell (cpp/assemble_matrix.cpp:417-548,
+ * 99-268).  bc0 / bc1 may be NULL.  plan may be NULL (row search per entry). */
+int mpcx_assemble_matrix_f64(const mpcx_integral* integral, const mpcx_mesh* mesh,
+                             const mpcx_dofmap* dofmap0, const mpcx_dofmap* dofmap1,
+                             const int8_t* bc0, const int8_t* bc1,
+                             const mpcx_mpc* mpc0, const mpcx_mpc* mpc1,
+                             const mpcx_csr* A, const mpcx_plan* plan, void* stream);
+
+/* A[d, d] += diagval for the listed unrolled dofs.  Slave diagonal
+ * (cpp/assemble_matrix.cpp:711-724) and Dirichlet diagonal
+ * (python/src/dolfinx_mpc/assemble_matrix.py:59-62). */
+int mpcx_add_diagonal_f64(const mpcx_csr* A, const int32_t* dofs, int64_t n,
+                          double diagval, void* stream);
+
+/* Builds the scatter plan on the device (one row search per entry). */
+int mpcx_build_plan(const mpcx_dofmap* dofmap0, const mpcx_dofmap* dofmap1,
+                    const int32_t* cells, int64_t num_cells, const mpcx_csr* A,
+                    void* lpos_out, int32_t width, void* stream);
+
+/* b += integral with K^T b_e.  Replaces _assemble_entities_impl + modify_mpc_vec
+ * (cpp/assemble_vector.cpp:34-91, cpp/assemble_vector.h:35-69).  b is NOT zeroed. */
+int mpcx_assemble_vector_f64(const mpcx_integral* integral, const mpcx_mesh* mesh,
+                             const mpcx_dofmap* dofmap, const mpcx_mpc* mpc,
+                             double* b, void* stream);
+
+/* b -= scale * K^T A_e (g - x0) on cells with a Dirichlet column.  Replaces
+ * lift_bc_entities + lift_bcs_cell (cpp/lifting.h:45-134,250-301).  x0 may be NULL. */
+int mpcx_apply_lifting_f64(const mpcx_integral* integral, const mpcx_mesh* mesh,
+                           const mpcx_dofmap* dofmap0, const mpcx_dofmap* dofmap1,
+                           const int8_t* bc_markers1, const double* bc_values1,
+                           const double* x0, double scale, const mpcx_mpc* mpc0,
+                           double* b, void* stream);
+
+/* u[s] = sum_k coeff_k u[master_k] / u[s] = 0 for every slave.  Replaces
+ * MultiPointConstraint::backsubstitution / homogenize (cpp/MultiPointConstraint.h:129-152). */
+int mpcx_backsubstitution_f64(const mpcx_mpc* mpc, double* u, void* stream);
+int mpcx_homogenize_f64(const mpcx_mpc* mpc, double* u, void* stream);
+
+/* Ghost-row exchange helpers (PETSc MatAssembly / VecGhostUpdate(ADD, REVERSE) in the
+ * reference's callers, python/src/dolfinx_mpc/assemble_matrix.py:60-64):
+ * dst[i] = src[idx[i]]  and  dst[idx[i]] += src[i]. */
+int mpcx_gather_f64(const double* src, const int64_t* idx, int64_t n, double* dst, void* stream);
+int mpcx_scatter_add_f64(double* dst, const int64_t* idx, int64_t n, const double* src, void* stream);
+
+/* Sparsity pattern with the MPC additions, on the HOST (cold path; replaces
+ * create_sparsity_pattern, cpp/utils.h:381-496).  All pointers are host pointers.
+ * The scalar CSR is returned in malloc'ed arrays released with mpcx_free_host. */
+typedef struct mpcx_mpc_host
+{
+  const int32_t* masters;
+  const int32_t* offsets;
+  const int32_t* cell_to_slaves;
+  const int32_t* cell_to_slaves_offsets;
+} mpcx_mpc_host;
+
+int mpcx_create_pattern_host(const int32_t* dofmap0, int32_t nd0, int32_t bs0,
+                             const int32_t* dofmap1, int32_t nd1, int32_t bs1,
+                             int64_t num_cells, int64_t num_block_rows,
+                             const mpcx_mpc_host* mpc0, const mpcx_mpc_host* mpc1,
+                             int32_t num_threads, int64_t** row_ptr_out,
+                             int32_t** col_out, int64_t* nnz_out);
+void mpcx_free_host(void* p);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MPCX_H */
