@@ -1,0 +1,192 @@
+"""GPU parity tests: the CUDA path (through the C ABI, libmpcx.so) against the CPU oracle on the same inputs.
+
+Bar (BASELINE.json north_star): CSR ``row_ptr`` / ``col`` and all integer maps bit-exact; CSR values and RHS
+within 1e-10 relative, with the floor ``1e-10 * ||row||_inf`` for entries that cancel to ~0 (SURVEY.md section 7,
+"Relative tolerance near zero"); plus the reference's own identities ``K^H A K == A_mpc[free, free]``,
+``K^H b == b_mpc[free]`` at its tolerance 5e-12 (python/src/dolfinx_mpc/utils/test.py:202-265).
+"""
+import numpy as np
+import pytest
+import scipy.sparse as sp
+
+import problems
+
+pytestmark = pytest.mark.gpu
+
+RTOL = 1e-10
+
+
+def _mpc(c):
+    from dolfinx_mpc_b200 import MultiPointConstraint
+
+    mpc = MultiPointConstraint(c.V)
+    mpc.add_constraint(c.V, *c.data)
+    mpc.finalize()
+    return mpc
+
+
+def assert_csr_close(rp, col, val, rp_o, col_o, val_o):
+    assert np.array_equal(rp, rp_o), "row_ptr differs from the oracle"
+    assert np.array_equal(col, col_o), "col differs from the oracle"
+    n = len(rp) - 1
+    rows = np.repeat(np.arange(n), np.diff(rp))
+    rownorm = np.zeros(n)
+    np.maximum.at(rownorm, rows, np.abs(val_o))
+    tol = RTOL * np.maximum(np.abs(val_o), rownorm[rows])
+    bad = np.abs(val - val_o) > tol
+    assert not bad.any(), f"{bad.sum()} CSR values differ; worst {np.abs(val - val_o).max():.3e}"
+
+
+def assert_vec_close(b, b_o):
+    scale = np.abs(b_o).max() if len(b_o) else 1.0
+    assert np.all(np.abs(b - b_o) <= RTOL * np.maximum(np.abs(b_o), scale)), np.abs(b - b_o).max()
+
+
+@pytest.mark.parametrize("name", list(problems.ALL_CASES))
+def test_matrix_vector_lifting_match_oracle(oracle, name):
+    import dolfinx_mpc_b200 as mpcx
+
+    c = problems.ALL_CASES[name]()
+    mpc = _mpc(c)
+    m = oracle.mpc_from_arrays(c.V, c.data)
+    n = c.V.num_dofs
+
+    # matrix
+    A = mpcx.assemble_matrix(c.a, mpc, bcs=c.bcs, diagval=1.0)
+    rp, col, val = A.getValuesCSR()
+    rp_o, col_o, val_o = oracle.assemble_matrix(c.a, m, bcs=c.bcs, diagval=1.0)
+    assert_csr_close(rp, col, val, rp_o, col_o, val_o)
+
+    # re-assembly into the same matrix (cached pattern + plan) gives the same result
+    mpcx.assemble_matrix(c.a, mpc, bcs=c.bcs, diagval=1.0, A=A)
+    assert_csr_close(*A.getValuesCSR(), rp_o, col_o, val_o)
+
+    # reference identity with an unconstrained oracle assembly
+    e = oracle.OracleMPC.empty(c.V)
+    A_org = sp.csr_matrix(oracle.assemble_matrix(c.a, e, bcs=c.bcs)[::-1], shape=(n, n))
+    slaves, masters, coeffs, _, offsets = c.data
+    K = oracle.transformation_matrix(n, slaves, masters, coeffs, offsets)
+    oracle.compare_mpc_lhs(A_org, A.to_scipy(), K, slaves)
+
+    if c.L is None:
+        return
+    b = mpcx.assemble_vector(c.L, mpc)
+    b_o = oracle.assemble_vector(c.L, m)
+    assert_vec_close(b.array, b_o)
+    b0 = oracle.assemble_vector(c.L, e)
+    if c.a_lift is not None and c.bcs:
+        mpcx.apply_lifting(b, [c.a_lift], [c.bcs], mpc)
+        oracle.apply_lifting(b_o, [c.a_lift], [c.bcs], m)
+        assert_vec_close(b.array, b_o)
+        oracle.apply_lifting(b0, [c.a_lift], [c.bcs], e)
+    oracle.compare_mpc_rhs(b0, b.array, K, slaves)
+
+
+@pytest.mark.parametrize("name", ["periodic2d-P1-8-bc1", "slip3d-P1-3", "contact3d"])
+def test_lifting_with_x0_and_scale(oracle, name):
+    import dolfinx_mpc_b200 as mpcx
+
+    c = problems.ALL_CASES[name]()
+    mpc = _mpc(c)
+    m = oracle.mpc_from_arrays(c.V, c.data)
+    rng = np.random.default_rng(5)
+    x0 = rng.random(c.V.num_dofs)
+    b = mpcx.assemble_vector(c.L, mpc)
+    b_o = oracle.assemble_vector(c.L, m)
+    mpcx.apply_lifting(b, [c.a_lift], [c.bcs], mpc, x0=[x0], scale=-0.7)
+    oracle.apply_lifting(b_o, [c.a_lift], [c.bcs], m, x0=[x0], scale=-0.7)
+    assert_vec_close(b.array, b_o)
+
+
+def test_no_plan_path_matches(oracle):
+    """Row-search scatter (plan == NULL) and planned scatter give the same matrix."""
+    import dolfinx_mpc_b200 as mpcx
+
+    c = problems.case_periodic_3d(4, 1, (0, 1), True)
+    mpc = _mpc(c)
+    m = oracle.mpc_from_arrays(c.V, c.data)
+    A = mpcx.create_matrix(c.a, mpc)
+    A.max_block_row = 1 << 20  # disables the plan
+    mpcx.assemble_matrix(c.a, mpc, bcs=c.bcs, A=A)
+    assert_csr_close(*A.getValuesCSR(), *oracle.assemble_matrix(c.a, m, bcs=c.bcs))
+
+
+def test_backsubstitution_homogenize(oracle):
+    from dolfinx_mpc_b200 import fem
+
+    c = problems.case_contact_3d()
+    mpc = _mpc(c)
+    m = oracle.mpc_from_arrays(c.V, c.data)
+    rng = np.random.default_rng(2)
+    u = fem.Function(c.V, rng.random(c.V.num_dofs))
+    u_o = u.array.copy()
+    mpc.backsubstitution(u)
+    oracle.backsubstitution(m, u_o)
+    assert np.allclose(u.array, u_o, rtol=1e-14, atol=0)
+    mpc.homogenize(u)
+    oracle.homogenize(m, u_o)
+    assert np.array_equal(u.array, u_o)
+
+
+def test_pattern_error_is_loud():
+    """An insertion outside the pattern must raise, never be dropped silently."""
+    import dolfinx_mpc_b200 as mpcx
+    from dolfinx_mpc_b200 import _lib
+
+    c = problems.case_periodic_2d(6, 1, False)
+    mpc = _mpc(c)
+    empty = mpcx.MultiPointConstraint(c.V)
+    empty.finalize()
+    A = mpcx.create_matrix(c.a, empty)  # pattern without the master columns
+    with pytest.raises(_lib.MpcxError):
+        mpcx.assemble_matrix(c.a, mpc, A=A)
+
+
+def test_rectangular_constraint_pair(oracle):
+    """mpc0 != mpc1 (python/tests/test_rectangular_assembly.py): rows eliminated with one constraint, columns
+    with another; no slave diagonal (cpp/assemble_matrix.cpp:711-724)."""
+    import dolfinx_mpc_b200 as mpcx
+    from dolfinx_mpc_b200 import generators as gen
+
+    c = problems.case_periodic_2d(6, 1, False)
+    mpc0 = _mpc(c)
+    data1 = gen.periodic_constraint(c.V, axes=(1,), scale=0.5)
+    mpc1 = mpcx.MultiPointConstraint(c.V)
+    mpc1.add_constraint(c.V, *data1)
+    mpc1.finalize()
+    A = mpcx.assemble_matrix(c.a, (mpc0, mpc1))
+    m0 = oracle.mpc_from_arrays(c.V, c.data)
+    m1 = oracle.mpc_from_arrays(c.V, data1)
+    assert_csr_close(*A.getValuesCSR(), *oracle.assemble_matrix(c.a, m0, m1, same_space=False))
+
+
+def test_mid_size_properties(oracle):
+    """A size the oracle still finishes in seconds (32^3 P1, periodic x/y): entry-wise parity, and the
+    size-independent properties used at full BASELINE sizes: constant vectors are in the null space of the
+    Laplace part on free rows, slave rows hold only the diagonal, sum(b) is preserved by K^T."""
+    import dolfinx_mpc_b200 as mpcx
+    from dolfinx_mpc_b200 import fem, generators as gen
+
+    mesh = gen.create_unit_cube(32, 32, 32)
+    V = gen.functionspace(mesh, 1)
+    data = gen.periodic_constraint(V, axes=(0, 1))
+    mpc = mpcx.MultiPointConstraint(V)
+    mpc.add_constraint(V, *data)
+    mpc.finalize()
+    a = fem.laplace(V)
+    f = fem.Function(V)
+    f.interpolate(problems._f3d)
+    L = fem.source(V, f)
+    A = mpcx.assemble_matrix(a, mpc)
+    b = mpcx.assemble_vector(L, mpc)
+    m = oracle.mpc_from_arrays(V, data)
+    assert_csr_close(*A.getValuesCSR(), *oracle.assemble_matrix(a, m))
+    assert_vec_close(b.array, oracle.assemble_vector(L, m))
+    S = A.to_scipy()
+    free = np.setdiff1d(np.arange(V.num_dofs), mpc.slaves)
+    ones = np.zeros(V.num_dofs)
+    ones[free] = 1.0
+    assert np.abs((S @ ones)[free]).max() < 1e-12
+    assert np.array_equal(S.diagonal()[mpc.slaves], np.ones(len(mpc.slaves)))
+    e = oracle.OracleMPC.empty(V)
+    assert abs(b.array.sum() - oracle.assemble_vector(L, e).sum()) < 1e-12
