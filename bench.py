@@ -1,0 +1,401 @@
+#!/usr/bin/env python
+"""bench.py -- cells assembled/sec (matrix + vector) for MPC-constrained assembly on B200.
+
+Workload (BASELINE.json configs[1]): 3D unit-cube Poisson, P1 tetrahedra (Kuhn split), 256^3 dofs, periodic
+x/y multi-point constraint, Dirichlet on z in {0, 1}, fp64.  One "step" = what LinearProblem.solve does before
+the linear solve (python/src/dolfinx_mpc/problem.py:539-582): zero + assemble_matrix (bulk cells, slave-cell
+elimination, slave and Dirichlet diagonals), zero + assemble_vector, apply_lifting.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--n 256]
+
+N > 1 is launched by torchrun (one rank per GPU); cells shard by z-slab ownership, per-GPU work fixed
+(weak scaling), ghost rows reduced over NCCL at the end of every step.
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+FALLBACK_HBM_GBS = 6650.0  # /opt/skills/guides/B200_PROFILING.md fallback
+
+
+def f_source(x):
+    # python/benchmarks/bench_periodic.py:85-91
+    return x[0] * np.sin(5 * np.pi * x[1]) + np.exp(-((x[0] - 0.5) ** 2 + (x[1] - 0.5) ** 2) / 0.02)
+
+
+def build_problem(n: int, nz: int | None = None):
+    """Unit-cube P1 Poisson with n^2 x (nz or n) nodes, periodic x/y, Dirichlet z-faces (host arrays)."""
+    from dolfinx_mpc_b200 import MultiPointConstraint, fem, generators as gen
+
+    nz = n if nz is None else nz
+    mesh = gen.create_box(n - 1, n - 1, nz - 1, p1=(1.0, 1.0, (nz - 1) / (n - 1)))
+    V = gen.functionspace(mesh, 1)
+    zmax = mesh.x[:, 2].max()
+    bc_dofs = fem.locate_dofs_geometrical(V, lambda x: np.isclose(x[2], 0) | np.isclose(x[2], zmax))
+    bcs = [fem.DirichletBC(V, bc_dofs, 0.25)]
+    data = gen.periodic_constraint(V, axes=(0, 1), exclude_dofs=bc_dofs)
+    mpc = MultiPointConstraint(V)
+    mpc.add_constraint(V, *data)
+    mpc.finalize()
+    a = fem.laplace(V)
+    f = fem.Function(V)
+    f.interpolate(f_source)
+    L = fem.source(V, f)
+    return dict(mesh=mesh, V=V, bcs=bcs, data=data, mpc=mpc, a=a, L=L, f=f)
+
+
+def algorithmic_bytes(P, nnz: int, with_rhs: bool) -> float:
+    """SURVEY.md section 8(d) compulsory-traffic formula, exact nnz of the built pattern."""
+    V, mesh = P["V"], P["mesh"]
+    nc = mesh.num_cells_local
+    nd, ng = V.nd, mesh.x_dofmap.shape[1]
+    ndofs = V.num_dofs
+    per_cell = 4 * nd + 4 * ng + 4
+    glob = 24 * mesh.x.shape[0] + 2 * ndofs + nnz * 12 + 8 * (ndofs + 1) + (8 * ndofs if with_rhs else 0)
+    return per_cell * nc + glob
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.proc = None
+        self.gpu = gpu_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.gpu)], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+        except OSError:
+            self.proc = None
+
+    def stop(self) -> dict:
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            out, _ = self.proc.communicate(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+            out, _ = self.proc.communicate()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in out.strip().splitlines():
+            p = [q.strip() for q in line.split(",")]
+            if len(p) < 9:
+                continue
+            try:
+                sm.append(float(p[1]))
+                mx.append(float(p[2]))
+            except ValueError:
+                continue
+            for name, v in zip(names, p[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ------------------------------------------------------------------------------------------------ CPU reference arm
+
+def cpu_reference(n: int, steps: int, warmup: int, budget_s: float, label: str):
+    """The reference's algorithm (oracle port, oracle/mpc_oracle.c -- the reference itself cannot be built in
+    this image) on all host cores: R = nproc independent ranks, each assembling its own z-slab into its own
+    local matrix / vector with no communication, as `mpirun -n R` does (README.md:30 of the reference);
+    time = slowest rank.  Each step is a bounded sample: slabs of `nz_s` node layers per rank."""
+    from oracle import oracle as orc
+
+    orc.build()
+    R = os.cpu_count() or 1
+    # calibrate the slab thickness on one rank so that a step lasts about budget_s / (steps + warmup)
+    nz_s = 3
+    P0 = build_problem(n, nz_s)
+    m0 = orc.mpc_from_arrays(P0["V"], P0["data"])
+    pat0 = orc.create_pattern(P0["a"], m0, m0)
+    t0 = time.perf_counter()
+    orc.assemble_matrix(P0["a"], m0, bcs=P0["bcs"], pattern=pat0)
+    b0 = orc.assemble_vector(P0["L"], m0)
+    orc.apply_lifting(b0, [P0["a"]], [P0["bcs"]], m0)
+    rate = P0["mesh"].num_cells_local / (time.perf_counter() - t0)  # cells/s, one rank, cold
+    per_step = budget_s / max(1, steps + warmup)
+    layers = int(rate * per_step / (6 * (n - 1) ** 2))
+    nz_s = int(min(max(3, layers + 1), max(3, n // R + 1)))
+    probs = []
+    for r in range(R):
+        P = P0 if nz_s == 3 and r == 0 else build_problem(n, nz_s)
+        m = orc.mpc_from_arrays(P["V"], P["data"])
+        pat = orc.create_pattern(P["a"], m, m)
+        probs.append((P, m, pat, np.zeros(P["V"].num_dofs)))
+    cells = sum(p[0]["mesh"].num_cells_local for p in probs)
+    times = np.zeros(R)
+
+    def work(r):
+        P, m, pat, b = probs[r]
+        t = time.perf_counter()
+        orc.assemble_matrix(P["a"], m, bcs=P["bcs"], pattern=pat)
+        orc.assemble_vector(P["L"], m, b)
+        orc.apply_lifting(b, [P["a"]], [P["bcs"]], m)
+        times[r] = time.perf_counter() - t
+
+    def one_step():
+        th = [threading.Thread(target=work, args=(r,)) for r in range(R)]
+        t = time.perf_counter()
+        for x in th:
+            x.start()
+        for x in th:
+            x.join()
+        return time.perf_counter() - t
+
+    for _ in range(warmup):
+        one_step()
+    dts = [one_step() for _ in range(steps)]
+    total = float(sum(dts))
+    value = cells * steps / total
+    sample = (f"{label}: {R} independent ranks (threads, GIL released in C), each a {n}x{n}x{nz_s}-node slab of the "
+              f"workload ({cells} cells per step in total), pattern cached, zero+matrix+vector+lifting timed")
+    return value, total / steps * 1e3, R, sample, cells
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    value, ms, R, sample, cells = cpu_reference(args.n, args.steps, args.warmup, args.ref_budget, "reference arm")
+    line = {
+        "impl": "reference", "metric": "cells assembled/sec (matrix+vector)", "value": value, "unit": "cells/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": workload_config(args.n, args.gpus),
+        "cpu_baseline": {"value": value, "unit": "cells/s", "cores": R, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": "cells/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(n, gpus):
+    return {"workload": f"3D unit-cube Poisson P1 (Kuhn tets), {n}^3 dofs per GPU, periodic x/y MPC, Dirichlet z-faces, fp64"
+                        " (BASELINE.json configs[1])",
+            "n": n, "gpus": gpus, "l2": "inputs (>3 GB per step) far larger than the 126 MB L2; no explicit flush",
+            "partition": "z-slabs by ownership, ghost-row NCCL reduce" if gpus > 1 else "single GPU"}
+
+
+# ------------------------------------------------------------------------------------------------ GPU arm
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+
+    import __graft_entry__ as ge
+    import dolfinx_mpc_b200 as mpcx
+    from dolfinx_mpc_b200 import _lib, device as dev
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (no CPU fallback); use --impl reference for the CPU arm")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    if rank == 0:
+        ge.build()
+    if world > 1:
+        dist.barrier()
+    lib = _lib.load()
+
+    n = args.n
+    if world > 1:
+        from dolfinx_mpc_b200 import distributed
+
+        P = distributed.build_slab_problem(n, rank, world, f_source)
+    else:
+        P = build_problem(n)
+    mesh, V, mpc, a, L, bcs, f = (P[k] for k in ("mesh", "V", "mpc", "a", "L", "bcs", "f"))
+    nc = mesh.num_cells_local
+    f.device_array = dev.to_dev(f.array)
+    A = mpcx.create_matrix(a, mpc)
+    b = mpcx.create_vector(mpc)
+    if world > 1:
+        distributed.attach_ghost_exchange(A, b, P)
+
+    def step():
+        mpcx.assemble_matrix(a, mpc, bcs=bcs, A=A)
+        mpcx.assemble_vector(L, mpc, b=b)
+        mpcx.apply_lifting(b, [a], [bcs], mpc)
+        b.ghostUpdate()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        step()
+    barrier()
+    lib.mpcx_profile_enable(1)
+    launches0 = lib.mpcx_launch_count()
+    clocks = ClockSampler(local_rank)
+    if rank == 0:
+        clocks.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    ev0.record()
+    for _ in range(args.steps):
+        step()
+    ev1.record()
+    barrier()
+    clk = clocks.stop() if rank == 0 else None
+    ms_total = ev0.elapsed_time(ev1)
+    launches = lib.mpcx_launch_count() - launches0
+    kms, kn = C.c_double(0), C.c_longlong(0)
+    _lib.check(lib.mpcx_profile_read(C.byref(kms), C.byref(kn)))
+    lib.mpcx_profile_enable(0)
+    if world > 1:
+        t = torch.tensor([ms_total], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_total = float(t.item())
+        cells_t = torch.tensor([nc], device="cuda", dtype=torch.int64)
+        dist.all_reduce(cells_t)
+        total_cells = int(cells_t.item())
+    else:
+        total_cells = nc
+    value = total_cells * args.steps / (ms_total * 1e-3)
+
+    # roofline of the dominant kernel (bulk matrix kernel), rank 0
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    peak, peak_src = FALLBACK_HBM_GBS, "fallback (B200_PROFILING.md)"
+    if os.path.exists(peaks_path):
+        try:
+            peak = float(json.load(open(peaks_path))["hbm_gbs"])
+            peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    k_ms = kms.value / max(1, kn.value)
+    alg = algorithmic_bytes(P, A.nnz, with_rhs=False)
+    achieved = alg / (k_ms * 1e-3) / 1e9
+    roofline = {"bound": "hbm", "kernel": "matrix bulk kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": achieved / peak, "peak_source": peak_src, "traffic": args.traffic,
+                "algorithmic_bytes_per_launch": alg, "bytes_per_cell": alg / nc, "kernel_ms": k_ms,
+                "kernel_share_of_step": kms.value / ms_total}
+
+    # end-to-end through the public API with host (pinned) buffers: every array the call reads is copied
+    # host -> device inside the timed region, the assembled CSR values and RHS are copied back
+    e2e = run_e2e(args, P, A, b, step, world, barrier)
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        v, ms, R, sample, _ = cpu_reference(n, 1, 1, args.cpu_budget, "cpu_baseline")
+        cpu = {"value": v, "unit": "cells/s", "cores": R, "kind": "port", "sample": sample}
+
+    if rank == 0:
+        line = {
+            "metric": "cells assembled/sec (matrix+vector)", "value": value, "unit": "cells/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_total / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": dict(workload_config(n, world), cells_per_gpu=nc, dofs_per_gpu=V.num_dofs, nnz_per_gpu=A.nnz,
+                           slaves=len(mpc.slaves)),
+            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clk,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def run_e2e(args, P, A, b, step, world, barrier):
+    import torch
+
+    from dolfinx_mpc_b200 import device as dev
+
+    mesh, V, mpc, f = P["mesh"], P["V"], P["mpc"], P["f"]
+    mdev, sdev, cdev = dev.mesh_dev(mesh), dev.space_dev(V), dev.mpc_dev(mpc)
+    bc_key = [k for k in V._dev if isinstance(k, tuple) and k[0] in ("bc_markers", "lift")]
+    dst = [mdev["x"], mdev["x_dofmap"], sdev["dofmap"], f.device_array]
+    dst += [cdev[k] for k in ("is_slave", "masters", "coeffs", "offsets", "c2s", "c2s_off", "slaves")]
+    for k in bc_key:
+        v = V._dev[k]
+        dst += list(v) if isinstance(v, tuple) else [v]
+    dst = [t for t in dst if t is not None and t.numel() > 0]
+    src = [t.cpu().pin_memory() for t in dst]
+    out_val = torch.empty(A.nnz, dtype=torch.float64).pin_memory()
+    out_b = torch.empty(b.data.numel(), dtype=torch.float64).pin_memory()
+    h2d = sum(t.numel() * t.element_size() for t in src)
+    d2h = out_val.numel() * 8 + out_b.numel() * 8
+
+    def e2e_step():
+        for s, d in zip(src, dst):
+            d.copy_(s, non_blocking=True)
+        step()
+        out_val.copy_(A.val, non_blocking=True)
+        out_b.copy_(b.data, non_blocking=True)
+
+    for _ in range(max(1, min(args.warmup, 2))):
+        e2e_step()
+    barrier()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    k = max(1, min(args.steps, 5))
+    ev0.record()
+    for _ in range(k):
+        e2e_step()
+    ev1.record()
+    barrier()
+    ms = ev0.elapsed_time(ev1)
+    nc = mesh.num_cells_local
+    if world > 1:
+        import torch.distributed as dist
+
+        t = torch.tensor([ms], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+        c = torch.tensor([nc], device="cuda", dtype=torch.int64)
+        dist.all_reduce(c)
+        nc = int(c.item())
+    return {"value": nc * k / (ms * 1e-3), "unit": "cells/s", "h2d_bytes_per_step": int(h2d),
+            "d2h_bytes_per_step": int(d2h), "ms_per_step": ms / k, "steps": k,
+            "note": "pinned host copies of every array the assembly reads (geometry, dofmaps, MPC arrays, bc markers, "
+                    "coefficient) uploaded each step; CSR values and RHS downloaded; pattern/plan stay in the "
+                    "device matrix handle like the reference's cached Mat"}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--n", type=int, default=256, help="nodes per side (per GPU)")
+    ap.add_argument("--cpu-budget", type=float, default=15.0, help="seconds of CPU work for cpu_baseline")
+    ap.add_argument("--ref-budget", type=float, default=60.0, help="seconds of CPU work for --impl reference")
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--traffic", type=float, default=None, help="dram bytes per launch of the dominant kernel "
+                    "from an ncu --set full capture (profiles/), reported as roofline.traffic")
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl == "ours":
+        args.warmup = 3
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -65,7 +65,7 @@ SYMBOLS = (
     "mpcx_last_error", "mpcx_abi_version", "mpcx_device_error", "mpcx_assemble_matrix_f64",
     "mpcx_add_diagonal_f64", "mpcx_build_plan", "mpcx_assemble_vector_f64", "mpcx_apply_lifting_f64",
     "mpcx_backsubstitution_f64", "mpcx_homogenize_f64", "mpcx_gather_f64", "mpcx_scatter_add_f64",
-    "mpcx_create_pattern_host", "mpcx_free_host",
+    "mpcx_create_pattern_host", "mpcx_free_host", "mpcx_profile_enable", "mpcx_launch_count", "mpcx_profile_read",
 )
 
 _lib = None
@@ -104,6 +104,9 @@ def load():
     lib.mpcx_scatter_add_f64.argtypes = [vp, vp, i64, vp, vp]
     lib.mpcx_create_pattern_host.argtypes = [vp, i32, i32, vp, i32, i32, i64, i64, P(MpcHostS), P(MpcHostS), i32,
                                              P(P(C.c_int64)), P(P(C.c_int32)), P(i64)]
+    lib.mpcx_profile_enable.argtypes = [C.c_int]
+    lib.mpcx_launch_count.restype = C.c_longlong
+    lib.mpcx_profile_read.argtypes = [P(C.c_double), P(C.c_longlong)]
     lib.mpcx_free_host.argtypes = [vp]
     lib.mpcx_free_host.restype = None
     _lib = lib

@@ -72,15 +72,27 @@ def create_matrix(form: Form, mpc0: MultiPointConstraint, mpc1: Optional[MultiPo
 
 
 def _bc_markers(V, bcs, n: int):
-    """int8 marker over the unrolled dofs of ``V`` or None when no bc lives on it
-    (``cpp/assemble_matrix.cpp:687-705``)."""
+    """Device int8 marker over the unrolled dofs of ``V`` or None when no bc lives on it
+    (``cpp/assemble_matrix.cpp:687-705``).  Built on the host once per set of bcs and kept on the device."""
     mine = [bc for bc in bcs if bc.function_space is V or bc.function_space.dofmap is V.dofmap]
     if not mine:
         return None
-    m = np.zeros(n, dtype=np.int8)
-    for bc in mine:
-        bc.mark_dofs(m)
-    return m
+    key = ("bc_markers", n) + tuple(id(bc) for bc in mine)
+    if key not in V._dev:
+        m = np.zeros(n, dtype=np.int8)
+        for bc in mine:
+            bc.mark_dofs(m)
+        V._dev[key] = _dev.to_dev(m)
+    return V._dev[key]
+
+
+def _bc_owned_dofs(bc):
+    """Owned dofs of a bc on the device (``dolfinx.fem.petsc.insert_diagonal`` touches owned rows only)."""
+    if "owned_dofs" not in bc._dev:
+        V = bc.function_space
+        dofs = bc.dofs[bc.dofs < V.index_map.size_local * V.bs]
+        bc._dev["owned_dofs"] = (_dev.to_dev(dofs) if len(dofs) else None, len(dofs))
+    return bc._dev["owned_dofs"]
 
 
 def assemble_matrix(form: Form, constraint: Union[MultiPointConstraint, Sequence[MultiPointConstraint]],
@@ -99,10 +111,8 @@ def assemble_matrix(form: Form, constraint: Union[MultiPointConstraint, Sequence
     A.zeroEntries()
     V0, V1 = form.function_spaces
     st = _dev.stream_ptr()
-    bc0 = _bc_markers(V0, bcs, A.shape[0])
-    bc1 = _bc_markers(V1, bcs, A.shape[1])
-    bc0_d = None if bc0 is None else _dev.to_dev(bc0)
-    bc1_d = bc0_d if (bc1 is not None and bc0 is not None and V0 is V1) else (None if bc1 is None else _dev.to_dev(bc1))
+    bc0_d = _bc_markers(V0, bcs, A.shape[0])
+    bc1_d = bc0_d if (V0 is V1 and A.shape[0] == A.shape[1]) else _bc_markers(V1, bcs, A.shape[1])
     mesh_s = _dev.mesh_dev(form.mesh)["struct"]
     d0 = _dev.dofmap_struct(V0, A.shape[0])
     d1 = _dev.dofmap_struct(V1, A.shape[1])
@@ -118,20 +128,19 @@ def assemble_matrix(form: Form, constraint: Union[MultiPointConstraint, Sequence
         _lib.check(lib.mpcx_assemble_matrix_f64(C.byref(s), C.byref(mesh_s), C.byref(d0), C.byref(d1),
                                                 _dev.ptr(bc0_d), _dev.ptr(bc1_d), C.byref(m0), C.byref(m1),
                                                 C.byref(As), None if plan is None else C.byref(plan), st))
-    # slave diagonal for owned slaves when both sides share the constraint space (cpp/assemble_matrix.cpp:711-724)
-    if mpc0.function_space is mpc1.function_space and mpc0.num_local_slaves > 0:
+    # slave diagonal for owned slaves when both sides share the constraint space (cpp/assemble_matrix.cpp:711-724).
+    # In the reference every MultiPointConstraint owns a freshly created (extended) function space
+    # (cpp/MultiPointConstraint.h:117-120), so the shared_ptr comparison holds only for one and the same object.
+    if mpc0 is mpc1 and mpc0.num_local_slaves > 0:
         sl = _dev.mpc_dev(mpc0)["slaves"]
         _lib.check(lib.mpcx_add_diagonal_f64(C.byref(As), _dev.ptr(sl), mpc0.num_local_slaves, float(diagval), st))
     # Dirichlet diagonal (assemble_matrix.py:59-62 -> dolfinx insert_diagonal: owned dofs of every bc)
     if V0 is V1:
-        n_owned = V0.index_map.size_local * V0.bs
         for bc in bcs:
             if bc.function_space is V0 or bc.function_space.dofmap is V0.dofmap:
-                dofs = bc.dofs[bc.dofs < n_owned]
-                if len(dofs):
-                    t = _dev.to_dev(dofs)
-                    keep.append(t)
-                    _lib.check(lib.mpcx_add_diagonal_f64(C.byref(As), _dev.ptr(t), len(dofs), float(diagval), st))
+                t, nd_ = _bc_owned_dofs(bc)
+                if nd_:
+                    _lib.check(lib.mpcx_add_diagonal_f64(C.byref(As), _dev.ptr(t), nd_, float(diagval), st))
     _lib.check(lib.mpcx_device_error(st))
     A.assemble()
     return A

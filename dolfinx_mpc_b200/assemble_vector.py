@@ -62,14 +62,19 @@ def apply_lifting(b: Vector, form: Sequence[Form], bcs: Sequence[Sequence[Dirich
             continue
         V0, V1 = a.function_spaces
         n1 = V1.num_dofs
-        markers = np.zeros(n1, dtype=np.int8)  # cpp/lifting.h:166-180
-        values = np.zeros(n1, dtype=np.float64)
-        for bc in bcs[j]:
-            bc.mark_dofs(markers)
-            bc.set(values)
-        if not markers.any():
+        if not bcs[j]:
             continue
-        mk, vl = _dev.to_dev(markers), _dev.to_dev(values)
+        key = ("lift", n1) + tuple((id(bc), bc.version) for bc in bcs[j])
+        if key not in V1._dev:  # bc_markers1 / bc_values1 of cpp/lifting.h:166-180, kept on the device
+            markers = np.zeros(n1, dtype=np.int8)
+            values = np.zeros(n1, dtype=np.float64)
+            for bc in bcs[j]:
+                bc.mark_dofs(markers)
+                bc.set(values)
+            V1._dev[key] = (_dev.to_dev(markers), _dev.to_dev(values)) if markers.any() else None
+        if V1._dev[key] is None:
+            continue
+        mk, vl = V1._dev[key]
         x0_d = None
         if len(x0):
             x0_d = x0[j].data if isinstance(x0[j], Vector) else _dev.to_dev(np.asarray(x0[j], dtype=np.float64))

@@ -14,12 +14,55 @@
 #include <stdio.h>
 #include <string.h>
 
+#include <atomic>
+#include <mutex>
+#include <vector>
+
 #include "mpcx.h"
 
 namespace
 {
 thread_local char g_err[512] = "";
 __device__ int g_dev_err = 0;
+
+// ---- instrumentation (bench.py): launch counter and CUDA-event bracket of the dominant kernel
+std::atomic<long long> g_launches{0};
+bool g_profile = false;
+struct EvPair { cudaEvent_t a, b; };
+std::vector<EvPair> g_ev_pool, g_ev_used;
+std::mutex g_ev_mutex;
+#define MPCX_COUNT_LAUNCH() (g_launches.fetch_add(1, std::memory_order_relaxed))
+
+struct KernelTimer
+{
+  // records start on construction and stop on destruction when profiling is on
+  cudaStream_t s;
+  EvPair ev{};
+  bool on;
+  explicit KernelTimer(cudaStream_t stream) : s(stream), on(g_profile)
+  {
+    if (!on) return;
+    std::lock_guard<std::mutex> lk(g_ev_mutex);
+    if (g_ev_pool.empty())
+    {
+      cudaEventCreate(&ev.a);
+      cudaEventCreate(&ev.b);
+    }
+    else
+    {
+      ev = g_ev_pool.back();
+      g_ev_pool.pop_back();
+    }
+    cudaEventRecord(ev.a, s);
+  }
+  ~KernelTimer()
+  {
+    if (!on) return;
+    cudaEventRecord(ev.b, s);
+    std::lock_guard<std::mutex> lk(g_ev_mutex);
+    g_ev_used.push_back(ev);
+  }
+};
 
 int fail(int code, const char* fmt, const char* a = "")
 {
@@ -673,6 +716,35 @@ extern "C" {
 const char* mpcx_last_error(void) { return g_err; }
 int mpcx_abi_version(void) { return MPCX_ABI_VERSION; }
 
+int mpcx_profile_enable(int on)
+{
+  g_profile = on != 0;
+  return MPCX_OK;
+}
+
+long long mpcx_launch_count(void) { return g_launches.load(); }
+
+int mpcx_profile_read(double* ms_sum, long long* n_timed)
+{
+  std::lock_guard<std::mutex> lk(g_ev_mutex);
+  double tot = 0.0;
+  long long n = 0;
+  for (auto& ev : g_ev_used)
+  {
+    float ms = 0.f;
+    cudaError_t e = cudaEventSynchronize(ev.b);
+    if (e == cudaSuccess) e = cudaEventElapsedTime(&ms, ev.a, ev.b);
+    if (e != cudaSuccess) return cuda_check(e, "profile_read");
+    tot += ms;
+    ++n;
+    g_ev_pool.push_back(ev);
+  }
+  g_ev_used.clear();
+  if (ms_sum) *ms_sum = tot;
+  if (n_timed) *n_timed = n;
+  return MPCX_OK;
+}
+
 int mpcx_device_error(void* stream)
 {
   int h = 0, zero = 0;
@@ -733,38 +805,42 @@ int mpcx_assemble_matrix_f64(const mpcx_integral* integral, const mpcx_mesh* mes
     if (nwork <= 0) return;
     const int grid = grid_for_warps(nwork, 4);
     if (width == 2)
-      k_matrix_generic<uint16_t><<<grid, 128, smem, s>>>(tab, in, md, dofmap0->map, dofmap1->map, nd, nd, bs, bs, bc0, bc1,
+      MPCX_COUNT_LAUNCH(), k_matrix_generic<uint16_t><<<grid, 128, smem, s>>>(tab, in, md, dofmap0->map, dofmap1->map, nd, nd, bs, bs, bc0, bc1,
                                                          m0, m1, Ad, (const uint16_t*)lpos, mode, spw);
     else
-      k_matrix_generic<uint8_t><<<grid, 128, smem, s>>>(tab, in, md, dofmap0->map, dofmap1->map, nd, nd, bs, bs, bc0, bc1,
+      MPCX_COUNT_LAUNCH(), k_matrix_generic<uint8_t><<<grid, 128, smem, s>>>(tab, in, md, dofmap0->map, dofmap1->map, nd, nd, bs, bs, bc0, bc1,
                                                         m0, m1, Ad, (const uint8_t*)lpos, mode, spw);
   };
   if (fast)
   {
     const long long nb = (in.ncells + 255) / 256;
+    KernelTimer kt(s);  // dominant kernel of the call
     if (t->tdim == 3)
     {
       if (width == 1)
-        k_matrix_p1_laplace<3, uint8_t><<<(unsigned)nb, 256, 0, s>>>(in, md, dofmap0->map, dofmap1->map, bc0, bc1, m0.c2s_off, m1.c2s_off, Ad, (const uint8_t*)lpos);
+        MPCX_COUNT_LAUNCH(), k_matrix_p1_laplace<3, uint8_t><<<(unsigned)nb, 256, 0, s>>>(in, md, dofmap0->map, dofmap1->map, bc0, bc1, m0.c2s_off, m1.c2s_off, Ad, (const uint8_t*)lpos);
       else
-        k_matrix_p1_laplace<3, uint16_t><<<(unsigned)nb, 256, 0, s>>>(in, md, dofmap0->map, dofmap1->map, bc0, bc1, m0.c2s_off, m1.c2s_off, Ad, (const uint16_t*)lpos);
+        MPCX_COUNT_LAUNCH(), k_matrix_p1_laplace<3, uint16_t><<<(unsigned)nb, 256, 0, s>>>(in, md, dofmap0->map, dofmap1->map, bc0, bc1, m0.c2s_off, m1.c2s_off, Ad, (const uint16_t*)lpos);
     }
     else
     {
       if (width == 1)
-        k_matrix_p1_laplace<2, uint8_t><<<(unsigned)nb, 256, 0, s>>>(in, md, dofmap0->map, dofmap1->map, bc0, bc1, m0.c2s_off, m1.c2s_off, Ad, (const uint8_t*)lpos);
+        MPCX_COUNT_LAUNCH(), k_matrix_p1_laplace<2, uint8_t><<<(unsigned)nb, 256, 0, s>>>(in, md, dofmap0->map, dofmap1->map, bc0, bc1, m0.c2s_off, m1.c2s_off, Ad, (const uint8_t*)lpos);
       else
-        k_matrix_p1_laplace<2, uint16_t><<<(unsigned)nb, 256, 0, s>>>(in, md, dofmap0->map, dofmap1->map, bc0, bc1, m0.c2s_off, m1.c2s_off, Ad, (const uint16_t*)lpos);
+        MPCX_COUNT_LAUNCH(), k_matrix_p1_laplace<2, uint16_t><<<(unsigned)nb, 256, 0, s>>>(in, md, dofmap0->map, dofmap1->map, bc0, bc1, m0.c2s_off, m1.c2s_off, Ad, (const uint16_t*)lpos);
     }
-    launch_generic(1, in.nslave_cells);
   }
   else if (have_split && lpos)
   {
+    KernelTimer kt(s);
     launch_generic(2, in.ncells);         // bulk cells, planned scatter
-    launch_generic(1, in.nslave_cells);   // slave cells, elimination
   }
   else
+  {
+    KernelTimer kt(s);
     launch_generic(0, in.ncells);
+  }
+  if (have_split && lpos) launch_generic(1, in.nslave_cells);   // slave cells, elimination
   return cuda_check(cudaGetLastError(), "assemble_matrix launch");
 }
 
@@ -773,7 +849,7 @@ int mpcx_add_diagonal_f64(const mpcx_csr* A, const int32_t* dofs, int64_t n, dou
   if (!A || (n > 0 && !dofs)) return fail(MPCX_ERR_ARG, "null argument");
   if (n <= 0) return MPCX_OK;
   const CsrD Ad{(const long long*)A->row_ptr, A->col, A->val};
-  k_add_diag<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(Ad, dofs, n, diagval);
+  MPCX_COUNT_LAUNCH(), k_add_diag<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(Ad, dofs, n, diagval);
   return cuda_check(cudaGetLastError(), "add_diagonal launch");
 }
 
@@ -788,10 +864,10 @@ int mpcx_build_plan(const mpcx_dofmap* dofmap0, const mpcx_dofmap* dofmap1, cons
   long long nb = (tot + 255) / 256;
   if (nb > 148LL * 64) nb = 148LL * 64;
   if (width == 1)
-    k_build_plan<uint8_t><<<(unsigned)nb, 256, 0, (cudaStream_t)stream>>>(dofmap0->map, dofmap1->map, dofmap0->nd, dofmap1->nd,
+    MPCX_COUNT_LAUNCH(), k_build_plan<uint8_t><<<(unsigned)nb, 256, 0, (cudaStream_t)stream>>>(dofmap0->map, dofmap1->map, dofmap0->nd, dofmap1->nd,
                                                                           dofmap0->bs, dofmap1->bs, cells, num_cells, Ad, (uint8_t*)lpos_out);
   else
-    k_build_plan<uint16_t><<<(unsigned)nb, 256, 0, (cudaStream_t)stream>>>(dofmap0->map, dofmap1->map, dofmap0->nd, dofmap1->nd,
+    MPCX_COUNT_LAUNCH(), k_build_plan<uint16_t><<<(unsigned)nb, 256, 0, (cudaStream_t)stream>>>(dofmap0->map, dofmap1->map, dofmap0->nd, dofmap1->nd,
                                                                            dofmap0->bs, dofmap1->bs, cells, num_cells, Ad, (uint16_t*)lpos_out);
   return cuda_check(cudaGetLastError(), "build_plan launch");
 }
@@ -817,15 +893,15 @@ int mpcx_assemble_vector_f64(const mpcx_integral* integral, const mpcx_mesh* mes
   if (integral->kernel == MPCX_KERNEL_SOURCE && bs == 1 && p1_simplex && w_ok)
   {
     const long long nb = (in.ncells + 255) / 256;
-    if (t->tdim == 3) k_vector_p1_source<3><<<(unsigned)nb, 256, 0, s>>>(in, md, dofmap->map, m.c2s_off, m, b);
-    else k_vector_p1_source<2><<<(unsigned)nb, 256, 0, s>>>(in, md, dofmap->map, m.c2s_off, m, b);
+    if (t->tdim == 3) MPCX_COUNT_LAUNCH(), k_vector_p1_source<3><<<(unsigned)nb, 256, 0, s>>>(in, md, dofmap->map, m.c2s_off, m, b);
+    else MPCX_COUNT_LAUNCH(), k_vector_p1_source<2><<<(unsigned)nb, 256, 0, s>>>(in, md, dofmap->map, m.c2s_off, m, b);
   }
   else
   {
     const int wcount = in.cstride > 0 ? in.cstride : 1;
     const int spw = 3 * mesh->ng + n + 3 * nd + wcount + 1;
     const size_t smem = (size_t)spw * 4 * sizeof(double);
-    k_vector_generic<<<grid_for_warps(in.ncells, 4), 128, smem, s>>>(tab, in, md, dofmap->map, nd, bs, m, b, spw);
+    MPCX_COUNT_LAUNCH(), k_vector_generic<<<grid_for_warps(in.ncells, 4), 128, smem, s>>>(tab, in, md, dofmap->map, nd, bs, m, b, spw);
   }
   return cuda_check(cudaGetLastError(), "assemble_vector launch");
 }
@@ -853,7 +929,7 @@ int mpcx_apply_lifting_f64(const mpcx_integral* integral, const mpcx_mesh* mesh,
     rc = cuda_check(cudaFuncSetAttribute(k_lifting_generic, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "smem attr");
     if (rc) return rc;
   }
-  k_lifting_generic<<<grid_for_warps(in.ncells, 4), 128, smem, (cudaStream_t)stream>>>(
+  MPCX_COUNT_LAUNCH(), k_lifting_generic<<<grid_for_warps(in.ncells, 4), 128, smem, (cudaStream_t)stream>>>(
       tab, in, md, dofmap0->map, dofmap1->map, nd, nd, bs, bs, bc_markers1, bc_values1, x0, scale, make_mpc(mpc0), b, spw);
   return cuda_check(cudaGetLastError(), "apply_lifting launch");
 }
@@ -862,7 +938,7 @@ int mpcx_backsubstitution_f64(const mpcx_mpc* mpc, double* u, void* stream)
 {
   if (!mpc || !u) return fail(MPCX_ERR_ARG, "null argument");
   if (mpc->num_slaves <= 0) return MPCX_OK;
-  k_backsub<<<(mpc->num_slaves + 255) / 256, 256, 0, (cudaStream_t)stream>>>(make_mpc(mpc), mpc->slaves, mpc->num_slaves, u, 0);
+  MPCX_COUNT_LAUNCH(), k_backsub<<<(mpc->num_slaves + 255) / 256, 256, 0, (cudaStream_t)stream>>>(make_mpc(mpc), mpc->slaves, mpc->num_slaves, u, 0);
   return cuda_check(cudaGetLastError(), "backsubstitution launch");
 }
 
@@ -870,7 +946,7 @@ int mpcx_homogenize_f64(const mpcx_mpc* mpc, double* u, void* stream)
 {
   if (!mpc || !u) return fail(MPCX_ERR_ARG, "null argument");
   if (mpc->num_slaves <= 0) return MPCX_OK;
-  k_backsub<<<(mpc->num_slaves + 255) / 256, 256, 0, (cudaStream_t)stream>>>(make_mpc(mpc), mpc->slaves, mpc->num_slaves, u, 1);
+  MPCX_COUNT_LAUNCH(), k_backsub<<<(mpc->num_slaves + 255) / 256, 256, 0, (cudaStream_t)stream>>>(make_mpc(mpc), mpc->slaves, mpc->num_slaves, u, 1);
   return cuda_check(cudaGetLastError(), "homogenize launch");
 }
 
@@ -880,7 +956,7 @@ int mpcx_gather_f64(const double* src, const int64_t* idx, int64_t n, double* ds
   if (!src || !idx || !dst) return fail(MPCX_ERR_ARG, "null argument");
   long long nb = (n + 255) / 256;
   if (nb > 148LL * 32) nb = 148LL * 32;
-  k_gather<<<(unsigned)nb, 256, 0, (cudaStream_t)stream>>>(src, (const long long*)idx, n, dst);
+  MPCX_COUNT_LAUNCH(), k_gather<<<(unsigned)nb, 256, 0, (cudaStream_t)stream>>>(src, (const long long*)idx, n, dst);
   return cuda_check(cudaGetLastError(), "gather launch");
 }
 
@@ -890,7 +966,7 @@ int mpcx_scatter_add_f64(double* dst, const int64_t* idx, int64_t n, const doubl
   if (!src || !idx || !dst) return fail(MPCX_ERR_ARG, "null argument");
   long long nb = (n + 255) / 256;
   if (nb > 148LL * 32) nb = 148LL * 32;
-  k_scatter_add<<<(unsigned)nb, 256, 0, (cudaStream_t)stream>>>(dst, (const long long*)idx, n, src);
+  MPCX_COUNT_LAUNCH(), k_scatter_add<<<(unsigned)nb, 256, 0, (cudaStream_t)stream>>>(dst, (const long long*)idx, n, src);
   return cuda_check(cudaGetLastError(), "scatter_add launch");
 }
 

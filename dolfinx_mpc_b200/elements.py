@@ -51,6 +51,8 @@ def make_quadrature(cell_type: str, degree: int):
     if cell_type == "triangle":
         if degree <= 1:
             return np.array([[1 / 3, 1 / 3]]), np.array([0.5])
+        if degree == 2:  # 3-point rule (what Basix' default scheme gives for degree 2)
+            return np.array([[1 / 6, 1 / 6], [1 / 6, 2 / 3], [2 / 3, 1 / 6]]), np.full(3, 1 / 6)
         r, wr = _gauss_jacobi_01(m, 1)
         s, ws = _gauss_jacobi_01(m, 0)
         pts = np.array([[ri, sj * (1 - ri)] for ri in r for sj in s])
@@ -59,6 +61,9 @@ def make_quadrature(cell_type: str, degree: int):
     if cell_type == "tetrahedron":
         if degree <= 1:
             return np.array([[0.25, 0.25, 0.25]]), np.array([1 / 6])
+        if degree == 2:  # 4-point rule
+            a, b = 0.5854101966249685, 0.1381966011250105
+            return np.array([[b, b, b], [a, b, b], [b, a, b], [b, b, a]]), np.full(4, 1 / 24)
         r, wr = _gauss_jacobi_01(m, 2)
         s, ws = _gauss_jacobi_01(m, 1)
         t, wt = _gauss_jacobi_01(m, 0)

@@ -164,7 +164,18 @@ class DirichletBC:
     def __init__(self, V: FunctionSpace, dofs: np.ndarray, value=0.0):
         self.function_space = V
         self.dofs = np.ascontiguousarray(dofs, dtype=np.int32)
-        self.value = value
+        self._value = value
+        self.version = 0  # bumped on every change of the value: keys the device-side marker/value caches
+        self._dev = {}
+
+    @property
+    def value(self):
+        return self._value
+
+    @value.setter
+    def value(self, v):
+        self._value = v
+        self.version += 1
 
     def mark_dofs(self, markers: np.ndarray):
         markers[self.dofs] = 1

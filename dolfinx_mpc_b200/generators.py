@@ -54,22 +54,29 @@ def create_unit_square(nx: int, ny: int, cell_type: str = "triangle") -> Mesh:
 
 def create_box(nx: int, ny: int, nz: int, cell_type: str = "tetrahedron", p0=(0.0, 0.0, 0.0),
                p1=(1.0, 1.0, 1.0)) -> Mesh:
-    """Structured box; tetrahedra are the Kuhn split (6 per cube, all sharing the (0,0,0)-(1,1,1) diagonal)."""
+    """Structured box; tetrahedra are the Kuhn split (6 per cube, all sharing the (0,0,0)-(1,1,1) diagonal).
+
+    Cells are numbered cube-major (x fastest, z slowest), the 6 tetrahedra of a cube consecutively; int32
+    throughout so that the 10^8-cell benchmark meshes are built without 64-bit temporaries."""
     x = _lattice((nx, ny, nz), p0, p1)
     sx, sy = nx + 1, (nx + 1) * (ny + 1)
-    K, J, I = np.meshgrid(np.arange(nz), np.arange(ny), np.arange(nx), indexing="ij")
-    v0 = (I + sx * J + sy * K).ravel().astype(np.int64)
-    e = (1, sx, sy)
+    assert (nx + 1) * (ny + 1) * (nz + 1) < 2**31
+    v0 = (np.arange(nx, dtype=np.int32)[None, None, :] + np.int32(sx) * np.arange(ny, dtype=np.int32)[None, :, None]
+          + np.int32(sy) * np.arange(nz, dtype=np.int32)[:, None, None]).reshape(-1)
+    e = (np.int32(1), np.int32(sx), np.int32(sy))
     if cell_type == "tetrahedron":
-        tets = []
-        for a, b, c in itertools.permutations(range(3)):
-            tets.append(np.stack([v0, v0 + e[a], v0 + e[a] + e[b], v0 + e[a] + e[b] + e[c]], 1))
-        cells = np.stack(tets, 1).reshape(-1, 4)
+        cells = np.empty((len(v0), 6, 4), dtype=np.int32)
+        for t, (a, b, c) in enumerate(itertools.permutations(range(3))):
+            cells[:, t, 0] = v0
+            cells[:, t, 1] = v0 + e[a]
+            cells[:, t, 2] = v0 + (e[a] + e[b])
+            cells[:, t, 3] = v0 + (e[a] + e[b] + e[c])
+        cells = cells.reshape(-1, 4)
     elif cell_type == "hexahedron":
         cells = np.stack([v0 + (i * e[0] + j * e[1] + k * e[2]) for k in (0, 1) for j in (0, 1) for i in (0, 1)], 1)
     else:
         raise ValueError(cell_type)
-    return Mesh(x, cells.astype(np.int32), cell_type)
+    return Mesh(x, cells.astype(np.int32, copy=False), cell_type)
 
 
 def create_unit_cube(nx: int, ny: int, nz: int, cell_type: str = "tetrahedron") -> Mesh:

@@ -145,6 +145,14 @@ typedef struct mpcx_plan
 const char* mpcx_last_error(void);
 int mpcx_abi_version(void);
 
+/* Instrumentation used by bench.py.  mpcx_launch_count: kernels launched by this library since load.
+ * mpcx_profile_enable(1): every following mpcx_assemble_matrix_f64 call brackets its dominant (bulk) kernel
+ * with CUDA events on the launch stream; mpcx_profile_read waits for them and returns the summed duration
+ * in milliseconds and the number of bracketed launches, then forgets them. */
+int mpcx_profile_enable(int on);
+long long mpcx_launch_count(void);
+int mpcx_profile_read(double* ms_sum, long long* n_timed);
+
 /* Reads and clears the device-side error flag (syncs `stream`). 0 = none,
  * MPCX_ERR_PATTERN = an insertion missed the pattern. */
 int mpcx_device_error(void* stream);

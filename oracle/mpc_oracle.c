@@ -106,6 +106,12 @@ static int jacobian(const orc_tables* t, int q, const double* X, double* K,
   return 1;
 }
 
+/* Affine cells (simplex, ng == tdim + 1) have a constant Jacobian: FFCx-generated kernels
+ * evaluate it once, outside the quadrature loop. */
+static int is_affine(const orc_tables* t) { return t->ng == t->tdim + 1; }
+#define GEOM_AT(q) \
+  if ((q) == 0 || !affine) { if (jacobian(t, (q), X, K, &detJ)) return; }
+
 /* physical gradients g[i][k] = sum_a K[a][k] dphi[q][a][i] */
 static void phys_grads(const orc_tables* t, int q, const double* K, double* g)
 {
@@ -128,10 +134,11 @@ static void k_laplace(double* A, const double* w, const double* c,
   (void)w; (void)e; (void)p;
   const orc_tables* t = (const orc_tables*)cd;
   const int n = t->nd * t->bs, bs = t->bs;
-  double K[9], detJ, g[3 * 64];
+  double K[9], detJ = 0, g[3 * 64];
+  const int affine = is_affine(t);
   for (int q = 0; q < t->nq; ++q)
   {
-    if (jacobian(t, q, X, K, &detJ)) return;
+    GEOM_AT(q)
     phys_grads(t, q, K, g);
     const double s = c[0] * t->weights[q] * fabs(detJ);
     for (int i = 0; i < t->nd; ++i)
@@ -152,10 +159,11 @@ static void k_laplace_varcoef(double* A, const double* w, const double* c,
   (void)e; (void)p;
   const orc_tables* t = (const orc_tables*)cd;
   const int n = t->nd * t->bs, bs = t->bs;
-  double K[9], detJ, g[3 * 64];
+  double K[9], detJ = 0, g[3 * 64];
+  const int affine = is_affine(t);
   for (int q = 0; q < t->nq; ++q)
   {
-    if (jacobian(t, q, X, K, &detJ)) return;
+    GEOM_AT(q)
     phys_grads(t, q, K, g);
     double kap = 0;
     for (int k = 0; k < t->nd; ++k) kap += t->phi[q * t->nd + k] * w[k];
@@ -177,10 +185,11 @@ static void k_mass(double* A, const double* w, const double* c, const double* X,
   (void)w; (void)e; (void)p;
   const orc_tables* t = (const orc_tables*)cd;
   const int n = t->nd * t->bs, bs = t->bs;
-  double K[9], detJ;
+  double K[9], detJ = 0;
+  const int affine = is_affine(t);
   for (int q = 0; q < t->nq; ++q)
   {
-    if (jacobian(t, q, X, K, &detJ)) return;
+    GEOM_AT(q)
     const double s = c[0] * t->weights[q] * fabs(detJ);
     for (int i = 0; i < t->nd; ++i)
       for (int j = 0; j < t->nd; ++j)
@@ -201,10 +210,11 @@ static void k_elasticity(double* A, const double* w, const double* c,
   const orc_tables* t = (const orc_tables*)cd;
   const int bs = t->bs, n = t->nd * bs, gd = t->gdim;
   const double mu = c[0], lmbda = c[1];
-  double K[9], detJ, g[3 * 64];
+  double K[9], detJ = 0, g[3 * 64];
+  const int affine = is_affine(t);
   for (int q = 0; q < t->nq; ++q)
   {
-    if (jacobian(t, q, X, K, &detJ)) return;
+    GEOM_AT(q)
     phys_grads(t, q, K, g);
     const double s = t->weights[q] * fabs(detJ);
     for (int i = 0; i < t->nd; ++i)
@@ -231,10 +241,11 @@ static void k_source(double* b, const double* w, const double* c,
   (void)e; (void)p;
   const orc_tables* t = (const orc_tables*)cd;
   const int bs = t->bs;
-  double K[9], detJ;
+  double K[9], detJ = 0;
+  const int affine = is_affine(t);
   for (int q = 0; q < t->nq; ++q)
   {
-    if (jacobian(t, q, X, K, &detJ)) return;
+    GEOM_AT(q)
     const double s = c[0] * t->weights[q] * fabs(detJ);
     for (int a = 0; a < bs; ++a)
     {
@@ -603,6 +614,24 @@ int orc_assemble_cells_vector(int kernel, const orc_tables* tab, const orc_mesh*
   }
   free(X); free(be); free(be_copy);
   return ORC_OK;
+}
+
+/* dolfinx::fem::pack_coefficients as called at cpp/assemble_matrix.cpp:587-589 and
+ * cpp/assemble_vector.cpp:113-116 (DOLFINx code, not in /root/reference): for every
+ * active entity, in iteration order, the cell-local dof values of one coefficient are
+ * copied into its column range [offset, offset + nd*bs) of the packed row. */
+void orc_pack_coefficient(const double* u, const orc_dofmap* dm, const int32_t* cells,
+                          int64_t num_cells, double* w, int cstride, int offset)
+{
+  const int nd = dm->nd, bs = dm->bs;
+  for (int64_t e = 0; e < num_cells; ++e)
+  {
+    const int32_t cell = cells ? cells[e] : (int32_t)e;
+    const int32_t* d = dm->map + (int64_t)cell * nd;
+    double* row = w + e * cstride + offset;
+    for (int i = 0; i < nd; ++i)
+      for (int k = 0; k < bs; ++k) row[i * bs + k] = u[(int64_t)d[i] * bs + k];
+  }
 }
 
 /* cpp/lifting.h:45-134 (lift_bc_entities) + :250-301 (lift_bcs_cell).

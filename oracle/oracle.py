@@ -180,12 +180,28 @@ def create_pattern(form, m0: OracleMPC, m1: OracleMPC):
     return row_ptr, col
 
 
-def _integral_args(form, it):
+def _pack_coefficients(form, it, cells, n, libpath=None):
+    """``pack_coefficients`` in C (the reference calls DOLFINx's C++ routine inside the timed path)."""
+    if not it.coefficients:
+        return None, 0
+    L = lib(libpath)
+    cstride = sum(f.function_space.nd * f.function_space.bs for f in it.coefficients)
+    w = np.empty((n, cstride))
+    off = 0
+    for f in it.coefficients:
+        Vf = f.function_space
+        d = _Dofmap(_a(Vf.dofmap), Vf.nd, Vf.bs)
+        L.orc_pack_coefficient(_p(f.array), C.byref(d), _p(cells), C.c_int64(n), _p(w), C.c_int(cstride), C.c_int(off))
+        off += Vf.nd * Vf.bs
+    return w, cstride
+
+
+def _integral_args(form, it, libpath=None):
     tab = form.tables(it)
     t = _tables(tab, form.function_spaces[0].bs)
-    w, cstride = form.pack_coefficients(it)
     cells = it.cells
     n = form.mesh.num_cells_local if cells is None else len(cells)
+    w, cstride = _pack_coefficients(form, it, cells, n, libpath)
     return t, tab, w, cstride, cells, n
 
 
