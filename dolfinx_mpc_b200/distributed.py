@@ -1,0 +1,299 @@
+"""Multi-GPU assembly: cells sharded by ownership, one ghost-row exchange at the end of every assembly.
+
+The reference assembles process-local cells with no communication (``README.md:30``) into rows for owned and
+ghost dofs; the cross-rank reduction happens afterwards in its callers -- PETSc ``MatAssemblyBegin/End``
+(``python/src/dolfinx_mpc/assemble_matrix.py:64``) and ``VecGhostUpdate(ADD_VALUES, SCATTER_REVERSE)``
+(``python/tests/test_vector_assembly.py:51``).  Here every GPU owns a local CSR over its owned + ghost rows
+(ghost rows last, so their values are one contiguous segment of ``val``); after the assembly kernels the
+ghost-row segments travel to their owners in ONE collective (``all_to_all_single`` over NCCL / NVLink) and are
+added in place by a scatter-add kernel.  As in a PETSc MPIAIJ matrix, the owner's rows are extended at setup
+with the columns that only off-process cells couple to ("pattern ghosts": extra local column ids after the
+index-map ghosts), so the exchange is a pure value transfer through a precomputed position table.
+
+Everything in this module except ``GhostExchange.reduce_*`` is once-per-pattern host code (numpy +
+``torch.distributed`` object collectives).
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Callable, Optional
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+from . import fem
+from . import generators as gen
+from .fem import IndexMap
+from .multipointconstraint import MultiPointConstraint
+
+
+# ------------------------------------------------------------------ pre-partitioned structured problem
+
+def slab_index_map(n: int, nzc: int, rank: int, world: int) -> IndexMap:
+    """Node ownership of the z-slab partition: rank r owns the node planes [r*nzc, (r+1)*nzc) -- the last rank
+    also the top plane -- and ghosts the plane (r+1)*nzc owned by rank r+1."""
+    plane = n * n
+    lo = rank * nzc * plane
+    n_own_planes = nzc + (1 if rank == world - 1 else 0)
+    size_local = n_own_planes * plane
+    total = (world * nzc + 1) * plane
+    if rank < world - 1:
+        ghosts = np.arange(plane, dtype=np.int64) + (rank + 1) * nzc * plane
+        owners = np.full(plane, rank + 1, dtype=np.int32)
+    else:
+        ghosts = np.zeros(0, np.int64)
+        owners = np.zeros(0, np.int32)
+    return IndexMap(size_local, ghosts, owners, (lo, lo + size_local), total, rank)
+
+
+def build_slab_problem(n: int, rank: int, world: int, f_expr: Callable, periodic_z: bool = False,
+                       nzc: Optional[int] = None, dirichlet: Optional[bool] = None, bc_value: float = 0.25):
+    """P1 Poisson on the box [0,1]^2 x [0, world*nzc/(n-1)] with n x n x (world*nzc + 1) nodes, cut into
+    ``world`` z-slabs of ``nzc`` cube layers.  Periodic in x and y; in z either Dirichlet on both end planes
+    (BASELINE.json configs[1] stacked) or periodic as well (configs[3]: the slaves of the top plane have
+    their masters on rank 0, which become extra ghosts of the last rank)."""
+    nzc = (n - 1) if nzc is None else nzc
+    dirichlet = (not periodic_z) if dirichlet is None else dirichlet
+    h = 1.0 / (n - 1)
+    z0 = rank * nzc * h
+    mesh = gen.create_box(n - 1, n - 1, nzc, p0=(0.0, 0.0, z0), p1=(1.0, 1.0, z0 + nzc * h))
+    mesh.rank, mesh.comm_size = rank, world
+    imap = slab_index_map(n, nzc, rank, world)
+    # local numbering == lattice numbering of the slab: owned planes first, the ghost (top) plane last
+    V = fem.FunctionSpace(mesh, 1, mesh.x_dofmap.copy(), 1, imap, mesh.x.copy())
+    X = V.tabulate_dof_coordinates()
+    ztop = world * nzc * h
+    bcs, exclude = [], None
+    if dirichlet:
+        on = np.zeros(X.shape[0], dtype=bool)
+        if rank == 0:
+            on |= np.isclose(X[:, 2], 0.0)
+        if rank == world - 1:
+            on |= np.isclose(X[:, 2], ztop)
+        exclude = np.flatnonzero(on).astype(np.int32)
+        bcs = [fem.DirichletBC(V, exclude, bc_value)]
+    data = gen.periodic_constraint(V, axes=(0, 1), exclude_dofs=exclude)
+    if periodic_z and rank == world - 1:
+        # top plane -> plane z = 0 (owner rank 0) composed with the x/y wrap; replaces the x/y entries there
+        plane = n * n
+        top_local = np.arange(plane, dtype=np.int64) + nzc * plane
+        i, j = top_local % n, (top_local // n) % n
+        m_glob = (i % (n - 1)) + n * (j % (n - 1))  # k = 0 plane, wrapped in x and y
+        keep = ~np.isin(data[0], top_local)
+        slaves = np.concatenate([data[0][keep], top_local.astype(np.int32)])
+        masters = np.concatenate([data[1][keep], m_glob])
+        owners = np.concatenate([data[3][keep], np.zeros(plane, np.int32)])
+        coeffs = np.ones(len(slaves))
+        if exclude is not None and len(exclude):
+            ok = ~np.isin(slaves, exclude)
+            slaves, masters, owners, coeffs = slaves[ok], masters[ok], owners[ok], coeffs[ok]
+        data = (slaves.astype(np.int32), masters, coeffs, owners.astype(np.int32),
+                np.arange(len(slaves) + 1, dtype=np.int32))
+    mpc = MultiPointConstraint(V)
+    mpc.add_constraint(V, *data)
+    mpc.finalize()
+    a = fem.laplace(V)
+    f = fem.Function(V)
+    f.interpolate(f_expr)
+    L = fem.source(V, f)
+    return dict(mesh=mesh, V=V, bcs=bcs, data=data, mpc=mpc, a=a, L=L, f=f, n=n, nzc=nzc, rank=rank, world=world)
+
+
+# ------------------------------------------------------------------ pattern extension + exchange plan (setup)
+
+def _all_to_all_objects(objs, group):
+    """objs[r] goes to rank r; returns the list received (one entry per source rank)."""
+    world = dist.get_world_size(group)
+    gathered = [None] * world
+    dist.all_gather_object(gathered, objs, group=group)
+    me = dist.get_rank(group)
+    return [gathered[src][me] for src in range(world)]
+
+
+def extend_pattern(row_ptr: np.ndarray, col: np.ndarray, imap_rows: IndexMap, imap_cols: IndexMap, bs0: int, bs1: int,
+                   group=None):
+    """Merge the ghost-row patterns of all ranks into their owners' rows.
+
+    Returns ``(row_ptr, col, col_global, plan)``: the extended local CSR (ghost rows unchanged, still last),
+    the global id of every local column (owned, index-map ghosts, then pattern ghosts) and the exchange plan
+    ``{"send_idx": int64[], "send_counts": [...], "recv_pos": int64[], "recv_counts": [...]}`` -- values
+    ``val[send_idx]`` ordered by destination rank, and the positions in the owner's ``val`` where the received
+    values are added.
+    """
+    world = dist.get_world_size(group)
+    me = dist.get_rank(group)
+    n_owned_r = imap_rows.size_local * bs0
+    n_rows = len(row_ptr) - 1
+    ncols_local = (imap_cols.size_local + imap_cols.num_ghosts) * bs1
+
+    def col_l2g(c):
+        c = np.asarray(c, dtype=np.int64)
+        return imap_cols.local_to_global(c // bs1) * bs1 + c % bs1
+
+    # ghost rows -> (global row, global cols) per owner
+    ghost_rows = np.arange(n_owned_r, n_rows, dtype=np.int64)
+    g_owner = np.repeat(imap_rows.owners.astype(np.int64), bs0)
+    g_glob = np.repeat(imap_rows.ghosts.astype(np.int64), bs0) * bs0 + np.tile(np.arange(bs0), imap_rows.num_ghosts)
+    send, send_idx, send_counts = [], [], []
+    for dst in range(world):
+        rows = ghost_rows[g_owner == dst]
+        if len(rows) == 0:
+            send.append(None)
+            send_counts.append(0)
+            continue
+        lens = (row_ptr[rows + 1] - row_ptr[rows]).astype(np.int64)
+        idx = np.concatenate([np.arange(row_ptr[r], row_ptr[r + 1]) for r in rows]) if len(rows) else np.zeros(0, np.int64)
+        send.append((g_glob[rows - n_owned_r], lens, col_l2g(col[idx])))
+        send_idx.append(idx.astype(np.int64))
+        send_counts.append(int(len(idx)))
+    recv = _all_to_all_objects(send, group)
+
+    # owner side: add the received (row, col) pairs to the owned rows
+    lo_r = imap_rows.local_range[0] * bs0
+    col_global = col_l2g(np.arange(ncols_local))
+    extra_r, extra_c = [], []
+    for src in range(world):
+        if recv[src] is None:
+            continue
+        grow, lens, gcols = recv[src]
+        extra_r.append(np.repeat(grow - lo_r, lens))
+        extra_c.append(gcols)
+    recv_pos, recv_counts = np.zeros(0, np.int64), [0] * world
+    if extra_r:
+        er = np.concatenate(extra_r)
+        ec_g = np.concatenate(extra_c)
+        assert er.min() >= 0 and er.max() < n_owned_r, "received a ghost row this rank does not own"
+        # global -> local column, allocating pattern ghosts for unknown columns
+        blk = ec_g // bs1
+        loc = imap_cols.global_to_local(blk)
+        unknown = loc < 0
+        new_blocks = np.unique(blk[unknown])
+        if len(new_blocks):
+            loc[unknown] = np.searchsorted(new_blocks, blk[unknown]) + imap_cols.size_local + imap_cols.num_ghosts
+            newg = (new_blocks[:, None] * bs1 + np.arange(bs1)[None, :]).reshape(-1)
+            col_global = np.concatenate([col_global, newg])
+        ec = loc * bs1 + ec_g % bs1
+        # merge: union of the old entries of the owned rows and the received ones
+        old_r = np.repeat(np.arange(n_rows, dtype=np.int64), np.diff(row_ptr))
+        ncol_tot = len(col_global)
+        keys = np.unique(np.concatenate([old_r * ncol_tot + col.astype(np.int64), er * ncol_tot + ec]))
+        new_r, new_c = keys // ncol_tot, keys % ncol_tot
+        new_row_ptr = np.zeros(n_rows + 1, dtype=np.int64)
+        np.cumsum(np.bincount(new_r, minlength=n_rows), out=new_row_ptr[1:])
+        # positions of the received entries, per source rank in arrival order
+        recv_pos = np.searchsorted(keys, er * ncol_tot + ec).astype(np.int64)
+        recv_counts = [0 if recv[s] is None else int(recv[s][1].sum()) for s in range(world)]
+        # send indices refer to ghost rows, which moved: shift by the growth of the owned part
+        shift = new_row_ptr[n_owned_r] - row_ptr[n_owned_r]
+        send_idx = [i + shift for i in send_idx]
+        row_ptr, col = new_row_ptr, new_c.astype(np.int32)
+    plan = {"send_idx": np.concatenate(send_idx) if send_idx else np.zeros(0, np.int64),
+            "send_counts": send_counts, "recv_pos": recv_pos, "recv_counts": recv_counts}
+    return row_ptr, col, col_global, plan
+
+
+def vector_plan(imap: IndexMap, bs: int, group=None):
+    """Exchange plan of ``VecGhostUpdate(ADD, REVERSE)``: ghost entries grouped by owner, and on the owner
+    the local positions they are added to."""
+    world = dist.get_world_size(group)
+    n_owned = imap.size_local * bs
+    g_owner = np.repeat(imap.owners.astype(np.int64), bs)
+    g_glob = np.repeat(imap.ghosts.astype(np.int64), bs) * bs + np.tile(np.arange(bs), imap.num_ghosts)
+    send, send_idx, send_counts = [], [], []
+    for dst in range(world):
+        sel = np.flatnonzero(g_owner == dst)
+        send.append(g_glob[sel] if len(sel) else None)
+        send_idx.append(sel + n_owned)
+        send_counts.append(len(sel))
+    recv = _all_to_all_objects(send, group)
+    lo = imap.local_range[0] * bs
+    pos = [r - lo for r in recv if r is not None]
+    return {"send_idx": np.concatenate(send_idx).astype(np.int64), "send_counts": send_counts,
+            "recv_pos": np.concatenate(pos).astype(np.int64) if pos else np.zeros(0, np.int64),
+            "recv_counts": [0 if r is None else len(r) for r in recv]}
+
+
+# ------------------------------------------------------------------ per-step exchange (device)
+
+class GhostExchange:
+    """One ``all_to_all_single`` of packed ghost values followed by an owner-side scatter-add kernel.
+
+    ``send_idx`` / ``recv_pos`` live on the device.  When the ghost values to send are one contiguous slice of
+    the source array (single owner, the slab case) the pack kernel is skipped and the slice is sent in place.
+    """
+
+    def __init__(self, plan: dict, device, group=None):
+        self.group = group
+        self.send_counts = list(plan["send_counts"])
+        self.recv_counts = list(plan["recv_counts"])
+        si = np.asarray(plan["send_idx"], dtype=np.int64)
+        self.n_send, self.n_recv = int(si.size), int(np.asarray(plan["recv_pos"]).size)
+        self.contiguous = self.n_send > 0 and bool(np.all(np.diff(si) == 1))
+        self.send_start = int(si[0]) if self.n_send else 0
+        self.send_idx = torch.from_numpy(si).to(device)
+        self.recv_pos = torch.from_numpy(np.asarray(plan["recv_pos"], dtype=np.int64)).to(device)
+        self.send_buf = torch.empty(self.n_send, dtype=torch.float64, device=device)
+        self.recv_buf = torch.empty(self.n_recv, dtype=torch.float64, device=device)
+
+    # the two device primitives; tests on CPU substitute torch index ops for them
+    def _gather(self, src: torch.Tensor, idx: torch.Tensor, out: torch.Tensor):
+        from . import _lib, device as _dev
+
+        _lib.check(_lib.load().mpcx_gather_f64(src.data_ptr(), idx.data_ptr(), idx.numel(), out.data_ptr(),
+                                               _dev.stream_ptr()))
+
+    def _scatter_add(self, dst: torch.Tensor, idx: torch.Tensor, vals: torch.Tensor):
+        from . import _lib, device as _dev
+
+        _lib.check(_lib.load().mpcx_scatter_add_f64(dst.data_ptr(), idx.data_ptr(), idx.numel(), vals.data_ptr(),
+                                                    _dev.stream_ptr()))
+
+    def reduce(self, values: torch.Tensor):
+        if self.contiguous:
+            send = values[self.send_start:self.send_start + self.n_send]
+        else:
+            send = self.send_buf
+            if self.n_send:
+                self._gather(values, self.send_idx, send)
+        dist.all_to_all_single(self.recv_buf, send, self.recv_counts, self.send_counts, group=self.group)
+        if self.n_recv:
+            self._scatter_add(values, self.recv_pos, self.recv_buf)
+
+
+class MatVecExchange:
+    """What ``la.Matrix.assemble`` / ``la.Vector.ghostUpdate`` call."""
+
+    def __init__(self, mat_plan, vec_plan, device, group=None, cls=GhostExchange):
+        self.mat = cls(mat_plan, device, group) if mat_plan is not None else None
+        self.vec = cls(vec_plan, device, group) if vec_plan is not None else None
+
+    def reduce_matrix(self, A):
+        self.mat.reduce(A.val)
+
+    def reduce_vector(self, b):
+        self.vec.reduce(b.data)
+
+
+def create_matrix(a: fem.Form, mpc: MultiPointConstraint, group=None):
+    """Distributed counterpart of ``create_matrix``: local pattern, extended with the off-process couplings of
+    the owned rows, plus the attached ghost-row exchange."""
+    from . import device as _dev
+    from .assemble_matrix import create_sparsity_pattern
+    from .la import Matrix
+
+    row_ptr, col = create_sparsity_pattern(a, mpc)
+    V = mpc.function_space
+    row_ptr, col, col_global, plan = extend_pattern(row_ptr, col, V.index_map, V.index_map, V.bs, V.bs, group)
+    A = Matrix(row_ptr, col, (V.num_dofs, len(col_global)), (V.bs, V.bs))
+    A.col_global = col_global
+    A.ghost_exchange = MatVecExchange(plan, None, _dev.device(), group)
+    return A
+
+
+def attach_ghost_exchange(A, b, P, group=None):
+    """bench.py helper: ``A`` must come from :func:`create_matrix`; attaches the vector exchange to ``b``."""
+    from . import device as _dev
+
+    V = P["mpc"].function_space
+    b.ghost_exchange = MatVecExchange(None, vector_plan(V.index_map, V.bs, group), _dev.device(), group)

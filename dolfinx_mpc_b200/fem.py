@@ -56,6 +56,14 @@ class IndexMap:
     def num_ghosts(self) -> int:
         return len(self.ghosts)
 
+    def owner_of_local(self, local: np.ndarray) -> np.ndarray:
+        """Owning rank of local blocks (this rank for owned ones)."""
+        local = np.asarray(local, dtype=np.int64)
+        out = np.full(local.shape, self.rank, dtype=np.int32)
+        g = local >= self.size_local
+        out[g] = self.owners[local[g] - self.size_local]
+        return out
+
     def local_to_global(self, local: np.ndarray) -> np.ndarray:
         local = np.asarray(local, dtype=np.int64)
         out = local + self.local_range[0]

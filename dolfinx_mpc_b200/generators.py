@@ -172,7 +172,7 @@ def periodic_constraint(V: FunctionSpace, axes: Sequence[int] = (0,), scale: flo
         slaves, masters = slaves[keep], masters[keep]
     n = len(slaves)
     return (slaves.astype(np.int32), V.index_map.local_to_global(masters // bs) * bs + masters % bs,
-            np.full(n, scale, dtype=np.float64), np.full(n, V.index_map.rank, np.int32),
+            np.full(n, scale, dtype=np.float64), V.index_map.owner_of_local(masters // bs),
             np.arange(n + 1, dtype=np.int32))
 
 

@@ -152,6 +152,24 @@ class OracleMPC:
                     _a(self.c2s_offsets), _a(self.slaves), len(self.slaves), self.num_local_slaves)
 
 
+class WrappedMPC:
+    """Oracle view of already packed constraint arrays (e.g. a rank-local constraint whose masters were mapped
+    to the extended local numbering by the caller, cpp/MultiPointConstraint.h:117-125)."""
+
+    def __init__(self, V, is_slave, masters, coeffs, offsets, c2s, c2s_offsets, slaves, num_local_slaves):
+        self.V = V
+        self.is_slave = np.ascontiguousarray(is_slave, np.int8)
+        self.masters = np.ascontiguousarray(masters, np.int32)
+        self.coeffs = np.ascontiguousarray(coeffs, np.float64)
+        self.offsets = np.ascontiguousarray(offsets, np.int32)
+        self.c2s = np.ascontiguousarray(c2s, np.int32)
+        self.c2s_offsets = np.ascontiguousarray(c2s_offsets, np.int32)
+        self.slaves = np.ascontiguousarray(slaves, np.int32)
+        self.num_local_slaves = int(num_local_slaves)
+
+    struct = OracleMPC.struct
+
+
 def mpc_from_arrays(V, data) -> OracleMPC:
     """From ``add_constraint``-style arrays with GLOBAL masters on a serial space (global == local)."""
     slaves, masters, coeffs, owners, offsets = data

@@ -1,0 +1,127 @@
+"""World-size-2 tests (gloo, CPU) of the multi-GPU host logic: slab partition, extended index map with
+non-local masters as ghosts, pattern extension on the owner, and the ghost-row / ghost-entry exchange plan.
+
+The per-rank local assembly is done by the CPU oracle (the CUDA kernels need a GPU); the exchange runs through
+``GhostExchange`` with its two device primitives replaced by torch CPU index ops.  The owned rows of all ranks
+together must reproduce the serial assembly of the global problem (what PETSc MatAssembly / VecGhostUpdate give
+the reference, python/src/dolfinx_mpc/assemble_matrix.py:64, python/tests/test_vector_assembly.py:51).
+"""
+import os
+import sys
+
+import numpy as np
+import pytest
+import scipy.sparse as sp
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _f(x):
+    return x[0] * np.sin(5 * np.pi * x[1]) + x[2] ** 2 + 0.3
+
+
+def _worker(rank, world, port, periodic_z, n, nzc, out_dir):
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from dolfinx_mpc_b200 import create_sparsity_pattern, distributed as D
+    from oracle import oracle as orc
+
+    class CpuExchange(D.GhostExchange):
+        def _gather(self, src, idx, out):
+            out.copy_(src[idx])
+
+        def _scatter_add(self, dst, idx, vals):
+            dst.index_add_(0, idx, vals)
+
+    P = D.build_slab_problem(n, rank, world, _f, periodic_z=periodic_z, nzc=nzc)
+    mpc, V = P["mpc"], P["mpc"].function_space
+    rp, col = create_sparsity_pattern(P["a"], mpc, num_threads=2)
+    rp, col, col_global, plan = D.extend_pattern(rp, col, V.index_map, V.index_map, 1, 1)
+    m = orc.WrappedMPC(V, mpc.is_slave, mpc.masters.array, mpc.coefficients()[0], mpc.masters.offsets,
+                       mpc.cell_to_slaves.array, mpc.cell_to_slaves.offsets, mpc.slaves, mpc.num_local_slaves)
+    _, _, val = orc.assemble_matrix(P["a"], m, bcs=P["bcs"], pattern=(rp, col))
+    b = orc.assemble_vector(P["L"], m)
+    if P["bcs"]:
+        orc.apply_lifting(b, [P["a"]], [P["bcs"]], m)
+    ex = D.MatVecExchange(plan, D.vector_plan(V.index_map, 1), torch.device("cpu"), cls=CpuExchange)
+    tv, tb = torch.from_numpy(val), torch.from_numpy(b)
+    ex.mat.reduce(tv)
+    ex.vec.reduce(tb)
+    n_owned = V.index_map.size_local
+    rows = np.repeat(np.arange(len(rp) - 1), np.diff(rp))
+    own = rows < n_owned
+    lo = V.index_map.local_range[0]
+    np.savez(os.path.join(out_dir, f"rank{rank}.npz"), r=rows[own] + lo, c=col_global[col[own]], v=val[own],
+             b=b[:n_owned], lo=lo, slaves=V.index_map.local_to_global(mpc.slaves[:mpc.num_local_slaves]),
+             nghost=V.index_map.num_ghosts, ncol=len(col_global))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("periodic_z", [False, True])
+def test_two_rank_assembly_matches_serial(oracle, tmp_path, periodic_z):
+    from dolfinx_mpc_b200 import fem, generators as gen
+
+    n, nzc, world = 5, 3, 2
+    port = 29600 + (os.getpid() % 200) + (1 if periodic_z else 0)
+    mp.spawn(_worker, args=(world, port, periodic_z, n, nzc, str(tmp_path)), nprocs=world, join=True)
+
+    # serial global problem with the same lattice numbering
+    h = 1.0 / (n - 1)
+    mesh = gen.create_box(n - 1, n - 1, world * nzc, p1=(1.0, 1.0, world * nzc * h))
+    V = gen.functionspace(mesh, 1)
+    bcs, exclude = [], None
+    if not periodic_z:
+        exclude = fem.locate_dofs_geometrical(V, lambda x: np.isclose(x[2], 0) | np.isclose(x[2], world * nzc * h))
+        bcs = [fem.DirichletBC(V, exclude, 0.25)]
+    data = gen.periodic_constraint(V, axes=(0, 1, 2) if periodic_z else (0, 1), exclude_dofs=exclude)
+    m = oracle.mpc_from_arrays(V, data)
+    a = fem.laplace(V)
+    f = fem.Function(V)
+    f.interpolate(_f)
+    L = fem.source(V, f)
+    rp, col, val = oracle.assemble_matrix(a, m, bcs=bcs)
+    b = oracle.assemble_vector(L, m)
+    if bcs:
+        oracle.apply_lifting(b, [a], [bcs], m)
+    N = V.num_dofs
+    S = sp.csr_matrix((val, col, rp), shape=(N, N))
+
+    parts = [np.load(tmp_path / f"rank{r}.npz") for r in range(world)]
+    R = np.concatenate([p["r"] for p in parts])
+    Cc = np.concatenate([p["c"] for p in parts])
+    Vv = np.concatenate([p["v"] for p in parts])
+    D_ = sp.csr_matrix((Vv, (R, Cc)), shape=(N, N))
+    # same pattern (the union of the owners' rows is the serial pattern) ...
+    Dp = sp.csr_matrix((np.ones_like(Vv), (R, Cc)), shape=(N, N))
+    Sp = sp.csr_matrix((np.ones_like(val), col, rp), shape=(N, N))
+    assert (Dp != Sp).nnz == 0
+    assert len(R) == len(val), "owned rows hold duplicate or missing entries"
+    # ... and the same values / right-hand side
+    scale = np.abs(val).max()
+    assert np.abs((D_ - S)).max() <= 1e-12 * scale
+    bd = np.concatenate([p["b"] for p in parts])
+    assert np.allclose(bd, b, rtol=1e-12, atol=1e-14)
+    assert sorted(np.concatenate([p["slaves"] for p in parts])) == sorted(data[0])
+    if periodic_z:  # masters on rank 0 became extra ghosts of the last rank; rank 0 got pattern ghosts
+        assert parts[1]["nghost"] > 0 and parts[0]["ncol"] > (nzc + 1) * n * n
+
+
+def test_slab_index_map_roundtrip():
+    from dolfinx_mpc_b200 import distributed as D
+
+    n, nzc, world = 4, 2, 3
+    seen = np.zeros((world * nzc + 1) * n * n, dtype=int)
+    for r in range(world):
+        im = D.slab_index_map(n, nzc, r, world)
+        loc = np.arange(im.size_local + im.num_ghosts)
+        g = im.local_to_global(loc)
+        assert np.array_equal(im.global_to_local(g), loc)
+        seen[g[: im.size_local]] += 1
+        assert np.all(im.owner_of_local(loc[im.size_local:]) == r + 1)
+    assert np.all(seen == 1)
