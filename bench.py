@@ -233,7 +233,7 @@ def run_ours(args):
     mesh, V, mpc, a, L, bcs, f = (P[k] for k in ("mesh", "V", "mpc", "a", "L", "bcs", "f"))
     nc = mesh.num_cells_local
     f.device_array = dev.to_dev(f.array)
-    A = mpcx.create_matrix(a, mpc)
+    A = distributed.create_matrix(a, mpc) if world > 1 else mpcx.create_matrix(a, mpc)
     b = mpcx.create_vector(mpc)
     if world > 1:
         distributed.attach_ghost_exchange(A, b, P)

@@ -66,6 +66,7 @@ SYMBOLS = (
     "mpcx_add_diagonal_f64", "mpcx_build_plan", "mpcx_assemble_vector_f64", "mpcx_apply_lifting_f64",
     "mpcx_backsubstitution_f64", "mpcx_homogenize_f64", "mpcx_gather_f64", "mpcx_scatter_add_f64",
     "mpcx_create_pattern_host", "mpcx_free_host", "mpcx_profile_enable", "mpcx_launch_count", "mpcx_profile_read",
+    "mpcx_flag_cells",
 )
 
 _lib = None
@@ -97,7 +98,8 @@ def load():
     lib.mpcx_build_plan.argtypes = [P(DofmapS), P(DofmapS), vp, i64, P(CsrS), vp, i32, vp]
     lib.mpcx_assemble_vector_f64.argtypes = [P(IntegralS), P(MeshS), P(DofmapS), P(MpcS), vp, vp]
     lib.mpcx_apply_lifting_f64.argtypes = [P(IntegralS), P(MeshS), P(DofmapS), P(DofmapS), vp, vp, vp, f64,
-                                           P(MpcS), vp, vp]
+                                           P(MpcS), vp, i64, vp, vp]
+    lib.mpcx_flag_cells.argtypes = [P(DofmapS), vp, i64, vp, vp, vp]
     lib.mpcx_backsubstitution_f64.argtypes = [P(MpcS), vp, vp]
     lib.mpcx_homogenize_f64.argtypes = [P(MpcS), vp, vp]
     lib.mpcx_gather_f64.argtypes = [vp, vp, i64, vp, vp]

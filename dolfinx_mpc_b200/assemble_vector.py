@@ -7,6 +7,7 @@ from collections.abc import Sequence
 from typing import Optional
 
 import numpy as np
+import torch
 
 from . import _lib
 from . import device as _dev
@@ -75,6 +76,7 @@ def apply_lifting(b: Vector, form: Sequence[Form], bcs: Sequence[Sequence[Dirich
         if V1._dev[key] is None:
             continue
         mk, vl = V1._dev[key]
+        mkey = ("lift_markers",) + tuple(id(bc) for bc in bcs[j])
         x0_d = None
         if len(x0):
             x0_d = x0[j].data if isinstance(x0[j], Vector) else _dev.to_dev(np.asarray(x0[j], dtype=np.float64))
@@ -87,9 +89,18 @@ def apply_lifting(b: Vector, form: Sequence[Form], bcs: Sequence[Sequence[Dirich
             if it.integral_type != "cell":
                 raise RuntimeError(f"{it.integral_type} integrals have no device kernel yet")
             s = _dev.integral_struct(a, it, (constraint,), keep)
+            # cells of this integral with a Dirichlet column: found once on the device, then reused
+            if mkey not in it._dev:
+                ncells = int(s.num_cells)
+                flags = torch.zeros(ncells, dtype=torch.int8, device=_dev.device())
+                _lib.check(lib.mpcx_flag_cells(C.byref(d1), s.cells, ncells, _dev.ptr(mk), _dev.ptr(flags), st))
+                it._dev[mkey] = torch.nonzero(flags).to(torch.int32).reshape(-1)
+            lst = it._dev[mkey]
+            if lst.numel() == 0:
+                continue
             _lib.check(lib.mpcx_apply_lifting_f64(C.byref(s), C.byref(mesh_s), C.byref(d0), C.byref(d1),
                                                   _dev.ptr(mk), _dev.ptr(vl), _dev.ptr(x0_d), float(scale),
-                                                  C.byref(m0), _dev.ptr(b.data), st))
+                                                  C.byref(m0), _dev.ptr(lst), lst.numel(), _dev.ptr(b.data), st))
 
 
 def set_bc(b: Vector, bcs: Sequence[DirichletBC], x0=None, scale: float = 1.0):

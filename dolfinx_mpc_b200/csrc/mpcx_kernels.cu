@@ -393,7 +393,7 @@ __global__ void __launch_bounds__(128)
 k_lifting_generic(Tab t, IntD in, MeshD mesh, const int* __restrict__ dm0, const int* __restrict__ dm1,
                   int nd0, int nd1, int bs0, int bs1, const int8_t* __restrict__ bcm,
                   const double* __restrict__ bcv, const double* __restrict__ x0, double scale, MpcD m0,
-                  double* __restrict__ b, int smem_per_warp)
+                  const int* __restrict__ bc_cells, long long nlist, double* __restrict__ b, int smem_per_warp)
 {
   extern __shared__ double smem[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -405,8 +405,9 @@ k_lifting_generic(Tab t, IntD in, MeshD mesh, const int* __restrict__ dm0, const
   double* w = g + 3 * t.nd;
   double* gx = w + (in.cstride > 0 ? in.cstride : 1);  // scale*(g - x0) per column, 0 where no bc
   const long long wstride = (long long)gridDim.x * (blockDim.x >> 5);
-  for (long long index = (long long)blockIdx.x * (blockDim.x >> 5) + warp; index < in.ncells; index += wstride)
+  for (long long it = (long long)blockIdx.x * (blockDim.x >> 5) + warp; it < nlist; it += wstride)
   {
+    const long long index = bc_cells ? (long long)__ldg(bc_cells + it) : it;
     const int cell = in.cells ? __ldg(in.cells + index) : (int)index;
     __syncwarp();
     bool any = false;  // cpp/lifting.h:93-109
@@ -566,56 +567,6 @@ __device__ __forceinline__ void p1_geometry(const double (*X)[3], P1Geom<TD>& G)
   }
 }
 
-// Thread per cell, scalar P1 Laplace, cells without slaves only (slave cells go through
-// k_matrix_generic in mode 1).  Scatter through the precomputed plan.
-template <int TD, typename PosT>
-__global__ void __launch_bounds__(256)
-k_matrix_p1_laplace(IntD in, MeshD mesh, const int* __restrict__ dm0, const int* __restrict__ dm1,
-                    const int8_t* __restrict__ bc0, const int8_t* __restrict__ bc1,
-                    const int* __restrict__ c2s0, const int* __restrict__ c2s1, CsrD A,
-                    const PosT* __restrict__ lpos)
-{
-  constexpr int NV = TD + 1;
-  const long long index = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (index >= in.ncells) return;
-  const int cell = in.cells ? __ldg(in.cells + index) : (int)index;
-  if (__ldg(c2s0 + cell + 1) > __ldg(c2s0 + cell) || __ldg(c2s1 + cell + 1) > __ldg(c2s1 + cell)) return;
-  int xd[NV], r[NV], c[NV];
-#pragma unroll
-  for (int v = 0; v < NV; ++v)
-  {
-    xd[v] = __ldg(mesh.xd + (long long)cell * NV + v);
-    r[v] = __ldg(dm0 + (long long)cell * NV + v);
-    c[v] = __ldg(dm1 + (long long)cell * NV + v);
-  }
-  double X[NV][3];
-  load_vertices<TD>(mesh, xd, X);
-  P1Geom<TD> G;
-  p1_geometry<TD>(X, G);
-  const double s = in.c[0] * G.vol;
-  bool zr[NV], zc[NV];
-#pragma unroll
-  for (int v = 0; v < NV; ++v)
-  {
-    zr[v] = bc0 ? bc0[r[v]] : false;
-    zc[v] = bc1 ? bc1[c[v]] : false;
-  }
-  const PosT* lp = lpos + index * (NV * NV);
-#pragma unroll
-  for (int i = 0; i < NV; ++i)
-  {
-    const long long rp = __ldg(A.rp + r[i]);
-#pragma unroll
-    for (int j = 0; j < NV; ++j)
-    {
-      double d = 0.0;
-#pragma unroll
-      for (int k = 0; k < TD; ++k) d += G.g[i][k] * G.g[j][k];
-      if (!(zr[i] || zc[j])) atomicAdd(A.val + rp + lp[i * NV + j], s * d);
-    }
-  }
-}
-
 // Thread per cell, P1 source vector b_i = c0 * vol/((d+1)(d+2)) * (f_i + sum_j f_j), scalar.
 template <int TD>
 __global__ void __launch_bounds__(256)
@@ -658,6 +609,221 @@ k_vector_p1_source(IntD in, MeshD mesh, const int* __restrict__ dm, const int* _
     else
       atomicAdd(b + r[v], val);
   }
+}
+
+// Closed-form scalar P1 element matrices in registers (affine simplex): Laplace, mass, Laplace with a
+// P1 coefficient (one-point rule at the centroid, which is what the tabulated degree-1 rule evaluates).
+template <int TD>
+__device__ __forceinline__ void p1_element(int kernel, const P1Geom<TD>& G, const double* c, const double* w,
+                                           double (*Ae)[TD + 1])
+{
+  constexpr int NV = TD + 1;
+  if (kernel == MPCX_KERNEL_MASS)
+  {
+    const double s = c[0] * G.vol / double((TD + 1) * (TD + 2));
+#pragma unroll
+    for (int i = 0; i < NV; ++i)
+#pragma unroll
+      for (int j = 0; j < NV; ++j) Ae[i][j] = i == j ? 2.0 * s : s;
+    return;
+  }
+  double s = c[0] * G.vol;
+  if (kernel == MPCX_KERNEL_LAPLACE_VARCOEF)
+  {
+    double kap = 0.0;
+#pragma unroll
+    for (int v = 0; v < NV; ++v) kap += w[v];
+    s *= kap * (1.0 / NV);
+  }
+#pragma unroll
+  for (int i = 0; i < NV; ++i)
+#pragma unroll
+    for (int j = 0; j < NV; ++j)
+    {
+      double d = 0.0;
+#pragma unroll
+      for (int k = 0; k < TD; ++k) d += G.g[i][k] * G.g[j][k];
+      Ae[i][j] = s * d;
+    }
+}
+
+template <int TD>
+__device__ __forceinline__ void p1_load_w(const IntD& in, long long index, int cell, double* w)
+{
+  constexpr int NV = TD + 1;
+#pragma unroll
+  for (int v = 0; v < NV; ++v)
+    w[v] = in.coeffs ? __ldg(in.coeffs + index * in.cstride + v)
+                     : (in.wnodal ? __ldg(in.wnodal + __ldg(in.wmap + (long long)cell * NV + v)) : 0.0);
+}
+
+// Thread per cell, scalar P1 (Laplace / mass / variable-coefficient Laplace), cells without slaves only
+// (slave cells go through k_matrix_p1_mpc).  Scatter through the precomputed plan.
+template <int TD, typename PosT>
+__global__ void __launch_bounds__(256)
+k_matrix_p1_bulk(IntD in, MeshD mesh, const int* __restrict__ dm0, const int* __restrict__ dm1,
+                 const int8_t* __restrict__ bc0, const int8_t* __restrict__ bc1,
+                 const int* __restrict__ c2s0, const int* __restrict__ c2s1, CsrD A,
+                 const PosT* __restrict__ lpos)
+{
+  constexpr int NV = TD + 1;
+  const long long index = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (index >= in.ncells) return;
+  const int cell = in.cells ? __ldg(in.cells + index) : (int)index;
+  if (__ldg(c2s0 + cell + 1) > __ldg(c2s0 + cell) || __ldg(c2s1 + cell + 1) > __ldg(c2s1 + cell)) return;
+  int xd[NV], r[NV], c[NV];
+#pragma unroll
+  for (int v = 0; v < NV; ++v)
+  {
+    xd[v] = __ldg(mesh.xd + (long long)cell * NV + v);
+    r[v] = __ldg(dm0 + (long long)cell * NV + v);
+    c[v] = __ldg(dm1 + (long long)cell * NV + v);
+  }
+  double X[NV][3], w[NV], Ae[NV][NV];
+  load_vertices<TD>(mesh, xd, X);
+  P1Geom<TD> G;
+  p1_geometry<TD>(X, G);
+  p1_load_w<TD>(in, index, cell, w);
+  p1_element<TD>(in.kernel, G, in.c, w, Ae);
+  bool zr[NV], zc[NV];
+#pragma unroll
+  for (int v = 0; v < NV; ++v)
+  {
+    zr[v] = bc0 ? bc0[r[v]] : false;
+    zc[v] = bc1 ? bc1[c[v]] : false;
+  }
+  const PosT* lp = lpos + index * (NV * NV);
+#pragma unroll
+  for (int i = 0; i < NV; ++i)
+  {
+    const long long rp = __ldg(A.rp + r[i]);
+#pragma unroll
+    for (int j = 0; j < NV; ++j)
+      if (!(zr[i] || zc[j])) atomicAdd(A.val + rp + lp[i * NV + j], Ae[i][j]);
+  }
+}
+
+// Thread per slave cell, scalar P1: K^T A_e K entry-wise (cpp/assemble_matrix.cpp:99-268) with the element
+// matrix in registers; every target is located by a search of its CSR row.
+template <int TD>
+__global__ void __launch_bounds__(128)
+k_matrix_p1_mpc(IntD in, MeshD mesh, const int* __restrict__ dm0, const int* __restrict__ dm1,
+                const int8_t* __restrict__ bc0, const int8_t* __restrict__ bc1, MpcD m0, MpcD m1, CsrD A)
+{
+  constexpr int NV = TD + 1;
+  const long long it = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (it >= in.nslave_cells) return;
+  const long long index = __ldg(in.slave_cells + it);
+  const int cell = in.cells ? __ldg(in.cells + index) : (int)index;
+  int xd[NV], r[NV], c[NV];
+#pragma unroll
+  for (int v = 0; v < NV; ++v)
+  {
+    xd[v] = __ldg(mesh.xd + (long long)cell * NV + v);
+    r[v] = __ldg(dm0 + (long long)cell * NV + v);
+    c[v] = __ldg(dm1 + (long long)cell * NV + v);
+  }
+  double X[NV][3], w[NV], Ae[NV][NV];
+  load_vertices<TD>(mesh, xd, X);
+  P1Geom<TD> G;
+  p1_geometry<TD>(X, G);
+  p1_load_w<TD>(in, index, cell, w);
+  p1_element<TD>(in.kernel, G, in.c, w, Ae);
+#pragma unroll
+  for (int i = 0; i < NV; ++i)
+  {
+    if (bc0 && bc0[r[i]]) continue;
+    const bool sr = m0.is_slave[r[i]];
+    const int r0 = sr ? m0.offsets[r[i]] : 0, r1 = sr ? m0.offsets[r[i] + 1] : 1;
+#pragma unroll
+    for (int j = 0; j < NV; ++j)
+    {
+      if (bc1 && bc1[c[j]]) continue;
+      const bool sc = m1.is_slave[c[j]];
+      const int c0 = sc ? m1.offsets[c[j]] : 0, c1 = sc ? m1.offsets[c[j] + 1] : 1;
+      const double v = Ae[i][j];
+      for (int a = r0; a < r1; ++a)
+      {
+        const int tr = sr ? m0.masters[a] : r[i];
+        const double wr = sr ? m0.coeffs[a] : 1.0;
+        for (int b = c0; b < c1; ++b)
+        {
+          const int tc = sc ? m1.masters[b] : c[j];
+          const double wc = sc ? m1.coeffs[b] : 1.0;
+          csr_add(A, tr, tc, wr * wc * v);
+        }
+      }
+    }
+  }
+}
+
+// Thread per listed cell (cells with a Dirichlet column), scalar P1: b -= scale K^T A_e (g - x0)
+// (cpp/lifting.h:77-133,250-301).  A cell of the list without a bc column is skipped (:93-109).
+template <int TD>
+__global__ void __launch_bounds__(128)
+k_lifting_p1(IntD in, MeshD mesh, const int* __restrict__ dm0, const int* __restrict__ dm1,
+             const int* __restrict__ bc_cells, long long nlist, const int8_t* __restrict__ bcm,
+             const double* __restrict__ bcv, const double* __restrict__ x0, double scale, MpcD m0,
+             double* __restrict__ b)
+{
+  constexpr int NV = TD + 1;
+  const long long it = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (it >= nlist) return;
+  const long long index = bc_cells ? (long long)__ldg(bc_cells + it) : it;
+  const int cell = in.cells ? __ldg(in.cells + index) : (int)index;
+  int c[NV];
+  double gx[NV];
+  bool any = false;
+#pragma unroll
+  for (int v = 0; v < NV; ++v)
+  {
+    c[v] = __ldg(dm1 + (long long)cell * NV + v);
+    const bool isbc = bcm[c[v]];
+    gx[v] = isbc ? scale * (bcv[c[v]] - (x0 ? x0[c[v]] : 0.0)) : 0.0;
+    any |= isbc;
+  }
+  if (!any) return;
+  int xd[NV], r[NV];
+#pragma unroll
+  for (int v = 0; v < NV; ++v)
+  {
+    xd[v] = __ldg(mesh.xd + (long long)cell * NV + v);
+    r[v] = __ldg(dm0 + (long long)cell * NV + v);
+  }
+  double X[NV][3], w[NV], Ae[NV][NV];
+  load_vertices<TD>(mesh, xd, X);
+  P1Geom<TD> G;
+  p1_geometry<TD>(X, G);
+  p1_load_w<TD>(in, index, cell, w);
+  p1_element<TD>(in.kernel, G, in.c, w, Ae);
+#pragma unroll
+  for (int i = 0; i < NV; ++i)
+  {
+    double v = 0.0;
+#pragma unroll
+    for (int j = 0; j < NV; ++j) v -= Ae[i][j] * gx[j];
+    const int o0 = m0.is_slave[r[i]] ? m0.offsets[r[i]] : 0, o1 = m0.is_slave[r[i]] ? m0.offsets[r[i] + 1] : 0;
+    if (o1 > o0)
+      for (int a = o0; a < o1; ++a) atomicAdd(b + m0.masters[a], m0.coeffs[a] * v);
+    else
+      atomicAdd(b + r[i], v);
+  }
+}
+
+// flags[i] = 1 when active cell i has a dof d with marker[d] != 0 (setup of the lifting / bc cell lists)
+__global__ void k_flag_cells(const int* __restrict__ dm, int nd, int bs, const int* __restrict__ cells,
+                             long long ncells, const int8_t* __restrict__ marker, int8_t* __restrict__ flags)
+{
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= ncells) return;
+  const int cell = cells ? cells[i] : (int)i;
+  bool any = false;
+  for (int k = 0; k < nd; ++k)
+  {
+    const long long d = (long long)__ldg(dm + (long long)cell * nd + k) * bs;
+    for (int a = 0; a < bs; ++a) any |= marker[d + a] != 0;
+  }
+  flags[i] = any ? 1 : 0;
 }
 
 // ------------------------------------------------------------------ host helpers
@@ -786,10 +952,15 @@ int mpcx_assemble_matrix_f64(const mpcx_integral* integral, const mpcx_mesh* mes
   const int width = plan ? plan->width : 0;
   const int nd = t->nd, bs = t->bs, n = nd * bs;
 
-  const bool p1_simplex = t->nd == t->tdim + 1 && t->ng == t->tdim + 1 && t->nq == 1;
+  const bool p1_simplex = t->nd == t->tdim + 1 && t->ng == t->tdim + 1;
   // the bulk/elimination split needs the list of slave cells (or a constraint without slaves)
   const bool have_split = integral->slave_cells != nullptr || (mpc0->num_slaves == 0 && mpc1->num_slaves == 0);
-  const bool fast = lpos && have_split && integral->kernel == MPCX_KERNEL_LAPLACE && bs == 1 && p1_simplex;
+  const int kid = integral->kernel;
+  const bool w_ok = kid != MPCX_KERNEL_LAPLACE_VARCOEF
+                    || (in.coeffs ? in.cstride == nd : (in.wnd == nd && in.wbs == 1));
+  const bool closed_form = (kid == MPCX_KERNEL_LAPLACE || kid == MPCX_KERNEL_MASS || kid == MPCX_KERNEL_LAPLACE_VARCOEF)
+                           && bs == 1 && p1_simplex && w_ok;
+  const bool fast = lpos && have_split && closed_form;
   // generic kernel resources
   const int wcount = in.cstride > 0 ? in.cstride : 1;
   int spw = 3 * mesh->ng + n * n + 3 * nd + wcount + (2 * nd + 1) / 2 + 1;
@@ -813,34 +984,40 @@ int mpcx_assemble_matrix_f64(const mpcx_integral* integral, const mpcx_mesh* mes
   };
   if (fast)
   {
-    const long long nb = (in.ncells + 255) / 256;
-    KernelTimer kt(s);  // dominant kernel of the call
-    if (t->tdim == 3)
+    const unsigned nb = (unsigned)((in.ncells + 255) / 256);
     {
-      if (width == 1)
-        MPCX_COUNT_LAUNCH(), k_matrix_p1_laplace<3, uint8_t><<<(unsigned)nb, 256, 0, s>>>(in, md, dofmap0->map, dofmap1->map, bc0, bc1, m0.c2s_off, m1.c2s_off, Ad, (const uint8_t*)lpos);
+      KernelTimer kt(s);  // dominant kernel of the call
+      MPCX_COUNT_LAUNCH();
+      if (t->tdim == 3 && width == 1)
+        k_matrix_p1_bulk<3, uint8_t><<<nb, 256, 0, s>>>(in, md, dofmap0->map, dofmap1->map, bc0, bc1, m0.c2s_off, m1.c2s_off, Ad, (const uint8_t*)lpos);
+      else if (t->tdim == 3)
+        k_matrix_p1_bulk<3, uint16_t><<<nb, 256, 0, s>>>(in, md, dofmap0->map, dofmap1->map, bc0, bc1, m0.c2s_off, m1.c2s_off, Ad, (const uint16_t*)lpos);
+      else if (width == 1)
+        k_matrix_p1_bulk<2, uint8_t><<<nb, 256, 0, s>>>(in, md, dofmap0->map, dofmap1->map, bc0, bc1, m0.c2s_off, m1.c2s_off, Ad, (const uint8_t*)lpos);
       else
-        MPCX_COUNT_LAUNCH(), k_matrix_p1_laplace<3, uint16_t><<<(unsigned)nb, 256, 0, s>>>(in, md, dofmap0->map, dofmap1->map, bc0, bc1, m0.c2s_off, m1.c2s_off, Ad, (const uint16_t*)lpos);
+        k_matrix_p1_bulk<2, uint16_t><<<nb, 256, 0, s>>>(in, md, dofmap0->map, dofmap1->map, bc0, bc1, m0.c2s_off, m1.c2s_off, Ad, (const uint16_t*)lpos);
     }
-    else
+    if (in.nslave_cells > 0)
     {
-      if (width == 1)
-        MPCX_COUNT_LAUNCH(), k_matrix_p1_laplace<2, uint8_t><<<(unsigned)nb, 256, 0, s>>>(in, md, dofmap0->map, dofmap1->map, bc0, bc1, m0.c2s_off, m1.c2s_off, Ad, (const uint8_t*)lpos);
-      else
-        MPCX_COUNT_LAUNCH(), k_matrix_p1_laplace<2, uint16_t><<<(unsigned)nb, 256, 0, s>>>(in, md, dofmap0->map, dofmap1->map, bc0, bc1, m0.c2s_off, m1.c2s_off, Ad, (const uint16_t*)lpos);
+      const unsigned nbs = (unsigned)((in.nslave_cells + 127) / 128);
+      MPCX_COUNT_LAUNCH();
+      if (t->tdim == 3) k_matrix_p1_mpc<3><<<nbs, 128, 0, s>>>(in, md, dofmap0->map, dofmap1->map, bc0, bc1, m0, m1, Ad);
+      else k_matrix_p1_mpc<2><<<nbs, 128, 0, s>>>(in, md, dofmap0->map, dofmap1->map, bc0, bc1, m0, m1, Ad);
     }
   }
   else if (have_split && lpos)
   {
-    KernelTimer kt(s);
-    launch_generic(2, in.ncells);         // bulk cells, planned scatter
+    {
+      KernelTimer kt(s);
+      launch_generic(2, in.ncells);       // bulk cells, planned scatter
+    }
+    launch_generic(1, in.nslave_cells);   // slave cells, elimination
   }
   else
   {
     KernelTimer kt(s);
     launch_generic(0, in.ncells);
   }
-  if (have_split && lpos) launch_generic(1, in.nslave_cells);   // slave cells, elimination
   return cuda_check(cudaGetLastError(), "assemble_matrix launch");
 }
 
@@ -908,7 +1085,8 @@ int mpcx_assemble_vector_f64(const mpcx_integral* integral, const mpcx_mesh* mes
 
 int mpcx_apply_lifting_f64(const mpcx_integral* integral, const mpcx_mesh* mesh, const mpcx_dofmap* dofmap0,
                            const mpcx_dofmap* dofmap1, const int8_t* bc_markers1, const double* bc_values1,
-                           const double* x0, double scale, const mpcx_mpc* mpc0, double* b, void* stream)
+                           const double* x0, double scale, const mpcx_mpc* mpc0, const int32_t* bc_cells,
+                           int64_t num_bc_cells, double* b, void* stream)
 {
   int rc = check_integral(integral, true);
   if (rc) return rc;
@@ -916,11 +1094,29 @@ int mpcx_apply_lifting_f64(const mpcx_integral* integral, const mpcx_mesh* mesh,
   const mpcx_tables* t = integral->tables;
   if (dofmap0->nd != t->nd || dofmap1->nd != t->nd || dofmap0->bs != t->bs || dofmap1->bs != t->bs)
     return fail(MPCX_ERR_UNSUPPORTED, "test/trial dofmaps must match the tabulated element");
-  if (integral->num_cells == 0) return MPCX_OK;
+  const long long nlist = bc_cells ? num_bc_cells : integral->num_cells;
+  if (integral->num_cells == 0 || nlist <= 0) return MPCX_OK;
   const Tab tab = make_tab(t);
   IntD in = make_int(integral);
   const MeshD md{mesh->x, mesh->x_dofmap, mesh->ng, mesh->x_stride};
   const int nd = t->nd, bs = t->bs, n = nd * bs;
+  const int kid = integral->kernel;
+  const bool p1_simplex = t->nd == t->tdim + 1 && t->ng == t->tdim + 1;
+  const bool w_ok = kid != MPCX_KERNEL_LAPLACE_VARCOEF
+                    || (in.coeffs ? in.cstride == nd : (in.wnd == nd && in.wbs == 1));
+  if ((kid == MPCX_KERNEL_LAPLACE || kid == MPCX_KERNEL_MASS || kid == MPCX_KERNEL_LAPLACE_VARCOEF) && bs == 1
+      && p1_simplex && w_ok)
+  {
+    const unsigned nb = (unsigned)((nlist + 127) / 128);
+    MPCX_COUNT_LAUNCH();
+    if (t->tdim == 3)
+      k_lifting_p1<3><<<nb, 128, 0, (cudaStream_t)stream>>>(in, md, dofmap0->map, dofmap1->map, bc_cells, nlist, bc_markers1,
+                                                            bc_values1, x0, scale, make_mpc(mpc0), b);
+    else
+      k_lifting_p1<2><<<nb, 128, 0, (cudaStream_t)stream>>>(in, md, dofmap0->map, dofmap1->map, bc_cells, nlist, bc_markers1,
+                                                            bc_values1, x0, scale, make_mpc(mpc0), b);
+    return cuda_check(cudaGetLastError(), "apply_lifting launch");
+  }
   const int wcount = in.cstride > 0 ? in.cstride : 1;
   const int spw = 3 * mesh->ng + n * n + 3 * nd + wcount + n + 1;
   const size_t smem = (size_t)spw * 4 * sizeof(double);
@@ -929,9 +1125,20 @@ int mpcx_apply_lifting_f64(const mpcx_integral* integral, const mpcx_mesh* mesh,
     rc = cuda_check(cudaFuncSetAttribute(k_lifting_generic, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "smem attr");
     if (rc) return rc;
   }
-  MPCX_COUNT_LAUNCH(), k_lifting_generic<<<grid_for_warps(in.ncells, 4), 128, smem, (cudaStream_t)stream>>>(
-      tab, in, md, dofmap0->map, dofmap1->map, nd, nd, bs, bs, bc_markers1, bc_values1, x0, scale, make_mpc(mpc0), b, spw);
+  MPCX_COUNT_LAUNCH(), k_lifting_generic<<<grid_for_warps(nlist, 4), 128, smem, (cudaStream_t)stream>>>(
+      tab, in, md, dofmap0->map, dofmap1->map, nd, nd, bs, bs, bc_markers1, bc_values1, x0, scale, make_mpc(mpc0),
+      bc_cells, nlist, b, spw);
   return cuda_check(cudaGetLastError(), "apply_lifting launch");
+}
+
+int mpcx_flag_cells(const mpcx_dofmap* dofmap, const int32_t* cells, int64_t num_cells, const int8_t* marker,
+                    int8_t* flags_out, void* stream)
+{
+  if (!dofmap || !marker || !flags_out) return fail(MPCX_ERR_ARG, "null argument");
+  if (num_cells <= 0) return MPCX_OK;
+  MPCX_COUNT_LAUNCH(), k_flag_cells<<<(unsigned)((num_cells + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+      dofmap->map, dofmap->nd, dofmap->bs, cells, num_cells, marker, flags_out);
+  return cuda_check(cudaGetLastError(), "flag_cells launch");
 }
 
 int mpcx_backsubstitution_f64(const mpcx_mpc* mpc, double* u, void* stream)

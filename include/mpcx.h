@@ -184,12 +184,21 @@ int mpcx_assemble_vector_f64(const mpcx_integral* integral, const mpcx_mesh* mes
                              double* b, void* stream);
 
 /* b -= scale * K^T A_e (g - x0) on cells with a Dirichlet column.  Replaces
- * lift_bc_entities + lift_bcs_cell (cpp/lifting.h:45-134,250-301).  x0 may be NULL. */
+ * lift_bc_entities + lift_bcs_cell (cpp/lifting.h:45-134,250-301).  x0 may be NULL.
+ * bc_cells (optional): positions in the active list of the cells to visit -- normally the
+ * cells with a marked column dof, found once by mpcx_flag_cells; NULL = visit every active
+ * cell and test it, as the reference does (cpp/lifting.h:93-109). */
 int mpcx_apply_lifting_f64(const mpcx_integral* integral, const mpcx_mesh* mesh,
                            const mpcx_dofmap* dofmap0, const mpcx_dofmap* dofmap1,
                            const int8_t* bc_markers1, const double* bc_values1,
                            const double* x0, double scale, const mpcx_mpc* mpc0,
+                           const int32_t* bc_cells, int64_t num_bc_cells,
                            double* b, void* stream);
+
+/* flags_out[i] = 1 when active cell i (cells[i], or i when cells == NULL) has a dof d with
+ * marker[d] != 0.  Setup helper for the list above. */
+int mpcx_flag_cells(const mpcx_dofmap* dofmap, const int32_t* cells, int64_t num_cells,
+                    const int8_t* marker, int8_t* flags_out, void* stream);
 
 /* u[s] = sum_k coeff_k u[master_k] / u[s] = 0 for every slave.  Replaces
  * MultiPointConstraint::backsubstitution / homogenize (cpp/MultiPointConstraint.h:129-152). */
