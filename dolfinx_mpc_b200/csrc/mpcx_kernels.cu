@@ -16,6 +16,7 @@
 
 #include <atomic>
 #include <mutex>
+#include <algorithm>
 #include <vector>
 
 #include "mpcx.h"
@@ -826,6 +827,12 @@ __global__ void k_flag_cells(const int* __restrict__ dm, int nd, int bs, const i
   flags[i] = any ? 1 : 0;
 }
 
+}  // namespace
+
+#include "mpcx_tile.cuh"
+
+namespace
+{
 // ------------------------------------------------------------------ host helpers
 Tab make_tab(const mpcx_tables* t)
 {
@@ -1175,6 +1182,81 @@ int mpcx_scatter_add_f64(double* dst, const int64_t* idx, int64_t n, const doubl
   if (nb > 148LL * 32) nb = 148LL * 32;
   MPCX_COUNT_LAUNCH(), k_scatter_add<<<(unsigned)nb, 256, 0, (cudaStream_t)stream>>>(dst, (const long long*)idx, n, src);
   return cuda_check(cudaGetLastError(), "scatter_add launch");
+}
+
+
+int mpcx_tile_plan_create(const mpcx_mesh* mesh, const mpcx_dofmap* dofmap0, const mpcx_dofmap* dofmap1,
+                          const int32_t* cells, int64_t num_cells, const int8_t* skip, const int8_t* bc0,
+                          const int8_t* bc1, const mpcx_csr* A, int32_t max_tile_cells, int32_t max_tile_rows,
+                          void* stream, mpcx_tile_plan** plan_out)
+{
+  if (!mesh || !dofmap0 || !dofmap1 || !A || !plan_out) return fail(MPCX_ERR_ARG, "null argument");
+  if (num_cells < 0) return fail(MPCX_ERR_ARG, "bad sizes");
+  TilePlan* P = nullptr;
+  const int rc = tile_plan_build(mesh, dofmap0, dofmap1, cells, num_cells, skip, bc0, bc1, A, max_tile_cells,
+                                 max_tile_rows, (cudaStream_t)stream, &P);
+  *plan_out = reinterpret_cast<mpcx_tile_plan*>(P);
+  return rc;
+}
+
+void mpcx_tile_plan_destroy(mpcx_tile_plan* plan) { tile_plan_free(reinterpret_cast<TilePlan*>(plan)); }
+
+int mpcx_tile_plan_info(const mpcx_tile_plan* plan, int64_t* out, int32_t n)
+{
+  if (!plan || !out) return fail(MPCX_ERR_ARG, "null argument");
+  const TilePlan* P = reinterpret_cast<const TilePlan*>(plan);
+  const int64_t v[10] = {P->nt, P->R, P->cap, P->max_cells, P->max_nodes, P->max_dests, P->max_src, P->total_cells,
+                         P->total_src, P->bytes};
+  for (int i = 0; i < n && i < 10; ++i) out[i] = v[i];
+  return MPCX_OK;
+}
+
+int mpcx_assemble_matrix_tiled_f64(const mpcx_integral* integral, const mpcx_mesh* mesh,
+                                   const mpcx_dofmap* dofmap0, const mpcx_dofmap* dofmap1, const int8_t* bc0,
+                                   const int8_t* bc1, const mpcx_mpc* mpc0, const mpcx_mpc* mpc1,
+                                   const mpcx_csr* A, const mpcx_tile_plan* plan, int32_t accumulate, void* stream)
+{
+  int rc = check_integral(integral, true);
+  if (rc) return rc;
+  if (!mesh || !dofmap0 || !dofmap1 || !mpc0 || !mpc1 || !A || !plan) return fail(MPCX_ERR_ARG, "null argument");
+  const TilePlan* P = reinterpret_cast<const TilePlan*>(plan);
+  const mpcx_tables* t = integral->tables;
+  IntD in = make_int(integral);
+  const int nd = t->nd, bs = t->bs, kid = integral->kernel;
+  const bool p1_simplex = nd == t->tdim + 1 && t->ng == t->tdim + 1;
+  const bool w_ok = kid != MPCX_KERNEL_LAPLACE_VARCOEF || (in.coeffs ? in.cstride == nd : (in.wnd == nd && in.wbs == 1));
+  if (!((kid == MPCX_KERNEL_LAPLACE || kid == MPCX_KERNEL_MASS || kid == MPCX_KERNEL_LAPLACE_VARCOEF) && bs == 1 && p1_simplex && w_ok))
+    return fail(MPCX_ERR_UNSUPPORTED, "the tile kernel covers scalar P1 simplex Laplace / mass / variable-coefficient Laplace");
+  if (dofmap0->nd != nd || dofmap1->nd != nd || dofmap0->bs != bs || dofmap1->bs != bs || P->ne != nd * nd || P->ng != t->ng
+      || P->nrows != A->num_rows)
+    return fail(MPCX_ERR_ARG, "tile plan was built for a different element or matrix");
+  if (integral->slave_cells == nullptr && (mpc0->num_slaves > 0 || mpc1->num_slaves > 0))
+    return fail(MPCX_ERR_ARG, "the tile path needs the list of slave cells");
+  cudaStream_t s = (cudaStream_t)stream;
+  const MeshD md{mesh->x, mesh->x_dofmap, mesh->ng, mesh->x_stride};
+  const CsrD Ad{(const long long*)A->row_ptr, A->col, A->val};
+  const TilePlanD Pd{P->R, P->cap, P->max_nodes, P->tile_cell_off, P->tile_node_off, P->tile_dest_off, P->tile_src_off,
+                     P->node_ids, P->cell_pos, P->row_of_rank, P->cell_nodes, P->dest_src_end, P->dest_row, P->dest_pos, P->src};
+  const size_t smem = sizeof(double) * (size_t)(3 * P->max_nodes + P->ne * P->cap) + sizeof(uint16_t) * (size_t)(P->max_src + 8);
+  if (t->tdim == 3)
+    rc = cuda_check(cudaFuncSetAttribute(k_tile_matrix_p1<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "smem attr");
+  else
+    rc = cuda_check(cudaFuncSetAttribute(k_tile_matrix_p1<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "smem attr");
+  if (rc) return rc;
+  {
+    KernelTimer kt(s);  // dominant kernel of the call
+    MPCX_COUNT_LAUNCH();
+    if (t->tdim == 3) k_tile_matrix_p1<3><<<P->nt, MPCX_TILE_THREADS, smem, s>>>(Pd, in, md, Ad, accumulate);
+    else k_tile_matrix_p1<2><<<P->nt, MPCX_TILE_THREADS, smem, s>>>(Pd, in, md, Ad, accumulate);
+  }
+  if (in.nslave_cells > 0)
+  {
+    const unsigned nbs = (unsigned)((in.nslave_cells + 127) / 128);
+    MPCX_COUNT_LAUNCH();
+    if (t->tdim == 3) k_matrix_p1_mpc<3><<<nbs, 128, 0, s>>>(in, md, dofmap0->map, dofmap1->map, bc0, bc1, make_mpc(mpc0), make_mpc(mpc1), Ad);
+    else k_matrix_p1_mpc<2><<<nbs, 128, 0, s>>>(in, md, dofmap0->map, dofmap1->map, bc0, bc1, make_mpc(mpc0), make_mpc(mpc1), Ad);
+  }
+  return cuda_check(cudaGetLastError(), "assemble_matrix_tiled launch");
 }
 
 }  // extern "C"

@@ -10,6 +10,7 @@ SciPy / numpy on the host only for checking.
 from __future__ import annotations
 
 import ctypes as C
+import os
 from typing import Optional
 
 import numpy as np
@@ -33,6 +34,10 @@ class Matrix:
             max_block_row = int(np.diff(self.row_ptr_host).max(initial=0)) // max(1, self.bs[1])
         self.max_block_row = max_block_row
         self._plans = {}
+        self._tile_plans = {}
+        # "tile": atomic-free gather through a tile plan where a tile kernel exists, "atomic": red.global.add scatter
+        self.scatter = os.environ.get("MPCX_SCATTER", "tile")
+        self.tile_cells = int(os.environ.get("MPCX_TILE_CELLS", "0"))
         self.ghost_exchange = None  # set by distributed.attach_ghost_exchange
 
     def struct(self) -> _lib.CsrS:
@@ -63,6 +68,47 @@ class Matrix:
             _lib.check(lib.mpcx_device_error(_dev.stream_ptr()))
             self._plans[key] = (lpos, _lib.PlanS(_dev.ptr(lpos), width))
         return self._plans[key][1]
+
+    def tile_plan(self, form, integral, s_integral, bc0_d, bc1_d, key_extra=()):
+        """Tile plan (csrc/mpcx_tile.cuh) for one integral into this pattern; built on the device on first use.
+        Returns None when the element has no tile kernel."""
+        V0, V1 = form.function_spaces
+        tab = form.tables(integral)
+        p1 = V0.nd == tab.tdim + 1 and tab.ng == tab.tdim + 1 and V0.bs == 1 and V1.bs == 1 and V1.nd == V0.nd
+        if not p1 or int(integral.kernel) not in (0, 1, 4):
+            return None
+        key = (id(V0), id(V1), id(integral), _dev.ptr(bc0_d), _dev.ptr(bc1_d)) + tuple(key_extra)
+        if key not in self._tile_plans:
+            lib = _lib.load()
+            ncells = int(s_integral.num_cells)
+            skip = None
+            if s_integral.num_slave_cells > 0:
+                skip = torch.zeros(ncells, dtype=torch.int8, device=_dev.device())
+                skip[integral._dev[[k for k in integral._dev if isinstance(k, tuple) and k[0] == "slave_cells"
+                                    and k[1:] == tuple(key_extra)][0]][0].long()] = 1
+            d0 = _dev.dofmap_struct(V0, self.shape[0])
+            d1 = _dev.dofmap_struct(V1, self.shape[1])
+            mesh_s = _dev.mesh_dev(form.mesh)["struct"]
+            A = self.struct()
+            handle = C.c_void_p()
+            _lib.check(lib.mpcx_tile_plan_create(C.byref(mesh_s), C.byref(d0), C.byref(d1), s_integral.cells, ncells,
+                                                 _dev.ptr(skip), _dev.ptr(bc0_d), _dev.ptr(bc1_d), C.byref(A),
+                                                 self.tile_cells, 0, _dev.stream_ptr(), C.byref(handle)))
+            _lib.check(lib.mpcx_device_error(_dev.stream_ptr()))
+            info = (C.c_int64 * 10)()
+            lib.mpcx_tile_plan_info(handle, info, 10)
+            self._tile_plans[key] = (handle, dict(zip(("tiles", "rows_per_tile", "cap", "max_cells", "max_nodes",
+                                                       "max_dests", "max_src", "tile_cells", "sources", "bytes"),
+                                                      [int(v) for v in info])))
+        return self._tile_plans[key]
+
+    def __del__(self):
+        try:
+            lib = _lib.load()
+            for handle, _ in self._tile_plans.values():
+                lib.mpcx_tile_plan_destroy(handle)
+        except Exception:
+            pass
 
     def assemble(self):
         """Finish assembly: with several ranks, send ghost-row values to their owners and add

@@ -61,6 +61,12 @@ def test_matrix_vector_lifting_match_oracle(oracle, name):
     mpcx.assemble_matrix(c.a, mpc, bcs=c.bcs, diagval=1.0, A=A)
     assert_csr_close(*A.getValuesCSR(), rp_o, col_o, val_o)
 
+    # both scatter strategies: atomic-free tile gather (default where a tile kernel exists) and atomic scatter
+    A2 = mpcx.create_matrix(c.a, mpc)
+    A2.scatter = "atomic"
+    mpcx.assemble_matrix(c.a, mpc, bcs=c.bcs, diagval=1.0, A=A2)
+    assert_csr_close(*A2.getValuesCSR(), rp_o, col_o, val_o)
+
     # reference identity with an unconstrained oracle assembly
     e = oracle.OracleMPC.empty(c.V)
     A_org = sp.csr_matrix(oracle.assemble_matrix(c.a, e, bcs=c.bcs)[::-1], shape=(n, n))
@@ -190,3 +196,45 @@ def test_mid_size_properties(oracle):
     assert np.array_equal(S.diagonal()[mpc.slaves], np.ones(len(mpc.slaves)))
     e = oracle.OracleMPC.empty(V)
     assert abs(b.array.sum() - oracle.assemble_vector(L, e).sum()) < 1e-12
+
+
+@pytest.mark.parametrize("tile_cells", [0, 64, 2000])
+def test_tile_plan_properties(oracle, tile_cells):
+    """The tile path: every cell is evaluated at least once, the plan respects its capacity, two assemblies
+    are bit-identical (fixed summation order), and the result matches the oracle -- on a mesh whose node
+    numbering is scrambled so that tiles cannot rely on lexicographic locality."""
+    import dolfinx_mpc_b200 as mpcx
+    from dolfinx_mpc_b200 import fem, generators as gen
+
+    mesh0 = gen.create_unit_cube(12, 10, 9)
+    rng = np.random.default_rng(11)
+    perm = rng.permutation(mesh0.x.shape[0]).astype(np.int32)  # old node -> new node
+    x = np.empty_like(mesh0.x)
+    x[perm] = mesh0.x
+    cells = perm[mesh0.x_dofmap][rng.permutation(mesh0.num_cells)]
+    mesh = fem.Mesh(x, cells, "tetrahedron")
+    V = gen.functionspace(mesh, 1)
+    bc_dofs = fem.locate_dofs_geometrical(V, lambda x: np.isclose(x[2], 0))
+    bcs = [fem.DirichletBC(V, bc_dofs, 0.3)]
+    data = gen.periodic_constraint(V, axes=(0,), exclude_dofs=bc_dofs)
+    mpc = mpcx.MultiPointConstraint(V)
+    mpc.add_constraint(V, *data)
+    mpc.finalize()
+    w = fem.Function(V)
+    w.interpolate(lambda x: 1.0 + x[0] * x[1])
+    a = fem.laplace(V, 1.5) + fem.mass(V, 0.25) + fem.laplace_varcoef(V, w, 2.0)
+    A = mpcx.create_matrix(a, mpc)
+    A.tile_cells = tile_cells
+    mpcx.assemble_matrix(a, mpc, bcs=bcs, A=A)
+    v1 = A.val.clone()
+    infos = [info for _, info in A._tile_plans.values()]
+    assert len(infos) == 3
+    for info in infos:
+        assert info["tile_cells"] >= mesh.num_cells_local - len(mpc.slave_cells)
+        assert info["max_cells"] <= max(info["cap"], 1) and info["cap"] * 16 <= 65536
+        if tile_cells:
+            assert info["max_cells"] <= tile_cells or info["rows_per_tile"] == 1
+    mpcx.assemble_matrix(a, mpc, bcs=bcs, A=A)
+    assert bool((A.val == v1).all()), "tile assembly is not bit-reproducible"
+    m = oracle.mpc_from_arrays(V, data)
+    assert_csr_close(*A.getValuesCSR(), *oracle.assemble_matrix(a, m, bcs=bcs))
