@@ -100,13 +100,12 @@ def load():
     lib.mpcx_assemble_vector_f64.argtypes = [P(IntegralS), P(MeshS), P(DofmapS), P(MpcS), vp, vp]
     lib.mpcx_apply_lifting_f64.argtypes = [P(IntegralS), P(MeshS), P(DofmapS), P(DofmapS), vp, vp, vp, f64,
                                            P(MpcS), vp, i64, vp, vp]
-    lib.mpcx_tile_plan_create.argtypes = [P(MeshS), P(DofmapS), P(DofmapS), vp, i64, vp, vp, vp, P(CsrS), i32, i32, vp,
-                                          P(vp)]
+    lib.mpcx_tile_plan_create.argtypes = [P(MeshS), P(DofmapS), P(DofmapS), vp, i64, vp, vp, vp, P(CsrS), vp, P(vp)]
     lib.mpcx_tile_plan_destroy.argtypes = [vp]
     lib.mpcx_tile_plan_destroy.restype = None
     lib.mpcx_tile_plan_info.argtypes = [vp, P(i64), i32]
     lib.mpcx_assemble_matrix_tiled_f64.argtypes = [P(IntegralS), P(MeshS), P(DofmapS), P(DofmapS), vp, vp, P(MpcS),
-                                                   P(MpcS), P(CsrS), vp, i32, vp]
+                                                   P(MpcS), P(CsrS), vp, vp]
     lib.mpcx_flag_cells.argtypes = [P(DofmapS), vp, i64, vp, vp, vp]
     lib.mpcx_backsubstitution_f64.argtypes = [P(MpcS), vp, vp]
     lib.mpcx_homogenize_f64.argtypes = [P(MpcS), vp, vp]

@@ -119,28 +119,21 @@ def assemble_matrix(form: Form, constraint: Union[MultiPointConstraint, Sequence
     m1 = _dev.mpc_dev(mpc1)["struct"]
     As = A.struct()
     keep = []
-    zeroed = False  # the tile kernel of the first integral stores every value: no zero-fill pass is needed
-    for k, it in enumerate(form.integrals):
+    A.zeroEntries()
+    for it in form.integrals:
         if it.integral_type != "cell":
             raise RuntimeError(f"{it.integral_type} integrals have no device kernel yet")
         s = _dev.integral_struct(form, it, (mpc0, mpc1), keep)
         tile = A.tile_plan(form, it, s, bc0_d, bc1_d, (id(mpc0), id(mpc1))) if A.scatter == "tile" else None
         if tile is not None:
-            accumulate = 1 if (k > 0 or zeroed) else 0
             _lib.check(lib.mpcx_assemble_matrix_tiled_f64(C.byref(s), C.byref(mesh_s), C.byref(d0), C.byref(d1),
                                                           _dev.ptr(bc0_d), _dev.ptr(bc1_d), C.byref(m0), C.byref(m1),
-                                                          C.byref(As), tile[0], accumulate, st))
-            zeroed = True
+                                                          C.byref(As), tile[0], st))
             continue
-        if not zeroed:
-            A.zeroEntries()
-            zeroed = True
         plan = A.plan(form, it)
         _lib.check(lib.mpcx_assemble_matrix_f64(C.byref(s), C.byref(mesh_s), C.byref(d0), C.byref(d1),
                                                 _dev.ptr(bc0_d), _dev.ptr(bc1_d), C.byref(m0), C.byref(m1),
                                                 C.byref(As), None if plan is None else C.byref(plan), st))
-    if not zeroed:
-        A.zeroEntries()
     # slave diagonal for owned slaves when both sides share the constraint space (cpp/assemble_matrix.cpp:711-724).
     # In the reference every MultiPointConstraint owns a freshly created (extended) function space
     # (cpp/MultiPointConstraint.h:117-120), so the shared_ptr comparison holds only for one and the same object.

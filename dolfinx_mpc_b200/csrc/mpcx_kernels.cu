@@ -1187,14 +1187,12 @@ int mpcx_scatter_add_f64(double* dst, const int64_t* idx, int64_t n, const doubl
 
 int mpcx_tile_plan_create(const mpcx_mesh* mesh, const mpcx_dofmap* dofmap0, const mpcx_dofmap* dofmap1,
                           const int32_t* cells, int64_t num_cells, const int8_t* skip, const int8_t* bc0,
-                          const int8_t* bc1, const mpcx_csr* A, int32_t max_tile_cells, int32_t max_tile_rows,
-                          void* stream, mpcx_tile_plan** plan_out)
+                          const int8_t* bc1, const mpcx_csr* A, void* stream, mpcx_tile_plan** plan_out)
 {
   if (!mesh || !dofmap0 || !dofmap1 || !A || !plan_out) return fail(MPCX_ERR_ARG, "null argument");
   if (num_cells < 0) return fail(MPCX_ERR_ARG, "bad sizes");
   TilePlan* P = nullptr;
-  const int rc = tile_plan_build(mesh, dofmap0, dofmap1, cells, num_cells, skip, bc0, bc1, A, max_tile_cells,
-                                 max_tile_rows, (cudaStream_t)stream, &P);
+  const int rc = tile_plan_build(mesh, dofmap0, dofmap1, cells, num_cells, skip, bc0, bc1, A, (cudaStream_t)stream, &P);
   *plan_out = reinterpret_cast<mpcx_tile_plan*>(P);
   return rc;
 }
@@ -1205,16 +1203,15 @@ int mpcx_tile_plan_info(const mpcx_tile_plan* plan, int64_t* out, int32_t n)
 {
   if (!plan || !out) return fail(MPCX_ERR_ARG, "null argument");
   const TilePlan* P = reinterpret_cast<const TilePlan*>(plan);
-  const int64_t v[10] = {P->nt, P->R, P->cap, P->max_cells, P->max_nodes, P->max_dests, P->max_src, P->total_cells,
-                         P->total_src, P->bytes};
-  for (int i = 0; i < n && i < 10; ++i) out[i] = v[i];
+  const int64_t v[8] = {P->nt, P->C, P->n_bulk, P->max_nodes, P->max_dests, P->total_nodes, P->total_dests, P->bytes};
+  for (int i = 0; i < n && i < 8; ++i) out[i] = v[i];
   return MPCX_OK;
 }
 
 int mpcx_assemble_matrix_tiled_f64(const mpcx_integral* integral, const mpcx_mesh* mesh,
                                    const mpcx_dofmap* dofmap0, const mpcx_dofmap* dofmap1, const int8_t* bc0,
                                    const int8_t* bc1, const mpcx_mpc* mpc0, const mpcx_mpc* mpc1,
-                                   const mpcx_csr* A, const mpcx_tile_plan* plan, int32_t accumulate, void* stream)
+                                   const mpcx_csr* A, const mpcx_tile_plan* plan, void* stream)
 {
   int rc = check_integral(integral, true);
   if (rc) return rc;
@@ -1235,19 +1232,20 @@ int mpcx_assemble_matrix_tiled_f64(const mpcx_integral* integral, const mpcx_mes
   cudaStream_t s = (cudaStream_t)stream;
   const MeshD md{mesh->x, mesh->x_dofmap, mesh->ng, mesh->x_stride};
   const CsrD Ad{(const long long*)A->row_ptr, A->col, A->val};
-  const TilePlanD Pd{P->R, P->cap, P->max_nodes, P->tile_cell_off, P->tile_node_off, P->tile_dest_off, P->tile_src_off,
-                     P->node_ids, P->cell_pos, P->row_of_rank, P->cell_nodes, P->dest_src_end, P->dest_row, P->dest_pos, P->src};
-  const size_t smem = sizeof(double) * (size_t)(3 * P->max_nodes + P->ne * P->cap) + sizeof(uint16_t) * (size_t)(P->max_src + 8);
-  if (t->tdim == 3)
-    rc = cuda_check(cudaFuncSetAttribute(k_tile_matrix_p1<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "smem attr");
-  else
-    rc = cuda_check(cudaFuncSetAttribute(k_tile_matrix_p1<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "smem attr");
-  if (rc) return rc;
+  if (P->nt > 0)
   {
+    const TilePlanD Pd{P->C, P->max_nodes, P->max_dests, P->n_bulk, P->cell_pos, P->tile_node_off, P->node_ids, P->dest_k,
+                       P->tile_ns, P->tile_dest_off, P->cell_nodes, P->dest_end, P->src};
+    const size_t smem = tile_smem_bytes(P->ne, t->tdim + 1, P->C, P->max_nodes, P->max_dests);
+    if (t->tdim == 3)
+      rc = cuda_check(cudaFuncSetAttribute(k_ctile_matrix_p1<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "smem attr");
+    else
+      rc = cuda_check(cudaFuncSetAttribute(k_ctile_matrix_p1<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "smem attr");
+    if (rc) return rc;
     KernelTimer kt(s);  // dominant kernel of the call
     MPCX_COUNT_LAUNCH();
-    if (t->tdim == 3) k_tile_matrix_p1<3><<<P->nt, MPCX_TILE_THREADS, smem, s>>>(Pd, in, md, Ad, accumulate);
-    else k_tile_matrix_p1<2><<<P->nt, MPCX_TILE_THREADS, smem, s>>>(Pd, in, md, Ad, accumulate);
+    if (t->tdim == 3) k_ctile_matrix_p1<3><<<P->nt, MPCX_TILE_THREADS, smem, s>>>(Pd, in, md, Ad);
+    else k_ctile_matrix_p1<2><<<P->nt, MPCX_TILE_THREADS, smem, s>>>(Pd, in, md, Ad);
   }
   if (in.nslave_cells > 0)
   {

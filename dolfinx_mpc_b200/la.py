@@ -35,9 +35,9 @@ class Matrix:
         self.max_block_row = max_block_row
         self._plans = {}
         self._tile_plans = {}
-        # "tile": atomic-free gather through a tile plan where a tile kernel exists, "atomic": red.global.add scatter
+        # "tile": entries combined per 512-cell tile in shared memory, one reduction per (tile, entry), where a
+        # tile kernel exists; "atomic": one red.global.add per element entry
         self.scatter = os.environ.get("MPCX_SCATTER", "tile")
-        self.tile_cells = int(os.environ.get("MPCX_TILE_CELLS", "0"))
         self.ghost_exchange = None  # set by distributed.attach_ghost_exchange
 
     def struct(self) -> _lib.CsrS:
@@ -93,12 +93,12 @@ class Matrix:
             handle = C.c_void_p()
             _lib.check(lib.mpcx_tile_plan_create(C.byref(mesh_s), C.byref(d0), C.byref(d1), s_integral.cells, ncells,
                                                  _dev.ptr(skip), _dev.ptr(bc0_d), _dev.ptr(bc1_d), C.byref(A),
-                                                 self.tile_cells, 0, _dev.stream_ptr(), C.byref(handle)))
+                                                 _dev.stream_ptr(), C.byref(handle)))
             _lib.check(lib.mpcx_device_error(_dev.stream_ptr()))
-            info = (C.c_int64 * 10)()
-            lib.mpcx_tile_plan_info(handle, info, 10)
-            self._tile_plans[key] = (handle, dict(zip(("tiles", "rows_per_tile", "cap", "max_cells", "max_nodes",
-                                                       "max_dests", "max_src", "tile_cells", "sources", "bytes"),
+            info = (C.c_int64 * 8)()
+            lib.mpcx_tile_plan_info(handle, info, 8)
+            self._tile_plans[key] = (handle, dict(zip(("tiles", "cells_per_tile", "bulk_cells", "max_nodes",
+                                                       "max_dests", "tile_nodes", "dests", "bytes"),
                                                       [int(v) for v in info])))
         return self._tile_plans[key]
 

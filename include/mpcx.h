@@ -166,29 +166,29 @@ int mpcx_assemble_matrix_f64(const mpcx_integral* integral, const mpcx_mesh* mes
                              const mpcx_mpc* mpc0, const mpcx_mpc* mpc1,
                              const mpcx_csr* A, const mpcx_plan* plan, void* stream);
 
-/* Tile plan: atomic-free assembly of the cells without slave dofs (see csrc/mpcx_tile.cuh).  Built once per
- * (pattern, dofmaps, active cells, bc markers) on the device -- the role MatSetPreallocationCOO plays for PETSc's
- * device assembly.  `skip[i] != 0` excludes active cell i (cells holding slave dofs: the elimination kernel
- * handles them).  max_tile_cells / max_tile_rows <= 0 pick defaults sized for two CTAs per SM. */
+/* Tile plan for the cells without slave dofs (see csrc/mpcx_tile.cuh): cells ordered along a Morton curve, cut
+ * into tiles of 512; per tile its vertices, CSR destinations and the element entries summing into each.  Built
+ * once per (pattern, dofmaps, active cells, bc markers) on the device -- the role MatSetPreallocationCOO plays
+ * for PETSc's device assembly.  `skip[i] != 0` excludes active cell i (cells holding slave dofs: the
+ * elimination kernel handles them). */
 typedef struct mpcx_tile_plan mpcx_tile_plan;
 int mpcx_tile_plan_create(const mpcx_mesh* mesh, const mpcx_dofmap* dofmap0, const mpcx_dofmap* dofmap1,
                           const int32_t* cells, int64_t num_cells, const int8_t* skip,
-                          const int8_t* bc0, const int8_t* bc1, const mpcx_csr* A,
-                          int32_t max_tile_cells, int32_t max_tile_rows, void* stream,
+                          const int8_t* bc0, const int8_t* bc1, const mpcx_csr* A, void* stream,
                           mpcx_tile_plan** plan_out);
 void mpcx_tile_plan_destroy(mpcx_tile_plan* plan);
-/* out[0..9] = tiles, rows per tile, element-buffer stride, max cells / vertices / dests / sources per tile,
- * total tile cells (>= active cells: border cells are evaluated once per tile), total sources, plan bytes */
+/* out[0..7] = tiles, cells per tile, bulk cells, max vertices / dests per tile, total tile vertices,
+ * total dests (= red.global.add operations per assembly), plan bytes */
 int mpcx_tile_plan_info(const mpcx_tile_plan* plan, int64_t* out, int32_t n);
 
-/* Same contract as mpcx_assemble_matrix_f64, bulk cells through the tile plan.  accumulate == 0: the bulk
- * kernel STORES every CSR value of the matrix (no zeroing needed beforehand); != 0: it adds to them (second
- * and later integrals of a form).  Slave cells are eliminated afterwards and added with atomics. */
+/* Same contract as mpcx_assemble_matrix_f64 (A += integral; the caller zeroes A), bulk cells through the
+ * tile plan: element entries are combined per tile in shared memory and added with one reduction per
+ * (tile, CSR entry); slave cells are eliminated afterwards by the same kernel as in mpcx_assemble_matrix_f64. */
 int mpcx_assemble_matrix_tiled_f64(const mpcx_integral* integral, const mpcx_mesh* mesh,
                                    const mpcx_dofmap* dofmap0, const mpcx_dofmap* dofmap1,
                                    const int8_t* bc0, const int8_t* bc1,
                                    const mpcx_mpc* mpc0, const mpcx_mpc* mpc1, const mpcx_csr* A,
-                                   const mpcx_tile_plan* plan, int32_t accumulate, void* stream);
+                                   const mpcx_tile_plan* plan, void* stream);
 
 /* A[d, d] += diagval for the listed unrolled dofs.  Slave diagonal
  * (cpp/assemble_matrix.cpp:711-724) and Dirichlet diagonal
