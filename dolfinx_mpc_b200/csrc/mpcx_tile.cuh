@@ -25,6 +25,11 @@
 namespace
 {
 #define MPCX_CT_INVALID 0xffffffffu
+#define MPCX_TILE_THREADS 512
+// element-buffer stride in doubles: odd, so that the 16 entries of one cell fall into 16 different bank pairs
+// (phase 2 reads many entries of the same few cells at once)
+#define MPCX_TILE_STRIDE (MPCX_TILE_THREADS + 1)
+
 
 struct TilePlan
 {
@@ -217,7 +222,7 @@ k_ct_build(int pass, const int* __restrict__ order, long long n_bulk, const int*
     for (int e = 0; e < NEc; ++e)
     {
       keys[e] = MPCX_CT_INVALID;
-      vals[e] = (unsigned short)(e * NT + cl);
+      vals[e] = (unsigned short)(e * MPCX_TILE_STRIDE + cl);
       if (active)
       {
         const int p = e / n1, q = e - p * n1;
@@ -278,14 +283,12 @@ k_ct_build(int pass, const int* __restrict__ order, long long n_bulk, const int*
 }
 
 // ------------------------------------------------------------------ the assembly kernel
-#define MPCX_TILE_THREADS 512
-
 // Shared-memory layout of one tile (sections 16-byte aligned):
 //   Xs[max_nodes][3] f64 | ebuf[NE][C] f64 | dk[max_dests] i32 | ssrc[NE*C] u16 | cnode[C][NV] u16 | dend[max_dests] u16
 __host__ __device__ inline size_t tile_smem_bytes(int ne, int nv, int C, int max_nodes, int max_dests)
 {
   auto al = [](size_t b) { return (b + 15) & ~(size_t)15; };
-  return al(24 * (size_t)max_nodes) + al(8 * (size_t)ne * C) + al(4 * (size_t)max_dests) + al(2 * (size_t)ne * C)
+  return al(24 * (size_t)max_nodes) + al(8 * (size_t)ne * (C + 1)) + al(4 * (size_t)max_dests) + al(2 * (size_t)ne * C)
          + al(2 * (size_t)nv * C) + al(2 * (size_t)max_dests);
 }
 
@@ -298,7 +301,7 @@ k_ctile_matrix_p1(TilePlanD P, IntD in, MeshD mesh, CsrD A)
   auto al = [](size_t b) { return (b + 15) & ~(size_t)15; };
   unsigned char* sp = tile_smem;
   double* Xs = reinterpret_cast<double*>(sp); sp += al(24 * (size_t)P.max_nodes);
-  double* ebuf = reinterpret_cast<double*>(sp); sp += al(8 * (size_t)NE * NT);
+  double* ebuf = reinterpret_cast<double*>(sp); sp += al(8 * (size_t)NE * MPCX_TILE_STRIDE);
   int* dk = reinterpret_cast<int*>(sp); sp += al(4 * (size_t)P.max_dests);
   uint16_t* ssrc = reinterpret_cast<uint16_t*>(sp); sp += al(2 * (size_t)NE * NT);
   uint16_t* cnode = reinterpret_cast<uint16_t*>(sp); sp += al(2 * (size_t)NV * NT);
@@ -359,7 +362,7 @@ k_ctile_matrix_p1(TilePlanD P, IntD in, MeshD mesh, CsrD A)
 #pragma unroll
     for (int i = 0; i < NV; ++i)
 #pragma unroll
-      for (int j = 0; j < NV; ++j) ebuf[(i * NV + j) * NT + tid] = Ae[i][j];
+      for (int j = 0; j < NV; ++j) ebuf[(i * NV + j) * MPCX_TILE_STRIDE + tid] = Ae[i][j];
   }
   __syncthreads();
 

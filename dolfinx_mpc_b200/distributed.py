@@ -143,7 +143,10 @@ def extend_pattern(row_ptr: np.ndarray, col: np.ndarray, imap_rows: IndexMap, im
             send_counts.append(0)
             continue
         lens = (row_ptr[rows + 1] - row_ptr[rows]).astype(np.int64)
-        idx = np.concatenate([np.arange(row_ptr[r], row_ptr[r + 1]) for r in rows]) if len(rows) else np.zeros(0, np.int64)
+        if np.all(np.diff(rows) == 1):  # ghosts of one owner are usually one contiguous block of rows
+            idx = np.arange(row_ptr[rows[0]], row_ptr[rows[-1] + 1])
+        else:
+            idx = np.concatenate([np.arange(row_ptr[r], row_ptr[r + 1]) for r in rows])
         send.append((g_glob[rows - n_owned_r], lens, col_l2g(col[idx])))
         send_idx.append(idx.astype(np.int64))
         send_counts.append(int(len(idx)))
@@ -174,20 +177,38 @@ def extend_pattern(row_ptr: np.ndarray, col: np.ndarray, imap_rows: IndexMap, im
             newg = (new_blocks[:, None] * bs1 + np.arange(bs1)[None, :]).reshape(-1)
             col_global = np.concatenate([col_global, newg])
         ec = loc * bs1 + ec_g % bs1
-        # merge: union of the old entries of the owned rows and the received ones
-        old_r = np.repeat(np.arange(n_rows, dtype=np.int64), np.diff(row_ptr))
+        # merge, touching only the owned rows that receive something: union of their old entries and the
+        # received ones, sorted by column; every other row is copied as a block
         ncol_tot = len(col_global)
-        keys = np.unique(np.concatenate([old_r * ncol_tot + col.astype(np.int64), er * ncol_tot + ec]))
-        new_r, new_c = keys // ncol_tot, keys % ncol_tot
+        rows_a = np.unique(er)
+        old_len = np.diff(row_ptr)
+        old_idx = np.concatenate([np.arange(row_ptr[r], row_ptr[r + 1]) for r in rows_a])
+        old_keys = np.repeat(rows_a, old_len[rows_a]) * ncol_tot + col[old_idx].astype(np.int64)
+        keys = np.unique(np.concatenate([old_keys, er * ncol_tot + ec]))  # sorted by (row, col)
+        k_rows = keys // ncol_tot
+        cstart = np.searchsorted(k_rows, rows_a)  # start of every affected row inside `keys`
+        new_len = old_len.copy()
+        new_len[rows_a] = np.diff(np.append(cstart, len(keys)))
         new_row_ptr = np.zeros(n_rows + 1, dtype=np.int64)
-        np.cumsum(np.bincount(new_r, minlength=n_rows), out=new_row_ptr[1:])
+        np.cumsum(new_len, out=new_row_ptr[1:])
+        new_col = np.empty(int(new_row_ptr[-1]), dtype=np.int32)
+        prev = 0  # copy the untouched row blocks between affected rows
+        for j, r in enumerate(rows_a):
+            if r > prev:
+                new_col[new_row_ptr[prev]:new_row_ptr[r]] = col[row_ptr[prev]:row_ptr[r]]
+            e = cstart[j + 1] if j + 1 < len(rows_a) else len(keys)
+            new_col[new_row_ptr[r]:new_row_ptr[r + 1]] = (keys[cstart[j]:e] % ncol_tot).astype(np.int32)
+            prev = r + 1
+        new_col[new_row_ptr[prev]:] = col[row_ptr[prev]:]
         # positions of the received entries, per source rank in arrival order
-        recv_pos = np.searchsorted(keys, er * ncol_tot + ec).astype(np.int64)
+        kpos = np.searchsorted(keys, er * ncol_tot + ec)
+        ridx = np.searchsorted(rows_a, er)
+        recv_pos = (new_row_ptr[er] + (kpos - cstart[ridx])).astype(np.int64)
         recv_counts = [0 if recv[s] is None else int(recv[s][1].sum()) for s in range(world)]
         # send indices refer to ghost rows, which moved: shift by the growth of the owned part
         shift = new_row_ptr[n_owned_r] - row_ptr[n_owned_r]
         send_idx = [i + shift for i in send_idx]
-        row_ptr, col = new_row_ptr, new_c.astype(np.int32)
+        row_ptr, col = new_row_ptr, new_col
     plan = {"send_idx": np.concatenate(send_idx) if send_idx else np.zeros(0, np.int64),
             "send_counts": send_counts, "recv_pos": recv_pos, "recv_counts": recv_counts}
     return row_ptr, col, col_global, plan
