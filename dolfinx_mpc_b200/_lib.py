@@ -67,7 +67,7 @@ SYMBOLS = (
     "mpcx_backsubstitution_f64", "mpcx_homogenize_f64", "mpcx_gather_f64", "mpcx_scatter_add_f64",
     "mpcx_create_pattern_host", "mpcx_free_host", "mpcx_profile_enable", "mpcx_launch_count", "mpcx_profile_read",
     "mpcx_flag_cells", "mpcx_tile_plan_create", "mpcx_tile_plan_destroy", "mpcx_tile_plan_info",
-    "mpcx_assemble_matrix_tiled_f64",
+    "mpcx_assemble_matrix_tiled_f64", "mpcx_vector_tile_plan_create", "mpcx_assemble_vector_tiled_f64",
 )
 
 _lib = None
@@ -106,6 +106,8 @@ def load():
     lib.mpcx_tile_plan_info.argtypes = [vp, P(i64), i32]
     lib.mpcx_assemble_matrix_tiled_f64.argtypes = [P(IntegralS), P(MeshS), P(DofmapS), P(DofmapS), vp, vp, P(MpcS),
                                                    P(MpcS), P(CsrS), vp, vp]
+    lib.mpcx_vector_tile_plan_create.argtypes = [P(MeshS), P(DofmapS), vp, i64, vp, vp, P(vp)]
+    lib.mpcx_assemble_vector_tiled_f64.argtypes = [P(IntegralS), P(MeshS), P(DofmapS), P(MpcS), vp, vp, vp]
     lib.mpcx_flag_cells.argtypes = [P(DofmapS), vp, i64, vp, vp, vp]
     lib.mpcx_backsubstitution_f64.argtypes = [P(MpcS), vp, vp]
     lib.mpcx_homogenize_f64.argtypes = [P(MpcS), vp, vp]

@@ -39,9 +39,61 @@ def assemble_vector(form: Form, constraint: MultiPointConstraint, b: Optional[Ve
         if it.integral_type != "cell":
             raise RuntimeError(f"{it.integral_type} integrals have no device kernel yet")
         s = _dev.integral_struct(form, it, (constraint,), keep)
+        plan = _vector_tile_plan(form, it, s, constraint, mesh_s, dm)
+        if plan is not None:
+            _lib.check(lib.mpcx_assemble_vector_tiled_f64(C.byref(s), C.byref(mesh_s), C.byref(dm), C.byref(m),
+                                                          _dev.ptr(b.data), plan[0], st))
+            continue
         _lib.check(lib.mpcx_assemble_vector_f64(C.byref(s), C.byref(mesh_s), C.byref(dm), C.byref(m),
                                                 _dev.ptr(b.data), st))
     return b
+
+
+class _PlanHandle:
+    """Owns a tile plan of libmpcx (released with the object that caches it)."""
+
+    def __init__(self, handle):
+        self.handle = handle
+
+    def __del__(self):
+        try:
+            _lib.load().mpcx_tile_plan_destroy(self.handle)
+        except Exception:
+            pass
+
+
+def _vector_tile_plan(form: Form, it, s_integral, constraint, mesh_s, dm):
+    """Vector tile plan (csrc/mpcx_tile.cuh) of one integral, built on the device on first use and cached on
+    the integral; None when the element has no vector tile kernel (or MPCX_SCATTER=atomic)."""
+    import os
+
+    if os.environ.get("MPCX_SCATTER", "tile") != "tile":
+        return None
+    V = form.function_spaces[0]
+    tab = form.tables(it)
+    p1 = V.nd == tab.tdim + 1 and tab.ng == tab.tdim + 1 and V.bs == 1
+    if not p1 or int(it.kernel) != 3:
+        return None
+    if s_integral.coeff_nodal and (s_integral.coeff_nd != V.nd or s_integral.coeff_bs != 1):
+        return None
+    key = ("vector_tile_plan", id(V), id(constraint))
+    if key not in it._dev:
+        lib = _lib.load()
+        ncells = int(s_integral.num_cells)
+        skip = None
+        if s_integral.num_slave_cells > 0:
+            skip = torch.zeros(ncells, dtype=torch.int8, device=_dev.device())
+            skip[it._dev[("slave_cells", id(constraint))][0].long()] = 1
+        handle = C.c_void_p()
+        _lib.check(lib.mpcx_vector_tile_plan_create(C.byref(mesh_s), C.byref(dm), s_integral.cells, ncells,
+                                                    _dev.ptr(skip), _dev.stream_ptr(), C.byref(handle)))
+        _lib.check(lib.mpcx_device_error(_dev.stream_ptr()))
+        info = (C.c_int64 * 8)()
+        lib.mpcx_tile_plan_info(handle, info, 8)
+        it._dev[key] = (handle, _PlanHandle(handle),
+                        dict(zip(("tiles", "cells_per_tile", "bulk_cells", "max_nodes", "max_dests", "tile_nodes",
+                                  "dests", "bytes"), [int(v) for v in info])))
+    return it._dev[key]
 
 
 def apply_lifting(b: Vector, form: Sequence[Form], bcs: Sequence[Sequence[DirichletBC]],

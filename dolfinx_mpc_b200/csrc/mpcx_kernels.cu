@@ -13,6 +13,7 @@
 #include <stdint.h>
 #include <stdio.h>
 #include <string.h>
+#include <stdlib.h>
 
 #include <atomic>
 #include <mutex>
@@ -572,11 +573,13 @@ __device__ __forceinline__ void p1_geometry(const double (*X)[3], P1Geom<TD>& G)
 template <int TD>
 __global__ void __launch_bounds__(256)
 k_vector_p1_source(IntD in, MeshD mesh, const int* __restrict__ dm, const int* __restrict__ c2s,
-                   MpcD m, double* __restrict__ b)
+                   MpcD m, double* __restrict__ b, const int* __restrict__ list, long long nlist)
 {
   constexpr int NV = TD + 1;
-  const long long index = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (index >= in.ncells) return;
+  // list == nullptr: every active cell; otherwise only the listed positions (the slave cells of a tiled assembly)
+  const long long it = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (it >= (list ? nlist : in.ncells)) return;
+  const long long index = list ? (long long)__ldg(list + it) : it;
   const int cell = in.cells ? __ldg(in.cells + index) : (int)index;
   int xd[NV], r[NV];
 #pragma unroll
@@ -1077,8 +1080,8 @@ int mpcx_assemble_vector_f64(const mpcx_integral* integral, const mpcx_mesh* mes
   if (integral->kernel == MPCX_KERNEL_SOURCE && bs == 1 && p1_simplex && w_ok)
   {
     const long long nb = (in.ncells + 255) / 256;
-    if (t->tdim == 3) MPCX_COUNT_LAUNCH(), k_vector_p1_source<3><<<(unsigned)nb, 256, 0, s>>>(in, md, dofmap->map, m.c2s_off, m, b);
-    else MPCX_COUNT_LAUNCH(), k_vector_p1_source<2><<<(unsigned)nb, 256, 0, s>>>(in, md, dofmap->map, m.c2s_off, m, b);
+    if (t->tdim == 3) MPCX_COUNT_LAUNCH(), k_vector_p1_source<3><<<(unsigned)nb, 256, 0, s>>>(in, md, dofmap->map, m.c2s_off, m, b, nullptr, 0);
+    else MPCX_COUNT_LAUNCH(), k_vector_p1_source<2><<<(unsigned)nb, 256, 0, s>>>(in, md, dofmap->map, m.c2s_off, m, b, nullptr, 0);
   }
   else
   {
@@ -1235,17 +1238,17 @@ int mpcx_assemble_matrix_tiled_f64(const mpcx_integral* integral, const mpcx_mes
   if (P->nt > 0)
   {
     const TilePlanD Pd{P->C, P->max_nodes, P->max_dests, P->n_bulk, P->cell_pos, P->tile_node_off, P->node_ids, P->dest_k,
-                       P->tile_ns, P->tile_dest_off, P->cell_nodes, P->dest_end, P->src};
+                       P->tile_ns, P->tile_nd, P->tile_dest_off, P->cell_nodes, P->dest_end, P->src, P->cell_rows};
     const size_t smem = tile_smem_bytes(P->ne, t->tdim + 1, P->C, P->max_nodes, P->max_dests);
-    if (t->tdim == 3)
-      rc = cuda_check(cudaFuncSetAttribute(k_ctile_matrix_p1<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "smem attr");
-    else
-      rc = cuda_check(cudaFuncSetAttribute(k_ctile_matrix_p1<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "smem attr");
+    // plan records staged by TMA bulk copies (default) or by per-thread loads (MPCX_TILE_TMA=0, for comparison)
+    static const bool use_tma = [] { const char* e = getenv("MPCX_TILE_TMA"); return !(e && e[0] == '0'); }();
+    auto kern = t->tdim == 3 ? (use_tma ? k_ctile_matrix_p1<3, true> : k_ctile_matrix_p1<3, false>)
+                             : (use_tma ? k_ctile_matrix_p1<2, true> : k_ctile_matrix_p1<2, false>);
+    rc = cuda_check(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "smem attr");
     if (rc) return rc;
     KernelTimer kt(s);  // dominant kernel of the call
     MPCX_COUNT_LAUNCH();
-    if (t->tdim == 3) k_ctile_matrix_p1<3><<<P->nt, MPCX_TILE_THREADS, smem, s>>>(Pd, in, md, Ad);
-    else k_ctile_matrix_p1<2><<<P->nt, MPCX_TILE_THREADS, smem, s>>>(Pd, in, md, Ad);
+    kern<<<P->nt, MPCX_TILE_THREADS, smem, s>>>(Pd, in, md, Ad);
   }
   if (in.nslave_cells > 0)
   {
@@ -1255,6 +1258,61 @@ int mpcx_assemble_matrix_tiled_f64(const mpcx_integral* integral, const mpcx_mes
     else k_matrix_p1_mpc<2><<<nbs, 128, 0, s>>>(in, md, dofmap0->map, dofmap1->map, bc0, bc1, make_mpc(mpc0), make_mpc(mpc1), Ad);
   }
   return cuda_check(cudaGetLastError(), "assemble_matrix_tiled launch");
+}
+
+int mpcx_vector_tile_plan_create(const mpcx_mesh* mesh, const mpcx_dofmap* dofmap, const int32_t* cells,
+                                 int64_t num_cells, const int8_t* skip, void* stream, mpcx_tile_plan** plan_out)
+{
+  if (!mesh || !dofmap || !plan_out) return fail(MPCX_ERR_ARG, "null argument");
+  if (num_cells < 0) return fail(MPCX_ERR_ARG, "bad sizes");
+  TilePlan* P = nullptr;
+  const int rc = tile_plan_build(mesh, dofmap, dofmap, cells, num_cells, skip, nullptr, nullptr, nullptr, (cudaStream_t)stream, &P);
+  *plan_out = reinterpret_cast<mpcx_tile_plan*>(P);
+  return rc;
+}
+
+int mpcx_assemble_vector_tiled_f64(const mpcx_integral* integral, const mpcx_mesh* mesh, const mpcx_dofmap* dofmap,
+                                   const mpcx_mpc* mpc, double* b, const mpcx_tile_plan* plan, void* stream)
+{
+  int rc = check_integral(integral, false);
+  if (rc) return rc;
+  if (!mesh || !dofmap || !mpc || !b || !plan) return fail(MPCX_ERR_ARG, "null argument");
+  const TilePlan* P = reinterpret_cast<const TilePlan*>(plan);
+  const mpcx_tables* t = integral->tables;
+  IntD in = make_int(integral);
+  const int nd = t->nd, bs = t->bs;
+  const bool p1_simplex = nd == t->tdim + 1 && t->ng == t->tdim + 1;
+  const bool w_ok = in.coeffs ? in.cstride == nd : (in.wnd == nd && in.wbs == 1);
+  if (!(integral->kernel == MPCX_KERNEL_SOURCE && bs == 1 && p1_simplex && w_ok))
+    return fail(MPCX_ERR_UNSUPPORTED, "the vector tile kernel covers the scalar P1 simplex source term");
+  if (!P->vec || dofmap->nd != nd || dofmap->bs != 1 || P->ne != nd || P->ng != t->ng || P->nrows != dofmap->num_dofs)
+    return fail(MPCX_ERR_ARG, "tile plan was built for a different element or space");
+  if (integral->slave_cells == nullptr && mpc->num_slaves > 0)
+    return fail(MPCX_ERR_ARG, "the tile path needs the list of slave cells");
+  cudaStream_t s = (cudaStream_t)stream;
+  const MeshD md{mesh->x, mesh->x_dofmap, mesh->ng, mesh->x_stride};
+  const MpcD m = make_mpc(mpc);
+  if (P->nt > 0)
+  {
+    const TilePlanD Pd{P->C, P->max_nodes, P->max_dests, P->n_bulk, P->cell_pos, P->tile_node_off, P->node_ids, P->dest_k,
+                       P->tile_ns, P->tile_nd, P->tile_dest_off, P->cell_nodes, P->dest_end, P->src, P->cell_rows};
+    const size_t smem = vtile_smem_bytes(t->tdim + 1, P->C, P->max_nodes, P->max_dests);
+    // coefficient gathered through the very dofmap the plan's rows come from: stage it once per tile row
+    const int w_by_row = (!in.coeffs && in.wnodal && in.wmap == dofmap->map) ? 1 : 0;
+    auto kern = t->tdim == 3 ? k_ctile_vector_p1<3> : k_ctile_vector_p1<2>;
+    rc = cuda_check(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "smem attr");
+    if (rc) return rc;
+    MPCX_COUNT_LAUNCH();
+    kern<<<P->nt, MPCX_TILE_THREADS, smem, s>>>(Pd, in, md, w_by_row, b);
+  }
+  if (in.nslave_cells > 0)
+  {
+    const unsigned nbs = (unsigned)((in.nslave_cells + 255) / 256);
+    MPCX_COUNT_LAUNCH();
+    if (t->tdim == 3) k_vector_p1_source<3><<<nbs, 256, 0, s>>>(in, md, dofmap->map, m.c2s_off, m, b, in.slave_cells, in.nslave_cells);
+    else k_vector_p1_source<2><<<nbs, 256, 0, s>>>(in, md, dofmap->map, m.c2s_off, m, b, in.slave_cells, in.nslave_cells);
+  }
+  return cuda_check(cudaGetLastError(), "assemble_vector_tiled launch");
 }
 
 }  // extern "C"

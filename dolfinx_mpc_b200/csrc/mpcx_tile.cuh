@@ -36,18 +36,19 @@ struct TilePlan
   int nt = 0, C = 0, ne = 0, ng = 0, nd0 = 0, nd1 = 0;
   int max_nodes = 0, max_dests = 0;
   long long nrows = 0, n_bulk = 0, total_nodes = 0, total_dests = 0, total_src = 0, bytes = 0;
-  int *cell_pos = nullptr, *tile_node_off = nullptr, *node_ids = nullptr, *dest_k = nullptr, *tile_ns = nullptr;
+  int *cell_pos = nullptr, *tile_node_off = nullptr, *node_ids = nullptr, *dest_k = nullptr, *tile_ns = nullptr, *tile_nd = nullptr;
   long long* tile_dest_off = nullptr;
-  uint16_t *cell_nodes = nullptr, *dest_end = nullptr, *src = nullptr;
+  uint16_t *cell_nodes = nullptr, *dest_end = nullptr, *src = nullptr, *cell_rows = nullptr;
+  int vec = 0;  // 1: vector plan (dests = row dofs, ne = nd0)
 };
 
 struct TilePlanD  // what the kernel sees
 {
   int C, max_nodes, max_dests;
   long long n_bulk;
-  const int *cell_pos, *tile_node_off, *node_ids, *dest_k, *tile_ns;
+  const int *cell_pos, *tile_node_off, *node_ids, *dest_k, *tile_ns, *tile_nd;
   const long long* tile_dest_off;
-  const uint16_t *cell_nodes, *dest_end, *src;
+  const uint16_t *cell_nodes, *dest_end, *src, *cell_rows;
 };
 
 // ------------------------------------------------------------------ setup kernels (cold path)
@@ -146,7 +147,7 @@ k_ct_build(int pass, const int* __restrict__ order, long long n_bulk, const int*
            int* __restrict__ tile_nd, int* __restrict__ tile_ns, const int* __restrict__ tile_node_off,
            const long long* __restrict__ tile_dest_off, int* __restrict__ cell_pos, int* __restrict__ node_ids,
            uint16_t* __restrict__ cell_nodes, int* __restrict__ dest_k, uint16_t* __restrict__ dest_end,
-           uint16_t* __restrict__ src)
+           uint16_t* __restrict__ src, int extra_off, int vec, uint16_t* __restrict__ cell_rows)
 {
   using SortD = cub::BlockRadixSort<unsigned, NT, NEc, unsigned short>;
   using SortN = cub::BlockRadixSort<unsigned, NT, NGc, unsigned short>;
@@ -223,7 +224,9 @@ k_ct_build(int pass, const int* __restrict__ order, long long n_bulk, const int*
     {
       keys[e] = MPCX_CT_INVALID;
       vals[e] = (unsigned short)(e * MPCX_TILE_STRIDE + cl);
-      if (active)
+      if (active && vec)
+        keys[e] = (unsigned)dm0[(long long)cell * nd0 + e];  // vector plan (bs == 1): dest = row dof of local entry e
+      else if (active)
       {
         const int p = e / n1, q = e - p * n1;
         const int r = dm0[(long long)cell * nd0 + p / bs0] * bs0 + p % bs0;
@@ -261,23 +264,77 @@ k_ct_build(int pass, const int* __restrict__ order, long long n_bulk, const int*
     }
     else
     {
+      // Dests are emitted in order of DESCENDING source count (stable), so that the lanes of a warp of the
+      // assembly kernel's reduction phase run the same number of iterations (diagonal entries collect ~24
+      // element entries, off-diagonals 4-6: in CSR order a warp would idle for most of the longest lane's loop).
+      unsigned char* xp = ct_smem + extra_off;
+      unsigned* dkey = reinterpret_cast<unsigned*>(xp);                       // [NT*NEc]   CSR entry of dest d
+      unsigned short* dstart = reinterpret_cast<unsigned short*>(dkey + NT * NEc);  // [NT*NEc+1] first source rank of d
+      unsigned short* nst = dstart + NT * NEc + 8;                            // [NT*NEc]   first source rank after reordering
+      unsigned short* npos = nst + NT * NEc;                                  // [NT*NEc]   position of d after reordering
       const long long doff = tile_dest_off[t];
       uint16_t* s = src + first * NEc;
-      int di = hoff;
+      {
+        int di = hoff;
+#pragma unroll
+        for (int e = 0; e < NEc; ++e)
+          if (keys[e] != MPCX_CT_INVALID && head[e])
+          {
+            dkey[di] = keys[e];
+            dstart[di] = (unsigned short)(cl * NEc + e);  // valid keys sort first: rank == position among the valid sources
+            ++di;
+          }
+        if (cl == 0) dstart[total] = (unsigned short)vtotal;
+      }
+      __syncthreads();
+      unsigned ckey[NEc];
+      unsigned short cval[NEc];
 #pragma unroll
       for (int e = 0; e < NEc; ++e)
       {
-        if (keys[e] == MPCX_CT_INVALID) continue;
-        const int rank = cl * NEc + e;  // valid keys sort first, so rank == position among the valid sources
-        if (head[e])
-        {
-          dest_k[doff + di] = (int)keys[e];
-          if (di > 0) dest_end[doff + di - 1] = (uint16_t)rank;
-          ++di;
-        }
-        s[rank] = vals[e];
+        const int d = cl * NEc + e;
+        const int c = d < total ? (int)dstart[d + 1] - (int)dstart[d] : 0;
+        ckey[e] = d < total ? (unsigned)(63 - (c < 63 ? c : 63)) : 64u;
+        cval[e] = (unsigned short)d;
       }
-      if (cl == 0 && total > 0) dest_end[doff + total - 1] = (uint16_t)vtotal;
+      SortD(sortd).Sort(ckey, cval, 0, 7);  // LSD radix sort: stable, so the plan is deterministic
+      __syncthreads();
+      int cnt[NEc], csum = 0;
+#pragma unroll
+      for (int e = 0; e < NEc; ++e)
+      {
+        const int d = cval[e];
+        cnt[e] = ckey[e] != 64u ? (int)dstart[d + 1] - (int)dstart[d] : 0;
+        csum += cnt[e];
+      }
+      int coff, ctotal;
+      Scan(scan).ExclusiveSum(csum, coff, ctotal);
+      __syncthreads();
+#pragma unroll
+      for (int e = 0; e < NEc; ++e)
+      {
+        if (ckey[e] == 64u) continue;
+        const int d = cval[e], p = cl * NEc + e;
+        nst[d] = (unsigned short)coff;
+        npos[d] = (unsigned short)p;
+        coff += cnt[e];
+        dest_k[doff + p] = (int)dkey[d];
+        dest_end[doff + p] = (uint16_t)coff;
+      }
+      __syncthreads();
+      {
+        int d = hoff - 1;  // items before the thread's first head continue the previous thread's dest
+#pragma unroll
+        for (int e = 0; e < NEc; ++e)
+        {
+          if (keys[e] == MPCX_CT_INVALID) continue;
+          if (head[e]) ++d;
+          const int rank = cl * NEc + e;
+          s[(int)nst[d] + (rank - (int)dstart[d])] = vals[e];
+          if (vec)  // tile-local row of (cell, local entry): lets the kernel stage per-row data once per tile
+            cell_rows[first * NEc + (vals[e] % MPCX_TILE_STRIDE) * NEc + vals[e] / MPCX_TILE_STRIDE] = npos[d];
+        }
+      }
     }
   }
 }
@@ -289,10 +346,42 @@ __host__ __device__ inline size_t tile_smem_bytes(int ne, int nv, int C, int max
 {
   auto al = [](size_t b) { return (b + 15) & ~(size_t)15; };
   return al(24 * (size_t)max_nodes) + al(8 * (size_t)ne * (C + 1)) + al(4 * (size_t)max_dests) + al(2 * (size_t)ne * C)
-         + al(2 * (size_t)nv * C) + al(2 * (size_t)max_dests);
+         + al(2 * (size_t)nv * C) + al(2 * (size_t)max_dests) + 16;
 }
 
-template <int TD>
+// ---- 1-D TMA (cp.async.bulk global -> shared, completion on an mbarrier) for the contiguous plan records
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count)
+{
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned bytes)
+{
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_load_1d(void* dst, const void* src, unsigned bytes, unsigned long long* bar)
+{
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+               "l"(src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity)
+{
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_LOOP:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra WAIT_DONE;\n"
+      "bra WAIT_LOOP;\n"
+      "WAIT_DONE:\n"
+      "}\n" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+
+template <int TD, bool TMA>
 __global__ void __launch_bounds__(MPCX_TILE_THREADS)
 k_ctile_matrix_p1(TilePlanD P, IntD in, MeshD mesh, CsrD A)
 {
@@ -305,38 +394,69 @@ k_ctile_matrix_p1(TilePlanD P, IntD in, MeshD mesh, CsrD A)
   int* dk = reinterpret_cast<int*>(sp); sp += al(4 * (size_t)P.max_dests);
   uint16_t* ssrc = reinterpret_cast<uint16_t*>(sp); sp += al(2 * (size_t)NE * NT);
   uint16_t* cnode = reinterpret_cast<uint16_t*>(sp); sp += al(2 * (size_t)NV * NT);
-  uint16_t* dend = reinterpret_cast<uint16_t*>(sp);
+  uint16_t* dend = reinterpret_cast<uint16_t*>(sp); sp += al(2 * (size_t)P.max_dests);
+  unsigned long long* bar = reinterpret_cast<unsigned long long*>(sp);
   const int t = blockIdx.x, tid = threadIdx.x;
   const long long first = (long long)t * NT;
   const int nc_t = (int)((P.n_bulk - first) < NT ? (P.n_bulk - first) : NT);
   const int n0 = P.tile_node_off[t], nn_t = P.tile_node_off[t + 1] - n0;
-  const long long d0 = P.tile_dest_off[t];
-  const int nd_t = (int)(P.tile_dest_off[t + 1] - d0);
+  const long long d0 = P.tile_dest_off[t];  // multiple of 8: 16-byte aligned dest records
+  const int nd_t = P.tile_nd[t];
   const int ns_t = P.tile_ns[t];
 
-  // phase 0: every global read of the tile, issued as independent coalesced loads
+  // phase 0: every global read of the tile.  The contiguous plan records travel by TMA bulk copies issued by
+  // one thread; meanwhile all threads gather the vertex coordinates (the only indirect read).
+  if (TMA)
+  {
+    if (tid == 0)
+    {
+      mbar_init(bar, 1);
+      const unsigned b_src = (unsigned)(((ns_t + 7) / 8) * 16), b_cn = (unsigned)(2 * NV * NT);
+      const unsigned nd8 = (unsigned)((nd_t + 7) & ~7);
+      mbar_expect_tx(bar, b_src + b_cn + nd8 * 6);
+      if (b_src) tma_load_1d(ssrc, P.src + first * NE, b_src, bar);
+      tma_load_1d(cnode, P.cell_nodes + first * NV, b_cn, bar);
+      if (nd8)
+      {
+        tma_load_1d(dk, P.dest_k + d0, nd8 * 4, bar);
+        tma_load_1d(dend, P.dest_end + d0, nd8 * 2, bar);
+      }
+    }
+  }
   for (int i = tid; i < nn_t; i += NT)
   {
     const double* p = mesh.x + (long long)__ldg(P.node_ids + n0 + i) * mesh.xs;
-    Xs[3 * i] = __ldg(p);
-    Xs[3 * i + 1] = __ldg(p + 1);
+    if (mesh.xs == 4)
+    {
+      const double2 a = __ldg(reinterpret_cast<const double2*>(p));
+      Xs[3 * i] = a.x; Xs[3 * i + 1] = a.y;
+    }
+    else
+    {
+      Xs[3 * i] = __ldg(p);
+      Xs[3 * i + 1] = __ldg(p + 1);
+    }
     Xs[3 * i + 2] = __ldg(p + 2);
   }
+  if (!TMA)
   {
-    const uint4* g = reinterpret_cast<const uint4*>(P.src + first * NE);
-    uint4* s = reinterpret_cast<uint4*>(ssrc);
-    for (int i = tid; i < (ns_t + 7) / 8; i += NT) s[i] = __ldg(g + i);
+    {
+      const uint4* g = reinterpret_cast<const uint4*>(P.src + first * NE);
+      uint4* s = reinterpret_cast<uint4*>(ssrc);
+      for (int i = tid; i < (ns_t + 7) / 8; i += NT) s[i] = __ldg(g + i);
+    }
+    for (int k = tid; k < nd_t; k += NT)
+    {
+      dk[k] = __ldg(P.dest_k + d0 + k);
+      dend[k] = __ldg(P.dest_end + d0 + k);
+    }
+    if (NV == 4)
+      reinterpret_cast<uint2*>(cnode)[tid] = __ldg(reinterpret_cast<const uint2*>(P.cell_nodes) + first + tid);
+    else
+      for (int i = tid; i < NT * NV; i += NT) cnode[i] = __ldg(P.cell_nodes + first * NV + i);
   }
-  for (int k = tid; k < nd_t; k += NT)
-  {
-    dk[k] = __ldg(P.dest_k + d0 + k);
-    dend[k] = __ldg(P.dest_end + d0 + k);
-  }
-  if (NV == 4)
-    reinterpret_cast<uint2*>(cnode)[tid] = __ldg(reinterpret_cast<const uint2*>(P.cell_nodes) + first + tid);
-  else
-    for (int i = tid; i < NT * NV; i += NT) cnode[i] = __ldg(P.cell_nodes + first * NV + i);
-  __syncthreads();
+  __syncthreads();  // Xs complete; the mbarrier initialisation is visible to every thread
+  if (TMA) mbar_wait(bar, 0);
 
   // phase 1: thread = cell; element matrix -> element buffer, entry-major (conflict-free stores)
   if (tid < nc_t)
@@ -382,6 +502,129 @@ k_ctile_matrix_p1(TilePlanD P, IntD in, MeshD mesh, CsrD A)
   }
 }
 
+// ------------------------------------------------------------------ vector tile kernel (P1 source term)
+// Same three phases for the load vector b_i = c0 |K|/((d+1)(d+2)) (f_i + sum_j f_j)
+// (cpp/assemble_vector.cpp:163-185 with the P1 source kernel): 4 element entries per cell, dests = the row dofs
+// of the tile, one red.global.add.f64 per (tile, row) instead of one per (cell, vertex).  When the coefficient
+// lives in the same space as the test function its values are staged once per tile row.
+//   Xs[max_nodes][3] f64 | ebuf[NV][C+1] f64 | fs[max_dests] f64 | dk[max_dests] i32 | ssrc[NV*C] u16 |
+//   cnode[C][NV] u16 | crow[C][NV] u16 | dend[max_dests] u16 | mbarrier
+__host__ __device__ inline size_t vtile_smem_bytes(int nv, int C, int max_nodes, int max_dests)
+{
+  auto al = [](size_t b) { return (b + 15) & ~(size_t)15; };
+  return al(24 * (size_t)max_nodes) + al(8 * (size_t)nv * (C + 1)) + al(8 * (size_t)max_dests) + al(4 * (size_t)max_dests)
+         + 3 * al(2 * (size_t)nv * C) + al(2 * (size_t)max_dests) + 16;
+}
+
+template <int TD>
+__global__ void __launch_bounds__(MPCX_TILE_THREADS)
+k_ctile_vector_p1(TilePlanD P, IntD in, MeshD mesh, int w_by_row, double* __restrict__ b)
+{
+  constexpr int NV = TD + 1, NT = MPCX_TILE_THREADS;
+  extern __shared__ __align__(16) unsigned char tile_smem[];
+  auto al = [](size_t b_) { return (b_ + 15) & ~(size_t)15; };
+  unsigned char* sp = tile_smem;
+  double* Xs = reinterpret_cast<double*>(sp); sp += al(24 * (size_t)P.max_nodes);
+  double* ebuf = reinterpret_cast<double*>(sp); sp += al(8 * (size_t)NV * MPCX_TILE_STRIDE);
+  double* fs = reinterpret_cast<double*>(sp); sp += al(8 * (size_t)P.max_dests);
+  int* dk = reinterpret_cast<int*>(sp); sp += al(4 * (size_t)P.max_dests);
+  uint16_t* ssrc = reinterpret_cast<uint16_t*>(sp); sp += al(2 * (size_t)NV * NT);
+  uint16_t* cnode = reinterpret_cast<uint16_t*>(sp); sp += al(2 * (size_t)NV * NT);
+  uint16_t* crow = reinterpret_cast<uint16_t*>(sp); sp += al(2 * (size_t)NV * NT);
+  uint16_t* dend = reinterpret_cast<uint16_t*>(sp); sp += al(2 * (size_t)P.max_dests);
+  unsigned long long* bar = reinterpret_cast<unsigned long long*>(sp);
+  const int t = blockIdx.x, tid = threadIdx.x;
+  const long long first = (long long)t * NT;
+  const int nc_t = (int)((P.n_bulk - first) < NT ? (P.n_bulk - first) : NT);
+  const int n0 = P.tile_node_off[t], nn_t = P.tile_node_off[t + 1] - n0;
+  const long long d0 = P.tile_dest_off[t];
+  const int nd_t = P.tile_nd[t];
+  const int ns_t = P.tile_ns[t];
+
+  if (tid == 0)
+  {
+    mbar_init(bar, 1);
+    const unsigned b_src = (unsigned)(((ns_t + 7) / 8) * 16), b_cn = (unsigned)(2 * NV * NT);
+    const unsigned nd8 = (unsigned)((nd_t + 7) & ~7);
+    mbar_expect_tx(bar, b_src + 2 * b_cn + nd8 * 6);
+    if (b_src) tma_load_1d(ssrc, P.src + first * NV, b_src, bar);
+    tma_load_1d(cnode, P.cell_nodes + first * NV, b_cn, bar);
+    tma_load_1d(crow, P.cell_rows + first * NV, b_cn, bar);
+    if (nd8)
+    {
+      tma_load_1d(dk, P.dest_k + d0, nd8 * 4, bar);
+      tma_load_1d(dend, P.dest_end + d0, nd8 * 2, bar);
+    }
+  }
+  for (int i = tid; i < nn_t; i += NT)
+  {
+    const double* p = mesh.x + (long long)__ldg(P.node_ids + n0 + i) * mesh.xs;
+    if (mesh.xs == 4)
+    {
+      const double2 a = __ldg(reinterpret_cast<const double2*>(p));
+      Xs[3 * i] = a.x; Xs[3 * i + 1] = a.y;
+    }
+    else
+    {
+      Xs[3 * i] = __ldg(p);
+      Xs[3 * i + 1] = __ldg(p + 1);
+    }
+    Xs[3 * i + 2] = __ldg(p + 2);
+  }
+  if (w_by_row)  // coefficient in the test space: one read per tile row (straight from the plan, no wait on the TMA)
+    for (int k = tid; k < nd_t; k += NT) fs[k] = __ldg(in.wnodal + __ldg(P.dest_k + d0 + k));
+  __syncthreads();
+  mbar_wait(bar, 0);
+
+  // phase 1: thread = cell
+  if (tid < nc_t)
+  {
+    double X[NV][3];
+#pragma unroll
+    for (int v = 0; v < NV; ++v)
+    {
+      const int l = cnode[tid * NV + v];
+      X[v][0] = Xs[3 * l];
+      X[v][1] = Xs[3 * l + 1];
+      X[v][2] = TD == 3 ? Xs[3 * l + 2] : 0.0;
+    }
+    P1Geom<TD> G;
+    p1_geometry<TD>(X, G);
+    double f[NV], fsum = 0.0;
+    if (w_by_row)
+    {
+#pragma unroll
+      for (int v = 0; v < NV; ++v) f[v] = fs[crow[tid * NV + v]];
+    }
+    else
+    {
+      const long long index = __ldg(P.cell_pos + first + tid);
+      p1_load_w<TD>(in, index, in.cells ? __ldg(in.cells + index) : (int)index, f);
+    }
+#pragma unroll
+    for (int v = 0; v < NV; ++v) fsum += f[v];
+    const double s = in.c[0] * G.vol / double((TD + 1) * (TD + 2));
+#pragma unroll
+    for (int v = 0; v < NV; ++v) ebuf[v * MPCX_TILE_STRIDE + tid] = s * (f[v] + fsum);
+  }
+  __syncthreads();
+
+  // phase 2: thread = row of the tile
+  for (int k = tid; k < nd_t; k += NT)
+  {
+    const int beg = k ? dend[k - 1] : 0, end = dend[k];
+    double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+    int p = beg;
+    for (; p + 4 <= end; p += 4)
+    {
+      const int a = ssrc[p], bb = ssrc[p + 1], c = ssrc[p + 2], d = ssrc[p + 3];
+      s0 += ebuf[a]; s1 += ebuf[bb]; s2 += ebuf[c]; s3 += ebuf[d];
+    }
+    for (; p < end; ++p) s0 += ebuf[ssrc[p]];
+    atomicAdd(b + dk[k], (s0 + s1) + (s2 + s3));
+  }
+}
+
 // ------------------------------------------------------------------ host side of the setup
 #define TP_CK(call)                                                      \
   do {                                                                   \
@@ -398,8 +641,8 @@ cudaError_t tp_alloc(T** p, long long n)
 void tile_plan_free(TilePlan* P)
 {
   if (!P) return;
-  cudaFree(P->cell_pos); cudaFree(P->tile_node_off); cudaFree(P->node_ids); cudaFree(P->dest_k); cudaFree(P->tile_ns);
-  cudaFree(P->tile_dest_off); cudaFree(P->cell_nodes); cudaFree(P->dest_end); cudaFree(P->src);
+  cudaFree(P->cell_pos); cudaFree(P->tile_node_off); cudaFree(P->node_ids); cudaFree(P->dest_k); cudaFree(P->tile_ns); cudaFree(P->tile_nd);
+  cudaFree(P->tile_dest_off); cudaFree(P->cell_nodes); cudaFree(P->dest_end); cudaFree(P->src); cudaFree(P->cell_rows);
   delete P;
 }
 
@@ -415,15 +658,18 @@ cudaError_t ct_build_launch(int pass, int nt, cudaStream_t s, const int* order, 
   size_t smem = sizeof(typename cub::BlockRadixSort<unsigned, NT, NEc, unsigned short>::TempStorage);
   smem = std::max(smem, sizeof(typename cub::BlockRadixSort<unsigned, NT, NGc, unsigned short>::TempStorage));
   smem = std::max(smem, sizeof(typename cub::BlockDiscontinuity<unsigned, NT>::TempStorage));
-  smem = std::max(smem, sizeof(typename cub::BlockScan<int, NT>::TempStorage)) + 16;
+  smem = (std::max(smem, sizeof(typename cub::BlockScan<int, NT>::TempStorage)) + 15) & ~(size_t)15;
+  const int extra_off = (int)smem;
+  smem += (size_t)NT * NEc * 4 + 3 * ((size_t)NT * NEc + 8) * 2 + 16;  // dkey, dstart, nst, npos of the count ordering
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
   kern<<<nt, NT, smem, s>>>(pass, order, n_bulk, cells, md, dm0->map, dm1->map, dm0->nd, dm1->nd, dm0->bs, dm1->bs, bc0, bc1, A,
                             tile_nn, tile_nd, P->tile_ns, P->tile_node_off, P->tile_dest_off, P->cell_pos, P->node_ids,
-                            P->cell_nodes, P->dest_k, P->dest_end, P->src);
+                            P->cell_nodes, P->dest_k, P->dest_end, P->src, extra_off, P->vec, P->cell_rows);
   return cudaGetLastError();
 }
 
+// Acsr == nullptr builds a VECTOR plan: dests are the row dofs of dm0 (bs == 1), ne = nd0 entries per cell.
 int tile_plan_build(const mpcx_mesh* mesh, const mpcx_dofmap* dm0, const mpcx_dofmap* dm1, const int32_t* cells,
                     long long nc, const int8_t* skip, const int8_t* bc0, const int8_t* bc1, const mpcx_csr* Acsr,
                     cudaStream_t s, TilePlan** out)
@@ -431,17 +677,20 @@ int tile_plan_build(const mpcx_mesh* mesh, const mpcx_dofmap* dm0, const mpcx_do
   int rc = MPCX_OK;
   TilePlan* P = new TilePlan();
   const MeshD md{mesh->x, mesh->x_dofmap, mesh->ng, mesh->x_stride};
-  const CsrD A{(const long long*)Acsr->row_ptr, Acsr->col, Acsr->val};
+  const bool vec = Acsr == nullptr;
+  const CsrD A{vec ? nullptr : (const long long*)Acsr->row_ptr, vec ? nullptr : Acsr->col, vec ? nullptr : Acsr->val};
   constexpr int C = MPCX_TILE_THREADS;
-  P->C = C; P->nd0 = dm0->nd; P->nd1 = dm1->nd; P->ng = mesh->ng; P->nrows = Acsr->num_rows;
-  P->ne = dm0->nd * dm0->bs * dm1->nd * dm1->bs;
+  P->vec = vec ? 1 : 0;
+  P->C = C; P->nd0 = dm0->nd; P->nd1 = dm1->nd; P->ng = mesh->ng; P->nrows = vec ? dm0->num_dofs : Acsr->num_rows;
+  P->ne = vec ? dm0->nd : dm0->nd * dm0->bs * dm1->nd * dm1->bs;
   unsigned long long *mm = nullptr, *code = nullptr, *code2 = nullptr;
-  int *iota = nullptr, *order = nullptr, *tile_nn = nullptr, *tile_nd = nullptr;
+  int *iota = nullptr, *order = nullptr, *tile_nn = nullptr;
   long long* nb_dev = nullptr;
   void* tmp = nullptr;
   size_t tmp_bytes = 0, tb = 0;
   std::vector<int> h_nn, h_nd, noff;
   std::vector<long long> h_doff;
+  long long n_dests = 0, alloc_dests = 0;
   BBox bb;
   int variant = 0;
   auto need_tmp = [&](size_t bytes) -> cudaError_t {
@@ -452,14 +701,18 @@ int tile_plan_build(const mpcx_mesh* mesh, const mpcx_dofmap* dm0, const mpcx_do
     return cudaMalloc(&tmp, tmp_bytes);
   };
   auto build = [&](int pass) -> cudaError_t {
-    if (variant == 16) return ct_build_launch<16, 4>(pass, P->nt, s, order, P->n_bulk, cells, md, dm0, dm1, bc0, bc1, A, tile_nn, tile_nd, P);
-    return ct_build_launch<9, 3>(pass, P->nt, s, order, P->n_bulk, cells, md, dm0, dm1, bc0, bc1, A, tile_nn, tile_nd, P);
+    if (variant == 4) return ct_build_launch<4, 4>(pass, P->nt, s, order, P->n_bulk, cells, md, dm0, dm1, bc0, bc1, A, tile_nn, P->tile_nd, P);
+    if (variant == 3) return ct_build_launch<3, 3>(pass, P->nt, s, order, P->n_bulk, cells, md, dm0, dm1, bc0, bc1, A, tile_nn, P->tile_nd, P);
+    if (variant == 16) return ct_build_launch<16, 4>(pass, P->nt, s, order, P->n_bulk, cells, md, dm0, dm1, bc0, bc1, A, tile_nn, P->tile_nd, P);
+    return ct_build_launch<9, 3>(pass, P->nt, s, order, P->n_bulk, cells, md, dm0, dm1, bc0, bc1, A, tile_nn, P->tile_nd, P);
   };
 
-  if (P->ne == 16 && mesh->ng == 4) variant = 16;
-  else if (P->ne == 9 && mesh->ng == 3) variant = 9;
-  else { rc = fail(MPCX_ERR_UNSUPPORTED, "tile plan: only 3x3 / 4x4 element matrices (scalar P1 simplices) so far"); goto done; }
-  if (Acsr->nnz >= (1ll << 31) - 1 || nc >= (1ll << 31)) { rc = fail(MPCX_ERR_UNSUPPORTED, "tile plan: nnz or cells >= 2^31 on one device"); goto done; }
+  if (vec && dm0->bs == 1 && P->ne == 4 && mesh->ng == 4) variant = 4;
+  else if (vec && dm0->bs == 1 && P->ne == 3 && mesh->ng == 3) variant = 3;
+  else if (!vec && P->ne == 16 && mesh->ng == 4) variant = 16;
+  else if (!vec && P->ne == 9 && mesh->ng == 3) variant = 9;
+  else { rc = fail(MPCX_ERR_UNSUPPORTED, "tile plan: only scalar P1 simplices (3x3 / 4x4 element matrices, 3 / 4 element vectors) so far"); goto done; }
+  if ((!vec && Acsr->nnz >= (1ll << 31) - 1) || nc >= (1ll << 31)) { rc = fail(MPCX_ERR_UNSUPPORTED, "tile plan: nnz or cells >= 2^31 on one device"); goto done; }
 
   // 1. bounding box -> Morton quantisation
   {
@@ -491,41 +744,52 @@ int tile_plan_build(const mpcx_mesh* mesh, const mpcx_dofmap* dm0, const mpcx_do
   if (P->nt == 0) goto done;  // nothing but slave cells: an empty plan is valid
 
   // 3. pass 0: sizes of every tile
-  TP_CK(tp_alloc(&tile_nn, P->nt)); TP_CK(tp_alloc(&tile_nd, P->nt)); TP_CK(tp_alloc(&P->tile_ns, P->nt));
+  TP_CK(tp_alloc(&tile_nn, P->nt)); TP_CK(tp_alloc(&P->tile_nd, P->nt)); TP_CK(tp_alloc(&P->tile_ns, P->nt));
   TP_CK(build(0));
   h_nn.resize(P->nt); h_nd.resize(P->nt);
   TP_CK(cudaMemcpyAsync(h_nn.data(), tile_nn, sizeof(int) * P->nt, cudaMemcpyDeviceToHost, s));
-  TP_CK(cudaMemcpyAsync(h_nd.data(), tile_nd, sizeof(int) * P->nt, cudaMemcpyDeviceToHost, s));
+  TP_CK(cudaMemcpyAsync(h_nd.data(), P->tile_nd, sizeof(int) * P->nt, cudaMemcpyDeviceToHost, s));
   TP_CK(cudaStreamSynchronize(s));
   noff.assign(P->nt + 1, 0);
   h_doff.assign(P->nt + 1, 0);
   for (int t = 0; t < P->nt; ++t)
   {
     noff[t + 1] = noff[t] + h_nn[t];
-    h_doff[t + 1] = h_doff[t] + h_nd[t];
+    h_doff[t + 1] = h_doff[t] + ((h_nd[t] + 7) & ~7);  // 16-byte aligned records for the TMA bulk copies
+    n_dests += h_nd[t];
     P->max_nodes = std::max(P->max_nodes, h_nn[t]);
     P->max_dests = std::max(P->max_dests, h_nd[t]);
   }
   P->total_nodes = noff[P->nt];
-  P->total_dests = h_doff[P->nt];
+  P->total_dests = n_dests;
+  alloc_dests = h_doff[P->nt] + 8;
   P->total_src = (long long)P->nt * C * P->ne;
   P->max_nodes = (P->max_nodes + 1) & ~1;
+  P->max_dests = (P->max_dests + 7) & ~7;  // the TMA copies move whole groups of 8 dest records
   TP_CK(tp_alloc(&P->tile_node_off, P->nt + 1)); TP_CK(tp_alloc(&P->tile_dest_off, P->nt + 1));
   TP_CK(cudaMemcpyAsync(P->tile_node_off, noff.data(), sizeof(int) * (P->nt + 1), cudaMemcpyHostToDevice, s));
   TP_CK(cudaMemcpyAsync(P->tile_dest_off, h_doff.data(), sizeof(long long) * (P->nt + 1), cudaMemcpyHostToDevice, s));
   TP_CK(cudaStreamSynchronize(s));
   // 4. pass 1: the records
   TP_CK(tp_alloc(&P->cell_pos, (long long)P->nt * C)); TP_CK(tp_alloc(&P->node_ids, P->total_nodes));
-  TP_CK(tp_alloc(&P->cell_nodes, (long long)P->nt * C * P->ng)); TP_CK(tp_alloc(&P->dest_k, P->total_dests));
-  TP_CK(tp_alloc(&P->dest_end, P->total_dests)); TP_CK(tp_alloc(&P->src, P->total_src + 8));
+  TP_CK(tp_alloc(&P->cell_nodes, (long long)P->nt * C * P->ng)); TP_CK(tp_alloc(&P->dest_k, alloc_dests));
+  TP_CK(tp_alloc(&P->dest_end, alloc_dests)); TP_CK(tp_alloc(&P->src, P->total_src + 8));
   TP_CK(cudaMemsetAsync(P->cell_nodes, 0, sizeof(uint16_t) * (size_t)P->nt * C * P->ng, s));
+  TP_CK(cudaMemsetAsync(P->dest_k, 0, sizeof(int) * (size_t)alloc_dests, s));
+  TP_CK(cudaMemsetAsync(P->dest_end, 0, sizeof(uint16_t) * (size_t)alloc_dests, s));
+  if (vec)
+  {
+    TP_CK(tp_alloc(&P->cell_rows, (long long)P->nt * C * P->ne));
+    TP_CK(cudaMemsetAsync(P->cell_rows, 0, sizeof(uint16_t) * (size_t)P->nt * C * P->ne, s));
+  }
   TP_CK(build(1));
   TP_CK(cudaStreamSynchronize(s));
   P->bytes = (long long)sizeof(uint16_t) * (P->total_src + (long long)P->nt * C * P->ng + P->total_dests)
-             + (long long)sizeof(int) * (P->total_nodes + P->total_dests + (long long)P->nt * C) + (long long)(P->nt + 1) * 16;
+             + (long long)sizeof(int) * (P->total_nodes + P->total_dests + (long long)P->nt * C) + (long long)(P->nt + 1) * 16
+             + (vec ? (long long)sizeof(uint16_t) * P->nt * C * P->ne : 0);
 
 done:
-  cudaFree(mm); cudaFree(code); cudaFree(code2); cudaFree(iota); cudaFree(order); cudaFree(tile_nn); cudaFree(tile_nd);
+  cudaFree(mm); cudaFree(code); cudaFree(code2); cudaFree(iota); cudaFree(order); cudaFree(tile_nn);
   cudaFree(nb_dev); cudaFree(tmp);
   if (rc != MPCX_OK) { tile_plan_free(P); P = nullptr; }
   *out = P;

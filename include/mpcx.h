@@ -190,6 +190,15 @@ int mpcx_assemble_matrix_tiled_f64(const mpcx_integral* integral, const mpcx_mes
                                    const mpcx_mpc* mpc0, const mpcx_mpc* mpc1, const mpcx_csr* A,
                                    const mpcx_tile_plan* plan, void* stream);
 
+/* Tile plan for the load vector (same tiling; dests are the row dofs, built once per (dofmap, active cells,
+ * skip flags)) and the tiled counterpart of mpcx_assemble_vector_f64: element entries of the constraint-free
+ * cells are combined per tile, one reduction per (tile, row); cells holding slaves (integral->slave_cells) go
+ * through the elimination path of mpcx_assemble_vector_f64 (cpp/assemble_vector.h:35-69).  b is NOT zeroed. */
+int mpcx_vector_tile_plan_create(const mpcx_mesh* mesh, const mpcx_dofmap* dofmap, const int32_t* cells,
+                                 int64_t num_cells, const int8_t* skip, void* stream, mpcx_tile_plan** plan_out);
+int mpcx_assemble_vector_tiled_f64(const mpcx_integral* integral, const mpcx_mesh* mesh, const mpcx_dofmap* dofmap,
+                                   const mpcx_mpc* mpc, double* b, const mpcx_tile_plan* plan, void* stream);
+
 /* A[d, d] += diagval for the listed unrolled dofs.  Slave diagonal
  * (cpp/assemble_matrix.cpp:711-724) and Dirichlet diagonal
  * (python/src/dolfinx_mpc/assemble_matrix.py:59-62). */

@@ -232,3 +232,12 @@ def test_tile_plan_properties(oracle):
         assert info["dests"] < 8 * nbulk  # 16 entries per cell before the per-tile combination
     m = oracle.mpc_from_arrays(V, data)
     assert_csr_close(*A.getValuesCSR(), *oracle.assemble_matrix(a, m, bcs=bcs))
+    # load vector through the vector tile plan (one reduction per (tile, row)), twice into the same vector
+    L = fem.source(V, w, 0.7)
+    b = mpcx.assemble_vector(L, mpc)
+    plans = [v for k, v in L.integrals[0]._dev.items() if isinstance(k, tuple) and k[0] == "vector_tile_plan"]
+    assert len(plans) == 1 and plans[0][2]["bulk_cells"] == nbulk and plans[0][2]["dests"] < 2 * nbulk
+    b_o = oracle.assemble_vector(L, m)
+    assert_vec_close(b.array, b_o)
+    mpcx.assemble_vector(L, mpc, b=b)
+    assert_vec_close(b.array, b_o)

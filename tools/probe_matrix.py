@@ -31,6 +31,16 @@ for _ in range(args.reps):
 ms, n = C.c_double(0), C.c_longlong(0)
 lib.mpcx_profile_read(C.byref(ms), C.byref(n))
 nc = P["mesh"].num_cells_local
+b = mpcx.create_vector(P["mpc"])
+for _ in range(2):
+    mpcx.assemble_vector(P["L"], P["mpc"], b=b)
+e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+e0.record()
+for _ in range(args.reps):
+    mpcx.assemble_vector(P["L"], P["mpc"], b=b)
+e1.record()
+torch.cuda.synchronize()
+print(f"assemble_vector (zero + kernels): {e0.elapsed_time(e1) / args.reps:.3f} ms")
 info = [i for _, i in A._tile_plans.values()]
 print(f"n={args.n} scatter={args.scatter} cells={nc} bulk kernel {ms.value / n.value:.3f} ms "
       f"-> {nc / (ms.value / n.value * 1e-3) / 1e9:.2f} Gcells/s  plan={info}")
