@@ -88,11 +88,11 @@ def _vector_tile_plan(form: Form, it, s_integral, constraint, mesh_s, dm):
         _lib.check(lib.mpcx_vector_tile_plan_create(C.byref(mesh_s), C.byref(dm), s_integral.cells, ncells,
                                                     _dev.ptr(skip), _dev.stream_ptr(), C.byref(handle)))
         _lib.check(lib.mpcx_device_error(_dev.stream_ptr()))
-        info = (C.c_int64 * 8)()
-        lib.mpcx_tile_plan_info(handle, info, 8)
+        info = (C.c_int64 * 10)()
+        lib.mpcx_tile_plan_info(handle, info, 10)
         it._dev[key] = (handle, _PlanHandle(handle),
                         dict(zip(("tiles", "cells_per_tile", "bulk_cells", "max_nodes", "max_dests", "tile_nodes",
-                                  "dests", "bytes"), [int(v) for v in info])))
+                                  "dests", "bytes", "max_slots", "slots"), [int(v) for v in info])))
     return it._dev[key]
 
 

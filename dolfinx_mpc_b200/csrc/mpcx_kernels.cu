@@ -600,7 +600,7 @@ k_vector_p1_source(IntD in, MeshD mesh, const int* __restrict__ dm, const int* _
                      : __ldg(in.wnodal + __ldg(in.wmap + (long long)cell * NV + v));
     fs += f[v];
   }
-  const double s = in.c[0] * G.vol / double((TD + 1) * (TD + 2));
+  const double s = in.c[0] * G.vol * (1.0 / double((TD + 1) * (TD + 2)));
   const bool has_slaves = __ldg(c2s + cell + 1) > __ldg(c2s + cell);
 #pragma unroll
   for (int v = 0; v < NV; ++v)
@@ -624,7 +624,7 @@ __device__ __forceinline__ void p1_element(int kernel, const P1Geom<TD>& G, cons
   constexpr int NV = TD + 1;
   if (kernel == MPCX_KERNEL_MASS)
   {
-    const double s = c[0] * G.vol / double((TD + 1) * (TD + 2));
+    const double s = c[0] * G.vol * (1.0 / double((TD + 1) * (TD + 2)));
 #pragma unroll
     for (int i = 0; i < NV; ++i)
 #pragma unroll
@@ -1206,8 +1206,9 @@ int mpcx_tile_plan_info(const mpcx_tile_plan* plan, int64_t* out, int32_t n)
 {
   if (!plan || !out) return fail(MPCX_ERR_ARG, "null argument");
   const TilePlan* P = reinterpret_cast<const TilePlan*>(plan);
-  const int64_t v[8] = {P->nt, P->C, P->n_bulk, P->max_nodes, P->max_dests, P->total_nodes, P->total_dests, P->bytes};
-  for (int i = 0; i < n && i < 8; ++i) out[i] = v[i];
+  const int64_t v[10] = {P->nt, P->C, P->n_bulk, P->max_nodes, P->max_dests, P->total_nodes, P->total_dests, P->bytes,
+                         P->max_slots, P->total_slots};
+  for (int i = 0; i < n && i < 10; ++i) out[i] = v[i];
   return MPCX_OK;
 }
 
@@ -1237,13 +1238,9 @@ int mpcx_assemble_matrix_tiled_f64(const mpcx_integral* integral, const mpcx_mes
   const CsrD Ad{(const long long*)A->row_ptr, A->col, A->val};
   if (P->nt > 0)
   {
-    const TilePlanD Pd{P->C, P->max_nodes, P->max_dests, P->n_bulk, P->cell_pos, P->tile_node_off, P->node_ids, P->dest_k,
-                       P->tile_ns, P->tile_nd, P->tile_dest_off, P->cell_nodes, P->dest_end, P->src, P->cell_rows};
-    const size_t smem = tile_smem_bytes(P->ne, t->tdim + 1, P->C, P->max_nodes, P->max_dests);
-    // plan records staged by TMA bulk copies (default) or by per-thread loads (MPCX_TILE_TMA=0, for comparison)
-    static const bool use_tma = [] { const char* e = getenv("MPCX_TILE_TMA"); return !(e && e[0] == '0'); }();
-    auto kern = t->tdim == 3 ? (use_tma ? k_ctile_matrix_p1<3, true> : k_ctile_matrix_p1<3, false>)
-                             : (use_tma ? k_ctile_matrix_p1<2, true> : k_ctile_matrix_p1<2, false>);
+    const TilePlanD Pd = tile_plan_view(P);
+    const size_t smem = tile_smem_bytes(P->max_nodes, P->max_dests, P->max_slots, false);
+    auto kern = t->tdim == 3 ? k_ctile_matrix_p1<3> : k_ctile_matrix_p1<2>;
     rc = cuda_check(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "smem attr");
     if (rc) return rc;
     KernelTimer kt(s);  // dominant kernel of the call
@@ -1294,9 +1291,8 @@ int mpcx_assemble_vector_tiled_f64(const mpcx_integral* integral, const mpcx_mes
   const MpcD m = make_mpc(mpc);
   if (P->nt > 0)
   {
-    const TilePlanD Pd{P->C, P->max_nodes, P->max_dests, P->n_bulk, P->cell_pos, P->tile_node_off, P->node_ids, P->dest_k,
-                       P->tile_ns, P->tile_nd, P->tile_dest_off, P->cell_nodes, P->dest_end, P->src, P->cell_rows};
-    const size_t smem = vtile_smem_bytes(t->tdim + 1, P->C, P->max_nodes, P->max_dests);
+    const TilePlanD Pd = tile_plan_view(P);
+    const size_t smem = tile_smem_bytes(P->max_nodes, P->max_dests, P->max_slots, true);
     // coefficient gathered through the very dofmap the plan's rows come from: stage it once per tile row
     const int w_by_row = (!in.coeffs && in.wnodal && in.wmap == dofmap->map) ? 1 : 0;
     auto kern = t->tdim == 3 ? k_ctile_vector_p1<3> : k_ctile_vector_p1<2>;

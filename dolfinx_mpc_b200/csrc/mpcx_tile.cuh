@@ -8,47 +8,57 @@
 //
 //   setup (once per pattern / dofmap / bc set, mpcx_tile_plan_create, all on the device):
 //     the cells are ordered along a Morton curve through the mesh and cut into tiles of C consecutive cells;
-//     for every tile the plan holds its distinct vertices, the tile-local vertex ids of its cells, its
-//     distinct CSR entries ("dests") and, per dest, the element-matrix entries ("sources") summing into it;
+//     for every tile the plan holds its distinct vertices, the tile-local vertex ids of its cells and its
+//     distinct CSR entries ("dests"), ordered by descending number of contributing element entries
+//     ("sources") and cut into groups of 32 (one per lane of a warp).  Every source owns one slot of the
+//     tile's element buffer: slot = base(group) + 32 * i + lane for the i-th source of the dest held by `lane`;
 //   assembly (k_ctile_matrix_p1, one CTA of C threads per tile):
-//     phase 0  every global read of the tile (vertex coordinates, plan records) as independent coalesced loads
-//              into shared memory -- vertex coordinates are fetched once per tile, not once per cell,
-//     phase 1  thread = cell: closed-form element matrix -> shared element buffer (conflict-free stores),
-//     phase 2  thread = dest: sums its sources from the buffer, ONE red.global.add.f64 per (tile, dest).
+//     phase 0  one thread issues TMA bulk copies (cp.async.bulk + mbarrier) of the tile's dest records into
+//              shared memory; every thread prefetches its cell's record and the tile's vertex coordinates
+//              are gathered once per tile, not once per cell,
+//     phase 1  thread = cell: closed-form element matrix, each entry stored to its slot,
+//     phase 2  thread = dest: sums its column of the group's [count][32] slot block -- stride-32 reads,
+//              conflict-free, same trip count on every lane -- then ONE red.global.add.f64 per (tile, dest).
 //   A P1 tetrahedron mesh has about 4 distinct dests per cell in a 512-cell tile instead of 16 entries per
 //   cell, so the RED traffic drops 4x, and the gathers of x[x_dofmap] / row_ptr disappear from the hot loop.
+//   (profiles/r01_d -> r01_e: ordering the dests by count and slotting the buffer removed the divergent,
+//   bank-conflicted gather that made phase 2 two thirds of the instructions.)
 //
 // Cells holding slave dofs are excluded (the `skip` flags) and handled by the elimination kernel.
+// The load vector uses the same machinery with 4 entries per cell and dests = row dofs (k_ctile_vector_p1).
 #pragma once
 #include <cub/cub.cuh>
 
 namespace
 {
 #define MPCX_CT_INVALID 0xffffffffu
+#define MPCX_CT_NOSLOT 0xffffu
 #define MPCX_TILE_THREADS 512
-// element-buffer stride in doubles: odd, so that the 16 entries of one cell fall into 16 different bank pairs
-// (phase 2 reads many entries of the same few cells at once)
-#define MPCX_TILE_STRIDE (MPCX_TILE_THREADS + 1)
-
+// slot of the i-th source of the dest held by lane l of a group: base + 33 i + l.  The odd stride spreads the
+// sources of one dest (written by neighbouring cells at the same time) over the banks; lanes still read consecutive slots.
+#define MPCX_CT_GSTRIDE 33
 
 struct TilePlan
 {
   int nt = 0, C = 0, ne = 0, ng = 0, nd0 = 0, nd1 = 0;
-  int max_nodes = 0, max_dests = 0;
-  long long nrows = 0, n_bulk = 0, total_nodes = 0, total_dests = 0, total_src = 0, bytes = 0;
-  int *cell_pos = nullptr, *tile_node_off = nullptr, *node_ids = nullptr, *dest_k = nullptr, *tile_ns = nullptr, *tile_nd = nullptr;
+  int max_nodes = 0, max_dests = 0, max_slots = 0;
+  long long nrows = 0, n_bulk = 0, total_nodes = 0, total_dests = 0, total_slots = 0, bytes = 0;
+  int *cell_pos = nullptr, *tile_node_off = nullptr, *node_ids = nullptr, *dest_k = nullptr, *tile_nd = nullptr,
+      *tile_slots = nullptr;
+  unsigned* ginfo = nullptr;
   long long* tile_dest_off = nullptr;
-  uint16_t *cell_nodes = nullptr, *dest_end = nullptr, *src = nullptr, *cell_rows = nullptr;
+  uint16_t *cell_nodes = nullptr, *dest_cnt = nullptr, *cell_slot = nullptr, *cell_rows = nullptr;
   int vec = 0;  // 1: vector plan (dests = row dofs, ne = nd0)
 };
 
 struct TilePlanD  // what the kernel sees
 {
-  int C, max_nodes, max_dests;
+  int C, max_nodes, max_dests, max_slots;
   long long n_bulk;
-  const int *cell_pos, *tile_node_off, *node_ids, *dest_k, *tile_ns, *tile_nd;
+  const int *cell_pos, *tile_node_off, *node_ids, *dest_k, *tile_nd;
+  const unsigned* ginfo;
   const long long* tile_dest_off;
-  const uint16_t *cell_nodes, *dest_end, *src, *cell_rows;
+  const uint16_t *cell_nodes, *dest_cnt, *cell_slot, *cell_rows;
 };
 
 // ------------------------------------------------------------------ setup kernels (cold path)
@@ -137,27 +147,34 @@ __global__ void k_tp_count_bulk(const unsigned long long* __restrict__ sorted_co
   *n_bulk = lo;
 }
 
-// One CTA per tile, thread = cell.  pass 0 counts the distinct vertices / dests / valid sources of the tile,
-// pass 1 (after the host scanned the counts) writes the plan records.
+// One CTA per tile, thread = cell.  pass 0 sizes the tile (distinct vertices, dests, element-buffer slots),
+// pass 1 (after the host scanned the sizes) writes the plan records.
 template <int NT, int NEc, int NGc>
 __global__ void __launch_bounds__(NT)
 k_ct_build(int pass, const int* __restrict__ order, long long n_bulk, const int* __restrict__ cells, MeshD mesh,
            const int* __restrict__ dm0, const int* __restrict__ dm1, int nd0, int nd1, int bs0, int bs1,
-           const int8_t* __restrict__ bc0, const int8_t* __restrict__ bc1, CsrD A, int* __restrict__ tile_nn,
-           int* __restrict__ tile_nd, int* __restrict__ tile_ns, const int* __restrict__ tile_node_off,
-           const long long* __restrict__ tile_dest_off, int* __restrict__ cell_pos, int* __restrict__ node_ids,
-           uint16_t* __restrict__ cell_nodes, int* __restrict__ dest_k, uint16_t* __restrict__ dest_end,
-           uint16_t* __restrict__ src, int extra_off, int vec, uint16_t* __restrict__ cell_rows)
+           const int8_t* __restrict__ bc0, const int8_t* __restrict__ bc1, CsrD A, int vec, int extra_off,
+           int* __restrict__ tile_nn, int* __restrict__ tile_nd, int* __restrict__ tile_slots,
+           const int* __restrict__ tile_node_off, const long long* __restrict__ tile_dest_off,
+           int* __restrict__ cell_pos, int* __restrict__ node_ids, uint16_t* __restrict__ cell_nodes,
+           int* __restrict__ dest_k, uint16_t* __restrict__ dest_cnt, unsigned* __restrict__ ginfo,
+           uint16_t* __restrict__ cell_slot, uint16_t* __restrict__ cell_rows)
 {
   using SortD = cub::BlockRadixSort<unsigned, NT, NEc, unsigned short>;
   using SortN = cub::BlockRadixSort<unsigned, NT, NGc, unsigned short>;
   using DiscD = cub::BlockDiscontinuity<unsigned, NT>;
   using Scan = cub::BlockScan<int, NT>;
+  constexpr int N = NT * NEc;  // most sources (and dests) a tile can have
   extern __shared__ __align__(16) unsigned char ct_smem[];
   auto& sortd = *reinterpret_cast<typename SortD::TempStorage*>(ct_smem);
   auto& sortn = *reinterpret_cast<typename SortN::TempStorage*>(ct_smem);
   auto& disc = *reinterpret_cast<typename DiscD::TempStorage*>(ct_smem);
   auto& scan = *reinterpret_cast<typename Scan::TempStorage*>(ct_smem);
+  unsigned* dkey = reinterpret_cast<unsigned*>(ct_smem + extra_off);  // [N]     key (CSR entry / row dof) of dest d
+  int* gbase = reinterpret_cast<int*>(dkey + N);                      // [N/32+1] first slot of dest group g
+  unsigned short* dstart = reinterpret_cast<unsigned short*>(gbase + N / 32 + 1);  // [N+8]  first source rank of d
+  unsigned short* npos = dstart + N + 8;                               // [N]     position of d in count order
+  unsigned short* pcnt = npos + N;                                     // [N+32]  source count at position p
   const int t = blockIdx.x, cl = threadIdx.x;
   const long long first = (long long)t * NT;
   const int nc_t = (int)((n_bulk - first) < NT ? (n_bulk - first) : NT);
@@ -215,138 +232,149 @@ k_ct_build(int pass, const int* __restrict__ order, long long n_bulk, const int*
   __syncthreads();
 
   // ---- dests and sources
+  unsigned keys[NEc];
+  unsigned short vals[NEc];
+  const int n1 = nd1 * bs1;
+#pragma unroll
+  for (int e = 0; e < NEc; ++e)
   {
-    unsigned keys[NEc];
-    unsigned short vals[NEc];
-    const int n1 = nd1 * bs1;
+    keys[e] = MPCX_CT_INVALID;
+    vals[e] = (unsigned short)(cl * NEc + e);  // (cell of the tile, local entry)
+    if (active && vec)
+      keys[e] = (unsigned)dm0[(long long)cell * nd0 + e];  // vector plan (bs == 1): dest = row dof of local entry e
+    else if (active)
+    {
+      const int p = e / n1, q = e - p * n1;
+      const int r = dm0[(long long)cell * nd0 + p / bs0] * bs0 + p % bs0;
+      const int c = dm1[(long long)cell * nd1 + q / bs1] * bs1 + q % bs1;
+      // bc rows / columns are zeroed before insertion (cpp/assemble_matrix.cpp:513-533): no source at all
+      if (!((bc0 && bc0[r]) || (bc1 && bc1[c])))
+      {
+        const long long k = csr_find(A, r, c);
+        if (k < 0) g_dev_err = MPCX_ERR_PATTERN; else keys[e] = (unsigned)k;
+      }
+    }
+  }
+  SortD(sortd).Sort(keys, vals);
+  __syncthreads();
+  int head[NEc];
+  DiscD(disc).FlagHeads(head, keys, cub::Inequality());
+  __syncthreads();
+  int h = 0, nv = 0;
+#pragma unroll
+  for (int e = 0; e < NEc; ++e)
+  {
+    const bool valid = keys[e] != MPCX_CT_INVALID;
+    head[e] = head[e] && valid;
+    h += head[e];
+    nv += valid;
+  }
+  int hoff, total, voff, vtotal;
+  Scan(scan).ExclusiveSum(h, hoff, total);
+  __syncthreads();
+  Scan(scan).ExclusiveSum(nv, voff, vtotal);
+  __syncthreads();
+  {
+    int di = hoff;
+#pragma unroll
+    for (int e = 0; e < NEc; ++e)
+      if (keys[e] != MPCX_CT_INVALID && head[e])
+      {
+        dkey[di] = keys[e];
+        dstart[di] = (unsigned short)(cl * NEc + e);  // valid keys sort first: rank == position among the valid sources
+        ++di;
+      }
+    if (cl == 0) dstart[total] = (unsigned short)vtotal;
+  }
+  __syncthreads();
+  // Dests in order of DESCENDING source count (stable LSD radix sort, so the plan is deterministic): the lanes of a
+  // warp of the reduction phase then run the same number of iterations (diagonal entries collect ~24 element
+  // entries, off-diagonals 4-6; in CSR order a warp would idle for most of its longest lane's loop).
+  unsigned ckey[NEc];
+  unsigned short cval[NEc];
+#pragma unroll
+  for (int e = 0; e < NEc; ++e)
+  {
+    const int d = cl * NEc + e;
+    const int c = d < total ? (int)dstart[d + 1] - (int)dstart[d] : 0;
+    ckey[e] = d < total ? (unsigned)(63 - (c < 63 ? c : 63)) : 64u;
+    cval[e] = (unsigned short)d;
+  }
+  SortD(sortd).Sort(ckey, cval, 0, 7);
+  __syncthreads();
+#pragma unroll
+  for (int e = 0; e < NEc; ++e)
+  {
+    const int p = cl * NEc + e;  // position in count order
+    if (ckey[e] == 64u) continue;
+    const int d = cval[e];
+    pcnt[p] = (unsigned short)((int)dstart[d + 1] - (int)dstart[d]);
+    npos[d] = (unsigned short)p;
+  }
+  __syncthreads();
+  // groups of 32 dests; group g owns the slot block [gbase[g], gbase[g] + 32 * (largest count in g))
+  const int ngroups = (total + 31) >> 5;
+  int gmax = 0;
+  if (cl < ngroups)
+    for (int l = 0; l < 32; ++l)
+    {
+      const int p = cl * 32 + l;
+      const int c = p < total ? (int)pcnt[p] : 0;
+      gmax = c > gmax ? c : gmax;
+    }
+  int goff, slots;
+  Scan(scan).ExclusiveSum(gmax * MPCX_CT_GSTRIDE, goff, slots);
+  __syncthreads();
+  if (pass == 0)
+  {
+    if (cl == 0) { tile_nd[t] = total; tile_slots[t] = slots; }
+    return;
+  }
+  if (slots >= (int)MPCX_CT_NOSLOT) g_dev_err = MPCX_ERR_UNSUPPORTED;  // cannot happen: the host checked the sizes of pass 0
+  const long long doff = tile_dest_off[t];  // multiple of 128
+  if (cl < ngroups)
+  {
+    gbase[cl] = goff;
+    ginfo[(doff >> 5) + cl] = (unsigned)goff | ((unsigned)gmax << 16);  // first slot | largest count of the group
+  }
+#pragma unroll
+  for (int e = 0; e < NEc; ++e)
+  {
+    if (ckey[e] == 64u) continue;
+    const int p = cl * NEc + e;
+    dest_k[doff + p] = (int)dkey[cval[e]];
+    dest_cnt[doff + p] = pcnt[p];
+  }
+  __syncthreads();
+  {
+    int d = hoff - 1;  // items before the thread's first head continue the previous thread's dest
 #pragma unroll
     for (int e = 0; e < NEc; ++e)
     {
-      keys[e] = MPCX_CT_INVALID;
-      vals[e] = (unsigned short)(e * MPCX_TILE_STRIDE + cl);
-      if (active && vec)
-        keys[e] = (unsigned)dm0[(long long)cell * nd0 + e];  // vector plan (bs == 1): dest = row dof of local entry e
-      else if (active)
+      if (keys[e] == MPCX_CT_INVALID)
       {
-        const int p = e / n1, q = e - p * n1;
-        const int r = dm0[(long long)cell * nd0 + p / bs0] * bs0 + p % bs0;
-        const int c = dm1[(long long)cell * nd1 + q / bs1] * bs1 + q % bs1;
-        // bc rows / columns are zeroed before insertion (cpp/assemble_matrix.cpp:513-533): no source at all
-        if (!((bc0 && bc0[r]) || (bc1 && bc1[c])))
-        {
-          const long long k = csr_find(A, r, c);
-          if (k < 0) g_dev_err = MPCX_ERR_PATTERN; else keys[e] = (unsigned)k;
-        }
+        cell_slot[first * NEc + vals[e]] = (uint16_t)slots;  // bc-zeroed entry: stored to the spare slot nobody reads
+        continue;
       }
-    }
-    SortD(sortd).Sort(keys, vals);
-    __syncthreads();
-    int head[NEc];
-    DiscD(disc).FlagHeads(head, keys, cub::Inequality());
-    __syncthreads();
-    int h = 0, nv = 0;
-#pragma unroll
-    for (int e = 0; e < NEc; ++e)
-    {
-      const bool valid = keys[e] != MPCX_CT_INVALID;
-      head[e] = head[e] && valid;
-      h += head[e];
-      nv += valid;
-    }
-    int hoff, total, voff, vtotal;
-    Scan(scan).ExclusiveSum(h, hoff, total);
-    __syncthreads();
-    Scan(scan).ExclusiveSum(nv, voff, vtotal);
-    __syncthreads();
-    if (pass == 0)
-    {
-      if (cl == 0) { tile_nd[t] = total; tile_ns[t] = vtotal; }
-    }
-    else
-    {
-      // Dests are emitted in order of DESCENDING source count (stable), so that the lanes of a warp of the
-      // assembly kernel's reduction phase run the same number of iterations (diagonal entries collect ~24
-      // element entries, off-diagonals 4-6: in CSR order a warp would idle for most of the longest lane's loop).
-      unsigned char* xp = ct_smem + extra_off;
-      unsigned* dkey = reinterpret_cast<unsigned*>(xp);                       // [NT*NEc]   CSR entry of dest d
-      unsigned short* dstart = reinterpret_cast<unsigned short*>(dkey + NT * NEc);  // [NT*NEc+1] first source rank of d
-      unsigned short* nst = dstart + NT * NEc + 8;                            // [NT*NEc]   first source rank after reordering
-      unsigned short* npos = nst + NT * NEc;                                  // [NT*NEc]   position of d after reordering
-      const long long doff = tile_dest_off[t];
-      uint16_t* s = src + first * NEc;
-      {
-        int di = hoff;
-#pragma unroll
-        for (int e = 0; e < NEc; ++e)
-          if (keys[e] != MPCX_CT_INVALID && head[e])
-          {
-            dkey[di] = keys[e];
-            dstart[di] = (unsigned short)(cl * NEc + e);  // valid keys sort first: rank == position among the valid sources
-            ++di;
-          }
-        if (cl == 0) dstart[total] = (unsigned short)vtotal;
-      }
-      __syncthreads();
-      unsigned ckey[NEc];
-      unsigned short cval[NEc];
-#pragma unroll
-      for (int e = 0; e < NEc; ++e)
-      {
-        const int d = cl * NEc + e;
-        const int c = d < total ? (int)dstart[d + 1] - (int)dstart[d] : 0;
-        ckey[e] = d < total ? (unsigned)(63 - (c < 63 ? c : 63)) : 64u;
-        cval[e] = (unsigned short)d;
-      }
-      SortD(sortd).Sort(ckey, cval, 0, 7);  // LSD radix sort: stable, so the plan is deterministic
-      __syncthreads();
-      int cnt[NEc], csum = 0;
-#pragma unroll
-      for (int e = 0; e < NEc; ++e)
-      {
-        const int d = cval[e];
-        cnt[e] = ckey[e] != 64u ? (int)dstart[d + 1] - (int)dstart[d] : 0;
-        csum += cnt[e];
-      }
-      int coff, ctotal;
-      Scan(scan).ExclusiveSum(csum, coff, ctotal);
-      __syncthreads();
-#pragma unroll
-      for (int e = 0; e < NEc; ++e)
-      {
-        if (ckey[e] == 64u) continue;
-        const int d = cval[e], p = cl * NEc + e;
-        nst[d] = (unsigned short)coff;
-        npos[d] = (unsigned short)p;
-        coff += cnt[e];
-        dest_k[doff + p] = (int)dkey[d];
-        dest_end[doff + p] = (uint16_t)coff;
-      }
-      __syncthreads();
-      {
-        int d = hoff - 1;  // items before the thread's first head continue the previous thread's dest
-#pragma unroll
-        for (int e = 0; e < NEc; ++e)
-        {
-          if (keys[e] == MPCX_CT_INVALID) continue;
-          if (head[e]) ++d;
-          const int rank = cl * NEc + e;
-          s[(int)nst[d] + (rank - (int)dstart[d])] = vals[e];
-          if (vec)  // tile-local row of (cell, local entry): lets the kernel stage per-row data once per tile
-            cell_rows[first * NEc + (vals[e] % MPCX_TILE_STRIDE) * NEc + vals[e] / MPCX_TILE_STRIDE] = npos[d];
-        }
-      }
+      if (head[e]) ++d;
+      const int i = cl * NEc + e - (int)dstart[d];  // i-th source of dest d
+      const int p = npos[d];
+      cell_slot[first * NEc + vals[e]] = (uint16_t)(gbase[p >> 5] + MPCX_CT_GSTRIDE * i + (p & 31));
+      if (vec)  // tile-local row of (cell, local entry): lets the kernel stage per-row data once per tile
+        cell_rows[first * NEc + vals[e]] = (uint16_t)p;
     }
   }
 }
 
-// ------------------------------------------------------------------ the assembly kernel
-// Shared-memory layout of one tile (sections 16-byte aligned):
-//   Xs[max_nodes][3] f64 | ebuf[NE][C] f64 | dk[max_dests] i32 | ssrc[NE*C] u16 | cnode[C][NV] u16 | dend[max_dests] u16
-__host__ __device__ inline size_t tile_smem_bytes(int ne, int nv, int C, int max_nodes, int max_dests)
+// ------------------------------------------------------------------ the assembly kernels
+// Shared memory of one tile (sections 16-byte aligned; dest arrays sized for whole groups of 128 records):
+//   Xs[max_nodes][3] f64 | ebuf[max_slots + 1] f64 | (vector: fs[max_dests] f64) | dk[max_dests] i32 |
+//   gi[max_dests/32] u32 | dcnt[max_dests] u16 | mbarrier
+__host__ __device__ inline size_t tile_smem_bytes(int max_nodes, int max_dests, int max_slots, bool vec)
 {
   auto al = [](size_t b) { return (b + 15) & ~(size_t)15; };
-  return al(24 * (size_t)max_nodes) + al(8 * (size_t)ne * (C + 1)) + al(4 * (size_t)max_dests) + al(2 * (size_t)ne * C)
-         + al(2 * (size_t)nv * C) + al(2 * (size_t)max_dests) + 16;
+  return al(24 * (size_t)max_nodes) + al(8 * (size_t)(max_slots + 1)) + (vec ? al(8 * (size_t)max_dests) : 0) + al(4 * (size_t)max_dests)
+         + al(4 * (size_t)(max_dests / 32)) + al(2 * (size_t)max_dests) + 16;
 }
 
 // ---- 1-D TMA (cp.async.bulk global -> shared, completion on an mbarrier) for the contiguous plan records
@@ -381,94 +409,129 @@ __device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned pari
       : "memory");
 }
 
-template <int TD, bool TMA>
-__global__ void __launch_bounds__(MPCX_TILE_THREADS)
-k_ctile_matrix_p1(TilePlanD P, IntD in, MeshD mesh, CsrD A)
+struct TileSmem
 {
-  constexpr int NV = TD + 1, NE = NV * NV, NT = MPCX_TILE_THREADS;
-  extern __shared__ __align__(16) unsigned char tile_smem[];
-  auto al = [](size_t b) { return (b + 15) & ~(size_t)15; };
-  unsigned char* sp = tile_smem;
-  double* Xs = reinterpret_cast<double*>(sp); sp += al(24 * (size_t)P.max_nodes);
-  double* ebuf = reinterpret_cast<double*>(sp); sp += al(8 * (size_t)NE * MPCX_TILE_STRIDE);
-  int* dk = reinterpret_cast<int*>(sp); sp += al(4 * (size_t)P.max_dests);
-  uint16_t* ssrc = reinterpret_cast<uint16_t*>(sp); sp += al(2 * (size_t)NE * NT);
-  uint16_t* cnode = reinterpret_cast<uint16_t*>(sp); sp += al(2 * (size_t)NV * NT);
-  uint16_t* dend = reinterpret_cast<uint16_t*>(sp); sp += al(2 * (size_t)P.max_dests);
-  unsigned long long* bar = reinterpret_cast<unsigned long long*>(sp);
-  const int t = blockIdx.x, tid = threadIdx.x;
-  const long long first = (long long)t * NT;
-  const int nc_t = (int)((P.n_bulk - first) < NT ? (P.n_bulk - first) : NT);
-  const int n0 = P.tile_node_off[t], nn_t = P.tile_node_off[t + 1] - n0;
-  const long long d0 = P.tile_dest_off[t];  // multiple of 8: 16-byte aligned dest records
-  const int nd_t = P.tile_nd[t];
-  const int ns_t = P.tile_ns[t];
+  double *Xs, *ebuf, *fs;
+  int* dk;
+  unsigned* gi;
+  uint16_t* dcnt;
+  unsigned long long* bar;
+};
 
-  // phase 0: every global read of the tile.  The contiguous plan records travel by TMA bulk copies issued by
-  // one thread; meanwhile all threads gather the vertex coordinates (the only indirect read).
-  if (TMA)
+__device__ __forceinline__ TileSmem tile_carve(unsigned char* sp, const TilePlanD& P, bool vec)
+{
+  auto al = [](size_t b) { return (b + 15) & ~(size_t)15; };
+  TileSmem S;
+  S.Xs = reinterpret_cast<double*>(sp); sp += al(24 * (size_t)P.max_nodes);
+  S.ebuf = reinterpret_cast<double*>(sp); sp += al(8 * (size_t)(P.max_slots + 1));
+  S.fs = reinterpret_cast<double*>(sp); if (vec) sp += al(8 * (size_t)P.max_dests);
+  S.dk = reinterpret_cast<int*>(sp); sp += al(4 * (size_t)P.max_dests);
+  S.gi = reinterpret_cast<unsigned*>(sp); sp += al(4 * (size_t)(P.max_dests / 32));
+  S.dcnt = reinterpret_cast<uint16_t*>(sp); sp += al(2 * (size_t)P.max_dests);
+  S.bar = reinterpret_cast<unsigned long long*>(sp);
+  return S;
+}
+
+// phase 0, shared by both kernels: TMA of the dest records (thread 0) + gather of the tile's vertex coordinates
+__device__ __forceinline__ void tile_stage(const TileSmem& S, const TilePlanD& P, const MeshD& mesh, int t, int tid,
+                                           long long d0, int nd_t)
+{
+  constexpr int NT = MPCX_TILE_THREADS;
+  if (tid == 0)
   {
-    if (tid == 0)
+    mbar_init(S.bar, 1);
+    const unsigned nd8 = (unsigned)((nd_t + 7) & ~7), ng4 = (unsigned)((((nd_t + 31) >> 5) + 3) & ~3);
+    mbar_expect_tx(S.bar, nd8 * 6 + ng4 * 4);
+    if (nd8)
     {
-      mbar_init(bar, 1);
-      const unsigned b_src = (unsigned)(((ns_t + 7) / 8) * 16), b_cn = (unsigned)(2 * NV * NT);
-      const unsigned nd8 = (unsigned)((nd_t + 7) & ~7);
-      mbar_expect_tx(bar, b_src + b_cn + nd8 * 6);
-      if (b_src) tma_load_1d(ssrc, P.src + first * NE, b_src, bar);
-      tma_load_1d(cnode, P.cell_nodes + first * NV, b_cn, bar);
-      if (nd8)
-      {
-        tma_load_1d(dk, P.dest_k + d0, nd8 * 4, bar);
-        tma_load_1d(dend, P.dest_end + d0, nd8 * 2, bar);
-      }
+      tma_load_1d(S.dk, P.dest_k + d0, nd8 * 4, S.bar);
+      tma_load_1d(S.dcnt, P.dest_cnt + d0, nd8 * 2, S.bar);
+      tma_load_1d(S.gi, P.ginfo + (d0 >> 5), ng4 * 4, S.bar);
     }
   }
+  const int n0 = __ldg(P.tile_node_off + t), nn_t = __ldg(P.tile_node_off + t + 1) - n0;
   for (int i = tid; i < nn_t; i += NT)
   {
     const double* p = mesh.x + (long long)__ldg(P.node_ids + n0 + i) * mesh.xs;
     if (mesh.xs == 4)
     {
       const double2 a = __ldg(reinterpret_cast<const double2*>(p));
-      Xs[3 * i] = a.x; Xs[3 * i + 1] = a.y;
+      S.Xs[3 * i] = a.x; S.Xs[3 * i + 1] = a.y;
     }
     else
     {
-      Xs[3 * i] = __ldg(p);
-      Xs[3 * i + 1] = __ldg(p + 1);
+      S.Xs[3 * i] = __ldg(p);
+      S.Xs[3 * i + 1] = __ldg(p + 1);
     }
-    Xs[3 * i + 2] = __ldg(p + 2);
+    S.Xs[3 * i + 2] = __ldg(p + 2);
   }
-  if (!TMA)
-  {
-    {
-      const uint4* g = reinterpret_cast<const uint4*>(P.src + first * NE);
-      uint4* s = reinterpret_cast<uint4*>(ssrc);
-      for (int i = tid; i < (ns_t + 7) / 8; i += NT) s[i] = __ldg(g + i);
-    }
-    for (int k = tid; k < nd_t; k += NT)
-    {
-      dk[k] = __ldg(P.dest_k + d0 + k);
-      dend[k] = __ldg(P.dest_end + d0 + k);
-    }
-    if (NV == 4)
-      reinterpret_cast<uint2*>(cnode)[tid] = __ldg(reinterpret_cast<const uint2*>(P.cell_nodes) + first + tid);
-    else
-      for (int i = tid; i < NT * NV; i += NT) cnode[i] = __ldg(P.cell_nodes + first * NV + i);
-  }
-  __syncthreads();  // Xs complete; the mbarrier initialisation is visible to every thread
-  if (TMA) mbar_wait(bar, 0);
+}
 
-  // phase 1: thread = cell; element matrix -> element buffer, entry-major (conflict-free stores)
+// phase 2, shared by both kernels: dest k = column (k & 31) of its group's slot block.  The trip count is the
+// group's largest count (warp-uniform: no divergence bookkeeping); rows past the lane's own count are not read.
+__device__ __forceinline__ double tile_reduce(const TileSmem& S, int k)
+{
+  const unsigned g = S.gi[k >> 5];
+  const double* e = S.ebuf + (g & 0xffffu) + (k & 31);
+  const int cmax = (int)(g >> 16), cnt = S.dcnt[k];
+  double s0 = 0.0, s1 = 0.0;
+  int i = 0;
+#pragma unroll 1
+  for (; i + 2 <= cmax; i += 2, e += 2 * MPCX_CT_GSTRIDE)
+  {
+    if (i < cnt) s0 += e[0];
+    if (i + 1 < cnt) s1 += e[MPCX_CT_GSTRIDE];
+  }
+  if (i < cnt) s0 += e[0];
+  return s0 + s1;
+}
+
+template <int TD>
+__global__ void __launch_bounds__(MPCX_TILE_THREADS)
+k_ctile_matrix_p1(TilePlanD P, IntD in, MeshD mesh, CsrD A)
+{
+  constexpr int NV = TD + 1, NE = NV * NV, NT = MPCX_TILE_THREADS;
+  extern __shared__ __align__(16) unsigned char tile_smem[];
+  const TileSmem S = tile_carve(tile_smem, P, false);
+  const int t = blockIdx.x, tid = threadIdx.x;
+  const long long first = (long long)t * NT;
+  const int nc_t = (int)((P.n_bulk - first) < NT ? (P.n_bulk - first) : NT);
+  const long long d0 = __ldg(P.tile_dest_off + t);
+  const int nd_t = __ldg(P.tile_nd + t);
+
+  // this thread's cell record: tile-local vertices and the slot of each element entry (coalesced 8 + 32 bytes)
+  uint16_t cn[NV], slot[NE];
+  if (NV == 4)
+  {
+    const uint2 a = __ldg(reinterpret_cast<const uint2*>(P.cell_nodes) + first + tid);
+    cn[0] = a.x & 0xffff; cn[1] = a.x >> 16; cn[2] = a.y & 0xffff; cn[3] = a.y >> 16;
+    const uint4* sp = reinterpret_cast<const uint4*>(P.cell_slot) + (first + tid) * 2;
+    const uint4 s0 = __ldg(sp), s1 = __ldg(sp + 1);
+    const unsigned w[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
+#pragma unroll
+    for (int e = 0; e < 8; ++e) { slot[2 * e] = w[e] & 0xffff; slot[2 * e + 1] = w[e] >> 16; }
+  }
+  else
+  {
+#pragma unroll
+    for (int v = 0; v < NV; ++v) cn[v] = __ldg(P.cell_nodes + (first + tid) * NV + v);
+#pragma unroll
+    for (int e = 0; e < NE; ++e) slot[e] = __ldg(P.cell_slot + (first + tid) * NE + e);
+  }
+  tile_stage(S, P, mesh, t, tid, d0, nd_t);
+  __syncthreads();  // Xs complete; the mbarrier initialisation is visible to every thread
+
+  // phase 1: thread = cell; element matrix entries to their slots
   if (tid < nc_t)
   {
     double X[NV][3];
 #pragma unroll
     for (int v = 0; v < NV; ++v)
     {
-      const int l = cnode[tid * NV + v];
-      X[v][0] = Xs[3 * l];
-      X[v][1] = Xs[3 * l + 1];
-      X[v][2] = TD == 3 ? Xs[3 * l + 2] : 0.0;
+      const int l = cn[v];
+      X[v][0] = S.Xs[3 * l];
+      X[v][1] = S.Xs[3 * l + 1];
+      X[v][2] = TD == 3 ? S.Xs[3 * l + 2] : 0.0;
     }
     P1Geom<TD> G;
     p1_geometry<TD>(X, G);
@@ -482,111 +545,68 @@ k_ctile_matrix_p1(TilePlanD P, IntD in, MeshD mesh, CsrD A)
 #pragma unroll
     for (int i = 0; i < NV; ++i)
 #pragma unroll
-      for (int j = 0; j < NV; ++j) ebuf[(i * NV + j) * MPCX_TILE_STRIDE + tid] = Ae[i][j];
+      for (int j = 0; j < NV; ++j)
+        S.ebuf[slot[i * NV + j]] = Ae[i][j];  // bc-zeroed entries go to the tile's spare slot
   }
   __syncthreads();
+  mbar_wait(S.bar, 0);
 
-  // phase 2: thread = dest; sum of its sources (4 independent chains), one RED per (tile, dest)
-  for (int k = tid; k < nd_t; k += NT)
-  {
-    const int beg = k ? dend[k - 1] : 0, end = dend[k];
-    double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
-    int p = beg;
-    for (; p + 4 <= end; p += 4)
-    {
-      const int a = ssrc[p], b = ssrc[p + 1], c = ssrc[p + 2], d = ssrc[p + 3];
-      s0 += ebuf[a]; s1 += ebuf[b]; s2 += ebuf[c]; s3 += ebuf[d];
-    }
-    for (; p < end; ++p) s0 += ebuf[ssrc[p]];
-    atomicAdd(A.val + dk[k], (s0 + s1) + (s2 + s3));
-  }
+  // phase 2: thread = dest, one RED per (tile, dest)
+  for (int k = tid; k < nd_t; k += NT) atomicAdd(A.val + S.dk[k], tile_reduce(S, k));
 }
 
-// ------------------------------------------------------------------ vector tile kernel (P1 source term)
-// Same three phases for the load vector b_i = c0 |K|/((d+1)(d+2)) (f_i + sum_j f_j)
-// (cpp/assemble_vector.cpp:163-185 with the P1 source kernel): 4 element entries per cell, dests = the row dofs
-// of the tile, one red.global.add.f64 per (tile, row) instead of one per (cell, vertex).  When the coefficient
-// lives in the same space as the test function its values are staged once per tile row.
-//   Xs[max_nodes][3] f64 | ebuf[NV][C+1] f64 | fs[max_dests] f64 | dk[max_dests] i32 | ssrc[NV*C] u16 |
-//   cnode[C][NV] u16 | crow[C][NV] u16 | dend[max_dests] u16 | mbarrier
-__host__ __device__ inline size_t vtile_smem_bytes(int nv, int C, int max_nodes, int max_dests)
-{
-  auto al = [](size_t b) { return (b + 15) & ~(size_t)15; };
-  return al(24 * (size_t)max_nodes) + al(8 * (size_t)nv * (C + 1)) + al(8 * (size_t)max_dests) + al(4 * (size_t)max_dests)
-         + 3 * al(2 * (size_t)nv * C) + al(2 * (size_t)max_dests) + 16;
-}
-
+// Load vector b_i = c0 |K|/((d+1)(d+2)) (f_i + sum_j f_j) (cpp/assemble_vector.cpp:163-185 with the P1 source
+// kernel): NV entries per cell, dests = the row dofs of the tile, one red.global.add.f64 per (tile, row) instead
+// of one per (cell, vertex).  When the coefficient lives in the test space (w_by_row) its values are staged once
+// per tile row.
 template <int TD>
 __global__ void __launch_bounds__(MPCX_TILE_THREADS)
 k_ctile_vector_p1(TilePlanD P, IntD in, MeshD mesh, int w_by_row, double* __restrict__ b)
 {
   constexpr int NV = TD + 1, NT = MPCX_TILE_THREADS;
   extern __shared__ __align__(16) unsigned char tile_smem[];
-  auto al = [](size_t b_) { return (b_ + 15) & ~(size_t)15; };
-  unsigned char* sp = tile_smem;
-  double* Xs = reinterpret_cast<double*>(sp); sp += al(24 * (size_t)P.max_nodes);
-  double* ebuf = reinterpret_cast<double*>(sp); sp += al(8 * (size_t)NV * MPCX_TILE_STRIDE);
-  double* fs = reinterpret_cast<double*>(sp); sp += al(8 * (size_t)P.max_dests);
-  int* dk = reinterpret_cast<int*>(sp); sp += al(4 * (size_t)P.max_dests);
-  uint16_t* ssrc = reinterpret_cast<uint16_t*>(sp); sp += al(2 * (size_t)NV * NT);
-  uint16_t* cnode = reinterpret_cast<uint16_t*>(sp); sp += al(2 * (size_t)NV * NT);
-  uint16_t* crow = reinterpret_cast<uint16_t*>(sp); sp += al(2 * (size_t)NV * NT);
-  uint16_t* dend = reinterpret_cast<uint16_t*>(sp); sp += al(2 * (size_t)P.max_dests);
-  unsigned long long* bar = reinterpret_cast<unsigned long long*>(sp);
+  const TileSmem S = tile_carve(tile_smem, P, true);
   const int t = blockIdx.x, tid = threadIdx.x;
   const long long first = (long long)t * NT;
   const int nc_t = (int)((P.n_bulk - first) < NT ? (P.n_bulk - first) : NT);
-  const int n0 = P.tile_node_off[t], nn_t = P.tile_node_off[t + 1] - n0;
-  const long long d0 = P.tile_dest_off[t];
-  const int nd_t = P.tile_nd[t];
-  const int ns_t = P.tile_ns[t];
+  const long long d0 = __ldg(P.tile_dest_off + t);
+  const int nd_t = __ldg(P.tile_nd + t);
 
-  if (tid == 0)
+  uint16_t cn[NV], slot[NV], crow[NV];
+  if (NV == 4)
   {
-    mbar_init(bar, 1);
-    const unsigned b_src = (unsigned)(((ns_t + 7) / 8) * 16), b_cn = (unsigned)(2 * NV * NT);
-    const unsigned nd8 = (unsigned)((nd_t + 7) & ~7);
-    mbar_expect_tx(bar, b_src + 2 * b_cn + nd8 * 6);
-    if (b_src) tma_load_1d(ssrc, P.src + first * NV, b_src, bar);
-    tma_load_1d(cnode, P.cell_nodes + first * NV, b_cn, bar);
-    tma_load_1d(crow, P.cell_rows + first * NV, b_cn, bar);
-    if (nd8)
+    const uint2 a = __ldg(reinterpret_cast<const uint2*>(P.cell_nodes) + first + tid);
+    const uint2 s = __ldg(reinterpret_cast<const uint2*>(P.cell_slot) + first + tid);
+    const uint2 r = __ldg(reinterpret_cast<const uint2*>(P.cell_rows) + first + tid);
+    cn[0] = a.x & 0xffff; cn[1] = a.x >> 16; cn[2] = a.y & 0xffff; cn[3] = a.y >> 16;
+    slot[0] = s.x & 0xffff; slot[1] = s.x >> 16; slot[2] = s.y & 0xffff; slot[3] = s.y >> 16;
+    crow[0] = r.x & 0xffff; crow[1] = r.x >> 16; crow[2] = r.y & 0xffff; crow[3] = r.y >> 16;
+  }
+  else
+  {
+#pragma unroll
+    for (int v = 0; v < NV; ++v)
     {
-      tma_load_1d(dk, P.dest_k + d0, nd8 * 4, bar);
-      tma_load_1d(dend, P.dest_end + d0, nd8 * 2, bar);
+      cn[v] = __ldg(P.cell_nodes + (first + tid) * NV + v);
+      slot[v] = __ldg(P.cell_slot + (first + tid) * NV + v);
+      crow[v] = __ldg(P.cell_rows + (first + tid) * NV + v);
     }
   }
-  for (int i = tid; i < nn_t; i += NT)
-  {
-    const double* p = mesh.x + (long long)__ldg(P.node_ids + n0 + i) * mesh.xs;
-    if (mesh.xs == 4)
-    {
-      const double2 a = __ldg(reinterpret_cast<const double2*>(p));
-      Xs[3 * i] = a.x; Xs[3 * i + 1] = a.y;
-    }
-    else
-    {
-      Xs[3 * i] = __ldg(p);
-      Xs[3 * i + 1] = __ldg(p + 1);
-    }
-    Xs[3 * i + 2] = __ldg(p + 2);
-  }
-  if (w_by_row)  // coefficient in the test space: one read per tile row (straight from the plan, no wait on the TMA)
-    for (int k = tid; k < nd_t; k += NT) fs[k] = __ldg(in.wnodal + __ldg(P.dest_k + d0 + k));
+  tile_stage(S, P, mesh, t, tid, d0, nd_t);
+  if (w_by_row)  // one coefficient read per tile row (straight from the plan: no wait on the TMA)
+    for (int k = tid; k < nd_t; k += NT) S.fs[k] = __ldg(in.wnodal + __ldg(P.dest_k + d0 + k));
   __syncthreads();
-  mbar_wait(bar, 0);
 
-  // phase 1: thread = cell
   if (tid < nc_t)
   {
     double X[NV][3];
 #pragma unroll
     for (int v = 0; v < NV; ++v)
     {
-      const int l = cnode[tid * NV + v];
-      X[v][0] = Xs[3 * l];
-      X[v][1] = Xs[3 * l + 1];
-      X[v][2] = TD == 3 ? Xs[3 * l + 2] : 0.0;
+      const int l = cn[v];
+      X[v][0] = S.Xs[3 * l];
+      X[v][1] = S.Xs[3 * l + 1];
+      X[v][2] = TD == 3 ? S.Xs[3 * l + 2] : 0.0;
     }
     P1Geom<TD> G;
     p1_geometry<TD>(X, G);
@@ -594,7 +614,7 @@ k_ctile_vector_p1(TilePlanD P, IntD in, MeshD mesh, int w_by_row, double* __rest
     if (w_by_row)
     {
 #pragma unroll
-      for (int v = 0; v < NV; ++v) f[v] = fs[crow[tid * NV + v]];
+      for (int v = 0; v < NV; ++v) f[v] = S.fs[crow[v]];
     }
     else
     {
@@ -603,26 +623,14 @@ k_ctile_vector_p1(TilePlanD P, IntD in, MeshD mesh, int w_by_row, double* __rest
     }
 #pragma unroll
     for (int v = 0; v < NV; ++v) fsum += f[v];
-    const double s = in.c[0] * G.vol / double((TD + 1) * (TD + 2));
+    const double sc = in.c[0] * G.vol * (1.0 / double((TD + 1) * (TD + 2)));
 #pragma unroll
-    for (int v = 0; v < NV; ++v) ebuf[v * MPCX_TILE_STRIDE + tid] = s * (f[v] + fsum);
+    for (int v = 0; v < NV; ++v) S.ebuf[slot[v]] = sc * (f[v] + fsum);  // a vector plan has no bc-zeroed entries
   }
   __syncthreads();
+  mbar_wait(S.bar, 0);
 
-  // phase 2: thread = row of the tile
-  for (int k = tid; k < nd_t; k += NT)
-  {
-    const int beg = k ? dend[k - 1] : 0, end = dend[k];
-    double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
-    int p = beg;
-    for (; p + 4 <= end; p += 4)
-    {
-      const int a = ssrc[p], bb = ssrc[p + 1], c = ssrc[p + 2], d = ssrc[p + 3];
-      s0 += ebuf[a]; s1 += ebuf[bb]; s2 += ebuf[c]; s3 += ebuf[d];
-    }
-    for (; p < end; ++p) s0 += ebuf[ssrc[p]];
-    atomicAdd(b + dk[k], (s0 + s1) + (s2 + s3));
-  }
+  for (int k = tid; k < nd_t; k += NT) atomicAdd(b + S.dk[k], tile_reduce(S, k));
 }
 
 // ------------------------------------------------------------------ host side of the setup
@@ -641,31 +649,38 @@ cudaError_t tp_alloc(T** p, long long n)
 void tile_plan_free(TilePlan* P)
 {
   if (!P) return;
-  cudaFree(P->cell_pos); cudaFree(P->tile_node_off); cudaFree(P->node_ids); cudaFree(P->dest_k); cudaFree(P->tile_ns); cudaFree(P->tile_nd);
-  cudaFree(P->tile_dest_off); cudaFree(P->cell_nodes); cudaFree(P->dest_end); cudaFree(P->src); cudaFree(P->cell_rows);
+  cudaFree(P->cell_pos); cudaFree(P->tile_node_off); cudaFree(P->node_ids); cudaFree(P->dest_k); cudaFree(P->tile_nd);
+  cudaFree(P->tile_slots); cudaFree(P->ginfo); cudaFree(P->tile_dest_off); cudaFree(P->cell_nodes); cudaFree(P->dest_cnt);
+  cudaFree(P->cell_slot); cudaFree(P->cell_rows);
   delete P;
+}
+
+inline TilePlanD tile_plan_view(const TilePlan* P)
+{
+  return TilePlanD{P->C, P->max_nodes, P->max_dests, P->max_slots, P->n_bulk, P->cell_pos, P->tile_node_off, P->node_ids,
+                   P->dest_k, P->tile_nd, P->ginfo, P->tile_dest_off, P->cell_nodes, P->dest_cnt, P->cell_slot, P->cell_rows};
 }
 
 inline unsigned tp_grid(long long n, int b = 256) { return (unsigned)((n + b - 1) / b > 0 ? (n + b - 1) / b : 1); }
 
 template <int NEc, int NGc>
-cudaError_t ct_build_launch(int pass, int nt, cudaStream_t s, const int* order, long long n_bulk, const int* cells, MeshD md,
-                            const mpcx_dofmap* dm0, const mpcx_dofmap* dm1, const int8_t* bc0, const int8_t* bc1, CsrD A,
-                            int* tile_nn, int* tile_nd, TilePlan* P)
+cudaError_t ct_build_launch(int pass, cudaStream_t s, const int* order, const int* cells, MeshD md, const mpcx_dofmap* dm0,
+                            const mpcx_dofmap* dm1, const int8_t* bc0, const int8_t* bc1, CsrD A, int* tile_nn, TilePlan* P)
 {
-  constexpr int NT = MPCX_TILE_THREADS;
+  constexpr int NT = MPCX_TILE_THREADS, N = NT * NEc;
   auto kern = k_ct_build<NT, NEc, NGc>;
   size_t smem = sizeof(typename cub::BlockRadixSort<unsigned, NT, NEc, unsigned short>::TempStorage);
   smem = std::max(smem, sizeof(typename cub::BlockRadixSort<unsigned, NT, NGc, unsigned short>::TempStorage));
   smem = std::max(smem, sizeof(typename cub::BlockDiscontinuity<unsigned, NT>::TempStorage));
   smem = (std::max(smem, sizeof(typename cub::BlockScan<int, NT>::TempStorage)) + 15) & ~(size_t)15;
   const int extra_off = (int)smem;
-  smem += (size_t)NT * NEc * 4 + 3 * ((size_t)NT * NEc + 8) * 2 + 16;  // dkey, dstart, nst, npos of the count ordering
+  smem += (size_t)N * 4 + (size_t)(N / 32 + 1) * 4 + ((size_t)N + 8 + N + N + 32) * 2 + 16;  // dkey, gbase, dstart, npos, pcnt
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
-  kern<<<nt, NT, smem, s>>>(pass, order, n_bulk, cells, md, dm0->map, dm1->map, dm0->nd, dm1->nd, dm0->bs, dm1->bs, bc0, bc1, A,
-                            tile_nn, tile_nd, P->tile_ns, P->tile_node_off, P->tile_dest_off, P->cell_pos, P->node_ids,
-                            P->cell_nodes, P->dest_k, P->dest_end, P->src, extra_off, P->vec, P->cell_rows);
+  kern<<<P->nt, NT, smem, s>>>(pass, order, P->n_bulk, cells, md, dm0->map, dm1->map, dm0->nd, dm1->nd, dm0->bs, dm1->bs, bc0,
+                               bc1, A, P->vec, extra_off, tile_nn, P->tile_nd, P->tile_slots, P->tile_node_off,
+                               P->tile_dest_off, P->cell_pos, P->node_ids, P->cell_nodes, P->dest_k, P->dest_cnt, P->ginfo,
+                               P->cell_slot, P->cell_rows);
   return cudaGetLastError();
 }
 
@@ -688,9 +703,9 @@ int tile_plan_build(const mpcx_mesh* mesh, const mpcx_dofmap* dm0, const mpcx_do
   long long* nb_dev = nullptr;
   void* tmp = nullptr;
   size_t tmp_bytes = 0, tb = 0;
-  std::vector<int> h_nn, h_nd, noff;
+  std::vector<int> h_nn, h_nd, h_sl, noff;
   std::vector<long long> h_doff;
-  long long n_dests = 0, alloc_dests = 0;
+  long long alloc_dests = 0;
   BBox bb;
   int variant = 0;
   auto need_tmp = [&](size_t bytes) -> cudaError_t {
@@ -701,10 +716,10 @@ int tile_plan_build(const mpcx_mesh* mesh, const mpcx_dofmap* dm0, const mpcx_do
     return cudaMalloc(&tmp, tmp_bytes);
   };
   auto build = [&](int pass) -> cudaError_t {
-    if (variant == 4) return ct_build_launch<4, 4>(pass, P->nt, s, order, P->n_bulk, cells, md, dm0, dm1, bc0, bc1, A, tile_nn, P->tile_nd, P);
-    if (variant == 3) return ct_build_launch<3, 3>(pass, P->nt, s, order, P->n_bulk, cells, md, dm0, dm1, bc0, bc1, A, tile_nn, P->tile_nd, P);
-    if (variant == 16) return ct_build_launch<16, 4>(pass, P->nt, s, order, P->n_bulk, cells, md, dm0, dm1, bc0, bc1, A, tile_nn, P->tile_nd, P);
-    return ct_build_launch<9, 3>(pass, P->nt, s, order, P->n_bulk, cells, md, dm0, dm1, bc0, bc1, A, tile_nn, P->tile_nd, P);
+    if (variant == 4) return ct_build_launch<4, 4>(pass, s, order, cells, md, dm0, dm1, bc0, bc1, A, tile_nn, P);
+    if (variant == 3) return ct_build_launch<3, 3>(pass, s, order, cells, md, dm0, dm1, bc0, bc1, A, tile_nn, P);
+    if (variant == 16) return ct_build_launch<16, 4>(pass, s, order, cells, md, dm0, dm1, bc0, bc1, A, tile_nn, P);
+    return ct_build_launch<9, 3>(pass, s, order, cells, md, dm0, dm1, bc0, bc1, A, tile_nn, P);
   };
 
   if (vec && dm0->bs == 1 && P->ne == 4 && mesh->ng == 4) variant = 4;
@@ -744,28 +759,34 @@ int tile_plan_build(const mpcx_mesh* mesh, const mpcx_dofmap* dm0, const mpcx_do
   if (P->nt == 0) goto done;  // nothing but slave cells: an empty plan is valid
 
   // 3. pass 0: sizes of every tile
-  TP_CK(tp_alloc(&tile_nn, P->nt)); TP_CK(tp_alloc(&P->tile_nd, P->nt)); TP_CK(tp_alloc(&P->tile_ns, P->nt));
+  TP_CK(tp_alloc(&tile_nn, P->nt)); TP_CK(tp_alloc(&P->tile_nd, P->nt)); TP_CK(tp_alloc(&P->tile_slots, P->nt));
   TP_CK(build(0));
-  h_nn.resize(P->nt); h_nd.resize(P->nt);
+  h_nn.resize(P->nt); h_nd.resize(P->nt); h_sl.resize(P->nt);
   TP_CK(cudaMemcpyAsync(h_nn.data(), tile_nn, sizeof(int) * P->nt, cudaMemcpyDeviceToHost, s));
   TP_CK(cudaMemcpyAsync(h_nd.data(), P->tile_nd, sizeof(int) * P->nt, cudaMemcpyDeviceToHost, s));
+  TP_CK(cudaMemcpyAsync(h_sl.data(), P->tile_slots, sizeof(int) * P->nt, cudaMemcpyDeviceToHost, s));
   TP_CK(cudaStreamSynchronize(s));
   noff.assign(P->nt + 1, 0);
   h_doff.assign(P->nt + 1, 0);
   for (int t = 0; t < P->nt; ++t)
   {
     noff[t + 1] = noff[t] + h_nn[t];
-    h_doff[t + 1] = h_doff[t] + ((h_nd[t] + 7) & ~7);  // 16-byte aligned records for the TMA bulk copies
-    n_dests += h_nd[t];
+    h_doff[t + 1] = h_doff[t] + ((h_nd[t] + 127) & ~127);  // 16-byte aligned dest / group records for the TMA bulk copies
+    P->total_dests += h_nd[t];
+    P->total_slots += h_sl[t];
     P->max_nodes = std::max(P->max_nodes, h_nn[t]);
     P->max_dests = std::max(P->max_dests, h_nd[t]);
+    P->max_slots = std::max(P->max_slots, h_sl[t]);
   }
   P->total_nodes = noff[P->nt];
-  P->total_dests = n_dests;
-  alloc_dests = h_doff[P->nt] + 8;
-  P->total_src = (long long)P->nt * C * P->ne;
+  alloc_dests = h_doff[P->nt] + 128;
   P->max_nodes = (P->max_nodes + 1) & ~1;
-  P->max_dests = (P->max_dests + 7) & ~7;  // the TMA copies move whole groups of 8 dest records
+  P->max_dests = (P->max_dests + 127) & ~127;  // the TMA copies move whole groups of records
+  if (P->max_slots >= (int)MPCX_CT_NOSLOT || tile_smem_bytes(P->max_nodes, P->max_dests, P->max_slots, vec) > 200 * 1024)
+  {
+    rc = fail(MPCX_ERR_UNSUPPORTED, "tile plan: a tile needs more element-buffer slots than shared memory holds");
+    goto done;
+  }
   TP_CK(tp_alloc(&P->tile_node_off, P->nt + 1)); TP_CK(tp_alloc(&P->tile_dest_off, P->nt + 1));
   TP_CK(cudaMemcpyAsync(P->tile_node_off, noff.data(), sizeof(int) * (P->nt + 1), cudaMemcpyHostToDevice, s));
   TP_CK(cudaMemcpyAsync(P->tile_dest_off, h_doff.data(), sizeof(long long) * (P->nt + 1), cudaMemcpyHostToDevice, s));
@@ -773,10 +794,13 @@ int tile_plan_build(const mpcx_mesh* mesh, const mpcx_dofmap* dm0, const mpcx_do
   // 4. pass 1: the records
   TP_CK(tp_alloc(&P->cell_pos, (long long)P->nt * C)); TP_CK(tp_alloc(&P->node_ids, P->total_nodes));
   TP_CK(tp_alloc(&P->cell_nodes, (long long)P->nt * C * P->ng)); TP_CK(tp_alloc(&P->dest_k, alloc_dests));
-  TP_CK(tp_alloc(&P->dest_end, alloc_dests)); TP_CK(tp_alloc(&P->src, P->total_src + 8));
+  TP_CK(tp_alloc(&P->dest_cnt, alloc_dests)); TP_CK(tp_alloc(&P->ginfo, alloc_dests / 32));
+  TP_CK(tp_alloc(&P->cell_slot, (long long)P->nt * C * P->ne));
   TP_CK(cudaMemsetAsync(P->cell_nodes, 0, sizeof(uint16_t) * (size_t)P->nt * C * P->ng, s));
   TP_CK(cudaMemsetAsync(P->dest_k, 0, sizeof(int) * (size_t)alloc_dests, s));
-  TP_CK(cudaMemsetAsync(P->dest_end, 0, sizeof(uint16_t) * (size_t)alloc_dests, s));
+  TP_CK(cudaMemsetAsync(P->dest_cnt, 0, sizeof(uint16_t) * (size_t)alloc_dests, s));
+  TP_CK(cudaMemsetAsync(P->ginfo, 0, sizeof(unsigned) * (size_t)(alloc_dests / 32), s));
+  TP_CK(cudaMemsetAsync(P->cell_slot, 0xff, sizeof(uint16_t) * (size_t)P->nt * C * P->ne, s));  // MPCX_CT_NOSLOT
   if (vec)
   {
     TP_CK(tp_alloc(&P->cell_rows, (long long)P->nt * C * P->ne));
@@ -784,9 +808,9 @@ int tile_plan_build(const mpcx_mesh* mesh, const mpcx_dofmap* dm0, const mpcx_do
   }
   TP_CK(build(1));
   TP_CK(cudaStreamSynchronize(s));
-  P->bytes = (long long)sizeof(uint16_t) * (P->total_src + (long long)P->nt * C * P->ng + P->total_dests)
-             + (long long)sizeof(int) * (P->total_nodes + P->total_dests + (long long)P->nt * C) + (long long)(P->nt + 1) * 16
-             + (vec ? (long long)sizeof(uint16_t) * P->nt * C * P->ne : 0);
+  // bytes one assembly reads from the plan
+  P->bytes = (long long)sizeof(uint16_t) * ((long long)P->nt * C * (P->ne * (vec ? 2 : 1) + P->ng) + P->total_dests)
+             + (long long)sizeof(int) * (P->total_nodes + P->total_dests + P->total_dests / 32) + (long long)(P->nt + 1) * 16;
 
 done:
   cudaFree(mm); cudaFree(code); cudaFree(code2); cudaFree(iota); cudaFree(order); cudaFree(tile_nn);

@@ -95,10 +95,10 @@ class Matrix:
                                                  _dev.ptr(skip), _dev.ptr(bc0_d), _dev.ptr(bc1_d), C.byref(A),
                                                  _dev.stream_ptr(), C.byref(handle)))
             _lib.check(lib.mpcx_device_error(_dev.stream_ptr()))
-            info = (C.c_int64 * 8)()
-            lib.mpcx_tile_plan_info(handle, info, 8)
+            info = (C.c_int64 * 10)()
+            lib.mpcx_tile_plan_info(handle, info, 10)
             self._tile_plans[key] = (handle, dict(zip(("tiles", "cells_per_tile", "bulk_cells", "max_nodes",
-                                                       "max_dests", "tile_nodes", "dests", "bytes"),
+                                                       "max_dests", "tile_nodes", "dests", "bytes", "max_slots", "slots"),
                                                       [int(v) for v in info])))
         return self._tile_plans[key]
 

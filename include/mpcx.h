@@ -177,8 +177,9 @@ int mpcx_tile_plan_create(const mpcx_mesh* mesh, const mpcx_dofmap* dofmap0, con
                           const int8_t* bc0, const int8_t* bc1, const mpcx_csr* A, void* stream,
                           mpcx_tile_plan** plan_out);
 void mpcx_tile_plan_destroy(mpcx_tile_plan* plan);
-/* out[0..7] = tiles, cells per tile, bulk cells, max vertices / dests per tile, total tile vertices,
- * total dests (= red.global.add operations per assembly), plan bytes */
+/* out[0..9] = tiles, cells per tile, bulk cells, max vertices / dests per tile, total tile vertices,
+ * total dests (= red.global.add operations per assembly), plan bytes read per assembly, max / total
+ * element-buffer slots */
 int mpcx_tile_plan_info(const mpcx_tile_plan* plan, int64_t* out, int32_t n);
 
 /* Same contract as mpcx_assemble_matrix_f64 (A += integral; the caller zeroes A), bulk cells through the

@@ -31,6 +31,8 @@ for _ in range(args.reps):
 ms, n = C.c_double(0), C.c_longlong(0)
 lib.mpcx_profile_read(C.byref(ms), C.byref(n))
 nc = P["mesh"].num_cells_local
+from dolfinx_mpc_b200 import device as _dev
+P["f"].device_array = _dev.to_dev(P["f"].array)
 b = mpcx.create_vector(P["mpc"])
 for _ in range(2):
     mpcx.assemble_vector(P["L"], P["mpc"], b=b)
