@@ -127,4 +127,6 @@ def load():
 def check(status: int):
     if status != OK:
         msg = load().mpcx_last_error().decode()
-        raise MpcxError(f"mpcx status {status}: {msg}")
+        err = MpcxError(f"mpcx status {status}: {msg}")
+        err.status = status
+        raise err

@@ -85,14 +85,20 @@ def _vector_tile_plan(form: Form, it, s_integral, constraint, mesh_s, dm):
             skip = torch.zeros(ncells, dtype=torch.int8, device=_dev.device())
             skip[it._dev[("slave_cells", id(constraint))][0].long()] = 1
         handle = C.c_void_p()
-        _lib.check(lib.mpcx_vector_tile_plan_create(C.byref(mesh_s), C.byref(dm), s_integral.cells, ncells,
-                                                    _dev.ptr(skip), _dev.stream_ptr(), C.byref(handle)))
+        try:
+            _lib.check(lib.mpcx_vector_tile_plan_create(C.byref(mesh_s), C.byref(dm), s_integral.cells, ncells,
+                                                        _dev.ptr(skip), _dev.stream_ptr(), C.byref(handle)))
+        except _lib.MpcxError as e:  # tiles that do not fit the plan format: atomic-scatter kernel instead
+            if getattr(e, "status", None) != _lib.ERR_UNSUPPORTED:
+                raise
+            it._dev[key] = None
+            return None
         _lib.check(lib.mpcx_device_error(_dev.stream_ptr()))
-        info = (C.c_int64 * 10)()
-        lib.mpcx_tile_plan_info(handle, info, 10)
+        info = (C.c_int64 * 14)()
+        lib.mpcx_tile_plan_info(handle, info, 14)
         it._dev[key] = (handle, _PlanHandle(handle),
                         dict(zip(("tiles", "cells_per_tile", "bulk_cells", "max_nodes", "max_dests", "tile_nodes",
-                                  "dests", "bytes", "max_slots", "slots"), [int(v) for v in info])))
+                                  "dests", "bytes", "max_slots", "slots", "max_runs", "runs", "max_stage", "symmetric"), [int(v) for v in info])))
     return it._dev[key]
 
 

@@ -1206,9 +1206,9 @@ int mpcx_tile_plan_info(const mpcx_tile_plan* plan, int64_t* out, int32_t n)
 {
   if (!plan || !out) return fail(MPCX_ERR_ARG, "null argument");
   const TilePlan* P = reinterpret_cast<const TilePlan*>(plan);
-  const int64_t v[10] = {P->nt, P->C, P->n_bulk, P->max_nodes, P->max_dests, P->total_nodes, P->total_dests, P->bytes,
-                         P->max_slots, P->total_slots};
-  for (int i = 0; i < n && i < 10; ++i) out[i] = v[i];
+  const int64_t v[14] = {P->nt, P->C, P->n_bulk, P->max_nodes, P->max_dests, P->total_nodes, P->total_dests, P->bytes,
+                         P->max_slots, P->total_slots, P->max_runs, P->total_runs, P->max_stage, P->sym};
+  for (int i = 0; i < n && i < 14; ++i) out[i] = v[i];
   return MPCX_OK;
 }
 
@@ -1233,14 +1233,16 @@ int mpcx_assemble_matrix_tiled_f64(const mpcx_integral* integral, const mpcx_mes
     return fail(MPCX_ERR_ARG, "tile plan was built for a different element or matrix");
   if (integral->slave_cells == nullptr && (mpc0->num_slaves > 0 || mpc1->num_slaves > 0))
     return fail(MPCX_ERR_ARG, "the tile path needs the list of slave cells");
+  if (((uintptr_t)A->val & 15) != 0) return fail(MPCX_ERR_ARG, "the tile path needs a 16-byte aligned value array");
   cudaStream_t s = (cudaStream_t)stream;
   const MeshD md{mesh->x, mesh->x_dofmap, mesh->ng, mesh->x_stride};
   const CsrD Ad{(const long long*)A->row_ptr, A->col, A->val};
   if (P->nt > 0)
   {
     const TilePlanD Pd = tile_plan_view(P);
-    const size_t smem = tile_smem_bytes(P->max_nodes, P->max_dests, P->max_slots, false);
-    auto kern = t->tdim == 3 ? k_ctile_matrix_p1<3> : k_ctile_matrix_p1<2>;
+    const size_t smem = tile_smem_bytes(P->max_nodes, P->max_dests, P->max_slots, P->max_runs, P->max_stage, false, P->sym != 0);
+    auto kern = t->tdim == 3 ? (P->sym ? k_ctile_matrix_p1<3, true> : k_ctile_matrix_p1<3, false>)
+                             : (P->sym ? k_ctile_matrix_p1<2, true> : k_ctile_matrix_p1<2, false>);
     rc = cuda_check(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "smem attr");
     if (rc) return rc;
     KernelTimer kt(s);  // dominant kernel of the call
@@ -1286,13 +1288,14 @@ int mpcx_assemble_vector_tiled_f64(const mpcx_integral* integral, const mpcx_mes
     return fail(MPCX_ERR_ARG, "tile plan was built for a different element or space");
   if (integral->slave_cells == nullptr && mpc->num_slaves > 0)
     return fail(MPCX_ERR_ARG, "the tile path needs the list of slave cells");
+  if (((uintptr_t)b & 15) != 0) return fail(MPCX_ERR_ARG, "the tile path needs a 16-byte aligned vector");
   cudaStream_t s = (cudaStream_t)stream;
   const MeshD md{mesh->x, mesh->x_dofmap, mesh->ng, mesh->x_stride};
   const MpcD m = make_mpc(mpc);
   if (P->nt > 0)
   {
     const TilePlanD Pd = tile_plan_view(P);
-    const size_t smem = tile_smem_bytes(P->max_nodes, P->max_dests, P->max_slots, true);
+    const size_t smem = tile_smem_bytes(P->max_nodes, P->max_dests, P->max_slots, P->max_runs, P->max_stage, true, false);
     // coefficient gathered through the very dofmap the plan's rows come from: stage it once per tile row
     const int w_by_row = (!in.coeffs && in.wnodal && in.wmap == dofmap->map) ? 1 : 0;
     auto kern = t->tdim == 3 ? k_ctile_vector_p1<3> : k_ctile_vector_p1<2>;

@@ -17,12 +17,17 @@
 //              shared memory; every thread prefetches its cell's record and the tile's vertex coordinates
 //              are gathered once per tile, not once per cell,
 //     phase 1  thread = cell: closed-form element matrix, each entry stored to its slot,
-//     phase 2  thread = dest: sums its column of the group's [count][32] slot block -- stride-32 reads,
-//              conflict-free, same trip count on every lane -- then ONE red.global.add.f64 per (tile, dest).
+//     phase 2  thread = dest: sums its column of the group's [count][33] slot block -- conflict-free reads, same
+//              trip count on every lane -- and stores the sum to the tile's staging buffer, where the dests lie
+//              in CSR order, cut into runs of (nearly) consecutive entries, gaps and 16-byte padding zero-filled,
+//     phase 3  one TMA bulk reduction per run (cp.reduce.async.bulk.global.shared::cta.add.f64, SASS UBLKRED):
+//              the copy engine adds the run into A.val in L2, about 220 bulk operations per tile instead of
+//              ~2100 red.global.add.f64 lane operations through the LSU (1.3 cycles each, profiles/r01_g: the
+//              REDs were half of the L1/LSU time that bounds the kernel).
 //   A P1 tetrahedron mesh has about 4 distinct dests per cell in a 512-cell tile instead of 16 entries per
-//   cell, so the RED traffic drops 4x, and the gathers of x[x_dofmap] / row_ptr disappear from the hot loop.
-//   (profiles/r01_d -> r01_e: ordering the dests by count and slotting the buffer removed the divergent,
-//   bank-conflicted gather that made phase 2 two thirds of the instructions.)
+//   cell, and the gathers of x[x_dofmap] / row_ptr disappear from the hot loop.
+//   Requirements of phase 3: A.val (b) 16-byte aligned, capacity rounded up to an even number of entries
+//   (a run may be padded with one zero past the last entry).
 //
 // Cells holding slave dofs are excluded (the `skip` flags) and handled by the elimination kernel.
 // The load vector uses the same machinery with 4 entries per cell and dests = row dofs (k_ctile_vector_p1).
@@ -38,27 +43,37 @@ namespace
 // sources of one dest (written by neighbouring cells at the same time) over the banks; lanes still read consecutive slots.
 #define MPCX_CT_GSTRIDE 33
 
+// dests whose CSR positions (row dofs) differ by at most this much share a run; the gaps are zero-filled
+#define MPCX_CT_RUNGAP 4
+#define MPCX_CT_MAXRUNS 2048
+
 struct TilePlan
 {
   int nt = 0, C = 0, ne = 0, ng = 0, nd0 = 0, nd1 = 0;
-  int max_nodes = 0, max_dests = 0, max_slots = 0;
-  long long nrows = 0, n_bulk = 0, total_nodes = 0, total_dests = 0, total_slots = 0, bytes = 0;
+  int max_nodes = 0, max_dests = 0, max_slots = 0, max_runs = 0, max_stage = 0;
+  long long nrows = 0, nvals = 0, n_bulk = 0, total_nodes = 0, total_dests = 0, total_slots = 0, total_runs = 0, bytes = 0;
   int *cell_pos = nullptr, *tile_node_off = nullptr, *node_ids = nullptr, *dest_k = nullptr, *tile_nd = nullptr,
-      *tile_slots = nullptr;
+      *tile_slots = nullptr, *tile_nr = nullptr, *tile_stage = nullptr;
+  int2* runs = nullptr;
   unsigned* ginfo = nullptr;
-  long long* tile_dest_off = nullptr;
-  uint16_t *cell_nodes = nullptr, *dest_cnt = nullptr, *cell_slot = nullptr, *cell_rows = nullptr;
+  long long *tile_dest_off = nullptr, *tile_run_off = nullptr;
+  uint16_t *cell_nodes = nullptr, *dest_spos = nullptr, *dest_spos2 = nullptr, *cell_slot = nullptr, *cell_rows = nullptr;
+  uint8_t* dest_cnt = nullptr;
   int vec = 0;  // 1: vector plan (dests = row dofs, ne = nd0)
+  int sym = 0;  // 1: symmetric matrix plan (upper-triangular records feed both (r, c) and (c, r))
+  int ns = 0;   // slots per cell record: ne, or nd (nd + 1) / 2 for a symmetric plan
 };
 
 struct TilePlanD  // what the kernel sees
 {
-  int C, max_nodes, max_dests, max_slots;
+  int C, max_nodes, max_dests, max_slots, max_runs, max_stage;
   long long n_bulk;
-  const int *cell_pos, *tile_node_off, *node_ids, *dest_k, *tile_nd;
+  const int *cell_pos, *tile_node_off, *node_ids, *dest_k, *tile_nd, *tile_nr, *tile_stage;
+  const int2* runs;
   const unsigned* ginfo;
-  const long long* tile_dest_off;
-  const uint16_t *cell_nodes, *dest_cnt, *cell_slot, *cell_rows;
+  const long long *tile_dest_off, *tile_run_off;
+  const uint16_t *cell_nodes, *dest_spos, *dest_spos2, *cell_slot, *cell_rows;
+  const uint8_t* dest_cnt;
 };
 
 // ------------------------------------------------------------------ setup kernels (cold path)
@@ -147,34 +162,44 @@ __global__ void k_tp_count_bulk(const unsigned long long* __restrict__ sorted_co
   *n_bulk = lo;
 }
 
-// One CTA per tile, thread = cell.  pass 0 sizes the tile (distinct vertices, dests, element-buffer slots),
-// pass 1 (after the host scanned the sizes) writes the plan records.
+// One CTA per tile, thread = cell.  pass 0 sizes the tile (distinct vertices, dest records, runs, element-buffer
+// slots), pass 1 (after the host scanned the sizes) writes the plan records.
 template <int NT, int NEc, int NGc>
 __global__ void __launch_bounds__(NT)
 k_ct_build(int pass, const int* __restrict__ order, long long n_bulk, const int* __restrict__ cells, MeshD mesh,
            const int* __restrict__ dm0, const int* __restrict__ dm1, int nd0, int nd1, int bs0, int bs1,
-           const int8_t* __restrict__ bc0, const int8_t* __restrict__ bc1, CsrD A, int vec, int extra_off,
-           int* __restrict__ tile_nn, int* __restrict__ tile_nd, int* __restrict__ tile_slots,
+           const int8_t* __restrict__ bc0, const int8_t* __restrict__ bc1, CsrD A, long long nrows, int vec, int sym,
+           int extra_off, int* __restrict__ tile_nn, int* __restrict__ tile_nd, int* __restrict__ tile_slots,
+           int* __restrict__ tile_nr, int* __restrict__ tile_stage,
            const int* __restrict__ tile_node_off, const long long* __restrict__ tile_dest_off,
-           int* __restrict__ cell_pos, int* __restrict__ node_ids, uint16_t* __restrict__ cell_nodes,
-           int* __restrict__ dest_k, uint16_t* __restrict__ dest_cnt, unsigned* __restrict__ ginfo,
+           const long long* __restrict__ tile_run_off, int* __restrict__ cell_pos, int* __restrict__ node_ids,
+           uint16_t* __restrict__ cell_nodes, int* __restrict__ dest_k, uint8_t* __restrict__ dest_cnt,
+           uint16_t* __restrict__ dest_spos, uint16_t* __restrict__ dest_spos2, unsigned* __restrict__ ginfo,
+           int2* __restrict__ runs,
            uint16_t* __restrict__ cell_slot, uint16_t* __restrict__ cell_rows)
 {
   using SortD = cub::BlockRadixSort<unsigned, NT, NEc, unsigned short>;
   using SortN = cub::BlockRadixSort<unsigned, NT, NGc, unsigned short>;
   using DiscD = cub::BlockDiscontinuity<unsigned, NT>;
   using Scan = cub::BlockScan<int, NT>;
-  constexpr int N = NT * NEc;  // most sources (and dests) a tile can have
+  constexpr int N = NT * NEc;  // most sources, dests and staging positions a tile can have
+  constexpr int MR = MPCX_CT_MAXRUNS < N ? MPCX_CT_MAXRUNS : N;
   extern __shared__ __align__(16) unsigned char ct_smem[];
   auto& sortd = *reinterpret_cast<typename SortD::TempStorage*>(ct_smem);
   auto& sortn = *reinterpret_cast<typename SortN::TempStorage*>(ct_smem);
   auto& disc = *reinterpret_cast<typename DiscD::TempStorage*>(ct_smem);
   auto& scan = *reinterpret_cast<typename Scan::TempStorage*>(ct_smem);
-  unsigned* dkey = reinterpret_cast<unsigned*>(ct_smem + extra_off);  // [N]     key (CSR entry / row dof) of dest d
+  unsigned* dkey = reinterpret_cast<unsigned*>(ct_smem + extra_off);  // [N]      key (CSR entry / row dof) of dest d, ascending
   int* gbase = reinterpret_cast<int*>(dkey + N);                      // [N/32+1] first slot of dest group g
-  unsigned short* dstart = reinterpret_cast<unsigned short*>(gbase + N / 32 + 1);  // [N+8]  first source rank of d
-  unsigned short* npos = dstart + N + 8;                               // [N]     position of d in count order
-  unsigned short* pcnt = npos + N;                                     // [N+32]  source count at position p
+  int* rk0 = gbase + N / 32 + 1;                                      // [MR]     first (even) key of run r
+  int* rend = rk0 + MR;                                               // [MR]     end (even) key of run r, then its staging offset
+  unsigned short* dstart = reinterpret_cast<unsigned short*>(rend + MR);  // [N+8]  first source rank of d
+  unsigned short* dj = dstart + N + 8;                                 // [N]     staging position of dest d
+  unsigned short* rcnt = dj + N;                                       // [N]     sources of the record of dest d (0: no record)
+  unsigned short* npos = rcnt + N;                                     // [N]     position of d's record in count order
+  unsigned short* pcnt = npos + N;                                     // [N+32]  source count of record p
+  unsigned short* part = pcnt + N + 32;                                // [N]     dest whose record collects d's sources
+  unsigned short* sp2 = part + N;                                      // [N]     staging position of the transposed entry
   const int t = blockIdx.x, cl = threadIdx.x;
   const long long first = (long long)t * NT;
   const int nc_t = (int)((n_bulk - first) < NT ? (n_bulk - first) : NT);
@@ -235,6 +260,7 @@ k_ct_build(int pass, const int* __restrict__ order, long long n_bulk, const int*
   unsigned keys[NEc];
   unsigned short vals[NEc];
   const int n1 = nd1 * bs1;
+  int degenerate = 0;
 #pragma unroll
   for (int e = 0; e < NEc; ++e)
   {
@@ -248,6 +274,7 @@ k_ct_build(int pass, const int* __restrict__ order, long long n_bulk, const int*
       const int r = dm0[(long long)cell * nd0 + p / bs0] * bs0 + p % bs0;
       const int c = dm1[(long long)cell * nd1 + q / bs1] * bs1 + q % bs1;
       // bc rows / columns are zeroed before insertion (cpp/assemble_matrix.cpp:513-533): no source at all
+      if (sym && p != q && r == c) degenerate = 1;  // a cell listing one dof twice: no symmetric plan
       if (!((bc0 && bc0[r]) || (bc1 && bc1[c])))
       {
         const long long k = csr_find(A, r, c);
@@ -287,39 +314,150 @@ k_ct_build(int pass, const int* __restrict__ order, long long n_bulk, const int*
     if (cl == 0) dstart[total] = (unsigned short)vtotal;
   }
   __syncthreads();
-  // Dests in order of DESCENDING source count (stable LSD radix sort, so the plan is deterministic): the lanes of a
-  // warp of the reduction phase then run the same number of iterations (diagonal entries collect ~24 element
-  // entries, off-diagonals 4-6; in CSR order a warp would idle for most of its longest lane's loop).
-  unsigned ckey[NEc];
-  unsigned short cval[NEc];
+
+  // ---- staging layout: the dests in key order, cut into runs wherever two keys differ by more than RUNGAP; a run
+  // covers [even floor of its first key, even ceiling past its last key): gaps and padding stay zero
+  int rid[NEc], nf = 0;
 #pragma unroll
   for (int e = 0; e < NEc; ++e)
   {
     const int d = cl * NEc + e;
-    const int c = d < total ? (int)dstart[d + 1] - (int)dstart[d] : 0;
-    ckey[e] = d < total ? (unsigned)(63 - (c < 63 ? c : 63)) : 64u;
-    cval[e] = (unsigned short)d;
+    rid[e] = (d < total && (d == 0 || dkey[d] - dkey[d - 1] > (unsigned)MPCX_CT_RUNGAP)) ? 1 : 0;
+    nf += rid[e];
   }
-  SortD(sortd).Sort(ckey, cval, 0, 7);
+  int roff, nruns;
+  Scan(scan).ExclusiveSum(nf, roff, nruns);
   __syncthreads();
+  const bool runs_ok = nruns <= MR;
+  {
+    int r = roff - 1;
+#pragma unroll
+    for (int e = 0; e < NEc; ++e)
+    {
+      const int d = cl * NEc + e;
+      const bool hd = rid[e] != 0;
+      if (hd) ++r;
+      rid[e] = r;
+      if (d >= total || !runs_ok) continue;
+      if (hd) rk0[r] = (int)(dkey[d] & ~1u);
+      if (d == total - 1 || dkey[d + 1] - dkey[d] > (unsigned)MPCX_CT_RUNGAP) rend[r] = (int)((dkey[d] + 2u) & ~1u);
+    }
+  }
+  __syncthreads();
+  int rlen[NEc], lsum = 0;
 #pragma unroll
   for (int e = 0; e < NEc; ++e)
   {
-    const int p = cl * NEc + e;  // position in count order
-    if (ckey[e] == 64u) continue;
-    const int d = cval[e];
-    pcnt[p] = (unsigned short)((int)dstart[d + 1] - (int)dstart[d]);
-    npos[d] = (unsigned short)p;
+    const int r = cl * NEc + e;
+    rlen[e] = (runs_ok && r < nruns) ? rend[r] - rk0[r] : 0;
+    lsum += rlen[e];
+  }
+  int loff, stage;
+  Scan(scan).ExclusiveSum(lsum, loff, stage);
+  __syncthreads();
+  bool ok = runs_ok && stage < 65536;  // otherwise the tile does not fit the plan format (the host reports it)
+  if (ok)
+  {
+    const long long ro = pass == 1 ? tile_run_off[t] : 0;
+#pragma unroll
+    for (int e = 0; e < NEc; ++e)
+    {
+      const int r = cl * NEc + e;
+      if (r >= nruns) continue;
+      rend[r] = loff;  // from here on: staging offset of the run
+      if (pass == 1) runs[ro + r] = make_int2(rk0[r], loff | (rlen[e] << 16));
+      loff += rlen[e];
+    }
   }
   __syncthreads();
-  // groups of 32 dests; group g owns the slot block [gbase[g], gbase[g] + 32 * (largest count in g))
-  const int ngroups = (total + 31) >> 5;
+  int bad = degenerate;
+#pragma unroll
+  for (int e = 0; e < NEc; ++e)
+  {
+    const int d = cl * NEc + e;
+    if (d >= total || !ok) continue;
+    dj[d] = (unsigned short)(rend[rid[e]] + (int)dkey[d] - rk0[rid[e]]);
+    rcnt[d] = (unsigned short)((int)dstart[d + 1] - (int)dstart[d]);
+    part[d] = (unsigned short)d;
+  }
+  __syncthreads();
+  // ---- symmetric plan: the record of an upper-triangular dest (row <= col) also feeds the transposed entry, lower
+  // dests get no record; the transposed entry lies in the same tile because the same cells contribute to both
+  if (sym && ok)
+  {
+#pragma unroll
+    for (int e = 0; e < NEc; ++e)
+    {
+      const int d = cl * NEc + e;
+      if (d >= total) continue;
+      const long long k = dkey[d];
+      long long lo = 0, hi = nrows;  // row of entry k: last row with row_ptr <= k
+      while (hi - lo > 1)
+      {
+        const long long mid = (lo + hi) >> 1;
+        if (A.rp[mid] <= k) lo = mid; else hi = mid;
+      }
+      const int a = (int)lo, b = A.col[k];
+      if (a == b) { sp2[d] = dj[d]; continue; }
+      const long long kT = csr_find(A, b, a);
+      int l2 = 0, h2 = total;  // position of the transposed entry among the tile's dests
+      while (l2 < h2)
+      {
+        const int mid = (l2 + h2) >> 1;
+        if ((long long)dkey[mid] < kT) l2 = mid + 1; else h2 = mid;
+      }
+      if (kT < 0 || l2 >= total || (long long)dkey[l2] != kT
+          || (int)dstart[l2 + 1] - (int)dstart[l2] != (int)dstart[d + 1] - (int)dstart[d])
+      {
+        bad = 1;  // pattern or contributions not symmetric after all
+        continue;
+      }
+      if (a < b) sp2[d] = dj[l2];
+      else { rcnt[d] = 0; part[d] = (unsigned short)l2; }
+    }
+  }
+  bad = __syncthreads_or(bad);
+  if (bad) ok = false;
+
+  // ---- records in order of DESCENDING source count (stable LSD radix sort, so the plan is deterministic): the lanes
+  // of a warp of the reduction phase then run the same number of iterations (diagonal entries collect ~24 element
+  // entries, off-diagonals 4-6; in CSR order a warp would idle for most of its longest lane's loop).
+  unsigned ckey[NEc];
+  unsigned short cval[NEc];
+  int nr_local = 0, big = 0;
+#pragma unroll
+  for (int e = 0; e < NEc; ++e)
+  {
+    const int d = cl * NEc + e;
+    const int c = (ok && d < total) ? (int)rcnt[d] : 0;
+    ckey[e] = c > 0 ? (unsigned)(63 - (c < 63 ? c : 63)) : 64u;
+    cval[e] = (unsigned short)d;
+    nr_local += c > 0;
+    big |= c > 255;
+  }
+  SortD(sortd).Sort(ckey, cval, 0, 7);
+  __syncthreads();
+  int dummy, nrec;
+  Scan(scan).ExclusiveSum(nr_local, dummy, nrec);
+  big = __syncthreads_or(big);
+  if (big) ok = false;  // a record count must fit 8 bits
+#pragma unroll
+  for (int e = 0; e < NEc; ++e)
+  {
+    const int p = cl * NEc + e;  // position in count order; the records sort first
+    if (ckey[e] == 64u) continue;
+    pcnt[p] = rcnt[cval[e]];
+    npos[cval[e]] = (unsigned short)p;
+  }
+  __syncthreads();
+  // groups of 32 records; group g owns the slot block [gbase[g], gbase[g] + GSTRIDE * (largest count in g))
+  const int ngroups = (nrec + 31) >> 5;
   int gmax = 0;
   if (cl < ngroups)
     for (int l = 0; l < 32; ++l)
     {
       const int p = cl * 32 + l;
-      const int c = p < total ? (int)pcnt[p] : 0;
+      const int c = p < nrec ? (int)pcnt[p] : 0;
       gmax = c > gmax ? c : gmax;
     }
   int goff, slots;
@@ -327,10 +465,15 @@ k_ct_build(int pass, const int* __restrict__ order, long long n_bulk, const int*
   __syncthreads();
   if (pass == 0)
   {
-    if (cl == 0) { tile_nd[t] = total; tile_slots[t] = slots; }
+    // a tile that does not fit reports a size no launch can satisfy: the host turns it into MPCX_ERR_UNSUPPORTED
+    if (cl == 0)
+    {
+      tile_nd[t] = ok ? nrec : (1 << 30);
+      tile_slots[t] = slots; tile_nr[t] = ok ? nruns : 0; tile_stage[t] = ok ? stage : 0;
+    }
     return;
   }
-  if (slots >= (int)MPCX_CT_NOSLOT) g_dev_err = MPCX_ERR_UNSUPPORTED;  // cannot happen: the host checked the sizes of pass 0
+  if (!ok || slots >= (int)MPCX_CT_NOSLOT) { g_dev_err = MPCX_ERR_UNSUPPORTED; return; }  // the host checked pass 0
   const long long doff = tile_dest_off[t];  // multiple of 128
   if (cl < ngroups)
   {
@@ -341,40 +484,55 @@ k_ct_build(int pass, const int* __restrict__ order, long long n_bulk, const int*
   for (int e = 0; e < NEc; ++e)
   {
     if (ckey[e] == 64u) continue;
-    const int p = cl * NEc + e;
-    dest_k[doff + p] = (int)dkey[cval[e]];
-    dest_cnt[doff + p] = pcnt[p];
+    const int p = cl * NEc + e, d = cval[e];
+    dest_cnt[doff + p] = (uint8_t)pcnt[p];
+    dest_spos[doff + p] = dj[d];
+    if (sym) dest_spos2[doff + p] = sp2[d];
+    if (vec) dest_k[doff + p] = (int)dkey[d];  // row dof: lets the kernel stage per-row data once per tile
   }
   __syncthreads();
   {
+    constexpr int NVc = NGc;                                  // P1: entries form an NVc x NVc matrix
+    const int NS = sym ? NVc * (NVc + 1) / 2 : NEc;           // slots per cell record
     int d = hoff - 1;  // items before the thread's first head continue the previous thread's dest
 #pragma unroll
     for (int e = 0; e < NEc; ++e)
     {
-      if (keys[e] == MPCX_CT_INVALID)
+      const bool valid = keys[e] != MPCX_CT_INVALID;
+      if (valid && head[e]) ++d;
+      const int cidx = vals[e] / NEc, ent = vals[e] - cidx * NEc;
+      int si = ent;
+      if (sym)
       {
-        cell_slot[first * NEc + vals[e]] = (uint16_t)slots;  // bc-zeroed entry: stored to the spare slot nobody reads
-        continue;
+        const int i = ent / NVc, j = ent - i * NVc;
+        if (i > j) continue;  // the kernel stores the upper triangle only
+        si = i * NVc - (i * (i - 1)) / 2 + (j - i);
       }
-      if (head[e]) ++d;
-      const int i = cl * NEc + e - (int)dstart[d];  // i-th source of dest d
-      const int p = npos[d];
-      cell_slot[first * NEc + vals[e]] = (uint16_t)(gbase[p >> 5] + MPCX_CT_GSTRIDE * i + (p & 31));
-      if (vec)  // tile-local row of (cell, local entry): lets the kernel stage per-row data once per tile
-        cell_rows[first * NEc + vals[e]] = (uint16_t)p;
+      uint16_t sl = (uint16_t)slots;  // bc-zeroed entry: stored to the spare slot nobody reads
+      if (valid)
+      {
+        const int i_src = cl * NEc + e - (int)dstart[d];  // i-th source of dest d (same cell order in the transposed dest)
+        const int p = npos[part[d]];
+        sl = (uint16_t)(gbase[p >> 5] + MPCX_CT_GSTRIDE * i_src + (p & 31));
+        if (vec) cell_rows[first * NEc + vals[e]] = (uint16_t)p;
+      }
+      cell_slot[first * NS + cidx * NS + si] = sl;
     }
   }
 }
 
 // ------------------------------------------------------------------ the assembly kernels
-// Shared memory of one tile (sections 16-byte aligned; dest arrays sized for whole groups of 128 records):
-//   Xs[max_nodes][3] f64 | ebuf[max_slots + 1] f64 | (vector: fs[max_dests] f64) | dk[max_dests] i32 |
-//   gi[max_dests/32] u32 | dcnt[max_dests] u16 | mbarrier
-__host__ __device__ inline size_t tile_smem_bytes(int max_nodes, int max_dests, int max_slots, bool vec)
+// Shared memory of one tile (sections 16-byte aligned; record arrays sized for whole groups of 128 records):
+//   Xs[max_nodes][3] f64 | stage[max_stage] f64 | ebuf[max_slots + 1] f64 | (vector: fs[max_dests] f64) |
+//   runs[max_runs] int2 | gi[max_dests/32] u32 | spos[max_dests] u16 | (sym: spos2[max_dests] u16) |
+//   dcnt[max_dests] u8 | mbarrier
+__host__ __device__ inline size_t tile_smem_bytes(int max_nodes, int max_dests, int max_slots, int max_runs, int max_stage,
+                                                  bool vec, bool sym)
 {
   auto al = [](size_t b) { return (b + 15) & ~(size_t)15; };
-  return al(24 * (size_t)max_nodes) + al(8 * (size_t)(max_slots + 1)) + (vec ? al(8 * (size_t)max_dests) : 0) + al(4 * (size_t)max_dests)
-         + al(4 * (size_t)(max_dests / 32)) + al(2 * (size_t)max_dests) + 16;
+  return al(24 * (size_t)max_nodes) + al(8 * (size_t)max_stage) + al(8 * (size_t)(max_slots + 1))
+         + (vec ? al(8 * (size_t)max_dests) : 0) + al(8 * (size_t)max_runs) + al(4 * (size_t)(max_dests / 32))
+         + (sym ? 2 : 1) * al(2 * (size_t)max_dests) + al((size_t)max_dests) + 16;
 }
 
 // ---- 1-D TMA (cp.async.bulk global -> shared, completion on an mbarrier) for the contiguous plan records
@@ -409,46 +567,64 @@ __device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned pari
       : "memory");
 }
 
+__device__ __forceinline__ void tma_reduce_add_f64(double* dst, const double* src_smem, unsigned bytes)
+{
+  asm volatile("cp.reduce.async.bulk.global.shared::cta.bulk_group.add.f64 [%0], [%1], %2;" ::"l"(dst), "r"(smem_u32(src_smem)),
+               "r"(bytes)
+               : "memory");
+}
+
 struct TileSmem
 {
-  double *Xs, *ebuf, *fs;
-  int* dk;
+  double *Xs, *stage, *ebuf, *fs;
+  int2* runs;
   unsigned* gi;
-  uint16_t* dcnt;
+  uint16_t *spos, *spos2;
+  uint8_t* dcnt;
   unsigned long long* bar;
 };
 
-__device__ __forceinline__ TileSmem tile_carve(unsigned char* sp, const TilePlanD& P, bool vec)
+__device__ __forceinline__ TileSmem tile_carve(unsigned char* sp, const TilePlanD& P, bool vec, bool sym)
 {
   auto al = [](size_t b) { return (b + 15) & ~(size_t)15; };
   TileSmem S;
   S.Xs = reinterpret_cast<double*>(sp); sp += al(24 * (size_t)P.max_nodes);
+  S.stage = reinterpret_cast<double*>(sp); sp += al(8 * (size_t)P.max_stage);
   S.ebuf = reinterpret_cast<double*>(sp); sp += al(8 * (size_t)(P.max_slots + 1));
   S.fs = reinterpret_cast<double*>(sp); if (vec) sp += al(8 * (size_t)P.max_dests);
-  S.dk = reinterpret_cast<int*>(sp); sp += al(4 * (size_t)P.max_dests);
+  S.runs = reinterpret_cast<int2*>(sp); sp += al(8 * (size_t)P.max_runs);
   S.gi = reinterpret_cast<unsigned*>(sp); sp += al(4 * (size_t)(P.max_dests / 32));
-  S.dcnt = reinterpret_cast<uint16_t*>(sp); sp += al(2 * (size_t)P.max_dests);
+  S.spos = reinterpret_cast<uint16_t*>(sp); sp += al(2 * (size_t)P.max_dests);
+  S.spos2 = reinterpret_cast<uint16_t*>(sp); if (sym) sp += al(2 * (size_t)P.max_dests);
+  S.dcnt = reinterpret_cast<uint8_t*>(sp); sp += al((size_t)P.max_dests);
   S.bar = reinterpret_cast<unsigned long long*>(sp);
   return S;
 }
 
-// phase 0, shared by both kernels: TMA of the dest records (thread 0) + gather of the tile's vertex coordinates
+// phase 0, shared by both kernels: TMA of the record / run arrays (thread 0), zero fill of the staging buffer and
+// gather of the tile's vertex coordinates
+template <bool SYM>
 __device__ __forceinline__ void tile_stage(const TileSmem& S, const TilePlanD& P, const MeshD& mesh, int t, int tid,
-                                           long long d0, int nd_t)
+                                           long long d0, int nd_t, int nr_t)
 {
   constexpr int NT = MPCX_TILE_THREADS;
   if (tid == 0)
   {
     mbar_init(S.bar, 1);
-    const unsigned nd8 = (unsigned)((nd_t + 7) & ~7), ng4 = (unsigned)((((nd_t + 31) >> 5) + 3) & ~3);
-    mbar_expect_tx(S.bar, nd8 * 6 + ng4 * 4);
-    if (nd8)
+    const unsigned nd16 = (unsigned)((nd_t + 15) & ~15), ng4 = (unsigned)((((nd_t + 31) >> 5) + 3) & ~3);
+    const unsigned nr2 = (unsigned)((nr_t + 1) & ~1);
+    mbar_expect_tx(S.bar, nd16 * (SYM ? 5 : 3) + ng4 * 4 + nr2 * 8);
+    if (nd16)
     {
-      tma_load_1d(S.dk, P.dest_k + d0, nd8 * 4, S.bar);
-      tma_load_1d(S.dcnt, P.dest_cnt + d0, nd8 * 2, S.bar);
+      tma_load_1d(S.dcnt, P.dest_cnt + d0, nd16, S.bar);
+      tma_load_1d(S.spos, P.dest_spos + d0, nd16 * 2, S.bar);
+      if (SYM) tma_load_1d(S.spos2, P.dest_spos2 + d0, nd16 * 2, S.bar);
       tma_load_1d(S.gi, P.ginfo + (d0 >> 5), ng4 * 4, S.bar);
+      tma_load_1d(S.runs, P.runs + __ldg(P.tile_run_off + t), nr2 * 8, S.bar);
     }
   }
+  const int st_t = __ldg(P.tile_stage + t);  // even
+  for (int i = tid; i < (st_t >> 1); i += NT) reinterpret_cast<double2*>(S.stage)[i] = make_double2(0.0, 0.0);
   const int n0 = __ldg(P.tile_node_off + t), nn_t = __ldg(P.tile_node_off + t + 1) - n0;
   for (int i = tid; i < nn_t; i += NT)
   {
@@ -467,59 +643,90 @@ __device__ __forceinline__ void tile_stage(const TileSmem& S, const TilePlanD& P
   }
 }
 
-// phase 2, shared by both kernels: dest k = column (k & 31) of its group's slot block.  The trip count is the
-// group's largest count (warp-uniform: no divergence bookkeeping); rows past the lane's own count are not read.
-__device__ __forceinline__ double tile_reduce(const TileSmem& S, int k)
+// phases 2 and 3, shared by both kernels.  Record k = column (k & 31) of its group's slot block; the trip count is
+// the group's largest count (warp-uniform: no divergence bookkeeping), rows past the lane's own count are not
+// read.  The sum goes to the record's staging position (and to the transposed entry's in a symmetric plan), then
+// one bulk reduction per run.
+template <bool SYM>
+__device__ __forceinline__ void tile_reduce_and_add(const TileSmem& S, int tid, int nd_t, int nr_t, double* __restrict__ out)
 {
-  const unsigned g = S.gi[k >> 5];
-  const double* e = S.ebuf + (g & 0xffffu) + (k & 31);
-  const int cmax = (int)(g >> 16), cnt = S.dcnt[k];
-  double s0 = 0.0, s1 = 0.0;
-  int i = 0;
-#pragma unroll 1
-  for (; i + 2 <= cmax; i += 2, e += 2 * MPCX_CT_GSTRIDE)
+  constexpr int NT = MPCX_TILE_THREADS;
+  for (int k = tid; k < nd_t; k += NT)
   {
+    const unsigned g = S.gi[k >> 5];
+    const double* e = S.ebuf + (g & 0xffffu) + (k & 31);
+    const int cmax = (int)(g >> 16), cnt = S.dcnt[k];
+    double s0 = 0.0, s1 = 0.0;
+    int i = 0;
+#pragma unroll 1
+    for (; i + 2 <= cmax; i += 2, e += 2 * MPCX_CT_GSTRIDE)
+    {
+      if (i < cnt) s0 += e[0];
+      if (i + 1 < cnt) s1 += e[MPCX_CT_GSTRIDE];
+    }
     if (i < cnt) s0 += e[0];
-    if (i + 1 < cnt) s1 += e[MPCX_CT_GSTRIDE];
+    const double v = s0 + s1;
+    S.stage[S.spos[k]] = v;
+    if (SYM) S.stage[S.spos2[k]] = v;
   }
-  if (i < cnt) s0 += e[0];
-  return s0 + s1;
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // staging writes -> visible to the copy engine
+  __syncthreads();
+  if (tid < nr_t)
+  {
+    for (int r = tid; r < nr_t; r += NT)
+    {
+      const int2 rr = S.runs[r];
+      tma_reduce_add_f64(out + rr.x, S.stage + (rr.y & 0xffff), (unsigned)(rr.y >> 16) * 8u);
+    }
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+    asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");  // the staging buffer must outlive the reads
+  }
 }
 
-template <int TD>
+// SYM: the element matrix is symmetric and so are dofmaps and bc markers of both sides: only the upper triangle is
+// stored and summed, every record feeds entry (r, c) and entry (c, r).
+template <int TD, bool SYM>
 __global__ void __launch_bounds__(MPCX_TILE_THREADS)
 k_ctile_matrix_p1(TilePlanD P, IntD in, MeshD mesh, CsrD A)
 {
-  constexpr int NV = TD + 1, NE = NV * NV, NT = MPCX_TILE_THREADS;
+  constexpr int NV = TD + 1, NS = SYM ? NV * (NV + 1) / 2 : NV * NV, NT = MPCX_TILE_THREADS;
   extern __shared__ __align__(16) unsigned char tile_smem[];
-  const TileSmem S = tile_carve(tile_smem, P, false);
+  const TileSmem S = tile_carve(tile_smem, P, false, SYM);
   const int t = blockIdx.x, tid = threadIdx.x;
   const long long first = (long long)t * NT;
   const int nc_t = (int)((P.n_bulk - first) < NT ? (P.n_bulk - first) : NT);
   const long long d0 = __ldg(P.tile_dest_off + t);
-  const int nd_t = __ldg(P.tile_nd + t);
+  const int nd_t = __ldg(P.tile_nd + t), nr_t = __ldg(P.tile_nr + t);
 
-  // this thread's cell record: tile-local vertices and the slot of each element entry (coalesced 8 + 32 bytes)
-  uint16_t cn[NV], slot[NE];
+  // this thread's cell record: tile-local vertices and the slot of each stored element entry (coalesced reads)
+  uint16_t cn[NV], slot[NS];
   if (NV == 4)
   {
     const uint2 a = __ldg(reinterpret_cast<const uint2*>(P.cell_nodes) + first + tid);
     cn[0] = a.x & 0xffff; cn[1] = a.x >> 16; cn[2] = a.y & 0xffff; cn[3] = a.y >> 16;
-    const uint4* sp = reinterpret_cast<const uint4*>(P.cell_slot) + (first + tid) * 2;
-    const uint4 s0 = __ldg(sp), s1 = __ldg(sp + 1);
-    const unsigned w[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
-#pragma unroll
-    for (int e = 0; e < 8; ++e) { slot[2 * e] = w[e] & 0xffff; slot[2 * e + 1] = w[e] >> 16; }
   }
   else
   {
 #pragma unroll
     for (int v = 0; v < NV; ++v) cn[v] = __ldg(P.cell_nodes + (first + tid) * NV + v);
-#pragma unroll
-    for (int e = 0; e < NE; ++e) slot[e] = __ldg(P.cell_slot + (first + tid) * NE + e);
   }
-  tile_stage(S, P, mesh, t, tid, d0, nd_t);
-  __syncthreads();  // Xs complete; the mbarrier initialisation is visible to every thread
+  if (NS % 2 == 0)
+  {
+    const unsigned* sp = reinterpret_cast<const unsigned*>(P.cell_slot) + (first + tid) * (NS / 2);
+#pragma unroll
+    for (int e = 0; e < NS / 2; ++e)
+    {
+      const unsigned w = __ldg(sp + e);
+      slot[2 * e] = w & 0xffff; slot[2 * e + 1] = w >> 16;
+    }
+  }
+  else
+  {
+#pragma unroll
+    for (int e = 0; e < NS; ++e) slot[e] = __ldg(P.cell_slot + (first + tid) * NS + e);
+  }
+  tile_stage<SYM>(S, P, mesh, t, tid, d0, nd_t, nr_t);
+  __syncthreads();  // Xs complete, staging buffer zeroed; the mbarrier initialisation is visible to every thread
 
   // phase 1: thread = cell; element matrix entries to their slots
   if (tid < nc_t)
@@ -542,35 +749,33 @@ k_ctile_matrix_p1(TilePlanD P, IntD in, MeshD mesh, CsrD A)
       p1_load_w<TD>(in, index, in.cells ? __ldg(in.cells + index) : (int)index, w);
     }
     p1_element<TD>(in.kernel, G, in.c, w, Ae);
+    int si = 0;
 #pragma unroll
     for (int i = 0; i < NV; ++i)
 #pragma unroll
-      for (int j = 0; j < NV; ++j)
-        S.ebuf[slot[i * NV + j]] = Ae[i][j];  // bc-zeroed entries go to the tile's spare slot
+      for (int j = SYM ? i : 0; j < NV; ++j) S.ebuf[slot[si++]] = Ae[i][j];  // bc-zeroed entries go to the tile's spare slot
   }
   __syncthreads();
   mbar_wait(S.bar, 0);
-
-  // phase 2: thread = dest, one RED per (tile, dest)
-  for (int k = tid; k < nd_t; k += NT) atomicAdd(A.val + S.dk[k], tile_reduce(S, k));
+  tile_reduce_and_add<SYM>(S, tid, nd_t, nr_t, A.val);
 }
 
 // Load vector b_i = c0 |K|/((d+1)(d+2)) (f_i + sum_j f_j) (cpp/assemble_vector.cpp:163-185 with the P1 source
-// kernel): NV entries per cell, dests = the row dofs of the tile, one red.global.add.f64 per (tile, row) instead
-// of one per (cell, vertex).  When the coefficient lives in the test space (w_by_row) its values are staged once
-// per tile row.
+// kernel): NV entries per cell, dests = the row dofs of the tile, one bulk reduction per run of rows instead of
+// one red.global.add.f64 per (cell, vertex).  When the coefficient lives in the test space (w_by_row) its values
+// are staged once per tile row.
 template <int TD>
 __global__ void __launch_bounds__(MPCX_TILE_THREADS)
 k_ctile_vector_p1(TilePlanD P, IntD in, MeshD mesh, int w_by_row, double* __restrict__ b)
 {
   constexpr int NV = TD + 1, NT = MPCX_TILE_THREADS;
   extern __shared__ __align__(16) unsigned char tile_smem[];
-  const TileSmem S = tile_carve(tile_smem, P, true);
+  const TileSmem S = tile_carve(tile_smem, P, true, false);
   const int t = blockIdx.x, tid = threadIdx.x;
   const long long first = (long long)t * NT;
   const int nc_t = (int)((P.n_bulk - first) < NT ? (P.n_bulk - first) : NT);
   const long long d0 = __ldg(P.tile_dest_off + t);
-  const int nd_t = __ldg(P.tile_nd + t);
+  const int nd_t = __ldg(P.tile_nd + t), nr_t = __ldg(P.tile_nr + t);
 
   uint16_t cn[NV], slot[NV], crow[NV];
   if (NV == 4)
@@ -592,7 +797,7 @@ k_ctile_vector_p1(TilePlanD P, IntD in, MeshD mesh, int w_by_row, double* __rest
       crow[v] = __ldg(P.cell_rows + (first + tid) * NV + v);
     }
   }
-  tile_stage(S, P, mesh, t, tid, d0, nd_t);
+  tile_stage<false>(S, P, mesh, t, tid, d0, nd_t, nr_t);
   if (w_by_row)  // one coefficient read per tile row (straight from the plan: no wait on the TMA)
     for (int k = tid; k < nd_t; k += NT) S.fs[k] = __ldg(in.wnodal + __ldg(P.dest_k + d0 + k));
   __syncthreads();
@@ -629,8 +834,7 @@ k_ctile_vector_p1(TilePlanD P, IntD in, MeshD mesh, int w_by_row, double* __rest
   }
   __syncthreads();
   mbar_wait(S.bar, 0);
-
-  for (int k = tid; k < nd_t; k += NT) atomicAdd(b + S.dk[k], tile_reduce(S, k));
+  tile_reduce_and_add<false>(S, tid, nd_t, nr_t, b);
 }
 
 // ------------------------------------------------------------------ host side of the setup
@@ -650,15 +854,18 @@ void tile_plan_free(TilePlan* P)
 {
   if (!P) return;
   cudaFree(P->cell_pos); cudaFree(P->tile_node_off); cudaFree(P->node_ids); cudaFree(P->dest_k); cudaFree(P->tile_nd);
-  cudaFree(P->tile_slots); cudaFree(P->ginfo); cudaFree(P->tile_dest_off); cudaFree(P->cell_nodes); cudaFree(P->dest_cnt);
-  cudaFree(P->cell_slot); cudaFree(P->cell_rows);
+  cudaFree(P->tile_slots); cudaFree(P->tile_nr); cudaFree(P->tile_stage); cudaFree(P->runs); cudaFree(P->ginfo);
+  cudaFree(P->tile_dest_off); cudaFree(P->tile_run_off); cudaFree(P->cell_nodes); cudaFree(P->dest_cnt); cudaFree(P->dest_spos);
+  cudaFree(P->dest_spos2); cudaFree(P->cell_slot); cudaFree(P->cell_rows);
   delete P;
 }
 
 inline TilePlanD tile_plan_view(const TilePlan* P)
 {
-  return TilePlanD{P->C, P->max_nodes, P->max_dests, P->max_slots, P->n_bulk, P->cell_pos, P->tile_node_off, P->node_ids,
-                   P->dest_k, P->tile_nd, P->ginfo, P->tile_dest_off, P->cell_nodes, P->dest_cnt, P->cell_slot, P->cell_rows};
+  return TilePlanD{P->C, P->max_nodes, P->max_dests, P->max_slots, P->max_runs, P->max_stage, P->n_bulk, P->cell_pos,
+                   P->tile_node_off, P->node_ids, P->dest_k, P->tile_nd, P->tile_nr, P->tile_stage, P->runs, P->ginfo,
+                   P->tile_dest_off, P->tile_run_off, P->cell_nodes, P->dest_spos, P->dest_spos2, P->cell_slot, P->cell_rows,
+                   P->dest_cnt};
 }
 
 inline unsigned tp_grid(long long n, int b = 256) { return (unsigned)((n + b - 1) / b > 0 ? (n + b - 1) / b : 1); }
@@ -674,12 +881,15 @@ cudaError_t ct_build_launch(int pass, cudaStream_t s, const int* order, const in
   smem = std::max(smem, sizeof(typename cub::BlockDiscontinuity<unsigned, NT>::TempStorage));
   smem = (std::max(smem, sizeof(typename cub::BlockScan<int, NT>::TempStorage)) + 15) & ~(size_t)15;
   const int extra_off = (int)smem;
-  smem += (size_t)N * 4 + (size_t)(N / 32 + 1) * 4 + ((size_t)N + 8 + N + N + 32) * 2 + 16;  // dkey, gbase, dstart, npos, pcnt
+  constexpr int MR = MPCX_CT_MAXRUNS < N ? MPCX_CT_MAXRUNS : N;
+  // dkey, gbase, rk0, rend | dstart, dj, rcnt, npos, pcnt, part, sp2
+  smem += (size_t)N * 4 + (size_t)(N / 32 + 1) * 4 + 2 * (size_t)MR * 4 + ((size_t)N + 8 + 3 * (size_t)N + N + 32 + 2 * (size_t)N) * 2 + 16;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
   kern<<<P->nt, NT, smem, s>>>(pass, order, P->n_bulk, cells, md, dm0->map, dm1->map, dm0->nd, dm1->nd, dm0->bs, dm1->bs, bc0,
-                               bc1, A, P->vec, extra_off, tile_nn, P->tile_nd, P->tile_slots, P->tile_node_off,
-                               P->tile_dest_off, P->cell_pos, P->node_ids, P->cell_nodes, P->dest_k, P->dest_cnt, P->ginfo,
+                               bc1, A, P->nrows, P->vec, P->sym, extra_off, tile_nn, P->tile_nd, P->tile_slots, P->tile_nr,
+                               P->tile_stage, P->tile_node_off, P->tile_dest_off, P->tile_run_off, P->cell_pos, P->node_ids,
+                               P->cell_nodes, P->dest_k, P->dest_cnt, P->dest_spos, P->dest_spos2, P->ginfo, P->runs,
                                P->cell_slot, P->cell_rows);
   return cudaGetLastError();
 }
@@ -697,14 +907,22 @@ int tile_plan_build(const mpcx_mesh* mesh, const mpcx_dofmap* dm0, const mpcx_do
   constexpr int C = MPCX_TILE_THREADS;
   P->vec = vec ? 1 : 0;
   P->C = C; P->nd0 = dm0->nd; P->nd1 = dm1->nd; P->ng = mesh->ng; P->nrows = vec ? dm0->num_dofs : Acsr->num_rows;
+  P->nvals = vec ? dm0->num_dofs : Acsr->nnz;
+  // symmetric plan: same dofmap and bc markers on both sides (every tile kernel's element matrix is symmetric)
+  // (MPCX_TILE_SYM=0 forces the general plan, read at every plan creation: used by the tests)
+  const char* sym_env = getenv("MPCX_TILE_SYM");
+  P->sym = (!vec && dm0->map == dm1->map && dm0->bs == 1 && dm1->bs == 1 && bc0 == bc1 && Acsr->num_rows < (1ll << 31)
+            && !(sym_env && sym_env[0] == '0')) ? 1 : 0;
   P->ne = vec ? dm0->nd : dm0->nd * dm0->bs * dm1->nd * dm1->bs;
+  P->ns = P->sym ? dm0->nd * (dm0->nd + 1) / 2 : P->ne;
   unsigned long long *mm = nullptr, *code = nullptr, *code2 = nullptr;
   int *iota = nullptr, *order = nullptr, *tile_nn = nullptr;
   long long* nb_dev = nullptr;
   void* tmp = nullptr;
   size_t tmp_bytes = 0, tb = 0;
-  std::vector<int> h_nn, h_nd, h_sl, noff;
-  std::vector<long long> h_doff;
+  std::vector<int> h_nn, h_nd, h_sl, h_nr, h_st, noff;
+  std::vector<long long> h_doff, h_roff;
+  bool fits = true;
   long long alloc_dests = 0;
   BBox bb;
   int variant = 0;
@@ -760,16 +978,25 @@ int tile_plan_build(const mpcx_mesh* mesh, const mpcx_dofmap* dm0, const mpcx_do
 
   // 3. pass 0: sizes of every tile
   TP_CK(tp_alloc(&tile_nn, P->nt)); TP_CK(tp_alloc(&P->tile_nd, P->nt)); TP_CK(tp_alloc(&P->tile_slots, P->nt));
+  TP_CK(tp_alloc(&P->tile_nr, P->nt)); TP_CK(tp_alloc(&P->tile_stage, P->nt));
   TP_CK(build(0));
-  h_nn.resize(P->nt); h_nd.resize(P->nt); h_sl.resize(P->nt);
+  h_nn.resize(P->nt); h_nd.resize(P->nt); h_sl.resize(P->nt); h_nr.resize(P->nt); h_st.resize(P->nt);
+  TP_CK(cudaMemcpyAsync(h_st.data(), P->tile_stage, sizeof(int) * P->nt, cudaMemcpyDeviceToHost, s));
+  TP_CK(cudaMemcpyAsync(h_nr.data(), P->tile_nr, sizeof(int) * P->nt, cudaMemcpyDeviceToHost, s));
   TP_CK(cudaMemcpyAsync(h_nn.data(), tile_nn, sizeof(int) * P->nt, cudaMemcpyDeviceToHost, s));
   TP_CK(cudaMemcpyAsync(h_nd.data(), P->tile_nd, sizeof(int) * P->nt, cudaMemcpyDeviceToHost, s));
   TP_CK(cudaMemcpyAsync(h_sl.data(), P->tile_slots, sizeof(int) * P->nt, cudaMemcpyDeviceToHost, s));
   TP_CK(cudaStreamSynchronize(s));
   noff.assign(P->nt + 1, 0);
   h_doff.assign(P->nt + 1, 0);
+  h_roff.assign(P->nt + 1, 0);
   for (int t = 0; t < P->nt; ++t)
   {
+    if (h_nd[t] >= (1 << 30)) { fits = false; break; }  // too many runs / staging positions for the plan format
+    h_roff[t + 1] = h_roff[t] + ((h_nr[t] + 1) & ~1);
+    P->total_runs += h_nr[t];
+    P->max_runs = std::max(P->max_runs, h_nr[t]);
+    P->max_stage = std::max(P->max_stage, h_st[t]);
     noff[t + 1] = noff[t] + h_nn[t];
     h_doff[t + 1] = h_doff[t] + ((h_nd[t] + 127) & ~127);  // 16-byte aligned dest / group records for the TMA bulk copies
     P->total_dests += h_nd[t];
@@ -782,25 +1009,37 @@ int tile_plan_build(const mpcx_mesh* mesh, const mpcx_dofmap* dm0, const mpcx_do
   alloc_dests = h_doff[P->nt] + 128;
   P->max_nodes = (P->max_nodes + 1) & ~1;
   P->max_dests = (P->max_dests + 127) & ~127;  // the TMA copies move whole groups of records
-  if (P->max_slots >= (int)MPCX_CT_NOSLOT || tile_smem_bytes(P->max_nodes, P->max_dests, P->max_slots, vec) > 200 * 1024)
+  P->max_runs = (P->max_runs + 1) & ~1;
+  if (!fits || P->max_slots >= (int)MPCX_CT_NOSLOT
+      || tile_smem_bytes(P->max_nodes, P->max_dests, P->max_slots, P->max_runs, P->max_stage, vec, P->sym != 0) > 226 * 1024)
   {
     rc = fail(MPCX_ERR_UNSUPPORTED, "tile plan: a tile needs more element-buffer slots than shared memory holds");
     goto done;
   }
   TP_CK(tp_alloc(&P->tile_node_off, P->nt + 1)); TP_CK(tp_alloc(&P->tile_dest_off, P->nt + 1));
+  TP_CK(tp_alloc(&P->tile_run_off, P->nt + 1));
+  TP_CK(cudaMemcpyAsync(P->tile_run_off, h_roff.data(), sizeof(long long) * (P->nt + 1), cudaMemcpyHostToDevice, s));
   TP_CK(cudaMemcpyAsync(P->tile_node_off, noff.data(), sizeof(int) * (P->nt + 1), cudaMemcpyHostToDevice, s));
   TP_CK(cudaMemcpyAsync(P->tile_dest_off, h_doff.data(), sizeof(long long) * (P->nt + 1), cudaMemcpyHostToDevice, s));
   TP_CK(cudaStreamSynchronize(s));
   // 4. pass 1: the records
   TP_CK(tp_alloc(&P->cell_pos, (long long)P->nt * C)); TP_CK(tp_alloc(&P->node_ids, P->total_nodes));
-  TP_CK(tp_alloc(&P->cell_nodes, (long long)P->nt * C * P->ng)); TP_CK(tp_alloc(&P->dest_k, alloc_dests));
-  TP_CK(tp_alloc(&P->dest_cnt, alloc_dests)); TP_CK(tp_alloc(&P->ginfo, alloc_dests / 32));
-  TP_CK(tp_alloc(&P->cell_slot, (long long)P->nt * C * P->ne));
+  TP_CK(tp_alloc(&P->cell_nodes, (long long)P->nt * C * P->ng)); TP_CK(tp_alloc(&P->dest_k, vec ? alloc_dests : 1));
+  TP_CK(tp_alloc(&P->dest_cnt, alloc_dests)); TP_CK(tp_alloc(&P->dest_spos, alloc_dests));
+  TP_CK(tp_alloc(&P->ginfo, alloc_dests / 32)); TP_CK(tp_alloc(&P->runs, h_roff[P->nt] + 2));
+  TP_CK(cudaMemsetAsync(P->runs, 0, sizeof(int2) * (size_t)(h_roff[P->nt] + 2), s));
+  TP_CK(cudaMemsetAsync(P->dest_spos, 0, sizeof(uint16_t) * (size_t)alloc_dests, s));
+  TP_CK(tp_alloc(&P->cell_slot, (long long)P->nt * C * P->ns));
+  if (P->sym)
+  {
+    TP_CK(tp_alloc(&P->dest_spos2, alloc_dests));
+    TP_CK(cudaMemsetAsync(P->dest_spos2, 0, sizeof(uint16_t) * (size_t)alloc_dests, s));
+  }
   TP_CK(cudaMemsetAsync(P->cell_nodes, 0, sizeof(uint16_t) * (size_t)P->nt * C * P->ng, s));
-  TP_CK(cudaMemsetAsync(P->dest_k, 0, sizeof(int) * (size_t)alloc_dests, s));
-  TP_CK(cudaMemsetAsync(P->dest_cnt, 0, sizeof(uint16_t) * (size_t)alloc_dests, s));
+  TP_CK(cudaMemsetAsync(P->dest_k, 0xff, sizeof(int) * (size_t)(vec ? alloc_dests : 1), s));  // fillers: -1
+  TP_CK(cudaMemsetAsync(P->dest_cnt, 0, sizeof(uint8_t) * (size_t)alloc_dests, s));
   TP_CK(cudaMemsetAsync(P->ginfo, 0, sizeof(unsigned) * (size_t)(alloc_dests / 32), s));
-  TP_CK(cudaMemsetAsync(P->cell_slot, 0xff, sizeof(uint16_t) * (size_t)P->nt * C * P->ne, s));  // MPCX_CT_NOSLOT
+  TP_CK(cudaMemsetAsync(P->cell_slot, 0, sizeof(uint16_t) * (size_t)P->nt * C * P->ns, s));
   if (vec)
   {
     TP_CK(tp_alloc(&P->cell_rows, (long long)P->nt * C * P->ne));
@@ -809,8 +1048,10 @@ int tile_plan_build(const mpcx_mesh* mesh, const mpcx_dofmap* dm0, const mpcx_do
   TP_CK(build(1));
   TP_CK(cudaStreamSynchronize(s));
   // bytes one assembly reads from the plan
-  P->bytes = (long long)sizeof(uint16_t) * ((long long)P->nt * C * (P->ne * (vec ? 2 : 1) + P->ng) + P->total_dests)
-             + (long long)sizeof(int) * (P->total_nodes + P->total_dests + P->total_dests / 32) + (long long)(P->nt + 1) * 16;
+  P->bytes = (long long)sizeof(uint16_t) * ((long long)P->nt * C * (P->ns + (vec ? P->ne : 0) + P->ng) + (P->sym ? 2 : 1) * P->total_dests)
+             + P->total_dests
+             + (long long)sizeof(int) * (P->total_nodes + (vec ? P->total_dests : 0) + P->total_dests / 32 + 2 * P->total_runs)
+             + (long long)P->nt * 32;
 
 done:
   cudaFree(mm); cudaFree(code); cudaFree(code2); cudaFree(iota); cudaFree(order); cudaFree(tile_nn);

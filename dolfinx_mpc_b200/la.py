@@ -29,7 +29,9 @@ class Matrix:
         self.nnz = int(self.row_ptr_host[-1])
         self.row_ptr = _dev.to_dev(self.row_ptr_host)
         self.col = _dev.to_dev(self.col_host)
-        self.val = torch.zeros(self.nnz, dtype=torch.float64, device=_dev.device())
+        # capacity rounded up to an even count: the tile kernels add whole 16-byte runs (include/mpcx.h)
+        self._val_storage = torch.zeros(self.nnz + (self.nnz & 1), dtype=torch.float64, device=_dev.device())
+        self.val = self._val_storage[: self.nnz]
         if max_block_row is None:
             max_block_row = int(np.diff(self.row_ptr_host).max(initial=0)) // max(1, self.bs[1])
         self.max_block_row = max_block_row
@@ -91,22 +93,31 @@ class Matrix:
             mesh_s = _dev.mesh_dev(form.mesh)["struct"]
             A = self.struct()
             handle = C.c_void_p()
-            _lib.check(lib.mpcx_tile_plan_create(C.byref(mesh_s), C.byref(d0), C.byref(d1), s_integral.cells, ncells,
-                                                 _dev.ptr(skip), _dev.ptr(bc0_d), _dev.ptr(bc1_d), C.byref(A),
-                                                 _dev.stream_ptr(), C.byref(handle)))
+            try:
+                _lib.check(lib.mpcx_tile_plan_create(C.byref(mesh_s), C.byref(d0), C.byref(d1), s_integral.cells, ncells,
+                                                     _dev.ptr(skip), _dev.ptr(bc0_d), _dev.ptr(bc1_d), C.byref(A),
+                                                     _dev.stream_ptr(), C.byref(handle)))
+            except _lib.MpcxError as e:
+                # a mesh whose tiles do not fit the plan format (e.g. a vertex shared by thousands of cells) is
+                # assembled by the atomic-scatter kernels instead -- still on the device
+                if getattr(e, "status", None) != _lib.ERR_UNSUPPORTED:
+                    raise
+                self._tile_plans[key] = None
+                return None
             _lib.check(lib.mpcx_device_error(_dev.stream_ptr()))
-            info = (C.c_int64 * 10)()
-            lib.mpcx_tile_plan_info(handle, info, 10)
+            info = (C.c_int64 * 14)()
+            lib.mpcx_tile_plan_info(handle, info, 14)
             self._tile_plans[key] = (handle, dict(zip(("tiles", "cells_per_tile", "bulk_cells", "max_nodes",
-                                                       "max_dests", "tile_nodes", "dests", "bytes", "max_slots", "slots"),
+                                                       "max_dests", "tile_nodes", "dests", "bytes", "max_slots", "slots", "max_runs", "runs", "max_stage", "symmetric"),
                                                       [int(v) for v in info])))
         return self._tile_plans[key]
 
     def __del__(self):
         try:
             lib = _lib.load()
-            for handle, _ in self._tile_plans.values():
-                lib.mpcx_tile_plan_destroy(handle)
+            for entry in self._tile_plans.values():
+                if entry is not None:
+                    lib.mpcx_tile_plan_destroy(entry[0])
         except Exception:
             pass
 
@@ -131,7 +142,10 @@ class Matrix:
 
 class Vector:
     def __init__(self, n: int, data: Optional[torch.Tensor] = None):
-        self.data = torch.zeros(n, dtype=torch.float64, device=_dev.device()) if data is None else data
+        if data is None:  # capacity rounded up to an even count (tile kernels add whole 16-byte runs)
+            self._storage = torch.zeros(n + (n & 1), dtype=torch.float64, device=_dev.device())
+            data = self._storage[:n]
+        self.data = data
         self.ghost_exchange = None
 
     def set(self, v: float):

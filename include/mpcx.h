@@ -177,14 +177,17 @@ int mpcx_tile_plan_create(const mpcx_mesh* mesh, const mpcx_dofmap* dofmap0, con
                           const int8_t* bc0, const int8_t* bc1, const mpcx_csr* A, void* stream,
                           mpcx_tile_plan** plan_out);
 void mpcx_tile_plan_destroy(mpcx_tile_plan* plan);
-/* out[0..9] = tiles, cells per tile, bulk cells, max vertices / dests per tile, total tile vertices,
- * total dests (= red.global.add operations per assembly), plan bytes read per assembly, max / total
- * element-buffer slots */
+/* out[0..13] = tiles, cells per tile, bulk cells, max vertices / dest records per tile, total tile vertices,
+ * total dest records, plan bytes read per assembly, max / total element-buffer slots, max / total runs
+ * (= TMA bulk reductions per assembly), max staging positions per tile, 1 for a symmetric plan (same dofmap
+ * and bc markers on both sides: upper-triangular records feed entry (r, c) and entry (c, r)) */
 int mpcx_tile_plan_info(const mpcx_tile_plan* plan, int64_t* out, int32_t n);
 
 /* Same contract as mpcx_assemble_matrix_f64 (A += integral; the caller zeroes A), bulk cells through the
  * tile plan: element entries are combined per tile in shared memory and added with one reduction per
- * (tile, CSR entry); slave cells are eliminated afterwards by the same kernel as in mpcx_assemble_matrix_f64. */
+ * (tile, CSR entry), added to A.val by TMA bulk reductions over runs of consecutive entries; slave cells are
+ * eliminated afterwards by the same kernel as in mpcx_assemble_matrix_f64.  A.val must be 16-byte aligned and
+ * have room for nnz rounded up to an even count (a run may carry one zero of padding past the last entry). */
 int mpcx_assemble_matrix_tiled_f64(const mpcx_integral* integral, const mpcx_mesh* mesh,
                                    const mpcx_dofmap* dofmap0, const mpcx_dofmap* dofmap1,
                                    const int8_t* bc0, const int8_t* bc1,
@@ -194,7 +197,8 @@ int mpcx_assemble_matrix_tiled_f64(const mpcx_integral* integral, const mpcx_mes
 /* Tile plan for the load vector (same tiling; dests are the row dofs, built once per (dofmap, active cells,
  * skip flags)) and the tiled counterpart of mpcx_assemble_vector_f64: element entries of the constraint-free
  * cells are combined per tile, one reduction per (tile, row); cells holding slaves (integral->slave_cells) go
- * through the elimination path of mpcx_assemble_vector_f64 (cpp/assemble_vector.h:35-69).  b is NOT zeroed. */
+ * through the elimination path of mpcx_assemble_vector_f64 (cpp/assemble_vector.h:35-69).  b is NOT zeroed; it
+ * must be 16-byte aligned with room for num_dofs rounded up to an even count. */
 int mpcx_vector_tile_plan_create(const mpcx_mesh* mesh, const mpcx_dofmap* dofmap, const int32_t* cells,
                                  int64_t num_cells, const int8_t* skip, void* stream, mpcx_tile_plan** plan_out);
 int mpcx_assemble_vector_tiled_f64(const mpcx_integral* integral, const mpcx_mesh* mesh, const mpcx_dofmap* dofmap,

@@ -229,9 +229,21 @@ def test_tile_plan_properties(oracle):
     nbulk = mesh.num_cells_local - len(mpc.slave_cells)
     for info in infos:
         assert info["bulk_cells"] == nbulk and info["tiles"] == -(-nbulk // info["cells_per_tile"])
-        assert info["dests"] < 8 * nbulk  # 16 entries per cell before the per-tile combination
+        assert info["symmetric"] == 1 and info["dests"] < 4 * nbulk  # 16 entries per cell before the per-tile combination
+        assert info["runs"] < info["dests"]  # bulk reductions cover several CSR entries each
     m = oracle.mpc_from_arrays(V, data)
-    assert_csr_close(*A.getValuesCSR(), *oracle.assemble_matrix(a, m, bcs=bcs))
+    ref = oracle.assemble_matrix(a, m, bcs=bcs)
+    assert_csr_close(*A.getValuesCSR(), *ref)
+    # the general (non-symmetric) tile plan gives the same matrix
+    import os
+    os.environ["MPCX_TILE_SYM"] = "0"
+    try:
+        A_g = mpcx.create_matrix(a, mpc)
+        mpcx.assemble_matrix(a, mpc, bcs=bcs, A=A_g)
+    finally:
+        del os.environ["MPCX_TILE_SYM"]
+    assert all(info["symmetric"] == 0 for _, info in A_g._tile_plans.values())
+    assert_csr_close(*A_g.getValuesCSR(), *ref)
     # load vector through the vector tile plan (one reduction per (tile, row)), twice into the same vector
     L = fem.source(V, w, 0.7)
     b = mpcx.assemble_vector(L, mpc)
