@@ -9,7 +9,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libmpcx.so")
+# MPCX_LIB: alternative build of the same library (kernel tuning experiments, tools/)
+LIB_PATH = os.environ.get("MPCX_LIB") or os.path.join(_HERE, "libmpcx.so")
 
 MAX_CONSTANTS = 8
 

@@ -38,7 +38,9 @@ namespace
 {
 #define MPCX_CT_INVALID 0xffffffffu
 #define MPCX_CT_NOSLOT 0xffffu
+#ifndef MPCX_TILE_THREADS
 #define MPCX_TILE_THREADS 512
+#endif
 // slot of the i-th source of the dest held by lane l of a group: base + 33 i + l.  The odd stride spreads the
 // sources of one dest (written by neighbouring cells at the same time) over the banks; lanes still read consecutive slots.
 #define MPCX_CT_GSTRIDE 33
@@ -671,9 +673,11 @@ __device__ __forceinline__ void tile_reduce_and_add(const TileSmem& S, int tid, 
   }
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // staging writes -> visible to the copy engine
   __syncthreads();
-  if (tid < nr_t)
+  // the bulk reduction takes uniform operands: one lane per warp issues, so the 16 warps issue side by side
+  // instead of one warp walking its lanes one after the other
+  if ((tid & 31) == 0 && (tid >> 5) < nr_t)
   {
-    for (int r = tid; r < nr_t; r += NT)
+    for (int r = tid >> 5; r < nr_t; r += NT / 32)
     {
       const int2 rr = S.runs[r];
       tma_reduce_add_f64(out + rr.x, S.stage + (rr.y & 0xffff), (unsigned)(rr.y >> 16) * 8u);
