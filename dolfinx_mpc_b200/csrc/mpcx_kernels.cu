@@ -884,6 +884,24 @@ int grid_for_warps(long long nwork, int warps_per_block)
   if (blocks < 1) blocks = 1;
   return (int)blocks;
 }
+
+// grid of a persistent tile kernel: as many CTAs as fit on the device at once (at most one per tile)
+int persistent_grid(const void* kern, size_t smem, int nt, int* grid)
+{
+  int rc = cuda_check(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "smem attr");
+  if (rc) return rc;
+  int dev = 0, sms = 0, per_sm = 0;
+  rc = cuda_check(cudaGetDevice(&dev), "get device");
+  if (rc) return rc;
+  rc = cuda_check(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev), "sm count");
+  if (rc) return rc;
+  rc = cuda_check(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, MPCX_TILE_THREADS, smem), "occupancy");
+  if (rc) return rc;
+  if (per_sm < 1) return fail(MPCX_ERR_UNSUPPORTED, "tile kernel does not fit on an SM");
+  const long long g = (long long)per_sm * sms;
+  *grid = (int)(g < nt ? g : nt);
+  return MPCX_OK;
+}
 }  // namespace
 
 // ====================================================================== C ABI
@@ -1240,14 +1258,16 @@ int mpcx_assemble_matrix_tiled_f64(const mpcx_integral* integral, const mpcx_mes
   if (P->nt > 0)
   {
     const TilePlanD Pd = tile_plan_view(P);
-    const size_t smem = tile_smem_bytes(P->max_nodes, P->max_dests, P->max_slots, P->max_runs, P->max_stage, false, P->sym != 0);
-    auto kern = t->tdim == 3 ? (P->sym ? k_ctile_matrix_p1<3, true> : k_ctile_matrix_p1<3, false>)
-                             : (P->sym ? k_ctile_matrix_p1<2, true> : k_ctile_matrix_p1<2, false>);
-    rc = cuda_check(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "smem attr");
+    const size_t smem = tile_smem_bytes(P->max_nodes, P->max_dests, P->max_slots, P->max_runs, P->max_stage, P->C, t->tdim + 1,
+                                        P->ns, false, P->sym != 0);
+    auto kern = t->tdim == 3 ? (P->sym ? k_ptile_matrix_p1<3, true> : k_ptile_matrix_p1<3, false>)
+                             : (P->sym ? k_ptile_matrix_p1<2, true> : k_ptile_matrix_p1<2, false>);
+    int grid = 0;
+    rc = persistent_grid((const void*)kern, smem, P->nt, &grid);
     if (rc) return rc;
     KernelTimer kt(s);  // dominant kernel of the call
     MPCX_COUNT_LAUNCH();
-    kern<<<P->nt, MPCX_TILE_THREADS, smem, s>>>(Pd, in, md, Ad);
+    kern<<<grid, MPCX_TILE_THREADS, smem, s>>>(Pd, P->nt, in, md, Ad);
   }
   if (in.nslave_cells > 0)
   {
@@ -1295,14 +1315,16 @@ int mpcx_assemble_vector_tiled_f64(const mpcx_integral* integral, const mpcx_mes
   if (P->nt > 0)
   {
     const TilePlanD Pd = tile_plan_view(P);
-    const size_t smem = tile_smem_bytes(P->max_nodes, P->max_dests, P->max_slots, P->max_runs, P->max_stage, true, false);
+    const size_t smem = tile_smem_bytes(P->max_nodes, P->max_dests, P->max_slots, P->max_runs, P->max_stage, P->C, t->tdim + 1,
+                                        P->ns, true, false);
     // coefficient gathered through the very dofmap the plan's rows come from: stage it once per tile row
     const int w_by_row = (!in.coeffs && in.wnodal && in.wmap == dofmap->map) ? 1 : 0;
-    auto kern = t->tdim == 3 ? k_ctile_vector_p1<3> : k_ctile_vector_p1<2>;
-    rc = cuda_check(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "smem attr");
+    auto kern = t->tdim == 3 ? k_ptile_vector_p1<3> : k_ptile_vector_p1<2>;
+    int grid = 0;
+    rc = persistent_grid((const void*)kern, smem, P->nt, &grid);
     if (rc) return rc;
     MPCX_COUNT_LAUNCH();
-    kern<<<P->nt, MPCX_TILE_THREADS, smem, s>>>(Pd, in, md, w_by_row, b);
+    kern<<<grid, MPCX_TILE_THREADS, smem, s>>>(Pd, P->nt, in, md, w_by_row, b);
   }
   if (in.nslave_cells > 0)
   {

@@ -57,6 +57,7 @@ struct TilePlan
   int *cell_pos = nullptr, *tile_node_off = nullptr, *node_ids = nullptr, *dest_k = nullptr, *tile_nd = nullptr,
       *tile_slots = nullptr, *tile_nr = nullptr, *tile_stage = nullptr;
   int2* runs = nullptr;
+  int4* hdr = nullptr;  // per-tile header, 3 x int4 (see load_hdr)
   unsigned* ginfo = nullptr;
   long long *tile_dest_off = nullptr, *tile_run_off = nullptr;
   uint16_t *cell_nodes = nullptr, *dest_spos = nullptr, *dest_spos2 = nullptr, *cell_slot = nullptr, *cell_rows = nullptr;
@@ -72,6 +73,7 @@ struct TilePlanD  // what the kernel sees
   long long n_bulk;
   const int *cell_pos, *tile_node_off, *node_ids, *dest_k, *tile_nd, *tile_nr, *tile_stage;
   const int2* runs;
+  const int4* hdr;
   const unsigned* ginfo;
   const long long *tile_dest_off, *tile_run_off;
   const uint16_t *cell_nodes, *dest_spos, *dest_spos2, *cell_slot, *cell_rows;
@@ -524,17 +526,19 @@ k_ct_build(int pass, const int* __restrict__ order, long long n_bulk, const int*
 }
 
 // ------------------------------------------------------------------ the assembly kernels
-// Shared memory of one tile (sections 16-byte aligned; record arrays sized for whole groups of 128 records):
-//   Xs[max_nodes][3] f64 | stage[max_stage] f64 | ebuf[max_slots + 1] f64 | (vector: fs[max_dests] f64) |
-//   runs[max_runs] int2 | gi[max_dests/32] u32 | spos[max_dests] u16 | (sym: spos2[max_dests] u16) |
-//   dcnt[max_dests] u8 | mbarrier
+// Shared memory of one CTA (sections 16-byte aligned; record arrays sized for whole groups of 128 records):
+//   Xs[max_nodes][3] f64 | stage[max_stage] f64 (matrix) | ebuf[max_slots + 1] f64 | fs[max_dests] f64 (vector) |
+//   R: runs[max_runs] int2 (matrix) | gi[max_dests/32] u32 | dk[max_dests] i32 (vector) | spos[max_dests] u16,
+//      spos2[max_dests] u16 (matrix / symmetric) | dcnt[max_dests] u8 |
+//   C: cnode[C][NV] u16 | cslot[C][NS] u16 | crow[C][NV] u16 (vector) | 2 mbarriers
 __host__ __device__ inline size_t tile_smem_bytes(int max_nodes, int max_dests, int max_slots, int max_runs, int max_stage,
-                                                  bool vec, bool sym)
+                                                  int C, int nv, int ns, bool vec, bool sym)
 {
   auto al = [](size_t b) { return (b + 15) & ~(size_t)15; };
-  return al(24 * (size_t)max_nodes) + al(8 * (size_t)max_stage) + al(8 * (size_t)(max_slots + 1))
-         + (vec ? al(8 * (size_t)max_dests) : 0) + al(8 * (size_t)max_runs) + al(4 * (size_t)(max_dests / 32))
-         + (sym ? 2 : 1) * al(2 * (size_t)max_dests) + al((size_t)max_dests) + 16;
+  size_t b = al(24 * (size_t)max_nodes) + al(8 * (size_t)(max_slots + 1)) + al(4 * (size_t)(max_dests / 32)) + al((size_t)max_dests);
+  if (vec) b += al(8 * (size_t)max_dests) + al(4 * (size_t)max_dests) + al(2 * (size_t)C * nv);
+  else b += al(8 * (size_t)max_stage) + al(8 * (size_t)max_runs) + (sym ? 2 : 1) * al(2 * (size_t)max_dests);
+  return b + al(2 * (size_t)C * nv) + al(2 * (size_t)C * ns) + 16;
 }
 
 // ---- 1-D TMA (cp.async.bulk global -> shared, completion on an mbarrier) for the contiguous plan records
@@ -581,264 +585,331 @@ struct TileSmem
   double *Xs, *stage, *ebuf, *fs;
   int2* runs;
   unsigned* gi;
-  uint16_t *spos, *spos2;
+  int* dk;
+  uint16_t *spos, *spos2, *cnode, *cslot, *crow;
   uint8_t* dcnt;
-  unsigned long long* bar;
+  unsigned long long *barR, *barC;
 };
 
-__device__ __forceinline__ TileSmem tile_carve(unsigned char* sp, const TilePlanD& P, bool vec, bool sym)
+__device__ __forceinline__ TileSmem tile_carve(unsigned char* sp, const TilePlanD& P, int nv, int ns, bool vec, bool sym)
 {
   auto al = [](size_t b) { return (b + 15) & ~(size_t)15; };
   TileSmem S;
   S.Xs = reinterpret_cast<double*>(sp); sp += al(24 * (size_t)P.max_nodes);
-  S.stage = reinterpret_cast<double*>(sp); sp += al(8 * (size_t)P.max_stage);
+  S.stage = reinterpret_cast<double*>(sp); if (!vec) sp += al(8 * (size_t)P.max_stage);
   S.ebuf = reinterpret_cast<double*>(sp); sp += al(8 * (size_t)(P.max_slots + 1));
   S.fs = reinterpret_cast<double*>(sp); if (vec) sp += al(8 * (size_t)P.max_dests);
-  S.runs = reinterpret_cast<int2*>(sp); sp += al(8 * (size_t)P.max_runs);
+  S.runs = reinterpret_cast<int2*>(sp); if (!vec) sp += al(8 * (size_t)P.max_runs);
   S.gi = reinterpret_cast<unsigned*>(sp); sp += al(4 * (size_t)(P.max_dests / 32));
-  S.spos = reinterpret_cast<uint16_t*>(sp); sp += al(2 * (size_t)P.max_dests);
-  S.spos2 = reinterpret_cast<uint16_t*>(sp); if (sym) sp += al(2 * (size_t)P.max_dests);
+  S.dk = reinterpret_cast<int*>(sp); if (vec) sp += al(4 * (size_t)P.max_dests);
+  S.spos = reinterpret_cast<uint16_t*>(sp); if (!vec) sp += al(2 * (size_t)P.max_dests);
+  S.spos2 = reinterpret_cast<uint16_t*>(sp); if (!vec && sym) sp += al(2 * (size_t)P.max_dests);
   S.dcnt = reinterpret_cast<uint8_t*>(sp); sp += al((size_t)P.max_dests);
-  S.bar = reinterpret_cast<unsigned long long*>(sp);
+  S.cnode = reinterpret_cast<uint16_t*>(sp); sp += al(2 * (size_t)P.C * nv);
+  S.cslot = reinterpret_cast<uint16_t*>(sp); sp += al(2 * (size_t)P.C * ns);
+  S.crow = reinterpret_cast<uint16_t*>(sp); if (vec) sp += al(2 * (size_t)P.C * nv);
+  S.barR = reinterpret_cast<unsigned long long*>(sp);
+  S.barC = S.barR + 1;
   return S;
 }
 
-// phase 0, shared by both kernels: TMA of the record / run arrays (thread 0), zero fill of the staging buffer and
-// gather of the tile's vertex coordinates
-template <bool SYM>
-__device__ __forceinline__ void tile_stage(const TileSmem& S, const TilePlanD& P, const MeshD& mesh, int t, int tid,
-                                           long long d0, int nd_t, int nr_t)
+// Per-tile header (3 x int4): {vertex offset, vertices, records, runs} {staging size, -, record offset lo, hi}
+// {run offset lo, hi, -, -}.  Every thread reads the same 48 bytes (one broadcast transaction per warp).
+struct TileHdr
 {
-  constexpr int NT = MPCX_TILE_THREADS;
-  if (tid == 0)
-  {
-    mbar_init(S.bar, 1);
-    const unsigned nd16 = (unsigned)((nd_t + 15) & ~15), ng4 = (unsigned)((((nd_t + 31) >> 5) + 3) & ~3);
-    const unsigned nr2 = (unsigned)((nr_t + 1) & ~1);
-    mbar_expect_tx(S.bar, nd16 * (SYM ? 5 : 3) + ng4 * 4 + nr2 * 8);
-    if (nd16)
-    {
-      tma_load_1d(S.dcnt, P.dest_cnt + d0, nd16, S.bar);
-      tma_load_1d(S.spos, P.dest_spos + d0, nd16 * 2, S.bar);
-      if (SYM) tma_load_1d(S.spos2, P.dest_spos2 + d0, nd16 * 2, S.bar);
-      tma_load_1d(S.gi, P.ginfo + (d0 >> 5), ng4 * 4, S.bar);
-      tma_load_1d(S.runs, P.runs + __ldg(P.tile_run_off + t), nr2 * 8, S.bar);
-    }
-  }
-  const int st_t = __ldg(P.tile_stage + t);  // even
-  for (int i = tid; i < (st_t >> 1); i += NT) reinterpret_cast<double2*>(S.stage)[i] = make_double2(0.0, 0.0);
-  const int n0 = __ldg(P.tile_node_off + t), nn_t = __ldg(P.tile_node_off + t + 1) - n0;
-  for (int i = tid; i < nn_t; i += NT)
-  {
-    const double* p = mesh.x + (long long)__ldg(P.node_ids + n0 + i) * mesh.xs;
-    if (mesh.xs == 4)
-    {
-      const double2 a = __ldg(reinterpret_cast<const double2*>(p));
-      S.Xs[3 * i] = a.x; S.Xs[3 * i + 1] = a.y;
-    }
-    else
-    {
-      S.Xs[3 * i] = __ldg(p);
-      S.Xs[3 * i + 1] = __ldg(p + 1);
-    }
-    S.Xs[3 * i + 2] = __ldg(p + 2);
-  }
+  int node_off, nn, nd, nr, stage;
+  long long dest_off, run_off;
+};
+__device__ __forceinline__ TileHdr load_hdr(const int4* __restrict__ hdr, int t)
+{
+  const int4 a = __ldg(hdr + 3 * (long long)t), b = __ldg(hdr + 3 * (long long)t + 1), c = __ldg(hdr + 3 * (long long)t + 2);
+  TileHdr h;
+  h.node_off = a.x; h.nn = a.y; h.nd = a.z; h.nr = a.w; h.stage = b.x;
+  h.dest_off = (long long)(unsigned)b.z | ((long long)b.w << 32);
+  h.run_off = (long long)(unsigned)c.x | ((long long)c.y << 32);
+  return h;
 }
 
-// phases 2 and 3, shared by both kernels.  Record k = column (k & 31) of its group's slot block; the trip count is
-// the group's largest count (warp-uniform: no divergence bookkeeping), rows past the lane's own count are not
-// read.  The sum goes to the record's staging position (and to the transposed entry's in a symmetric plan), then
-// one bulk reduction per run.
-template <bool SYM>
-__device__ __forceinline__ void tile_reduce_and_add(const TileSmem& S, int tid, int nd_t, int nr_t, double* __restrict__ out)
+// TMA bulk copies of one tile's dest-side records (R) and cell-side records (C), issued by one thread
+template <bool VEC, bool SYM>
+__device__ __forceinline__ void tma_records(const TileSmem& S, const TilePlanD& P, const TileHdr& h)
 {
-  constexpr int NT = MPCX_TILE_THREADS;
-  for (int k = tid; k < nd_t; k += NT)
+  const unsigned nd16 = (unsigned)((h.nd + 15) & ~15), ng4 = (unsigned)((((h.nd + 31) >> 5) + 3) & ~3);
+  const unsigned nr2 = VEC ? 0u : (unsigned)((h.nr + 1) & ~1);
+  mbar_expect_tx(S.barR, nd16 * (VEC ? 5 : (SYM ? 5 : 3)) + ng4 * 4 + nr2 * 8);
+  if (!nd16) return;
+  tma_load_1d(S.dcnt, P.dest_cnt + h.dest_off, nd16, S.barR);
+  tma_load_1d(S.gi, P.ginfo + (h.dest_off >> 5), ng4 * 4, S.barR);
+  if (VEC)
+    tma_load_1d(S.dk, P.dest_k + h.dest_off, nd16 * 4, S.barR);
+  else
   {
-    const unsigned g = S.gi[k >> 5];
-    const double* e = S.ebuf + (g & 0xffffu) + (k & 31);
-    const int cmax = (int)(g >> 16), cnt = S.dcnt[k];
-    double s0 = 0.0, s1 = 0.0;
-    int i = 0;
+    tma_load_1d(S.spos, P.dest_spos + h.dest_off, nd16 * 2, S.barR);
+    if (SYM) tma_load_1d(S.spos2, P.dest_spos2 + h.dest_off, nd16 * 2, S.barR);
+    if (nr2) tma_load_1d(S.runs, P.runs + h.run_off, nr2 * 8, S.barR);
+  }
+}
+template <bool VEC>
+__device__ __forceinline__ void tma_cells(const TileSmem& S, const TilePlanD& P, int t, int nv, int ns)
+{
+  const long long first = (long long)t * P.C;
+  const unsigned bn = (unsigned)(2 * nv * P.C), bs = (unsigned)(2 * ns * P.C);
+  mbar_expect_tx(S.barC, bn + bs + (VEC ? bn : 0u));
+  tma_load_1d(S.cnode, P.cell_nodes + first * nv, bn, S.barC);
+  tma_load_1d(S.cslot, P.cell_slot + first * ns, bs, S.barC);
+  if (VEC) tma_load_1d(S.crow, P.cell_rows + first * nv, bn, S.barC);
+}
+
+__device__ __forceinline__ void load_vertex(const MeshD& mesh, int node, double& x0, double& x1, double& x2)
+{
+  const double* p = mesh.x + (long long)node * mesh.xs;
+  if (mesh.xs == 4)
+  {
+    const double2 a = __ldg(reinterpret_cast<const double2*>(p));
+    x0 = a.x; x1 = a.y;
+  }
+  else
+  {
+    x0 = __ldg(p); x1 = __ldg(p + 1);
+  }
+  x2 = __ldg(p + 2);
+}
+
+// sum of record k = column (k & 31) of its group's slot block; the trip count is the group's largest count
+// (warp-uniform: no divergence bookkeeping), rows past the lane's own count are not read
+__device__ __forceinline__ double tile_record_sum(const TileSmem& S, int k)
+{
+  const unsigned g = S.gi[k >> 5];
+  const double* e = S.ebuf + (g & 0xffffu) + (k & 31);
+  const int cmax = (int)(g >> 16), cnt = S.dcnt[k];
+  double s0 = 0.0, s1 = 0.0;
+  int i = 0;
 #pragma unroll 1
-    for (; i + 2 <= cmax; i += 2, e += 2 * MPCX_CT_GSTRIDE)
-    {
-      if (i < cnt) s0 += e[0];
-      if (i + 1 < cnt) s1 += e[MPCX_CT_GSTRIDE];
-    }
-    if (i < cnt) s0 += e[0];
-    const double v = s0 + s1;
-    S.stage[S.spos[k]] = v;
-    if (SYM) S.stage[S.spos2[k]] = v;
-  }
-  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // staging writes -> visible to the copy engine
-  __syncthreads();
-  // the bulk reduction takes uniform operands: one lane per warp issues, so the 16 warps issue side by side
-  // instead of one warp walking its lanes one after the other
-  if ((tid & 31) == 0 && (tid >> 5) < nr_t)
+  for (; i + 2 <= cmax; i += 2, e += 2 * MPCX_CT_GSTRIDE)
   {
-    for (int r = tid >> 5; r < nr_t; r += NT / 32)
-    {
-      const int2 rr = S.runs[r];
-      tma_reduce_add_f64(out + rr.x, S.stage + (rr.y & 0xffff), (unsigned)(rr.y >> 16) * 8u);
-    }
-    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-    asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");  // the staging buffer must outlive the reads
+    if (i < cnt) s0 += e[0];
+    if (i + 1 < cnt) s1 += e[MPCX_CT_GSTRIDE];
   }
+  if (i < cnt) s0 += e[0];
+  return s0 + s1;
 }
 
+// Persistent CTAs (2 per SM) walk the tiles with stride gridDim.x; while tile t computes, the records of tile t+1
+// arrive by TMA and its vertex coordinates travel through registers, so the per-tile latency chain
+// (header -> vertex ids -> coordinates -> records) is off the critical path (profiles/r01_k: that chain, not a
+// throughput limit, bounded the one-tile-per-CTA kernel).  Buffers are single: each is refilled right after the
+// barrier that ends its last use.
+//   top      vertex id of tile t+1 -> register
+//   phase 1  wait C(t); thread = cell: element matrix -> slots; then x[vertex id] of t+1 -> registers
+//   sync 1   TMA C(t+1)
+//   phase 2  wait R(t); thread = record: column sum -> staging position(s); vertex registers -> Xs
+//   sync 2
+//   phase 3  one lane per warp: TMA bulk reduce-add per run; wait until the staging buffer has been read
+//   sync 3   TMA R(t+1); zero the staging buffer for t+1; header of t+2
 // SYM: the element matrix is symmetric and so are dofmaps and bc markers of both sides: only the upper triangle is
 // stored and summed, every record feeds entry (r, c) and entry (c, r).
 template <int TD, bool SYM>
 __global__ void __launch_bounds__(MPCX_TILE_THREADS)
-k_ctile_matrix_p1(TilePlanD P, IntD in, MeshD mesh, CsrD A)
+k_ptile_matrix_p1(TilePlanD P, int nt, IntD in, MeshD mesh, CsrD A)
 {
   constexpr int NV = TD + 1, NS = SYM ? NV * (NV + 1) / 2 : NV * NV, NT = MPCX_TILE_THREADS;
   extern __shared__ __align__(16) unsigned char tile_smem[];
-  const TileSmem S = tile_carve(tile_smem, P, false, SYM);
-  const int t = blockIdx.x, tid = threadIdx.x;
-  const long long first = (long long)t * NT;
-  const int nc_t = (int)((P.n_bulk - first) < NT ? (P.n_bulk - first) : NT);
-  const long long d0 = __ldg(P.tile_dest_off + t);
-  const int nd_t = __ldg(P.tile_nd + t), nr_t = __ldg(P.tile_nr + t);
-
-  // this thread's cell record: tile-local vertices and the slot of each stored element entry (coalesced reads)
-  uint16_t cn[NV], slot[NS];
-  if (NV == 4)
-  {
-    const uint2 a = __ldg(reinterpret_cast<const uint2*>(P.cell_nodes) + first + tid);
-    cn[0] = a.x & 0xffff; cn[1] = a.x >> 16; cn[2] = a.y & 0xffff; cn[3] = a.y >> 16;
-  }
-  else
-  {
-#pragma unroll
-    for (int v = 0; v < NV; ++v) cn[v] = __ldg(P.cell_nodes + (first + tid) * NV + v);
-  }
-  if (NS % 2 == 0)
-  {
-    const unsigned* sp = reinterpret_cast<const unsigned*>(P.cell_slot) + (first + tid) * (NS / 2);
-#pragma unroll
-    for (int e = 0; e < NS / 2; ++e)
-    {
-      const unsigned w = __ldg(sp + e);
-      slot[2 * e] = w & 0xffff; slot[2 * e + 1] = w >> 16;
-    }
-  }
-  else
-  {
-#pragma unroll
-    for (int e = 0; e < NS; ++e) slot[e] = __ldg(P.cell_slot + (first + tid) * NS + e);
-  }
-  tile_stage<SYM>(S, P, mesh, t, tid, d0, nd_t, nr_t);
-  __syncthreads();  // Xs complete, staging buffer zeroed; the mbarrier initialisation is visible to every thread
-
-  // phase 1: thread = cell; element matrix entries to their slots
-  if (tid < nc_t)
-  {
-    double X[NV][3];
-#pragma unroll
-    for (int v = 0; v < NV; ++v)
-    {
-      const int l = cn[v];
-      X[v][0] = S.Xs[3 * l];
-      X[v][1] = S.Xs[3 * l + 1];
-      X[v][2] = TD == 3 ? S.Xs[3 * l + 2] : 0.0;
-    }
-    P1Geom<TD> G;
-    p1_geometry<TD>(X, G);
-    double w[NV], Ae[NV][NV];
-    if (in.kernel == MPCX_KERNEL_LAPLACE_VARCOEF)
-    {
-      const long long index = __ldg(P.cell_pos + first + tid);
-      p1_load_w<TD>(in, index, in.cells ? __ldg(in.cells + index) : (int)index, w);
-    }
-    p1_element<TD>(in.kernel, G, in.c, w, Ae);
-    int si = 0;
-#pragma unroll
-    for (int i = 0; i < NV; ++i)
-#pragma unroll
-      for (int j = SYM ? i : 0; j < NV; ++j) S.ebuf[slot[si++]] = Ae[i][j];  // bc-zeroed entries go to the tile's spare slot
-  }
+  const TileSmem S = tile_carve(tile_smem, P, NV, NS, false, SYM);
+  const int tid = threadIdx.x;
+  int t = blockIdx.x;
+  if (t >= nt) return;
+  if (tid == 0) { mbar_init(S.barR, 1); mbar_init(S.barC, 1); }
   __syncthreads();
-  mbar_wait(S.bar, 0);
-  tile_reduce_and_add<SYM>(S, tid, nd_t, nr_t, A.val);
+  TileHdr h = load_hdr(P.hdr, t), hn = h;
+  if (tid == 0) { tma_records<false, SYM>(S, P, h); tma_cells<false>(S, P, t, NV, NS); }
+  for (int i = tid; i < (h.stage >> 1); i += NT) reinterpret_cast<double2*>(S.stage)[i] = make_double2(0.0, 0.0);
+  for (int i = tid; i < h.nn; i += NT)
+    load_vertex(mesh, __ldg(P.node_ids + h.node_off + i), S.Xs[3 * i], S.Xs[3 * i + 1], S.Xs[3 * i + 2]);
+  int tn = t + gridDim.x;
+  bool has_next = tn < nt;
+  if (has_next) hn = load_hdr(P.hdr, tn);
+  __syncthreads();
+  unsigned phase = 0;
+  for (;;)
+  {
+    const long long first = (long long)t * NT;
+    const int nc_t = (int)((P.n_bulk - first) < NT ? (P.n_bulk - first) : NT);
+    int nid = -1;
+    if (has_next && tid < hn.nn) nid = __ldg(P.node_ids + hn.node_off + tid);
+
+    // phase 1: thread = cell; element matrix entries to their slots
+    mbar_wait(S.barC, phase);
+    if (tid < nc_t)
+    {
+      double X[NV][3];
+#pragma unroll
+      for (int v = 0; v < NV; ++v)
+      {
+        const int l = S.cnode[tid * NV + v];
+        X[v][0] = S.Xs[3 * l];
+        X[v][1] = S.Xs[3 * l + 1];
+        X[v][2] = TD == 3 ? S.Xs[3 * l + 2] : 0.0;
+      }
+      P1Geom<TD> G;
+      p1_geometry<TD>(X, G);
+      double w[NV], Ae[NV][NV];
+      if (in.kernel == MPCX_KERNEL_LAPLACE_VARCOEF)
+      {
+        const long long index = __ldg(P.cell_pos + first + tid);
+        p1_load_w<TD>(in, index, in.cells ? __ldg(in.cells + index) : (int)index, w);
+      }
+      p1_element<TD>(in.kernel, G, in.c, w, Ae);
+      uint16_t slot[NS];
+      if (NS % 2 == 0)
+      {
+        const unsigned* sp = reinterpret_cast<const unsigned*>(S.cslot) + tid * (NS / 2);
+#pragma unroll
+        for (int e = 0; e < NS / 2; ++e)
+        {
+          const unsigned ww = sp[e];
+          slot[2 * e] = ww & 0xffff; slot[2 * e + 1] = ww >> 16;
+        }
+      }
+      else
+      {
+#pragma unroll
+        for (int e = 0; e < NS; ++e) slot[e] = S.cslot[tid * NS + e];
+      }
+      int si = 0;
+#pragma unroll
+      for (int i = 0; i < NV; ++i)
+#pragma unroll
+        for (int j = SYM ? i : 0; j < NV; ++j) S.ebuf[slot[si++]] = Ae[i][j];  // bc-zeroed entries go to the tile's spare slot
+    }
+    double xg0 = 0.0, xg1 = 0.0, xg2 = 0.0;
+    if (nid >= 0) load_vertex(mesh, nid, xg0, xg1, xg2);
+    __syncthreads();  // 1: element buffer complete; cell records and Xs are free
+    if (tid == 0 && has_next) tma_cells<false>(S, P, tn, NV, NS);
+
+    // phase 2: thread = record; the sum goes to its staging position (and the transposed entry's)
+    mbar_wait(S.barR, phase);
+    for (int k = tid; k < h.nd; k += NT)
+    {
+      const double v = tile_record_sum(S, k);
+      S.stage[S.spos[k]] = v;
+      if (SYM) S.stage[S.spos2[k]] = v;
+    }
+    if (nid >= 0) { S.Xs[3 * tid] = xg0; S.Xs[3 * tid + 1] = xg1; S.Xs[3 * tid + 2] = xg2; }
+    if (has_next)
+      for (int i = tid + NT; i < hn.nn; i += NT)  // a tile with more vertices than threads (never on simplicial meshes)
+        load_vertex(mesh, __ldg(P.node_ids + hn.node_off + i), S.Xs[3 * i], S.Xs[3 * i + 1], S.Xs[3 * i + 2]);
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // staging writes -> visible to the copy engine
+    __syncthreads();  // 2: staging buffer and next Xs complete
+
+    // phase 3: the bulk reduction takes uniform operands: one lane per warp issues, the 16 warps side by side
+    if ((tid & 31) == 0 && (tid >> 5) < h.nr)
+    {
+      for (int r = tid >> 5; r < h.nr; r += NT / 32)
+      {
+        const int2 rr = S.runs[r];
+        tma_reduce_add_f64(A.val + rr.x, S.stage + (rr.y & 0xffff), (unsigned)(rr.y >> 16) * 8u);
+      }
+      asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+      asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");  // the staging buffer must outlive the reads
+    }
+    __syncthreads();  // 3: staging buffer and dest records are free
+    if (!has_next) break;
+    if (tid == 0) tma_records<false, SYM>(S, P, hn);
+    for (int i = tid; i < (hn.stage >> 1); i += NT) reinterpret_cast<double2*>(S.stage)[i] = make_double2(0.0, 0.0);
+    h = hn; t = tn; tn += gridDim.x; has_next = tn < nt; phase ^= 1u;
+    if (has_next) hn = load_hdr(P.hdr, tn);
+  }
 }
 
 // Load vector b_i = c0 |K|/((d+1)(d+2)) (f_i + sum_j f_j) (cpp/assemble_vector.cpp:163-185 with the P1 source
-// kernel): NV entries per cell, dests = the row dofs of the tile, one bulk reduction per run of rows instead of
-// one red.global.add.f64 per (cell, vertex).  When the coefficient lives in the test space (w_by_row) its values
-// are staged once per tile row.
+// kernel), same pipeline with NV entries per cell and dests = the row dofs of the tile.  A tile has ~0.4 rows per
+// cell scattered through b, so the sums are added with one red.global.add.f64 per (tile, row) -- no staging, no
+// phase 3.  When the coefficient lives in the test space (w_by_row) its values are staged once per tile row.
 template <int TD>
 __global__ void __launch_bounds__(MPCX_TILE_THREADS)
-k_ctile_vector_p1(TilePlanD P, IntD in, MeshD mesh, int w_by_row, double* __restrict__ b)
+k_ptile_vector_p1(TilePlanD P, int nt, IntD in, MeshD mesh, int w_by_row, double* __restrict__ b)
 {
   constexpr int NV = TD + 1, NT = MPCX_TILE_THREADS;
   extern __shared__ __align__(16) unsigned char tile_smem[];
-  const TileSmem S = tile_carve(tile_smem, P, true, false);
-  const int t = blockIdx.x, tid = threadIdx.x;
-  const long long first = (long long)t * NT;
-  const int nc_t = (int)((P.n_bulk - first) < NT ? (P.n_bulk - first) : NT);
-  const long long d0 = __ldg(P.tile_dest_off + t);
-  const int nd_t = __ldg(P.tile_nd + t), nr_t = __ldg(P.tile_nr + t);
-
-  uint16_t cn[NV], slot[NV], crow[NV];
-  if (NV == 4)
-  {
-    const uint2 a = __ldg(reinterpret_cast<const uint2*>(P.cell_nodes) + first + tid);
-    const uint2 s = __ldg(reinterpret_cast<const uint2*>(P.cell_slot) + first + tid);
-    const uint2 r = __ldg(reinterpret_cast<const uint2*>(P.cell_rows) + first + tid);
-    cn[0] = a.x & 0xffff; cn[1] = a.x >> 16; cn[2] = a.y & 0xffff; cn[3] = a.y >> 16;
-    slot[0] = s.x & 0xffff; slot[1] = s.x >> 16; slot[2] = s.y & 0xffff; slot[3] = s.y >> 16;
-    crow[0] = r.x & 0xffff; crow[1] = r.x >> 16; crow[2] = r.y & 0xffff; crow[3] = r.y >> 16;
-  }
-  else
-  {
-#pragma unroll
-    for (int v = 0; v < NV; ++v)
-    {
-      cn[v] = __ldg(P.cell_nodes + (first + tid) * NV + v);
-      slot[v] = __ldg(P.cell_slot + (first + tid) * NV + v);
-      crow[v] = __ldg(P.cell_rows + (first + tid) * NV + v);
-    }
-  }
-  tile_stage<false>(S, P, mesh, t, tid, d0, nd_t, nr_t);
-  if (w_by_row)  // one coefficient read per tile row (straight from the plan: no wait on the TMA)
-    for (int k = tid; k < nd_t; k += NT) S.fs[k] = __ldg(in.wnodal + __ldg(P.dest_k + d0 + k));
+  const TileSmem S = tile_carve(tile_smem, P, NV, NV, true, false);
+  const int tid = threadIdx.x;
+  int t = blockIdx.x;
+  if (t >= nt) return;
+  if (tid == 0) { mbar_init(S.barR, 1); mbar_init(S.barC, 1); }
   __syncthreads();
-
-  if (tid < nc_t)
-  {
-    double X[NV][3];
-#pragma unroll
-    for (int v = 0; v < NV; ++v)
-    {
-      const int l = cn[v];
-      X[v][0] = S.Xs[3 * l];
-      X[v][1] = S.Xs[3 * l + 1];
-      X[v][2] = TD == 3 ? S.Xs[3 * l + 2] : 0.0;
-    }
-    P1Geom<TD> G;
-    p1_geometry<TD>(X, G);
-    double f[NV], fsum = 0.0;
-    if (w_by_row)
-    {
-#pragma unroll
-      for (int v = 0; v < NV; ++v) f[v] = S.fs[crow[v]];
-    }
-    else
-    {
-      const long long index = __ldg(P.cell_pos + first + tid);
-      p1_load_w<TD>(in, index, in.cells ? __ldg(in.cells + index) : (int)index, f);
-    }
-#pragma unroll
-    for (int v = 0; v < NV; ++v) fsum += f[v];
-    const double sc = in.c[0] * G.vol * (1.0 / double((TD + 1) * (TD + 2)));
-#pragma unroll
-    for (int v = 0; v < NV; ++v) S.ebuf[slot[v]] = sc * (f[v] + fsum);  // a vector plan has no bc-zeroed entries
-  }
+  TileHdr h = load_hdr(P.hdr, t), hn = h;
+  if (tid == 0) { tma_records<true, false>(S, P, h); tma_cells<true>(S, P, t, NV, NV); }
+  for (int i = tid; i < h.nn; i += NT)
+    load_vertex(mesh, __ldg(P.node_ids + h.node_off + i), S.Xs[3 * i], S.Xs[3 * i + 1], S.Xs[3 * i + 2]);
+  if (w_by_row)
+    for (int k = tid; k < h.nd; k += NT) S.fs[k] = __ldg(in.wnodal + __ldg(P.dest_k + h.dest_off + k));
+  int tn = t + gridDim.x;
+  bool has_next = tn < nt;
+  if (has_next) hn = load_hdr(P.hdr, tn);
   __syncthreads();
-  mbar_wait(S.bar, 0);
-  tile_reduce_and_add<false>(S, tid, nd_t, nr_t, b);
+  unsigned phase = 0;
+  for (;;)
+  {
+    const long long first = (long long)t * NT;
+    const int nc_t = (int)((P.n_bulk - first) < NT ? (P.n_bulk - first) : NT);
+    int nid = -1, fid = -1;
+    if (has_next && tid < hn.nn) nid = __ldg(P.node_ids + hn.node_off + tid);
+    if (has_next && w_by_row && tid < hn.nd) fid = __ldg(P.dest_k + hn.dest_off + tid);
+
+    mbar_wait(S.barC, phase);
+    if (tid < nc_t)
+    {
+      double X[NV][3];
+#pragma unroll
+      for (int v = 0; v < NV; ++v)
+      {
+        const int l = S.cnode[tid * NV + v];
+        X[v][0] = S.Xs[3 * l];
+        X[v][1] = S.Xs[3 * l + 1];
+        X[v][2] = TD == 3 ? S.Xs[3 * l + 2] : 0.0;
+      }
+      P1Geom<TD> G;
+      p1_geometry<TD>(X, G);
+      double f[NV], fsum = 0.0;
+      if (w_by_row)
+      {
+#pragma unroll
+        for (int v = 0; v < NV; ++v) f[v] = S.fs[S.crow[tid * NV + v]];
+      }
+      else
+      {
+        const long long index = __ldg(P.cell_pos + first + tid);
+        p1_load_w<TD>(in, index, in.cells ? __ldg(in.cells + index) : (int)index, f);
+      }
+#pragma unroll
+      for (int v = 0; v < NV; ++v) fsum += f[v];
+      const double sc = in.c[0] * G.vol * (1.0 / double((TD + 1) * (TD + 2)));
+#pragma unroll
+      for (int v = 0; v < NV; ++v) S.ebuf[S.cslot[tid * NV + v]] = sc * (f[v] + fsum);  // a vector plan has no bc-zeroed entries
+    }
+    double xg0 = 0.0, xg1 = 0.0, xg2 = 0.0, fg = 0.0;
+    if (nid >= 0) load_vertex(mesh, nid, xg0, xg1, xg2);
+    if (fid >= 0) fg = __ldg(in.wnodal + fid);
+    __syncthreads();  // 1: element buffer complete; cell records, Xs and fs are free
+    if (tid == 0 && has_next) tma_cells<true>(S, P, tn, NV, NV);
+
+    mbar_wait(S.barR, phase);
+    for (int k = tid; k < h.nd; k += NT) atomicAdd(b + S.dk[k], tile_record_sum(S, k));
+    if (nid >= 0) { S.Xs[3 * tid] = xg0; S.Xs[3 * tid + 1] = xg1; S.Xs[3 * tid + 2] = xg2; }
+    if (fid >= 0) S.fs[tid] = fg;
+    if (has_next)
+    {
+      for (int i = tid + NT; i < hn.nn; i += NT)
+        load_vertex(mesh, __ldg(P.node_ids + hn.node_off + i), S.Xs[3 * i], S.Xs[3 * i + 1], S.Xs[3 * i + 2]);
+      if (w_by_row)
+        for (int k = tid + NT; k < hn.nd; k += NT) S.fs[k] = __ldg(in.wnodal + __ldg(P.dest_k + hn.dest_off + k));
+    }
+    __syncthreads();  // 2: dest records are free; next Xs / fs complete
+    if (!has_next) break;
+    if (tid == 0) tma_records<true, false>(S, P, hn);
+    h = hn; t = tn; tn += gridDim.x; has_next = tn < nt; phase ^= 1u;
+    if (has_next) hn = load_hdr(P.hdr, tn);
+  }
 }
 
 // ------------------------------------------------------------------ host side of the setup
@@ -858,7 +929,7 @@ void tile_plan_free(TilePlan* P)
 {
   if (!P) return;
   cudaFree(P->cell_pos); cudaFree(P->tile_node_off); cudaFree(P->node_ids); cudaFree(P->dest_k); cudaFree(P->tile_nd);
-  cudaFree(P->tile_slots); cudaFree(P->tile_nr); cudaFree(P->tile_stage); cudaFree(P->runs); cudaFree(P->ginfo);
+  cudaFree(P->tile_slots); cudaFree(P->tile_nr); cudaFree(P->tile_stage); cudaFree(P->runs); cudaFree(P->hdr); cudaFree(P->ginfo);
   cudaFree(P->tile_dest_off); cudaFree(P->tile_run_off); cudaFree(P->cell_nodes); cudaFree(P->dest_cnt); cudaFree(P->dest_spos);
   cudaFree(P->dest_spos2); cudaFree(P->cell_slot); cudaFree(P->cell_rows);
   delete P;
@@ -867,7 +938,7 @@ void tile_plan_free(TilePlan* P)
 inline TilePlanD tile_plan_view(const TilePlan* P)
 {
   return TilePlanD{P->C, P->max_nodes, P->max_dests, P->max_slots, P->max_runs, P->max_stage, P->n_bulk, P->cell_pos,
-                   P->tile_node_off, P->node_ids, P->dest_k, P->tile_nd, P->tile_nr, P->tile_stage, P->runs, P->ginfo,
+                   P->tile_node_off, P->node_ids, P->dest_k, P->tile_nd, P->tile_nr, P->tile_stage, P->runs, P->hdr, P->ginfo,
                    P->tile_dest_off, P->tile_run_off, P->cell_nodes, P->dest_spos, P->dest_spos2, P->cell_slot, P->cell_rows,
                    P->dest_cnt};
 }
@@ -924,7 +995,7 @@ int tile_plan_build(const mpcx_mesh* mesh, const mpcx_dofmap* dm0, const mpcx_do
   long long* nb_dev = nullptr;
   void* tmp = nullptr;
   size_t tmp_bytes = 0, tb = 0;
-  std::vector<int> h_nn, h_nd, h_sl, h_nr, h_st, noff;
+  std::vector<int> h_nn, h_nd, h_sl, h_nr, h_st, noff, h_hdr;
   std::vector<long long> h_doff, h_roff;
   bool fits = true;
   long long alloc_dests = 0;
@@ -1015,7 +1086,7 @@ int tile_plan_build(const mpcx_mesh* mesh, const mpcx_dofmap* dm0, const mpcx_do
   P->max_dests = (P->max_dests + 127) & ~127;  // the TMA copies move whole groups of records
   P->max_runs = (P->max_runs + 1) & ~1;
   if (!fits || P->max_slots >= (int)MPCX_CT_NOSLOT
-      || tile_smem_bytes(P->max_nodes, P->max_dests, P->max_slots, P->max_runs, P->max_stage, vec, P->sym != 0) > 226 * 1024)
+      || tile_smem_bytes(P->max_nodes, P->max_dests, P->max_slots, P->max_runs, P->max_stage, C, mesh->ng, P->ns, vec, P->sym != 0) > 226 * 1024)
   {
     rc = fail(MPCX_ERR_UNSUPPORTED, "tile plan: a tile needs more element-buffer slots than shared memory holds");
     goto done;
@@ -1023,6 +1094,16 @@ int tile_plan_build(const mpcx_mesh* mesh, const mpcx_dofmap* dm0, const mpcx_do
   TP_CK(tp_alloc(&P->tile_node_off, P->nt + 1)); TP_CK(tp_alloc(&P->tile_dest_off, P->nt + 1));
   TP_CK(tp_alloc(&P->tile_run_off, P->nt + 1));
   TP_CK(cudaMemcpyAsync(P->tile_run_off, h_roff.data(), sizeof(long long) * (P->nt + 1), cudaMemcpyHostToDevice, s));
+  h_hdr.resize(12 * (size_t)P->nt);
+  for (int t = 0; t < P->nt; ++t)
+  {
+    int* q = h_hdr.data() + 12 * (size_t)t;
+    q[0] = noff[t]; q[1] = h_nn[t]; q[2] = h_nd[t]; q[3] = h_nr[t];
+    q[4] = h_st[t]; q[5] = 0; q[6] = (int)(unsigned)(h_doff[t] & 0xffffffffll); q[7] = (int)(h_doff[t] >> 32);
+    q[8] = (int)(unsigned)(h_roff[t] & 0xffffffffll); q[9] = (int)(h_roff[t] >> 32); q[10] = q[11] = 0;
+  }
+  TP_CK(tp_alloc(&P->hdr, 3 * (long long)P->nt));
+  TP_CK(cudaMemcpyAsync(P->hdr, h_hdr.data(), sizeof(int) * h_hdr.size(), cudaMemcpyHostToDevice, s));
   TP_CK(cudaMemcpyAsync(P->tile_node_off, noff.data(), sizeof(int) * (P->nt + 1), cudaMemcpyHostToDevice, s));
   TP_CK(cudaMemcpyAsync(P->tile_dest_off, h_doff.data(), sizeof(long long) * (P->nt + 1), cudaMemcpyHostToDevice, s));
   TP_CK(cudaStreamSynchronize(s));
