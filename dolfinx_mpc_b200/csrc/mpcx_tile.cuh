@@ -38,15 +38,20 @@ namespace
 {
 #define MPCX_CT_INVALID 0xffffffffu
 #define MPCX_CT_NOSLOT 0xffffu
+// cells per tile = threads per CTA of the tile kernels (448: two CTAs with double-buffered records fit one SM)
 #ifndef MPCX_TILE_THREADS
-#define MPCX_TILE_THREADS 512
+#define MPCX_TILE_THREADS 448
 #endif
 // slot of the i-th source of the dest held by lane l of a group: base + 33 i + l.  The odd stride spreads the
 // sources of one dest (written by neighbouring cells at the same time) over the banks; lanes still read consecutive slots.
 #define MPCX_CT_GSTRIDE 33
 
-// dests whose CSR positions (row dofs) differ by at most this much share a run; the gaps are zero-filled
-#define MPCX_CT_RUNGAP 4
+// dests whose CSR positions (row dofs) differ by at most this much share a run; the gaps are zero-filled.  16 merges
+// the partial rows of a tile's boundary vertices with their neighbours along a line of consecutive dofs: ~35 bulk
+// reductions per tile instead of ~117 with a gap of 4 (the copy engine takes a few hundred cycles per operation)
+#ifndef MPCX_CT_RUNGAP
+#define MPCX_CT_RUNGAP 16
+#endif
 #define MPCX_CT_MAXRUNS 2048
 
 struct TilePlan
@@ -528,17 +533,18 @@ k_ct_build(int pass, const int* __restrict__ order, long long n_bulk, const int*
 // ------------------------------------------------------------------ the assembly kernels
 // Shared memory of one CTA (sections 16-byte aligned; record arrays sized for whole groups of 128 records):
 //   Xs[max_nodes][3] f64 | stage[max_stage] f64 (matrix) | ebuf[max_slots + 1] f64 | fs[max_dests] f64 (vector) |
-//   R: runs[max_runs] int2 (matrix) | gi[max_dests/32] u32 | dk[max_dests] i32 (vector) | spos[max_dests] u16,
-//      spos2[max_dests] u16 (matrix / symmetric) | dcnt[max_dests] u8 |
-//   C: cnode[C][NV] u16 | cslot[C][NS] u16 | crow[C][NV] u16 (vector) | 2 mbarriers
+//   R (two copies in the matrix kernel): runs[max_runs] int2 (matrix) | gi[max_dests/32] u32 | dk[max_dests] i32
+//      (vector) | spos[max_dests] u16, spos2[max_dests] u16 (matrix / symmetric) | dcnt[max_dests] u8 |
+//   C: cnode[C][NV] u16 | cslot[C][NS] u16 | crow[C][NV] u16 (vector) | 3 mbarriers
 __host__ __device__ inline size_t tile_smem_bytes(int max_nodes, int max_dests, int max_slots, int max_runs, int max_stage,
                                                   int C, int nv, int ns, bool vec, bool sym)
 {
   auto al = [](size_t b) { return (b + 15) & ~(size_t)15; };
-  size_t b = al(24 * (size_t)max_nodes) + al(8 * (size_t)(max_slots + 1)) + al(4 * (size_t)(max_dests / 32)) + al((size_t)max_dests);
-  if (vec) b += al(8 * (size_t)max_dests) + al(4 * (size_t)max_dests) + al(2 * (size_t)C * nv);
-  else b += al(8 * (size_t)max_stage) + al(8 * (size_t)max_runs) + (sym ? 2 : 1) * al(2 * (size_t)max_dests);
-  return b + al(2 * (size_t)C * nv) + al(2 * (size_t)C * ns) + 16;
+  size_t b = al(24 * (size_t)max_nodes) + al(8 * (size_t)(max_slots + 1));
+  const size_t rec = al(4 * (size_t)(max_dests / 32)) + al((size_t)max_dests);  // gi, dcnt
+  if (vec) b += rec + al(8 * (size_t)max_dests) + al(4 * (size_t)max_dests) + al(2 * (size_t)C * nv);
+  else b += al(8 * (size_t)max_stage) + 2 * (rec + al(8 * (size_t)max_runs) + (sym ? 2 : 1) * al(2 * (size_t)max_dests));
+  return b + al(2 * (size_t)C * nv) + al(2 * (size_t)C * ns) + 32;
 }
 
 // ---- 1-D TMA (cp.async.bulk global -> shared, completion on an mbarrier) for the contiguous plan records
@@ -580,16 +586,38 @@ __device__ __forceinline__ void tma_reduce_add_f64(double* dst, const double* sr
                : "memory");
 }
 
-struct TileSmem
+struct TileRec  // dest-side records of one tile
 {
-  double *Xs, *stage, *ebuf, *fs;
   int2* runs;
   unsigned* gi;
   int* dk;
-  uint16_t *spos, *spos2, *cnode, *cslot, *crow;
+  uint16_t *spos, *spos2;
   uint8_t* dcnt;
-  unsigned long long *barR, *barC;
+  unsigned long long* bar;
 };
+struct TileSmem
+{
+  double *Xs, *stage, *ebuf, *fs;
+  TileRec R0;          // first copy of the dest-side records
+  unsigned rstride;    // bytes to the second copy (matrix kernel)
+  uint16_t *cnode, *cslot, *crow;
+  unsigned long long* barC;
+};
+
+// copy c (0 / 1) of the dest-side records: pointer arithmetic instead of an indexed array keeps TileSmem in registers
+__device__ __forceinline__ TileRec tile_rec(const TileSmem& S, unsigned c)
+{
+  const size_t o = (size_t)c * S.rstride;
+  TileRec R;
+  R.runs = reinterpret_cast<int2*>(reinterpret_cast<unsigned char*>(S.R0.runs) + o);
+  R.gi = reinterpret_cast<unsigned*>(reinterpret_cast<unsigned char*>(S.R0.gi) + o);
+  R.dk = S.R0.dk;
+  R.spos = reinterpret_cast<uint16_t*>(reinterpret_cast<unsigned char*>(S.R0.spos) + o);
+  R.spos2 = reinterpret_cast<uint16_t*>(reinterpret_cast<unsigned char*>(S.R0.spos2) + o);
+  R.dcnt = S.R0.dcnt + o;
+  R.bar = S.R0.bar + c;
+  return R;
+}
 
 __device__ __forceinline__ TileSmem tile_carve(unsigned char* sp, const TilePlanD& P, int nv, int ns, bool vec, bool sym)
 {
@@ -599,17 +627,21 @@ __device__ __forceinline__ TileSmem tile_carve(unsigned char* sp, const TilePlan
   S.stage = reinterpret_cast<double*>(sp); if (!vec) sp += al(8 * (size_t)P.max_stage);
   S.ebuf = reinterpret_cast<double*>(sp); sp += al(8 * (size_t)(P.max_slots + 1));
   S.fs = reinterpret_cast<double*>(sp); if (vec) sp += al(8 * (size_t)P.max_dests);
-  S.runs = reinterpret_cast<int2*>(sp); if (!vec) sp += al(8 * (size_t)P.max_runs);
-  S.gi = reinterpret_cast<unsigned*>(sp); sp += al(4 * (size_t)(P.max_dests / 32));
-  S.dk = reinterpret_cast<int*>(sp); if (vec) sp += al(4 * (size_t)P.max_dests);
-  S.spos = reinterpret_cast<uint16_t*>(sp); if (!vec) sp += al(2 * (size_t)P.max_dests);
-  S.spos2 = reinterpret_cast<uint16_t*>(sp); if (!vec && sym) sp += al(2 * (size_t)P.max_dests);
-  S.dcnt = reinterpret_cast<uint8_t*>(sp); sp += al((size_t)P.max_dests);
+  unsigned char* r0 = sp;
+  TileRec& R = S.R0;
+  R.runs = reinterpret_cast<int2*>(sp); if (!vec) sp += al(8 * (size_t)P.max_runs);
+  R.gi = reinterpret_cast<unsigned*>(sp); sp += al(4 * (size_t)(P.max_dests / 32));
+  R.dk = reinterpret_cast<int*>(sp); if (vec) sp += al(4 * (size_t)P.max_dests);
+  R.spos = reinterpret_cast<uint16_t*>(sp); if (!vec) sp += al(2 * (size_t)P.max_dests);
+  R.spos2 = reinterpret_cast<uint16_t*>(sp); if (!vec && sym) sp += al(2 * (size_t)P.max_dests);
+  R.dcnt = reinterpret_cast<uint8_t*>(sp); sp += al((size_t)P.max_dests);
+  S.rstride = (unsigned)(sp - r0);
+  if (!vec) sp += S.rstride;  // second copy
   S.cnode = reinterpret_cast<uint16_t*>(sp); sp += al(2 * (size_t)P.C * nv);
   S.cslot = reinterpret_cast<uint16_t*>(sp); sp += al(2 * (size_t)P.C * ns);
   S.crow = reinterpret_cast<uint16_t*>(sp); if (vec) sp += al(2 * (size_t)P.C * nv);
-  S.barR = reinterpret_cast<unsigned long long*>(sp);
-  S.barC = S.barR + 1;
+  R.bar = reinterpret_cast<unsigned long long*>(sp);
+  S.barC = R.bar + 2;
   return S;
 }
 
@@ -632,21 +664,21 @@ __device__ __forceinline__ TileHdr load_hdr(const int4* __restrict__ hdr, int t)
 
 // TMA bulk copies of one tile's dest-side records (R) and cell-side records (C), issued by one thread
 template <bool VEC, bool SYM>
-__device__ __forceinline__ void tma_records(const TileSmem& S, const TilePlanD& P, const TileHdr& h)
+__device__ __forceinline__ void tma_records(const TileRec& R, const TilePlanD& P, const TileHdr& h)
 {
   const unsigned nd16 = (unsigned)((h.nd + 15) & ~15), ng4 = (unsigned)((((h.nd + 31) >> 5) + 3) & ~3);
   const unsigned nr2 = VEC ? 0u : (unsigned)((h.nr + 1) & ~1);
-  mbar_expect_tx(S.barR, nd16 * (VEC ? 5 : (SYM ? 5 : 3)) + ng4 * 4 + nr2 * 8);
+  mbar_expect_tx(R.bar, nd16 * (VEC ? 5 : (SYM ? 5 : 3)) + ng4 * 4 + nr2 * 8);
   if (!nd16) return;
-  tma_load_1d(S.dcnt, P.dest_cnt + h.dest_off, nd16, S.barR);
-  tma_load_1d(S.gi, P.ginfo + (h.dest_off >> 5), ng4 * 4, S.barR);
+  tma_load_1d(R.dcnt, P.dest_cnt + h.dest_off, nd16, R.bar);
+  tma_load_1d(R.gi, P.ginfo + (h.dest_off >> 5), ng4 * 4, R.bar);
   if (VEC)
-    tma_load_1d(S.dk, P.dest_k + h.dest_off, nd16 * 4, S.barR);
+    tma_load_1d(R.dk, P.dest_k + h.dest_off, nd16 * 4, R.bar);
   else
   {
-    tma_load_1d(S.spos, P.dest_spos + h.dest_off, nd16 * 2, S.barR);
-    if (SYM) tma_load_1d(S.spos2, P.dest_spos2 + h.dest_off, nd16 * 2, S.barR);
-    if (nr2) tma_load_1d(S.runs, P.runs + h.run_off, nr2 * 8, S.barR);
+    tma_load_1d(R.spos, P.dest_spos + h.dest_off, nd16 * 2, R.bar);
+    if (SYM) tma_load_1d(R.spos2, P.dest_spos2 + h.dest_off, nd16 * 2, R.bar);
+    if (nr2) tma_load_1d(R.runs, P.runs + h.run_off, nr2 * 8, R.bar);
   }
 }
 template <bool VEC>
@@ -677,11 +709,11 @@ __device__ __forceinline__ void load_vertex(const MeshD& mesh, int node, double&
 
 // sum of record k = column (k & 31) of its group's slot block; the trip count is the group's largest count
 // (warp-uniform: no divergence bookkeeping), rows past the lane's own count are not read
-__device__ __forceinline__ double tile_record_sum(const TileSmem& S, int k)
+__device__ __forceinline__ double tile_record_sum(const double* ebuf, const TileRec& R, int k)
 {
-  const unsigned g = S.gi[k >> 5];
-  const double* e = S.ebuf + (g & 0xffffu) + (k & 31);
-  const int cmax = (int)(g >> 16), cnt = S.dcnt[k];
+  const unsigned g = R.gi[k >> 5];
+  const double* e = ebuf + (g & 0xffffu) + (k & 31);
+  const int cmax = (int)(g >> 16), cnt = R.dcnt[k];
   double s0 = 0.0, s1 = 0.0;
   int i = 0;
 #pragma unroll 1
@@ -694,51 +726,50 @@ __device__ __forceinline__ double tile_record_sum(const TileSmem& S, int k)
   return s0 + s1;
 }
 
-// Persistent CTAs (2 per SM) walk the tiles with stride gridDim.x; while tile t computes, the records of tile t+1
-// arrive by TMA and its vertex coordinates travel through registers, so the per-tile latency chain
-// (header -> vertex ids -> coordinates -> records) is off the critical path (profiles/r01_k: that chain, not a
-// throughput limit, bounded the one-tile-per-CTA kernel).  Buffers are single: each is refilled right after the
-// barrier that ends its last use.
+// Persistent CTAs (2 per SM) walk the tiles with stride gridDim.x.  While tile t computes, the records of tile t+1
+// arrive by TMA, its vertex coordinates travel through registers and the copy engine is still adding tile t-1 into
+// A.val: the per-tile latency chain (header -> vertex ids -> coordinates -> records) and the bulk reductions are
+// off the critical path (profiles/r01_k: that chain, not a throughput limit, bounded the one-tile-per-CTA kernel).
 //   top      vertex id of tile t+1 -> register
-//   phase 1  wait C(t); thread = cell: element matrix -> slots; then x[vertex id] of t+1 -> registers
-//   sync 1   TMA C(t+1)
+//   phase 1  wait C(t); thread = cell: element matrix -> slots; then x[vertex id] of t+1 -> registers;
+//            issuing lanes: wait until the reductions of t-1 have read the staging buffer
+//   sync 1   TMA C(t+1), TMA R(t+1) into the other record buffer; zero the staging buffer
+//   sync 1b
 //   phase 2  wait R(t); thread = record: column sum -> staging position(s); vertex registers -> Xs
-//   sync 2
-//   phase 3  one lane per warp: TMA bulk reduce-add per run; wait until the staging buffer has been read
-//   sync 3   TMA R(t+1); zero the staging buffer for t+1; header of t+2
+//   sync 2   warp 0 issues the TMA bulk reduce-add of the tile's runs and moves on
 // SYM: the element matrix is symmetric and so are dofmaps and bc markers of both sides: only the upper triangle is
 // stored and summed, every record feeds entry (r, c) and entry (c, r).
 template <int TD, bool SYM>
-__global__ void __launch_bounds__(MPCX_TILE_THREADS)
+__global__ void __launch_bounds__(MPCX_TILE_THREADS, 2)
 k_ptile_matrix_p1(TilePlanD P, int nt, IntD in, MeshD mesh, CsrD A)
 {
   constexpr int NV = TD + 1, NS = SYM ? NV * (NV + 1) / 2 : NV * NV, NT = MPCX_TILE_THREADS;
   extern __shared__ __align__(16) unsigned char tile_smem[];
   const TileSmem S = tile_carve(tile_smem, P, NV, NS, false, SYM);
   const int tid = threadIdx.x;
+  const bool issuer = tid < 32;  // warp 0 hands the runs to the copy engine, one run per lane and trip
   int t = blockIdx.x;
   if (t >= nt) return;
-  if (tid == 0) { mbar_init(S.barR, 1); mbar_init(S.barC, 1); }
+  if (tid == 0) { mbar_init(S.R0.bar, 1); mbar_init(S.R0.bar + 1, 1); mbar_init(S.barC, 1); }
   __syncthreads();
   TileHdr h = load_hdr(P.hdr, t), hn = h;
-  if (tid == 0) { tma_records<false, SYM>(S, P, h); tma_cells<false>(S, P, t, NV, NS); }
-  for (int i = tid; i < (h.stage >> 1); i += NT) reinterpret_cast<double2*>(S.stage)[i] = make_double2(0.0, 0.0);
+  if (tid == 0) { tma_records<false, SYM>(S.R0, P, h); tma_cells<false>(S, P, t, NV, NS); }
   for (int i = tid; i < h.nn; i += NT)
     load_vertex(mesh, __ldg(P.node_ids + h.node_off + i), S.Xs[3 * i], S.Xs[3 * i + 1], S.Xs[3 * i + 2]);
   int tn = t + gridDim.x;
   bool has_next = tn < nt;
   if (has_next) hn = load_hdr(P.hdr, tn);
   __syncthreads();
-  unsigned phase = 0;
-  for (;;)
+  for (unsigned it = 0;; ++it)
   {
+    const TileRec R = tile_rec(S, it & 1);
     const long long first = (long long)t * NT;
     const int nc_t = (int)((P.n_bulk - first) < NT ? (P.n_bulk - first) : NT);
     int nid = -1;
     if (has_next && tid < hn.nn) nid = __ldg(P.node_ids + hn.node_off + tid);
 
     // phase 1: thread = cell; element matrix entries to their slots
-    mbar_wait(S.barC, phase);
+    mbar_wait(S.barC, it & 1);
     if (tid < nc_t)
     {
       double X[NV][3];
@@ -783,42 +814,42 @@ k_ptile_matrix_p1(TilePlanD P, int nt, IntD in, MeshD mesh, CsrD A)
     }
     double xg0 = 0.0, xg1 = 0.0, xg2 = 0.0;
     if (nid >= 0) load_vertex(mesh, nid, xg0, xg1, xg2);
-    __syncthreads();  // 1: element buffer complete; cell records and Xs are free
-    if (tid == 0 && has_next) tma_cells<false>(S, P, tn, NV, NS);
+    if (issuer) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");  // reductions of t-1 have read the staging buffer
+    __syncthreads();  // 1: element buffer complete; cell records, Xs, staging buffer and the other record buffer are free
+    if (tid == 0 && has_next) { tma_cells<false>(S, P, tn, NV, NS); tma_records<false, SYM>(tile_rec(S, (it & 1) ^ 1), P, hn); }
+    for (int i = tid; i < (h.stage >> 1); i += NT) reinterpret_cast<double2*>(S.stage)[i] = make_double2(0.0, 0.0);
+    __syncthreads();  // 1b: staging buffer zeroed
 
     // phase 2: thread = record; the sum goes to its staging position (and the transposed entry's)
-    mbar_wait(S.barR, phase);
+    mbar_wait(R.bar, (it >> 1) & 1);
     for (int k = tid; k < h.nd; k += NT)
     {
-      const double v = tile_record_sum(S, k);
-      S.stage[S.spos[k]] = v;
-      if (SYM) S.stage[S.spos2[k]] = v;
+      const double v = tile_record_sum(S.ebuf, R, k);
+      S.stage[R.spos[k]] = v;
+      if (SYM) S.stage[R.spos2[k]] = v;
     }
     if (nid >= 0) { S.Xs[3 * tid] = xg0; S.Xs[3 * tid + 1] = xg1; S.Xs[3 * tid + 2] = xg2; }
     if (has_next)
       for (int i = tid + NT; i < hn.nn; i += NT)  // a tile with more vertices than threads (never on simplicial meshes)
         load_vertex(mesh, __ldg(P.node_ids + hn.node_off + i), S.Xs[3 * i], S.Xs[3 * i + 1], S.Xs[3 * i + 2]);
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // staging writes -> visible to the copy engine
-    __syncthreads();  // 2: staging buffer and next Xs complete
+    __syncthreads();  // 2: staging buffer and next Xs complete; element buffer free
 
-    // phase 3: the bulk reduction takes uniform operands: one lane per warp issues, the 16 warps side by side
-    if ((tid & 31) == 0 && (tid >> 5) < h.nr)
+    // warp 0 issues the bulk reductions (uniform operands: the lanes take turns) and moves on to the next tile
+    if (issuer)
     {
-      for (int r = tid >> 5; r < h.nr; r += NT / 32)
+      for (int r = tid; r < h.nr; r += 32)
       {
-        const int2 rr = S.runs[r];
+        const int2 rr = R.runs[r];
         tma_reduce_add_f64(A.val + rr.x, S.stage + (rr.y & 0xffff), (unsigned)(rr.y >> 16) * 8u);
       }
       asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-      asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");  // the staging buffer must outlive the reads
     }
-    __syncthreads();  // 3: staging buffer and dest records are free
     if (!has_next) break;
-    if (tid == 0) tma_records<false, SYM>(S, P, hn);
-    for (int i = tid; i < (hn.stage >> 1); i += NT) reinterpret_cast<double2*>(S.stage)[i] = make_double2(0.0, 0.0);
-    h = hn; t = tn; tn += gridDim.x; has_next = tn < nt; phase ^= 1u;
+    h = hn; t = tn; tn += gridDim.x; has_next = tn < nt;
     if (has_next) hn = load_hdr(P.hdr, tn);
   }
+  if (issuer) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");  // the staging buffer must outlive the reads
 }
 
 // Load vector b_i = c0 |K|/((d+1)(d+2)) (f_i + sum_j f_j) (cpp/assemble_vector.cpp:163-185 with the P1 source
@@ -835,10 +866,11 @@ k_ptile_vector_p1(TilePlanD P, int nt, IntD in, MeshD mesh, int w_by_row, double
   const int tid = threadIdx.x;
   int t = blockIdx.x;
   if (t >= nt) return;
-  if (tid == 0) { mbar_init(S.barR, 1); mbar_init(S.barC, 1); }
+  const TileRec R = S.R0;
+  if (tid == 0) { mbar_init(R.bar, 1); mbar_init(S.barC, 1); }
   __syncthreads();
   TileHdr h = load_hdr(P.hdr, t), hn = h;
-  if (tid == 0) { tma_records<true, false>(S, P, h); tma_cells<true>(S, P, t, NV, NV); }
+  if (tid == 0) { tma_records<true, false>(R, P, h); tma_cells<true>(S, P, t, NV, NV); }
   for (int i = tid; i < h.nn; i += NT)
     load_vertex(mesh, __ldg(P.node_ids + h.node_off + i), S.Xs[3 * i], S.Xs[3 * i + 1], S.Xs[3 * i + 2]);
   if (w_by_row)
@@ -893,8 +925,8 @@ k_ptile_vector_p1(TilePlanD P, int nt, IntD in, MeshD mesh, int w_by_row, double
     __syncthreads();  // 1: element buffer complete; cell records, Xs and fs are free
     if (tid == 0 && has_next) tma_cells<true>(S, P, tn, NV, NV);
 
-    mbar_wait(S.barR, phase);
-    for (int k = tid; k < h.nd; k += NT) atomicAdd(b + S.dk[k], tile_record_sum(S, k));
+    mbar_wait(R.bar, phase);
+    for (int k = tid; k < h.nd; k += NT) atomicAdd(b + R.dk[k], tile_record_sum(S.ebuf, R, k));
     if (nid >= 0) { S.Xs[3 * tid] = xg0; S.Xs[3 * tid + 1] = xg1; S.Xs[3 * tid + 2] = xg2; }
     if (fid >= 0) S.fs[tid] = fg;
     if (has_next)
@@ -906,7 +938,7 @@ k_ptile_vector_p1(TilePlanD P, int nt, IntD in, MeshD mesh, int w_by_row, double
     }
     __syncthreads();  // 2: dest records are free; next Xs / fs complete
     if (!has_next) break;
-    if (tid == 0) tma_records<true, false>(S, P, hn);
+    if (tid == 0) tma_records<true, false>(R, P, hn);
     h = hn; t = tn; tn += gridDim.x; has_next = tn < nt; phase ^= 1u;
     if (has_next) hn = load_hdr(P.hdr, tn);
   }
