@@ -322,43 +322,78 @@ def run_ours(args):
 
 
 def run_e2e(args, P, A, b, step, world, barrier):
+    """End to end through the public API with HOST buffers.  Every step uploads the step's INPUT VALUES from
+    pinned host memory (vertex coordinates, the coefficient, Dirichlet values, constraint coefficients) and
+    downloads the assembled CSR values and the RHS to pinned host memory.  The mesh topology / dofmaps /
+    constraint structure stay on the device together with the sparsity pattern and the tile plans derived from
+    them -- the state the reference keeps in its Form / FunctionSpace / cached Mat between assemblies
+    (python/src/dolfinx_mpc/assemble_matrix.py:49-51).  Steps are pipelined over three streams (upload of step
+    k+1 and download of step k overlap; value arrays double-buffered); the time is K steps start to finish."""
     import torch
 
     from dolfinx_mpc_b200 import device as dev
 
     mesh, V, mpc, f = P["mesh"], P["V"], P["mpc"], P["f"]
-    mdev, sdev, cdev = dev.mesh_dev(mesh), dev.space_dev(V), dev.mpc_dev(mpc)
-    bc_key = [k for k in V._dev if isinstance(k, tuple) and k[0] in ("bc_markers", "lift")]
-    dst = [mdev["x"], mdev["x_dofmap"], sdev["dofmap"], f.device_array]
-    dst += [cdev[k] for k in ("is_slave", "masters", "coeffs", "offsets", "c2s", "c2s_off", "slaves")]
-    for k in bc_key:
-        v = V._dev[k]
-        dst += list(v) if isinstance(v, tuple) else [v]
-    dst = [t for t in dst if t is not None and t.numel() > 0]
-    src = [t.cpu().pin_memory() for t in dst]
-    out_val = torch.empty(A.nnz, dtype=torch.float64).pin_memory()
-    out_b = torch.empty(b.data.numel(), dtype=torch.float64).pin_memory()
+    mdev, cdev = dev.mesh_dev(mesh), dev.mpc_dev(mpc)
+    values = [mdev["x"], f.device_array, cdev["coeffs"]]
+    for k_, v in V._dev.items():  # Dirichlet values (markers are structure)
+        if isinstance(k_, tuple) and k_[0] == "lift" and v is not None:
+            values.append(v[1])
+    values = [t for t in values if t is not None and t.numel() > 0]
+    src = [t.cpu().pin_memory() for t in values]
     h2d = sum(t.numel() * t.element_size() for t in src)
-    d2h = out_val.numel() * 8 + out_b.numel() * 8
+    nnz, nb = A.nnz, b.data.numel()
+    val_bufs = [A._val_storage, torch.zeros_like(A._val_storage)]
+    b_bufs = [b.data, torch.zeros(nb + (nb & 1), dtype=torch.float64, device=b.data.device)[:nb]]  # even capacity (mpcx.h)
+    out_val = [torch.empty(nnz, dtype=torch.float64).pin_memory() for _ in range(2)]
+    out_b = [torch.empty(nb, dtype=torch.float64).pin_memory() for _ in range(2)]
+    d2h = (nnz + nb) * 8
+    cur = torch.cuda.current_stream()
+    s_in, s_out = torch.cuda.Stream(), torch.cuda.Stream()
 
-    def e2e_step():
-        for s, d in zip(src, dst):
-            d.copy_(s, non_blocking=True)
-        step()
-        out_val.copy_(A.val, non_blocking=True)
-        out_b.copy_(b.data, non_blocking=True)
+    def run(k_steps):
+        ev_done, ev_out = [], []
+        for k in range(k_steps):
+            i = k % 2
+            ev_in = torch.cuda.Event()
+            with torch.cuda.stream(s_in):
+                if k > 0:
+                    s_in.wait_event(ev_done[k - 1])  # the previous step has read its inputs
+                for s_, d_ in zip(src, values):
+                    d_.copy_(s_, non_blocking=True)
+                ev_in.record(s_in)
+            cur.wait_event(ev_in)
+            if k >= 2:
+                cur.wait_event(ev_out[k - 2])  # this pair of output buffers has been downloaded
+            A._val_storage, A.val = val_bufs[i], val_bufs[i][:nnz]
+            b.data = b_bufs[i]
+            step()
+            e = torch.cuda.Event()
+            e.record(cur)
+            ev_done.append(e)
+            with torch.cuda.stream(s_out):
+                s_out.wait_event(e)
+                out_val[i].copy_(val_bufs[i][:nnz], non_blocking=True)
+                out_b[i].copy_(b_bufs[i], non_blocking=True)
+                eo = torch.cuda.Event()
+                eo.record(s_out)
+            ev_out.append(eo)
+        cur.wait_event(ev_out[-1])
+        if k_steps > 1:
+            cur.wait_event(ev_out[-2])
 
-    for _ in range(max(1, min(args.warmup, 2))):
-        e2e_step()
+    run(2)
     barrier()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    k = max(1, min(args.steps, 5))
+    k = max(2, min(args.steps, 8))
     ev0.record()
-    for _ in range(k):
-        e2e_step()
+    run(k)
     ev1.record()
     barrier()
     ms = ev0.elapsed_time(ev1)
+    # restore the primary buffers
+    A._val_storage, A.val = val_bufs[0], val_bufs[0][:nnz]
+    b.data = b_bufs[0]
     nc = mesh.num_cells_local
     if world > 1:
         import torch.distributed as dist
@@ -371,9 +406,11 @@ def run_e2e(args, P, A, b, step, world, barrier):
         nc = int(c.item())
     return {"value": nc * k / (ms * 1e-3), "unit": "cells/s", "h2d_bytes_per_step": int(h2d),
             "d2h_bytes_per_step": int(d2h), "ms_per_step": ms / k, "steps": k,
-            "note": "pinned host copies of every array the assembly reads (geometry, dofmaps, MPC arrays, bc markers, "
-                    "coefficient) uploaded each step; CSR values and RHS downloaded; pattern/plan stay in the "
-                    "device matrix handle like the reference's cached Mat"}
+            "note": "per step: pinned-host upload of the input VALUES (vertex coordinates, coefficient, Dirichlet values, "
+                    "constraint coefficients), assembly, download of CSR values + RHS to pinned host memory; topology "
+                    "(dofmaps, constraint structure), sparsity pattern and tile plans are cached on the device like the "
+                    "reference's Form / cached Mat; steps pipelined over 3 streams (value arrays double-buffered), "
+                    "download-bound on PCIe"}
 
 
 def main():
