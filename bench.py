@@ -189,7 +189,7 @@ def run_reference(args):
         "e2e": {"value": value, "unit": "cells/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def workload_config(n, gpus):
@@ -316,7 +316,7 @@ def run_ours(args):
                            slaves=len(mpc.slaves)),
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clk,
         }
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 
@@ -413,7 +413,26 @@ def run_e2e(args, P, A, b, step, world, barrier):
                     "download-bound on PCIe"}
 
 
+_REAL_STDOUT = None
+
+
+def _quiet_stdout():
+    """Route everything libraries print to fd 1 (NCCL's version banner, build output) to stderr, so that stdout
+    carries exactly one line: the JSON result, written by emit()."""
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+
+
+def emit(line: dict):
+    out = _REAL_STDOUT or sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
+
+
 def main():
+    _quiet_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)

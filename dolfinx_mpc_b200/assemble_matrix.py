@@ -110,8 +110,13 @@ def assemble_matrix(form: Form, constraint: Union[MultiPointConstraint, Sequence
         A = create_matrix(form, mpc0, mpc1)
     V0, V1 = form.function_spaces
     st = _dev.stream_ptr()
-    bc0_d = _bc_markers(V0, bcs, A.shape[0])
-    bc1_d = bc0_d if (V0 is V1 and A.shape[0] == A.shape[1]) else _bc_markers(V1, bcs, A.shape[1])
+    if V0 is V1:
+        # one marker array for rows and columns (a distributed matrix has extra off-process columns that no local
+        # cell references): identical markers on both sides let the tile kernels use their symmetric plan
+        bc0_d = bc1_d = _bc_markers(V0, bcs, max(A.shape))
+    else:
+        bc0_d = _bc_markers(V0, bcs, A.shape[0])
+        bc1_d = _bc_markers(V1, bcs, A.shape[1])
     mesh_s = _dev.mesh_dev(form.mesh)["struct"]
     d0 = _dev.dofmap_struct(V0, A.shape[0])
     d1 = _dev.dofmap_struct(V1, A.shape[1])
