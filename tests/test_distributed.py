@@ -1,4 +1,4 @@
-"""World-size-2 tests (gloo, CPU) of the multi-GPU host logic: slab partition, extended index map with
+"""World-size-2 and -3 tests (gloo, CPU) of the multi-GPU host logic: slab partition, extended index map with
 non-local masters as ghosts, pattern extension on the owner, and the ghost-row / ghost-entry exchange plan.
 
 The per-rank local assembly is done by the CPU oracle (the CUDA kernels need a GPU); the exchange runs through
@@ -63,12 +63,13 @@ def _worker(rank, world, port, periodic_z, n, nzc, out_dir):
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("periodic_z", [False, True])
-def test_two_rank_assembly_matches_serial(oracle, tmp_path, periodic_z):
+@pytest.mark.parametrize("world,periodic_z", [(2, False), (2, True), (3, False), (3, True)])
+def test_multi_rank_assembly_matches_serial(oracle, tmp_path, world, periodic_z):
+    """world = 3 adds a middle rank that owns one interface and ghosts another (the 4- and 8-GPU layouts)."""
     from dolfinx_mpc_b200 import fem, generators as gen
 
-    n, nzc, world = 5, 3, 2
-    port = 29600 + (os.getpid() % 200) + (1 if periodic_z else 0)
+    n, nzc = 5, 3
+    port = 29600 + (os.getpid() % 200) + (1 if periodic_z else 0) + 2 * world
     mp.spawn(_worker, args=(world, port, periodic_z, n, nzc, str(tmp_path)), nprocs=world, join=True)
 
     # serial global problem with the same lattice numbering
@@ -109,7 +110,7 @@ def test_two_rank_assembly_matches_serial(oracle, tmp_path, periodic_z):
     assert np.allclose(bd, b, rtol=1e-12, atol=1e-14)
     assert sorted(np.concatenate([p["slaves"] for p in parts])) == sorted(data[0])
     if periodic_z:  # masters on rank 0 became extra ghosts of the last rank; rank 0 got pattern ghosts
-        assert parts[1]["nghost"] > 0 and parts[0]["ncol"] > (nzc + 1) * n * n
+        assert parts[-1]["nghost"] > 0 and parts[0]["ncol"] > (nzc + 1) * n * n
 
 
 def test_slab_index_map_roundtrip():

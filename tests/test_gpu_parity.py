@@ -253,3 +253,78 @@ def test_tile_plan_properties(oracle):
     assert_vec_close(b.array, b_o)
     mpcx.assemble_vector(L, mpc, b=b)
     assert_vec_close(b.array, b_o)
+
+
+def test_full_size_properties():
+    """BASELINE.json configs[1] at full size (256^3 P1 Poisson, periodic x/y, Dirichlet z; 99.5 M cells, 253 M nnz),
+    where the oracle is too slow: size-independent properties, all evaluated on the device.
+    * tile path and atomic-scatter path (two independent kernels and plans) agree entry-wise within 1e-10;
+    * constants are in the null space of the constrained Laplacian on rows that are neither slave nor Dirichlet,
+      once the Dirichlet columns are put back (K^T A K of a consistent stiffness matrix);
+    * slave rows and Dirichlet rows hold exactly the diagonal value; the matrix is symmetric (checked through
+      x^T A y == y^T A x for two random vectors);
+    * re-assembly into the same matrix reproduces the values within round-off of the atomics' ordering;
+    * sum(b) before lifting equals the integral of f computed independently, K^T preserving sums for periodic
+      constraints with coefficient 1."""
+    import os
+
+    import torch
+
+    import bench
+    import dolfinx_mpc_b200 as mpcx
+    from dolfinx_mpc_b200 import device as dev
+
+    n = int(os.environ.get("MPCX_TEST_FULL_N", "256"))
+    P = bench.build_problem(n)
+    mesh, V, mpc, a, L, bcs, f = (P[k] for k in ("mesh", "V", "mpc", "a", "L", "bcs", "f"))
+    A = mpcx.create_matrix(a, mpc)
+    assert A.scatter == "tile"
+    mpcx.assemble_matrix(a, mpc, bcs=bcs, A=A)
+    assert all(info["symmetric"] == 1 for _, info in A._tile_plans.values())
+    v_tile = A.val.clone()
+    A2 = mpcx.create_matrix(a, mpc)
+    A2.scatter = "atomic"
+    mpcx.assemble_matrix(a, mpc, bcs=bcs, A=A2)
+    N = V.num_dofs
+    rows = torch.repeat_interleave(torch.arange(N, device=A.val.device), A.row_ptr[1:] - A.row_ptr[:-1])
+    cols = A.col.long()
+    rownorm = torch.zeros(N, dtype=torch.float64, device=A.val.device).scatter_reduce_(0, rows, v_tile.abs(), "amax")
+    assert bool(((v_tile - A2.val).abs() <= RTOL * torch.maximum(A2.val.abs(), rownorm[rows])).all())
+    del A2
+
+    def spmv(x):
+        return torch.zeros(N, dtype=torch.float64, device=x.device).index_add_(0, rows, v_tile * x[cols])
+
+    is_slave = dev.to_dev(mpc.is_slave).bool()
+    is_bc = torch.zeros(N, dtype=torch.bool, device=A.val.device)
+    is_bc[dev.to_dev(bcs[0].dofs).long()] = True
+    free = ~(is_slave | is_bc)
+    # rows of free dofs: A restricted to non-bc columns times ones == -(columns zeroed by the bc), i.e. the full
+    # constrained Laplacian annihilates constants; equivalently the lifting vector with g = 1 equals -A_free @ 1.
+    ones = free.double()
+    r = spmv(ones)
+    lift = mpcx.create_vector(mpc)
+    bc_one = [type(bcs[0])(V, bcs[0].dofs, 1.0)]
+    mpcx.apply_lifting(lift, [a], [bc_one], mpc)
+    scale = float(v_tile.abs().max())
+    assert float((r - lift.data)[free].abs().max()) <= 1e-10 * scale
+    # slave / Dirichlet rows: diagonal only
+    diag = rows == cols
+    special = (is_slave | is_bc)[rows]
+    assert bool((v_tile[special & ~diag] == 0).all()) and bool((v_tile[special & diag] == 1.0).all())
+    # symmetry
+    g = torch.Generator(device=A.val.device).manual_seed(3)
+    x = torch.rand(N, dtype=torch.float64, device=A.val.device, generator=g)
+    y = torch.rand(N, dtype=torch.float64, device=A.val.device, generator=g)
+    xay, yax = float(x @ spmv(y)), float(y @ spmv(x))
+    assert abs(xay - yax) <= 1e-10 * abs(xay)
+    # re-assembly
+    mpcx.assemble_matrix(a, mpc, bcs=bcs, A=A)
+    assert bool(((A.val - v_tile).abs() <= 1e-12 * rownorm[rows]).all())
+    # load vector: K^T with unit coefficients preserves the sum; compare with the P1 quadrature of f, sum_K |K|/4 sum_v f_v
+    b = mpcx.assemble_vector(L, mpc)
+    h = 1.0 / (n - 1)
+    fx = torch.from_numpy(f.array).to(A.val.device)
+    cells = dev.to_dev(mesh.x_dofmap).long()
+    expected = float((fx[cells].sum(dim=1) * (h ** 3 / 6.0 / 4.0)).sum())
+    assert abs(float(b.data.sum()) - expected) <= 1e-10 * abs(expected)
