@@ -20,7 +20,7 @@ OK, ERR_ARG, ERR_UNSUPPORTED, ERR_CUDA, ERR_PATTERN, ERR_ALLOC = range(6)
 class Tables(C.Structure):
     _fields_ = [("tdim", C.c_int32), ("gdim", C.c_int32), ("nd", C.c_int32), ("ng", C.c_int32),
                 ("nq", C.c_int32), ("bs", C.c_int32), ("weights", C.c_void_p), ("phi", C.c_void_p),
-                ("dphi", C.c_void_p), ("gdphi", C.c_void_p)]
+                ("dphi", C.c_void_p), ("gdphi", C.c_void_p), ("nfacets", C.c_int32), ("facet_tangents", C.c_void_p)]
 
 
 class MeshS(C.Structure):
@@ -49,7 +49,7 @@ class IntegralS(C.Structure):
                 ("num_cells", C.c_int64), ("coeffs", C.c_void_p), ("cstride", C.c_int32),
                 ("coeff_nodal", C.c_void_p), ("coeff_dofmap", C.c_void_p), ("coeff_nd", C.c_int32),
                 ("coeff_bs", C.c_int32), ("num_constants", C.c_int32), ("constants", C.c_double * MAX_CONSTANTS),
-                ("slave_cells", C.c_void_p), ("num_slave_cells", C.c_int64)]
+                ("slave_cells", C.c_void_p), ("num_slave_cells", C.c_int64), ("local_facets", C.c_void_p)]
 
 
 class PlanS(C.Structure):

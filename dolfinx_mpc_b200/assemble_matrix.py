@@ -126,16 +126,17 @@ def assemble_matrix(form: Form, constraint: Union[MultiPointConstraint, Sequence
     keep = []
     A.zeroEntries()
     for it in form.integrals:
-        if it.integral_type != "cell":
+        if it.integral_type not in ("cell", "exterior_facet"):
             raise RuntimeError(f"{it.integral_type} integrals have no device kernel yet")
         s = _dev.integral_struct(form, it, (mpc0, mpc1), keep)
-        tile = A.tile_plan(form, it, s, bc0_d, bc1_d, (id(mpc0), id(mpc1))) if A.scatter == "tile" else None
+        facet = it.integral_type == "exterior_facet"  # surface-sized: generic kernel, row search per entry
+        tile = A.tile_plan(form, it, s, bc0_d, bc1_d, (id(mpc0), id(mpc1))) if A.scatter == "tile" and not facet else None
         if tile is not None:
             _lib.check(lib.mpcx_assemble_matrix_tiled_f64(C.byref(s), C.byref(mesh_s), C.byref(d0), C.byref(d1),
                                                           _dev.ptr(bc0_d), _dev.ptr(bc1_d), C.byref(m0), C.byref(m1),
                                                           C.byref(As), tile[0], st))
             continue
-        plan = A.plan(form, it)
+        plan = None if facet else A.plan(form, it)
         _lib.check(lib.mpcx_assemble_matrix_f64(C.byref(s), C.byref(mesh_s), C.byref(d0), C.byref(d1),
                                                 _dev.ptr(bc0_d), _dev.ptr(bc1_d), C.byref(m0), C.byref(m1),
                                                 C.byref(As), None if plan is None else C.byref(plan), st))

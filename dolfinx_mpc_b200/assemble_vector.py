@@ -36,10 +36,10 @@ def assemble_vector(form: Form, constraint: MultiPointConstraint, b: Optional[Ve
     m = _dev.mpc_dev(constraint)["struct"]
     keep = []
     for it in form.integrals:
-        if it.integral_type != "cell":
+        if it.integral_type not in ("cell", "exterior_facet"):
             raise RuntimeError(f"{it.integral_type} integrals have no device kernel yet")
         s = _dev.integral_struct(form, it, (constraint,), keep)
-        plan = _vector_tile_plan(form, it, s, constraint, mesh_s, dm)
+        plan = None if it.integral_type != "cell" else _vector_tile_plan(form, it, s, constraint, mesh_s, dm)
         if plan is not None:
             _lib.check(lib.mpcx_assemble_vector_tiled_f64(C.byref(s), C.byref(mesh_s), C.byref(dm), C.byref(m),
                                                           _dev.ptr(b.data), plan[0], st))
@@ -144,7 +144,7 @@ def apply_lifting(b: Vector, form: Sequence[Form], bcs: Sequence[Sequence[Dirich
         d1 = _dev.dofmap_struct(V1, n1)
         m0 = _dev.mpc_dev(constraint)["struct"]
         for it in a.integrals:
-            if it.integral_type != "cell":
+            if it.integral_type not in ("cell", "exterior_facet"):
                 raise RuntimeError(f"{it.integral_type} integrals have no device kernel yet")
             s = _dev.integral_struct(a, it, (constraint,), keep)
             # cells of this integral with a Dirichlet column: found once on the device, then reused

@@ -83,6 +83,7 @@ struct Tab
 {
   int tdim, gdim, nd, ng, nq, bs;
   const double *w, *phi, *dphi, *gdphi;
+  const double* ftan;  // facet tables: tangents of every local facet; in an entity view: of this facet (or null)
 };
 struct MeshD
 {
@@ -117,7 +118,25 @@ struct IntD
   double c[MPCX_MAX_CONSTANTS];
   const int* slave_cells;
   long long nslave_cells;
+  const int* lfacets;  // exterior-facet integral: local facet of every active entity
 };
+
+// Tables of one entity: the cell itself, or local facet lfacets[index] of it (cpp/assemble_matrix.cpp:361-362)
+__device__ __forceinline__ Tab entity_view(const Tab& t, const IntD& in, long long index)
+{
+  Tab v = t;
+  if (in.lfacets)
+  {
+    const int f = __ldg(in.lfacets + index);
+    v.phi += (size_t)f * t.nq * t.nd;
+    v.dphi += (size_t)f * t.nq * t.tdim * t.nd;
+    v.gdphi += (size_t)f * t.nq * t.tdim * t.ng;
+    v.ftan = t.ftan + (size_t)f * (t.tdim - 1) * t.tdim;
+  }
+  else
+    v.ftan = nullptr;
+  return v;
+}
 
 __device__ __forceinline__ long long csr_find(const CsrD& A, int row, int c)
 {
@@ -138,10 +157,34 @@ __device__ __forceinline__ void csr_add(const CsrD& A, int row, int c, double v)
   else g_dev_err = MPCX_ERR_PATTERN;
 }
 
-// Geometry at quadrature point q (all lanes redundantly): K = J^-1 as K[a*3+k], detJ.
+// Geometry at quadrature point q (all lanes redundantly): K = J^-1 as K[a*3+k], detJ.  For a facet view detJ is
+// the surface measure |J t| (2-D) / |J t1 x J t2| (3-D), so that w_q |detJ| is the scale in both cases.
+__device__ __forceinline__ void jacobian_cell(const Tab& t, int q, const double* X, double* K, double& detJ, double* J);
 __device__ __forceinline__ void jacobian(const Tab& t, int q, const double* X, double* K, double& detJ)
 {
-  double J[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+  double J[9];
+  jacobian_cell(t, q, X, K, detJ, J);
+  if (t.ftan)
+  {
+    double a[3] = {0, 0, 0}, b[3] = {0, 0, 0};
+    for (int k = 0; k < t.tdim; ++k)
+      for (int c = 0; c < t.tdim; ++c)
+      {
+        a[k] += J[k * 3 + c] * __ldg(t.ftan + c);
+        if (t.tdim == 3) b[k] += J[k * 3 + c] * __ldg(t.ftan + 3 + c);
+      }
+    if (t.tdim == 2)
+      detJ = sqrt(a[0] * a[0] + a[1] * a[1]);
+    else
+    {
+      const double cx = a[1] * b[2] - a[2] * b[1], cy = a[2] * b[0] - a[0] * b[2], cz = a[0] * b[1] - a[1] * b[0];
+      detJ = sqrt(cx * cx + cy * cy + cz * cz);
+    }
+  }
+}
+__device__ __forceinline__ void jacobian_cell(const Tab& t, int q, const double* X, double* K, double& detJ, double* J)
+{
+  for (int i = 0; i < 9; ++i) J[i] = 0.0;
   for (int a = 0; a < t.tdim; ++a)
     for (int g = 0; g < t.ng; ++g)
     {
@@ -315,7 +358,7 @@ k_matrix_generic(Tab t, IntD in, MeshD mesh, const int* __restrict__ dm0, const 
     for (int e = lane; e < nd0; e += 32) d0[e] = __ldg(dm0 + (long long)cell * nd0 + e);
     for (int e = lane; e < nd1; e += 32) d1[e] = __ldg(dm1 + (long long)cell * nd1 + e);
     __syncwarp();
-    tabulate_warp(t, in.kernel, in.c, X, w, Ae, g, lane);
+    tabulate_warp(entity_view(t, in, index), in.kernel, in.c, X, w, Ae, g, lane);
     for (int e = lane; e < n0 * n1; e += 32)
     {
       const int p = e / n1, q = e - p * n1;
@@ -374,7 +417,7 @@ k_vector_generic(Tab t, IntD in, MeshD mesh, const int* __restrict__ dm, int nd,
     __syncwarp();
     load_cell(mesh, in, index, cell, X, w, lane);
     __syncwarp();
-    tabulate_warp(t, in.kernel, in.c, X, w, be, g, lane);
+    tabulate_warp(entity_view(t, in, index), in.kernel, in.c, X, w, be, g, lane);
     for (int e = lane; e < n; e += 32)
     {
       const int ib = e / bs, ia = e - ib * bs;
@@ -424,7 +467,7 @@ k_lifting_generic(Tab t, IntD in, MeshD mesh, const int* __restrict__ dm0, const
     if (!__any_sync(0xffffffffu, any)) continue;
     load_cell(mesh, in, index, cell, X, w, lane);
     __syncwarp();
-    tabulate_warp(t, in.kernel, in.c, X, w, Ae, g, lane);  // un-zeroed A_e (cpp/lifting.h:266-299)
+    tabulate_warp(entity_view(t, in, index), in.kernel, in.c, X, w, Ae, g, lane);  // un-zeroed A_e (cpp/lifting.h:266-299)
     for (int p = lane; p < n0; p += 32)
     {
       double v = 0.0;
@@ -839,7 +882,7 @@ namespace
 // ------------------------------------------------------------------ host helpers
 Tab make_tab(const mpcx_tables* t)
 {
-  return Tab{t->tdim, t->gdim, t->nd, t->ng, t->nq, t->bs, t->weights, t->phi, t->dphi, t->gdphi};
+  return Tab{t->tdim, t->gdim, t->nd, t->ng, t->nq, t->bs, t->weights, t->phi, t->dphi, t->gdphi, t->facet_tangents};
 }
 MpcD make_mpc(const mpcx_mpc* m)
 {
@@ -854,6 +897,7 @@ IntD make_int(const mpcx_integral* in)
   if (!d.coeffs && d.wnodal) d.cstride = d.wnd * d.wbs;
   for (int i = 0; i < MPCX_MAX_CONSTANTS; ++i) d.c[i] = i < in->num_constants ? in->constants[i] : 0.0;
   d.slave_cells = in->slave_cells; d.nslave_cells = in->num_slave_cells;
+  d.lfacets = in->local_facets;
   return d;
 }
 
@@ -871,6 +915,9 @@ int check_integral(const mpcx_integral* in, bool bilinear)
   if (t->tdim != t->gdim || (t->tdim != 2 && t->tdim != 3))
     return fail(MPCX_ERR_UNSUPPORTED, "only tdim == gdim in {2, 3} has device kernels");
   if (k == MPCX_KERNEL_ELASTICITY && t->bs != t->gdim) return fail(MPCX_ERR_ARG, "elasticity needs bs == gdim");
+  if (in->local_facets && (t->nfacets <= 0 || !t->facet_tangents))
+    return fail(MPCX_ERR_ARG, "an exterior-facet integral needs facet tables");
+  if (in->local_facets && !in->cells) return fail(MPCX_ERR_ARG, "an exterior-facet integral needs the cells of its facets");
   const bool needs_w = k == MPCX_KERNEL_SOURCE || k == MPCX_KERNEL_LAPLACE_VARCOEF;
   if (needs_w && !in->coeffs && !in->coeff_nodal) return fail(MPCX_ERR_ARG, "kernel needs coefficients");
   return MPCX_OK;
@@ -988,7 +1035,7 @@ int mpcx_assemble_matrix_f64(const mpcx_integral* integral, const mpcx_mesh* mes
                     || (in.coeffs ? in.cstride == nd : (in.wnd == nd && in.wbs == 1));
   const bool closed_form = (kid == MPCX_KERNEL_LAPLACE || kid == MPCX_KERNEL_MASS || kid == MPCX_KERNEL_LAPLACE_VARCOEF)
                            && bs == 1 && p1_simplex && w_ok;
-  const bool fast = lpos && have_split && closed_form;
+  const bool fast = lpos && have_split && closed_form && !integral->local_facets;  // facets: generic kernel
   // generic kernel resources
   const int wcount = in.cstride > 0 ? in.cstride : 1;
   int spw = 3 * mesh->ng + n * n + 3 * nd + wcount + (2 * nd + 1) / 2 + 1;
@@ -1095,7 +1142,7 @@ int mpcx_assemble_vector_f64(const mpcx_integral* integral, const mpcx_mesh* mes
   const int nd = t->nd, bs = t->bs, n = nd * bs;
   const bool p1_simplex = t->nd == t->tdim + 1 && t->ng == t->tdim + 1;
   const bool w_ok = in.coeffs ? in.cstride == nd : (in.wnd == nd && in.wbs == 1);
-  if (integral->kernel == MPCX_KERNEL_SOURCE && bs == 1 && p1_simplex && w_ok)
+  if (integral->kernel == MPCX_KERNEL_SOURCE && bs == 1 && p1_simplex && w_ok && !integral->local_facets)
   {
     const long long nb = (in.ncells + 255) / 256;
     if (t->tdim == 3) MPCX_COUNT_LAUNCH(), k_vector_p1_source<3><<<(unsigned)nb, 256, 0, s>>>(in, md, dofmap->map, m.c2s_off, m, b, nullptr, 0);
@@ -1133,7 +1180,7 @@ int mpcx_apply_lifting_f64(const mpcx_integral* integral, const mpcx_mesh* mesh,
   const bool w_ok = kid != MPCX_KERNEL_LAPLACE_VARCOEF
                     || (in.coeffs ? in.cstride == nd : (in.wnd == nd && in.wbs == 1));
   if ((kid == MPCX_KERNEL_LAPLACE || kid == MPCX_KERNEL_MASS || kid == MPCX_KERNEL_LAPLACE_VARCOEF) && bs == 1
-      && p1_simplex && w_ok)
+      && p1_simplex && w_ok && !integral->local_facets)
   {
     const unsigned nb = (unsigned)((nlist + 127) / 128);
     MPCX_COUNT_LAUNCH();
@@ -1244,6 +1291,7 @@ int mpcx_assemble_matrix_tiled_f64(const mpcx_integral* integral, const mpcx_mes
   const int nd = t->nd, bs = t->bs, kid = integral->kernel;
   const bool p1_simplex = nd == t->tdim + 1 && t->ng == t->tdim + 1;
   const bool w_ok = kid != MPCX_KERNEL_LAPLACE_VARCOEF || (in.coeffs ? in.cstride == nd : (in.wnd == nd && in.wbs == 1));
+  if (integral->local_facets) return fail(MPCX_ERR_UNSUPPORTED, "the tile kernels cover cell integrals");
   if (!((kid == MPCX_KERNEL_LAPLACE || kid == MPCX_KERNEL_MASS || kid == MPCX_KERNEL_LAPLACE_VARCOEF) && bs == 1 && p1_simplex && w_ok))
     return fail(MPCX_ERR_UNSUPPORTED, "the tile kernel covers scalar P1 simplex Laplace / mass / variable-coefficient Laplace");
   if (dofmap0->nd != nd || dofmap1->nd != nd || dofmap0->bs != bs || dofmap1->bs != bs || P->ne != nd * nd || P->ng != t->ng
@@ -1302,8 +1350,8 @@ int mpcx_assemble_vector_tiled_f64(const mpcx_integral* integral, const mpcx_mes
   const int nd = t->nd, bs = t->bs;
   const bool p1_simplex = nd == t->tdim + 1 && t->ng == t->tdim + 1;
   const bool w_ok = in.coeffs ? in.cstride == nd : (in.wnd == nd && in.wbs == 1);
-  if (!(integral->kernel == MPCX_KERNEL_SOURCE && bs == 1 && p1_simplex && w_ok))
-    return fail(MPCX_ERR_UNSUPPORTED, "the vector tile kernel covers the scalar P1 simplex source term");
+  if (!(integral->kernel == MPCX_KERNEL_SOURCE && bs == 1 && p1_simplex && w_ok) || integral->local_facets)
+    return fail(MPCX_ERR_UNSUPPORTED, "the vector tile kernel covers the scalar P1 simplex source term over cells");
   if (!P->vec || dofmap->nd != nd || dofmap->bs != 1 || P->ne != nd || P->ng != t->ng || P->nrows != dofmap->num_dofs)
     return fail(MPCX_ERR_ARG, "tile plan was built for a different element or space");
   if (integral->slave_cells == nullptr && mpc->num_slaves > 0)

@@ -82,10 +82,12 @@ _tables_cache: dict = {}
 
 
 def tables_struct(tab, bs: int):
-    key = (tab.cell_type, tab.degree, tab.nq, bs, device().index)
+    key = (tab.cell_type, tab.degree, tab.nq, bs, tab.nfacets, device().index)
     if key not in _tables_cache:
         keep = [to_dev(tab.weights), to_dev(tab.phi), to_dev(tab.dphi), to_dev(tab.gdphi)]
-        s = _lib.Tables(tab.tdim, tab.gdim, tab.nd, tab.ng, tab.nq, bs, *[ptr(k) for k in keep])
+        ftan = to_dev(tab.ftan) if tab.nfacets else None
+        keep.append(ftan)
+        s = _lib.Tables(tab.tdim, tab.gdim, tab.nd, tab.ng, tab.nq, bs, *[ptr(k) for k in keep[:4]], tab.nfacets, ptr(ftan))
         _tables_cache[key] = (s, keep)
     return _tables_cache[key][0]
 
@@ -109,6 +111,10 @@ def integral_struct(form: Form, it: Integral, mpcs, keep: list) -> _lib.Integral
     if it.cells is not None and "cells" not in d:
         d["cells"] = to_dev(it.cells)
     s.cells = ptr(d.get("cells"))
+    if it.local_facets is not None:  # exterior-facet integral: (cells[i], local_facets[i]) pairs
+        if "local_facets" not in d:
+            d["local_facets"] = to_dev(it.local_facets)
+        s.local_facets = ptr(d["local_facets"])
     ncells = form.mesh.num_cells_local if it.cells is None else len(it.cells)
     s.num_cells = ncells
     if len(it.coefficients) == 1:

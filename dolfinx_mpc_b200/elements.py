@@ -17,6 +17,7 @@ from __future__ import annotations
 
 import dataclasses
 import functools
+from typing import Optional
 
 import numpy as np
 from scipy.special import roots_jacobi
@@ -158,6 +159,10 @@ class ElementTables:
     phi: np.ndarray  # (nq, nd)
     dphi: np.ndarray  # (nq, tdim, nd)
     gdphi: np.ndarray  # (nq, tdim, ng)
+    # exterior-facet tables: the arrays above hold nfacets consecutive copies, one per local facet (quadrature points
+    # of the reference facet mapped into the cell), and ftan the tangents of the reference facet map
+    nfacets: int = 0
+    ftan: Optional[np.ndarray] = None  # (nfacets, tdim - 1, tdim)
 
 
 @functools.lru_cache(maxsize=None)
@@ -170,4 +175,47 @@ def element_tables(cell_type: str, degree: int, qdegree: int) -> ElementTables:
         cell_type, degree, tdim, tdim, phi.shape[1], gdphi.shape[2], len(wts),
         np.ascontiguousarray(wts), np.ascontiguousarray(phi), np.ascontiguousarray(dphi),
         np.ascontiguousarray(gdphi),
+    )
+
+
+# Local facets as vertex tuples, DOLFINx / Basix numbering: simplex facet i is opposite vertex i; tensor-product
+# cells list their facets in lexicographic order of the vertex sets.
+FACETS = {
+    "triangle": ((1, 2), (0, 2), (0, 1)),
+    "tetrahedron": ((1, 2, 3), (0, 2, 3), (0, 1, 3), (0, 1, 2)),
+    "quadrilateral": ((0, 1), (0, 2), (1, 3), (2, 3)),
+    "hexahedron": ((0, 1, 2, 3), (0, 1, 4, 5), (0, 2, 4, 6), (1, 3, 5, 7), (2, 3, 6, 7), (4, 5, 6, 7)),
+}
+FACET_TYPE = {"triangle": "interval", "tetrahedron": "triangle", "quadrilateral": "interval", "hexahedron": "quadrilateral"}
+
+
+def reference_vertices(cell_type: str) -> np.ndarray:
+    tdim = CELL_TDIM[cell_type]
+    if is_simplex(cell_type):
+        return np.concatenate([np.zeros((1, tdim)), np.eye(tdim)])
+    return np.array([[(v >> a) & 1 for a in range(tdim)] for v in range(2**tdim)], dtype=np.float64)
+
+
+@functools.lru_cache(maxsize=None)
+def facet_tables(cell_type: str, degree: int, qdegree: int) -> ElementTables:
+    """Tables for exterior-facet integrals (the reference passes the local facet index to the generated kernel,
+    ``cpp/assemble_matrix.cpp:343-362``): per local facet the basis tabulated at the facet quadrature points.
+    The surface measure at a point is ``|J t|`` (2-D) or ``|J t_1 x J t_2|`` (3-D) with ``t`` the tangents of the
+    reference facet map, and the weights are those of the reference facet."""
+    tdim = CELL_TDIM[cell_type]
+    fpts, fw = make_quadrature(FACET_TYPE[cell_type], qdegree)
+    verts = reference_vertices(cell_type)
+    phis, dphis, gdphis, tans = [], [], [], []
+    for fv in FACETS[cell_type]:
+        v0 = verts[fv[0]]
+        t = np.array([verts[fv[a + 1]] - v0 for a in range(tdim - 1)])  # (tdim-1, tdim)
+        pts = v0[None, :] + fpts @ t
+        phi, dphi = tabulate(cell_type, degree, pts)
+        _, gdphi = tabulate(cell_type, 1, pts)
+        phis.append(phi); dphis.append(dphi); gdphis.append(gdphi); tans.append(t)
+    phi, dphi, gdphi = np.concatenate(phis), np.concatenate(dphis), np.concatenate(gdphis)
+    return ElementTables(
+        cell_type, degree, tdim, tdim, phi.shape[1], gdphi.shape[2], len(fw),
+        np.ascontiguousarray(fw), np.ascontiguousarray(phi), np.ascontiguousarray(dphi), np.ascontiguousarray(gdphi),
+        len(FACETS[cell_type]), np.ascontiguousarray(np.array(tans, dtype=np.float64)),
     )

@@ -219,16 +219,26 @@ def _qdegree(kernel: Kernel, cell_type: str, degree: int) -> int:
 
 @dataclasses.dataclass
 class Integral:
-    """One cell integral of a form: kernel id, integration domain, coefficients, constants."""
+    """One integral of a form: kernel id, integration domain, coefficients, constants.
+
+    ``facets``: (n, 2) array of (cell, local facet) pairs makes it an exterior-facet integral -- the layout of the
+    reference's facet lists (``cpp/assemble_matrix.cpp:343-348``); ``cells`` then holds the facets' cells."""
 
     kernel: Kernel
     constants: np.ndarray
     coefficients: Sequence[Function] = ()
     cells: Optional[np.ndarray] = None  # active cells (int32); None = every owned cell in order
     integral_type: str = "cell"
+    facets: Optional[np.ndarray] = None
+    local_facets: Optional[np.ndarray] = None
 
     def __post_init__(self):
         self.constants = np.ascontiguousarray(self.constants, dtype=np.float64)
+        if self.facets is not None:
+            self.facets = np.ascontiguousarray(self.facets, dtype=np.int32).reshape(-1, 2)
+            self.cells = self.facets[:, 0]
+            self.local_facets = np.ascontiguousarray(self.facets[:, 1])
+            self.integral_type = "exterior_facet"
         if self.cells is not None:
             self.cells = np.ascontiguousarray(self.cells, dtype=np.int32)
         self._dev = {}
@@ -256,8 +266,8 @@ class Form:
 
     def tables(self, integral: Integral) -> _el.ElementTables:
         V = self.function_spaces[0]
-        return _el.element_tables(self.mesh.cell_type, V.degree,
-                                  _qdegree(integral.kernel, self.mesh.cell_type, V.degree))
+        make = _el.facet_tables if integral.integral_type == "exterior_facet" else _el.element_tables
+        return make(self.mesh.cell_type, V.degree, _qdegree(integral.kernel, self.mesh.cell_type, V.degree))
 
     def active_cells(self, integral: Integral) -> np.ndarray:
         if integral.cells is None:
@@ -287,8 +297,9 @@ def laplace(V: FunctionSpace, kappa: float = 1.0, cells=None) -> Form:
     return Form(2, (V, V), [Integral(Kernel.LAPLACE, [kappa], cells=cells)])
 
 
-def mass(V: FunctionSpace, rho: float = 1.0, cells=None) -> Form:
-    return Form(2, (V, V), [Integral(Kernel.MASS, [rho], cells=cells)])
+def mass(V: FunctionSpace, rho: float = 1.0, cells=None, facets=None) -> Form:
+    """``rho * inner(u, v) * dx``, or ``* ds`` over the given exterior facets (a Robin term)."""
+    return Form(2, (V, V), [Integral(Kernel.MASS, [rho], cells=cells, facets=facets)])
 
 
 def elasticity(V: FunctionSpace, mu: float, lmbda: float, cells=None) -> Form:
@@ -302,7 +313,25 @@ def laplace_varcoef(V: FunctionSpace, w: Function, scale: float = 1.0, cells=Non
     return Form(2, (V, V), [Integral(Kernel.LAPLACE_VARCOEF, [scale], (w,), cells=cells)])
 
 
-def source(V: FunctionSpace, f: Function, scale: float = 1.0, cells=None) -> Form:
-    """``scale * inner(f, v) * dx`` with ``f`` interpolated into ``V`` (``python/benchmarks/bench_periodic.py:85-91``)."""
+def source(V: FunctionSpace, f: Function, scale: float = 1.0, cells=None, facets=None) -> Form:
+    """``scale * inner(f, v) * dx`` with ``f`` interpolated into ``V`` (``python/benchmarks/bench_periodic.py:85-91``),
+    or ``* ds`` over the given exterior facets (the traction term of ``python/tests/test_surface_integral.py:52-72``)."""
     assert f.function_space.bs == V.bs and f.function_space.nd == V.nd
-    return Form(1, (V,), [Integral(Kernel.SOURCE, [scale], (f,), cells=cells)])
+    return Form(1, (V,), [Integral(Kernel.SOURCE, [scale], (f,), cells=cells, facets=facets)])
+
+
+def locate_exterior_facets(mesh: Mesh, marker=None) -> np.ndarray:
+    """(cell, local facet) pairs of the boundary facets (facets of exactly one cell) whose vertices all satisfy
+    ``marker(x)``, x of shape (3, n) -- ``locate_entities_boundary`` + the facet-to-cell lookup DOLFINx does when it
+    builds a ``ds`` integration domain."""
+    fv = np.array(_el.FACETS[mesh.cell_type])  # (nf, nvf)
+    nc = mesh.num_cells_local
+    nodes = mesh.x_dofmap[:nc][:, fv]  # (nc, nf, nvf) geometry vertices of every local facet (P1 geometry)
+    key = np.sort(nodes.reshape(nc * fv.shape[0], -1), axis=1)
+    _, inv, cnt = np.unique(key, axis=0, return_inverse=True, return_counts=True)
+    boundary = cnt[inv.reshape(-1)] == 1
+    if marker is not None:
+        on = marker(mesh.x.T)
+        boundary &= on[nodes.reshape(nc * fv.shape[0], -1)].all(axis=1)
+    idx = np.flatnonzero(boundary)
+    return np.stack([idx // fv.shape[0], idx % fv.shape[0]], axis=1).astype(np.int32)

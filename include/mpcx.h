@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define MPCX_ABI_VERSION 1
+#define MPCX_ABI_VERSION 2
 #define MPCX_MAX_CONSTANTS 8
 
 typedef enum mpcx_status
@@ -62,6 +62,12 @@ typedef struct mpcx_tables
   const double* phi;     /* [nq][nd] */
   const double* dphi;    /* [nq][tdim][nd] */
   const double* gdphi;   /* [nq][tdim][ng] */
+  /* exterior-facet integrals (cpp/assemble_matrix.cpp:271-415): the arrays above hold nfacets consecutive tables,
+   * one per local facet (facet quadrature points mapped into the cell); facet_tangents [nfacets][tdim-1][tdim] are
+   * the tangents of the reference facet map, the surface measure being |J t| (2-D) or |J t1 x J t2| (3-D).
+   * nfacets == 0 for cell integrals. */
+  int32_t nfacets;
+  const double* facet_tangents;
 } mpcx_tables;
 
 /* Geometry: mesh.geometry().x() / dofmaps().front() (cpp/assemble_matrix.cpp:465-470).
@@ -130,6 +136,9 @@ typedef struct mpcx_integral
    * and the elimination kernel runs on this list only. */
   const int32_t* slave_cells;      /* values are POSITIONS into the active list */
   int64_t num_slave_cells;
+  /* exterior-facet integral: entity i is local facet local_facets[i] of cell cells[i] (the (cell, local facet)
+   * pairs of cpp/assemble_matrix.cpp:343-348); NULL for a cell integral.  Needs tables->nfacets > 0. */
+  const int32_t* local_facets;
 } mpcx_integral;
 
 /* Scatter plan: for every active cell and local entry (p, q) the offset of column

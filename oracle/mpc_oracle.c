@@ -53,7 +53,29 @@ typedef struct
   const double* phi;     /* [nq][nd] */
   const double* dphi;    /* [nq][tdim][nd]  reference derivatives */
   const double* gdphi;   /* [nq][tdim][ng]  geometry-map reference derivatives */
+  /* exterior-facet integrals: the arrays above hold nfacets consecutive tables, one per local facet; ftan are the
+   * tangents of the reference facet map, [nfacets][tdim-1][tdim].  nfacets == 0 for cell integrals. */
+  int32_t nfacets;
+  const double* ftan;
 } orc_tables;
+
+/* The tables of one entity: a cell (e == NULL) or local facet e[0] of a cell -- the entity_local_index argument of
+ * the UFCx kernel, passed at cpp/assemble_matrix.cpp:361-362 for exterior facets. */
+static orc_tables entity_view(const orc_tables* t, const int* e)
+{
+  orc_tables v = *t;
+  if (e && t->nfacets > 0)
+  {
+    const int f = e[0];
+    v.phi += (size_t)f * t->nq * t->nd;
+    v.dphi += (size_t)f * t->nq * t->tdim * t->nd;
+    v.gdphi += (size_t)f * t->nq * t->tdim * t->ng;
+    v.ftan = t->ftan + (size_t)f * (t->tdim - 1) * t->tdim;
+  }
+  else
+    v.ftan = NULL;
+  return v;
+}
 
 typedef void (*ufcx_kernel)(double* A, const double* w, const double* c,
                             const double* coordinate_dofs,
@@ -62,10 +84,39 @@ typedef void (*ufcx_kernel)(double* A, const double* w, const double* c,
                             void* custom_data);
 
 /* ---- geometry at one quadrature point: J = sum_g X_g (x) dpsi_g, K = J^-1 */
+/* On return *detJ holds the signed determinant for a cell integral and the (positive) surface measure
+ * |J t| (2-D) / |J t1 x J t2| (3-D) for a facet view, so that weights[q] * fabs(*detJ) is the scale in both cases. */
+static int jacobian_raw(const orc_tables* t, int q, const double* X, double* K,
+                        double* detJ, double* J);
 static int jacobian(const orc_tables* t, int q, const double* X, double* K,
                     double* detJ)
 {
-  double J[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0}; /* J[k][a], k<gdim, a<tdim */
+  double J[9];
+  if (jacobian_raw(t, q, X, K, detJ, J)) return 1;
+  if (t->ftan)
+  {
+    const int td = t->tdim;
+    double a[3] = {0, 0, 0}, b[3] = {0, 0, 0};
+    for (int k = 0; k < td; ++k)
+      for (int c = 0; c < td; ++c)
+      {
+        a[k] += J[k * 3 + c] * t->ftan[c];
+        if (td == 3) b[k] += J[k * 3 + c] * t->ftan[td + c];
+      }
+    if (td == 2)
+      *detJ = sqrt(a[0] * a[0] + a[1] * a[1]);
+    else
+    {
+      const double cx = a[1] * b[2] - a[2] * b[1], cy = a[2] * b[0] - a[0] * b[2], cz = a[0] * b[1] - a[1] * b[0];
+      *detJ = sqrt(cx * cx + cy * cy + cz * cz);
+    }
+  }
+  return 0;
+}
+static int jacobian_raw(const orc_tables* t, int q, const double* X, double* K,
+                        double* detJ, double* J)
+{
+  for (int i = 0; i < 9; ++i) J[i] = 0; /* J[k][a], k<gdim, a<tdim */
   const int td = t->tdim, gd = t->gdim;
   for (int a = 0; a < td; ++a)
     for (int g = 0; g < t->ng; ++g)
@@ -131,8 +182,9 @@ static void phys_grads(const orc_tables* t, int q, const double* K, double* g)
 static void k_laplace(double* A, const double* w, const double* c,
                       const double* X, const int* e, const uint8_t* p, void* cd)
 {
-  (void)w; (void)e; (void)p;
-  const orc_tables* t = (const orc_tables*)cd;
+  (void)w; (void)p;
+  const orc_tables tv = entity_view((const orc_tables*)cd, e);
+  const orc_tables* t = &tv;
   const int n = t->nd * t->bs, bs = t->bs;
   double K[9], detJ = 0, g[3 * 64];
   const int affine = is_affine(t);
@@ -156,8 +208,9 @@ static void k_laplace_varcoef(double* A, const double* w, const double* c,
                               const double* X, const int* e, const uint8_t* p,
                               void* cd)
 {
-  (void)e; (void)p;
-  const orc_tables* t = (const orc_tables*)cd;
+  (void)p;
+  const orc_tables tv = entity_view((const orc_tables*)cd, e);
+  const orc_tables* t = &tv;
   const int n = t->nd * t->bs, bs = t->bs;
   double K[9], detJ = 0, g[3 * 64];
   const int affine = is_affine(t);
@@ -182,8 +235,9 @@ static void k_laplace_varcoef(double* A, const double* w, const double* c,
 static void k_mass(double* A, const double* w, const double* c, const double* X,
                    const int* e, const uint8_t* p, void* cd)
 {
-  (void)w; (void)e; (void)p;
-  const orc_tables* t = (const orc_tables*)cd;
+  (void)w; (void)p;
+  const orc_tables tv = entity_view((const orc_tables*)cd, e);
+  const orc_tables* t = &tv;
   const int n = t->nd * t->bs, bs = t->bs;
   double K[9], detJ = 0;
   const int affine = is_affine(t);
@@ -206,8 +260,9 @@ static void k_elasticity(double* A, const double* w, const double* c,
                          const double* X, const int* e, const uint8_t* p,
                          void* cd)
 {
-  (void)w; (void)e; (void)p;
-  const orc_tables* t = (const orc_tables*)cd;
+  (void)w; (void)p;
+  const orc_tables tv = entity_view((const orc_tables*)cd, e);
+  const orc_tables* t = &tv;
   const int bs = t->bs, n = t->nd * bs, gd = t->gdim;
   const double mu = c[0], lmbda = c[1];
   double K[9], detJ = 0, g[3 * 64];
@@ -238,8 +293,9 @@ static void k_elasticity(double* A, const double* w, const double* c,
 static void k_source(double* b, const double* w, const double* c,
                      const double* X, const int* e, const uint8_t* p, void* cd)
 {
-  (void)e; (void)p;
-  const orc_tables* t = (const orc_tables*)cd;
+  (void)p;
+  const orc_tables tv = entity_view((const orc_tables*)cd, e);
+  const orc_tables* t = &tv;
   const int bs = t->bs;
   double K[9], detJ = 0;
   const int affine = is_affine(t);
@@ -504,8 +560,11 @@ int orc_assemble_cells_matrix(int kernel, const orc_tables* tab, const orc_mesh*
                               const double* constants, const orc_dofmap* dm0,
                               const orc_dofmap* dm1, const int8_t* bc0,
                               const int8_t* bc1, const orc_mpc* m0,
-                              const orc_mpc* m1, orc_csr* A)
+                              const orc_mpc* m1, orc_csr* A, const int32_t* local_facets)
 {
+  /* local_facets != NULL: exterior-facet integral over the (cells[i], local_facets[i]) pairs --
+   * assemble_exterior_facets, cpp/assemble_matrix.cpp:271-415: same steps as the cell loop, the local facet index
+   * handed to the kernel (:361-362) */
   ufcx_kernel fn = pick_kernel(kernel);
   if (!fn || kernel == K_SOURCE) return ORC_ERR_KERNEL;
   const int nd0 = dm0->nd, nd1 = dm1->nd, bs0 = dm0->bs, bs1 = dm1->bs;
@@ -524,7 +583,8 @@ int orc_assemble_cells_matrix(int kernel, const orc_tables* tab, const orc_mesh*
     for (int i = 0; i < ng; ++i)                       /* :495-501 */
       memcpy(X + 3 * i, mesh->x + 3 * (int64_t)xd[i], 3 * sizeof(double));
     memset(Ae, 0, sizeof(double) * (size_t)(ndim0 * ndim1)); /* :504 */
-    fn(Ae, coeffs ? coeffs + index * cstride : NULL, constants, X, NULL, NULL,
+    const int lf = local_facets ? local_facets[index] : 0;
+    fn(Ae, coeffs ? coeffs + index * cstride : NULL, constants, X, local_facets ? &lf : NULL, NULL,
        (void*)tab);                                    /* :505-506 */
     const int32_t* d0 = dm0->map + (int64_t)cell * nd0;
     const int32_t* d1 = dm1->map + (int64_t)cell * nd1;
@@ -584,8 +644,9 @@ int orc_assemble_cells_vector(int kernel, const orc_tables* tab, const orc_mesh*
                               const int32_t* cells, int64_t num_cells,
                               const double* coeffs, int cstride,
                               const double* constants, const orc_dofmap* dm,
-                              const orc_mpc* m, double* b)
+                              const orc_mpc* m, double* b, const int32_t* local_facets)
 {
+  /* local_facets != NULL: exterior facets, cpp/assemble_vector.cpp:196-240 */
   ufcx_kernel fn = pick_kernel(kernel);
   if (!fn || kernel != K_SOURCE) return ORC_ERR_KERNEL;
   const int nd = dm->nd, bs = dm->bs, n = nd * bs, ng = mesh->ng;
@@ -599,7 +660,8 @@ int orc_assemble_cells_vector(int kernel, const orc_tables* tab, const orc_mesh*
     for (int i = 0; i < ng; ++i)
       memcpy(X + 3 * i, mesh->x + 3 * (int64_t)xd[i], 3 * sizeof(double));
     memset(be, 0, sizeof(double) * (size_t)n);
-    fn(be, coeffs ? coeffs + e * cstride : NULL, constants, X, NULL, NULL,
+    const int lf = local_facets ? local_facets[e] : 0;
+    fn(be, coeffs ? coeffs + e * cstride : NULL, constants, X, local_facets ? &lf : NULL, NULL,
        (void*)tab);
     const int32_t* dofs = dm->map + (int64_t)cell * nd;
     const int ns = m->c2s_offsets[cell + 1] - m->c2s_offsets[cell];
@@ -642,8 +704,10 @@ int orc_apply_lifting_cells(int kernel, const orc_tables* tab, const orc_mesh* m
                             const double* constants, const orc_dofmap* dm0,
                             const orc_dofmap* dm1, const int8_t* bc_markers1,
                             const double* bc_values1, const double* x0,
-                            double scale, const orc_mpc* m0, double* b)
+                            double scale, const orc_mpc* m0, double* b,
+                            const int32_t* local_facets)
 {
+  /* local_facets != NULL: exterior facets, cpp/lifting.h:316-397 (same per-entity steps) */
   ufcx_kernel fn = pick_kernel(kernel);
   if (!fn || kernel == K_SOURCE) return ORC_ERR_KERNEL;
   const int nd0 = dm0->nd, nd1 = dm1->nd, bs0 = dm0->bs, bs1 = dm1->bs;
@@ -666,7 +730,8 @@ int orc_apply_lifting_cells(int kernel, const orc_tables* tab, const orc_mesh* m
     for (int i = 0; i < ng; ++i)
       memcpy(X + 3 * i, mesh->x + 3 * (int64_t)xd[i], 3 * sizeof(double));
     memset(Ae, 0, sizeof(double) * (size_t)(num_rows * num_cols));
-    fn(Ae, coeffs ? coeffs + e * cstride : NULL, constants, X, NULL, NULL,
+    const int lf = local_facets ? local_facets[e] : 0;
+    fn(Ae, coeffs ? coeffs + e * cstride : NULL, constants, X, local_facets ? &lf : NULL, NULL,
        (void*)tab);
     memset(be, 0, sizeof(double) * (size_t)num_rows);  /* :276-299 */
     for (int j = 0; j < nd1; ++j)

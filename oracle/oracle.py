@@ -43,7 +43,7 @@ def build(force: bool = False, march: Optional[str] = None, out: Optional[str] =
 class _Tables(C.Structure):
     _fields_ = [("tdim", C.c_int32), ("gdim", C.c_int32), ("nd", C.c_int32), ("ng", C.c_int32),
                 ("nq", C.c_int32), ("bs", C.c_int32), ("weights", C.c_void_p), ("phi", C.c_void_p),
-                ("dphi", C.c_void_p), ("gdphi", C.c_void_p)]
+                ("dphi", C.c_void_p), ("gdphi", C.c_void_p), ("nfacets", C.c_int32), ("ftan", C.c_void_p)]
 
 
 class _Mpc(C.Structure):
@@ -88,7 +88,7 @@ def _p(a):
 
 def _tables(tab, bs):
     return _Tables(tab.tdim, tab.gdim, tab.nd, tab.ng, tab.nq, bs, _a(tab.weights), _a(tab.phi), _a(tab.dphi),
-                   _a(tab.gdphi))
+                   _a(tab.gdphi), tab.nfacets, _a(tab.ftan) if tab.nfacets else None)
 
 
 def tabulate(kernel: int, tab, bs: int, X: np.ndarray, w=None, c=(1.0,)) -> np.ndarray:
@@ -256,7 +256,7 @@ def assemble_matrix(form, m0: OracleMPC, m1: Optional[OracleMPC] = None, bcs=(),
         t, tab, w, cstride, cells, n = _integral_args(form, it)
         rc = L.orc_assemble_cells_matrix(int(it.kernel), C.byref(t), C.byref(ms), _p(cells), C.c_int64(n), _p(w),
                                          C.c_int(cstride), _p(it.constants), C.byref(d0), C.byref(d1), _p(bc0),
-                                         _p(bc1), C.byref(s0), C.byref(s1), C.byref(A))
+                                         _p(bc1), C.byref(s0), C.byref(s1), C.byref(A), _p(it.local_facets))
         assert rc == 0, f"oracle matrix assembly failed with {rc}"
     L.orc_add_diagonal.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_double]
     if same_space and m0.num_local_slaves > 0:
@@ -286,7 +286,8 @@ def assemble_vector(form, m: OracleMPC, b: Optional[np.ndarray] = None, libpath:
     for it in form.integrals:
         t, tab, w, cstride, cells, n = _integral_args(form, it)
         rc = L.orc_assemble_cells_vector(int(it.kernel), C.byref(t), C.byref(ms), _p(cells), C.c_int64(n), _p(w),
-                                         C.c_int(cstride), _p(it.constants), C.byref(d), C.byref(s), _p(b))
+                                         C.c_int(cstride), _p(it.constants), C.byref(d), C.byref(s), _p(b),
+                                         _p(it.local_facets))
         assert rc == 0
     return b
 
@@ -295,7 +296,7 @@ def apply_lifting(b: np.ndarray, forms: Sequence, bcs: Sequence[Sequence], m: Or
     L = lib()
     L.orc_apply_lifting_cells.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int,
                                           C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
-                                          C.c_double, C.c_void_p, C.c_void_p]
+                                          C.c_double, C.c_void_p, C.c_void_p, C.c_void_p]
     s = m.struct()
     for j, a in enumerate(forms):
         if a is None:
@@ -315,7 +316,7 @@ def apply_lifting(b: np.ndarray, forms: Sequence, bcs: Sequence[Sequence], m: Or
             t, tab, w, cstride, cells, n = _integral_args(a, it)
             rc = L.orc_apply_lifting_cells(int(it.kernel), C.addressof(t), C.addressof(ms), _p(cells), n, _p(w),
                                            cstride, _p(it.constants), C.addressof(d0), C.addressof(d1), _p(markers),
-                                           _p(values), _p(x0j), float(scale), C.addressof(s), _p(b))
+                                           _p(values), _p(x0j), float(scale), C.addressof(s), _p(b), _p(it.local_facets))
             assert rc == 0
     return b
 

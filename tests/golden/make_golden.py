@@ -21,12 +21,14 @@ import problems  # noqa: E402
 from oracle import oracle as orc  # noqa: E402
 
 CASES = ["general2d-triangle-P1-5x3-m(1, 1)", "general2d-triangle-P1-1x8-m(0, 1)", "periodic2d-P1-8-bc1",
-         "periodic3d-P1-bs1-4-ax2-bc1", "slip3d-P2-2", "contact3d", "tie2d-bs2", "lifting-quad", "varcoef-subdomains"]
+         "periodic3d-P1-bs1-4-ax2-bc1", "slip3d-P2-2", "contact3d", "tie2d-bs2", "lifting-quad", "varcoef-subdomains",
+         "surface-traction2d", "surface-robin3d-P1"]
 
 
 def main():
     orc.build()
-    for name in CASES:
+    only = sys.argv[1:]  # optional: regenerate just these cases
+    for name in (only or CASES):
         c = problems.ALL_CASES[name]()
         m = orc.mpc_from_arrays(c.V, c.data)
         rp, col, val = orc.assemble_matrix(c.a, m, bcs=c.bcs)

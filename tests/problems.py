@@ -180,6 +180,47 @@ def case_hex(n=3):
     return Case("hex-periodic", V, fem.laplace(V) + fem.mass(V), _source(V, _f3d), data, [])
 
 
+def case_surface_traction_2d(n=6):
+    """python/tests/test_surface_integral.py:27-120: vector P1 elasticity on the unit square, Dirichlet on the left
+    wall, traction ``inner(g, v) * ds`` on the top facets, N-1 slaves on x = 1 tied to the master at (1, 1) with
+    coefficient 0.8 (component 1) -- plus a Robin term ``2 inner(u, v) * ds`` on the bottom facets so that the
+    bilinear form has an exterior-facet integral as well (cpp/assemble_matrix.cpp:271-415)."""
+    mesh = gen.create_unit_square(n, n)
+    V = gen.functionspace(mesh, 1, 2)
+    X = V.tabulate_dof_coordinates()
+    left = np.flatnonzero(np.isclose(X[:, 0], 0.0))
+    bc_dofs = (left[:, None] * 2 + np.arange(2)[None, :]).reshape(-1).astype(np.int32)
+    bcs = [fem.DirichletBC(V, bc_dofs, 0.2)]
+    right = np.flatnonzero(np.isclose(X[:, 0], 1.0) & ~np.isclose(X[:, 1], 1.0) & ~np.isclose(X[:, 1], 0.0))
+    master = int(np.flatnonzero(np.isclose(X[:, 0], 1.0) & np.isclose(X[:, 1], 1.0))[0])
+    data = gen.tie_constraint(V, right, master, 0.8, comp=1)
+    top = fem.locate_exterior_facets(mesh, lambda x: np.isclose(x[1], 1.0))
+    bottom = fem.locate_exterior_facets(mesh, lambda x: np.isclose(x[1], 0.0))
+    g = fem.Function(V)
+    g.interpolate(lambda x: np.stack([0.3 * x[0], -9.81 + 0.0 * x[0]]))
+    a = fem.elasticity(V, 50.0, 0.0) + fem.mass(V, 2.0, facets=bottom)
+    L = _source(V, _vec(_f2d, 2)) + fem.source(V, g, 1.0, facets=top)
+    return Case("surface-traction2d", V, a, L, data, bcs, a_lift=a)
+
+
+def case_surface_robin_3d(n=3, degree=1):
+    """Scalar Robin / Neumann terms over all boundary facets of a tetrahedral mesh with a periodic constraint
+    (exterior-facet integrals of matrix, vector and lifting: cpp/assemble_matrix.cpp:271-415,
+    cpp/assemble_vector.cpp:196-240, cpp/lifting.h:316-397)."""
+    mesh = gen.create_unit_cube(n, n, n)
+    V = gen.functionspace(mesh, degree)
+    dofs = fem.locate_dofs_geometrical(V, lambda x: np.isclose(x[2], 0.0))
+    bcs = [fem.DirichletBC(V, dofs, -0.4)]
+    data = gen.periodic_constraint(V, axes=(0,), exclude_dofs=dofs)
+    fac = fem.locate_exterior_facets(mesh, lambda x: np.isclose(x[2], 1.0) | np.isclose(x[1], 0.0) | np.isclose(x[1], 1.0))
+    allf = fem.locate_exterior_facets(mesh)
+    h = fem.Function(V)
+    h.interpolate(lambda x: 1.0 + x[0] * x[1] - x[2])
+    a = fem.laplace(V) + fem.mass(V, 1.5, facets=allf)
+    L = _source(V, _f3d) + fem.source(V, h, 0.7, facets=fac)
+    return Case(f"surface-robin3d-P{degree}", V, a, L, data, bcs, a_lift=a)
+
+
 ALL_CASES: dict = {}
 for _c in (
     lambda: case_general_2d("triangle", 1), lambda: case_general_2d("triangle", 2),
@@ -190,7 +231,8 @@ for _c in (
     lambda: case_periodic_3d(3, 2, (0, 1), True), lambda: case_periodic_3d(3, 1, (0,), True, bs=3),
     lambda: case_slip_elasticity_3d(2, 2), lambda: case_slip_elasticity_3d(3, 1),
     case_contact_3d, lambda: case_tie_2d(6, 2), lambda: case_tie_2d(5, 1), case_lifting_single_quad,
-    case_varcoef_subdomains, case_empty, case_hex,
+    case_varcoef_subdomains, case_empty, case_hex, case_surface_traction_2d,
+    lambda: case_surface_robin_3d(3, 1), lambda: case_surface_robin_3d(2, 2),
 ):
     _k = _c()
     ALL_CASES[_k.name] = _c

@@ -144,3 +144,31 @@ def test_lifting_solve_matches_reduced_system(oracle):
     assert np.allclose(u[slaves], u[np.asarray(masters)])
     h = u.copy(); oracle.homogenize(m, h)
     assert np.all(h[slaves] == 0)
+
+
+@pytest.mark.parametrize("make,measure", [
+    (lambda g: g.create_unit_square(4, 3), 4.0), (lambda g: g.create_unit_cube(3, 2, 4), 6.0),
+    (lambda g: g.create_rectangle(3, 4, "quadrilateral"), 4.0), (lambda g: g.create_box(2, 3, 2, "hexahedron"), 6.0)])
+def test_exterior_facet_integrals_known_answers(oracle, make, measure):
+    """Exterior-facet kernels (cpp/assemble_matrix.cpp:271-415, cpp/assemble_vector.cpp:196-240) pinned on
+    closed-form answers: int_boundary 1 ds = perimeter / surface area through both the linear form (f = 1) and the
+    bilinear form (1^T M 1), P1 and P2; and int_{y=1} x ds = 1/2 on a partial boundary."""
+    from dolfinx_mpc_b200 import fem, generators as gen
+
+    mesh = make(gen)
+    for degree in ((1, 2) if mesh.cell_type in ("triangle", "tetrahedron") else (1,)):
+        V = gen.functionspace(mesh, degree)
+        fac = fem.locate_exterior_facets(mesh)
+        f = fem.Function(V)
+        f.array[:] = 1.0
+        e = oracle.OracleMPC.empty(V)
+        assert abs(oracle.assemble_vector(fem.source(V, f, 1.0, facets=fac), e).sum() - measure) < 1e-12
+        assert abs(oracle.assemble_matrix(fem.mass(V, 1.0, facets=fac), e)[2].sum() - measure) < 1e-12
+    mesh = gen.create_unit_square(5, 5)
+    V = gen.functionspace(mesh, 1)
+    top = fem.locate_exterior_facets(mesh, lambda x: np.isclose(x[1], 1))
+    assert len(top) == 5 and np.all(top[:, 1] == 0)
+    f = fem.Function(V)
+    f.interpolate(lambda x: x[0])
+    b = oracle.assemble_vector(fem.source(V, f, 1.0, facets=top), oracle.OracleMPC.empty(V))
+    assert abs(b.sum() - 0.5) < 1e-13
