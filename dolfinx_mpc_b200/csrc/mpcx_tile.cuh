@@ -8,29 +8,33 @@
 //
 //   setup (once per pattern / dofmap / bc set, mpcx_tile_plan_create, all on the device):
 //     the cells are ordered along a Morton curve through the mesh and cut into tiles of C consecutive cells;
-//     for every tile the plan holds its distinct vertices, the tile-local vertex ids of its cells and its
-//     distinct CSR entries ("dests"), ordered by descending number of contributing element entries
-//     ("sources") and cut into groups of 32 (one per lane of a warp).  Every source owns one slot of the
-//     tile's element buffer: slot = base(group) + 32 * i + lane for the i-th source of the dest held by `lane`;
-//   assembly (k_ctile_matrix_p1, one CTA of C threads per tile):
-//     phase 0  one thread issues TMA bulk copies (cp.async.bulk + mbarrier) of the tile's dest records into
-//              shared memory; every thread prefetches its cell's record and the tile's vertex coordinates
-//              are gathered once per tile, not once per cell,
-//     phase 1  thread = cell: closed-form element matrix, each entry stored to its slot,
-//     phase 2  thread = dest: sums its column of the group's [count][33] slot block -- conflict-free reads, same
-//              trip count on every lane -- and stores the sum to the tile's staging buffer, where the dests lie
-//              in CSR order, cut into runs of (nearly) consecutive entries, gaps and 16-byte padding zero-filled,
-//     phase 3  one TMA bulk reduction per run (cp.reduce.async.bulk.global.shared::cta.add.f64, SASS UBLKRED):
-//              the copy engine adds the run into A.val in L2, about 220 bulk operations per tile instead of
-//              ~2100 red.global.add.f64 lane operations through the LSU (1.3 cycles each, profiles/r01_g: the
-//              REDs were half of the L1/LSU time that bounds the kernel).
-//   A P1 tetrahedron mesh has about 4 distinct dests per cell in a 512-cell tile instead of 16 entries per
+//     for every tile the plan holds its distinct vertices, the tile-local vertex ids of its cells and one record
+//     per distinct CSR entry ("dest") the tile contributes to, ordered by descending number of contributing element
+//     entries ("sources") and cut into groups of 32 (one per lane of a warp).  Every source owns one slot of the
+//     tile's element buffer: slot = base(group) + 33 * i + lane for the i-th source of the dest held by `lane`.
+//     In CSR order the dests are cut into runs of (nearly) consecutive entries, gaps and 16-byte padding being
+//     zero-filled positions of the tile's staging buffer.  A symmetric plan (same dofmap and bc markers on both
+//     sides; every tile kernel's element matrix is symmetric) keeps records for the upper triangle only, each
+//     feeding entry (r, c) and entry (c, r);
+//   assembly (k_ptile_matrix_p1): persistent CTAs walk the tiles; per tile
+//     - the cell records (vertex ids, slots) and dest records arrive by TMA bulk copies (cp.async.bulk + mbarrier,
+//       SASS UBLKCP) issued one tile ahead; the tile's vertex coordinates are gathered once per tile -- not once
+//       per cell -- through registers, also one tile ahead,
+//     - phase 1, thread = cell: closed-form element matrix, each stored entry written to its slot,
+//     - phase 2, thread = record: sums its column of the group's [count][33] slot block -- conflict-free reads, same
+//       trip count on every lane -- and stores the sum at the record's staging position(s),
+//     - one TMA bulk reduction per run (cp.reduce.async.bulk.global.shared::cta.add.f64, SASS UBLKRED): the copy
+//       engine adds the run into A.val in L2 -- about 35 bulk operations per tile instead of ~2100
+//       red.global.add.f64 lane operations through the LSU (1.3 cycles each, profiles/r01_g: the REDs were half of
+//       the L1/LSU time that bounded the kernel); the CTA moves on to the next tile meanwhile.
+//   A P1 tetrahedron mesh has about 4 distinct dests per cell in a 448-cell tile instead of 16 entries per
 //   cell, and the gathers of x[x_dofmap] / row_ptr disappear from the hot loop.
-//   Requirements of phase 3: A.val (b) 16-byte aligned, capacity rounded up to an even number of entries
+//   Requirements of the bulk reductions: A.val 16-byte aligned, capacity rounded up to an even number of entries
 //   (a run may be padded with one zero past the last entry).
 //
 // Cells holding slave dofs are excluded (the `skip` flags) and handled by the elimination kernel.
-// The load vector uses the same machinery with 4 entries per cell and dests = row dofs (k_ctile_vector_p1).
+// The load vector uses the same machinery with 4 entries per cell and dests = row dofs (k_ptile_vector_p1); a tile
+// touches few, scattered rows, so those sums are added with one red.global.add.f64 per (tile, row).
 #pragma once
 #include <cub/cub.cuh>
 
