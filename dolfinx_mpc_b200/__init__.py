@@ -4,7 +4,7 @@ Exports the names of ``python/src/dolfinx_mpc/__init__.py:14-41`` that belong to
 Importing the package does not need a GPU; calling any assembly routine does (no CPU fallback).
 """
 from .assemble_matrix import (assemble_matrix, assemble_matrix_nest, create_matrix, create_matrix_nest,
-                              create_sparsity_pattern)
+                              create_sparsity_pattern, create_sparsity_pattern_device)
 from .assemble_vector import (apply_lifting, assemble_vector, assemble_vector_nest, create_vector,
                               create_vector_nest, set_bc)
 from .multipointconstraint import MultiPointConstraint
@@ -12,6 +12,6 @@ from .multipointconstraint import MultiPointConstraint
 __all__ = [
     "assemble_matrix", "create_matrix", "create_matrix_nest", "assemble_matrix_nest", "assemble_vector",
     "apply_lifting", "assemble_vector_nest", "create_vector_nest", "create_vector", "set_bc",
-    "MultiPointConstraint", "create_sparsity_pattern",
+    "MultiPointConstraint", "create_sparsity_pattern", "create_sparsity_pattern_device",
 ]
 __version__ = "0.1.0"

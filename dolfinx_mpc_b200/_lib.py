@@ -69,6 +69,7 @@ SYMBOLS = (
     "mpcx_create_pattern_host", "mpcx_free_host", "mpcx_profile_enable", "mpcx_launch_count", "mpcx_profile_read",
     "mpcx_flag_cells", "mpcx_tile_plan_create", "mpcx_tile_plan_destroy", "mpcx_tile_plan_info",
     "mpcx_assemble_matrix_tiled_f64", "mpcx_vector_tile_plan_create", "mpcx_assemble_vector_tiled_f64",
+    "mpcx_pattern_create", "mpcx_pattern_export", "mpcx_pattern_destroy",
 )
 
 _lib = None
@@ -116,6 +117,10 @@ def load():
     lib.mpcx_scatter_add_f64.argtypes = [vp, vp, i64, vp, vp]
     lib.mpcx_create_pattern_host.argtypes = [vp, i32, i32, vp, i32, i32, i64, i64, P(MpcHostS), P(MpcHostS), i32,
                                              P(P(C.c_int64)), P(P(C.c_int32)), P(i64)]
+    lib.mpcx_pattern_create.argtypes = [P(DofmapS), P(DofmapS), i64, P(MpcS), P(MpcS), vp, P(vp), P(i64)]
+    lib.mpcx_pattern_export.argtypes = [vp, vp, vp, vp]
+    lib.mpcx_pattern_destroy.argtypes = [vp]
+    lib.mpcx_pattern_destroy.restype = None
     lib.mpcx_profile_enable.argtypes = [C.c_int]
     lib.mpcx_launch_count.restype = C.c_longlong
     lib.mpcx_profile_read.argtypes = [P(C.c_double), P(C.c_longlong)]

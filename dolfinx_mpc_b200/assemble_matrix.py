@@ -62,12 +62,53 @@ def create_sparsity_pattern(form: Form, mpc: Union[MultiPointConstraint, Sequenc
     return row_ptr, col
 
 
+def create_sparsity_pattern_device(form: Form, mpc: Union[MultiPointConstraint, Sequence[MultiPointConstraint]]):
+    """The same pattern built on the device (``mpcx_pattern_create`` / ``mpcx_pattern_export``): returns device
+    tensors ``(row_ptr int64, col int32)``.  Raises ``MpcxError`` with status ``ERR_UNSUPPORTED`` beyond 2^31 cell
+    couplings on one device."""
+    import torch
+
+    mpc0, mpc1 = _pair(mpc)
+    for m in (mpc0, mpc1):
+        m._not_finalized()
+    if form.rank != 2:
+        raise RuntimeError("Cannot create sparsity pattern. Form is not a bilinear form")
+    lib = _lib.load()
+    V0, V1 = form.function_spaces
+    n0, n1 = mpc0.function_space.num_dofs, mpc1.function_space.num_dofs
+    d0 = _dev.dofmap_struct(V0, n0)
+    d1 = _dev.dofmap_struct(V1, n1)
+    m0 = _dev.mpc_dev(mpc0)["struct"]
+    m1 = _dev.mpc_dev(mpc1)["struct"]
+    st = _dev.stream_ptr()
+    handle = C.c_void_p()
+    nnz = C.c_int64(0)
+    _lib.check(lib.mpcx_pattern_create(C.byref(d0), C.byref(d1), form.mesh.num_cells_local, C.byref(m0), C.byref(m1), st,
+                                       C.byref(handle), C.byref(nnz)))
+    try:
+        row_ptr = torch.empty(n0 + 1, dtype=torch.int64, device=_dev.device())
+        col = torch.empty(max(1, nnz.value), dtype=torch.int32, device=_dev.device())[: nnz.value]
+        _lib.check(lib.mpcx_pattern_export(handle, _dev.ptr(row_ptr), _dev.ptr(col), st))
+        torch.cuda.current_stream().synchronize()
+    finally:
+        lib.mpcx_pattern_destroy(handle)
+    return row_ptr, col
+
+
 def create_matrix(form: Form, mpc0: MultiPointConstraint, mpc1: Optional[MultiPointConstraint] = None) -> Matrix:
-    """``cpp.mpc.create_matrix`` (``cpp/utils.h:140-173``): pattern + zeroed device CSR."""
+    """``cpp.mpc.create_matrix`` (``cpp/utils.h:140-173``): pattern + zeroed device CSR.  The pattern is built on the
+    device; ``MPCX_PATTERN=host`` (or more than 2^31 cell couplings) selects the threaded host builder."""
     mpc1 = mpc0 if mpc1 is None else mpc1
-    row_ptr, col = create_sparsity_pattern(form, (mpc0, mpc1))
     shape = (mpc0.function_space.num_dofs, mpc1.function_space.num_dofs)
     bs = (form.function_spaces[0].bs, form.function_spaces[1].bs)
+    if os.environ.get("MPCX_PATTERN", "device") != "host":
+        try:
+            row_ptr, col = create_sparsity_pattern_device(form, (mpc0, mpc1))
+            return Matrix(row_ptr, col, shape, bs)
+        except _lib.MpcxError as e:
+            if getattr(e, "status", None) != _lib.ERR_UNSUPPORTED:
+                raise
+    row_ptr, col = create_sparsity_pattern(form, (mpc0, mpc1))
     return Matrix(row_ptr, col, shape, bs)
 
 

@@ -876,6 +876,7 @@ __global__ void k_flag_cells(const int* __restrict__ dm, int nd, int bs, const i
 }  // namespace
 
 #include "mpcx_tile.cuh"
+#include "mpcx_pattern_gpu.cuh"
 
 namespace
 {
@@ -1383,5 +1384,37 @@ int mpcx_assemble_vector_tiled_f64(const mpcx_integral* integral, const mpcx_mes
   }
   return cuda_check(cudaGetLastError(), "assemble_vector_tiled launch");
 }
+
+int mpcx_pattern_create(const mpcx_dofmap* dofmap0, const mpcx_dofmap* dofmap1, int64_t num_cells,
+                        const mpcx_mpc* mpc0, const mpcx_mpc* mpc1, void* stream, mpcx_pattern** pattern_out,
+                        int64_t* nnz_out)
+{
+  if (!dofmap0 || !dofmap1 || !pattern_out || !nnz_out || num_cells < 0) return fail(MPCX_ERR_ARG, "null argument");
+  if (dofmap0->bs < 1 || dofmap1->bs < 1 || dofmap0->num_dofs % dofmap0->bs || dofmap1->num_dofs % dofmap1->bs)
+    return fail(MPCX_ERR_ARG, "num_dofs must be a multiple of the block size");
+  Pattern* P = nullptr;
+  const int rc = pattern_build(dofmap0, dofmap1, num_cells, dofmap0->num_dofs / dofmap0->bs, dofmap1->num_dofs / dofmap1->bs,
+                               mpc0, mpc1, (cudaStream_t)stream, &P);
+  *pattern_out = reinterpret_cast<mpcx_pattern*>(P);
+  *nnz_out = P ? P->nnz_block * P->bs0 * P->bs1 : 0;
+  return rc;
+}
+
+int mpcx_pattern_export(const mpcx_pattern* pattern, int64_t* row_ptr_out, int32_t* col_out, void* stream)
+{
+  if (!pattern || !row_ptr_out || !col_out) return fail(MPCX_ERR_ARG, "null argument");
+  const Pattern* P = reinterpret_cast<const Pattern*>(pattern);
+  cudaStream_t s = (cudaStream_t)stream;
+  const long long nrows = P->nbr * P->bs0;
+  MPCX_COUNT_LAUNCH(), k_pat_export_rows<<<(unsigned)((nrows + 256) / 256), 256, 0, s>>>(P->start, P->nbr, P->bs0, P->bs1,
+                                                                                    (long long*)row_ptr_out);
+  const long long nt = P->nnz_block * P->bs0;
+  if (nt > 0)
+    MPCX_COUNT_LAUNCH(), k_pat_export_cols<<<(unsigned)((nt + 255) / 256), 256, 0, s>>>(P->keys, P->start, P->nnz_block, P->bs0,
+                                                                                   P->bs1, P->colbits, col_out);
+  return cuda_check(cudaGetLastError(), "pattern_export launch");
+}
+
+void mpcx_pattern_destroy(mpcx_pattern* pattern) { pattern_free(reinterpret_cast<Pattern*>(pattern)); }
 
 }  // extern "C"

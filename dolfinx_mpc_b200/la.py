@@ -21,19 +21,28 @@ from . import device as _dev
 
 
 class Matrix:
-    def __init__(self, row_ptr: np.ndarray, col: np.ndarray, shape, bs=(1, 1), max_block_row: Optional[int] = None):
+    def __init__(self, row_ptr, col, shape, bs=(1, 1), max_block_row: Optional[int] = None):
+        """``row_ptr`` / ``col``: numpy arrays (uploaded) or device tensors (used as they are; the host copies that
+        ``getValuesCSR`` / ``to_scipy`` hand out are downloaded on first use)."""
         self.shape = tuple(int(s) for s in shape)
         self.bs = tuple(bs)
-        self.row_ptr_host = np.ascontiguousarray(row_ptr, dtype=np.int64)
-        self.col_host = np.ascontiguousarray(col, dtype=np.int32)
-        self.nnz = int(self.row_ptr_host[-1])
-        self.row_ptr = _dev.to_dev(self.row_ptr_host)
-        self.col = _dev.to_dev(self.col_host)
+        if isinstance(row_ptr, torch.Tensor):
+            self.row_ptr, self.col = row_ptr, col
+            self._row_ptr_host = self._col_host = None
+            self.nnz = int(row_ptr[-1])
+            if max_block_row is None:
+                max_block_row = int((row_ptr[1:] - row_ptr[:-1]).max()) // max(1, self.bs[1]) if len(row_ptr) > 1 else 0
+        else:
+            self._row_ptr_host = np.ascontiguousarray(row_ptr, dtype=np.int64)
+            self._col_host = np.ascontiguousarray(col, dtype=np.int32)
+            self.nnz = int(self._row_ptr_host[-1])
+            self.row_ptr = _dev.to_dev(self._row_ptr_host)
+            self.col = _dev.to_dev(self._col_host)
+            if max_block_row is None:
+                max_block_row = int(np.diff(self._row_ptr_host).max(initial=0)) // max(1, self.bs[1])
         # capacity rounded up to an even count: the tile kernels add whole 16-byte runs (include/mpcx.h)
         self._val_storage = torch.zeros(self.nnz + (self.nnz & 1), dtype=torch.float64, device=_dev.device())
         self.val = self._val_storage[: self.nnz]
-        if max_block_row is None:
-            max_block_row = int(np.diff(self.row_ptr_host).max(initial=0)) // max(1, self.bs[1])
         self.max_block_row = max_block_row
         self._plans = {}
         self._tile_plans = {}
@@ -41,6 +50,18 @@ class Matrix:
         # tile kernel exists; "atomic": one red.global.add per element entry
         self.scatter = os.environ.get("MPCX_SCATTER", "tile")
         self.ghost_exchange = None  # set by distributed.attach_ghost_exchange
+
+    @property
+    def row_ptr_host(self) -> np.ndarray:
+        if self._row_ptr_host is None:
+            self._row_ptr_host = self.row_ptr.cpu().numpy()
+        return self._row_ptr_host
+
+    @property
+    def col_host(self) -> np.ndarray:
+        if self._col_host is None:
+            self._col_host = self.col.cpu().numpy()
+        return self._col_host
 
     def struct(self) -> _lib.CsrS:
         return _lib.CsrS(_dev.ptr(self.row_ptr), _dev.ptr(self.col), _dev.ptr(self.val), self.shape[0], self.nnz)

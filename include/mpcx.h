@@ -269,6 +269,18 @@ typedef struct mpcx_mpc_host
   const int32_t* cell_to_slaves_offsets;
 } mpcx_mpc_host;
 
+/* The same pattern built on the DEVICE (all pointers inside the structs are device pointers; mpc0 / mpc1 may be
+ * NULL): one 64-bit key per (block row, block column) coupling of every cell, CUB radix sort, duplicate removal.
+ * Two steps because the caller owns the CSR arrays: create returns the scalar nnz, export fills
+ * row_ptr_out [num_rows + 1] and col_out [nnz].  Fails with MPCX_ERR_UNSUPPORTED beyond 2^31 couplings per device
+ * (then mpcx_create_pattern_host applies). */
+typedef struct mpcx_pattern mpcx_pattern;
+int mpcx_pattern_create(const mpcx_dofmap* dofmap0, const mpcx_dofmap* dofmap1, int64_t num_cells,
+                        const mpcx_mpc* mpc0, const mpcx_mpc* mpc1, void* stream, mpcx_pattern** pattern_out,
+                        int64_t* nnz_out);
+int mpcx_pattern_export(const mpcx_pattern* pattern, int64_t* row_ptr_out, int32_t* col_out, void* stream);
+void mpcx_pattern_destroy(mpcx_pattern* pattern);
+
 int mpcx_create_pattern_host(const int32_t* dofmap0, int32_t nd0, int32_t bs0,
                              const int32_t* dofmap1, int32_t nd1, int32_t bs1,
                              int64_t num_cells, int64_t num_block_rows,

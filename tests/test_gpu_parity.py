@@ -328,3 +328,30 @@ def test_full_size_properties():
     cells = dev.to_dev(mesh.x_dofmap).long()
     expected = float((fx[cells].sum(dim=1) * (h ** 3 / 6.0 / 4.0)).sum())
     assert abs(float(b.data.sum()) - expected) <= 1e-10 * abs(expected)
+
+
+@pytest.mark.parametrize("name", list(problems.ALL_CASES))
+def test_device_pattern_matches_host_pattern(name):
+    """create_sparsity_pattern on the device (sort + unique of 64-bit coupling keys) against the threaded host
+    builder, itself bit-exact against the oracle's restatement of cpp/utils.h:381-496 (tests/test_cabi.py)."""
+    import dolfinx_mpc_b200 as mpcx
+
+    c = problems.ALL_CASES[name]()
+    mpc = _mpc(c)
+    rp_h, col_h = mpcx.create_sparsity_pattern(c.a, mpc)
+    rp_d, col_d = mpcx.create_sparsity_pattern_device(c.a, mpc)
+    assert np.array_equal(rp_d.cpu().numpy(), rp_h) and np.array_equal(col_d.cpu().numpy(), col_h)
+
+
+def test_device_pattern_rectangular_pair():
+    import dolfinx_mpc_b200 as mpcx
+    from dolfinx_mpc_b200 import generators as gen
+
+    c = problems.case_periodic_2d(6, 1, False)
+    mpc0 = _mpc(c)
+    mpc1 = mpcx.MultiPointConstraint(c.V)
+    mpc1.add_constraint(c.V, *gen.periodic_constraint(c.V, axes=(1,), scale=0.5))
+    mpc1.finalize()
+    rp_h, col_h = mpcx.create_sparsity_pattern(c.a, (mpc0, mpc1))
+    rp_d, col_d = mpcx.create_sparsity_pattern_device(c.a, (mpc0, mpc1))
+    assert np.array_equal(rp_d.cpu().numpy(), rp_h) and np.array_equal(col_d.cpu().numpy(), col_h)
