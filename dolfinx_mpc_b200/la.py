@@ -152,6 +152,25 @@ class Matrix:
     def getValuesCSR(self):
         return self.row_ptr_host, self.col_host, self.val.cpu().numpy()
 
+    # -- zero-copy hand-off on the device --------------------------------------------------------------------
+    def to_torch_sparse_csr(self):
+        """The matrix as a ``torch.sparse_csr_tensor`` sharing ``col`` and ``val`` with this object (cuSPARSE SpMV /
+        SpMM through ``A_t @ x``); only the row pointer is narrowed to int32 (n + 1 entries) because torch wants
+        both index arrays of one dtype.  Counterpart of handing the assembled ``Mat`` to a solver
+        (``python/src/dolfinx_mpc/problem.py:539-582``)."""
+        if self.nnz >= 2**31:
+            raise RuntimeError("more than 2^31 entries: use dlpack() and 64-bit row pointers")
+        crow = self.row_ptr.to(torch.int32)
+        return torch.sparse_csr_tensor(crow, self.col, self.val, size=self.shape, device=self.val.device)
+
+    def dlpack(self):
+        """DLPack capsules ``(row_ptr int64, col int32, val float64)`` of the device arrays -- zero-copy import into
+        CuPy (``cupyx.scipy.sparse.csr_matrix``), PETSc (``MatCreateSeqAIJCUSPARSE`` after narrowing ``row_ptr``)
+        or any other DLPack consumer."""
+        from torch.utils.dlpack import to_dlpack
+
+        return to_dlpack(self.row_ptr), to_dlpack(self.col), to_dlpack(self.val)
+
     def to_scipy(self):
         import scipy.sparse as sp
 

@@ -355,3 +355,23 @@ def test_device_pattern_rectangular_pair():
     rp_h, col_h = mpcx.create_sparsity_pattern(c.a, (mpc0, mpc1))
     rp_d, col_d = mpcx.create_sparsity_pattern_device(c.a, (mpc0, mpc1))
     assert np.array_equal(rp_d.cpu().numpy(), rp_h) and np.array_equal(col_d.cpu().numpy(), col_h)
+
+
+def test_device_handoff_spmv(oracle):
+    """The assembled CSR consumed on the device without a copy of col / val: cuSPARSE SpMV through a
+    torch.sparse_csr_tensor view equals the host SciPy product; DLPack round trip aliases the same memory."""
+    import torch
+    from torch.utils.dlpack import from_dlpack
+
+    import dolfinx_mpc_b200 as mpcx
+
+    c = problems.case_periodic_3d(4, 1, (0, 1), True)
+    mpc = _mpc(c)
+    A = mpcx.assemble_matrix(c.a, mpc, bcs=c.bcs)
+    At = A.to_torch_sparse_csr()
+    assert At.values().data_ptr() == A.val.data_ptr() and At.col_indices().data_ptr() == A.col.data_ptr()
+    x = np.random.default_rng(4).random(A.shape[1])
+    y = (At @ torch.from_numpy(x).to(A.val.device)).cpu().numpy()
+    assert np.allclose(y, A.to_scipy() @ x, rtol=1e-13, atol=1e-13)
+    rp, col, val = (from_dlpack(t) for t in A.dlpack())
+    assert val.data_ptr() == A.val.data_ptr() and rp.dtype == torch.int64 and col.dtype == torch.int32
