@@ -29,6 +29,9 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
 FALLBACK_HBM_GBS = 6650.0  # /opt/skills/guides/B200_PROFILING.md fallback
+# dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the bulk matrix kernel at n = 256 on one GPU, from the
+# `ncu --set full` capture summarised in profiles/r01_o256_ncu_full_summary.csv (7.263 GB read + 2.307 GB written)
+NCU_TRAFFIC_N256 = 9.570e9
 
 
 def f_source(x):
@@ -293,7 +296,9 @@ def run_ours(args):
     alg = algorithmic_bytes(P, A.nnz, with_rhs=False)
     achieved = alg / (k_ms * 1e-3) / 1e9
     roofline = {"bound": "hbm", "kernel": "matrix bulk kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": achieved / peak, "peak_source": peak_src, "traffic": args.traffic,
+                "frac": achieved / peak, "peak_source": peak_src,
+                "traffic": args.traffic if args.traffic is not None else (NCU_TRAFFIC_N256 if n == 256 else None),
+                "traffic_source": "profiles/r01_o256_ncu_full_summary.csv (ncu --set full, per launch)",
                 "algorithmic_bytes_per_launch": alg, "bytes_per_cell": alg / nc, "kernel_ms": k_ms,
                 "kernel_share_of_step": kms.value / ms_total}
 

@@ -160,8 +160,12 @@ class Matrix:
         (``python/src/dolfinx_mpc/problem.py:539-582``)."""
         if self.nnz >= 2**31:
             raise RuntimeError("more than 2^31 entries: use dlpack() and 64-bit row pointers")
+        import warnings
+
         crow = self.row_ptr.to(torch.int32)
-        return torch.sparse_csr_tensor(crow, self.col, self.val, size=self.shape, device=self.val.device)
+        with warnings.catch_warnings():
+            warnings.filterwarnings("ignore", message="Sparse CSR tensor support is in beta state")
+            return torch.sparse_csr_tensor(crow, self.col, self.val, size=self.shape, device=self.val.device)
 
     def dlpack(self):
         """DLPack capsules ``(row_ptr int64, col int32, val float64)`` of the device arrays -- zero-copy import into

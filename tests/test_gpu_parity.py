@@ -375,3 +375,31 @@ def test_device_handoff_spmv(oracle):
     assert np.allclose(y, A.to_scipy() @ x, rtol=1e-13, atol=1e-13)
     rp, col, val = (from_dlpack(t) for t in A.dlpack())
     assert val.data_ptr() == A.val.data_ptr() and rp.dtype == torch.int64 and col.dtype == torch.int32
+
+
+def test_tile_plan_fallback_on_a_fan_mesh(oracle):
+    """A vertex shared by 700 triangles: its diagonal entry collects 448 sources inside one tile, more than a tile
+    record holds (8-bit counts) -> the tile plan reports MPCX_ERR_UNSUPPORTED and the assembly must fall back to the
+    atomic-scatter kernels on the device, with the same result."""
+    import dolfinx_mpc_b200 as mpcx
+    from dolfinx_mpc_b200 import fem, generators as gen
+
+    n = 700
+    ang = 2 * np.pi * np.arange(n) / n
+    x = np.zeros((n + 1, 3))
+    x[1:, 0], x[1:, 1] = np.cos(ang), np.sin(ang)
+    cells = np.stack([np.zeros(n, np.int32), 1 + np.arange(n, dtype=np.int32), 1 + (np.arange(n, dtype=np.int32) + 1) % n], 1)
+    mesh = fem.Mesh(x, cells.astype(np.int32), "triangle")
+    V = gen.functionspace(mesh, 1)
+    mpc = mpcx.MultiPointConstraint(V)
+    mpc.add_constraint(V, *gen.empty_constraint())
+    mpc.finalize()
+    a = fem.laplace(V) + fem.mass(V, 0.5)
+    f = fem.Function(V)
+    f.interpolate(lambda x: 1.0 + x[0])
+    L = fem.source(V, f)
+    A = mpcx.assemble_matrix(a, mpc)
+    assert list(A._tile_plans.values()) == [None, None], "the tile plan should not fit this mesh"
+    m = oracle.mpc_from_arrays(V, gen.empty_constraint())
+    assert_csr_close(*A.getValuesCSR(), *oracle.assemble_matrix(a, m))
+    assert_vec_close(mpcx.assemble_vector(L, mpc).array, oracle.assemble_vector(L, m))
