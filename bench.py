@@ -120,6 +120,9 @@ class ClockSampler:
 
 # ------------------------------------------------------------------------------------------------ CPU reference arm
 
+LAST_ONE_RANK = None
+
+
 def cpu_reference(n: int, steps: int, warmup: int, budget_s: float, label: str):
     """The reference's algorithm (oracle port, oracle/mpc_oracle.c -- the reference itself cannot be built in
     this image) on all host cores: R = nproc independent ranks, each assembling its own z-slab into its own
@@ -168,6 +171,9 @@ def cpu_reference(n: int, steps: int, warmup: int, budget_s: float, label: str):
 
     for _ in range(warmup):
         one_step()
+    work(0)  # one rank alone (BASELINE.json configs[0] is quoted on 1 CPU rank): same slab, no neighbours on the cores
+    global LAST_ONE_RANK
+    LAST_ONE_RANK = P["mesh"].num_cells_local / times[0]
     dts = [one_step() for _ in range(steps)]
     total = float(sum(dts))
     value = cells * steps / total
@@ -187,7 +193,8 @@ def run_reference(args):
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": workload_config(args.n, args.gpus),
-        "cpu_baseline": {"value": value, "unit": "cells/s", "cores": R, "kind": "port", "sample": sample},
+        "cpu_baseline": {"value": value, "unit": "cells/s", "cores": R, "kind": "port", "sample": sample,
+                         "one_rank_value": LAST_ONE_RANK},
         "e2e": {"value": value, "unit": "cells/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -302,6 +309,22 @@ def run_ours(args):
                 "algorithmic_bytes_per_launch": alg, "bytes_per_cell": alg / nc, "kernel_ms": k_ms,
                 "kernel_share_of_step": kms.value / ms_total}
 
+    # matrix-only / vector-only split of the step, timed separately after the main loop
+    def timed(fn, reps=3):
+        fn()
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            fn()
+        e1.record()
+        barrier()
+        return e0.elapsed_time(e1) / reps
+
+    breakdown = {"assemble_matrix_ms": timed(lambda: mpcx.assemble_matrix(a, mpc, bcs=bcs, A=A)),
+                 "assemble_vector_ms": timed(lambda: mpcx.assemble_vector(L, mpc, b=b)),
+                 "apply_lifting_ms": timed(lambda: mpcx.apply_lifting(b, [a], [bcs], mpc))}
+
     # end-to-end through the public API with host (pinned) buffers: every array the call reads is copied
     # host -> device inside the timed region, the assembled CSR values and RHS are copied back
     e2e = run_e2e(args, P, A, b, step, world, barrier)
@@ -309,7 +332,8 @@ def run_ours(args):
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
         v, ms, R, sample, _ = cpu_reference(n, 1, 1, args.cpu_budget, "cpu_baseline")
-        cpu = {"value": v, "unit": "cells/s", "cores": R, "kind": "port", "sample": sample}
+        cpu = {"value": v, "unit": "cells/s", "cores": R, "kind": "port", "sample": sample,
+               "one_rank_value": LAST_ONE_RANK}
 
     if rank == 0:
         line = {
@@ -318,7 +342,8 @@ def run_ours(args):
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": dict(workload_config(n, world), cells_per_gpu=nc, dofs_per_gpu=V.num_dofs, nnz_per_gpu=A.nnz,
                            slaves=len(mpc.slaves)),
-            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clk,
+            "roofline": roofline, "breakdown": breakdown, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches),
+            "clocks": clk,
         }
         emit(line)
     if world > 1:
