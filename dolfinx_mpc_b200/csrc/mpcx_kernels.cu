@@ -344,6 +344,8 @@ k_matrix_generic(Tab t, IntD in, MeshD mesh, const int* __restrict__ dm0, const 
   double* w = g + 3 * t.nd;
   int* d0 = (int*)(w + (in.cstride > 0 ? in.cstride : 1));
   int* d1 = d0 + nd0;
+  int* offR = d1 + nd1;      // [n0 + 1] first row-target index of local row p
+  int* offC = offR + n0 + 1;  // [n1 + 1]
   const long long nwork = mode == 1 ? in.nslave_cells : in.ncells;
   const long long wstride = (long long)gridDim.x * (blockDim.x >> 5);
   for (long long it = (long long)blockIdx.x * (blockDim.x >> 5) + warp; it < nwork; it += wstride)
@@ -359,41 +361,61 @@ k_matrix_generic(Tab t, IntD in, MeshD mesh, const int* __restrict__ dm0, const 
     for (int e = lane; e < nd1; e += 32) d1[e] = __ldg(dm1 + (long long)cell * nd1 + e);
     __syncwarp();
     tabulate_warp(entity_view(t, in, index), in.kernel, in.c, X, w, Ae, g, lane);
-    for (int e = lane; e < n0 * n1; e += 32)
+    if (!has_slaves)
     {
-      const int p = e / n1, q = e - p * n1;
-      const int ib = p / bs0, ia = p - ib * bs0, jb = q / bs1, ja = q - jb * bs1;
-      const int r = d0[ib] * bs0 + ia, cc = d1[jb] * bs1 + ja;
-      // BC zeroing precedes elimination (cpp/assemble_matrix.cpp:513-545); a zeroed entry
-      // contributes nothing anywhere, so it is skipped.
-      if ((bc0 && bc0[r]) || (bc1 && bc1[cc])) continue;
-      const double v = Ae[e];
-      if (!has_slaves)
+      for (int e = lane; e < n0 * n1; e += 32)
       {
+        const int p = e / n1, q = e - p * n1;
+        const int ib = p / bs0, ia = p - ib * bs0, jb = q / bs1, ja = q - jb * bs1;
+        const int r = d0[ib] * bs0 + ia, cc = d1[jb] * bs1 + ja;
+        // BC zeroing precedes elimination (cpp/assemble_matrix.cpp:513-545); a zeroed entry
+        // contributes nothing anywhere, so it is skipped.
+        if ((bc0 && bc0[r]) || (bc1 && bc1[cc])) continue;
         if (lpos)
-        {
-          const long long pos = A.rp[r] + (long long)lpos[index * (nd0 * nd1) + ib * nd1 + jb] * bs1 + ja;
-          atomicAdd(A.val + pos, v);
-        }
+          atomicAdd(A.val + A.rp[r] + (long long)lpos[index * (nd0 * nd1) + ib * nd1 + jb] * bs1 + ja, Ae[e]);
         else
-          csr_add(A, r, cc, v);
-        continue;
+          csr_add(A, r, cc, Ae[e]);
       }
-      // K^T A_e K entry-wise (cpp/assemble_matrix.cpp:214-267): target lists of row and column dof
-      const bool sr = m0.is_slave[r], sc = m1.is_slave[cc];
-      const int r0 = sr ? m0.offsets[r] : 0, r1 = sr ? m0.offsets[r + 1] : 1;
-      const int c0 = sc ? m1.offsets[cc] : 0, c1 = sc ? m1.offsets[cc + 1] : 1;
-      for (int a = r0; a < r1; ++a)
+      continue;
+    }
+    // K^T A_e K entry-wise (cpp/assemble_matrix.cpp:214-267): G[t_p, t_q] += w_p w_q A_e[p, q] over the target lists
+    // of the row and column dofs (a free dof targets itself with weight 1, a slave its masters with weights alpha,
+    // a bc-zeroed dof nothing).  The (row target, column target) pairs of the whole cell are numbered
+    // consecutively and dealt to the lanes, so that a slave x slave entry (|masters|^2 insertions in the
+    // reference, :239-245) does not serialise on one lane.
+    if (lane == 0)
+    {
+      int acc = 0;
+      for (int p = 0; p < n0; ++p)
       {
-        const int tr = sr ? m0.masters[a] : r;
-        const double wr = sr ? m0.coeffs[a] : 1.0;
-        for (int b = c0; b < c1; ++b)
-        {
-          const int tc = sc ? m1.masters[b] : cc;
-          const double wc = sc ? m1.coeffs[b] : 1.0;
-          csr_add(A, tr, tc, wr * wc * v);
-        }
+        offR[p] = acc;
+        const int r = d0[p / bs0] * bs0 + p % bs0;
+        if (!(bc0 && bc0[r])) acc += m0.is_slave[r] ? m0.offsets[r + 1] - m0.offsets[r] : 1;
       }
+      offR[n0] = acc;
+      acc = 0;
+      for (int q = 0; q < n1; ++q)
+      {
+        offC[q] = acc;
+        const int cc = d1[q / bs1] * bs1 + q % bs1;
+        if (!(bc1 && bc1[cc])) acc += m1.is_slave[cc] ? m1.offsets[cc + 1] - m1.offsets[cc] : 1;
+      }
+      offC[n1] = acc;
+    }
+    __syncwarp();
+    const int NR = offR[n0], NC = offC[n1];
+    for (int idx = lane; idx < NR * NC; idx += 32)
+    {
+      const int tp = idx / NC, tq = idx - tp * NC;
+      int p = 0, q = 0;
+      for (int lo = 0, hi = n0; hi - lo > 1;) { const int mid = (lo + hi) >> 1; if (offR[mid] <= tp) lo = mid; else hi = mid; p = lo; }
+      for (int lo = 0, hi = n1; hi - lo > 1;) { const int mid = (lo + hi) >> 1; if (offC[mid] <= tq) lo = mid; else hi = mid; q = lo; }
+      const int r = d0[p / bs0] * bs0 + p % bs0, cc = d1[q / bs1] * bs1 + q % bs1;
+      const bool sr = m0.is_slave[r], sc = m1.is_slave[cc];
+      const int a = sr ? m0.offsets[r] + (tp - offR[p]) : 0, b = sc ? m1.offsets[cc] + (tq - offC[q]) : 0;
+      const int tr = sr ? m0.masters[a] : r, tc = sc ? m1.masters[b] : cc;
+      const double wgt = (sr ? m0.coeffs[a] : 1.0) * (sc ? m1.coeffs[b] : 1.0);
+      csr_add(A, tr, tc, wgt * Ae[p * n1 + q]);
     }
   }
 }
@@ -750,6 +772,63 @@ k_matrix_p1_bulk(IntD in, MeshD mesh, const int* __restrict__ dm0, const int* __
   }
 }
 
+// Thread per cell, P1 isotropic elasticity with bs == gdim (inner(sigma(u), grad(v)) dx, constant gradients on an
+// affine simplex), cells without slaves only.  Block (i, j) of the element matrix is
+//   vol * (mu g_i[b] g_j[a] + lambda g_i[a] g_j[b] + delta_ab mu g_i . g_j),   a = row component, b = column component,
+// the closed form of the one-point rule the tabulated kernel evaluates.  Scatter through the blocked plan.
+template <int TD, typename PosT>
+__global__ void __launch_bounds__(128)
+k_matrix_p1_elasticity_bulk(IntD in, MeshD mesh, const int* __restrict__ dm0, const int* __restrict__ dm1,
+                            const int8_t* __restrict__ bc0, const int8_t* __restrict__ bc1,
+                            const int* __restrict__ c2s0, const int* __restrict__ c2s1, CsrD A,
+                            const PosT* __restrict__ lpos)
+{
+  constexpr int NV = TD + 1;
+  const long long index = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (index >= in.ncells) return;
+  const int cell = in.cells ? __ldg(in.cells + index) : (int)index;
+  if (__ldg(c2s0 + cell + 1) > __ldg(c2s0 + cell) || __ldg(c2s1 + cell + 1) > __ldg(c2s1 + cell)) return;
+  int xd[NV], r[NV], c[NV];
+#pragma unroll
+  for (int v = 0; v < NV; ++v)
+  {
+    xd[v] = __ldg(mesh.xd + (long long)cell * NV + v);
+    r[v] = __ldg(dm0 + (long long)cell * NV + v);
+    c[v] = __ldg(dm1 + (long long)cell * NV + v);
+  }
+  double X[NV][3];
+  load_vertices<TD>(mesh, xd, X);
+  P1Geom<TD> G;
+  p1_geometry<TD>(X, G);
+  const double mu = in.c[0] * G.vol, lmbda = in.c[1] * G.vol;
+  const PosT* lp = lpos + index * (NV * NV);
+#pragma unroll
+  for (int i = 0; i < NV; ++i)
+#pragma unroll
+    for (int a = 0; a < TD; ++a)
+    {
+      const int row = r[i] * TD + a;
+      if (bc0 && bc0[row]) continue;  // zeroed rows contribute nothing (cpp/assemble_matrix.cpp:513-525)
+      double* dst = A.val + __ldg(A.rp + row);
+#pragma unroll
+      for (int j = 0; j < NV; ++j)
+      {
+        double dot = 0.0;
+#pragma unroll
+        for (int k = 0; k < TD; ++k) dot += G.g[i][k] * G.g[j][k];
+        double* blk = dst + (long long)lp[i * NV + j] * TD;
+#pragma unroll
+        for (int b = 0; b < TD; ++b)
+        {
+          if (bc1 && bc1[c[j] * TD + b]) continue;
+          double v = mu * G.g[i][b] * G.g[j][a] + lmbda * G.g[i][a] * G.g[j][b];
+          if (a == b) v += mu * dot;
+          atomicAdd(blk + b, v);
+        }
+      }
+    }
+}
+
 // Thread per slave cell, scalar P1: K^T A_e K entry-wise (cpp/assemble_matrix.cpp:99-268) with the element
 // matrix in registers; every target is located by a search of its CSR row.
 template <int TD>
@@ -1039,7 +1118,7 @@ int mpcx_assemble_matrix_f64(const mpcx_integral* integral, const mpcx_mesh* mes
   const bool fast = lpos && have_split && closed_form && !integral->local_facets;  // facets: generic kernel
   // generic kernel resources
   const int wcount = in.cstride > 0 ? in.cstride : 1;
-  int spw = 3 * mesh->ng + n * n + 3 * nd + wcount + (2 * nd + 1) / 2 + 1;
+  int spw = 3 * mesh->ng + n * n + 3 * nd + wcount + (2 * nd + 2 * n + 2 + 1) / 2 + 1;
   const size_t smem = (size_t)spw * 4 * sizeof(double);
   if (smem > 48 * 1024)
   {
@@ -1058,7 +1137,26 @@ int mpcx_assemble_matrix_f64(const mpcx_integral* integral, const mpcx_mesh* mes
       MPCX_COUNT_LAUNCH(), k_matrix_generic<uint8_t><<<grid, 128, smem, s>>>(tab, in, md, dofmap0->map, dofmap1->map, nd, nd, bs, bs, bc0, bc1,
                                                         m0, m1, Ad, (const uint8_t*)lpos, mode, spw);
   };
-  if (fast)
+  const bool fast_elasticity = lpos && have_split && kid == MPCX_KERNEL_ELASTICITY && p1_simplex && bs == t->tdim
+                               && !integral->local_facets;
+  if (fast_elasticity)
+  {
+    const unsigned nb = (unsigned)((in.ncells + 127) / 128);
+    {
+      KernelTimer kt(s);
+      MPCX_COUNT_LAUNCH();
+      if (t->tdim == 3 && width == 1)
+        k_matrix_p1_elasticity_bulk<3, uint8_t><<<nb, 128, 0, s>>>(in, md, dofmap0->map, dofmap1->map, bc0, bc1, m0.c2s_off, m1.c2s_off, Ad, (const uint8_t*)lpos);
+      else if (t->tdim == 3)
+        k_matrix_p1_elasticity_bulk<3, uint16_t><<<nb, 128, 0, s>>>(in, md, dofmap0->map, dofmap1->map, bc0, bc1, m0.c2s_off, m1.c2s_off, Ad, (const uint16_t*)lpos);
+      else if (width == 1)
+        k_matrix_p1_elasticity_bulk<2, uint8_t><<<nb, 128, 0, s>>>(in, md, dofmap0->map, dofmap1->map, bc0, bc1, m0.c2s_off, m1.c2s_off, Ad, (const uint8_t*)lpos);
+      else
+        k_matrix_p1_elasticity_bulk<2, uint16_t><<<nb, 128, 0, s>>>(in, md, dofmap0->map, dofmap1->map, bc0, bc1, m0.c2s_off, m1.c2s_off, Ad, (const uint16_t*)lpos);
+    }
+    launch_generic(1, in.nslave_cells);  // slave cells, elimination
+  }
+  else if (fast)
   {
     const unsigned nb = (unsigned)((in.ncells + 255) / 256);
     {
