@@ -829,6 +829,95 @@ k_matrix_p1_elasticity_bulk(IntD in, MeshD mesh, const int* __restrict__ dm0, co
     }
 }
 
+// Warp per cell, 3-D isotropic elasticity (bs == 3) on an affine tetrahedron with ND scalar basis functions (P2:
+// ND = 10), cells without slaves only.  The ND x ND node pairs are dealt to the lanes and each lane keeps the 3 x 3
+// blocks of its pairs in REGISTERS across the quadrature loop (the generic kernel accumulates the 900-entry element
+// matrix in shared memory, read-modify-write per quadrature point); only the physical gradients of the current
+// point go through shared memory.  Scatter through the blocked plan.
+template <int ND, typename PosT>
+__global__ void __launch_bounds__(128)
+k_matrix_elast3d_bulk(Tab t, IntD in, MeshD mesh, const int* __restrict__ dm0, const int* __restrict__ dm1,
+                      const int8_t* __restrict__ bc0, const int8_t* __restrict__ bc1, const int* __restrict__ c2s0,
+                      const int* __restrict__ c2s1, CsrD A, const PosT* __restrict__ lpos)
+{
+  constexpr int NP = ND * ND, PPL = (NP + 31) / 32;
+  __shared__ double sX[4][12], sg[4][ND * 3];
+  __shared__ int sd0[4][ND], sd1[4][ND];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  double* X = sX[warp];
+  double* g = sg[warp];
+  int *d0 = sd0[warp], *d1 = sd1[warp];
+  const double mu = in.c[0], lmbda = in.c[1];
+  const long long wstride = (long long)gridDim.x * 4;
+  for (long long index = (long long)blockIdx.x * 4 + warp; index < in.ncells; index += wstride)
+  {
+    const int cell = in.cells ? __ldg(in.cells + index) : (int)index;
+    if (__ldg(c2s0 + cell + 1) > __ldg(c2s0 + cell) || __ldg(c2s1 + cell + 1) > __ldg(c2s1 + cell)) continue;
+    __syncwarp();
+    if (lane < 12)
+    {
+      const int gi = lane / 3, k = lane - gi * 3;
+      X[lane] = __ldg(mesh.x + (long long)__ldg(mesh.xd + (long long)cell * 4 + gi) * mesh.xs + k);
+    }
+    if (lane < ND) { d0[lane] = __ldg(dm0 + (long long)cell * ND + lane); d1[lane] = __ldg(dm1 + (long long)cell * ND + lane); }
+    __syncwarp();
+    double K[9], detJ;
+    jacobian(t, 0, X, K, detJ);  // affine geometry: one Jacobian per cell
+    double acc[PPL][9];
+#pragma unroll
+    for (int u = 0; u < PPL; ++u)
+#pragma unroll
+      for (int e = 0; e < 9; ++e) acc[u][e] = 0.0;
+    for (int q = 0; q < t.nq; ++q)
+    {
+      if (lane < ND)  // physical gradients of basis function `lane` at point q
+      {
+        const double r0 = __ldg(t.dphi + (q * 3 + 0) * ND + lane), r1 = __ldg(t.dphi + (q * 3 + 1) * ND + lane),
+                     r2 = __ldg(t.dphi + (q * 3 + 2) * ND + lane);
+#pragma unroll
+        for (int k = 0; k < 3; ++k) g[lane * 3 + k] = K[k] * r0 + K[3 + k] * r1 + K[6 + k] * r2;
+      }
+      __syncwarp();
+      const double sc = __ldg(t.w + q) * fabs(detJ);
+#pragma unroll
+      for (int u = 0; u < PPL; ++u)
+      {
+        const int pr = lane + 32 * u;
+        if (pr < NP)
+        {
+          const int i = pr / ND, j = pr - i * ND;
+          const double gi[3] = {g[i * 3], g[i * 3 + 1], g[i * 3 + 2]}, gj[3] = {g[j * 3], g[j * 3 + 1], g[j * 3 + 2]};
+          const double md = mu * (gi[0] * gj[0] + gi[1] * gj[1] + gi[2] * gj[2]);
+#pragma unroll
+          for (int a = 0; a < 3; ++a)
+#pragma unroll
+            for (int b = 0; b < 3; ++b)
+              acc[u][a * 3 + b] += sc * (mu * gi[b] * gj[a] + lmbda * gi[a] * gj[b] + (a == b ? md : 0.0));
+        }
+      }
+      __syncwarp();
+    }
+#pragma unroll
+    for (int u = 0; u < PPL; ++u)
+    {
+      const int pr = lane + 32 * u;
+      if (pr >= NP) continue;
+      const int i = pr / ND, j = pr - i * ND;
+      const long long boff = (long long)lpos[index * NP + pr] * 3;
+#pragma unroll
+      for (int a = 0; a < 3; ++a)
+      {
+        const int row = d0[i] * 3 + a;
+        if (bc0 && bc0[row]) continue;  // zeroed rows contribute nothing (cpp/assemble_matrix.cpp:513-525)
+        double* dst = A.val + __ldg(A.rp + row) + boff;
+#pragma unroll
+        for (int b = 0; b < 3; ++b)
+          if (!(bc1 && bc1[d1[j] * 3 + b])) atomicAdd(dst + b, acc[u][a * 3 + b]);
+      }
+    }
+  }
+}
+
 // Thread per slave cell, scalar P1: K^T A_e K entry-wise (cpp/assemble_matrix.cpp:99-268) with the element
 // matrix in registers; every target is located by a search of its CSR row.
 template <int TD>
@@ -1139,7 +1228,22 @@ int mpcx_assemble_matrix_f64(const mpcx_integral* integral, const mpcx_mesh* mes
   };
   const bool fast_elasticity = lpos && have_split && kid == MPCX_KERNEL_ELASTICITY && p1_simplex && bs == t->tdim
                                && !integral->local_facets;
-  if (fast_elasticity)
+  const bool fast_p2_elasticity = lpos && have_split && kid == MPCX_KERNEL_ELASTICITY && t->tdim == 3 && bs == 3 && t->ng == 4
+                                  && nd == 10 && !integral->local_facets;
+  if (fast_p2_elasticity)
+  {
+    {
+      KernelTimer kt(s);
+      MPCX_COUNT_LAUNCH();
+      const int grid = grid_for_warps(in.ncells, 4);
+      if (width == 1)
+        k_matrix_elast3d_bulk<10, uint8_t><<<grid, 128, 0, s>>>(tab, in, md, dofmap0->map, dofmap1->map, bc0, bc1, m0.c2s_off, m1.c2s_off, Ad, (const uint8_t*)lpos);
+      else
+        k_matrix_elast3d_bulk<10, uint16_t><<<grid, 128, 0, s>>>(tab, in, md, dofmap0->map, dofmap1->map, bc0, bc1, m0.c2s_off, m1.c2s_off, Ad, (const uint16_t*)lpos);
+    }
+    launch_generic(1, in.nslave_cells);  // slave cells, elimination
+  }
+  else if (fast_elasticity)
   {
     const unsigned nb = (unsigned)((in.ncells + 127) / 128);
     {
