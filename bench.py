@@ -328,6 +328,9 @@ def run_ours(args):
     # end-to-end through the public API with host (pinned) buffers: every array the call reads is copied
     # host -> device inside the timed region, the assembled CSR values and RHS are copied back
     e2e = run_e2e(args, P, A, b, step, world, barrier)
+    # same pipeline when the assembled system is consumed on the device (Matrix.dlpack / to_torch_sparse_csr) and
+    # only two norms travel back: reported beside the headline e2e, not instead of it
+    e2e_dev = run_e2e(args, P, A, b, step, world, barrier, download="norms")
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
@@ -342,7 +345,8 @@ def run_ours(args):
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": dict(workload_config(n, world), cells_per_gpu=nc, dofs_per_gpu=V.num_dofs, nnz_per_gpu=A.nnz,
                            slaves=len(mpc.slaves)),
-            "roofline": roofline, "breakdown": breakdown, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches),
+            "roofline": roofline, "breakdown": breakdown, "cpu_baseline": cpu, "e2e": e2e,
+            "e2e_device_consumer": e2e_dev, "gpu_launches": int(launches),
             "clocks": clk,
         }
         emit(line)
@@ -350,7 +354,7 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
-def run_e2e(args, P, A, b, step, world, barrier):
+def run_e2e(args, P, A, b, step, world, barrier, download="full"):
     """End to end through the public API with HOST buffers.  Every step uploads the step's INPUT VALUES from
     pinned host memory (vertex coordinates, the coefficient, Dirichlet values, constraint coefficients) and
     downloads the assembled CSR values and the RHS to pinned host memory.  The mesh topology / dofmaps /
@@ -374,9 +378,10 @@ def run_e2e(args, P, A, b, step, world, barrier):
     nnz, nb = A.nnz, b.data.numel()
     val_bufs = [A._val_storage, torch.zeros_like(A._val_storage)]
     b_bufs = [b.data, torch.zeros(nb + (nb & 1), dtype=torch.float64, device=b.data.device)[:nb]]  # even capacity (mpcx.h)
-    out_val = [torch.empty(nnz, dtype=torch.float64).pin_memory() for _ in range(2)]
-    out_b = [torch.empty(nb, dtype=torch.float64).pin_memory() for _ in range(2)]
-    d2h = (nnz + nb) * 8
+    full = download == "full"  # "norms": the matrix stays on the device for a device-side consumer (DLPack hand-off)
+    out_val = [torch.empty(nnz if full else 1, dtype=torch.float64).pin_memory() for _ in range(2)]
+    out_b = [torch.empty(nb if full else 1, dtype=torch.float64).pin_memory() for _ in range(2)]
+    d2h = (nnz + nb) * 8 if full else 16
     cur = torch.cuda.current_stream()
     s_in, s_out = torch.cuda.Stream(), torch.cuda.Stream()
 
@@ -402,8 +407,12 @@ def run_e2e(args, P, A, b, step, world, barrier):
             ev_done.append(e)
             with torch.cuda.stream(s_out):
                 s_out.wait_event(e)
-                out_val[i].copy_(val_bufs[i][:nnz], non_blocking=True)
-                out_b[i].copy_(b_bufs[i], non_blocking=True)
+                if full:
+                    out_val[i].copy_(val_bufs[i][:nnz], non_blocking=True)
+                    out_b[i].copy_(b_bufs[i], non_blocking=True)
+                else:
+                    out_val[i].copy_(torch.linalg.vector_norm(val_bufs[i][:nnz]).reshape(1), non_blocking=True)
+                    out_b[i].copy_(torch.linalg.vector_norm(b_bufs[i]).reshape(1), non_blocking=True)
                 eo = torch.cuda.Event()
                 eo.record(s_out)
             ev_out.append(eo)
@@ -435,6 +444,7 @@ def run_e2e(args, P, A, b, step, world, barrier):
         nc = int(c.item())
     return {"value": nc * k / (ms * 1e-3), "unit": "cells/s", "h2d_bytes_per_step": int(h2d),
             "d2h_bytes_per_step": int(d2h), "ms_per_step": ms / k, "steps": k,
+            "download": "CSR values + RHS" if full else "Frobenius norm of the matrix and norm of the RHS (matrix consumed on the device)",
             "note": "per step: pinned-host upload of the input VALUES (vertex coordinates, coefficient, Dirichlet values, "
                     "constraint coefficients), assembly, download of CSR values + RHS to pinned host memory; topology "
                     "(dofmaps, constraint structure), sparsity pattern and tile plans are cached on the device like the "
