@@ -18,3 +18,14 @@ def oracle():
 
     orc.build()
     return orc
+
+
+@pytest.fixture
+def get_assemblers(request):
+    """The reference's backend switch (python/tests/conftest.py:4-22, options "C++" and "numba") with the third
+    option this repository adds: "cuda" = dolfinx_mpc_b200 (device kernels behind the same two callables)."""
+    if request.param == "cuda":
+        from dolfinx_mpc_b200 import assemble_matrix, assemble_vector
+
+        return (assemble_matrix, assemble_vector)
+    raise RuntimeError(f"Undefined assembler type: {request.param}.\nOptions here are 'cuda'")

@@ -403,3 +403,27 @@ def test_tile_plan_fallback_on_a_fan_mesh(oracle):
     m = oracle.mpc_from_arrays(V, gen.empty_constraint())
     assert_csr_close(*A.getValuesCSR(), *oracle.assemble_matrix(a, m))
     assert_vec_close(mpcx.assemble_vector(L, mpc).array, oracle.assemble_vector(L, m))
+
+
+@pytest.mark.parametrize("get_assemblers", ["cuda"], indirect=True)
+@pytest.mark.parametrize("master_point", [[1, 1], [0, 1]])
+def test_mpc_assembly_reference_style(oracle, get_assemblers, master_point):
+    """python/tests/test_matrix_assembly.py:20-57 transcribed: same fixture switch, same dictionary constraint, same
+    comparison K^T A K == A_mpc through the transformation matrix -- with "cuda" as the assembler."""
+    from dolfinx_mpc_b200 import MultiPointConstraint, fem, generators as gen
+
+    assemble_matrix, _ = get_assemblers
+    mesh = gen.create_unit_square(5, 3)
+    V = gen.functionspace(mesh, 1)
+    a = fem.laplace(V)
+    s_m_c = {(1, 0): {(0, 1): 0.43, (1, 1): 0.11}, (0, 0): {tuple(master_point): 0.69}}
+    mpc = MultiPointConstraint(V)
+    mpc.create_general_constraint(s_m_c)
+    mpc.finalize()
+    A_mpc = assemble_matrix(a, mpc)
+    e = oracle.OracleMPC.empty(V)
+    n = V.num_dofs
+    A_org = sp.csr_matrix(oracle.assemble_matrix(a, e)[::-1], shape=(n, n))
+    data = gen.general_constraint(V, s_m_c)
+    K = oracle.transformation_matrix(n, data[0], data[1], data[2], data[4])
+    oracle.compare_mpc_lhs(A_org, A_mpc.to_scipy(), K, data[0])
