@@ -863,9 +863,10 @@ k_matrix_elast3d_bulk(Tab t, IntD in, MeshD mesh, const int* __restrict__ dm0, c
     __syncwarp();
     double K[9], detJ;
     jacobian(t, 0, X, K, detJ);  // affine geometry: one Jacobian per cell
-    // the pairs of a lane are processed in rounds of RPL: 18 accumulators instead of 36 keep the kernel at ~90
-    // registers (5 blocks per SM instead of 3); the gradients of a quadrature point are recomputed per round
-    constexpr int RPL = 2, ROUNDS = (PPL + RPL - 1) / RPL;
+    // the pairs of a lane are processed in rounds of RPL pairs: 9 accumulators instead of 36 keep the kernel at 70
+    // registers (7 blocks per SM instead of 3: 3.45 -> 2.75 ms at 384 k cells); the gradients of a quadrature point
+    // are recomputed per round
+    constexpr int RPL = 1, ROUNDS = (PPL + RPL - 1) / RPL;
     for (int round = 0; round < ROUNDS; ++round)
     {
       double acc[RPL][9];
