@@ -90,3 +90,24 @@ def test_cuda_matches_oracle_on_random_constraints(oracle, cfg, seed):
     mpc.backsubstitution(uf)
     oracle.backsubstitution(m, u)
     assert np.allclose(uf.array, u, rtol=1e-13, atol=1e-14)  # sums of up to 4 signed terms: fma vs separate rounding
+
+
+@pytest.mark.parametrize("cfg", CONFIGS, ids=[f"{c}-P{d}-bs{b}" for c, d, b, _ in CONFIGS])
+def test_host_data_model_and_pattern_on_random_constraints(oracle, cfg):
+    """MultiPointConstraint.finalize (cpp/MultiPointConstraint.h:36-126) and the host pattern builder
+    (cpp/utils.h:381-496) against the oracle's restatements, bit for bit, on a random draw."""
+    import dolfinx_mpc_b200 as mpcx
+
+    V, a, L, data, bcs = draw(*cfg, seed=3)
+    mpc = mpcx.MultiPointConstraint(V)
+    mpc.add_constraint(V, *data)
+    mpc.finalize()
+    m = oracle.mpc_from_arrays(V, data)
+    assert np.array_equal(mpc.is_slave, m.is_slave) and np.array_equal(mpc.slaves, m.slaves)
+    assert np.array_equal(mpc.masters.offsets, m.offsets) and np.array_equal(mpc.masters.array, m.masters)
+    assert np.array_equal(mpc.coefficients()[0], m.coeffs)
+    assert np.array_equal(mpc.cell_to_slaves.offsets, m.c2s_offsets) and np.array_equal(mpc.cell_to_slaves.array, m.c2s)
+    assert mpc.num_local_slaves == m.num_local_slaves
+    rp, col = mpcx.create_sparsity_pattern(a, mpc, num_threads=3)
+    rp_o, col_o = oracle.create_pattern(a, m, m)
+    assert np.array_equal(rp, rp_o) and np.array_equal(col, col_o)
