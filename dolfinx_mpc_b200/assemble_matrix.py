@@ -171,7 +171,8 @@ def assemble_matrix(form: Form, constraint: Union[MultiPointConstraint, Sequence
             raise RuntimeError(f"{it.integral_type} integrals have no device kernel yet")
         s = _dev.integral_struct(form, it, (mpc0, mpc1), keep)
         facet = it.integral_type == "exterior_facet"  # surface-sized: generic kernel, row search per entry
-        tile = A.tile_plan(form, it, s, bc0_d, bc1_d, (id(mpc0), id(mpc1))) if A.scatter == "tile" and not facet else None
+        tile = (A.tile_plan(form, it, s, bc0_d, bc1_d, (id(mpc0), id(mpc1)), keepalive=(mpc0, mpc1))
+                if A.scatter == "tile" and not facet else None)
         if tile is not None:
             _lib.check(lib.mpcx_assemble_matrix_tiled_f64(C.byref(s), C.byref(mesh_s), C.byref(d0), C.byref(d1),
                                                           _dev.ptr(bc0_d), _dev.ptr(bc1_d), C.byref(m0), C.byref(m1),

@@ -143,6 +143,7 @@ def integral_struct(form: Form, it: Integral, mpcs, keep: list) -> _lib.Integral
         for m in mpcs:
             has |= np.diff(m.cell_to_slaves.offsets)[active] > 0
         pos = np.flatnonzero(has).astype(np.int32)
+        d[("keepalive",) + key] = tuple(mpcs)  # their id() keys the list: must not be reused while it is cached
         d[key] = (to_dev(pos) if len(pos) else None, len(pos))
     sc, nsc = d[key]
     # an empty list is passed as a non-null pointer to a dummy so the library knows the split is valid

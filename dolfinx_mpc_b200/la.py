@@ -46,6 +46,7 @@ class Matrix:
         self.max_block_row = max_block_row
         self._plans = {}
         self._tile_plans = {}
+        self._keepalive = {}  # objects whose id() keys a cached plan: kept alive so that the id cannot be reused
         # "tile": entries combined per 512-cell tile in shared memory, one reduction per (tile, entry), where a
         # tile kernel exists; "atomic": one red.global.add per element entry
         self.scatter = os.environ.get("MPCX_SCATTER", "tile")
@@ -76,6 +77,7 @@ class Matrix:
             return None
         key = (id(form.function_spaces[0]), id(form.function_spaces[1]), id(integral))
         if key not in self._plans:
+            self._keepalive[key] = (form.function_spaces, integral)
             V0, V1 = form.function_spaces
             ncells = form.mesh.num_cells_local if integral.cells is None else len(integral.cells)
             lpos = torch.empty(ncells * V0.nd * V1.nd, dtype=torch.uint8 if width == 1 else torch.int16,
@@ -92,7 +94,7 @@ class Matrix:
             self._plans[key] = (lpos, _lib.PlanS(_dev.ptr(lpos), width))
         return self._plans[key][1]
 
-    def tile_plan(self, form, integral, s_integral, bc0_d, bc1_d, key_extra=()):
+    def tile_plan(self, form, integral, s_integral, bc0_d, bc1_d, key_extra=(), keepalive=()):
         """Tile plan (csrc/mpcx_tile.cuh) for one integral into this pattern; built on the device on first use.
         Returns None when the element has no tile kernel."""
         V0, V1 = form.function_spaces
@@ -102,6 +104,7 @@ class Matrix:
             return None
         key = (id(V0), id(V1), id(integral), _dev.ptr(bc0_d), _dev.ptr(bc1_d)) + tuple(key_extra)
         if key not in self._tile_plans:
+            self._keepalive[key] = (V0, V1, integral, bc0_d, bc1_d, keepalive)
             lib = _lib.load()
             ncells = int(s_integral.num_cells)
             skip = None
