@@ -72,11 +72,13 @@ def algorithmic_bytes(P, nnz: int, with_rhs: bool) -> float:
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe).  The sampler is
+    started before the warm-up (nvidia-smi needs ~0.1 s to deliver its first line) and samples every 20 ms; only
+    the samples whose timestamp falls inside the timed window [t0, t1] are used."""
 
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
-         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
-         "clocks_event_reasons.sw_power_cap")
+    Q = ("timestamp,index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, gpu_index: int):
         self.proc = None
@@ -85,37 +87,40 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "100", "-i", str(self.gpu)], stdout=subprocess.PIPE,
+                                          "-lms", "20", "-i", str(self.gpu)], stdout=subprocess.PIPE,
                                          stderr=subprocess.DEVNULL, text=True)
         except OSError:
             self.proc = None
 
-    def stop(self) -> dict:
+    def stop(self, t0: float, t1: float) -> dict:
+        import datetime
+
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
+        time.sleep(0.05)
         self.proc.terminate()
         try:
             out, _ = self.proc.communicate(timeout=5)
         except subprocess.TimeoutExpired:
             self.proc.kill()
             out, _ = self.proc.communicate()
-        sm, mx, reasons = [], [], set()
+        rows = []
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         for line in out.strip().splitlines():
             p = [q.strip() for q in line.split(",")]
-            if len(p) < 9:
+            if len(p) < 10:
                 continue
             try:
-                sm.append(float(p[1]))
-                mx.append(float(p[2]))
+                ts = datetime.datetime.strptime(p[0], "%Y/%m/%d %H:%M:%S.%f").timestamp()
+                rows.append((ts, float(p[2]), float(p[3]), [n for n, v in zip(names, p[6:10]) if v.lower().startswith("active")]))
             except ValueError:
                 continue
-            for name, v in zip(names, p[5:9]):
-                if v.lower().startswith("active"):
-                    reasons.add(name)
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "samples": len(sm), "reasons": sorted(reasons)}
+        inside = [r for r in rows if t0 - 0.01 <= r[0] <= t1 + 0.01]
+        used = inside or rows[-3:]
+        reasons = sorted({n for r in used for n in r[3]})
+        return {"sm_mhz": float(np.median([r[1] for r in used])) if used else None,
+                "sm_max_mhz": max(r[2] for r in used) if used else None, "samples": len(inside),
+                "samples_total": len(rows), "reasons": reasons}
 
 
 # ------------------------------------------------------------------------------------------------ CPU reference arm
@@ -258,22 +263,24 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    clocks = ClockSampler(local_rank)
+    if rank == 0:
+        clocks.start()
     for _ in range(args.warmup):
         step()
     barrier()
     lib.mpcx_profile_enable(1)
     launches0 = lib.mpcx_launch_count()
-    clocks = ClockSampler(local_rank)
-    if rank == 0:
-        clocks.start()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
+    t_wall0 = time.time()
     ev0.record()
     for _ in range(args.steps):
         step()
     ev1.record()
     barrier()
-    clk = clocks.stop() if rank == 0 else None
+    t_wall1 = time.time()
+    clk = clocks.stop(t_wall0, t_wall1) if rank == 0 else None  # samples inside the timed window, 20 ms apart
     ms_total = ev0.elapsed_time(ev1)
     launches = lib.mpcx_launch_count() - launches0
     kms, kn = C.c_double(0), C.c_longlong(0)
@@ -325,8 +332,8 @@ def run_ours(args):
                  "assemble_vector_ms": timed(lambda: mpcx.assemble_vector(L, mpc, b=b)),
                  "apply_lifting_ms": timed(lambda: mpcx.apply_lifting(b, [a], [bcs], mpc))}
 
-    # end-to-end through the public API with host (pinned) buffers: every array the call reads is copied
-    # host -> device inside the timed region, the assembled CSR values and RHS are copied back
+    # end-to-end through the public API with host (pinned) buffers: the step's input values are copied host -> device
+    # inside the timed region, the assembled CSR values and RHS are copied back (see run_e2e)
     e2e = run_e2e(args, P, A, b, step, world, barrier)
     # same pipeline when the assembled system is consumed on the device (Matrix.dlpack / to_torch_sparse_csr) and
     # only two norms travel back: reported beside the headline e2e, not instead of it
