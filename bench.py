@@ -1,15 +1,20 @@
 #!/usr/bin/env python
 """bench.py -- cells assembled/sec (matrix + vector) for MPC-constrained assembly on B200.
 
-Workload (BASELINE.json configs[1]): 3D unit-cube Poisson, P1 tetrahedra (Kuhn split), 256^3 dofs, periodic
-x/y multi-point constraint, Dirichlet on z in {0, 1}, fp64.  One "step" = what LinearProblem.solve does before
-the linear solve (python/src/dolfinx_mpc/problem.py:539-582): zero + assemble_matrix (bulk cells, slave-cell
-elimination, slave and Dirichlet diagonals), zero + assemble_vector, apply_lifting.
+One "step" = what LinearProblem.solve does before the linear solve (python/src/dolfinx_mpc/problem.py:539-582):
+zero + assemble_matrix (bulk cells, slave-cell elimination, slave and Dirichlet diagonals), zero + assemble_vector,
+apply_lifting, ghost-row / ghost-entry reduction when the mesh is partitioned.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--n 256]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--config 2|3|4|5] [--n SIZE]
 
-N > 1 is launched by torchrun (one rank per GPU); cells shard by z-slab ownership, per-GPU work fixed
-(weak scaling), ghost rows reduced over NCCL at the end of every step.
+Workloads (BASELINE.json configs[i-1]):
+  --config 2  3D unit-cube Poisson P1, 256^3 dofs, periodic x/y MPC, Dirichlet z-faces, one GPU   (default at N = 1)
+  --config 3  3D elasticity P2 (bs = 3) on a rotated cube, slip constraint on the inclined face, ~50 M dofs, one GPU
+  --config 4  3D Poisson P1, 512 x 512 nodes in x/y, periodic on ALL faces, pre-partitioned in z-slabs of 64 cube
+              layers per GPU, ghost rows reduced over NCCL; 8 GPUs = the 512^3 problem          (default at N > 1)
+  --config 5  contact constraint between two stacked boxes with non-matching grids, P1 elasticity (bs = 3),
+              ~20 M dofs, up to 11 masters per slave, one GPU
+N > 1 is launched by torchrun (one rank per GPU); per-GPU work is fixed (weak scaling).
 """
 from __future__ import annotations
 
@@ -29,9 +34,10 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
 FALLBACK_HBM_GBS = 6650.0  # /opt/skills/guides/B200_PROFILING.md fallback
-# dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the bulk matrix kernel at n = 256 on one GPU, from the
-# `ncu --set full` capture summarised in profiles/r01_o256_ncu_full_summary.csv (7.263 GB read + 2.307 GB written)
-NCU_TRAFFIC_N256 = 9.570e9
+TRAFFIC_FILE = os.path.join(ROOT, "profiles", "traffic.json")  # written by tools/ncu_summary.py from ncu --set full captures
+
+DEFAULT_N = {2: 256, 3: 127, 4: 512, 5: 114}
+NZC_CFG4 = 64  # cube layers per GPU of config 4 (8 x 64 = 512 layers = the 512^3 problem)
 
 
 def f_source(x):
@@ -39,9 +45,25 @@ def f_source(x):
     return x[0] * np.sin(5 * np.pi * x[1]) + np.exp(-((x[0] - 0.5) ** 2 + (x[1] - 0.5) ** 2) / 0.02)
 
 
+def f_vector(x):
+    f = f_source(x)
+    return np.stack([f, -0.5 * f + 0.1, 0.25 * f - 0.2])
+
+
+# ------------------------------------------------------------------------------------------------ workloads
+
+def _finish(V, data, bcs, a, L, f, mesh, **extra):
+    from dolfinx_mpc_b200 import MultiPointConstraint
+
+    mpc = MultiPointConstraint(V)
+    mpc.add_constraint(V, *data)
+    mpc.finalize()
+    return dict(mesh=mesh, V=V, bcs=bcs, data=data, mpc=mpc, a=a, L=L, f=f, **extra)
+
+
 def build_problem(n: int, nz: int | None = None):
-    """Unit-cube P1 Poisson with n^2 x (nz or n) nodes, periodic x/y, Dirichlet z-faces (host arrays)."""
-    from dolfinx_mpc_b200 import MultiPointConstraint, fem, generators as gen
+    """Config 2: unit-cube P1 Poisson with n^2 x (nz or n) nodes, periodic x/y, Dirichlet z-faces (host arrays)."""
+    from dolfinx_mpc_b200 import fem, generators as gen
 
     nz = n if nz is None else nz
     mesh = gen.create_box(n - 1, n - 1, nz - 1, p1=(1.0, 1.0, (nz - 1) / (n - 1)))
@@ -50,14 +72,92 @@ def build_problem(n: int, nz: int | None = None):
     bc_dofs = fem.locate_dofs_geometrical(V, lambda x: np.isclose(x[2], 0) | np.isclose(x[2], zmax))
     bcs = [fem.DirichletBC(V, bc_dofs, 0.25)]
     data = gen.periodic_constraint(V, axes=(0, 1), exclude_dofs=bc_dofs)
-    mpc = MultiPointConstraint(V)
-    mpc.add_constraint(V, *data)
-    mpc.finalize()
-    a = fem.laplace(V)
     f = fem.Function(V)
     f.interpolate(f_source)
-    L = fem.source(V, f)
-    return dict(mesh=mesh, V=V, bcs=bcs, data=data, mpc=mpc, a=a, L=L, f=f)
+    return _finish(V, data, bcs, fem.laplace(V), fem.source(V, f), f, mesh)
+
+
+def build_slip_elasticity(n: int, theta: float = np.pi / 5):
+    """Config 3: P2 vector elasticity (E = 1e4, nu = 0.1: python/benchmarks/bench_elasticity_edge.py:116-135) on
+    n^3 cubes x 6 tetrahedra, geometry rotated by theta about (1,1,0)/sqrt(2) (python/tests/test_cube_contact.py:28,45),
+    slip u.n = 0 on the (rotated) face x = 1 (cpp/SlipConstraint.h:123-140), Dirichlet on the opposite face."""
+    from dolfinx_mpc_b200 import fem, generators as gen
+
+    mesh0 = gen.create_unit_cube(n, n, n)
+    V0 = gen.functionspace(mesh0, 2, 3)
+    X0 = V0.tabulate_dof_coordinates()
+    slip_blocks = np.flatnonzero(np.isclose(X0[:, 0], 1.0))
+    fixed = np.flatnonzero(np.isclose(X0[:, 0], 0.0))
+    k = np.array([1.0, 1.0, 0.0]) / np.sqrt(2)
+    Kx = np.array([[0, -k[2], k[1]], [k[2], 0, -k[0]], [-k[1], k[0], 0]])
+    R = np.eye(3) + np.sin(theta) * Kx + (1 - np.cos(theta)) * (Kx @ Kx)
+    mesh = fem.Mesh(mesh0.x @ R.T, mesh0.x_dofmap, mesh0.cell_type)
+    V = fem.FunctionSpace(mesh, 2, V0.dofmap, 3, V0.index_map, X0 @ R.T)
+    del mesh0, V0
+    normal = R @ np.array([1.0, 0.0, 0.0])
+    bc_dofs = (fixed[:, None] * 3 + np.arange(3)[None, :]).reshape(-1).astype(np.int32)
+    bcs = [fem.DirichletBC(V, bc_dofs, np.array([0.01, -0.02, 0.03]))]
+    data = gen.slip_constraint(V, slip_blocks, normal, exclude_dofs=bc_dofs)
+    E, nu = 1.0e4, 0.1
+    mu, lmbda = E / (2 * (1 + nu)), E * nu / ((1 + nu) * (1 - 2 * nu))
+    f = fem.Function(V)
+    f.interpolate(f_vector)
+    return _finish(V, data, bcs, fem.elasticity(V, mu, lmbda), fem.source(V, f), f, mesh)
+
+
+def build_contact(n: int):
+    """Config 5: two stacked boxes [0,1]^2 x [0,0.5] and [0,1]^2 x [0.5,1] meshed with n and 2n cells per unit
+    length (non-matching interface, python/tests/test_cube_contact.py:31-45,145-147), P1 vector elasticity
+    (E = 1e3, nu = 0), contact-slip on the interface: every upper interface block is a slave with the other
+    components of its block and the three vertices of the facing lower facet (x 3 components) as masters
+    (cpp/ContactConstraint.h:87-152); bottom face clamped."""
+    from dolfinx_mpc_b200 import fem, generators as gen
+
+    mesh = gen.create_stacked_boxes((n, n, max(1, n // 2)), (2 * n, 2 * n, n))
+    V = gen.functionspace(mesh, 1, 3)
+    X = V.tabulate_dof_coordinates()
+    bottom = np.flatnonzero(np.isclose(X[:, 2], 0.0))
+    bc_dofs = (bottom[:, None] * 3 + np.arange(3)[None, :]).reshape(-1).astype(np.int32)
+    bcs = [fem.DirichletBC(V, bc_dofs, 0.0)]
+    nrm = np.array([0.2, -0.1, 1.0])
+    data = gen.contact_constraint(V, 0.5, normal=nrm / np.linalg.norm(nrm))
+    f = fem.Function(V)
+    f.interpolate(f_vector)
+    return _finish(V, data, bcs, fem.elasticity(V, 1.0e3 / 2, 0.0), fem.source(V, f), f, mesh)
+
+
+def build_config(cfg: int, n: int, rank: int = 0, world: int = 1):
+    if cfg == 2:
+        if world > 1:  # config 2 stacked in z: per-GPU work fixed, Dirichlet on the two end planes
+            from dolfinx_mpc_b200 import distributed
+
+            return distributed.build_slab_problem(n, rank, world, f_source)
+        return build_problem(n)
+    if cfg == 4:
+        from dolfinx_mpc_b200 import distributed
+
+        nzc = NZC_CFG4 if n == DEFAULT_N[4] else max(2, n // 8)
+        return distributed.build_slab_problem(n, rank, world, f_source, periodic_z=True, nzc=nzc)
+    if world > 1:
+        raise SystemExit(f"--config {cfg} is a single-GPU workload here (its mesh is not pre-partitioned); use --gpus 1")
+    return build_slip_elasticity(n) if cfg == 3 else build_contact(n)
+
+
+def workload_config(cfg, n, gpus):
+    desc = {
+        2: f"3D unit-cube Poisson P1 (Kuhn tets), {n}^3 dofs per GPU, periodic x/y MPC, Dirichlet z-faces, fp64"
+           " (BASELINE.json configs[1])",
+        3: f"3D linear elasticity P2 (bs 3) on {n}^3 x 6 tets, rotated cube, slip constraint on the inclined face, "
+           f"{3 * (2 * n + 1) ** 3} dofs, fp64 (BASELINE.json configs[2])",
+        4: f"3D Poisson P1 (Kuhn tets), {n} x {n} x ({gpus} x {NZC_CFG4 if n == DEFAULT_N[4] else max(2, n // 8)} + 1) nodes, "
+           f"periodic on all faces, pre-partitioned into {gpus} z-slab(s), ghost-row NCCL reduce, fp64 (BASELINE.json "
+           "configs[3]: 8 GPUs = 512^3)",
+        5: f"contact constraint between two stacked boxes ({n} / {2 * n} cells per unit length), P1 elasticity (bs 3), "
+           "fp64 (BASELINE.json configs[4])",
+    }[cfg]
+    return {"workload": desc, "config_id": cfg, "n": n, "gpus": gpus,
+            "l2": "inputs (> 3 GB per step) far larger than the 126 MB L2; no explicit flush",
+            "partition": "z-slabs by ownership, ghost-row NCCL reduce" if gpus > 1 else "single GPU"}
 
 
 def algorithmic_bytes(P, nnz: int, with_rhs: bool) -> float:
@@ -128,41 +228,93 @@ class ClockSampler:
 LAST_ONE_RANK = None
 
 
-def cpu_reference(n: int, steps: int, warmup: int, budget_s: float, label: str):
-    """The reference's algorithm (oracle port, oracle/mpc_oracle.c -- the reference itself cannot be built in
-    this image) on all host cores: R = nproc independent ranks, each assembling its own z-slab into its own
-    local matrix / vector with no communication, as `mpirun -n R` does (README.md:30 of the reference);
-    time = slowest rank.  Each step is a bounded sample: slabs of `nz_s` node layers per rank."""
+def _oracle_rank(P):
+    """Oracle-side objects of one rank's problem: packed constraint (masters in the rank's extended local
+    numbering, cpp/MultiPointConstraint.h:117-125) and the local sparsity pattern."""
     from oracle import oracle as orc
 
-    orc.build()
-    R = os.cpu_count() or 1
-    # calibrate the slab thickness on one rank so that a step lasts about budget_s / (steps + warmup)
-    nz_s = 3
-    P0 = build_problem(n, nz_s)
-    m0 = orc.mpc_from_arrays(P0["V"], P0["data"])
-    pat0 = orc.create_pattern(P0["a"], m0, m0)
-    t0 = time.perf_counter()
-    orc.assemble_matrix(P0["a"], m0, bcs=P0["bcs"], pattern=pat0)
-    b0 = orc.assemble_vector(P0["L"], m0)
-    orc.apply_lifting(b0, [P0["a"]], [P0["bcs"]], m0)
-    rate = P0["mesh"].num_cells_local / (time.perf_counter() - t0)  # cells/s, one rank, cold
-    per_step = budget_s / max(1, steps + warmup)
-    layers = int(rate * per_step / (6 * (n - 1) ** 2))
-    nz_s = int(min(max(3, layers + 1), max(3, n // R + 1)))
-    # one slab problem shared read-only by the R ranks; every rank assembles into its own matrix values / vector
-    P = P0 if nz_s == 3 else build_problem(n, nz_s)
-    m = orc.mpc_from_arrays(P["V"], P["data"])
+    mpc = P["mpc"]
+    V = mpc.function_space
+    m = orc.WrappedMPC(V, mpc.is_slave, mpc.masters.array, mpc.coefficients()[0], mpc.masters.offsets,
+                       mpc.cell_to_slaves.array, mpc.cell_to_slaves.offsets, mpc.slaves, mpc.num_local_slaves)
     pat = orc.create_pattern(P["a"], m, m)
-    bs_ = [np.zeros(P["V"].num_dofs) for _ in range(R)]
-    cells = R * P["mesh"].num_cells_local
+    return m, pat
+
+
+def _divisor_at_most(k: int, limit: int) -> int:
+    return max(d for d in range(1, max(1, limit) + 1) if k % d == 0)
+
+
+def cpu_rank_problems(cfg: int, n: int, cores: int, budget_cells: float):
+    """The per-rank problems of the CPU arm: R ranks, EACH WITH ITS OWN ARRAYS (mesh, dofmap, constraint, pattern,
+    matrix, vector), as `mpirun -n R` gives the reference (README.md:30 of the reference: owner-local cells, no
+    communication during assembly).
+
+    Configs 2 and 4 (slab-partitionable P1 Poisson): the ranks' slabs together cover one GPU's whole workload when
+    `budget_cells` allows it (R = largest divisor of the number of cube layers <= cores); otherwise thinner slabs of
+    the same cross-section (a bounded sample).  Configs 3 and 5: R independent smaller instances of the same
+    problem (same element, constraint type and slaves-per-cell density), sized by the budget."""
+    from dolfinx_mpc_b200 import distributed
+
+    if cfg in (2, 4):
+        layers = (n - 1) if cfg == 2 else (NZC_CFG4 if n == DEFAULT_N[4] else max(2, n // 8))
+        per_layer = 6 * (n - 1) ** 2
+        R = _divisor_at_most(layers, cores)
+        nzc = layers // R
+        full = True
+        if R * nzc * per_layer > budget_cells:  # thinner slabs, all cores
+            R, full = cores, False
+            nzc = int(max(2, min(layers // R, budget_cells / (R * per_layer))))
+        probs = [distributed.build_slab_problem(n, r, R, f_source, periodic_z=(cfg == 4), nzc=nzc) for r in range(R)]
+        what = (f"{R} ranks x {n}x{n}x{nzc + 1}-node z-slabs, each rank its own arrays; "
+                + ("together the whole single-GPU workload" if full else "a bounded sample of the workload's slabs"))
+        return probs, what, full
+    R = cores
+    if cfg == 3:
+        ns = int(max(2, min(n, round((budget_cells / (6 * R)) ** (1 / 3)))))
+        probs = [build_slip_elasticity(ns) for _ in range(R)]
+        what = f"{R} ranks x an independent {ns}^3-cube instance of the P2 slip-elasticity problem (bounded sample)"
+    else:
+        ns = int(max(2, min(n, round((budget_cells / (6 * 4.5 * R)) ** (1 / 3)))))
+        probs = [build_contact(ns) for _ in range(R)]
+        what = f"{R} ranks x an independent instance of the contact problem with {ns} / {2 * ns} cells per unit length (bounded sample)"
+    return probs, what, False
+
+
+CPU_RATE_GUESS = {2: 2.5e6, 3: 2.5e4, 4: 2.5e6, 5: 3.0e5}  # cells/s per rank, only used to size the sample
+
+
+def cpu_reference(cfg: int, n: int, steps: int, warmup: int, budget_s: float, label: str):
+    """The reference's algorithm (oracle port, oracle/mpc_oracle.c -- the reference itself cannot be built in
+    this image) on the host cores: R independent ranks, each assembling its own partition into its own local
+    matrix / vector with no communication, as `mpirun -n R` does; time of a step = slowest rank."""
+    from oracle import oracle as orc
+
+    orc.build(march="native")
+    cores = os.cpu_count() or 1
+    per_step = budget_s / max(1, steps + warmup)
+    probs, what, full = cpu_rank_problems(cfg, n, cores, CPU_RATE_GUESS[cfg] * cores * per_step)
+    R = len(probs)
+    setup = [None] * R
+
+    def prepare(r):
+        setup[r] = _oracle_rank(probs[r])
+
+    th = [threading.Thread(target=prepare, args=(r,)) for r in range(R)]
+    [t.start() for t in th]
+    [t.join() for t in th]
+    bs_ = [np.zeros(p["mpc"].function_space.num_dofs) for p in probs]
+    cells = sum(p["mesh"].num_cells_local for p in probs)
     times = np.zeros(R)
 
     def work(r):
+        P = probs[r]
+        m, pat = setup[r]
         t = time.perf_counter()
         orc.assemble_matrix(P["a"], m, bcs=P["bcs"], pattern=pat)
         orc.assemble_vector(P["L"], m, bs_[r])
-        orc.apply_lifting(bs_[r], [P["a"]], [P["bcs"]], m)
+        if P["bcs"]:
+            orc.apply_lifting(bs_[r], [P["a"]], [P["bcs"]], m)
         times[r] = time.perf_counter() - t
 
     def one_step():
@@ -176,41 +328,34 @@ def cpu_reference(n: int, steps: int, warmup: int, budget_s: float, label: str):
 
     for _ in range(warmup):
         one_step()
-    work(0)  # one rank alone (BASELINE.json configs[0] is quoted on 1 CPU rank): same slab, no neighbours on the cores
+    work(0)  # one rank alone (BASELINE.json configs[0] is quoted on 1 CPU rank): no neighbours on the cores
     global LAST_ONE_RANK
-    LAST_ONE_RANK = P["mesh"].num_cells_local / times[0]
+    LAST_ONE_RANK = probs[0]["mesh"].num_cells_local / times[0]
     dts = [one_step() for _ in range(steps)]
     total = float(sum(dts))
     value = cells * steps / total
-    sample = (f"{label}: {R} independent ranks (threads, GIL released in C), each assembling a {n}x{n}x{nz_s}-node slab "
-              f"of the workload into its own matrix / vector ({cells} cells per step in total), pattern cached, "
-              f"zero+matrix+vector+lifting timed")
-    return value, total / steps * 1e3, R, sample, cells
+    sample = (f"{label}: {what} ({cells} cells per step in total), GIL released in C, pattern cached, "
+              f"zero+matrix+vector+lifting timed, oracle built with -march=native")
+    return value, total / steps * 1e3, R, sample, cells, full
 
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    value, ms, R, sample, cells = cpu_reference(args.n, args.steps, args.warmup, args.ref_budget, "reference arm")
+    value, ms, R, sample, cells, full = cpu_reference(args.config, args.n, args.steps, args.warmup, args.ref_budget,
+                                                      "reference arm")
     line = {
         "impl": "reference", "metric": "cells assembled/sec (matrix+vector)", "value": value, "unit": "cells/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": workload_config(args.n, args.gpus),
+        "config": workload_config(args.config, args.n, args.gpus),
         "cpu_baseline": {"value": value, "unit": "cells/s", "cores": R, "kind": "port", "sample": sample,
-                         "one_rank_value": LAST_ONE_RANK},
+                         "one_rank_value": LAST_ONE_RANK, "whole_single_gpu_workload": full},
         "e2e": {"value": value, "unit": "cells/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     emit(line)
-
-
-def workload_config(n, gpus):
-    return {"workload": f"3D unit-cube Poisson P1 (Kuhn tets), {n}^3 dofs per GPU, periodic x/y MPC, Dirichlet z-faces, fp64"
-                        " (BASELINE.json configs[1])",
-            "n": n, "gpus": gpus, "l2": "inputs (>3 GB per step) far larger than the 126 MB L2; no explicit flush",
-            "partition": "z-slabs by ownership, ghost-row NCCL reduce" if gpus > 1 else "single GPU"}
 
 
 # ------------------------------------------------------------------------------------------------ GPU arm
@@ -237,26 +382,29 @@ def run_ours(args):
         dist.barrier()
     lib = _lib.load()
 
-    n = args.n
-    if world > 1:
-        from dolfinx_mpc_b200 import distributed
-
-        P = distributed.build_slab_problem(n, rank, world, f_source)
-    else:
-        P = build_problem(n)
+    cfg, n = args.config, args.n
+    P = build_config(cfg, n, rank, world)
     mesh, V, mpc, a, L, bcs, f = (P[k] for k in ("mesh", "V", "mpc", "a", "L", "bcs", "f"))
     nc = mesh.num_cells_local
     f.device_array = dev.to_dev(f.array)
-    A = distributed.create_matrix(a, mpc) if world > 1 else mpcx.create_matrix(a, mpc)
-    b = mpcx.create_vector(mpc)
     if world > 1:
+        from dolfinx_mpc_b200 import distributed
+
+        A = distributed.create_matrix(a, mpc)
+        b = mpcx.create_vector(mpc)
         distributed.attach_ghost_exchange(A, b, P)
+    else:
+        A = mpcx.create_matrix(a, mpc)
+        b = mpcx.create_vector(mpc)
 
     def step():
-        mpcx.assemble_matrix(a, mpc, bcs=bcs, A=A)
-        mpcx.assemble_vector(L, mpc, b=b)
-        mpcx.apply_lifting(b, [a], [bcs], mpc)
-        b.ghostUpdate()
+        if args.unfused:
+            mpcx.assemble_matrix(a, mpc, bcs=bcs, A=A)
+            mpcx.assemble_vector(L, mpc, b=b)
+            mpcx.apply_lifting(b, [a], [bcs], mpc)
+            b.ghostUpdate()
+        else:
+            mpcx.assemble_system(a, L, mpc, bcs=bcs, A=A, b=b)
 
     def barrier():
         if world > 1:
@@ -297,7 +445,7 @@ def run_ours(args):
         total_cells = nc
     value = total_cells * args.steps / (ms_total * 1e-3)
 
-    # roofline of the dominant kernel (bulk matrix kernel), rank 0
+    # roofline of the dominant kernel (the bulk-cell kernel bracketed by CUDA events inside libmpcx), rank 0
     peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     peak, peak_src = FALLBACK_HBM_GBS, "fallback (B200_PROFILING.md)"
     if os.path.exists(peaks_path):
@@ -307,14 +455,24 @@ def run_ours(args):
         except Exception:
             pass
     k_ms = kms.value / max(1, kn.value)
-    alg = algorithmic_bytes(P, A.nnz, with_rhs=False)
+    fused = not args.unfused and getattr(A, "last_system_fused", False)
+    alg = algorithmic_bytes(P, A.nnz, with_rhs=fused)
     achieved = alg / (k_ms * 1e-3) / 1e9
-    roofline = {"bound": "hbm", "kernel": "matrix bulk kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": achieved / peak, "peak_source": peak_src,
-                "traffic": args.traffic if args.traffic is not None else (NCU_TRAFFIC_N256 if n == 256 else None),
-                "traffic_source": "profiles/r01_o256_ncu_full_summary.csv (ncu --set full, per launch)",
+    traffic, traffic_src = args.traffic, "command line"
+    if traffic is None and os.path.exists(TRAFFIC_FILE):
+        try:
+            ent = json.load(open(TRAFFIC_FILE)).get(f"cfg{cfg}_n{n}")
+            if ent:
+                traffic, traffic_src = float(ent["dram_bytes_per_launch"]), ent["source"]
+        except Exception:
+            pass
+    roofline = {"bound": "hbm", "kernel": "fused matrix + vector bulk-cell kernel" if fused else "matrix bulk-cell kernel",
+                "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": achieved / peak, "peak_source": peak_src, "traffic": traffic,
+                "traffic_source": traffic_src if traffic is not None else None,
                 "algorithmic_bytes_per_launch": alg, "bytes_per_cell": alg / nc, "kernel_ms": k_ms,
-                "kernel_share_of_step": kms.value / ms_total}
+                "kernel_share_of_step": kms.value / ms_total,
+                "step_algorithmic_frac": algorithmic_bytes(P, A.nnz, True) / (ms_total / args.steps * 1e-3) / 1e9 / peak}
 
     # matrix-only / vector-only split of the step, timed separately after the main loop
     def timed(fn, reps=3):
@@ -332,8 +490,7 @@ def run_ours(args):
                  "assemble_vector_ms": timed(lambda: mpcx.assemble_vector(L, mpc, b=b)),
                  "apply_lifting_ms": timed(lambda: mpcx.apply_lifting(b, [a], [bcs], mpc))}
 
-    # end-to-end through the public API with host (pinned) buffers: the step's input values are copied host -> device
-    # inside the timed region, the assembled CSR values and RHS are copied back (see run_e2e)
+    # end to end through the public API with host (pinned) buffers (see run_e2e)
     e2e = run_e2e(args, P, A, b, step, world, barrier)
     # same pipeline when the assembled system is consumed on the device (Matrix.dlpack / to_torch_sparse_csr) and
     # only two norms travel back: reported beside the headline e2e, not instead of it
@@ -341,17 +498,17 @@ def run_ours(args):
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
-        v, ms, R, sample, _ = cpu_reference(n, 1, 1, args.cpu_budget, "cpu_baseline")
+        v, ms, R, sample, _, full = cpu_reference(cfg, n, 1, 1, args.cpu_budget, "cpu_baseline")
         cpu = {"value": v, "unit": "cells/s", "cores": R, "kind": "port", "sample": sample,
-               "one_rank_value": LAST_ONE_RANK}
+               "one_rank_value": LAST_ONE_RANK, "whole_single_gpu_workload": full}
 
     if rank == 0:
         line = {
             "metric": "cells assembled/sec (matrix+vector)", "value": value, "unit": "cells/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_total / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": dict(workload_config(n, world), cells_per_gpu=nc, dofs_per_gpu=V.num_dofs, nnz_per_gpu=A.nnz,
-                           slaves=len(mpc.slaves)),
+            "config": dict(workload_config(cfg, n, world), cells_per_gpu=nc, dofs_per_gpu=V.num_dofs, nnz_per_gpu=A.nnz,
+                           slaves=len(mpc.slaves), step="fused assemble_system" if fused else "assemble_matrix + assemble_vector + apply_lifting"),
             "roofline": roofline, "breakdown": breakdown, "cpu_baseline": cpu, "e2e": e2e,
             "e2e_device_consumer": e2e_dev, "gpu_launches": int(launches),
             "clocks": clk,
@@ -362,84 +519,49 @@ def run_ours(args):
 
 
 def run_e2e(args, P, A, b, step, world, barrier, download="full"):
-    """End to end through the public API with HOST buffers.  Every step uploads the step's INPUT VALUES from
-    pinned host memory (vertex coordinates, the coefficient, Dirichlet values, constraint coefficients) and
-    downloads the assembled CSR values and the RHS to pinned host memory.  The mesh topology / dofmaps /
-    constraint structure stay on the device together with the sparsity pattern and the tile plans derived from
-    them -- the state the reference keeps in its Form / FunctionSpace / cached Mat between assemblies
-    (python/src/dolfinx_mpc/assemble_matrix.py:49-51).  Steps are pipelined over three streams (upload of step
-    k+1 and download of step k overlap; value arrays double-buffered); the time is K steps start to finish."""
+    """End to end through the public API with HOST buffers (dolfinx_mpc_b200.hostio.StepIO).  Every step uploads
+    the step's INPUT VALUES from pinned host memory (vertex coordinates, the coefficient, constraint coefficients;
+    Dirichlet values travel inside apply_lifting when they can change) and downloads the assembled CSR values and the
+    RHS to pinned host memory.  The mesh topology / dofmaps / constraint structure stay on the device together with
+    the sparsity pattern and the tile plans derived from them -- the state the reference keeps in its Form /
+    FunctionSpace / cached Mat between assemblies (python/src/dolfinx_mpc/assemble_matrix.py:49-51).  Steps are
+    pipelined over three streams (upload of step k+1 and download of step k overlap; value arrays double-buffered
+    when they fit); the time is K steps start to finish."""
     import torch
 
-    from dolfinx_mpc_b200 import device as dev
+    from dolfinx_mpc_b200.hostio import StepIO
 
-    mesh, V, mpc, f = P["mesh"], P["V"], P["mpc"], P["f"]
-    mdev, cdev = dev.mesh_dev(mesh), dev.mpc_dev(mpc)
-    values = [mdev["x"], f.device_array, cdev["coeffs"]]
-    for k_, v in V._dev.items():  # Dirichlet values (markers are structure)
-        if isinstance(k_, tuple) and k_[0] == "lift" and v is not None:
-            values.append(v[1])
-    values = [t for t in values if t is not None and t.numel() > 0]
-    src = [t.cpu().pin_memory() for t in values]
-    h2d = sum(t.numel() * t.element_size() for t in src)
-    nnz, nb = A.nnz, b.data.numel()
-    val_bufs = [A._val_storage, torch.zeros_like(A._val_storage)]
-    b_bufs = [b.data, torch.zeros(nb + (nb & 1), dtype=torch.float64, device=b.data.device)[:nb]]  # even capacity (mpcx.h)
-    full = download == "full"  # "norms": the matrix stays on the device for a device-side consumer (DLPack hand-off)
-    out_val = [torch.empty(nnz if full else 1, dtype=torch.float64).pin_memory() for _ in range(2)]
-    out_b = [torch.empty(nb if full else 1, dtype=torch.float64).pin_memory() for _ in range(2)]
-    d2h = (nnz + nb) * 8 if full else 16
+    io = StepIO(P["mesh"], [P["f"]], P["mpc"], A, b, download=download)
     cur = torch.cuda.current_stream()
-    s_in, s_out = torch.cuda.Stream(), torch.cuda.Stream()
 
     def run(k_steps):
         ev_done, ev_out = [], []
         for k in range(k_steps):
-            i = k % 2
-            ev_in = torch.cuda.Event()
-            with torch.cuda.stream(s_in):
-                if k > 0:
-                    s_in.wait_event(ev_done[k - 1])  # the previous step has read its inputs
-                for s_, d_ in zip(src, values):
-                    d_.copy_(s_, non_blocking=True)
-                ev_in.record(s_in)
+            i = k % io.nbuf
+            ev_in = io.upload(after=ev_done[k - 1] if k > 0 else None)  # the previous step has read its inputs
             cur.wait_event(ev_in)
-            if k >= 2:
-                cur.wait_event(ev_out[k - 2])  # this pair of output buffers has been downloaded
-            A._val_storage, A.val = val_bufs[i], val_bufs[i][:nnz]
-            b.data = b_bufs[i]
+            if k >= io.nbuf:
+                cur.wait_event(ev_out[k - io.nbuf])  # this set of output buffers has been downloaded
+            io.bind(i)
             step()
             e = torch.cuda.Event()
             e.record(cur)
             ev_done.append(e)
-            with torch.cuda.stream(s_out):
-                s_out.wait_event(e)
-                if full:
-                    out_val[i].copy_(val_bufs[i][:nnz], non_blocking=True)
-                    out_b[i].copy_(b_bufs[i], non_blocking=True)
-                else:
-                    out_val[i].copy_(torch.linalg.vector_norm(val_bufs[i][:nnz]).reshape(1), non_blocking=True)
-                    out_b[i].copy_(torch.linalg.vector_norm(b_bufs[i]).reshape(1), non_blocking=True)
-                eo = torch.cuda.Event()
-                eo.record(s_out)
-            ev_out.append(eo)
-        cur.wait_event(ev_out[-1])
-        if k_steps > 1:
-            cur.wait_event(ev_out[-2])
+            ev_out.append(io.download(i, after=e))
+        for e in ev_out[-io.nbuf:]:
+            cur.wait_event(e)
 
     run(2)
     barrier()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    k = max(2, min(args.steps, 8))
+    k = max(2, min(args.steps, 8 if io.d2h_bytes < (4 << 30) else 3))
     ev0.record()
     run(k)
     ev1.record()
     barrier()
     ms = ev0.elapsed_time(ev1)
-    # restore the primary buffers
-    A._val_storage, A.val = val_bufs[0], val_bufs[0][:nnz]
-    b.data = b_bufs[0]
-    nc = mesh.num_cells_local
+    io.release()
+    nc = P["mesh"].num_cells_local
     if world > 1:
         import torch.distributed as dist
 
@@ -449,14 +571,13 @@ def run_e2e(args, P, A, b, step, world, barrier, download="full"):
         c = torch.tensor([nc], device="cuda", dtype=torch.int64)
         dist.all_reduce(c)
         nc = int(c.item())
-    return {"value": nc * k / (ms * 1e-3), "unit": "cells/s", "h2d_bytes_per_step": int(h2d),
-            "d2h_bytes_per_step": int(d2h), "ms_per_step": ms / k, "steps": k,
-            "download": "CSR values + RHS" if full else "Frobenius norm of the matrix and norm of the RHS (matrix consumed on the device)",
-            "note": "per step: pinned-host upload of the input VALUES (vertex coordinates, coefficient, Dirichlet values, "
-                    "constraint coefficients), assembly, download of CSR values + RHS to pinned host memory; topology "
-                    "(dofmaps, constraint structure), sparsity pattern and tile plans are cached on the device like the "
-                    "reference's Form / cached Mat; steps pipelined over 3 streams (value arrays double-buffered), "
-                    "download-bound on PCIe"}
+    return {"value": nc * k / (ms * 1e-3), "unit": "cells/s", "h2d_bytes_per_step": int(io.h2d_bytes),
+            "d2h_bytes_per_step": int(io.d2h_bytes), "ms_per_step": ms / k, "steps": k,
+            "download": io.download_desc,
+            "note": "per step: pinned-host upload of the input VALUES (vertex coordinates, coefficient, constraint "
+                    "coefficients), assembly, download to pinned host memory; topology (dofmaps, constraint "
+                    "structure), sparsity pattern and tile plans are cached on the device like the reference's Form / "
+                    "cached Mat; steps pipelined over 3 streams"}
 
 
 _REAL_STDOUT = None
@@ -481,19 +602,30 @@ def main():
     _quiet_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
-    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--n", type=int, default=256, help="nodes per side (per GPU)")
-    ap.add_argument("--cpu-budget", type=float, default=15.0, help="seconds of CPU work for cpu_baseline")
-    ap.add_argument("--ref-budget", type=float, default=60.0, help="seconds of CPU work for --impl reference")
+    ap.add_argument("--config", type=int, default=None, choices=[2, 3, 4, 5],
+                    help="BASELINE.json config (1-based); default 2 on one GPU, 4 on several")
+    ap.add_argument("--n", type=int, default=None, help="size parameter of the config (nodes per side for 2 / 4, "
+                    "cubes per side for 3, lower-box cells per unit length for 5)")
+    ap.add_argument("--cpu-budget", type=float, default=12.0, help="seconds of CPU work for cpu_baseline")
+    ap.add_argument("--ref-budget", type=float, default=150.0, help="seconds of CPU work for --impl reference")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--unfused", action="store_true", help="step = three separate calls instead of assemble_system")
     ap.add_argument("--traffic", type=float, default=None, help="dram bytes per launch of the dominant kernel "
-                    "from an ncu --set full capture (profiles/), reported as roofline.traffic")
+                    "from an ncu --set full capture, reported as roofline.traffic (default: profiles/traffic.json)")
     args = ap.parse_args()
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.config is None:
+        args.config = 2 if max(world, args.gpus) == 1 else 4
+    if args.n is None:
+        args.n = DEFAULT_N[args.config]
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3
     if args.impl == "reference":
+        if args.steps > 20:  # the CPU arm's step is seconds, not milliseconds: keep the run within minutes
+            args.steps = 20
         run_reference(args)
     else:
         run_ours(args)

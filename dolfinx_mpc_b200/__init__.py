@@ -8,10 +8,11 @@ from .assemble_matrix import (assemble_matrix, assemble_matrix_nest, create_matr
 from .assemble_vector import (apply_lifting, assemble_vector, assemble_vector_nest, create_vector,
                               create_vector_nest, set_bc)
 from .multipointconstraint import MultiPointConstraint
+from .problem import assemble_system
 
 __all__ = [
     "assemble_matrix", "create_matrix", "create_matrix_nest", "assemble_matrix_nest", "assemble_vector",
     "apply_lifting", "assemble_vector_nest", "create_vector_nest", "create_vector", "set_bc",
-    "MultiPointConstraint", "create_sparsity_pattern", "create_sparsity_pattern_device",
+    "MultiPointConstraint", "create_sparsity_pattern", "create_sparsity_pattern_device", "assemble_system",
 ]
 __version__ = "0.1.0"

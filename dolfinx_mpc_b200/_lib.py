@@ -69,7 +69,7 @@ SYMBOLS = (
     "mpcx_create_pattern_host", "mpcx_free_host", "mpcx_profile_enable", "mpcx_launch_count", "mpcx_profile_read",
     "mpcx_flag_cells", "mpcx_tile_plan_create", "mpcx_tile_plan_destroy", "mpcx_tile_plan_info",
     "mpcx_assemble_matrix_tiled_f64", "mpcx_vector_tile_plan_create", "mpcx_assemble_vector_tiled_f64",
-    "mpcx_pattern_create", "mpcx_pattern_export", "mpcx_pattern_destroy",
+    "mpcx_pattern_create", "mpcx_pattern_export", "mpcx_pattern_destroy", "mpcx_assemble_system_tiled_f64",
 )
 
 _lib = None
@@ -110,6 +110,8 @@ def load():
                                                    P(MpcS), P(CsrS), vp, vp]
     lib.mpcx_vector_tile_plan_create.argtypes = [P(MeshS), P(DofmapS), vp, i64, vp, vp, P(vp)]
     lib.mpcx_assemble_vector_tiled_f64.argtypes = [P(IntegralS), P(MeshS), P(DofmapS), P(MpcS), vp, vp, vp]
+    lib.mpcx_assemble_system_tiled_f64.argtypes = [P(IntegralS), P(IntegralS), P(MeshS), P(DofmapS), vp, P(MpcS), P(CsrS),
+                                                   vp, vp, vp, vp]
     lib.mpcx_flag_cells.argtypes = [P(DofmapS), vp, i64, vp, vp, vp]
     lib.mpcx_backsubstitution_f64.argtypes = [P(MpcS), vp, vp]
     lib.mpcx_homogenize_f64.argtypes = [P(MpcS), vp, vp]

@@ -118,7 +118,7 @@ def _bc_markers(V, bcs, n: int):
     mine = [bc for bc in bcs if bc.function_space is V or bc.function_space.dofmap is V.dofmap]
     if not mine:
         return None
-    key = ("bc_markers", n) + tuple(id(bc) for bc in mine)
+    key = ("bc_markers", n) + tuple(bc.uid for bc in mine)  # monotonic uids: an id() could be reused
     if key not in V._dev:
         m = np.zeros(n, dtype=np.int8)
         for bc in mine:
@@ -174,14 +174,29 @@ def assemble_matrix(form: Form, constraint: Union[MultiPointConstraint, Sequence
         tile = (A.tile_plan(form, it, s, bc0_d, bc1_d, (id(mpc0), id(mpc1)), keepalive=(mpc0, mpc1))
                 if A.scatter == "tile" and not facet else None)
         if tile is not None:
-            _lib.check(lib.mpcx_assemble_matrix_tiled_f64(C.byref(s), C.byref(mesh_s), C.byref(d0), C.byref(d1),
-                                                          _dev.ptr(bc0_d), _dev.ptr(bc1_d), C.byref(m0), C.byref(m1),
-                                                          C.byref(As), tile[0], st))
-            continue
+            try:
+                _lib.check(lib.mpcx_assemble_matrix_tiled_f64(C.byref(s), C.byref(mesh_s), C.byref(d0), C.byref(d1),
+                                                              _dev.ptr(bc0_d), _dev.ptr(bc1_d), C.byref(m0),
+                                                              C.byref(m1), C.byref(As), tile[0], st))
+                continue
+            except _lib.MpcxError as e:
+                # e.g. a coefficient not laid out like the trial element (several packed coefficients): the
+                # library refuses before launching anything; the generic device kernel takes the integral
+                if getattr(e, "status", None) != _lib.ERR_UNSUPPORTED:
+                    raise
         plan = None if facet else A.plan(form, it)
         _lib.check(lib.mpcx_assemble_matrix_f64(C.byref(s), C.byref(mesh_s), C.byref(d0), C.byref(d1),
                                                 _dev.ptr(bc0_d), _dev.ptr(bc1_d), C.byref(m0), C.byref(m1),
                                                 C.byref(As), None if plan is None else C.byref(plan), st))
+    _add_diagonals(A, As, form, mpc0, mpc1, bcs, diagval, st)
+    _lib.check(lib.mpcx_device_error(st))
+    A.assemble()
+    return A
+
+
+def _add_diagonals(A, As, form, mpc0, mpc1, bcs, diagval, st):
+    lib = _lib.load()
+    V0, V1 = form.function_spaces
     # slave diagonal for owned slaves when both sides share the constraint space (cpp/assemble_matrix.cpp:711-724).
     # In the reference every MultiPointConstraint owns a freshly created (extended) function space
     # (cpp/MultiPointConstraint.h:117-120), so the shared_ptr comparison holds only for one and the same object.
@@ -195,9 +210,6 @@ def assemble_matrix(form: Form, constraint: Union[MultiPointConstraint, Sequence
                 t, nd_ = _bc_owned_dofs(bc)
                 if nd_:
                     _lib.check(lib.mpcx_add_diagonal_f64(C.byref(As), _dev.ptr(t), nd_, float(diagval), st))
-    _lib.check(lib.mpcx_device_error(st))
-    A.assemble()
-    return A
 
 
 def create_matrix_nest(a: Sequence[Sequence[Optional[Form]]], constraints: Sequence[MultiPointConstraint]):

@@ -12,6 +12,7 @@ import torch
 from . import _lib
 from . import device as _dev
 from .fem import DirichletBC, Form
+from .fem import Function as fem_Function
 from .la import Vector
 from .multipointconstraint import MultiPointConstraint
 
@@ -40,10 +41,14 @@ def assemble_vector(form: Form, constraint: MultiPointConstraint, b: Optional[Ve
             raise RuntimeError(f"{it.integral_type} integrals have no device kernel yet")
         s = _dev.integral_struct(form, it, (constraint,), keep)
         plan = None if it.integral_type != "cell" else _vector_tile_plan(form, it, s, constraint, mesh_s, dm)
-        if plan is not None:
-            _lib.check(lib.mpcx_assemble_vector_tiled_f64(C.byref(s), C.byref(mesh_s), C.byref(dm), C.byref(m),
-                                                          _dev.ptr(b.data), plan[0], st))
-            continue
+        if plan is not None and b.tile_ok:
+            try:
+                _lib.check(lib.mpcx_assemble_vector_tiled_f64(C.byref(s), C.byref(mesh_s), C.byref(dm), C.byref(m),
+                                                              _dev.ptr(b.data), plan[0], st))
+                continue
+            except _lib.MpcxError as e:  # coefficient layout without a tile kernel: generic device kernel
+                if getattr(e, "status", None) != _lib.ERR_UNSUPPORTED:
+                    raise
         _lib.check(lib.mpcx_assemble_vector_f64(C.byref(s), C.byref(mesh_s), C.byref(dm), C.byref(m),
                                                 _dev.ptr(b.data), st))
     return b
@@ -74,8 +79,8 @@ def _vector_tile_plan(form: Form, it, s_integral, constraint, mesh_s, dm):
     p1 = V.nd == tab.tdim + 1 and tab.ng == tab.tdim + 1 and V.bs == 1
     if not p1 or int(it.kernel) != 3:
         return None
-    if s_integral.coeff_nodal and (s_integral.coeff_nd != V.nd or s_integral.coeff_bs != 1):
-        return None
+    if len(it.coefficients) != 1 or s_integral.coeff_nd != V.nd or s_integral.coeff_bs != 1:
+        return None  # the C side's w_ok condition: the coefficient must be laid out like the test element
     key = ("vector_tile_plan", id(V), id(constraint))
     if key not in it._dev:
         lib = _lib.load()
@@ -124,18 +129,34 @@ def apply_lifting(b: Vector, form: Sequence[Form], bcs: Sequence[Sequence[Dirich
         n1 = V1.num_dofs
         if not bcs[j]:
             continue
-        key = ("lift", n1) + tuple((id(bc), bc.version) for bc in bcs[j])
-        if key not in V1._dev:  # bc_markers1 / bc_values1 of cpp/lifting.h:166-180, kept on the device
+        # bc_markers1 / bc_values1 of cpp/lifting.h:166-180.  Markers, the flagged cell lists and the bc dof indices
+        # are structure: cached per tuple of bcs (keyed by their monotonic uid, never by id()).  The VALUES are
+        # re-read on every call when they can change in place (Function- or array-valued bcs), or when ``value``
+        # was reassigned: only the bc-dof values travel (a persistent device buffer is updated in place).
+        mkey = ("lift", n1) + tuple(bc.uid for bc in bcs[j])
+        if mkey not in V1._dev:
             markers = np.zeros(n1, dtype=np.int8)
-            values = np.zeros(n1, dtype=np.float64)
             for bc in bcs[j]:
                 bc.mark_dofs(markers)
-                bc.set(values)
-            V1._dev[key] = (_dev.to_dev(markers), _dev.to_dev(values)) if markers.any() else None
-        if V1._dev[key] is None:
+            if markers.any():
+                V1._dev[mkey] = {"markers": _dev.to_dev(markers),
+                                 "values": torch.zeros(n1, dtype=torch.float64, device=_dev.device()),
+                                 "dofs": [_dev.to_dev(bc.dofs.astype(np.int64)) for bc in bcs[j]],
+                                 "versions": None}
+            else:
+                V1._dev[mkey] = None
+        entry = V1._dev[mkey]
+        if entry is None:
             continue
-        mk, vl = V1._dev[key]
-        mkey = ("lift_markers",) + tuple(id(bc) for bc in bcs[j])
+        versions = tuple(bc.version for bc in bcs[j])
+        if entry["versions"] != versions or any(bc.value_is_mutable for bc in bcs[j]):
+            for bc, dofs_d in zip(bcs[j], entry["dofs"]):  # in order: a later bc overrides an earlier one
+                if np.ndim(bc.value) == 0 and not isinstance(bc.value, fem_Function):
+                    entry["values"].index_fill_(0, dofs_d, float(bc.value))
+                else:
+                    entry["values"].index_copy_(0, dofs_d, _dev.to_dev(bc.values_at_dofs()))
+            entry["versions"] = versions
+        mk, vl = entry["markers"], entry["values"]
         x0_d = None
         if len(x0):
             x0_d = x0[j].data if isinstance(x0[j], Vector) else _dev.to_dev(np.asarray(x0[j], dtype=np.float64))
@@ -149,12 +170,13 @@ def apply_lifting(b: Vector, form: Sequence[Form], bcs: Sequence[Sequence[Dirich
                 raise RuntimeError(f"{it.integral_type} integrals have no device kernel yet")
             s = _dev.integral_struct(a, it, (constraint,), keep)
             # cells of this integral with a Dirichlet column: found once on the device, then reused
-            if mkey not in it._dev:
+            ckey = ("lift_cells",) + mkey[1:]
+            if ckey not in it._dev:
                 ncells = int(s.num_cells)
                 flags = torch.zeros(ncells, dtype=torch.int8, device=_dev.device())
                 _lib.check(lib.mpcx_flag_cells(C.byref(d1), s.cells, ncells, _dev.ptr(mk), _dev.ptr(flags), st))
-                it._dev[mkey] = torch.nonzero(flags).to(torch.int32).reshape(-1)
-            lst = it._dev[mkey]
+                it._dev[ckey] = torch.nonzero(flags).to(torch.int32).reshape(-1)
+            lst = it._dev[ckey]
             if lst.numel() == 0:
                 continue
             _lib.check(lib.mpcx_apply_lifting_f64(C.byref(s), C.byref(mesh_s), C.byref(d0), C.byref(d1),

@@ -1051,6 +1051,7 @@ __global__ void k_flag_cells(const int* __restrict__ dm, int nd, int bs, const i
 }  // namespace
 
 #include "mpcx_tile.cuh"
+#include "mpcx_tile_fused.cuh"
 #include "mpcx_pattern_gpu.cuh"
 
 namespace
@@ -1592,6 +1593,71 @@ int mpcx_assemble_vector_tiled_f64(const mpcx_integral* integral, const mpcx_mes
     else k_vector_p1_source<2><<<nbs, 256, 0, s>>>(in, md, dofmap->map, m.c2s_off, m, b, in.slave_cells, in.nslave_cells);
   }
   return cuda_check(cudaGetLastError(), "assemble_vector_tiled launch");
+}
+
+int mpcx_assemble_system_tiled_f64(const mpcx_integral* a_integral, const mpcx_integral* L_integral, const mpcx_mesh* mesh,
+                                   const mpcx_dofmap* dofmap, const int8_t* bc, const mpcx_mpc* mpc, const mpcx_csr* A,
+                                   double* b, const mpcx_tile_plan* matrix_plan, const mpcx_tile_plan* vector_plan,
+                                   void* stream)
+{
+  int rc = check_integral(a_integral, true);
+  if (rc) return rc;
+  rc = check_integral(L_integral, false);
+  if (rc) return rc;
+  if (!mesh || !dofmap || !mpc || !A || !b || !matrix_plan || !vector_plan) return fail(MPCX_ERR_ARG, "null argument");
+  const TilePlan* P = reinterpret_cast<const TilePlan*>(matrix_plan);
+  const TilePlan* Q = reinterpret_cast<const TilePlan*>(vector_plan);
+  const mpcx_tables* t = a_integral->tables;
+  const mpcx_tables* tl = L_integral->tables;
+  IntD ina = make_int(a_integral), inL = make_int(L_integral);
+  const int nd = t->nd, bs = t->bs, kid = a_integral->kernel;
+  const bool p1_simplex = nd == t->tdim + 1 && t->ng == t->tdim + 1;
+  const bool wa_ok = kid != MPCX_KERNEL_LAPLACE_VARCOEF || (ina.coeffs ? ina.cstride == nd : (ina.wnd == nd && ina.wbs == 1));
+  const bool wl_ok = inL.coeffs ? inL.cstride == nd : (inL.wnd == nd && inL.wbs == 1);
+  if (a_integral->local_facets || L_integral->local_facets) return fail(MPCX_ERR_UNSUPPORTED, "the tile kernels cover cell integrals");
+  if (!((kid == MPCX_KERNEL_LAPLACE || kid == MPCX_KERNEL_MASS || kid == MPCX_KERNEL_LAPLACE_VARCOEF) && bs == 1 && p1_simplex && wa_ok)
+      || L_integral->kernel != MPCX_KERNEL_SOURCE || !wl_ok || tl->nd != nd || tl->bs != 1 || tl->tdim != t->tdim || tl->ng != t->ng)
+    return fail(MPCX_ERR_UNSUPPORTED, "the fused tile kernel covers scalar P1 simplex Laplace / mass / variable-coefficient Laplace with the P1 source term");
+  if (dofmap->nd != nd || dofmap->bs != 1 || P->vec || !Q->vec || P->ne != nd * nd || Q->ne != nd || P->ng != t->ng
+      || P->nrows != A->num_rows || Q->nrows != dofmap->num_dofs)
+    return fail(MPCX_ERR_ARG, "tile plans were built for a different element, space or matrix");
+  if (P->nt != Q->nt || P->n_bulk != Q->n_bulk || P->C != Q->C)
+    return fail(MPCX_ERR_ARG, "matrix and vector tile plans do not share one tiling (same cells and skip flags needed)");
+  if (a_integral->cells != L_integral->cells || a_integral->num_cells != L_integral->num_cells
+      || a_integral->num_slave_cells != L_integral->num_slave_cells)
+    return fail(MPCX_ERR_ARG, "the fused path needs both integrals over the same cells");
+  if (a_integral->slave_cells == nullptr && mpc->num_slaves > 0) return fail(MPCX_ERR_ARG, "the tile path needs the list of slave cells");
+  if (((uintptr_t)A->val & 15) != 0) return fail(MPCX_ERR_ARG, "the tile path needs a 16-byte aligned value array");
+  cudaStream_t s = (cudaStream_t)stream;
+  const MeshD md{mesh->x, mesh->x_dofmap, mesh->ng, mesh->x_stride};
+  const CsrD Ad{(const long long*)A->row_ptr, A->col, A->val};
+  const MpcD m = make_mpc(mpc);
+  if (P->nt > 0)
+  {
+    const TilePlanD Pd = tile_plan_view(P), Qd = tile_plan_view(Q);
+    const size_t smem = fused_smem_bytes(Pd, Qd, t->tdim + 1, P->ns, P->sym != 0);
+    if (smem > 227 * 1024) return fail(MPCX_ERR_UNSUPPORTED, "fused tile kernel: a tile needs more shared memory than an SM has");
+    const int w_by_row = (!inL.coeffs && inL.wnodal && inL.wmap == dofmap->map) ? 1 : 0;
+    auto kern = t->tdim == 3 ? (P->sym ? k_ptile_system_p1<3, true> : k_ptile_system_p1<3, false>)
+                             : (P->sym ? k_ptile_system_p1<2, true> : k_ptile_system_p1<2, false>);
+    int grid = 0;
+    rc = persistent_grid((const void*)kern, smem, P->nt, &grid);
+    if (rc) return rc;
+    KernelTimer kt(s);  // dominant kernel of the call
+    MPCX_COUNT_LAUNCH();
+    kern<<<grid, MPCX_TILE_THREADS, smem, s>>>(Pd, Qd, P->nt, ina, inL, md, w_by_row, Ad, b);
+  }
+  if (ina.nslave_cells > 0)
+  {
+    const unsigned nbs = (unsigned)((ina.nslave_cells + 127) / 128), nbv = (unsigned)((ina.nslave_cells + 255) / 256);
+    MPCX_COUNT_LAUNCH();
+    if (t->tdim == 3) k_matrix_p1_mpc<3><<<nbs, 128, 0, s>>>(ina, md, dofmap->map, dofmap->map, bc, bc, m, m, Ad);
+    else k_matrix_p1_mpc<2><<<nbs, 128, 0, s>>>(ina, md, dofmap->map, dofmap->map, bc, bc, m, m, Ad);
+    MPCX_COUNT_LAUNCH();
+    if (t->tdim == 3) k_vector_p1_source<3><<<nbv, 256, 0, s>>>(inL, md, dofmap->map, m.c2s_off, m, b, inL.slave_cells, inL.nslave_cells);
+    else k_vector_p1_source<2><<<nbv, 256, 0, s>>>(inL, md, dofmap->map, m.c2s_off, m, b, inL.slave_cells, inL.nslave_cells);
+  }
+  return cuda_check(cudaGetLastError(), "assemble_system_tiled launch");
 }
 
 int mpcx_pattern_create(const mpcx_dofmap* dofmap0, const mpcx_dofmap* dofmap1, int64_t num_cells,

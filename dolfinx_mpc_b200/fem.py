@@ -169,11 +169,16 @@ class DirichletBC:
     """Dirichlet condition on unrolled local dofs (``mark_dofs`` / ``set`` of dolfinx::fem::DirichletBC,
     as used in ``cpp/assemble_matrix.cpp:691-705`` and ``cpp/lifting.h:176-180``)."""
 
+    _next_uid = 0
+
     def __init__(self, V: FunctionSpace, dofs: np.ndarray, value=0.0):
         self.function_space = V
         self.dofs = np.ascontiguousarray(dofs, dtype=np.int32)
         self._value = value
-        self.version = 0  # bumped on every change of the value: keys the device-side marker/value caches
+        self.version = 0  # bumped when ``value`` is reassigned (a Function / array value can also change in place)
+        # monotonic identity: keys device-side caches (id() of a collected object can be handed out again)
+        self.uid = DirichletBC._next_uid
+        DirichletBC._next_uid += 1
         self._dev = {}
 
     @property
@@ -185,18 +190,28 @@ class DirichletBC:
         self._value = v
         self.version += 1
 
+    @property
+    def value_is_mutable(self) -> bool:
+        """True when the value can change without ``value`` being reassigned (a Function or an array updated in
+        place -- the usual DOLFINx pattern for time-dependent conditions); such values are re-read on every
+        ``apply_lifting`` / ``set_bc`` call, as the reference does (``cpp/lifting.h:166-180``)."""
+        return isinstance(self._value, Function) or np.ndim(self._value) != 0
+
     def mark_dofs(self, markers: np.ndarray):
         markers[self.dofs] = 1
 
-    def set(self, values: np.ndarray):
+    def values_at_dofs(self) -> np.ndarray:
+        """The prescribed values at ``self.dofs`` (what ``set`` writes)."""
         if isinstance(self.value, Function):
-            values[self.dofs] = self.value.array[self.dofs]
-        elif np.ndim(self.value) == 0:
-            values[self.dofs] = float(self.value)
-        else:
-            v = np.asarray(self.value, dtype=np.float64)
-            bs = self.function_space.bs
-            values[self.dofs] = v[self.dofs % bs] if v.shape == (bs,) else v[self.dofs]
+            return self.value.array[self.dofs]
+        if np.ndim(self.value) == 0:
+            return np.full(len(self.dofs), float(self.value))
+        v = np.asarray(self.value, dtype=np.float64)
+        bs = self.function_space.bs
+        return v[self.dofs % bs] if v.shape == (bs,) else v[self.dofs]
+
+    def set(self, values: np.ndarray):
+        values[self.dofs] = self.values_at_dofs()
 
 
 def locate_dofs_geometrical(V: FunctionSpace, marker) -> np.ndarray:

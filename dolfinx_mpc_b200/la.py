@@ -70,6 +70,20 @@ class Matrix:
     def zeroEntries(self):
         self.val.zero_()
 
+    def values_storage(self) -> torch.Tensor:
+        """The device buffer behind ``val`` (capacity rounded up to an even number of entries)."""
+        return self._val_storage
+
+    def bind_values(self, storage: torch.Tensor):
+        """Assemble into another value buffer from now on (double-buffered outputs, a solver's own array ...):
+        a 16-byte aligned contiguous float64 device tensor with room for ``nnz`` rounded up to an even count."""
+        need = self.nnz + (self.nnz & 1)
+        if (storage.dtype != torch.float64 or storage.dim() != 1 or not storage.is_contiguous() or storage.numel() < need
+                or storage.data_ptr() % 16):
+            raise ValueError(f"value storage must be a 16-byte aligned contiguous float64 tensor of >= {need} entries")
+        self._val_storage = storage
+        self.val = storage[: self.nnz]
+
     def plan(self, form, integral) -> Optional[_lib.PlanS]:
         """Scatter plan for one integral of ``form`` into this pattern (built on first use, then cached)."""
         width = 1 if self.max_block_row <= 256 else (2 if self.max_block_row <= 65536 else 0)
@@ -189,11 +203,27 @@ class Matrix:
 
 class Vector:
     def __init__(self, n: int, data: Optional[torch.Tensor] = None):
-        if data is None:  # capacity rounded up to an even count (tile kernels add whole 16-byte runs)
+        """``data``: an external device tensor of length ``n`` to assemble into.  The tile kernels need a 16-byte
+        aligned buffer; an external tensor that is not (an odd-offset view) is still valid -- ``tile_ok`` is then
+        False and ``assemble_vector`` uses the atomic-scatter kernel."""
+        if data is None:  # capacity rounded up to an even count (include/mpcx.h)
             self._storage = torch.zeros(n + (n & 1), dtype=torch.float64, device=_dev.device())
             data = self._storage[:n]
+        else:
+            if data.dtype != torch.float64 or data.dim() != 1 or data.numel() != n or not data.is_contiguous():
+                raise ValueError("Vector data must be a contiguous float64 tensor of length n")
         self.data = data
         self.ghost_exchange = None
+
+    def bind(self, data: torch.Tensor):
+        """Assemble into ``data`` from now on (same length, float64, contiguous)."""
+        if data.dtype != torch.float64 or data.dim() != 1 or data.numel() != self.data.numel() or not data.is_contiguous():
+            raise ValueError("Vector.bind needs a contiguous float64 tensor of the same length")
+        self.data = data
+
+    @property
+    def tile_ok(self) -> bool:
+        return self.data.data_ptr() % 16 == 0
 
     def set(self, v: float):
         self.data.fill_(v)

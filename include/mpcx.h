@@ -213,6 +213,19 @@ int mpcx_vector_tile_plan_create(const mpcx_mesh* mesh, const mpcx_dofmap* dofma
 int mpcx_assemble_vector_tiled_f64(const mpcx_integral* integral, const mpcx_mesh* mesh, const mpcx_dofmap* dofmap,
                                    const mpcx_mpc* mpc, double* b, const mpcx_tile_plan* plan, void* stream);
 
+/* Matrix AND load vector of the same cells in ONE pass over the bulk cells (the assembly block of
+ * LinearProblem.solve, python/src/dolfinx_mpc/problem.py:539-566, calls assemble_matrix and assemble_vector back to
+ * back; each of them gathers the cell geometry again, cpp/assemble_matrix.cpp:488-506 and
+ * cpp/assemble_vector.cpp:163-185).  Same contract as mpcx_assemble_matrix_tiled_f64 followed by
+ * mpcx_assemble_vector_tiled_f64 on one space (test == trial == the space of L, one bc marker array, one
+ * constraint): A += a_integral, b += L_integral; the caller zeroes A and b.  Both tile plans must have been created
+ * for the same cells and skip flags (they then share one tiling).  Cells holding slaves go through the elimination
+ * kernels of both routines. */
+int mpcx_assemble_system_tiled_f64(const mpcx_integral* a_integral, const mpcx_integral* L_integral, const mpcx_mesh* mesh,
+                                   const mpcx_dofmap* dofmap, const int8_t* bc, const mpcx_mpc* mpc, const mpcx_csr* A,
+                                   double* b, const mpcx_tile_plan* matrix_plan, const mpcx_tile_plan* vector_plan,
+                                   void* stream);
+
 /* A[d, d] += diagval for the listed unrolled dofs.  Slave diagonal
  * (cpp/assemble_matrix.cpp:711-724) and Dirichlet diagonal
  * (python/src/dolfinx_mpc/assemble_matrix.py:59-62). */

@@ -255,79 +255,66 @@ def test_tile_plan_properties(oracle):
     assert_vec_close(b.array, b_o)
 
 
-def test_full_size_properties():
-    """BASELINE.json configs[1] at full size (256^3 P1 Poisson, periodic x/y, Dirichlet z; 99.5 M cells, 253 M nnz),
-    where the oracle is too slow: size-independent properties, all evaluated on the device.
-    * tile path and atomic-scatter path (two independent kernels and plans) agree entry-wise within 1e-10;
-    * constants are in the null space of the constrained Laplacian on rows that are neither slave nor Dirichlet,
-      once the Dirichlet columns are put back (K^T A K of a consistent stiffness matrix);
-    * slave rows and Dirichlet rows hold exactly the diagonal value; the matrix is symmetric (checked through
-      x^T A y == y^T A x for two random vectors);
-    * re-assembly into the same matrix reproduces the values within round-off of the atomics' ordering;
-    * sum(b) before lifting equals the integral of f computed independently, K^T preserving sums for periodic
-      constraints with coefficient 1."""
+def test_full_size_entry_for_entry(oracle):
+    """BASELINE.json configs[1] at full size -- the problem bench.py times (256^3 P1 Poisson, periodic x/y,
+    Dirichlet z; 99.5 M cells, 253 M nnz) -- assembled by the benchmarked call (the fused assemble_system) and
+    compared ENTRY FOR ENTRY with the oracle: the same C routines as everywhere else, run slab-wise on all host
+    threads (oracle.assemble_system_slabs; seconds at this size).  Bar: pattern bit-exact against the threaded
+    host builder (itself bit-exact against the oracle on every fixture), values and right-hand side within 1e-10
+    relative.  Also the separate assemble_matrix / assemble_vector / apply_lifting calls against the fused call, and
+    size-independent properties (slave / Dirichlet rows hold exactly the diagonal; symmetry)."""
     import os
 
     import torch
 
     import bench
     import dolfinx_mpc_b200 as mpcx
-    from dolfinx_mpc_b200 import device as dev
 
     n = int(os.environ.get("MPCX_TEST_FULL_N", "256"))
     P = bench.build_problem(n)
-    mesh, V, mpc, a, L, bcs, f = (P[k] for k in ("mesh", "V", "mpc", "a", "L", "bcs", "f"))
-    A = mpcx.create_matrix(a, mpc)
-    assert A.scatter == "tile"
-    mpcx.assemble_matrix(a, mpc, bcs=bcs, A=A)
-    assert all(info["symmetric"] == 1 for _, info in A._tile_plans.values())
-    v_tile = A.val.clone()
-    A2 = mpcx.create_matrix(a, mpc)
-    A2.scatter = "atomic"
-    mpcx.assemble_matrix(a, mpc, bcs=bcs, A=A2)
+    mesh, V, mpc, a, L, bcs = (P[k] for k in ("mesh", "V", "mpc", "a", "L", "bcs"))
+    A = mpcx.create_matrix(a, mpc)  # pattern built on the device
+    b = mpcx.create_vector(mpc)
+    mpcx.assemble_system(a, L, mpc, bcs=bcs, A=A, b=b)
+    assert A.last_system_fused and all(info["symmetric"] == 1 for _, info in A._tile_plans.values())
+    rp, col, val = A.getValuesCSR()
+    rp_h, col_h = mpcx.create_sparsity_pattern(a, mpc)
+    assert np.array_equal(rp, rp_h) and np.array_equal(col, col_h), "device pattern differs from the host builder"
+    del rp_h, col_h
+    m = oracle.mpc_from_arrays(V, P["data"])
+    val_o, b_o = oracle.assemble_system_slabs(a, L, m, bcs, (rp, col), 6 * (n - 1) ** 2, nthreads=os.cpu_count() or 1)
+    assert_csr_close(rp, col, val, rp, col, val_o)
+    assert_vec_close(b.array, b_o)
+    # slave / Dirichlet rows: exactly the diagonal
     N = V.num_dofs
-    rows = torch.repeat_interleave(torch.arange(N, device=A.val.device), A.row_ptr[1:] - A.row_ptr[:-1])
-    cols = A.col.long()
-    rownorm = torch.zeros(N, dtype=torch.float64, device=A.val.device).scatter_reduce_(0, rows, v_tile.abs(), "amax")
-    assert bool(((v_tile - A2.val).abs() <= RTOL * torch.maximum(A2.val.abs(), rownorm[rows])).all())
-    del A2
+    rows = np.repeat(np.arange(N, dtype=np.int32), np.diff(rp))
+    special = np.zeros(N, dtype=bool)
+    special[mpc.slaves] = True
+    special[bcs[0].dofs] = True
+    sp_rows = special[rows]
+    diag = rows == col
+    assert np.all(val[sp_rows & ~diag] == 0.0) and np.all(val[sp_rows & diag] == 1.0)
+    del rows, sp_rows, diag, val_o
+    # the three separate calls give the same system (atomics / reductions may reorder sums)
+    v_fused, b_fused = A.val.clone(), b.data.clone()
+    mpcx.assemble_matrix(a, mpc, bcs=bcs, A=A)
+    mpcx.assemble_vector(L, mpc, b=b)
+    mpcx.apply_lifting(b, [a], [bcs], mpc)
+    scale = float(v_fused.abs().max())
+    assert float((A.val - v_fused).abs().max()) <= 1e-12 * scale
+    assert float((b.data - b_fused).abs().max()) <= 1e-12 * float(b_fused.abs().max())
+    # symmetry, on the device
+    rows_d = torch.repeat_interleave(torch.arange(N, device=A.val.device), A.row_ptr[1:] - A.row_ptr[:-1])
+    cols_d = A.col.long()
 
     def spmv(x):
-        return torch.zeros(N, dtype=torch.float64, device=x.device).index_add_(0, rows, v_tile * x[cols])
+        return torch.zeros(N, dtype=torch.float64, device=x.device).index_add_(0, rows_d, v_fused * x[cols_d])
 
-    is_slave = dev.to_dev(mpc.is_slave).bool()
-    is_bc = torch.zeros(N, dtype=torch.bool, device=A.val.device)
-    is_bc[dev.to_dev(bcs[0].dofs).long()] = True
-    free = ~(is_slave | is_bc)
-    # rows of free dofs: A restricted to non-bc columns times ones == -(columns zeroed by the bc), i.e. the full
-    # constrained Laplacian annihilates constants; equivalently the lifting vector with g = 1 equals -A_free @ 1.
-    ones = free.double()
-    r = spmv(ones)
-    lift = mpcx.create_vector(mpc)
-    bc_one = [type(bcs[0])(V, bcs[0].dofs, 1.0)]
-    mpcx.apply_lifting(lift, [a], [bc_one], mpc)
-    scale = float(v_tile.abs().max())
-    assert float((r - lift.data)[free].abs().max()) <= 1e-10 * scale
-    # slave / Dirichlet rows: diagonal only
-    diag = rows == cols
-    special = (is_slave | is_bc)[rows]
-    assert bool((v_tile[special & ~diag] == 0).all()) and bool((v_tile[special & diag] == 1.0).all())
-    # symmetry
     g = torch.Generator(device=A.val.device).manual_seed(3)
     x = torch.rand(N, dtype=torch.float64, device=A.val.device, generator=g)
     y = torch.rand(N, dtype=torch.float64, device=A.val.device, generator=g)
     xay, yax = float(x @ spmv(y)), float(y @ spmv(x))
     assert abs(xay - yax) <= 1e-10 * abs(xay)
-    # re-assembly
-    mpcx.assemble_matrix(a, mpc, bcs=bcs, A=A)
-    assert bool(((A.val - v_tile).abs() <= 1e-12 * rownorm[rows]).all())
-    # load vector: K^T with unit coefficients preserves the sum; compare with the P1 quadrature of f, sum_K |K|/4 sum_v f_v
-    b = mpcx.assemble_vector(L, mpc)
-    h = 1.0 / (n - 1)
-    fx = torch.from_numpy(f.array).to(A.val.device)
-    cells = dev.to_dev(mesh.x_dofmap).long()
-    expected = float((fx[cells].sum(dim=1) * (h ** 3 / 6.0 / 4.0)).sum())
-    assert abs(float(b.data.sum()) - expected) <= 1e-10 * abs(expected)
 
 
 @pytest.mark.parametrize("name", list(problems.ALL_CASES))
@@ -427,3 +414,108 @@ def test_mpc_assembly_reference_style(oracle, get_assemblers, master_point):
     data = gen.general_constraint(V, s_m_c)
     K = oracle.transformation_matrix(n, data[0], data[1], data[2], data[4])
     oracle.compare_mpc_lhs(A_org, A_mpc.to_scipy(), K, data[0])
+
+
+@pytest.mark.parametrize("name", [k for k in problems.ALL_CASES])
+def test_assemble_system_matches_oracle(oracle, name):
+    """assemble_system (the assembly block of LinearProblem.solve, python/src/dolfinx_mpc/problem.py:539-572) against the
+    oracle's assemble_matrix + assemble_vector + apply_lifting: the fused matrix + vector tile kernel where the
+    forms allow it (one scalar P1 cell integral each), the three separate routines otherwise."""
+    import dolfinx_mpc_b200 as mpcx
+
+    c = problems.ALL_CASES[name]()
+    if c.L is None:
+        pytest.skip("no linear form")
+    mpc = _mpc(c)
+    m = oracle.mpc_from_arrays(c.V, c.data)
+    a_lift = c.a_lift if c.a_lift is not None else c.a
+    bcs = c.bcs if c.a_lift is not None else []
+    A, b = mpcx.assemble_system(c.a, c.L, mpc, bcs=bcs)
+    fusable = (len(c.a.integrals) == 1 and len(c.L.integrals) == 1 and c.V.bs == 1 and c.V.degree == 1
+               and c.V.mesh.cell_type in ("triangle", "tetrahedron") and int(c.a.integrals[0].kernel) in (0, 1, 4)
+               and c.a.integrals[0].cells is None and c.L.integrals[0].cells is None)
+    assert A.last_system_fused == fusable, name
+    assert_csr_close(*A.getValuesCSR(), *oracle.assemble_matrix(c.a, m, bcs=bcs))
+    b_o = oracle.assemble_vector(c.L, m)
+    if bcs:
+        oracle.apply_lifting(b_o, [a_lift], [bcs], m)
+    assert_vec_close(b.array, b_o)
+    # again into the same objects (cached plans), with x0 and scale
+    x0 = np.random.default_rng(7).random(c.V.num_dofs)
+    mpcx.assemble_system(c.a, c.L, mpc, bcs=bcs, A=A, b=b, x0=[x0], scale=0.6)
+    assert_csr_close(*A.getValuesCSR(), *oracle.assemble_matrix(c.a, m, bcs=bcs))
+    b_o = oracle.assemble_vector(c.L, m)
+    if bcs:
+        oracle.apply_lifting(b_o, [a_lift], [bcs], m, x0=[x0], scale=0.6)
+    assert_vec_close(b.array, b_o)
+
+
+def test_fused_system_general_plan_and_scrambled_mesh(oracle):
+    """The fused kernel on a mesh with scrambled node / cell numbering, once with the symmetric matrix plan and once
+    with the general one (MPCX_TILE_SYM=0), variable-coefficient Laplace + source sharing one coefficient."""
+    import os
+
+    import dolfinx_mpc_b200 as mpcx
+    from dolfinx_mpc_b200 import fem, generators as gen
+
+    mesh0 = gen.create_unit_cube(11, 9, 10)
+    rng = np.random.default_rng(12)
+    perm = rng.permutation(mesh0.x.shape[0]).astype(np.int32)
+    x = np.empty_like(mesh0.x)
+    x[perm] = mesh0.x
+    mesh = fem.Mesh(x, perm[mesh0.x_dofmap][rng.permutation(mesh0.num_cells)], "tetrahedron")
+    V = gen.functionspace(mesh, 1)
+    bc_dofs = fem.locate_dofs_geometrical(V, lambda x: np.isclose(x[2], 0))
+    bcs = [fem.DirichletBC(V, bc_dofs, 0.3)]
+    data = gen.periodic_constraint(V, axes=(0,), exclude_dofs=bc_dofs)
+    mpc = mpcx.MultiPointConstraint(V)
+    mpc.add_constraint(V, *data)
+    mpc.finalize()
+    w = fem.Function(V)
+    w.interpolate(lambda x: 1.0 + x[0] * x[1])
+    a, L = fem.laplace_varcoef(V, w, 2.0), fem.source(V, w, 0.7)
+    m = oracle.mpc_from_arrays(V, data)
+    ref = oracle.assemble_matrix(a, m, bcs=bcs)
+    b_o = oracle.assemble_vector(L, m)
+    oracle.apply_lifting(b_o, [a], [bcs], m)
+    for sym in ("1", "0"):
+        os.environ["MPCX_TILE_SYM"] = sym
+        try:
+            A, b = mpcx.assemble_system(a, L, mpc, bcs=bcs)
+        finally:
+            del os.environ["MPCX_TILE_SYM"]
+        assert A.last_system_fused and all(info["symmetric"] == int(sym) for _, info in A._tile_plans.values())
+        assert_csr_close(*A.getValuesCSR(), *ref)
+        assert_vec_close(b.array, b_o)
+
+
+def test_lifting_rereads_bc_values_changed_in_place(oracle):
+    """A Function-valued Dirichlet condition updated IN PLACE between two apply_lifting calls (the usual DOLFINx
+    pattern for time-dependent conditions): the second call must see the new values, as the reference re-reads
+    them on every call (cpp/lifting.h:166-180)."""
+    import dolfinx_mpc_b200 as mpcx
+    from dolfinx_mpc_b200 import fem
+
+    c = problems.case_periodic_3d(4, 1, (0, 1), True)
+    mpc = _mpc(c)
+    m = oracle.mpc_from_arrays(c.V, c.data)
+    g = fem.Function(c.V)
+    g.interpolate(lambda x: 1.0 + x[0] + 2.0 * x[1])
+    bcs = [fem.DirichletBC(c.V, c.bcs[0].dofs, g)]
+    for k in range(3):
+        if k == 1:
+            g.interpolate(lambda x: -3.0 * x[0] + x[1] ** 2)  # Function.interpolate writes g.array in place
+        if k == 2:
+            g.array[:] = 0.5 * g.array + 0.25
+        b = mpcx.assemble_vector(c.L, mpc)
+        mpcx.apply_lifting(b, [c.a_lift], [bcs], mpc)
+        b_o = oracle.assemble_vector(c.L, m)
+        oracle.apply_lifting(b_o, [c.a_lift], [bcs], m)
+        assert_vec_close(b.array, b_o)
+    # reassigning .value (scalar) is seen as well
+    bcs[0].value = 0.125
+    b = mpcx.assemble_vector(c.L, mpc)
+    mpcx.apply_lifting(b, [c.a_lift], [bcs], mpc)
+    b_o = oracle.assemble_vector(c.L, m)
+    oracle.apply_lifting(b_o, [c.a_lift], [bcs], m)
+    assert_vec_close(b.array, b_o)
