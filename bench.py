@@ -502,6 +502,9 @@ def run_ours(args):
         cpu = {"value": v, "unit": "cells/s", "cores": R, "kind": "port", "sample": sample,
                "one_rank_value": LAST_ONE_RANK, "whole_single_gpu_workload": full}
 
+    plans = [info for ent in A._tile_plans.values() if ent is not None for info in [ent[1]]]
+    for it_ in L.integrals:
+        plans += [v[2] for k_, v in it_._dev.items() if isinstance(k_, tuple) and k_[0] == "vector_tile_plan" and v is not None]
     if rank == 0:
         line = {
             "metric": "cells assembled/sec (matrix+vector)", "value": value, "unit": "cells/s", "n_gpus": world,
@@ -511,7 +514,7 @@ def run_ours(args):
                            slaves=len(mpc.slaves), step="fused assemble_system" if fused else "assemble_matrix + assemble_vector + apply_lifting"),
             "roofline": roofline, "breakdown": breakdown, "cpu_baseline": cpu, "e2e": e2e,
             "e2e_device_consumer": e2e_dev, "gpu_launches": int(launches),
-            "clocks": clk,
+            "clocks": clk, "tile_plans": plans, "lib": os.path.basename(_lib.LIB_PATH),
         }
         emit(line)
     if world > 1:

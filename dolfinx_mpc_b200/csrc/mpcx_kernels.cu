@@ -680,6 +680,80 @@ k_vector_p1_source(IntD in, MeshD mesh, const int* __restrict__ dm, const int* _
   }
 }
 
+// Source term on an AFFINE simplex with the coefficient in the test space (any Lagrange degree, any block size):
+//   b_e[i, a] = c0 |detJ| sum_j M[i][j] f[j, a],   M[i][j] = sum_q w_q phi_i(q) phi_j(q)  (reference mass matrix),
+// which is what the tabulated kernel evaluates point by point (cpp/assemble_vector.cpp:163-185 with the generated
+// kernel) because |detJ| does not depend on the quadrature point.  LPC lanes per cell (16 when the element vector has at
+// most 16 entries, else 32), lane = entry; M is built once per block in shared memory.  Elimination per entry as in
+// modify_mpc_vec (cpp/assemble_vector.h:52-68).  The generic warp-per-cell kernel re-evaluates the Jacobian on all
+// lanes at every quadrature point: 276 ms for the 40 M cells of BASELINE config 5, 569 ms for config 3 -- this
+// kernel: one RED per entry.
+template <int LPC>
+__global__ void __launch_bounds__(256)
+k_vector_affine_source(Tab t, IntD in, MeshD mesh, const int* __restrict__ dm, MpcD m, double* __restrict__ b)
+{
+  extern __shared__ double sm_aff[];
+  const int nd = t.nd, bs = t.bs, n = nd * bs;
+  constexpr int CPB = 256 / LPC;  // cells per block and pass
+  double* M = sm_aff;             // [nd][nd]
+  double* F = M + nd * nd;        // [CPB][n]
+  for (int e = threadIdx.x; e < nd * nd; e += blockDim.x)
+  {
+    const int i = e / nd, j = e - i * nd;
+    double acc = 0.0;
+    for (int q = 0; q < t.nq; ++q) acc += __ldg(t.w + q) * __ldg(t.phi + q * nd + i) * __ldg(t.phi + q * nd + j);
+    M[e] = acc;
+  }
+  __syncthreads();
+  const int sub = threadIdx.x / LPC, lane = threadIdx.x % LPC;
+  double* f = F + sub * n;
+  const unsigned mask = LPC == 32 ? 0xffffffffu : (0xffffu << (16 * ((threadIdx.x & 31) / 16)));
+  for (long long base = (long long)blockIdx.x * CPB; base < in.ncells; base += (long long)gridDim.x * CPB)
+  {
+    const long long index = base + sub;
+    const bool active = index < in.ncells;
+    const int cell = active ? (in.cells ? __ldg(in.cells + index) : (int)index) : 0;
+    __syncwarp(mask);
+    if (active && lane < n)
+    {
+      const int j = lane / bs, a = lane - j * bs;
+      f[lane] = in.coeffs ? __ldg(in.coeffs + index * in.cstride + lane)
+                          : __ldg(in.wnodal + (long long)__ldg(in.wmap + (long long)cell * nd + j) * bs + a);
+    }
+    // |detJ| of the affine map from the tdim + 1 vertices (every lane, registers only)
+    double X[4][3];
+    for (int v = 0; v <= t.tdim; ++v)
+    {
+      const double* p = mesh.x + (long long)__ldg(mesh.xd + (long long)cell * mesh.ng + v) * mesh.xs;
+      X[v][0] = __ldg(p); X[v][1] = __ldg(p + 1); X[v][2] = __ldg(p + 2);
+    }
+    double det;
+    if (t.tdim == 2)
+      det = (X[1][0] - X[0][0]) * (X[2][1] - X[0][1]) - (X[2][0] - X[0][0]) * (X[1][1] - X[0][1]);
+    else
+    {
+      const double a0 = X[1][0] - X[0][0], a1 = X[1][1] - X[0][1], a2 = X[1][2] - X[0][2];
+      const double b0 = X[2][0] - X[0][0], b1 = X[2][1] - X[0][1], b2 = X[2][2] - X[0][2];
+      const double c0 = X[3][0] - X[0][0], c1 = X[3][1] - X[0][1], c2 = X[3][2] - X[0][2];
+      det = a0 * (b1 * c2 - b2 * c1) - a1 * (b0 * c2 - b2 * c0) + a2 * (b0 * c1 - b1 * c0);
+    }
+    __syncwarp(mask);
+    if (active && lane < n)
+    {
+      const int i = lane / bs, a = lane - i * bs;
+      double acc = 0.0;
+      for (int j = 0; j < nd; ++j) acc += M[i * nd + j] * f[j * bs + a];
+      const double v = in.c[0] * fabs(det) * acc;
+      const int r = __ldg(dm + (long long)cell * nd + i) * bs + a;
+      const int o0 = m.is_slave[r] ? m.offsets[r] : 0, o1 = m.is_slave[r] ? m.offsets[r + 1] : 0;
+      if (o1 > o0)
+        for (int k = o0; k < o1; ++k) atomicAdd(b + m.masters[k], m.coeffs[k] * v);
+      else
+        atomicAdd(b + r, v);
+    }
+  }
+}
+
 // Closed-form scalar P1 element matrices in registers (affine simplex): Laplace, mass, Laplace with a
 // P1 coefficient (one-point rule at the centroid, which is what the tabulated degree-1 rule evaluates).
 template <int TD>
@@ -1359,6 +1433,18 @@ int mpcx_assemble_vector_f64(const mpcx_integral* integral, const mpcx_mesh* mes
     if (t->tdim == 3) MPCX_COUNT_LAUNCH(), k_vector_p1_source<3><<<(unsigned)nb, 256, 0, s>>>(in, md, dofmap->map, m.c2s_off, m, b, nullptr, 0);
     else MPCX_COUNT_LAUNCH(), k_vector_p1_source<2><<<(unsigned)nb, 256, 0, s>>>(in, md, dofmap->map, m.c2s_off, m, b, nullptr, 0);
   }
+  else if (integral->kernel == MPCX_KERNEL_SOURCE && t->ng == t->tdim + 1 && n <= 32 && !integral->local_facets
+           && (in.coeffs ? in.cstride == n : (in.wnd == nd && in.wbs == bs)))
+  {
+    // affine simplex, coefficient in the test space: reference mass matrix times nodal values
+    const int lpc = n <= 16 ? 16 : 32, cpb = 256 / lpc;
+    const size_t smem = sizeof(double) * ((size_t)nd * nd + (size_t)cpb * n);
+    long long nb = (in.ncells + cpb - 1) / cpb;
+    if (nb > 148LL * 64) nb = 148LL * 64;
+    MPCX_COUNT_LAUNCH();
+    if (lpc == 16) k_vector_affine_source<16><<<(unsigned)nb, 256, smem, s>>>(tab, in, md, dofmap->map, m, b);
+    else k_vector_affine_source<32><<<(unsigned)nb, 256, smem, s>>>(tab, in, md, dofmap->map, m, b);
+  }
   else
   {
     const int wcount = in.cstride > 0 ? in.cstride : 1;
@@ -1628,6 +1714,9 @@ int mpcx_assemble_system_tiled_f64(const mpcx_integral* a_integral, const mpcx_i
     return fail(MPCX_ERR_ARG, "the fused path needs both integrals over the same cells");
   if (a_integral->slave_cells == nullptr && mpc->num_slaves > 0) return fail(MPCX_ERR_ARG, "the tile path needs the list of slave cells");
   if (((uintptr_t)A->val & 15) != 0) return fail(MPCX_ERR_ARG, "the tile path needs a 16-byte aligned value array");
+  // b_r = f_r S1_r + S2_r needs f as a nodal function on the rows' own dofmap (see mpcx_tile_fused.cuh)
+  if (inL.coeffs || !inL.wnodal || inL.wmap != dofmap->map)
+    return fail(MPCX_ERR_UNSUPPORTED, "the fused tile kernel needs the source coefficient in the test space (same dofmap)");
   cudaStream_t s = (cudaStream_t)stream;
   const MeshD md{mesh->x, mesh->x_dofmap, mesh->ng, mesh->x_stride};
   const CsrD Ad{(const long long*)A->row_ptr, A->col, A->val};
@@ -1637,7 +1726,6 @@ int mpcx_assemble_system_tiled_f64(const mpcx_integral* a_integral, const mpcx_i
     const TilePlanD Pd = tile_plan_view(P), Qd = tile_plan_view(Q);
     const size_t smem = fused_smem_bytes(Pd, Qd, t->tdim + 1, P->ns, P->sym != 0);
     if (smem > 227 * 1024) return fail(MPCX_ERR_UNSUPPORTED, "fused tile kernel: a tile needs more shared memory than an SM has");
-    const int w_by_row = (!inL.coeffs && inL.wnodal && inL.wmap == dofmap->map) ? 1 : 0;
     auto kern = t->tdim == 3 ? (P->sym ? k_ptile_system_p1<3, true> : k_ptile_system_p1<3, false>)
                              : (P->sym ? k_ptile_system_p1<2, true> : k_ptile_system_p1<2, false>);
     int grid = 0;
@@ -1645,7 +1733,7 @@ int mpcx_assemble_system_tiled_f64(const mpcx_integral* a_integral, const mpcx_i
     if (rc) return rc;
     KernelTimer kt(s);  // dominant kernel of the call
     MPCX_COUNT_LAUNCH();
-    kern<<<grid, MPCX_TILE_THREADS, smem, s>>>(Pd, Qd, P->nt, ina, inL, md, w_by_row, Ad, b);
+    kern<<<grid, MPCX_TILE_THREADS, smem, s>>>(Pd, Qd, P->nt, ina, inL, md, Ad, b);
   }
   if (ina.nslave_cells > 0)
   {

@@ -57,6 +57,10 @@ namespace
 #define MPCX_CT_RUNGAP 16
 #endif
 #define MPCX_CT_MAXRUNS 2048
+// staging positions per tile above which the run gap is halved (see k_ct_build)
+#ifndef MPCX_CT_STAGECAP
+#define MPCX_CT_STAGECAP 3200
+#endif
 
 struct TilePlan
 {
@@ -71,6 +75,8 @@ struct TilePlan
   long long *tile_dest_off = nullptr, *tile_run_off = nullptr;
   uint16_t *cell_nodes = nullptr, *dest_spos = nullptr, *dest_spos2 = nullptr, *cell_slot = nullptr, *cell_rows = nullptr;
   uint8_t* dest_cnt = nullptr;
+  uint16_t* slot_cell = nullptr;       // vector plans: tile cell of the source held by every slot (inverse of cell_slot)
+  long long* tile_slot_off = nullptr;  // vector plans: first entry of the tile in slot_cell (multiple of 8)
   int vec = 0;  // 1: vector plan (dests = row dofs, ne = nd0)
   int sym = 0;  // 1: symmetric matrix plan (upper-triangular records feed both (r, c) and (c, r))
   int ns = 0;   // slots per cell record: ne, or nd (nd + 1) / 2 for a symmetric plan
@@ -87,6 +93,7 @@ struct TilePlanD  // what the kernel sees
   const long long *tile_dest_off, *tile_run_off;
   const uint16_t *cell_nodes, *dest_spos, *dest_spos2, *cell_slot, *cell_rows;
   const uint8_t* dest_cnt;
+  const uint16_t* slot_cell;
 };
 
 // ------------------------------------------------------------------ setup kernels (cold path)
@@ -189,7 +196,8 @@ k_ct_build(int pass, const int* __restrict__ order, long long n_bulk, const int*
            uint16_t* __restrict__ cell_nodes, int* __restrict__ dest_k, uint8_t* __restrict__ dest_cnt,
            uint16_t* __restrict__ dest_spos, uint16_t* __restrict__ dest_spos2, unsigned* __restrict__ ginfo,
            int2* __restrict__ runs,
-           uint16_t* __restrict__ cell_slot, uint16_t* __restrict__ cell_rows)
+           uint16_t* __restrict__ cell_slot, uint16_t* __restrict__ cell_rows,
+           const long long* __restrict__ tile_slot_off, uint16_t* __restrict__ slot_cell)
 {
   using SortD = cub::BlockRadixSort<unsigned, NT, NEc, unsigned short>;
   using SortN = cub::BlockRadixSort<unsigned, NT, NGc, unsigned short>;
@@ -328,46 +336,53 @@ k_ct_build(int pass, const int* __restrict__ order, long long n_bulk, const int*
   }
   __syncthreads();
 
-  // ---- staging layout: the dests in key order, cut into runs wherever two keys differ by more than RUNGAP; a run
-  // covers [even floor of its first key, even ceiling past its last key): gaps and padding stay zero
-  int rid[NEc], nf = 0;
-#pragma unroll
-  for (int e = 0; e < NEc; ++e)
+  // ---- staging layout: the dests in key order, cut into runs wherever two keys differ by more than the gap; a run
+  // covers [even floor of its first key, even ceiling past its last key): gaps and padding stay zero.  The gap starts
+  // at RUNGAP and is halved while the tile's staging buffer would exceed STAGECAP positions (a few tiles at corners
+  // of the Morton curve would otherwise size the shared memory of every CTA).
+  int rid[NEc], roff = 0, nruns = 0, stage = 0, loff = 0;
+  int rlen[NEc];
+  bool runs_ok = false;
+  for (unsigned gap = MPCX_CT_RUNGAP;; gap >>= 1)
   {
-    const int d = cl * NEc + e;
-    rid[e] = (d < total && (d == 0 || dkey[d] - dkey[d - 1] > (unsigned)MPCX_CT_RUNGAP)) ? 1 : 0;
-    nf += rid[e];
-  }
-  int roff, nruns;
-  Scan(scan).ExclusiveSum(nf, roff, nruns);
-  __syncthreads();
-  const bool runs_ok = nruns <= MR;
-  {
-    int r = roff - 1;
+    int nf = 0;
 #pragma unroll
     for (int e = 0; e < NEc; ++e)
     {
       const int d = cl * NEc + e;
-      const bool hd = rid[e] != 0;
-      if (hd) ++r;
-      rid[e] = r;
-      if (d >= total || !runs_ok) continue;
-      if (hd) rk0[r] = (int)(dkey[d] & ~1u);
-      if (d == total - 1 || dkey[d + 1] - dkey[d] > (unsigned)MPCX_CT_RUNGAP) rend[r] = (int)((dkey[d] + 2u) & ~1u);
+      rid[e] = (d < total && (d == 0 || dkey[d] - dkey[d - 1] > gap)) ? 1 : 0;
+      nf += rid[e];
     }
-  }
-  __syncthreads();
-  int rlen[NEc], lsum = 0;
+    Scan(scan).ExclusiveSum(nf, roff, nruns);
+    __syncthreads();
+    runs_ok = nruns <= MR;
+    {
+      int r = roff - 1;
 #pragma unroll
-  for (int e = 0; e < NEc; ++e)
-  {
-    const int r = cl * NEc + e;
-    rlen[e] = (runs_ok && r < nruns) ? rend[r] - rk0[r] : 0;
-    lsum += rlen[e];
+      for (int e = 0; e < NEc; ++e)
+      {
+        const int d = cl * NEc + e;
+        const bool hd = rid[e] != 0;
+        if (hd) ++r;
+        rid[e] = r;
+        if (d >= total || !runs_ok) continue;
+        if (hd) rk0[r] = (int)(dkey[d] & ~1u);
+        if (d == total - 1 || dkey[d + 1] - dkey[d] > gap) rend[r] = (int)((dkey[d] + 2u) & ~1u);
+      }
+    }
+    __syncthreads();
+    int lsum = 0;
+#pragma unroll
+    for (int e = 0; e < NEc; ++e)
+    {
+      const int r = cl * NEc + e;
+      rlen[e] = (runs_ok && r < nruns) ? rend[r] - rk0[r] : 0;
+      lsum += rlen[e];
+    }
+    Scan(scan).ExclusiveSum(lsum, loff, stage);
+    __syncthreads();
+    if (vec || gap <= 1 || (runs_ok && stage <= MPCX_CT_STAGECAP)) break;
   }
-  int loff, stage;
-  Scan(scan).ExclusiveSum(lsum, loff, stage);
-  __syncthreads();
   bool ok = runs_ok && stage < 65536;  // otherwise the tile does not fit the plan format (the host reports it)
   if (ok)
   {
@@ -527,7 +542,11 @@ k_ct_build(int pass, const int* __restrict__ order, long long n_bulk, const int*
         const int i_src = cl * NEc + e - (int)dstart[d];  // i-th source of dest d (same cell order in the transposed dest)
         const int p = npos[part[d]];
         sl = (uint16_t)(gbase[p >> 5] + MPCX_CT_GSTRIDE * i_src + (p & 31));
-        if (vec) cell_rows[first * NEc + vals[e]] = (uint16_t)p;
+        if (vec)
+        {
+          cell_rows[first * NEc + vals[e]] = (uint16_t)p;
+          slot_cell[tile_slot_off[t] + sl] = (uint16_t)cidx;
+        }
       }
       cell_slot[first * NS + cidx * NS + si] = sl;
     }
@@ -967,7 +986,7 @@ void tile_plan_free(TilePlan* P)
   cudaFree(P->cell_pos); cudaFree(P->tile_node_off); cudaFree(P->node_ids); cudaFree(P->dest_k); cudaFree(P->tile_nd);
   cudaFree(P->tile_slots); cudaFree(P->tile_nr); cudaFree(P->tile_stage); cudaFree(P->runs); cudaFree(P->hdr); cudaFree(P->ginfo);
   cudaFree(P->tile_dest_off); cudaFree(P->tile_run_off); cudaFree(P->cell_nodes); cudaFree(P->dest_cnt); cudaFree(P->dest_spos);
-  cudaFree(P->dest_spos2); cudaFree(P->cell_slot); cudaFree(P->cell_rows);
+  cudaFree(P->dest_spos2); cudaFree(P->cell_slot); cudaFree(P->cell_rows); cudaFree(P->slot_cell); cudaFree(P->tile_slot_off);
   delete P;
 }
 
@@ -976,7 +995,7 @@ inline TilePlanD tile_plan_view(const TilePlan* P)
   return TilePlanD{P->C, P->max_nodes, P->max_dests, P->max_slots, P->max_runs, P->max_stage, P->n_bulk, P->cell_pos,
                    P->tile_node_off, P->node_ids, P->dest_k, P->tile_nd, P->tile_nr, P->tile_stage, P->runs, P->hdr, P->ginfo,
                    P->tile_dest_off, P->tile_run_off, P->cell_nodes, P->dest_spos, P->dest_spos2, P->cell_slot, P->cell_rows,
-                   P->dest_cnt};
+                   P->dest_cnt, P->slot_cell};
 }
 
 inline unsigned tp_grid(long long n, int b = 256) { return (unsigned)((n + b - 1) / b > 0 ? (n + b - 1) / b : 1); }
@@ -1001,7 +1020,7 @@ cudaError_t ct_build_launch(int pass, cudaStream_t s, const int* order, const in
                                bc1, A, P->nrows, P->vec, P->sym, extra_off, tile_nn, P->tile_nd, P->tile_slots, P->tile_nr,
                                P->tile_stage, P->tile_node_off, P->tile_dest_off, P->tile_run_off, P->cell_pos, P->node_ids,
                                P->cell_nodes, P->dest_k, P->dest_cnt, P->dest_spos, P->dest_spos2, P->ginfo, P->runs,
-                               P->cell_slot, P->cell_rows);
+                               P->cell_slot, P->cell_rows, P->tile_slot_off, P->slot_cell);
   return cudaGetLastError();
 }
 
@@ -1032,7 +1051,7 @@ int tile_plan_build(const mpcx_mesh* mesh, const mpcx_dofmap* dm0, const mpcx_do
   void* tmp = nullptr;
   size_t tmp_bytes = 0, tb = 0;
   std::vector<int> h_nn, h_nd, h_sl, h_nr, h_st, noff, h_hdr;
-  std::vector<long long> h_doff, h_roff;
+  std::vector<long long> h_doff, h_roff, h_soff;
   bool fits = true;
   long long alloc_dests = 0;
   BBox bb;
@@ -1101,8 +1120,10 @@ int tile_plan_build(const mpcx_mesh* mesh, const mpcx_dofmap* dm0, const mpcx_do
   noff.assign(P->nt + 1, 0);
   h_doff.assign(P->nt + 1, 0);
   h_roff.assign(P->nt + 1, 0);
+  h_soff.assign(P->nt + 1, 0);
   for (int t = 0; t < P->nt; ++t)
   {
+    h_soff[t + 1] = h_soff[t] + ((h_sl[t] + 1 + 7) & ~7);  // slots + the spare one, 16-byte granules of uint16
     if (h_nd[t] >= (1 << 30)) { fits = false; break; }  // too many runs / staging positions for the plan format
     h_roff[t + 1] = h_roff[t] + ((h_nr[t] + 1) & ~1);
     P->total_runs += h_nr[t];
@@ -1136,7 +1157,8 @@ int tile_plan_build(const mpcx_mesh* mesh, const mpcx_dofmap* dm0, const mpcx_do
     int* q = h_hdr.data() + 12 * (size_t)t;
     q[0] = noff[t]; q[1] = h_nn[t]; q[2] = h_nd[t]; q[3] = h_nr[t];
     q[4] = h_st[t]; q[5] = 0; q[6] = (int)(unsigned)(h_doff[t] & 0xffffffffll); q[7] = (int)(h_doff[t] >> 32);
-    q[8] = (int)(unsigned)(h_roff[t] & 0xffffffffll); q[9] = (int)(h_roff[t] >> 32); q[10] = q[11] = 0;
+    q[8] = (int)(unsigned)(h_roff[t] & 0xffffffffll); q[9] = (int)(h_roff[t] >> 32);
+    q[10] = (int)(unsigned)(h_soff[t] & 0xffffffffll); q[11] = (int)(h_soff[t] >> 32); q[5] = h_sl[t];
   }
   TP_CK(tp_alloc(&P->hdr, 3 * (long long)P->nt));
   TP_CK(cudaMemcpyAsync(P->hdr, h_hdr.data(), sizeof(int) * h_hdr.size(), cudaMemcpyHostToDevice, s));
@@ -1165,6 +1187,10 @@ int tile_plan_build(const mpcx_mesh* mesh, const mpcx_dofmap* dm0, const mpcx_do
   {
     TP_CK(tp_alloc(&P->cell_rows, (long long)P->nt * C * P->ne));
     TP_CK(cudaMemsetAsync(P->cell_rows, 0, sizeof(uint16_t) * (size_t)P->nt * C * P->ne, s));
+    TP_CK(tp_alloc(&P->slot_cell, h_soff[P->nt] + 8));
+    TP_CK(cudaMemsetAsync(P->slot_cell, 0, sizeof(uint16_t) * (size_t)(h_soff[P->nt] + 8), s));
+    TP_CK(tp_alloc(&P->tile_slot_off, P->nt + 1));
+    TP_CK(cudaMemcpyAsync(P->tile_slot_off, h_soff.data(), sizeof(long long) * (P->nt + 1), cudaMemcpyHostToDevice, s));
   }
   TP_CK(build(1));
   TP_CK(cudaStreamSynchronize(s));
