@@ -20,7 +20,8 @@ OK, ERR_ARG, ERR_UNSUPPORTED, ERR_CUDA, ERR_PATTERN, ERR_ALLOC = range(6)
 class Tables(C.Structure):
     _fields_ = [("tdim", C.c_int32), ("gdim", C.c_int32), ("nd", C.c_int32), ("ng", C.c_int32),
                 ("nq", C.c_int32), ("bs", C.c_int32), ("weights", C.c_void_p), ("phi", C.c_void_p),
-                ("dphi", C.c_void_p), ("gdphi", C.c_void_p), ("nfacets", C.c_int32), ("facet_tangents", C.c_void_p)]
+                ("dphi", C.c_void_p), ("gdphi", C.c_void_p), ("nfacets", C.c_int32), ("facet_tangents", C.c_void_p),
+                ("nd1", C.c_int32), ("bs1", C.c_int32), ("phi1", C.c_void_p), ("dphi1", C.c_void_p)]
 
 
 class MeshS(C.Structure):

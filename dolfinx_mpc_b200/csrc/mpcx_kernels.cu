@@ -84,6 +84,8 @@ struct Tab
   int tdim, gdim, nd, ng, nq, bs;
   const double *w, *phi, *dphi, *gdphi;
   const double* ftan;  // facet tables: tangents of every local facet; in an entity view: of this facet (or null)
+  int nd1, bs1;        // trial element of a rectangular form (nd1 == 0: same element on both sides)
+  const double *phi1, *dphi1;
 };
 struct MeshD
 {
@@ -223,7 +225,8 @@ __device__ void tabulate_warp(const Tab& t, int kernel, const double* c, const d
                               const double* w, double* out, double* g, int lane)
 {
   const int nd = t.nd, bs = t.bs, n = nd * bs;
-  const int nout = (kernel == MPCX_KERNEL_SOURCE) ? n : n * n;
+  const int n1 = t.nd1 ? t.nd1 * t.bs1 : n;
+  const int nout = (kernel == MPCX_KERNEL_SOURCE) ? n : n * n1;
   for (int e = lane; e < nout; e += 32) out[e] = 0.0;
   __syncwarp();
   for (int q = 0; q < t.nq; ++q)
@@ -232,7 +235,33 @@ __device__ void tabulate_warp(const Tab& t, int kernel, const double* c, const d
     jacobian(t, q, X, K, detJ);
     const double s = __ldg(t.w + q) * fabs(detJ);
     const double* phi = t.phi + q * nd;
-    if (kernel == MPCX_KERNEL_MASS)
+    if (kernel == MPCX_KERNEL_DIV_TEST || kernel == MPCX_KERNEL_DIV_TRIAL)
+    {
+      // vector side V (nv scalar basis functions, gdim components), scalar side Q (ns basis functions):
+      //   DIV_TEST : A[(i, a), j] += c0 s phi^Q_j d_a phi^V_i        (rows = V, columns = Q)
+      //   DIV_TRIAL: A[j, (i, a)] += c0 s phi^Q_j d_a phi^V_i        (rows = Q, columns = V)
+      const bool vt = kernel == MPCX_KERNEL_DIV_TEST;
+      const int nv = vt ? nd : t.nd1, ns = vt ? t.nd1 : nd;
+      const double* dphv = vt ? t.dphi + (size_t)q * t.tdim * nd : t.dphi1 + (size_t)q * t.tdim * t.nd1;
+      const double* phs = vt ? t.phi1 + (size_t)q * t.nd1 : phi;
+      for (int e = lane; e < nv * t.gdim; e += 32)
+      {
+        const int i = e / t.gdim, k = e - i * t.gdim;
+        double sum = 0.0;
+        for (int a = 0; a < t.tdim; ++a) sum += K[a * 3 + k] * __ldg(dphv + a * nv + i);
+        g[i * 3 + k] = sum;
+      }
+      __syncwarp();
+      const double sc = c[0] * s;
+      for (int e = lane; e < nv * t.gdim * ns; e += 32)
+      {
+        const int ia = e / ns, j = e - ia * ns, i = ia / t.gdim, a = ia - i * t.gdim;
+        const double v = sc * __ldg(phs + j) * g[i * 3 + a];
+        if (vt) out[ia * n1 + j] += v; else out[j * n1 + ia] += v;
+      }
+      __syncwarp();
+    }
+    else if (kernel == MPCX_KERNEL_MASS)
     {
       const double sc = c[0] * s;
       for (int pr = lane; pr < nd * nd; pr += 32)
@@ -341,7 +370,7 @@ k_matrix_generic(Tab t, IntD in, MeshD mesh, const int* __restrict__ dm0, const 
   double* X = base;
   double* Ae = X + 3 * mesh.ng;
   double* g = Ae + n0 * n1;
-  double* w = g + 3 * t.nd;
+  double* w = g + 3 * (t.nd > t.nd1 ? t.nd : t.nd1);
   int* d0 = (int*)(w + (in.cstride > 0 ? in.cstride : 1));
   int* d1 = d0 + nd0;
   int* offR = d1 + nd1;      // [n0 + 1] first row-target index of local row p
@@ -469,7 +498,7 @@ k_lifting_generic(Tab t, IntD in, MeshD mesh, const int* __restrict__ dm0, const
   double* X = base;
   double* Ae = X + 3 * mesh.ng;
   double* g = Ae + n0 * n1;
-  double* w = g + 3 * t.nd;
+  double* w = g + 3 * (t.nd > t.nd1 ? t.nd : t.nd1);
   double* gx = w + (in.cstride > 0 ? in.cstride : 1);  // scale*(g - x0) per column, 0 where no bc
   const long long wstride = (long long)gridDim.x * (blockDim.x >> 5);
   for (long long it = (long long)blockIdx.x * (blockDim.x >> 5) + warp; it < nlist; it += wstride)
@@ -1133,7 +1162,8 @@ namespace
 // ------------------------------------------------------------------ host helpers
 Tab make_tab(const mpcx_tables* t)
 {
-  return Tab{t->tdim, t->gdim, t->nd, t->ng, t->nq, t->bs, t->weights, t->phi, t->dphi, t->gdphi, t->facet_tangents};
+  return Tab{t->tdim, t->gdim, t->nd, t->ng, t->nq, t->bs, t->weights, t->phi, t->dphi, t->gdphi, t->facet_tangents,
+             t->nd1, t->nd1 ? t->bs1 : 0, t->phi1, t->dphi1};
 }
 MpcD make_mpc(const mpcx_mpc* m)
 {
@@ -1157,15 +1187,26 @@ int check_integral(const mpcx_integral* in, bool bilinear)
   if (!in || !in->tables) return fail(MPCX_ERR_ARG, "null integral/tables");
   if (in->num_cells < 0 || in->num_constants > MPCX_MAX_CONSTANTS) return fail(MPCX_ERR_ARG, "bad sizes");
   const int k = in->kernel;
+  const bool is_div = k == MPCX_KERNEL_DIV_TEST || k == MPCX_KERNEL_DIV_TRIAL;
   const bool is_bilinear = k == MPCX_KERNEL_LAPLACE || k == MPCX_KERNEL_MASS || k == MPCX_KERNEL_ELASTICITY
-                           || k == MPCX_KERNEL_LAPLACE_VARCOEF;
-  if (k < 0 || k > MPCX_KERNEL_LAPLACE_VARCOEF) return fail(MPCX_ERR_UNSUPPORTED, "unknown kernel id");
+                           || k == MPCX_KERNEL_LAPLACE_VARCOEF || is_div;
+  if (k < 0 || k > MPCX_KERNEL_DIV_TRIAL) return fail(MPCX_ERR_UNSUPPORTED, "unknown kernel id");
   if (bilinear != is_bilinear)
     return fail(MPCX_ERR_UNSUPPORTED, "kernel rank does not match the assembly routine");
   const mpcx_tables* t = in->tables;
   if (t->tdim != t->gdim || (t->tdim != 2 && t->tdim != 3))
     return fail(MPCX_ERR_UNSUPPORTED, "only tdim == gdim in {2, 3} has device kernels");
   if (k == MPCX_KERNEL_ELASTICITY && t->bs != t->gdim) return fail(MPCX_ERR_ARG, "elasticity needs bs == gdim");
+  if (is_div)
+  {
+    if (t->nd1 <= 0 || !t->phi1 || !t->dphi1) return fail(MPCX_ERR_ARG, "the div coupling kernels need the trial element's tables");
+    if (in->local_facets) return fail(MPCX_ERR_UNSUPPORTED, "the div coupling kernels are cell integrals");
+    const bool vt = k == MPCX_KERNEL_DIV_TEST;
+    if ((vt ? t->bs : t->bs1) != t->gdim || (vt ? t->bs1 : t->bs) != 1)
+      return fail(MPCX_ERR_ARG, "div coupling: the vector side needs bs == gdim, the scalar side bs == 1");
+  }
+  else if (t->nd1 != 0)
+    return fail(MPCX_ERR_UNSUPPORTED, "this kernel has one element on both sides");
   if (in->local_facets && (t->nfacets <= 0 || !t->facet_tangents))
     return fail(MPCX_ERR_ARG, "an exterior-facet integral needs facet tables");
   if (in->local_facets && !in->cells) return fail(MPCX_ERR_ARG, "an exterior-facet integral needs the cells of its facets");
@@ -1263,8 +1304,9 @@ int mpcx_assemble_matrix_f64(const mpcx_integral* integral, const mpcx_mesh* mes
   if (rc) return rc;
   if (!mesh || !dofmap0 || !dofmap1 || !mpc0 || !mpc1 || !A) return fail(MPCX_ERR_ARG, "null argument");
   const mpcx_tables* t = integral->tables;
-  if (dofmap0->nd != t->nd || dofmap1->nd != t->nd || dofmap0->bs != t->bs || dofmap1->bs != t->bs)
-    return fail(MPCX_ERR_UNSUPPORTED, "test/trial dofmaps must match the tabulated element");
+  const int nd1 = t->nd1 ? t->nd1 : t->nd, bs1 = t->nd1 ? t->bs1 : t->bs;  // trial element (rectangular forms)
+  if (dofmap0->nd != t->nd || dofmap1->nd != nd1 || dofmap0->bs != t->bs || dofmap1->bs != bs1)
+    return fail(MPCX_ERR_UNSUPPORTED, "test/trial dofmaps must match the tabulated elements");
   if (mesh->ng != t->ng) return fail(MPCX_ERR_ARG, "geometry dofmap width does not match the tables");
   if (plan && plan->lpos && plan->width != 1 && plan->width != 2) return fail(MPCX_ERR_ARG, "plan width must be 1 or 2");
   if (integral->num_cells == 0) return MPCX_OK;
@@ -1276,7 +1318,7 @@ int mpcx_assemble_matrix_f64(const mpcx_integral* integral, const mpcx_mesh* mes
   const CsrD Ad{(const long long*)A->row_ptr, A->col, A->val};
   const void* lpos = plan ? plan->lpos : nullptr;
   const int width = plan ? plan->width : 0;
-  const int nd = t->nd, bs = t->bs, n = nd * bs;
+  const int nd = t->nd, bs = t->bs, n = nd * bs, n1 = nd1 * bs1;
 
   const bool p1_simplex = t->nd == t->tdim + 1 && t->ng == t->tdim + 1;
   // the bulk/elimination split needs the list of slave cells (or a constraint without slaves)
@@ -1289,7 +1331,7 @@ int mpcx_assemble_matrix_f64(const mpcx_integral* integral, const mpcx_mesh* mes
   const bool fast = lpos && have_split && closed_form && !integral->local_facets;  // facets: generic kernel
   // generic kernel resources
   const int wcount = in.cstride > 0 ? in.cstride : 1;
-  int spw = 3 * mesh->ng + n * n + 3 * nd + wcount + (2 * nd + 2 * n + 2 + 1) / 2 + 1;
+  int spw = 3 * mesh->ng + n * n1 + 3 * std::max(nd, nd1) + wcount + (nd + nd1 + n + n1 + 2 + 1) / 2 + 1;
   const size_t smem = (size_t)spw * 4 * sizeof(double);
   if (smem > 48 * 1024)
   {
@@ -1302,10 +1344,10 @@ int mpcx_assemble_matrix_f64(const mpcx_integral* integral, const mpcx_mesh* mes
     if (nwork <= 0) return;
     const int grid = grid_for_warps(nwork, 4);
     if (width == 2)
-      MPCX_COUNT_LAUNCH(), k_matrix_generic<uint16_t><<<grid, 128, smem, s>>>(tab, in, md, dofmap0->map, dofmap1->map, nd, nd, bs, bs, bc0, bc1,
+      MPCX_COUNT_LAUNCH(), k_matrix_generic<uint16_t><<<grid, 128, smem, s>>>(tab, in, md, dofmap0->map, dofmap1->map, nd, nd1, bs, bs1, bc0, bc1,
                                                          m0, m1, Ad, (const uint16_t*)lpos, mode, spw);
     else
-      MPCX_COUNT_LAUNCH(), k_matrix_generic<uint8_t><<<grid, 128, smem, s>>>(tab, in, md, dofmap0->map, dofmap1->map, nd, nd, bs, bs, bc0, bc1,
+      MPCX_COUNT_LAUNCH(), k_matrix_generic<uint8_t><<<grid, 128, smem, s>>>(tab, in, md, dofmap0->map, dofmap1->map, nd, nd1, bs, bs1, bc0, bc1,
                                                         m0, m1, Ad, (const uint8_t*)lpos, mode, spw);
   };
   const bool fast_elasticity = lpos && have_split && kid == MPCX_KERNEL_ELASTICITY && p1_simplex && bs == t->tdim
@@ -1464,8 +1506,9 @@ int mpcx_apply_lifting_f64(const mpcx_integral* integral, const mpcx_mesh* mesh,
   if (rc) return rc;
   if (!mesh || !dofmap0 || !dofmap1 || !mpc0 || !b || !bc_markers1 || !bc_values1) return fail(MPCX_ERR_ARG, "null argument");
   const mpcx_tables* t = integral->tables;
-  if (dofmap0->nd != t->nd || dofmap1->nd != t->nd || dofmap0->bs != t->bs || dofmap1->bs != t->bs)
-    return fail(MPCX_ERR_UNSUPPORTED, "test/trial dofmaps must match the tabulated element");
+  const int nd1 = t->nd1 ? t->nd1 : t->nd, bs1 = t->nd1 ? t->bs1 : t->bs;  // trial element (rectangular forms)
+  if (dofmap0->nd != t->nd || dofmap1->nd != nd1 || dofmap0->bs != t->bs || dofmap1->bs != bs1)
+    return fail(MPCX_ERR_UNSUPPORTED, "test/trial dofmaps must match the tabulated elements");
   const long long nlist = bc_cells ? num_bc_cells : integral->num_cells;
   if (integral->num_cells == 0 || nlist <= 0) return MPCX_OK;
   const Tab tab = make_tab(t);
@@ -1490,7 +1533,8 @@ int mpcx_apply_lifting_f64(const mpcx_integral* integral, const mpcx_mesh* mesh,
     return cuda_check(cudaGetLastError(), "apply_lifting launch");
   }
   const int wcount = in.cstride > 0 ? in.cstride : 1;
-  const int spw = 3 * mesh->ng + n * n + 3 * nd + wcount + n + 1;
+  const int n1 = nd1 * bs1;
+  const int spw = 3 * mesh->ng + n * n1 + 3 * std::max(nd, nd1) + wcount + n1 + 1;
   const size_t smem = (size_t)spw * 4 * sizeof(double);
   if (smem > 48 * 1024)
   {
@@ -1498,7 +1542,7 @@ int mpcx_apply_lifting_f64(const mpcx_integral* integral, const mpcx_mesh* mesh,
     if (rc) return rc;
   }
   MPCX_COUNT_LAUNCH(), k_lifting_generic<<<grid_for_warps(nlist, 4), 128, smem, (cudaStream_t)stream>>>(
-      tab, in, md, dofmap0->map, dofmap1->map, nd, nd, bs, bs, bc_markers1, bc_values1, x0, scale, make_mpc(mpc0),
+      tab, in, md, dofmap0->map, dofmap1->map, nd, nd1, bs, bs1, bc_markers1, bc_values1, x0, scale, make_mpc(mpc0),
       bc_cells, nlist, b, spw);
   return cuda_check(cudaGetLastError(), "apply_lifting launch");
 }

@@ -52,7 +52,7 @@ __host__ __device__ inline size_t fused_smem_bytes(const TilePlanD& P, const Til
 {
   auto al = [](size_t b) { return (b + 15) & ~(size_t)15; };
   size_t b = al(24 * (size_t)P.max_nodes) + al(8 * (size_t)P.max_stage) + al(8 * (size_t)(P.max_slots + 1))
-             + al(8 * (size_t)Q.max_dests) + al(16 * (size_t)P.C);
+             + al(8 * (size_t)Q.max_dests) + al(16 * (size_t)(P.C + 1));
   b += al(8 * (size_t)P.max_runs) + al(4 * (size_t)(P.max_dests / 32)) + (sym ? 2 : 1) * al(2 * (size_t)P.max_dests)
        + al((size_t)P.max_dests);
   b += al(4 * (size_t)(Q.max_dests / 32)) + al(4 * (size_t)Q.max_dests) + al((size_t)Q.max_dests);
@@ -69,7 +69,7 @@ __device__ __forceinline__ FusedSmem fused_carve(unsigned char* sp, const TilePl
   S.stage = reinterpret_cast<double*>(sp); sp += al(8 * (size_t)P.max_stage);
   S.ebuf = reinterpret_cast<double*>(sp); sp += al(8 * (size_t)(P.max_slots + 1));
   S.fs = reinterpret_cast<double*>(sp); sp += al(8 * (size_t)Q.max_dests);
-  S.cellv = reinterpret_cast<double2*>(sp); sp += al(16 * (size_t)P.C);
+  S.cellv = reinterpret_cast<double2*>(sp); sp += al(16 * (size_t)(P.C + 1));
   S.R.runs = reinterpret_cast<int2*>(sp); sp += al(8 * (size_t)P.max_runs);
   S.R.gi = reinterpret_cast<unsigned*>(sp); sp += al(4 * (size_t)(P.max_dests / 32));
   S.R.dk = nullptr;
@@ -153,14 +153,15 @@ k_ptile_system_p1(TilePlanD P, TilePlanD Q, int nt, IntD ina, IntD inL, MeshD me
   if (has_next) { hn = load_hdr(P.hdr, tn); hvn = load_vhdr(Q.hdr, tn); }
   __syncthreads();
   const double cL = inL.c[0] * (1.0 / double((TD + 1) * (TD + 2)));
-  double fcur = tid < hv.nd ? __ldg(inL.wnodal + __ldg(Q.dest_k + hv.dest_off + tid)) : 0.0;
+  double fcur = NT - 1 - tid < hv.nd ? __ldg(inL.wnodal + __ldg(Q.dest_k + hv.dest_off + (NT - 1 - tid))) : 0.0;
+  if (tid == 0) S.cellv[NT] = make_double2(0.0, 0.0);  // the pair read by lanes past their count
   for (unsigned it = 0;; ++it)
   {
     const long long first = (long long)t * NT;
     const int nc_t = (int)((P.n_bulk - first) < NT ? (P.n_bulk - first) : NT);
     int nid = -1, fid = -1;
     if (has_next && tid < hn.nn) nid = __ldg(P.node_ids + hn.node_off + tid);
-    if (has_next && tid < hvn.nd) fid = __ldg(Q.dest_k + hvn.dest_off + tid);
+    if (has_next && NT - 1 - tid < hvn.nd) fid = __ldg(Q.dest_k + hvn.dest_off + (NT - 1 - tid));  // row of this thread's record
 
     // phase 1: thread = cell
     mbar_wait(S.barC, it & 1);
@@ -230,22 +231,29 @@ k_ptile_system_p1(TilePlanD P, TilePlanD Q, int nt, IntD ina, IntD inL, MeshD me
       S.stage[S.R.spos[k]] = v;
       if (SYM) S.stage[S.R.spos2[k]] = v;
     }
-    for (int k = tid; k < hv.nd; k += NT)  // row records: thread k carries f of row k in a register (fcur)
+    // row records go to the LAST threads (the first ones hold the heaviest matrix records: those are ordered by
+    // descending source count); thread NT-1-k carries f of row k in a register (fcur)
+    for (int k = NT - 1 - tid; k < hv.nd; k += NT)
     {
       const unsigned g = S.giv[k >> 5];
       const uint16_t* e = S.vinc + (g & 0xffffu) + (k & 31);
       const int cnt = S.dcntv[k];
       double s1 = 0.0, s2 = 0.0;
-      for (int i = 0; i < cnt; ++i, e += MPCX_CT_GSTRIDE)
+#pragma unroll 1
+      for (int i = 0; i < cnt; i += 4, e += 4 * MPCX_CT_GSTRIDE)
       {
-        const double2 cv = S.cellv[*e];
-        s1 += cv.x; s2 += cv.y;
+        // four independent index -> pair loads in flight; lanes past their count read the zero pair at cellv[NT]
+        const int c0 = e[0], c1 = i + 1 < cnt ? (int)e[MPCX_CT_GSTRIDE] : NT, c2 = i + 2 < cnt ? (int)e[2 * MPCX_CT_GSTRIDE] : NT,
+                  c3 = i + 3 < cnt ? (int)e[3 * MPCX_CT_GSTRIDE] : NT;
+        const double2 v0 = S.cellv[c0], v1 = S.cellv[c1], v2 = S.cellv[c2], v3 = S.cellv[c3];
+        s1 += (v0.x + v1.x) + (v2.x + v3.x);
+        s2 += (v0.y + v1.y) + (v2.y + v3.y);
       }
       const int row = S.dkv[k];
       atomicAdd(b + row, (k < NT ? fcur : __ldg(inL.wnodal + row)) * s1 + s2);
     }
     if (nid >= 0) { S.Xs[3 * tid] = xg0; S.Xs[3 * tid + 1] = xg1; S.Xs[3 * tid + 2] = xg2; }
-    if (fid >= 0) S.fs[tid] = fg;
+    if (fid >= 0) S.fs[NT - 1 - tid] = fg;
     if (has_next)
     {
       for (int i = tid + NT; i < hn.nn; i += NT)

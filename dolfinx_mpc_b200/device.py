@@ -81,13 +81,16 @@ def mpc_dev(mpc) -> dict:
 _tables_cache: dict = {}
 
 
-def tables_struct(tab, bs: int):
-    key = (tab.cell_type, tab.degree, tab.nq, bs, tab.nfacets, device().index)
+def tables_struct(tab, bs: int, bs1: int = 0):
+    key = (tab.cell_type, tab.degree, tab.nq, bs, tab.nfacets, tab.degree1, tab.nd1, bs1, device().index)
     if key not in _tables_cache:
         keep = [to_dev(tab.weights), to_dev(tab.phi), to_dev(tab.dphi), to_dev(tab.gdphi)]
         ftan = to_dev(tab.ftan) if tab.nfacets else None
-        keep.append(ftan)
-        s = _lib.Tables(tab.tdim, tab.gdim, tab.nd, tab.ng, tab.nq, bs, *[ptr(k) for k in keep[:4]], tab.nfacets, ptr(ftan))
+        phi1 = to_dev(tab.phi1) if tab.nd1 else None
+        dphi1 = to_dev(tab.dphi1) if tab.nd1 else None
+        keep += [ftan, phi1, dphi1]
+        s = _lib.Tables(tab.tdim, tab.gdim, tab.nd, tab.ng, tab.nq, bs, *[ptr(k) for k in keep[:4]], tab.nfacets, ptr(ftan),
+                        tab.nd1, bs1 if tab.nd1 else 0, ptr(phi1), ptr(dphi1))
         _tables_cache[key] = (s, keep)
     return _tables_cache[key][0]
 
@@ -103,7 +106,7 @@ def function_dev(f: Function) -> torch.Tensor:
 def integral_struct(form: Form, it: Integral, mpcs, keep: list) -> _lib.IntegralS:
     """C struct for one integral; device arrays that must outlive the call are appended to ``keep``."""
     V = form.function_spaces[0]
-    tab = tables_struct(form.tables(it), V.bs)
+    tab = tables_struct(form.tables(it), V.bs, form.function_spaces[-1].bs)
     s = _lib.IntegralS()
     s.kernel = int(it.kernel)
     s.tables = C.pointer(tab)

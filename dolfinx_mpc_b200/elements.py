@@ -163,6 +163,12 @@ class ElementTables:
     # of the reference facet mapped into the cell), and ftan the tangents of the reference facet map
     nfacets: int = 0
     ftan: Optional[np.ndarray] = None  # (nfacets, tdim - 1, tdim)
+    # rectangular forms (test and trial elements differ, e.g. the div / grad blocks of Taylor-Hood): the trial
+    # element's basis at the same quadrature points; nd1 == 0 means "same element on both sides"
+    degree1: int = 0
+    nd1: int = 0
+    phi1: Optional[np.ndarray] = None  # (nq, nd1)
+    dphi1: Optional[np.ndarray] = None  # (nq, tdim, nd1)
 
 
 @functools.lru_cache(maxsize=None)
@@ -176,6 +182,16 @@ def element_tables(cell_type: str, degree: int, qdegree: int) -> ElementTables:
         np.ascontiguousarray(wts), np.ascontiguousarray(phi), np.ascontiguousarray(dphi),
         np.ascontiguousarray(gdphi),
     )
+
+
+@functools.lru_cache(maxsize=None)
+def mixed_element_tables(cell_type: str, degree0: int, degree1: int, qdegree: int) -> ElementTables:
+    """Tables of a cell integral whose test element (degree0) and trial element (degree1) differ."""
+    t0 = element_tables(cell_type, degree0, qdegree)
+    pts, _ = make_quadrature(cell_type, qdegree)
+    phi1, dphi1 = tabulate(cell_type, degree1, pts)
+    return dataclasses.replace(t0, degree1=degree1, nd1=phi1.shape[1], phi1=np.ascontiguousarray(phi1),
+                               dphi1=np.ascontiguousarray(dphi1))
 
 
 # Local facets as vertex tuples, DOLFINx / Basix numbering: simplex facet i is opposite vertex i; tensor-product

@@ -32,6 +32,9 @@ class Kernel(enum.IntEnum):
     ELASTICITY = 2  # inner(sigma(u), grad v) dx, c = [mu, lambda], bs == gdim
     SOURCE = 3  # c[0] * inner(f, v) dx, w = f at the cell dofs
     LAPLACE_VARCOEF = 4  # c[0] * w * inner(grad u, grad v) dx, w scalar, same element
+    # rectangular blocks (test and trial spaces differ: python/tests/test_rectangular_assembly.py:83-86)
+    DIV_TEST = 5  # c[0] * inner(p, div(v)) dx: test = vector space (bs == gdim), trial = scalar space
+    DIV_TRIAL = 6  # c[0] * inner(div(u), q) dx: test = scalar space, trial = vector space (bs == gdim)
 
 
 @dataclasses.dataclass
@@ -232,6 +235,11 @@ def _qdegree(kernel: Kernel, cell_type: str, degree: int) -> int:
     raise ValueError(kernel)
 
 
+def _qdegree_mixed(cell_type: str, degree0: int, degree1: int) -> int:
+    """phi * d(phi'): sum of the degrees minus one on simplices (affine map), sum of the degrees on tensor cells."""
+    return degree0 + degree1 - 1 if _el.is_simplex(cell_type) else degree0 + degree1
+
+
 @dataclasses.dataclass
 class Integral:
     """One integral of a form: kernel id, integration domain, coefficients, constants.
@@ -281,6 +289,12 @@ class Form:
 
     def tables(self, integral: Integral) -> _el.ElementTables:
         V = self.function_spaces[0]
+        if integral.kernel in (Kernel.DIV_TEST, Kernel.DIV_TRIAL):
+            if integral.integral_type != "cell":
+                raise RuntimeError("the div coupling kernels are cell integrals")
+            V1 = self.function_spaces[1]
+            return _el.mixed_element_tables(self.mesh.cell_type, V.degree, V1.degree,
+                                            _qdegree_mixed(self.mesh.cell_type, V.degree, V1.degree))
         make = _el.facet_tables if integral.integral_type == "exterior_facet" else _el.element_tables
         return make(self.mesh.cell_type, V.degree, _qdegree(integral.kernel, self.mesh.cell_type, V.degree))
 
@@ -321,6 +335,20 @@ def elasticity(V: FunctionSpace, mu: float, lmbda: float, cells=None) -> Form:
     """``inner(sigma(u), grad(v)) * dx`` as in ``python/benchmarks/bench_elasticity_edge.py:125-135``."""
     assert V.bs == V.mesh.tdim
     return Form(2, (V, V), [Integral(Kernel.ELASTICITY, [mu, lmbda], cells=cells)])
+
+
+def div_test(V: FunctionSpace, Q: FunctionSpace, scale: float = -1.0, cells=None) -> Form:
+    """``scale * inner(p, div(v)) * dx`` with ``v`` in the vector space ``V`` (test) and ``p`` in the scalar space
+    ``Q`` (trial): the ``a01`` block of ``python/tests/test_rectangular_assembly.py:83-86`` for ``scale = -1``."""
+    assert V.bs == V.mesh.tdim and Q.bs == 1 and V.mesh is Q.mesh
+    return Form(2, (V, Q), [Integral(Kernel.DIV_TEST, [scale], cells=cells)])
+
+
+def div_trial(Q: FunctionSpace, V: FunctionSpace, scale: float = -1.0, cells=None) -> Form:
+    """``scale * inner(div(u), q) * dx`` with ``q`` in the scalar space ``Q`` (test) and ``u`` in the vector space
+    ``V`` (trial): the ``a10`` block of the same test."""
+    assert V.bs == V.mesh.tdim and Q.bs == 1 and V.mesh is Q.mesh
+    return Form(2, (Q, V), [Integral(Kernel.DIV_TRIAL, [scale], cells=cells)])
 
 
 def laplace_varcoef(V: FunctionSpace, w: Function, scale: float = 1.0, cells=None) -> Form:

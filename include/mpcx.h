@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define MPCX_ABI_VERSION 2
+#define MPCX_ABI_VERSION 3
 #define MPCX_MAX_CONSTANTS 8
 
 typedef enum mpcx_status
@@ -51,7 +51,9 @@ typedef enum mpcx_kernel
   MPCX_KERNEL_MASS = 1,            /* c[0] * inner(u, v) dx */
   MPCX_KERNEL_ELASTICITY = 2,      /* inner(sigma(u), grad v) dx; c = {mu, lambda}; bs == gdim */
   MPCX_KERNEL_SOURCE = 3,          /* c[0] * inner(f, v) dx (linear form); w = f at the cell dofs */
-  MPCX_KERNEL_LAPLACE_VARCOEF = 4  /* c[0] * w * inner(grad u, grad v) dx; w scalar, same element */
+  MPCX_KERNEL_LAPLACE_VARCOEF = 4, /* c[0] * w * inner(grad u, grad v) dx; w scalar, same element */
+  MPCX_KERNEL_DIV_TEST = 5,        /* c[0] * inner(p, div v) dx; test = vector element (bs == gdim), trial = scalar */
+  MPCX_KERNEL_DIV_TRIAL = 6        /* c[0] * inner(div u, q) dx; test = scalar element, trial = vector (bs1 == gdim) */
 } mpcx_kernel;
 
 /* Tabulated element (what FFCx bakes into the generated kernel). */
@@ -68,6 +70,13 @@ typedef struct mpcx_tables
    * nfacets == 0 for cell integrals. */
   int32_t nfacets;
   const double* facet_tangents;
+  /* rectangular forms -- test and trial ELEMENTS differ (dofs[2], bs[2], num_dofs[2] of modify_mpc_cell,
+   * cpp/assemble_matrix.cpp:99-117; python/tests/test_rectangular_assembly.py:83-86): nd / bs / phi / dphi above
+   * describe the test element, nd1 / bs1 / phi1 / dphi1 the trial element at the same quadrature points.
+   * nd1 == 0: one element on both sides. */
+  int32_t nd1, bs1;
+  const double* phi1;  /* [nq][nd1] */
+  const double* dphi1; /* [nq][tdim][nd1] */
 } mpcx_tables;
 
 /* Geometry: mesh.geometry().x() / dofmaps().front() (cpp/assemble_matrix.cpp:465-470).

@@ -42,7 +42,9 @@ enum
   K_MASS = 1,
   K_ELASTICITY = 2,
   K_SOURCE = 3,
-  K_LAPLACE_VARCOEF = 4
+  K_LAPLACE_VARCOEF = 4,
+  K_DIV_TEST = 5,  /* c0 * inner(p, div v) dx: test = vector element, trial = scalar element */
+  K_DIV_TRIAL = 6  /* c0 * inner(div u, q) dx: test = scalar element, trial = vector element */
 };
 
 /* Tabulated element: the tables an FFCx kernel has baked into its source. */
@@ -57,6 +59,11 @@ typedef struct
    * tangents of the reference facet map, [nfacets][tdim-1][tdim].  nfacets == 0 for cell integrals. */
   int32_t nfacets;
   const double* ftan;
+  /* rectangular forms (test and trial elements differ; dofs[2] / bs[2] / num_dofs[2] of modify_mpc_cell,
+   * cpp/assemble_matrix.cpp:99-117): the trial element at the same quadrature points; nd1 == 0: same element. */
+  int32_t nd1, bs1;
+  const double* phi1;  /* [nq][nd1] */
+  const double* dphi1; /* [nq][tdim][nd1] */
 } orc_tables;
 
 /* The tables of one entity: a cell (e == NULL) or local facet e[0] of a cell -- the entity_local_index argument of
@@ -313,6 +320,50 @@ static void k_source(double* b, const double* w, const double* c,
   }
 }
 
+/* The off-diagonal blocks of a Taylor-Hood Stokes system (python/tests/test_rectangular_assembly.py:83-86:
+ * a01 = -inner(p, div(v)) dx, a10 = -inner(div(u), q) dx).  V = vector element (nv scalar basis functions x gdim
+ * components, interleaved), Q = scalar element (ns basis functions); A_e row-major [n0][n1] as the UFCx ABI has it. */
+static void div_coupling(double* A, const double* c, const double* X, const orc_tables* t, int v_is_test)
+{
+  const int nv = v_is_test ? t->nd : t->nd1, ns = v_is_test ? t->nd1 : t->nd, gd = t->gdim, td = t->tdim;
+  const int n1 = v_is_test ? ns : nv * gd;
+  double K[9], detJ = 0, g[3 * 64];
+  for (int q = 0; q < t->nq; ++q)
+  {
+    if (jacobian(t, q, X, K, &detJ)) return;
+    const double* dphv = v_is_test ? t->dphi + (size_t)q * td * nv : t->dphi1 + (size_t)q * td * nv;
+    const double* phs = v_is_test ? t->phi1 + (size_t)q * ns : t->phi + (size_t)q * ns;
+    for (int i = 0; i < nv; ++i)
+      for (int k = 0; k < gd; ++k)
+      {
+        double sum = 0;
+        for (int a = 0; a < td; ++a) sum += K[a * 3 + k] * dphv[a * nv + i];
+        g[i * 3 + k] = sum;
+      }
+    const double s = c[0] * t->weights[q] * fabs(detJ);
+    for (int i = 0; i < nv; ++i)
+      for (int a = 0; a < gd; ++a)
+        for (int j = 0; j < ns; ++j)
+        {
+          const double v = s * phs[j] * g[i * 3 + a];
+          if (v_is_test) A[(i * gd + a) * n1 + j] += v;
+          else A[j * n1 + i * gd + a] += v;
+        }
+  }
+}
+static void k_div_test(double* A, const double* w, const double* c, const double* X, const int* e, const uint8_t* p,
+                       void* cd)
+{
+  (void)w; (void)p; (void)e;
+  div_coupling(A, c, X, (const orc_tables*)cd, 1);
+}
+static void k_div_trial(double* A, const double* w, const double* c, const double* X, const int* e, const uint8_t* p,
+                        void* cd)
+{
+  (void)w; (void)p; (void)e;
+  div_coupling(A, c, X, (const orc_tables*)cd, 0);
+}
+
 static ufcx_kernel pick_kernel(int id)
 {
   switch (id)
@@ -322,6 +373,8 @@ static ufcx_kernel pick_kernel(int id)
   case K_ELASTICITY: return k_elasticity;
   case K_SOURCE: return k_source;
   case K_LAPLACE_VARCOEF: return k_laplace_varcoef;
+  case K_DIV_TEST: return k_div_test;
+  case K_DIV_TRIAL: return k_div_trial;
   default: return NULL;
   }
 }

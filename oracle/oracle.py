@@ -43,7 +43,8 @@ def build(force: bool = False, march: Optional[str] = None, out: Optional[str] =
 class _Tables(C.Structure):
     _fields_ = [("tdim", C.c_int32), ("gdim", C.c_int32), ("nd", C.c_int32), ("ng", C.c_int32),
                 ("nq", C.c_int32), ("bs", C.c_int32), ("weights", C.c_void_p), ("phi", C.c_void_p),
-                ("dphi", C.c_void_p), ("gdphi", C.c_void_p), ("nfacets", C.c_int32), ("ftan", C.c_void_p)]
+                ("dphi", C.c_void_p), ("gdphi", C.c_void_p), ("nfacets", C.c_int32), ("ftan", C.c_void_p),
+                ("nd1", C.c_int32), ("bs1", C.c_int32), ("phi1", C.c_void_p), ("dphi1", C.c_void_p)]
 
 
 class _Mpc(C.Structure):
@@ -86,23 +87,25 @@ def _p(a):
     return None if a is None else C.c_void_p(a.ctypes.data)
 
 
-def _tables(tab, bs):
+def _tables(tab, bs, bs1=0):
     return _Tables(tab.tdim, tab.gdim, tab.nd, tab.ng, tab.nq, bs, _a(tab.weights), _a(tab.phi), _a(tab.dphi),
-                   _a(tab.gdphi), tab.nfacets, _a(tab.ftan) if tab.nfacets else None)
+                   _a(tab.gdphi), tab.nfacets, _a(tab.ftan) if tab.nfacets else None,
+                   tab.nd1, bs1 if tab.nd1 else 0, _a(tab.phi1) if tab.nd1 else None, _a(tab.dphi1) if tab.nd1 else None)
 
 
-def tabulate(kernel: int, tab, bs: int, X: np.ndarray, w=None, c=(1.0,)) -> np.ndarray:
-    """One element tensor from the oracle kernels."""
+def tabulate(kernel: int, tab, bs: int, X: np.ndarray, w=None, c=(1.0,), bs1: int = 0) -> np.ndarray:
+    """One element tensor from the oracle kernels (``bs1``: block size of the trial element of a rectangular form)."""
     n = tab.nd * bs
-    size = n if kernel == 3 else n * n
+    n1 = tab.nd1 * bs1 if tab.nd1 else n
+    size = n if kernel == 3 else n * n1
     out = np.zeros(size)
     X = np.ascontiguousarray(X, dtype=np.float64)
     w = None if w is None else np.ascontiguousarray(w, dtype=np.float64)
     c = np.ascontiguousarray(c, dtype=np.float64)
-    t = _tables(tab, bs)
+    t = _tables(tab, bs, bs1)
     rc = lib().orc_tabulate(int(kernel), C.byref(t), _p(w), _p(c), _p(X), _p(out), size)
     assert rc == 0, rc
-    return out if kernel == 3 else out.reshape(n, n)
+    return out if kernel == 3 else out.reshape(n, n1)
 
 
 class OracleMPC:
@@ -216,7 +219,7 @@ def _pack_coefficients(form, it, cells, n, libpath=None):
 
 def _integral_args(form, it, libpath=None):
     tab = form.tables(it)
-    t = _tables(tab, form.function_spaces[0].bs)
+    t = _tables(tab, form.function_spaces[0].bs, form.function_spaces[-1].bs)
     cells = it.cells
     n = form.mesh.num_cells_local if cells is None else len(cells)
     w, cstride = _pack_coefficients(form, it, cells, n, libpath)
