@@ -57,6 +57,10 @@ namespace
 #define MPCX_CT_RUNGAP 16
 #endif
 #define MPCX_CT_MAXRUNS 2048
+// 1: bank-aware placement of the sources of every matrix record (see k_ct_build)
+#ifndef MPCX_CT_BANKOPT
+#define MPCX_CT_BANKOPT 1
+#endif
 // staging positions per tile above which the run gap is halved (see k_ct_build)
 #ifndef MPCX_CT_STAGECAP
 #define MPCX_CT_STAGECAP 3200
@@ -519,6 +523,131 @@ k_ct_build(int pass, const int* __restrict__ order, long long n_bulk, const int*
     if (vec) dest_k[doff + p] = (int)dkey[d];  // row dof: lets the kernel stage per-row data once per tile
   }
   __syncthreads();
+  // ---- bank-aware order of the sources of every record (matrix plans).  The i-th source of the record held by lane l
+  // of group g lives in slot gbase[g] + 33 i + l, i.e. in 8-byte bank (gbase[g] + l + i) mod 16; WHICH contributing cell
+  // gets which i is free.  The cell threads of one half-warp store element entry `si` with one STS.64: 16 slots that
+  // should fall into 16 different banks (random placement costs ~3 wavefronts instead of 1: 44 % of all shared-memory
+  // wavefronts of the fused kernel were bank conflicts, profiles/r02_a).  Deterministic coloured greedy: the records
+  // of one colour pick, source by source, the free position whose bank is least loaded in the table
+  // T[half-warp][si][bank] (read-only during the pick), then all of them book their picks; a second sweep re-picks
+  // every record against the complete table.
+  const bool opt = !vec && ok && (MPCX_CT_BANKOPT != 0);
+  unsigned short* srcv = dj;                                    // [N] (cell, entry) of the source at sorted position s
+  unsigned char* isrc = reinterpret_cast<unsigned char*>(sp2);  // [N] position picked for the source at sorted position s
+  unsigned* T32 = reinterpret_cast<unsigned*>(pcnt);            // [NT/16][NS][16] byte counters
+  if (opt)
+  {
+    constexpr int NVc = NGc;
+    const int NSo = sym ? NVc * (NVc + 1) / 2 : NEc;
+    const int twords = (NT / 16) * NSo * 4;
+#pragma unroll
+    for (int e = 0; e < NEc; ++e) srcv[cl * NEc + e] = vals[e];
+    for (int i = cl; i < twords; i += NT) T32[i] = 0u;
+    __syncthreads();
+    auto slot_group = [&](unsigned short sv) {
+      const int cidx = sv / NEc, ent = sv - cidx * NEc;
+      int si = ent;
+      if (sym)
+      {
+        int i = ent / NVc, j = ent - i * NVc;
+        if (i > j) { const int tmp = i; i = j; j = tmp; }  // the cell stores the upper-triangular twin
+        si = i * NVc - (i * (i - 1)) / 2 + (j - i);
+      }
+      return ((cidx >> 4) * NSo + si) * 16;
+    };
+    const unsigned char* T8 = reinterpret_cast<const unsigned char*>(T32);
+    constexpr int NCOL = 8, NSWEEP = 2;
+    for (int round = 0; round < NCOL * NSWEEP; ++round)
+    {
+      const unsigned col = (unsigned)(round % NCOL);
+      const bool refine = round >= NCOL;
+      // pick (T read-only), after taking the record's own entries out of the table in the refinement sweep
+      for (int pass2 = 0; pass2 < 3; ++pass2)
+      {
+        // pass2 0: un-book (refinement only), 1: pick, 2: book
+        if (pass2 == 0 && !refine) continue;
+        for (int d = cl; d < total; d += NT)
+        {
+          if (rcnt[d] == 0 || ((((unsigned)d * 2654435761u) >> 29) & (NCOL - 1)) != col) continue;
+          const int s0 = dstart[d], cnt = (int)dstart[d + 1] - s0;
+          const int p = npos[d];
+          const int B = gbase[p >> 5] + (p & 31);
+          if (pass2 == 1)
+          {
+            unsigned used = 0u;
+            for (int k = 0; k < cnt; ++k)
+            {
+              int best = k;
+              if (cnt <= 32)
+              {
+                const int gi = slot_group(srcv[s0 + k]);
+                int bestc = 1 << 30;
+                for (int j = 0; j < cnt; ++j)
+                {
+                  const int i = k + j < cnt ? k + j : k + j - cnt;  // ties keep the cell order
+                  if ((used >> i) & 1u) continue;
+                  const int c = T8[gi + ((B + i) & 15)];
+                  if (c < bestc) { bestc = c; best = i; }
+                }
+                used |= 1u << best;
+              }
+              isrc[s0 + k] = (unsigned char)best;
+            }
+          }
+          else
+          {
+            for (int k = 0; k < cnt; ++k)
+            {
+              const int idx = slot_group(srcv[s0 + k]) + ((B + (int)isrc[s0 + k]) & 15);
+              const unsigned one = 1u << (8 * (idx & 3));
+              if (pass2 == 2) atomicAdd(&T32[idx >> 2], one); else atomicSub(&T32[idx >> 2], one);
+            }
+          }
+        }
+        __syncthreads();
+      }
+    }
+  }
+  // Vector plans: the fused kernel GATHERS through the inverse slot map -- the thread of row record (group g, lane l)
+  // reads, at step i, the 16-byte pair of the cell in its slot i; a quarter-warp is conflict-free when its 8 cells
+  // differ mod 8.  Latin pattern, record by record: step i of lane l prefers a cell with (cell mod 8) == (l + i) mod 8.
+  const bool optv = vec && ok && (MPCX_CT_BANKOPT != 0);
+  if (optv)
+  {
+#pragma unroll
+    for (int e = 0; e < NEc; ++e) srcv[cl * NEc + e] = vals[e];
+    __syncthreads();
+    for (int d = cl; d < total; d += NT)
+    {
+      const int s0 = dstart[d], cnt = (int)dstart[d + 1] - s0, l = npos[d] & 7;
+      if (cnt > 32)
+      {
+        for (int k = 0; k < cnt; ++k) isrc[s0 + k] = (unsigned char)k;
+        continue;
+      }
+      unsigned used_src = 0u, used_pos = 0u;
+      for (int i = 0; i < cnt; ++i)
+      {
+        const int want = (l + i) & 7;
+        for (int k = 0; k < cnt; ++k)
+          if (!((used_src >> k) & 1u) && ((srcv[s0 + k] / NEc) & 7) == want)
+          {
+            used_src |= 1u << k; used_pos |= 1u << i;
+            isrc[s0 + k] = (unsigned char)i;
+            break;
+          }
+      }
+      int i = 0;
+      for (int k = 0; k < cnt; ++k)
+      {
+        if ((used_src >> k) & 1u) continue;
+        while ((used_pos >> i) & 1u) ++i;
+        isrc[s0 + k] = (unsigned char)i;
+        used_pos |= 1u << i;
+      }
+    }
+    __syncthreads();
+  }
   {
     constexpr int NVc = NGc;                                  // P1: entries form an NVc x NVc matrix
     const int NS = sym ? NVc * (NVc + 1) / 2 : NEc;           // slots per cell record
@@ -539,7 +668,9 @@ k_ct_build(int pass, const int* __restrict__ order, long long n_bulk, const int*
       uint16_t sl = (uint16_t)slots;  // bc-zeroed entry: stored to the spare slot nobody reads
       if (valid)
       {
-        const int i_src = cl * NEc + e - (int)dstart[d];  // i-th source of dest d (same cell order in the transposed dest)
+        // i-th source of dest d (same cell order in the transposed dest, whose record holds the picked positions)
+        const int rank = cl * NEc + e - (int)dstart[d];
+        const int i_src = (opt || optv) ? (int)isrc[(int)dstart[part[d]] + rank] : rank;
         const int p = npos[part[d]];
         sl = (uint16_t)(gbase[p >> 5] + MPCX_CT_GSTRIDE * i_src + (p & 31));
         if (vec)

@@ -30,23 +30,9 @@ struct FusedSmem
   int* dkv;
   uint8_t* dcntv;
   uint16_t *vinc, *cnode, *cslot, *crow;
+  int* hb;  // ring of 3 tile headers (matrix plan: 12 ints, vector plan: 12 ints), filled two tiles ahead
   unsigned long long *barC, *barR;
 };
-
-struct VHdr  // what the vector records of one tile need from the vector plan's header
-{
-  int nd, slots;
-  long long dest_off, slot_off;
-};
-__device__ __forceinline__ VHdr load_vhdr(const int4* __restrict__ hdr, int t)
-{
-  const int4 a = __ldg(hdr + 3 * (long long)t), b = __ldg(hdr + 3 * (long long)t + 1), c = __ldg(hdr + 3 * (long long)t + 2);
-  VHdr h;
-  h.nd = a.z; h.slots = b.y;
-  h.dest_off = (long long)(unsigned)b.z | ((long long)b.w << 32);
-  h.slot_off = (long long)(unsigned)c.z | ((long long)c.w << 32);
-  return h;
-}
 
 __host__ __device__ inline size_t fused_smem_bytes(const TilePlanD& P, const TilePlanD& Q, int nv, int ns, bool sym)
 {
@@ -57,7 +43,7 @@ __host__ __device__ inline size_t fused_smem_bytes(const TilePlanD& P, const Til
        + al((size_t)P.max_dests);
   b += al(4 * (size_t)(Q.max_dests / 32)) + al(4 * (size_t)Q.max_dests) + al((size_t)Q.max_dests);
   b += al(2 * (size_t)(Q.max_slots + 9)) + 2 * al(2 * (size_t)P.C * nv) + al(2 * (size_t)P.C * ns);
-  return b + 32;
+  return b + 32 + 3 * 24 * sizeof(int);
 }
 
 __device__ __forceinline__ FusedSmem fused_carve(unsigned char* sp, const TilePlanD& P, const TilePlanD& Q, int nv, int ns,
@@ -83,6 +69,7 @@ __device__ __forceinline__ FusedSmem fused_carve(unsigned char* sp, const TilePl
   S.cnode = reinterpret_cast<uint16_t*>(sp); sp += al(2 * (size_t)P.C * nv);
   S.cslot = reinterpret_cast<uint16_t*>(sp); sp += al(2 * (size_t)P.C * ns);
   S.crow = reinterpret_cast<uint16_t*>(sp); sp += al(2 * (size_t)P.C * nv);
+  S.hb = reinterpret_cast<int*>(sp); sp += 3 * 24 * sizeof(int);
   S.barC = reinterpret_cast<unsigned long long*>(sp);
   S.barR = S.barC + 1;
   S.R.bar = S.barR;
@@ -101,24 +88,40 @@ __device__ __forceinline__ void fused_tma_cells(const FusedSmem& S, const TilePl
 }
 
 // vector records of one tile: counts, group info, row dofs and the inverse slot map (second arrival on barR)
-__device__ __forceinline__ void fused_tma_vrecords(const FusedSmem& S, const TilePlanD& Q, const VHdr& h)
+__device__ __forceinline__ long long hdr64(const int* h, int w) { return (long long)(unsigned)h[w] | ((long long)h[w + 1] << 32); }
+
+__device__ __forceinline__ void fused_tma_vrecords(const FusedSmem& S, const TilePlanD& Q, const int* hv)
 {
-  const unsigned nd16 = (unsigned)((h.nd + 15) & ~15), ng4 = (unsigned)((((h.nd + 31) >> 5) + 3) & ~3);
-  const unsigned ns8 = nd16 ? (unsigned)((h.slots + 1 + 7) & ~7) : 0u;
+  const int nd = hv[2], slots = hv[5];
+  const long long dest_off = hdr64(hv, 6), slot_off = hdr64(hv, 10);
+  const unsigned nd16 = (unsigned)((nd + 15) & ~15), ng4 = (unsigned)((((nd + 31) >> 5) + 3) & ~3);
+  const unsigned ns8 = nd16 ? (unsigned)((slots + 1 + 7) & ~7) : 0u;
   mbar_expect_tx(S.barR, nd16 * 5 + ng4 * 4 + ns8 * 2);
   if (!nd16) return;
-  tma_load_1d(S.dcntv, Q.dest_cnt + h.dest_off, nd16, S.barR);
-  tma_load_1d(S.giv, Q.ginfo + (h.dest_off >> 5), ng4 * 4, S.barR);
-  tma_load_1d(S.dkv, Q.dest_k + h.dest_off, nd16 * 4, S.barR);
-  tma_load_1d(S.vinc, Q.slot_cell + h.slot_off, ns8 * 2, S.barR);
+  tma_load_1d(S.dcntv, Q.dest_cnt + dest_off, nd16, S.barR);
+  tma_load_1d(S.giv, Q.ginfo + (dest_off >> 5), ng4 * 4, S.barR);
+  tma_load_1d(S.dkv, Q.dest_k + dest_off, nd16 * 4, S.barR);
+  tma_load_1d(S.vinc, Q.slot_cell + slot_off, ns8 * 2, S.barR);
+}
+
+// matrix records of one tile from its header words in shared memory (first arrival on barR)
+template <bool SYM>
+__device__ __forceinline__ void fused_tma_mrecords(const FusedSmem& S, const TilePlanD& P, const int* hm)
+{
+  TileHdr h;
+  h.node_off = hm[0]; h.nn = hm[1]; h.nd = hm[2]; h.nr = hm[3]; h.stage = hm[4];
+  h.dest_off = hdr64(hm, 6); h.run_off = hdr64(hm, 8);
+  tma_records<false, SYM>(S.R, P, h);
 }
 
 // P: matrix plan, Q: vector plan of the same tiling.  ina: bilinear integral (Laplace / mass / variable-coefficient
-// Laplace), inL: the P1 source term with its coefficient in the test space.  Persistent CTAs, 2 per SM:
-//   top      vertex id / row dof of tile t+1 -> registers
+// Laplace), inL: the P1 source term with its coefficient in the test space.  Persistent CTAs, 2 per SM.  Tile headers
+// travel through a 3-slot ring in shared memory, loaded two tiles ahead by 24 threads (keeping them in registers of
+// every thread cost spills whose reloads missed the small L1 left beside 2 x 100 KB of shared memory).
+//   top      header words of tile t+2 -> register (24 threads); vertex id / row dof of tile t+1 -> registers
 //   phase 1  wait C(t); thread = cell: geometry once, element matrix -> matrix slots, (s, s F) -> cellv; then
-//            x[vertex id], f[row dof] of t+1 -> registers; warp 0 waits until the reductions of t-1 have read the
-//            staging buffer
+//            x[vertex id], f[row dof] of t+1 -> registers; header words -> ring; warp 0 waits until the reductions of
+//            t-1 have read the staging buffer
 //   sync 1   TMA C(t+1); zero the staging buffer
 //   sync 1b
 //   phase 2  wait R(t); thread = record: matrix column sum -> staging position(s); row record: gather the cell pairs
@@ -133,35 +136,60 @@ k_ptile_system_p1(TilePlanD P, TilePlanD Q, int nt, IntD ina, IntD inL, MeshD me
   const FusedSmem S = fused_carve(tile_smem, P, Q, NV, NS, SYM);
   const int tid = threadIdx.x;
   const bool issuer = tid < 32;
+  const int G = gridDim.x;
   int t = blockIdx.x;
   if (t >= nt) return;
-  if (tid == 0) { mbar_init(S.barC, 1); mbar_init(S.barR, 2); }
-  __syncthreads();
-  TileHdr h = load_hdr(P.hdr, t), hn = h;
-  VHdr hv = load_vhdr(Q.hdr, t), hvn = hv;
-  if (tid == 0)
+  // header loader threads: word w of the matrix (w < 12) or vector (w >= 12) header
+  const int hw_i = tid - 32;
+  const bool loader = hw_i >= 0 && hw_i < 24;
+  const int* hsrc = loader ? reinterpret_cast<const int*>(hw_i < 12 ? P.hdr : Q.hdr) + (hw_i < 12 ? hw_i : hw_i - 12) : nullptr;
+  if (tid == 0) { mbar_init(S.barC, 1); mbar_init(S.barR, 2); S.cellv[NT] = make_double2(0.0, 0.0); }
+  if (loader)
   {
-    tma_records<false, SYM>(S.R, P, h);
-    fused_tma_vrecords(S, Q, hv);
-    fused_tma_cells(S, P, Q, t, NV, NS);
+    S.hb[hw_i] = __ldg(hsrc + 12 * (long long)t);
+    if (t + G < nt) S.hb[24 + hw_i] = __ldg(hsrc + 12 * (long long)(t + G));
   }
-  for (int i = tid; i < h.nn; i += NT)
-    load_vertex(mesh, __ldg(P.node_ids + h.node_off + i), S.Xs[3 * i], S.Xs[3 * i + 1], S.Xs[3 * i + 2]);
-  for (int k = tid; k < hv.nd; k += NT) S.fs[k] = __ldg(inL.wnodal + __ldg(Q.dest_k + hv.dest_off + k));
-  int tn = t + gridDim.x;
-  bool has_next = tn < nt;
-  if (has_next) { hn = load_hdr(P.hdr, tn); hvn = load_vhdr(Q.hdr, tn); }
   __syncthreads();
+  {
+    const int* hm = S.hb;
+    const int* hv = S.hb + 12;
+    if (tid == 0)
+    {
+      fused_tma_mrecords<SYM>(S, P, hm);
+      fused_tma_vrecords(S, Q, hv);
+      fused_tma_cells(S, P, Q, t, NV, NS);
+    }
+    const int nn = hm[1], node_off = hm[0], ndv = hv[2];
+    const long long doffv = hdr64(hv, 6);
+    for (int i = tid; i < nn; i += NT)
+      load_vertex(mesh, __ldg(P.node_ids + node_off + i), S.Xs[3 * i], S.Xs[3 * i + 1], S.Xs[3 * i + 2]);
+    for (int k = tid; k < ndv; k += NT) S.fs[k] = __ldg(inL.wnodal + __ldg(Q.dest_k + doffv + k));
+  }
   const double cL = inL.c[0] * (1.0 / double((TD + 1) * (TD + 2)));
-  double fcur = NT - 1 - tid < hv.nd ? __ldg(inL.wnodal + __ldg(Q.dest_k + hv.dest_off + (NT - 1 - tid))) : 0.0;
-  if (tid == 0) S.cellv[NT] = make_double2(0.0, 0.0);  // the pair read by lanes past their count
+  // thread NT-1-k serves row record k and carries f of that row in a register
+  double fcur = 0.0;
+  {
+    const int* hv = S.hb + 12;
+    if (NT - 1 - tid < hv[2]) fcur = __ldg(inL.wnodal + __ldg(Q.dest_k + hdr64(hv, 6) + (NT - 1 - tid)));
+  }
+  __syncthreads();
+  int tn = t + G;
   for (unsigned it = 0;; ++it)
   {
+    const bool has_next = tn < nt;
+    const int* hm = S.hb + 24 * (it % 3);          // this tile
+    const int* hmn = S.hb + 24 * ((it + 1) % 3);   // next tile of this CTA
     const long long first = (long long)t * NT;
     const int nc_t = (int)((P.n_bulk - first) < NT ? (P.n_bulk - first) : NT);
+    int hword = 0;
+    const bool load2 = loader && tn + G < nt;
+    if (load2) hword = __ldg(hsrc + 12 * (long long)(tn + G));
     int nid = -1, fid = -1;
-    if (has_next && tid < hn.nn) nid = __ldg(P.node_ids + hn.node_off + tid);
-    if (has_next && NT - 1 - tid < hvn.nd) fid = __ldg(Q.dest_k + hvn.dest_off + (NT - 1 - tid));  // row of this thread's record
+    if (has_next)
+    {
+      if (tid < hmn[1]) nid = __ldg(P.node_ids + hmn[0] + tid);
+      if (NT - 1 - tid < hmn[12 + 2]) fid = __ldg(Q.dest_k + hdr64(hmn + 12, 6) + (NT - 1 - tid));
+    }
 
     // phase 1: thread = cell
     mbar_wait(S.barC, it & 1);
@@ -176,13 +204,13 @@ k_ptile_system_p1(TilePlanD P, TilePlanD Q, int nt, IntD ina, IntD inL, MeshD me
         X[v][1] = S.Xs[3 * l + 1];
         X[v][2] = TD == 3 ? S.Xs[3 * l + 2] : 0.0;
       }
-      P1Geom<TD> G;
-      p1_geometry<TD>(X, G);
+      P1Geom<TD> Gm;
+      p1_geometry<TD>(X, Gm);
       {
         double F = 0.0;
 #pragma unroll
         for (int v = 0; v < NV; ++v) F += S.fs[S.crow[tid * NV + v]];
-        const double sc = cL * G.vol;
+        const double sc = cL * Gm.vol;
         S.cellv[tid] = make_double2(sc, sc * F);
       }
       double w[NV], Ae[NV][NV];
@@ -191,7 +219,7 @@ k_ptile_system_p1(TilePlanD P, TilePlanD Q, int nt, IntD ina, IntD inL, MeshD me
         const long long index = __ldg(P.cell_pos + first + tid);
         p1_load_w<TD>(ina, index, ina.cells ? __ldg(ina.cells + index) : (int)index, w);
       }
-      p1_element<TD>(ina.kernel, G, ina.c, w, Ae);
+      p1_element<TD>(ina.kernel, Gm, ina.c, w, Ae);
       uint16_t slot[NS];
       if (NS % 2 == 0)
       {
@@ -217,66 +245,79 @@ k_ptile_system_p1(TilePlanD P, TilePlanD Q, int nt, IntD ina, IntD inL, MeshD me
     double xg0 = 0.0, xg1 = 0.0, xg2 = 0.0, fg = 0.0;
     if (nid >= 0) load_vertex(mesh, nid, xg0, xg1, xg2);
     if (fid >= 0) fg = __ldg(inL.wnodal + fid);
+    if (load2) S.hb[24 * ((it + 2) % 3) + hw_i] = hword;  // that slot held tile t-1's header: no reader left
     if (issuer) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");  // reductions of t-1 have read the staging buffer
     __syncthreads();  // 1: element buffers complete; cell records, Xs and the staging buffer are free
     if (tid == 0 && has_next) fused_tma_cells(S, P, Q, tn, NV, NS);
-    for (int i = tid; i < (h.stage >> 1); i += NT) reinterpret_cast<double2*>(S.stage)[i] = make_double2(0.0, 0.0);
+    {
+      const int half = hm[4] >> 1;
+      for (int i = tid; i < half; i += NT) reinterpret_cast<double2*>(S.stage)[i] = make_double2(0.0, 0.0);
+    }
     __syncthreads();  // 1b: staging buffer zeroed
 
     // phase 2: thread = record
     mbar_wait(S.barR, it & 1);
-    for (int k = tid; k < h.nd; k += NT)
     {
-      const double v = tile_record_sum(S.ebuf, S.R, k);
-      S.stage[S.R.spos[k]] = v;
-      if (SYM) S.stage[S.R.spos2[k]] = v;
+      const int nd = hm[2];
+      for (int k = tid; k < nd; k += NT)
+      {
+        const double v = tile_record_sum(S.ebuf, S.R, k);
+        S.stage[S.R.spos[k]] = v;
+        if (SYM) S.stage[S.R.spos2[k]] = v;
+      }
     }
     // row records go to the LAST threads (the first ones hold the heaviest matrix records: those are ordered by
-    // descending source count); thread NT-1-k carries f of row k in a register (fcur)
-    for (int k = NT - 1 - tid; k < hv.nd; k += NT)
+    // descending source count)
     {
-      const unsigned g = S.giv[k >> 5];
-      const uint16_t* e = S.vinc + (g & 0xffffu) + (k & 31);
-      const int cnt = S.dcntv[k];
-      double s1 = 0.0, s2 = 0.0;
-#pragma unroll 1
-      for (int i = 0; i < cnt; i += 4, e += 4 * MPCX_CT_GSTRIDE)
+      const int ndv = hm[12 + 2];
+      for (int k = NT - 1 - tid; k < ndv; k += NT)
       {
-        // four independent index -> pair loads in flight; lanes past their count read the zero pair at cellv[NT]
-        const int c0 = e[0], c1 = i + 1 < cnt ? (int)e[MPCX_CT_GSTRIDE] : NT, c2 = i + 2 < cnt ? (int)e[2 * MPCX_CT_GSTRIDE] : NT,
-                  c3 = i + 3 < cnt ? (int)e[3 * MPCX_CT_GSTRIDE] : NT;
-        const double2 v0 = S.cellv[c0], v1 = S.cellv[c1], v2 = S.cellv[c2], v3 = S.cellv[c3];
-        s1 += (v0.x + v1.x) + (v2.x + v3.x);
-        s2 += (v0.y + v1.y) + (v2.y + v3.y);
+        const unsigned g = S.giv[k >> 5];
+        const uint16_t* e = S.vinc + (g & 0xffffu) + (k & 31);
+        const int cnt = S.dcntv[k];
+        double s1 = 0.0, s2 = 0.0;
+#pragma unroll 1
+        for (int i = 0; i < cnt; i += 4, e += 4 * MPCX_CT_GSTRIDE)
+        {
+          // four independent index -> pair loads in flight; lanes past their count read the zero pair at cellv[NT]
+          const int c0 = e[0], c1 = i + 1 < cnt ? (int)e[MPCX_CT_GSTRIDE] : NT, c2 = i + 2 < cnt ? (int)e[2 * MPCX_CT_GSTRIDE] : NT,
+                    c3 = i + 3 < cnt ? (int)e[3 * MPCX_CT_GSTRIDE] : NT;
+          const double2 v0 = S.cellv[c0], v1 = S.cellv[c1], v2 = S.cellv[c2], v3 = S.cellv[c3];
+          s1 += (v0.x + v1.x) + (v2.x + v3.x);
+          s2 += (v0.y + v1.y) + (v2.y + v3.y);
+        }
+        const int row = S.dkv[k];
+        atomicAdd(b + row, (k < NT ? fcur : __ldg(inL.wnodal + row)) * s1 + s2);
       }
-      const int row = S.dkv[k];
-      atomicAdd(b + row, (k < NT ? fcur : __ldg(inL.wnodal + row)) * s1 + s2);
     }
     if (nid >= 0) { S.Xs[3 * tid] = xg0; S.Xs[3 * tid + 1] = xg1; S.Xs[3 * tid + 2] = xg2; }
     if (fid >= 0) S.fs[NT - 1 - tid] = fg;
     if (has_next)
     {
-      for (int i = tid + NT; i < hn.nn; i += NT)
-        load_vertex(mesh, __ldg(P.node_ids + hn.node_off + i), S.Xs[3 * i], S.Xs[3 * i + 1], S.Xs[3 * i + 2]);
-      for (int k = tid + NT; k < hvn.nd; k += NT) S.fs[k] = __ldg(inL.wnodal + __ldg(Q.dest_k + hvn.dest_off + k));
+      const int nn = hmn[1], ndvn = hmn[12 + 2];
+      if (nn > NT)  // a tile with more vertices than threads (never on simplicial meshes)
+        for (int i = tid + NT; i < nn; i += NT)
+          load_vertex(mesh, __ldg(P.node_ids + hmn[0] + i), S.Xs[3 * i], S.Xs[3 * i + 1], S.Xs[3 * i + 2]);
+      if (ndvn > NT)
+        for (int k = tid; k < ndvn - NT; k += NT) S.fs[k + NT] = __ldg(inL.wnodal + __ldg(Q.dest_k + hdr64(hmn + 12, 6) + k + NT));
     }
+    const int nr = hm[3];  // read before the barrier: the loader threads refill this ring slot during the next phase 1
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // staging writes -> visible to the copy engine
     __syncthreads();  // 2: staging buffer, next Xs / fs complete; element buffers and records free
 
     if (issuer)
     {
-      for (int r = tid; r < h.nr; r += 32)
+      for (int r = tid; r < nr; r += 32)
       {
         const int2 rr = S.R.runs[r];
         tma_reduce_add_f64(A.val + rr.x, S.stage + (rr.y & 0xffff), (unsigned)(rr.y >> 16) * 8u);
       }
       asm volatile("cp.async.bulk.commit_group;" ::: "memory");
       __syncwarp();  // every lane has read its runs: the record buffers may be refilled
-      if (tid == 0 && has_next) { tma_records<false, SYM>(S.R, P, hn); fused_tma_vrecords(S, Q, hvn); }
+      if (tid == 0 && has_next) { fused_tma_mrecords<SYM>(S, P, hmn); fused_tma_vrecords(S, Q, hmn + 12); }
     }
     if (!has_next) break;
-    h = hn; hv = hvn; t = tn; tn += gridDim.x; has_next = tn < nt; fcur = fg;
-    if (has_next) { hn = load_hdr(P.hdr, tn); hvn = load_vhdr(Q.hdr, tn); }
+    t = tn; tn += G; fcur = fg;
   }
   if (issuer) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");  // the staging buffer must outlive the reads
 }

@@ -221,6 +221,38 @@ def case_surface_robin_3d(n=3, degree=1):
     return Case(f"surface-robin3d-P{degree}", V, a, L, data, bcs, a_lift=a)
 
 
+@dataclasses.dataclass
+class StokesCase:
+    """Taylor-Hood blocks of python/tests/test_rectangular_assembly.py:25-199: P2 vector velocity x P1 pressure on a
+    rotated square, slip constraint on the (rotated) face x = 1, Dirichlet velocity on the face x = 0."""
+
+    V: fem.FunctionSpace
+    Q: fem.FunctionSpace
+    a: list  # [[a00, a01], [a10, None]]
+    L: list  # [L0, L1]
+    data_v: tuple
+    bcs: list
+
+
+def case_stokes_2d(n=4, theta=np.pi / 4, cell="triangle"):
+    mesh0 = gen.create_unit_square(n, n, cell)
+    V0 = gen.functionspace(mesh0, 2, 2)
+    X0 = V0.tabulate_dof_coordinates()
+    inlet = np.flatnonzero(np.isclose(X0[:, 0], 0.0))
+    slip_blocks = np.flatnonzero(np.isclose(X0[:, 0], 1.0))
+    mesh = gen.rotate_mesh(mesh0, theta, (0, 0, 1))
+    V = gen.functionspace(mesh, 2, 2)
+    Q = gen.functionspace(mesh, 1, 1)
+    bc_dofs = (inlet[:, None] * 2 + np.arange(2)[None, :]).reshape(-1).astype(np.int32)
+    bcs = [fem.DirichletBC(V, bc_dofs, np.array([0.3, -0.1]))]
+    normal = np.array([np.cos(theta), np.sin(theta)])
+    data_v = gen.slip_constraint(V, slip_blocks, normal, exclude_dofs=bc_dofs)
+    a = [[fem.laplace(V), fem.div_test(V, Q, -1.0)], [fem.div_trial(Q, V, -1.0), None]]
+    zero = fem.Function(Q)
+    L = [_source(V, _vec(_f2d, 2)), fem.source(Q, zero)]
+    return StokesCase(V, Q, a, L, data_v, bcs)
+
+
 ALL_CASES: dict = {}
 for _c in (
     lambda: case_general_2d("triangle", 1), lambda: case_general_2d("triangle", 2),
