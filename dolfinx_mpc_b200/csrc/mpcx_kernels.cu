@@ -14,6 +14,7 @@
 #include <stdio.h>
 #include <string.h>
 #include <stdlib.h>
+#include <dlfcn.h>
 
 #include <atomic>
 #include <mutex>
@@ -1790,6 +1791,133 @@ int mpcx_assemble_system_tiled_f64(const mpcx_integral* a_integral, const mpcx_i
     else k_vector_p1_source<2><<<nbv, 256, 0, s>>>(inL, md, dofmap->map, m.c2s_off, m, b, inL.slave_cells, inL.nslave_cells);
   }
   return cuda_check(cudaGetLastError(), "assemble_system_tiled launch");
+}
+
+// ---------------------------------------------------------------------- ghost-row reduce over NCCL
+// NCCL is bound at run time (dlopen of the libnccl.so.2 the process already uses -- PyTorch's -- or MPCX_NCCL_LIB), so
+// that the library loads on machines without NCCL; only the handful of entry points below are needed.
+struct mpcx_nccl_id { char internal[128]; };  // ncclUniqueId
+struct mpcx_comm { void* comm; int rank, world; };
+namespace
+{
+struct NcclApi
+{
+  void* lib = nullptr;
+  int (*GetUniqueId)(void*) = nullptr;
+  int (*CommInitRank)(void**, int, mpcx_nccl_id /* by value, as ncclCommInitRank takes it */, int) = nullptr;
+  int (*CommDestroy)(void*) = nullptr;
+  int (*GroupStart)() = nullptr;
+  int (*GroupEnd)() = nullptr;
+  int (*Send)(const void*, size_t, int, int, void*, cudaStream_t) = nullptr;
+  int (*Recv)(void*, size_t, int, int, void*, cudaStream_t) = nullptr;
+  const char* (*GetErrorString)(int) = nullptr;
+};
+NcclApi g_nccl;
+std::mutex g_nccl_mutex;
+}  // namespace
+namespace
+{
+int nccl_bind(const char* path)
+{
+  std::lock_guard<std::mutex> lk(g_nccl_mutex);
+  if (g_nccl.lib) return MPCX_OK;
+  const char* env = getenv("MPCX_NCCL_LIB");
+  void* h = nullptr;
+  if (path && path[0]) h = dlopen(path, RTLD_NOW | RTLD_GLOBAL);
+  if (!h && env && env[0]) h = dlopen(env, RTLD_NOW | RTLD_GLOBAL);
+  if (!h) h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_NOLOAD | RTLD_GLOBAL);
+  if (!h) h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+  if (!h) return fail(MPCX_ERR_UNSUPPORTED, "NCCL not found (libnccl.so.2): %s", dlerror());
+  NcclApi a;
+  a.lib = h;
+  a.GetUniqueId = (decltype(a.GetUniqueId))dlsym(h, "ncclGetUniqueId");
+  a.CommInitRank = (decltype(a.CommInitRank))dlsym(h, "ncclCommInitRank");
+  a.CommDestroy = (decltype(a.CommDestroy))dlsym(h, "ncclCommDestroy");
+  a.GroupStart = (decltype(a.GroupStart))dlsym(h, "ncclGroupStart");
+  a.GroupEnd = (decltype(a.GroupEnd))dlsym(h, "ncclGroupEnd");
+  a.Send = (decltype(a.Send))dlsym(h, "ncclSend");
+  a.Recv = (decltype(a.Recv))dlsym(h, "ncclRecv");
+  a.GetErrorString = (decltype(a.GetErrorString))dlsym(h, "ncclGetErrorString");
+  if (!a.GetUniqueId || !a.CommInitRank || !a.CommDestroy || !a.GroupStart || !a.GroupEnd || !a.Send || !a.Recv)
+    return fail(MPCX_ERR_UNSUPPORTED, "libnccl.so.2 lacks a required entry point");
+  g_nccl = a;
+  return MPCX_OK;
+}
+int nccl_check(int r, const char* where)
+{
+  if (r == 0) return MPCX_OK;
+  snprintf(g_err, sizeof(g_err), "NCCL error in %s: %s", where, g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "?");
+  return MPCX_ERR_CUDA;
+}
+}  // namespace
+
+int mpcx_nccl_load(const char* libnccl_path) { return nccl_bind(libnccl_path); }
+
+int mpcx_comm_unique_id(void* id128_out)
+{
+  if (!id128_out) return fail(MPCX_ERR_ARG, "null argument");
+  int rc = nccl_bind(nullptr);
+  if (rc) return rc;
+  return nccl_check(g_nccl.GetUniqueId(id128_out), "ncclGetUniqueId");
+}
+
+int mpcx_comm_create(const void* id128, int32_t rank, int32_t world, mpcx_comm** comm_out)
+{
+  if (!id128 || !comm_out || rank < 0 || rank >= world) return fail(MPCX_ERR_ARG, "bad communicator arguments");
+  int rc = nccl_bind(nullptr);
+  if (rc) return rc;
+  mpcx_nccl_id id;
+  memcpy(&id, id128, sizeof(id));
+  void* c = nullptr;
+  rc = nccl_check(g_nccl.CommInitRank(&c, world, id, rank), "ncclCommInitRank");
+  if (rc) return rc;
+  *comm_out = new mpcx_comm{c, rank, world};
+  return MPCX_OK;
+}
+
+void mpcx_comm_destroy(mpcx_comm* comm)
+{
+  if (!comm) return;
+  if (g_nccl.CommDestroy && comm->comm) g_nccl.CommDestroy(comm->comm);
+  delete comm;
+}
+
+int mpcx_ghost_reduce_f64(mpcx_comm* comm, double* values, const int64_t* send_idx, int64_t send_start,
+                          const int64_t* send_counts, const int64_t* recv_pos, const int64_t* recv_counts,
+                          double* send_buf, double* recv_buf, void* stream)
+{
+  if (!comm || !values || !send_counts || !recv_counts) return fail(MPCX_ERR_ARG, "null argument");
+  cudaStream_t s = (cudaStream_t)stream;
+  long long n_send = 0, n_recv = 0;
+  for (int r = 0; r < comm->world; ++r) { n_send += send_counts[r]; n_recv += recv_counts[r]; }
+  if ((n_send > 0 && send_idx && !send_buf) || (n_recv > 0 && (!recv_buf || !recv_pos))) return fail(MPCX_ERR_ARG, "missing buffers");
+  const double* src = values + send_start;
+  if (n_send > 0 && send_idx)
+  {
+    long long nb = (n_send + 255) / 256;
+    if (nb > 148LL * 32) nb = 148LL * 32;
+    MPCX_COUNT_LAUNCH(), k_gather<<<(unsigned)nb, 256, 0, s>>>(values, (const long long*)send_idx, n_send, send_buf);
+    src = send_buf;
+  }
+  int rc = nccl_check(g_nccl.GroupStart(), "ncclGroupStart");
+  if (rc) return rc;
+  long long os = 0, orv = 0;
+  for (int r = 0; r < comm->world && !rc; ++r)
+  {
+    if (send_counts[r] > 0) rc = nccl_check(g_nccl.Send(src + os, (size_t)send_counts[r], 8 /* ncclFloat64 */, r, comm->comm, s), "ncclSend");
+    if (!rc && recv_counts[r] > 0) rc = nccl_check(g_nccl.Recv(recv_buf + orv, (size_t)recv_counts[r], 8, r, comm->comm, s), "ncclRecv");
+    os += send_counts[r];
+    orv += recv_counts[r];
+  }
+  const int rc2 = nccl_check(g_nccl.GroupEnd(), "ncclGroupEnd");
+  if (rc || rc2) return rc ? rc : rc2;
+  if (n_recv > 0)
+  {
+    long long nb = (n_recv + 255) / 256;
+    if (nb > 148LL * 32) nb = 148LL * 32;
+    MPCX_COUNT_LAUNCH(), k_scatter_add<<<(unsigned)nb, 256, 0, s>>>(values, (const long long*)recv_pos, n_recv, recv_buf);
+  }
+  return cuda_check(cudaGetLastError(), "ghost_reduce launch");
 }
 
 int mpcx_pattern_create(const mpcx_dofmap* dofmap0, const mpcx_dofmap* dofmap1, int64_t num_cells,

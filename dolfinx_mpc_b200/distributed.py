@@ -237,8 +237,48 @@ def vector_plan(imap: IndexMap, bs: int, group=None):
 
 # ------------------------------------------------------------------ per-step exchange (device)
 
+_LIB_COMM = {}
+
+
+def lib_comm(group=None):
+    """The NCCL communicator of libmpcx for ``group`` (``mpcx_comm_create``): the unique id is made on rank 0 and
+    broadcast through ``torch.distributed``; NCCL itself is the library PyTorch already loaded.  None when the
+    process group is not NCCL (the gloo tests on the CPU)."""
+    if dist.get_backend(group) != "nccl":
+        return None
+    key = id(group)
+    if key not in _LIB_COMM:
+        from . import _lib
+
+        lib = _lib.load()
+        path = None
+        try:  # the NCCL build PyTorch ships with (same ABI as the one it talks to)
+            import glob
+            import os
+
+            import nvidia.nccl
+
+            hits = glob.glob(os.path.join(os.path.dirname(nvidia.nccl.__file__), "lib", "libnccl.so*"))
+            path = hits[0] if hits else None
+        except Exception:
+            path = None
+        _lib.check(lib.mpcx_nccl_load(path.encode() if path else None))
+        uid = (C.c_char * 128)()
+        if dist.get_rank(group) == 0:
+            _lib.check(lib.mpcx_comm_unique_id(uid))
+        box = [bytes(uid)]
+        dist.broadcast_object_list(box, src=dist.get_global_rank(group, 0) if group is not None else 0, group=group)
+        uid = (C.c_char * 128).from_buffer_copy(box[0])
+        comm = C.c_void_p()
+        _lib.check(lib.mpcx_comm_create(uid, dist.get_rank(group), dist.get_world_size(group), C.byref(comm)))
+        _LIB_COMM[key] = comm
+    return _LIB_COMM[key]
+
+
 class GhostExchange:
-    """One ``all_to_all_single`` of packed ghost values followed by an owner-side scatter-add kernel.
+    """Ghost values to their owners and added there, in ONE library call over NCCL (``mpcx_ghost_reduce_f64``: pack
+    kernel, grouped ncclSend / ncclRecv, scatter-add kernel on the caller's stream).  Without an NCCL process group
+    (gloo tests on the CPU) the same plan runs through ``all_to_all_single`` and two index primitives.
 
     ``send_idx`` / ``recv_pos`` live on the device.  When the ghost values to send are one contiguous slice of
     the source array (single owner, the slab case) the pack kernel is skipped and the slice is sent in place.
@@ -256,6 +296,12 @@ class GhostExchange:
         self.recv_pos = torch.from_numpy(np.asarray(plan["recv_pos"], dtype=np.int64)).to(device)
         self.send_buf = torch.empty(self.n_send, dtype=torch.float64, device=device)
         self.recv_buf = torch.empty(self.n_recv, dtype=torch.float64, device=device)
+        self.comm = None
+        if torch.device(device).type == "cuda" and dist.is_initialized():
+            self.comm = lib_comm(group)
+            world = dist.get_world_size(group)
+            self._sc = (C.c_int64 * world)(*self.send_counts)
+            self._rc = (C.c_int64 * world)(*self.recv_counts)
 
     # the two device primitives; tests on CPU substitute torch index ops for them
     def _gather(self, src: torch.Tensor, idx: torch.Tensor, out: torch.Tensor):
@@ -271,6 +317,15 @@ class GhostExchange:
                                                     _dev.stream_ptr()))
 
     def reduce(self, values: torch.Tensor):
+        if self.comm is not None:
+            from . import _lib, device as _dev
+
+            _lib.check(_lib.load().mpcx_ghost_reduce_f64(
+                self.comm, values.data_ptr(), None if self.contiguous else self.send_idx.data_ptr(),
+                self.send_start if self.contiguous else 0, self._sc, self.recv_pos.data_ptr() if self.n_recv else None,
+                self._rc, self.send_buf.data_ptr() if self.n_send else None,
+                self.recv_buf.data_ptr() if self.n_recv else None, _dev.stream_ptr()))
+            return
         if self.contiguous:
             send = values[self.send_start:self.send_start + self.n_send]
         else:

@@ -280,6 +280,24 @@ int mpcx_homogenize_f64(const mpcx_mpc* mpc, double* u, void* stream);
 int mpcx_gather_f64(const double* src, const int64_t* idx, int64_t n, double* dst, void* stream);
 int mpcx_scatter_add_f64(double* dst, const int64_t* idx, int64_t n, const double* src, void* stream);
 
+/* The exchange step of the distributed path in ONE call over NCCL (PETSc MatAssemblyBegin/End and
+ * VecGhostUpdate(ADD_VALUES, SCATTER_REVERSE) in the reference's callers, python/src/dolfinx_mpc/assemble_matrix.py:64,
+ * python/src/dolfinx_mpc/problem.py:566): pack the ghost values (values[send_idx[i]], ordered by destination rank; or
+ * the contiguous slice values[send_start ...] when send_idx == NULL -- ghost rows are numbered last), grouped
+ * ncclSend / ncclRecv with every peer that has a non-zero count, then values[recv_pos[i]] += received[i] at the owner.
+ * send_counts / recv_counts are HOST arrays of `world` entries; send_idx / recv_pos / buffers are device pointers.
+ * NCCL is bound at run time: mpcx_nccl_load(path) (NULL: the libnccl.so.2 already loaded in the process, else the
+ * default search path).  A communicator is created collectively from an id made on one rank (mpcx_comm_unique_id ->
+ * broadcast by the caller -> mpcx_comm_create on every rank). */
+typedef struct mpcx_comm mpcx_comm;
+int mpcx_nccl_load(const char* libnccl_path);
+int mpcx_comm_unique_id(void* id128_out);
+int mpcx_comm_create(const void* id128, int32_t rank, int32_t world, mpcx_comm** comm_out);
+void mpcx_comm_destroy(mpcx_comm* comm);
+int mpcx_ghost_reduce_f64(mpcx_comm* comm, double* values, const int64_t* send_idx, int64_t send_start,
+                          const int64_t* send_counts, const int64_t* recv_pos, const int64_t* recv_counts,
+                          double* send_buf, double* recv_buf, void* stream);
+
 /* Sparsity pattern with the MPC additions, on the HOST (cold path; replaces
  * create_sparsity_pattern, cpp/utils.h:381-496).  All pointers are host pointers.
  * The scalar CSR is returned in malloc'ed arrays released with mpcx_free_host. */
