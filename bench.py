@@ -360,6 +360,30 @@ def run_reference(args):
 
 # ------------------------------------------------------------------------------------------------ GPU arm
 
+def bind_to_gpu_numa_node(local_rank: int):
+    """Pin this rank's host threads (and with them the first-touch placement of its pinned staging buffers) to the
+    NUMA node its GPU hangs off: with 8 ranks downloading 2 GB per step each, buffers placed on the far socket were
+    what capped the end-to-end rate of round 1 near 88 GB/s in aggregate.  Best effort; returns what it did."""
+    try:
+        import torch
+
+        pr = torch.cuda.get_device_properties(local_rank)
+        bdf = f"{pr.pci_domain_id:04x}:{pr.pci_bus_id:02x}:{pr.pci_device_id:02x}.0"
+        node = int(open(f"/sys/bus/pci/devices/{bdf}/numa_node").read())
+        if node < 0:
+            return {"numa_node": None}
+        cpus = []
+        for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+            lo, _, hi = part.partition("-")
+            cpus += list(range(int(lo), int(hi or lo) + 1))
+        allowed = sorted(set(cpus) & os.sched_getaffinity(0))
+        if allowed:
+            os.sched_setaffinity(0, allowed)
+        return {"numa_node": node, "cpus": len(allowed)}
+    except Exception as e:  # no sysfs entry, containerised cpuset, ...
+        return {"numa_node": None, "why": type(e).__name__}
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -374,6 +398,7 @@ def run_ours(args):
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device (no CPU fallback); use --impl reference for the CPU arm")
     torch.cuda.set_device(local_rank)
+    numa = bind_to_gpu_numa_node(local_rank) if world > 1 else None
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     if rank == 0:
@@ -396,6 +421,8 @@ def run_ours(args):
     else:
         A = mpcx.create_matrix(a, mpc)
         b = mpcx.create_vector(mpc)
+
+    A.async_zero = not (args.no_async_zero or args.unfused)  # zero-fill of A overlapped with the previous assembly
 
     def step():
         if args.unfused:
@@ -495,6 +522,8 @@ def run_ours(args):
     # same pipeline when the assembled system is consumed on the device (Matrix.dlpack / to_torch_sparse_csr) and
     # only two norms travel back: reported beside the headline e2e, not instead of it
     e2e_dev = run_e2e(args, P, A, b, step, world, barrier, download="norms")
+    # symmetric systems (one constraint, one space): the upper triangle + RHS is all a host solver needs -- half the bytes
+    e2e_upper = run_e2e(args, P, A, b, step, world, barrier, download="upper") if A.nnz < (1 << 31) else None
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
@@ -511,10 +540,11 @@ def run_ours(args):
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_total / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": dict(workload_config(cfg, n, world), cells_per_gpu=nc, dofs_per_gpu=V.num_dofs, nnz_per_gpu=A.nnz,
-                           slaves=len(mpc.slaves), step="fused assemble_system" if fused else "assemble_matrix + assemble_vector + apply_lifting"),
+                           slaves=len(mpc.slaves), step="fused assemble_system" if fused else "assemble_matrix + assemble_vector + apply_lifting",
+                           zero_fill="second value buffer cleared on a side stream during the previous step" if not (args.no_async_zero or args.unfused) else "on the assembly stream"),
             "roofline": roofline, "breakdown": breakdown, "cpu_baseline": cpu, "e2e": e2e,
-            "e2e_device_consumer": e2e_dev, "gpu_launches": int(launches),
-            "clocks": clk, "tile_plans": plans, "lib": os.path.basename(_lib.LIB_PATH),
+            "e2e_device_consumer": e2e_dev, "e2e_upper_triangle": e2e_upper, "gpu_launches": int(launches),
+            "clocks": clk, "numa": numa, "tile_plans": plans, "lib": os.path.basename(_lib.LIB_PATH),
         }
         emit(line)
     if world > 1:
@@ -616,6 +646,8 @@ def main():
     ap.add_argument("--ref-budget", type=float, default=150.0, help="seconds of CPU work for --impl reference")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--unfused", action="store_true", help="step = three separate calls instead of assemble_system")
+    ap.add_argument("--no-async-zero", action="store_true", help="zero A on the assembly stream instead of clearing a "
+                    "second value buffer on a side stream during the previous step")
     ap.add_argument("--traffic", type=float, default=None, help="dram bytes per launch of the dominant kernel "
                     "from an ncu --set full capture, reported as roofline.traffic (default: profiles/traffic.json)")
     args = ap.parse_args()

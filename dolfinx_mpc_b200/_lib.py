@@ -71,7 +71,7 @@ SYMBOLS = (
     "mpcx_flag_cells", "mpcx_tile_plan_create", "mpcx_tile_plan_destroy", "mpcx_tile_plan_info",
     "mpcx_assemble_matrix_tiled_f64", "mpcx_vector_tile_plan_create", "mpcx_assemble_vector_tiled_f64",
     "mpcx_pattern_create", "mpcx_pattern_export", "mpcx_pattern_destroy", "mpcx_assemble_system_tiled_f64", "mpcx_nccl_load", "mpcx_comm_unique_id", "mpcx_comm_create",
-    "mpcx_comm_destroy", "mpcx_ghost_reduce_f64",
+    "mpcx_comm_destroy", "mpcx_ghost_reduce_f64", "mpcx_tile_plan_add_slave_cells",
 )
 
 _lib = None
@@ -114,6 +114,7 @@ def load():
     lib.mpcx_assemble_vector_tiled_f64.argtypes = [P(IntegralS), P(MeshS), P(DofmapS), P(MpcS), vp, vp, vp]
     lib.mpcx_assemble_system_tiled_f64.argtypes = [P(IntegralS), P(IntegralS), P(MeshS), P(DofmapS), vp, P(MpcS), P(CsrS),
                                                    vp, vp, vp, vp]
+    lib.mpcx_tile_plan_add_slave_cells.argtypes = [vp, P(IntegralS), P(DofmapS), P(DofmapS), vp, vp, P(MpcS), P(MpcS), P(CsrS), vp]
     lib.mpcx_nccl_load.argtypes = [C.c_char_p]
     lib.mpcx_comm_unique_id.argtypes = [vp]
     lib.mpcx_comm_create.argtypes = [vp, i32, i32, P(vp)]

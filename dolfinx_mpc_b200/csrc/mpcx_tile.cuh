@@ -81,6 +81,10 @@ struct TilePlan
   uint8_t* dest_cnt = nullptr;
   uint16_t* slot_cell = nullptr;       // vector plans: tile cell of the source held by every slot (inverse of cell_slot)
   long long* tile_slot_off = nullptr;  // vector plans: first entry of the tile in slot_cell (multiple of 8)
+  // scatter plan of the slave cells (mpcx_tile_plan_add_slave_cells): per slave cell the insertions of the elimination
+  long long *sp_off = nullptr, *sp_pos = nullptr, sp_cells = 0, sp_total = 0;
+  uint8_t* sp_ent = nullptr;
+  int *sp_ca = nullptr, *sp_cb = nullptr;
   int vec = 0;  // 1: vector plan (dests = row dofs, ne = nd0)
   int sym = 0;  // 1: symmetric matrix plan (upper-triangular records feed both (r, c) and (c, r))
   int ns = 0;   // slots per cell record: ne, or nd (nd + 1) / 2 for a symmetric plan
@@ -1118,6 +1122,7 @@ void tile_plan_free(TilePlan* P)
   cudaFree(P->tile_slots); cudaFree(P->tile_nr); cudaFree(P->tile_stage); cudaFree(P->runs); cudaFree(P->hdr); cudaFree(P->ginfo);
   cudaFree(P->tile_dest_off); cudaFree(P->tile_run_off); cudaFree(P->cell_nodes); cudaFree(P->dest_cnt); cudaFree(P->dest_spos);
   cudaFree(P->dest_spos2); cudaFree(P->cell_slot); cudaFree(P->cell_rows); cudaFree(P->slot_cell); cudaFree(P->tile_slot_off);
+  cudaFree(P->sp_off); cudaFree(P->sp_pos); cudaFree(P->sp_ent); cudaFree(P->sp_ca); cudaFree(P->sp_cb);
   delete P;
 }
 

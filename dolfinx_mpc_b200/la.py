@@ -51,6 +51,9 @@ class Matrix:
         # tile kernel exists; "atomic": one red.global.add per element entry
         self.scatter = os.environ.get("MPCX_SCATTER", "tile")
         self.ghost_exchange = None  # set by distributed.attach_ghost_exchange
+        # zero-fill overlapped with the previous assembly on a side stream (second value buffer); off by default
+        self.async_zero = os.environ.get("MPCX_ASYNC_ZERO", "0") == "1"
+        self._spare = None
 
     @property
     def row_ptr_host(self) -> np.ndarray:
@@ -68,7 +71,34 @@ class Matrix:
         return _lib.CsrS(_dev.ptr(self.row_ptr), _dev.ptr(self.col), _dev.ptr(self.val), self.shape[0], self.nnz)
 
     def zeroEntries(self):
-        self.val.zero_()
+        if self.async_zero:
+            self._swap_to_zeroed_buffer()
+        else:
+            self.val.zero_()
+
+    def _swap_to_zeroed_buffer(self):
+        """``async_zero``: two value buffers.  The assembly that starts now writes into the spare one, which was
+        cleared on a side stream WHILE the previous assembly ran (the tile kernels leave most of the DRAM bandwidth
+        unused); the buffer holding the previous values is cleared the same way now.  As with plain zeroing the
+        previous values are gone once this returns -- but ``val`` is a different tensor after every call, so views
+        taken earlier (``to_torch_sparse_csr``, ``dlpack``) must be taken again."""
+        cur = torch.cuda.current_stream(self.val.device)
+        if self._spare is None:
+            self._spare = torch.zeros_like(self._val_storage)
+            self._spare_ready = torch.cuda.Event()
+            self._spare_ready.record(cur)
+            self._zero_stream = torch.cuda.Stream(self.val.device)
+        cur.wait_event(self._spare_ready)  # the spare buffer is clear
+        old = self._val_storage
+        self._val_storage, self.val = self._spare, self._spare[: self.nnz]
+        done = torch.cuda.Event()
+        done.record(cur)  # everything enqueued so far that reads the old values
+        self._zero_stream.wait_event(done)
+        with torch.cuda.stream(self._zero_stream):
+            old.zero_()
+            self._spare_ready = torch.cuda.Event()
+            self._spare_ready.record(self._zero_stream)
+        self._spare = old
 
     def values_storage(self) -> torch.Tensor:
         """The device buffer behind ``val`` (capacity rounded up to an even number of entries)."""
@@ -83,6 +113,7 @@ class Matrix:
             raise ValueError(f"value storage must be a 16-byte aligned contiguous float64 tensor of >= {need} entries")
         self._val_storage = storage
         self.val = storage[: self.nnz]
+        self.async_zero, self._spare = False, None  # the caller manages the buffers from here on
 
     def plan(self, form, integral) -> Optional[_lib.PlanS]:
         """Scatter plan for one integral of ``form`` into this pattern (built on first use, then cached)."""
@@ -143,6 +174,14 @@ class Matrix:
                 self._tile_plans[key] = None
                 return None
             _lib.check(lib.mpcx_device_error(_dev.stream_ptr()))
+            if s_integral.num_slave_cells > 0 and len(keepalive) == 2 and os.environ.get("MPCX_SLAVE_PLAN", "1") != "0":
+                # scatter plan of the cells holding slaves: no constraint lookups / row searches at assembly time
+                m0 = _dev.mpc_dev(keepalive[0])["struct"]
+                m1 = _dev.mpc_dev(keepalive[1])["struct"]
+                _lib.check(lib.mpcx_tile_plan_add_slave_cells(handle, C.byref(s_integral), C.byref(d0), C.byref(d1),
+                                                              _dev.ptr(bc0_d), _dev.ptr(bc1_d), C.byref(m0), C.byref(m1),
+                                                              C.byref(A), _dev.stream_ptr()))
+                _lib.check(lib.mpcx_device_error(_dev.stream_ptr()))
             info = (C.c_int64 * 14)()
             lib.mpcx_tile_plan_info(handle, info, 14)
             self._tile_plans[key] = (handle, dict(zip(("tiles", "cells_per_tile", "bulk_cells", "max_nodes",

@@ -201,6 +201,15 @@ void mpcx_tile_plan_destroy(mpcx_tile_plan* plan);
  * and bc markers on both sides: upper-triangular records feed entry (r, c) and entry (c, r)) */
 int mpcx_tile_plan_info(const mpcx_tile_plan* plan, int64_t* out, int32_t n);
 
+/* Optional: scatter plan for the cells holding slaves (integral->slave_cells), stored inside a matrix tile plan of a
+ * scalar P1 space.  For every insertion modify_mpc_cell makes for such a cell (cpp/assemble_matrix.cpp:214-267: master
+ * rows, master columns, master x master, plus the unconstrained entries) it records the element entry, the CSR
+ * position and the indices of the row / column coefficients, so that the elimination kernel of the tiled routines
+ * needs neither constraint lookups nor row searches.  Coefficient VALUES are read at assembly time. */
+int mpcx_tile_plan_add_slave_cells(mpcx_tile_plan* plan, const mpcx_integral* integral, const mpcx_dofmap* dofmap0,
+                                   const mpcx_dofmap* dofmap1, const int8_t* bc0, const int8_t* bc1, const mpcx_mpc* mpc0,
+                                   const mpcx_mpc* mpc1, const mpcx_csr* A, void* stream);
+
 /* Same contract as mpcx_assemble_matrix_f64 (A += integral; the caller zeroes A), bulk cells through the
  * tile plan: element entries are combined per tile in shared memory and added with one reduction per
  * (tile, CSR entry), added to A.val by TMA bulk reductions over runs of consecutive entries; slave cells are

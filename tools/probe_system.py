@@ -18,12 +18,14 @@ ap.add_argument("--n", type=int, default=128)
 ap.add_argument("--config", type=int, default=2)
 ap.add_argument("--reps", type=int, default=5)
 ap.add_argument("--unfused", action="store_true")
+ap.add_argument("--async-zero", action="store_true")
 args = ap.parse_args()
 P = bench.build_config(args.config, args.n)
 a, L, mpc, bcs = P["a"], P["L"], P["mpc"], P["bcs"]
 P["f"].device_array = _dev.to_dev(P["f"].array)
 A = mpcx.create_matrix(a, mpc)
 b = mpcx.create_vector(mpc)
+A.async_zero = args.async_zero
 lib = _lib.load()
 
 
