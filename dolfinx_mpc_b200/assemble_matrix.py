@@ -163,9 +163,9 @@ def assemble_matrix(form: Form, constraint: Union[MultiPointConstraint, Sequence
     d1 = _dev.dofmap_struct(V1, A.shape[1])
     m0 = _dev.mpc_dev(mpc0)["struct"]
     m1 = _dev.mpc_dev(mpc1)["struct"]
-    As = A.struct()
     keep = []
     A.zeroEntries()
+    As = A.struct()  # after zeroEntries: with async_zero the values live in the other buffer now
     for it in form.integrals:
         if it.integral_type not in ("cell", "exterior_facet"):
             raise RuntimeError(f"{it.integral_type} integrals have no device kernel yet")

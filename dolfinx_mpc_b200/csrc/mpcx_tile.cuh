@@ -65,6 +65,10 @@ namespace
 #ifndef MPCX_CT_STAGECAP
 #define MPCX_CT_STAGECAP 3200
 #endif
+// ... but never at the price of more than this many runs per tile
+#ifndef MPCX_CT_RUNCAP
+#define MPCX_CT_RUNCAP 96
+#endif
 
 struct TilePlan
 {
@@ -351,8 +355,12 @@ k_ct_build(int pass, const int* __restrict__ order, long long n_bulk, const int*
   int rid[NEc], roff = 0, nruns = 0, stage = 0, loff = 0;
   int rlen[NEc];
   bool runs_ok = false;
-  for (unsigned gap = MPCX_CT_RUNGAP;; gap >>= 1)
+  // candidates: RUNGAP, then half and a quarter of it while the staging buffer is above STAGECAP -- provided the
+  // number of runs (bulk operations of the copy engine, a few hundred cycles each) stays below RUNCAP; otherwise back
+  // to RUNGAP, whatever the size
+  for (int trial = 0;; ++trial)
   {
+    const unsigned gap = trial < 3 ? (unsigned)MPCX_CT_RUNGAP >> trial : (unsigned)MPCX_CT_RUNGAP;
     int nf = 0;
 #pragma unroll
     for (int e = 0; e < NEc; ++e)
@@ -389,7 +397,7 @@ k_ct_build(int pass, const int* __restrict__ order, long long n_bulk, const int*
     }
     Scan(scan).ExclusiveSum(lsum, loff, stage);
     __syncthreads();
-    if (vec || gap <= 1 || (runs_ok && stage <= MPCX_CT_STAGECAP)) break;
+    if (vec || trial == 3 || (runs_ok && stage <= MPCX_CT_STAGECAP && (trial == 0 || nruns <= MPCX_CT_RUNCAP))) break;
   }
   bool ok = runs_ok && stage < 65536;  // otherwise the tile does not fit the plan format (the host reports it)
   if (ok)
@@ -1221,11 +1229,15 @@ int tile_plan_build(const mpcx_mesh* mesh, const mpcx_dofmap* dm0, const mpcx_do
     k_tp_bbox<<<148 * 8, 256, 0, s>>>(mesh->x, mesh->x_stride, mesh->num_nodes, mm);
     TP_CK(cudaMemcpyAsync(h, mm, sizeof(h), cudaMemcpyDeviceToHost, s));
     TP_CK(cudaStreamSynchronize(s));
+    // one scale for the three axes (the largest extent): Morton cells are cubes in PHYSICAL space, so that the tiles
+    // of a flat slab (a z-slab partition of a cube) are as compact as those of the cube itself; per-axis scaling
+    // turned them into 8 x 8 x 1 pancakes with 40 % more vertices and 7 x more runs per tile
+    double ext = 0.0;
+    for (int k = 0; k < 3; ++k) ext = std::max(ext, dec_f64(h[3 + k]) - dec_f64(h[k]));
     for (int k = 0; k < 3; ++k)
     {
-      const double lo = dec_f64(h[k]), hi = dec_f64(h[3 + k]);
-      bb.lo[k] = lo;
-      bb.inv[k] = hi > lo ? 1.0 / (hi - lo) : 0.0;
+      bb.lo[k] = dec_f64(h[k]);
+      bb.inv[k] = ext > 0.0 ? 1.0 / ext : 0.0;
     }
   }
   // 2. cells along the Morton curve (skipped cells last), tiles of C consecutive cells

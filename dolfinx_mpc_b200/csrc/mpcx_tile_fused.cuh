@@ -31,7 +31,7 @@ struct FusedSmem
   uint8_t* dcntv;
   uint16_t *vinc, *cnode, *cslot, *crow;
   int* hb;  // ring of 3 tile headers (matrix plan: 12 ints, vector plan: 12 ints), filled two tiles ahead
-  unsigned long long *barC, *barR, *barS;
+  unsigned long long *barC, *barR;
 };
 
 __host__ __device__ inline size_t fused_smem_bytes(const TilePlanD& P, const TilePlanD& Q, int nv, int ns, bool sym)
@@ -72,7 +72,6 @@ __device__ __forceinline__ FusedSmem fused_carve(unsigned char* sp, const TilePl
   S.hb = reinterpret_cast<int*>(sp); sp += 3 * 24 * sizeof(int);
   S.barC = reinterpret_cast<unsigned long long*>(sp);
   S.barR = S.barC + 1;
-  S.barS = S.barC + 2;
   S.R.bar = S.barR;
   return S;
 }
@@ -122,8 +121,9 @@ __device__ __forceinline__ void fused_tma_mrecords(const FusedSmem& S, const Til
 //   top      header words of tile t+2 -> register (24 threads); vertex id / row dof of tile t+1 -> registers
 //   phase 1  wait C(t); thread = cell: geometry once, element matrix -> matrix slots, (s, s F) -> cellv; then
 //            x[vertex id], f[row dof] of t+1 -> registers; header words -> ring; warp 0 waits until the reductions of
-//            t-1 have read the staging buffer and signals an mbarrier; every thread zeroes its share of the buffer
-//   sync 1   TMA C(t+1)
+//            t-1 have read the staging buffer
+//   sync 1   TMA C(t+1); zero the staging buffer
+//   sync 1b
 //   phase 2  wait R(t); thread = record: matrix column sum -> staging position(s); row record: gather the cell pairs
 //            -> red.global.add (f of the row travels in a register of its thread); registers -> Xs, fs of t+1
 //   sync 2   warp 0: TMA bulk reduce-add of the runs, then TMA R(t+1)
@@ -143,7 +143,7 @@ k_ptile_system_p1(TilePlanD P, TilePlanD Q, int nt, IntD ina, IntD inL, MeshD me
   const int hw_i = tid - 32;
   const bool loader = hw_i >= 0 && hw_i < 24;
   const int* hsrc = loader ? reinterpret_cast<const int*>(hw_i < 12 ? P.hdr : Q.hdr) + (hw_i < 12 ? hw_i : hw_i - 12) : nullptr;
-  if (tid == 0) { mbar_init(S.barC, 1); mbar_init(S.barR, 2); mbar_init(S.barS, 1); S.cellv[NT] = make_double2(0.0, 0.0); }
+  if (tid == 0) { mbar_init(S.barC, 1); mbar_init(S.barR, 2); S.cellv[NT] = make_double2(0.0, 0.0); }
   if (loader)
   {
     S.hb[hw_i] = __ldg(hsrc + 12 * (long long)t);
@@ -246,21 +246,16 @@ k_ptile_system_p1(TilePlanD P, TilePlanD Q, int nt, IntD ina, IntD inL, MeshD me
     if (nid >= 0) load_vertex(mesh, nid, xg0, xg1, xg2);
     if (fid >= 0) fg = __ldg(inL.wnodal + fid);
     if (load2) S.hb[24 * ((it + 2) % 3) + hw_i] = hword;  // that slot held tile t-1's header: no reader left
-    // the staging buffer is free once the reductions of t-1 have read it: warp 0 waits for that at the end of ITS
-    // phase 1 and signals barS; every thread then clears its share before the one barrier between the phases
-    if (issuer)
-    {
-      asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-      __syncwarp();
-      if (tid == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(S.barS)) : "memory");
-    }
-    mbar_wait(S.barS, it & 1);
+    if (issuer) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");  // reductions of t-1 have read the staging buffer
+    __syncthreads();  // 1: element buffers complete; cell records, Xs and the staging buffer are free
+    if (tid == 0 && has_next) fused_tma_cells(S, P, Q, tn, NV, NS);
     {
       const int half = hm[4] >> 1;
       for (int i = tid; i < half; i += NT) reinterpret_cast<double2*>(S.stage)[i] = make_double2(0.0, 0.0);
     }
-    __syncthreads();  // 1: element buffers complete, staging buffer zeroed; cell records and Xs are free
-    if (tid == 0 && has_next) fused_tma_cells(S, P, Q, tn, NV, NS);
+    // (measured: replacing this barrier by an mbarrier that warp 0 signals after its wait -- every thread clearing its
+    // share before barrier 1 -- was 2 % slower: profiles/README.md, r02_c)
+    __syncthreads();  // 1b: staging buffer zeroed
 
     // phase 2: thread = record
     mbar_wait(S.barR, it & 1);

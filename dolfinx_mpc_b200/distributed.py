@@ -103,12 +103,54 @@ def build_slab_problem(n: int, rank: int, world: int, f_expr: Callable, periodic
 # ------------------------------------------------------------------ pattern extension + exchange plan (setup)
 
 def _all_to_all_objects(objs, group):
-    """objs[r] goes to rank r; returns the list received (one entry per source rank)."""
+    """objs[r] goes to rank r; returns the list received (one entry per source rank).  Each entry is None or a tuple
+    of int64 numpy arrays.  Over NCCL the arrays travel point to point as device tensors (two
+    ``all_to_all_single`` calls: sizes, then payload) -- every rank moves only its own interface data; without NCCL
+    (the gloo tests on the CPU) the exchange falls back to ``all_gather_object``."""
     world = dist.get_world_size(group)
-    gathered = [None] * world
-    dist.all_gather_object(gathered, objs, group=group)
     me = dist.get_rank(group)
-    return [gathered[src][me] for src in range(world)]
+    if dist.get_backend(group) != "nccl":
+        gathered = [None] * world
+        dist.all_gather_object(gathered, objs, group=group)
+        return [gathered[src][me] for src in range(world)]
+    from . import device as _dev
+
+    dev = _dev.device()
+    narr = max([len(o) for o in objs if o is not None], default=0)
+    t = torch.tensor([narr], device=dev)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX, group=group)
+    narr = int(t.item())
+    # sizes[dst, k] = length of array k sent to dst (-1: nothing for that rank)
+    sizes = np.full((world, max(1, narr)), -1, dtype=np.int64)
+    for r, o in enumerate(objs):
+        if o is not None:
+            sizes[r, : len(o)] = [len(a) for a in o]
+    s_send = torch.from_numpy(sizes).to(dev)
+    s_recv = torch.empty_like(s_send)
+    dist.all_to_all_single(s_recv, s_send, group=group)
+    rsz = s_recv.cpu().numpy()
+    payload = [np.concatenate([np.asarray(a, dtype=np.int64).reshape(-1) for a in o]) if o is not None and len(o) else
+               np.zeros(0, np.int64) for o in objs]
+    send = torch.from_numpy(np.concatenate(payload) if payload else np.zeros(0, np.int64)).to(dev)
+    in_splits = [int(np.clip(rsz[r], 0, None).sum()) for r in range(world)]
+    out_splits = [len(p_) for p_ in payload]
+    recv = torch.empty(sum(in_splits), dtype=torch.int64, device=dev)
+    dist.all_to_all_single(recv, send, in_splits, out_splits, group=group)
+    flat = recv.cpu().numpy()
+    out, pos = [], 0
+    for r in range(world):
+        if rsz[r, 0] < 0:
+            out.append(None)
+            continue
+        arrs = []
+        for k in range(narr):
+            n = int(rsz[r, k])
+            if n < 0:
+                break
+            arrs.append(flat[pos:pos + n])
+            pos += n
+        out.append(tuple(arrs))
+    return out
 
 
 def extend_pattern(row_ptr: np.ndarray, col: np.ndarray, imap_rows: IndexMap, imap_cols: IndexMap, bs0: int, bs1: int,
@@ -224,15 +266,15 @@ def vector_plan(imap: IndexMap, bs: int, group=None):
     send, send_idx, send_counts = [], [], []
     for dst in range(world):
         sel = np.flatnonzero(g_owner == dst)
-        send.append(g_glob[sel] if len(sel) else None)
+        send.append((g_glob[sel],) if len(sel) else None)
         send_idx.append(sel + n_owned)
         send_counts.append(len(sel))
     recv = _all_to_all_objects(send, group)
     lo = imap.local_range[0] * bs
-    pos = [r - lo for r in recv if r is not None]
+    pos = [r[0] - lo for r in recv if r is not None]
     return {"send_idx": np.concatenate(send_idx).astype(np.int64), "send_counts": send_counts,
             "recv_pos": np.concatenate(pos).astype(np.int64) if pos else np.zeros(0, np.int64),
-            "recv_counts": [0 if r is None else len(r) for r in recv]}
+            "recv_counts": [0 if r is None else len(r[0]) for r in recv]}
 
 
 # ------------------------------------------------------------------ per-step exchange (device)

@@ -48,8 +48,8 @@ def assemble_system(a: Form, L: Form, constraint: MultiPointConstraint, bcs: Opt
         lib = _lib.load()
         st = _dev.stream_ptr()
         sa, sL, mesh_s, dm, bc_d, m, mplan, vplan, keep = plans
-        As = A.struct()
         A.zeroEntries()
+        As = A.struct()  # after zeroEntries: with async_zero the values live in the other buffer now
         b.set(0.0)
         try:
             _lib.check(lib.mpcx_assemble_system_tiled_f64(C.byref(sa), C.byref(sL), C.byref(mesh_s), C.byref(dm),
