@@ -2070,6 +2070,14 @@ int mpcx_ghost_reduce_f64(mpcx_comm* comm, double* values, const int64_t* send_i
   return cuda_check(cudaGetLastError(), "ghost_reduce launch");
 }
 
+#ifdef MPCX_TRACE
+// tuning builds only (not declared in mpcx.h): device buffer of 8 x 64 x warps x 12 clock stamps
+int mpcx_debug_set_trace(long long* buf)
+{
+  return cuda_check(cudaMemcpyToSymbol(g_trace, &buf, sizeof(buf)), "set_trace");
+}
+#endif
+
 int mpcx_pattern_create(const mpcx_dofmap* dofmap0, const mpcx_dofmap* dofmap1, int64_t num_cells,
                         const mpcx_mpc* mpc0, const mpcx_mpc* mpc1, void* stream, mpcx_pattern** pattern_out,
                         int64_t* nnz_out)

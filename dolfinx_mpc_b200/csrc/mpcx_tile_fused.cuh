@@ -21,6 +21,19 @@
 
 namespace
 {
+// Phase timeline of the fused kernel (tuning builds only: -DMPCX_TRACE, tools/probe_trace.py): clock64 of warp 0, a
+// middle and the last warp at the phase boundaries of the first iterations of the first CTAs.
+#ifdef MPCX_TRACE
+__device__ long long* g_trace = nullptr;
+#define MPCX_STAMP(k)                                                                                              \
+  do {                                                                                                             \
+    if (g_trace && blockIdx.x < 8 && it < 64 && (tid & 31) == 0)                                                   \
+      g_trace[(((long long)blockIdx.x * 64 + it) * (MPCX_TILE_THREADS / 32) + (tid >> 5)) * 12 + (k)] = clock64(); \
+  } while (0)
+#else
+#define MPCX_STAMP(k)
+#endif
+
 struct FusedSmem
 {
   double *Xs, *stage, *ebuf, *fs;
@@ -192,7 +205,9 @@ k_ptile_system_p1(TilePlanD P, TilePlanD Q, int nt, IntD ina, IntD inL, MeshD me
     }
 
     // phase 1: thread = cell
+    MPCX_STAMP(0);
     mbar_wait(S.barC, it & 1);
+    MPCX_STAMP(1);
     if (tid < nc_t)
     {
       double X[NV][3];
@@ -246,8 +261,11 @@ k_ptile_system_p1(TilePlanD P, TilePlanD Q, int nt, IntD ina, IntD inL, MeshD me
     if (nid >= 0) load_vertex(mesh, nid, xg0, xg1, xg2);
     if (fid >= 0) fg = __ldg(inL.wnodal + fid);
     if (load2) S.hb[24 * ((it + 2) % 3) + hw_i] = hword;  // that slot held tile t-1's header: no reader left
+    MPCX_STAMP(2);
     if (issuer) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");  // reductions of t-1 have read the staging buffer
+    MPCX_STAMP(3);
     __syncthreads();  // 1: element buffers complete; cell records, Xs and the staging buffer are free
+    MPCX_STAMP(4);
     if (tid == 0 && has_next) fused_tma_cells(S, P, Q, tn, NV, NS);
     {
       const int half = hm[4] >> 1;
@@ -256,9 +274,11 @@ k_ptile_system_p1(TilePlanD P, TilePlanD Q, int nt, IntD ina, IntD inL, MeshD me
     // (measured: replacing this barrier by an mbarrier that warp 0 signals after its wait -- every thread clearing its
     // share before barrier 1 -- was 2 % slower: profiles/README.md, r02_c)
     __syncthreads();  // 1b: staging buffer zeroed
+    MPCX_STAMP(5);
 
     // phase 2: thread = record
     mbar_wait(S.barR, it & 1);
+    MPCX_STAMP(6);
     {
       const int nd = hm[2];
       for (int k = tid; k < nd; k += NT)
@@ -268,6 +288,7 @@ k_ptile_system_p1(TilePlanD P, TilePlanD Q, int nt, IntD ina, IntD inL, MeshD me
         if (SYM) S.stage[S.R.spos2[k]] = v;
       }
     }
+    MPCX_STAMP(7);
     // row records go to the LAST threads (the first ones hold the heaviest matrix records: those are ordered by
     // descending source count)
     {
@@ -303,9 +324,11 @@ k_ptile_system_p1(TilePlanD P, TilePlanD Q, int nt, IntD ina, IntD inL, MeshD me
       if (ndvn > NT)
         for (int k = tid; k < ndvn - NT; k += NT) S.fs[k + NT] = __ldg(inL.wnodal + __ldg(Q.dest_k + hdr64(hmn + 12, 6) + k + NT));
     }
+    MPCX_STAMP(8);
     const int nr = hm[3];  // read before the barrier: the loader threads refill this ring slot during the next phase 1
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // staging writes -> visible to the copy engine
     __syncthreads();  // 2: staging buffer, next Xs / fs complete; element buffers and records free
+    MPCX_STAMP(9);
 
     if (issuer)
     {
@@ -318,6 +341,7 @@ k_ptile_system_p1(TilePlanD P, TilePlanD Q, int nt, IntD ina, IntD inL, MeshD me
       __syncwarp();  // every lane has read its runs: the record buffers may be refilled
       if (tid == 0 && has_next) { fused_tma_mrecords<SYM>(S, P, hmn); fused_tma_vrecords(S, Q, hmn + 12); }
     }
+    MPCX_STAMP(10);
     if (!has_next) break;
     t = tn; tn += G; fcur = fg;
   }
