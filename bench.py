@@ -155,7 +155,12 @@ def workload_config(cfg, n, gpus):
         5: f"contact constraint between two stacked boxes ({n} / {2 * n} cells per unit length), P1 elasticity (bs 3), "
            "fp64 (BASELINE.json configs[4])",
     }[cfg]
-    return {"workload": desc, "config_id": cfg, "n": n, "gpus": gpus,
+    nzc = NZC_CFG4 if n == DEFAULT_N[4] else max(2, n // 8)
+    cells, dofs = {2: (6 * (n - 1) ** 3, n ** 3), 3: (6 * n ** 3, 3 * (2 * n + 1) ** 3),
+                   4: (6 * (n - 1) ** 2 * nzc, n * n * (nzc + 1)),
+                   5: (6 * (n * n * max(1, n // 2) + 4 * n * n * n), 3 * ((n + 1) ** 2 * (max(1, n // 2) + 1) + (2 * n + 1) ** 2 * (n + 1)))}[cfg]
+    # the same dictionary in both arms (ours / reference): it describes the workload, nothing about the implementation
+    return {"workload": desc, "config_id": cfg, "n": n, "gpus": gpus, "cells_per_gpu": cells, "dofs_per_gpu": dofs,
             "l2": "inputs (> 3 GB per step) far larger than the 126 MB L2; no explicit flush",
             "partition": "z-slabs by ownership, ghost-row NCCL reduce" if gpus > 1 else "single GPU"}
 
@@ -422,7 +427,7 @@ def run_ours(args):
         A = mpcx.create_matrix(a, mpc)
         b = mpcx.create_vector(mpc)
 
-    A.async_zero = not (args.no_async_zero or args.unfused)  # zero-fill of A overlapped with the previous assembly
+    A.async_zero = bool(args.async_zero) and not args.unfused  # zero-fill of A overlapped with the previous assembly
 
     def step():
         if args.unfused:
@@ -539,9 +544,10 @@ def run_ours(args):
             "metric": "cells assembled/sec (matrix+vector)", "value": value, "unit": "cells/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_total / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": dict(workload_config(cfg, n, world), cells_per_gpu=nc, dofs_per_gpu=V.num_dofs, nnz_per_gpu=A.nnz,
-                           slaves=len(mpc.slaves), step="fused assemble_system" if fused else "assemble_matrix + assemble_vector + apply_lifting",
-                           zero_fill="second value buffer cleared on a side stream during the previous step" if not (args.no_async_zero or args.unfused) else "on the assembly stream"),
+            "config": workload_config(cfg, n, world),
+            "detail": dict(cells_rank0=nc, dofs_rank0=V.num_dofs, nnz_rank0=A.nnz, slaves_rank0=len(mpc.slaves),
+                           step="fused assemble_system" if fused else "assemble_matrix + assemble_vector + apply_lifting",
+                           zero_fill="second value buffer cleared on a side stream during the previous step" if A.async_zero else "on the assembly stream"),
             "roofline": roofline, "breakdown": breakdown, "cpu_baseline": cpu, "e2e": e2e,
             "e2e_device_consumer": e2e_dev, "e2e_upper_triangle": e2e_upper, "gpu_launches": int(launches),
             "clocks": clk, "numa": numa, "tile_plans": plans, "lib": os.path.basename(_lib.LIB_PATH),
@@ -646,8 +652,8 @@ def main():
     ap.add_argument("--ref-budget", type=float, default=150.0, help="seconds of CPU work for --impl reference")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--unfused", action="store_true", help="step = three separate calls instead of assemble_system")
-    ap.add_argument("--no-async-zero", action="store_true", help="zero A on the assembly stream instead of clearing a "
-                    "second value buffer on a side stream during the previous step")
+    ap.add_argument("--async-zero", action="store_true", help="clear a second value buffer on a side stream during the "
+                    "previous step instead of zeroing A on the assembly stream (measured: no gain, profiles/README.md)")
     ap.add_argument("--traffic", type=float, default=None, help="dram bytes per launch of the dominant kernel "
                     "from an ncu --set full capture, reported as roofline.traffic (default: profiles/traffic.json)")
     args = ap.parse_args()

@@ -67,7 +67,7 @@ namespace
 #endif
 // ... but never at the price of more than this many runs per tile
 #ifndef MPCX_CT_RUNCAP
-#define MPCX_CT_RUNCAP 96
+#define MPCX_CT_RUNCAP 256
 #endif
 
 struct TilePlan
@@ -355,12 +355,12 @@ k_ct_build(int pass, const int* __restrict__ order, long long n_bulk, const int*
   int rid[NEc], roff = 0, nruns = 0, stage = 0, loff = 0;
   int rlen[NEc];
   bool runs_ok = false;
-  // candidates: RUNGAP, then half and a quarter of it while the staging buffer is above STAGECAP -- provided the
+  // candidates: RUNGAP, then RUNGAP / 2 ... RUNGAP / 16 while the staging buffer is above STAGECAP -- provided the
   // number of runs (bulk operations of the copy engine, a few hundred cycles each) stays below RUNCAP; otherwise back
   // to RUNGAP, whatever the size
   for (int trial = 0;; ++trial)
   {
-    const unsigned gap = trial < 3 ? (unsigned)MPCX_CT_RUNGAP >> trial : (unsigned)MPCX_CT_RUNGAP;
+    const unsigned gap = trial < 5 ? (unsigned)MPCX_CT_RUNGAP >> trial : (unsigned)MPCX_CT_RUNGAP;
     int nf = 0;
 #pragma unroll
     for (int e = 0; e < NEc; ++e)
@@ -397,7 +397,7 @@ k_ct_build(int pass, const int* __restrict__ order, long long n_bulk, const int*
     }
     Scan(scan).ExclusiveSum(lsum, loff, stage);
     __syncthreads();
-    if (vec || trial == 3 || (runs_ok && stage <= MPCX_CT_STAGECAP && (trial == 0 || nruns <= MPCX_CT_RUNCAP))) break;
+    if (vec || trial == 5 || (runs_ok && stage <= MPCX_CT_STAGECAP && (trial == 0 || nruns <= MPCX_CT_RUNCAP))) break;
   }
   bool ok = runs_ok && stage < 65536;  // otherwise the tile does not fit the plan format (the host reports it)
   if (ok)

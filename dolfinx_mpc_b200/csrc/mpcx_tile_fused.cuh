@@ -262,7 +262,7 @@ k_ptile_system_p1(TilePlanD P, TilePlanD Q, int nt, IntD ina, IntD inL, MeshD me
     if (fid >= 0) fg = __ldg(inL.wnodal + fid);
     if (load2) S.hb[24 * ((it + 2) % 3) + hw_i] = hword;  // that slot held tile t-1's header: no reader left
     MPCX_STAMP(2);
-    if (issuer) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");  // reductions of t-1 have read the staging buffer
+    asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");  // this thread's reductions of t-1 have read the staging buffer
     MPCX_STAMP(3);
     __syncthreads();  // 1: element buffers complete; cell records, Xs and the staging buffer are free
     MPCX_STAMP(4);
@@ -325,17 +325,31 @@ k_ptile_system_p1(TilePlanD P, TilePlanD Q, int nt, IntD ina, IntD inL, MeshD me
         for (int k = tid; k < ndvn - NT; k += NT) S.fs[k + NT] = __ldg(inL.wnodal + __ldg(Q.dest_k + hdr64(hmn + 12, 6) + k + NT));
     }
     MPCX_STAMP(8);
-    const int nr = hm[3];  // read before the barrier: the loader threads refill this ring slot during the next phase 1
+    // Every warp hands a few runs to the copy engine (run r -> lane r / NW of warp r % NW): one warp issuing all ~40
+    // bulk reductions of a tile spent 3800 of the tile's 9400 cycles in that loop and was the last to arrive at barrier
+    // 1 of the next tile (phase timeline, profiles/r02_trace6.txt).  The run records are read BEFORE the barrier so that
+    // thread 0 can refill the record buffers right after it.
+    const int nr = hm[3];
+    constexpr int NW = NT / 32;
+    const int my_run = (tid & 31) * NW + (tid >> 5);
+    int2 rr = make_int2(0, 0);
+    if (nr <= NT && my_run < nr) rr = S.R.runs[my_run];
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // staging writes -> visible to the copy engine
     __syncthreads();  // 2: staging buffer, next Xs / fs complete; element buffers and records free
     MPCX_STAMP(9);
 
-    if (issuer)
+    if (nr <= NT)
+    {
+      if (my_run < nr) tma_reduce_add_f64(A.val + rr.x, S.stage + (rr.y & 0xffff), (unsigned)(rr.y >> 16) * 8u);
+      asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+      if (tid == 0 && has_next) { fused_tma_mrecords<SYM>(S, P, hmn); fused_tma_vrecords(S, Q, hmn + 12); }
+    }
+    else if (issuer)  // more runs than threads (pathological meshes): warp 0 takes them all
     {
       for (int r = tid; r < nr; r += 32)
       {
-        const int2 rr = S.R.runs[r];
-        tma_reduce_add_f64(A.val + rr.x, S.stage + (rr.y & 0xffff), (unsigned)(rr.y >> 16) * 8u);
+        const int2 r2 = S.R.runs[r];
+        tma_reduce_add_f64(A.val + r2.x, S.stage + (r2.y & 0xffff), (unsigned)(r2.y >> 16) * 8u);
       }
       asm volatile("cp.async.bulk.commit_group;" ::: "memory");
       __syncwarp();  // every lane has read its runs: the record buffers may be refilled
@@ -345,6 +359,6 @@ k_ptile_system_p1(TilePlanD P, TilePlanD Q, int nt, IntD ina, IntD inL, MeshD me
     if (!has_next) break;
     t = tn; tn += G; fcur = fg;
   }
-  if (issuer) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");  // the staging buffer must outlive the reads
+  asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");  // the staging buffer must outlive the reads
 }
 }  // namespace
