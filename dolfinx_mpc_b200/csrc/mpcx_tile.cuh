@@ -1239,6 +1239,14 @@ int tile_plan_build(const mpcx_mesh* mesh, const mpcx_dofmap* dm0, const mpcx_do
       bb.lo[k] = dec_f64(h[k]);
       bb.inv[k] = ext > 0.0 ? 1.0 / ext : 0.0;
     }
+    // tuning: MPCX_TILE_STRETCH="fx,fy,fz" divides the Morton scale of an axis by f (tiles f times longer along it)
+    if (const char* st = getenv("MPCX_TILE_STRETCH"))
+    {
+      double f[3] = {1.0, 1.0, 1.0};
+      if (sscanf(st, "%lf,%lf,%lf", &f[0], &f[1], &f[2]) >= 1)
+        for (int k = 0; k < 3; ++k)
+          if (f[k] > 0.0) bb.inv[k] /= f[k];
+    }
   }
   // 2. cells along the Morton curve (skipped cells last), tiles of C consecutive cells
   TP_CK(tp_alloc(&code, nc)); TP_CK(tp_alloc(&code2, nc)); TP_CK(tp_alloc(&iota, nc)); TP_CK(tp_alloc(&order, nc));
