@@ -71,7 +71,8 @@ SYMBOLS = (
     "mpcx_flag_cells", "mpcx_tile_plan_create", "mpcx_tile_plan_destroy", "mpcx_tile_plan_info",
     "mpcx_assemble_matrix_tiled_f64", "mpcx_vector_tile_plan_create", "mpcx_assemble_vector_tiled_f64",
     "mpcx_pattern_create", "mpcx_pattern_export", "mpcx_pattern_destroy", "mpcx_assemble_system_tiled_f64", "mpcx_nccl_load", "mpcx_comm_unique_id", "mpcx_comm_create",
-    "mpcx_comm_destroy", "mpcx_ghost_reduce_f64", "mpcx_tile_plan_add_slave_cells",
+    "mpcx_comm_destroy", "mpcx_ghost_reduce_f64", "mpcx_tile_plan_add_slave_cells", "mpcx_row_plan_create", "mpcx_row_plan_destroy",
+    "mpcx_assemble_matrix_rowgather_f64",
 )
 
 _lib = None
@@ -115,6 +116,10 @@ def load():
     lib.mpcx_assemble_system_tiled_f64.argtypes = [P(IntegralS), P(IntegralS), P(MeshS), P(DofmapS), vp, P(MpcS), P(CsrS),
                                                    vp, vp, vp, vp]
     lib.mpcx_tile_plan_add_slave_cells.argtypes = [vp, P(IntegralS), P(DofmapS), P(DofmapS), vp, vp, P(MpcS), P(MpcS), P(CsrS), vp]
+    lib.mpcx_row_plan_create.argtypes = [P(DofmapS), vp, i64, vp, P(CsrS), vp, P(vp)]
+    lib.mpcx_row_plan_destroy.argtypes = [vp]
+    lib.mpcx_row_plan_destroy.restype = None
+    lib.mpcx_assemble_matrix_rowgather_f64.argtypes = [P(IntegralS), P(MeshS), P(DofmapS), vp, P(MpcS), P(CsrS), vp, vp]
     lib.mpcx_nccl_load.argtypes = [C.c_char_p]
     lib.mpcx_comm_unique_id.argtypes = [vp]
     lib.mpcx_comm_create.argtypes = [vp, i32, i32, P(vp)]

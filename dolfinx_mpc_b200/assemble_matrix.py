@@ -164,12 +164,25 @@ def assemble_matrix(form: Form, constraint: Union[MultiPointConstraint, Sequence
     m0 = _dev.mpc_dev(mpc0)["struct"]
     m1 = _dev.mpc_dev(mpc1)["struct"]
     keep = []
-    A.zeroEntries()
+    # Blocked P1 elasticity: the first integral can be assembled by the row-gather kernel, which STORES every row of A
+    # (zeros included) instead of adding into a zeroed matrix -- no zero-fill then (csrc/mpcx_rowgather.cuh)
+    row_plan = None
+    if (A.scatter == "tile" and mpc0 is mpc1 and V0 is V1 and form.integrals and os.environ.get("MPCX_ROWGATHER", "1") != "0"):
+        it0 = form.integrals[0]
+        if it0.integral_type == "cell":
+            s0 = _dev.integral_struct(form, it0, (mpc0, mpc1), keep)
+            row_plan = A.row_plan(form, it0, s0, (id(mpc0), id(mpc1)), keepalive=(mpc0, mpc1))
+    if row_plan is None:
+        A.zeroEntries()
     As = A.struct()  # after zeroEntries: with async_zero the values live in the other buffer now
-    for it in form.integrals:
+    for n_it, it in enumerate(form.integrals):
         if it.integral_type not in ("cell", "exterior_facet"):
             raise RuntimeError(f"{it.integral_type} integrals have no device kernel yet")
         s = _dev.integral_struct(form, it, (mpc0, mpc1), keep)
+        if n_it == 0 and row_plan is not None:
+            _lib.check(lib.mpcx_assemble_matrix_rowgather_f64(C.byref(s), C.byref(mesh_s), C.byref(d0), _dev.ptr(bc0_d),
+                                                              C.byref(m0), C.byref(As), row_plan[0], st))
+            continue
         facet = it.integral_type == "exterior_facet"  # surface-sized: generic kernel, row search per entry
         tile = (A.tile_plan(form, it, s, bc0_d, bc1_d, (id(mpc0), id(mpc1)), keepalive=(mpc0, mpc1))
                 if A.scatter == "tile" and not facet else None)

@@ -1248,6 +1248,7 @@ __global__ void k_flag_cells(const int* __restrict__ dm, int nd, int bs, const i
 
 #include "mpcx_tile.cuh"
 #include "mpcx_tile_fused.cuh"
+#include "mpcx_rowgather.cuh"
 #include "mpcx_pattern_gpu.cuh"
 
 namespace
@@ -2077,6 +2078,70 @@ int mpcx_debug_set_trace(long long* buf)
   return cuda_check(cudaMemcpyToSymbol(g_trace, &buf, sizeof(buf)), "set_trace");
 }
 #endif
+
+int mpcx_row_plan_create(const mpcx_dofmap* dofmap, const int32_t* cells, int64_t num_cells, const int8_t* skip,
+                         const mpcx_csr* A, void* stream, mpcx_row_plan** plan_out)
+{
+  if (!dofmap || !A || !plan_out || num_cells < 0) return fail(MPCX_ERR_ARG, "null argument");
+  if (dofmap->bs < 1 || dofmap->num_dofs % dofmap->bs || A->nnz % ((long long)dofmap->bs * dofmap->bs))
+    return fail(MPCX_ERR_ARG, "the scalar CSR must be the bs x bs expansion of a block pattern");
+  RowPlan* P = nullptr;
+  int rc = row_plan_build(dofmap, cells, num_cells, skip, A, (cudaStream_t)stream, &P);
+  *plan_out = reinterpret_cast<mpcx_row_plan*>(P);
+  return rc;
+}
+
+void mpcx_row_plan_destroy(mpcx_row_plan* plan) { row_plan_free(reinterpret_cast<RowPlan*>(plan)); }
+
+int mpcx_assemble_matrix_rowgather_f64(const mpcx_integral* integral, const mpcx_mesh* mesh, const mpcx_dofmap* dofmap,
+                                       const int8_t* bc, const mpcx_mpc* mpc, const mpcx_csr* A, const mpcx_row_plan* plan,
+                                       void* stream)
+{
+  int rc = check_integral(integral, true);
+  if (rc) return rc;
+  if (!mesh || !dofmap || !mpc || !A || !plan) return fail(MPCX_ERR_ARG, "null argument");
+  const RowPlan* P = reinterpret_cast<const RowPlan*>(plan);
+  const mpcx_tables* t = integral->tables;
+  const int nd = t->nd, bs = t->bs;
+  if (integral->kernel != MPCX_KERNEL_ELASTICITY || integral->local_facets || nd != t->tdim + 1 || t->ng != t->tdim + 1
+      || bs != t->tdim || t->nd1 != 0)
+    return fail(MPCX_ERR_UNSUPPORTED, "the row-gather kernel covers P1 simplex elasticity with bs == gdim over cells");
+  if (dofmap->nd != nd || dofmap->bs != bs || P->nd != nd || P->bs != bs || P->nrows_b * bs != A->num_rows
+      || P->nnz_block * bs * bs != A->nnz)
+    return fail(MPCX_ERR_ARG, "row plan was built for a different space or matrix");
+  if (integral->slave_cells == nullptr && mpc->num_slaves > 0) return fail(MPCX_ERR_ARG, "the row-gather path needs the list of slave cells");
+  cudaStream_t s = (cudaStream_t)stream;
+  const IntD in = make_int(integral);
+  const MeshD md{mesh->x, mesh->x_dofmap, mesh->ng, mesh->x_stride};
+  const CsrD Ad{(const long long*)A->row_ptr, A->col, A->val};
+  const RowPlanD Pd{P->inc_off, P->inc, P->con_off, P->con, P->diag, P->nrows_b};
+  {
+    long long nb = (P->nrows_b + 7) / 8;
+    if (nb > 148LL * 64) nb = 148LL * 64;
+    if (nb < 1) nb = 1;
+    KernelTimer kt(s);  // dominant kernel of the call
+    MPCX_COUNT_LAUNCH();
+    if (t->tdim == 3) k_rowgather_elast_p1<3><<<(unsigned)nb, 256, 0, s>>>(Pd, in, md, dofmap->map, bc, Ad);
+    else k_rowgather_elast_p1<2><<<(unsigned)nb, 256, 0, s>>>(Pd, in, md, dofmap->map, bc, Ad);
+  }
+  if (in.nslave_cells > 0)  // cells holding slaves: elimination kernel, added on top of the stored rows
+  {
+    const Tab tab = make_tab(t);
+    const MpcD m = make_mpc(mpc);
+    const int n = nd * bs, wcount = in.cstride > 0 ? in.cstride : 1;
+    const int spw = 3 * mesh->ng + n * n + 3 * nd + wcount + (2 * nd + 2 * n + 2 + 1) / 2 + 1;
+    const size_t smem = (size_t)spw * 4 * sizeof(double);
+    if (smem > 48 * 1024)
+    {
+      rc = cuda_check(cudaFuncSetAttribute(k_matrix_generic<uint8_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "smem attr");
+      if (rc) return rc;
+    }
+    MPCX_COUNT_LAUNCH();
+    k_matrix_generic<uint8_t><<<grid_for_warps(in.nslave_cells, 4), 128, smem, s>>>(tab, in, md, dofmap->map, dofmap->map, nd, nd, bs, bs, bc, bc, m,
+                                                                                     m, Ad, (const uint8_t*)nullptr, 1, spw);
+  }
+  return cuda_check(cudaGetLastError(), "assemble_matrix_rowgather launch");
+}
 
 int mpcx_pattern_create(const mpcx_dofmap* dofmap0, const mpcx_dofmap* dofmap1, int64_t num_cells,
                         const mpcx_mpc* mpc0, const mpcx_mpc* mpc1, void* stream, mpcx_pattern** pattern_out,

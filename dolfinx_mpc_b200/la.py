@@ -46,6 +46,7 @@ class Matrix:
         self.max_block_row = max_block_row
         self._plans = {}
         self._tile_plans = {}
+        self._row_plans = []
         self._keepalive = {}  # objects whose id() keys a cached plan: kept alive so that the id cannot be reused
         # "tile": entries combined per 512-cell tile in shared memory, one reduction per (tile, entry), where a
         # tile kernel exists; "atomic": one red.global.add per element entry
@@ -189,12 +190,51 @@ class Matrix:
                                                       [int(v) for v in info])))
         return self._tile_plans[key]
 
+    def row_plan(self, form, integral, s_integral, key_extra=(), keepalive=()):
+        """Row plan (csrc/mpcx_rowgather.cuh) of one integral into this pattern, built on the device on first use;
+        None when the element has no row-gather kernel (P1 simplex elasticity with bs == gdim has)."""
+        V0, V1 = form.function_spaces
+        tab = form.tables(integral)
+        if not (V0 is V1 and int(integral.kernel) == 2 and integral.integral_type == "cell" and V0.nd == tab.tdim + 1
+                and tab.ng == tab.tdim + 1 and V0.bs == tab.tdim):
+            return None
+        key = ("row", id(V0), id(integral)) + tuple(key_extra)
+        if key not in self._tile_plans:
+            self._keepalive[key] = (V0, integral, keepalive)
+            lib = _lib.load()
+            ncells = int(s_integral.num_cells)
+            skip = None
+            if s_integral.num_slave_cells > 0:
+                skip = torch.zeros(ncells, dtype=torch.int8, device=_dev.device())
+                skip[integral._dev[[k for k in integral._dev if isinstance(k, tuple) and k[0] == "slave_cells"
+                                    and k[1:] == tuple(key_extra)][0]][0].long()] = 1
+            d0 = _dev.dofmap_struct(V0, self.shape[0])
+            A = self.struct()
+            handle = C.c_void_p()
+            try:
+                _lib.check(lib.mpcx_row_plan_create(C.byref(d0), s_integral.cells, ncells, _dev.ptr(skip), C.byref(A),
+                                                    _dev.stream_ptr(), C.byref(handle)))
+                _lib.check(lib.mpcx_device_error(_dev.stream_ptr()))
+            except _lib.MpcxError as e:  # e.g. a node shared by more than 255 cells: the atomic-scatter kernels take over
+                if getattr(e, "status", None) != _lib.ERR_UNSUPPORTED:
+                    raise
+                if handle:
+                    lib.mpcx_row_plan_destroy(handle)
+                self._tile_plans[key] = None
+                return None
+            self._row_plans.append(handle)
+            self._tile_plans[key] = (handle, {"row_plan": 1})
+        return self._tile_plans[key]
+
     def __del__(self):
         try:
             lib = _lib.load()
+            rows = set(h.value for h in self._row_plans)
             for entry in self._tile_plans.values():
-                if entry is not None:
+                if entry is not None and entry[0].value not in rows:
                     lib.mpcx_tile_plan_destroy(entry[0])
+            for h in self._row_plans:
+                lib.mpcx_row_plan_destroy(h)
         except Exception:
             pass
 

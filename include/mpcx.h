@@ -244,6 +244,21 @@ int mpcx_assemble_system_tiled_f64(const mpcx_integral* a_integral, const mpcx_i
                                    double* b, const mpcx_tile_plan* matrix_plan, const mpcx_tile_plan* vector_plan,
                                    void* stream);
 
+/* "Row gather" assembly of a blocked space (bs == gdim, P1 simplices, isotropic elasticity): one warp owns one block
+ * row, evaluates the cells around its node and STORES the finished row -- no atomics and no zero-fill: unlike every other
+ * routine here this one OVERWRITES A (all rows, zeros included) before the cells holding slaves are added by the
+ * elimination kernel, so it must be the first integral assembled into A and the caller must not zero A.  Replaces
+ * assemble_cells_impl + MatSetValuesBlockedLocal (cpp/assemble_matrix.cpp:417-548) for that element; the row plan
+ * (cells around every node, and for every block entry the (cell, i, j) contributions) is built once per pattern /
+ * dofmap / active cells / skip flags on the device.  One constraint and one bc marker array on both sides. */
+typedef struct mpcx_row_plan mpcx_row_plan;
+int mpcx_row_plan_create(const mpcx_dofmap* dofmap, const int32_t* cells, int64_t num_cells, const int8_t* skip,
+                         const mpcx_csr* A, void* stream, mpcx_row_plan** plan_out);
+void mpcx_row_plan_destroy(mpcx_row_plan* plan);
+int mpcx_assemble_matrix_rowgather_f64(const mpcx_integral* integral, const mpcx_mesh* mesh, const mpcx_dofmap* dofmap,
+                                       const int8_t* bc, const mpcx_mpc* mpc, const mpcx_csr* A, const mpcx_row_plan* plan,
+                                       void* stream);
+
 /* A[d, d] += diagval for the listed unrolled dofs.  Slave diagonal
  * (cpp/assemble_matrix.cpp:711-724) and Dirichlet diagonal
  * (python/src/dolfinx_mpc/assemble_matrix.py:59-62). */
