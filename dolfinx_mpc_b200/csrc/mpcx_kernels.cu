@@ -784,6 +784,56 @@ k_vector_affine_source(Tab t, IntD in, MeshD mesh, const int* __restrict__ dm, M
   }
 }
 
+// Thread per cell, P1 source vector of a BLOCKED space (bs = BS components, coefficient in the test space):
+// b_(i,a) = c0 vol / ((d+1)(d+2)) (f_(i,a) + sum_j f_(j,a)); elimination per entry as in modify_mpc_vec
+// (cpp/assemble_vector.h:52-68).  One RED per entry: 12 per tetrahedron for bs = 3.
+template <int TD, int BS>
+__global__ void __launch_bounds__(256)
+k_vector_p1_source_blocked(IntD in, MeshD mesh, const int* __restrict__ dm, MpcD m, double* __restrict__ b)
+{
+  constexpr int NV = TD + 1;
+  const long long index = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (index >= in.ncells) return;
+  const int cell = in.cells ? __ldg(in.cells + index) : (int)index;
+  int xd[NV], r[NV];
+#pragma unroll
+  for (int v = 0; v < NV; ++v)
+  {
+    xd[v] = __ldg(mesh.xd + (long long)cell * NV + v);
+    r[v] = __ldg(dm + (long long)cell * NV + v);
+  }
+  double X[NV][3];
+  load_vertices<TD>(mesh, xd, X);
+  P1Geom<TD> G;
+  p1_geometry<TD>(X, G);
+  const double s = in.c[0] * G.vol * (1.0 / double((TD + 1) * (TD + 2)));
+  const bool has_slaves = __ldg(m.c2s_off + cell + 1) > __ldg(m.c2s_off + cell);
+#pragma unroll
+  for (int a = 0; a < BS; ++a)
+  {
+    double f[NV], fs = 0.0;
+#pragma unroll
+    for (int v = 0; v < NV; ++v)
+    {
+      f[v] = in.coeffs ? __ldg(in.coeffs + index * in.cstride + v * BS + a)
+                       : __ldg(in.wnodal + (long long)__ldg(in.wmap + (long long)cell * NV + v) * BS + a);
+      fs += f[v];
+    }
+#pragma unroll
+    for (int v = 0; v < NV; ++v)
+    {
+      const double val = s * (f[v] + fs);
+      const int row = r[v] * BS + a;
+      int o0 = 0, o1 = 0;
+      if (has_slaves && m.is_slave[row]) { o0 = m.offsets[row]; o1 = m.offsets[row + 1]; }
+      if (o1 > o0)
+        for (int k = o0; k < o1; ++k) atomicAdd(b + m.masters[k], m.coeffs[k] * val);
+      else
+        atomicAdd(b + row, val);
+    }
+  }
+}
+
 // Closed-form scalar P1 element matrices in registers (affine simplex): Laplace, mass, Laplace with a
 // P1 coefficient (one-point rule at the centroid, which is what the tabulated degree-1 rule evaluates).
 template <int TD>
@@ -1568,6 +1618,16 @@ int mpcx_assemble_vector_f64(const mpcx_integral* integral, const mpcx_mesh* mes
     const long long nb = (in.ncells + 255) / 256;
     if (t->tdim == 3) MPCX_COUNT_LAUNCH(), k_vector_p1_source<3><<<(unsigned)nb, 256, 0, s>>>(in, md, dofmap->map, m.c2s_off, m, b, nullptr, 0);
     else MPCX_COUNT_LAUNCH(), k_vector_p1_source<2><<<(unsigned)nb, 256, 0, s>>>(in, md, dofmap->map, m.c2s_off, m, b, nullptr, 0);
+  }
+  else if (integral->kernel == MPCX_KERNEL_SOURCE && p1_simplex && (bs == 2 || bs == 3) && !integral->local_facets
+           && (in.coeffs ? in.cstride == n : (in.wnd == nd && in.wbs == bs)))
+  {
+    const unsigned nb = (unsigned)((in.ncells + 255) / 256);
+    MPCX_COUNT_LAUNCH();
+    if (t->tdim == 3 && bs == 3) k_vector_p1_source_blocked<3, 3><<<nb, 256, 0, s>>>(in, md, dofmap->map, m, b);
+    else if (t->tdim == 3) k_vector_p1_source_blocked<3, 2><<<nb, 256, 0, s>>>(in, md, dofmap->map, m, b);
+    else if (bs == 3) k_vector_p1_source_blocked<2, 3><<<nb, 256, 0, s>>>(in, md, dofmap->map, m, b);
+    else k_vector_p1_source_blocked<2, 2><<<nb, 256, 0, s>>>(in, md, dofmap->map, m, b);
   }
   else if (integral->kernel == MPCX_KERNEL_SOURCE && t->ng == t->tdim + 1 && n <= 32 && !integral->local_facets
            && (in.coeffs ? in.cstride == n : (in.wnd == nd && in.wbs == bs)))

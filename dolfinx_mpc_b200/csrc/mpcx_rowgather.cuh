@@ -29,7 +29,7 @@ struct RowPlan
   int* inc_off = nullptr;        // [nrows_b + 1] incidences (bulk cells around a node) of every block row
   unsigned* inc = nullptr;       // [n_inc] (position of the cell in the active list) * nd + local index of the node
   unsigned* con_off = nullptr;   // [nnz_block + 1] contributions of every block entry (block CSR order)
-  unsigned short* con = nullptr; // [n_con] (incidence within the row) << 4 | local column index j
+  unsigned short* con = nullptr; // [n_con] (incidence within the row) << 8 | local row index i << 4 | local column index j
   unsigned char* diag = nullptr; // [nrows_b] position of the diagonal block in its row
 };
 
@@ -88,7 +88,7 @@ __global__ void k_rp_low32(const unsigned long long* __restrict__ keys, long lon
   if (e < n) out[e] = (unsigned)(keys[e] & 0xffffffffull);
 }
 
-// one key per (incidence, local column j): (global block entry) << 12 | (incidence within the row) << 4 | j
+// one key per (incidence, local column j): (global block entry) << 16 | (incidence within the row) << 8 | i << 4 | j
 __global__ void k_rp_contrib_keys(const unsigned long long* __restrict__ ikeys, long long n_inc, const int* __restrict__ inc_off,
                                   const int* __restrict__ dm, int nd, int bs, const int* __restrict__ cells, CsrD A,
                                   unsigned long long* __restrict__ ckeys, unsigned char* __restrict__ diag)
@@ -98,6 +98,7 @@ __global__ void k_rp_contrib_keys(const unsigned long long* __restrict__ ikeys, 
   const long long I = (long long)(ikeys[e] >> 32);
   const unsigned low = (unsigned)(ikeys[e] & 0xffffffffull);
   const long long idx = low / nd;
+  const int il = (int)(low - idx * nd);
   const int cell = cells ? cells[idx] : (int)idx;
   const int klocal = (int)(e - inc_off[I]);
   const long long blk0 = A.rp[bs * I] / ((long long)bs * bs);
@@ -108,14 +109,14 @@ __global__ void k_rp_contrib_keys(const unsigned long long* __restrict__ ikeys, 
     const int k = blockcol_find(A, bs, I, J);
     if (k < 0) { g_dev_err = MPCX_ERR_PATTERN; ckeys[e * nd + j] = ~0ull; continue; }
     if (J == I) diag[I] = (unsigned char)k;
-    ckeys[e * nd + j] = ((unsigned long long)(blk0 + k) << 12) | ((unsigned long long)(klocal & 255) << 4) | (unsigned)j;
+    ckeys[e * nd + j] = ((unsigned long long)(blk0 + k) << 16) | ((unsigned long long)(klocal & 255) << 8) | ((unsigned)il << 4) | (unsigned)j;
   }
 }
 
 __global__ void k_rp_con(const unsigned long long* __restrict__ ckeys, long long n, unsigned short* __restrict__ con)
 {
   const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (e < n) con[e] = (unsigned short)(ckeys[e] & 0xfffull);
+  if (e < n) con[e] = (unsigned short)(ckeys[e] & 0xffffull);
 }
 
 // rows without any bulk cell still need their diagonal position (they are written as zeros; the value is unused)
@@ -147,7 +148,7 @@ int row_plan_build(const mpcx_dofmap* dm, const int32_t* cells, long long nc, co
   long long n_valid = 0;
   int last = 0;
   P->nd = nd; P->bs = bs; P->nrows_b = dm->num_dofs / bs; P->nnz_block = Acsr->nnz / ((long long)bs * bs);
-  if (nd > 16 || bs < 1 || P->nrows_b >= (1ll << 31) || n0 * nd >= (1ll << 32) || P->nnz_block >= (1ll << 40))
+  if (nd > 16 || bs < 1 || P->nrows_b >= (1ll << 31) || n0 * nd >= (1ll << 32) || P->nnz_block >= (1ll << 39))
   { rc = fail(MPCX_ERR_UNSUPPORTED, "row plan: sizes outside the plan format"); goto done; }
   RP_CK(cudaMalloc(&P->inc_off, sizeof(int) * (size_t)(P->nrows_b + 1)));
   RP_CK(cudaMalloc(&P->diag, (size_t)P->nrows_b + 1));
@@ -181,12 +182,12 @@ int row_plan_build(const mpcx_dofmap* dm, const int32_t* cells, long long nc, co
     if (e2 != cudaSuccess) { cudaFree(c1); rc = cuda_check(e2, "row plan alloc"); goto done; }
     k_rp_contrib_keys<<<(unsigned)((n_valid + 127) / 128), 128, 0, s>>>(k2, n_valid, P->inc_off, dm->map, nd, bs, cells, A, c1, P->diag);
     cudaFree(k1); k1 = nullptr;
-    e2 = cub::DeviceRadixSort::SortKeys(nullptr, tb, c1, c2, (int)P->n_con, 0, 52, s);
+    e2 = cub::DeviceRadixSort::SortKeys(nullptr, tb, c1, c2, (int)P->n_con, 0, 56, s);
     if (e2 == cudaSuccess) e2 = cudaMalloc(&tmp, tb);
-    if (e2 == cudaSuccess) e2 = cub::DeviceRadixSort::SortKeys(tmp, tb, c1, c2, (int)P->n_con, 0, 52, s);
+    if (e2 == cudaSuccess) e2 = cub::DeviceRadixSort::SortKeys(tmp, tb, c1, c2, (int)P->n_con, 0, 56, s);
     if (e2 == cudaSuccess)
     {
-      k_rp_lower<<<(unsigned)((P->nnz_block + 256) / 256), 256, 0, s>>>(c2, P->n_con, 12, P->nnz_block, nullptr, P->con_off);
+      k_rp_lower<<<(unsigned)((P->nnz_block + 256) / 256), 256, 0, s>>>(c2, P->n_con, 16, P->nnz_block, nullptr, P->con_off);
       k_rp_con<<<(unsigned)((P->n_con + 255) / 256), 256, 0, s>>>(c2, P->n_con, P->con);
       e2 = cudaStreamSynchronize(s);
     }
@@ -304,10 +305,8 @@ k_rowgather_elast_p1(RowPlanD P, IntD in, MeshD mesh, const int* __restrict__ dm
           for (unsigned q = c_lo; q < c_hi; ++q)
           {
             const unsigned cw = __ldg(P.con + q);
-            const int kl = (int)(cw >> 4) - ch, j = (int)(cw & 15u);
+            const int kl = (int)(cw >> 8) - ch, il = (int)((cw >> 4) & 15u), j = (int)(cw & 15u);
             if (kl < 0 || kl >= 32) continue;  // a cell of another chunk (rows with more than 32 cells only)
-            const unsigned w = __ldg(P.inc + i0 + ch + kl);
-            const int il = (int)(w % NV);
             const double* g = geo + kl * GS;
             double gi[TD], gj[TD];
 #pragma unroll
