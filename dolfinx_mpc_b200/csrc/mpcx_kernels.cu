@@ -2163,9 +2163,11 @@ int mpcx_assemble_matrix_rowgather_f64(const mpcx_integral* integral, const mpcx
   const RowPlan* P = reinterpret_cast<const RowPlan*>(plan);
   const mpcx_tables* t = integral->tables;
   const int nd = t->nd, bs = t->bs;
-  if (integral->kernel != MPCX_KERNEL_ELASTICITY || integral->local_facets || nd != t->tdim + 1 || t->ng != t->tdim + 1
+  const bool p1 = nd == t->tdim + 1;
+  const bool p2tet = t->tdim == 3 && nd == 10;
+  if (integral->kernel != MPCX_KERNEL_ELASTICITY || integral->local_facets || !(p1 || p2tet) || t->ng != t->tdim + 1
       || bs != t->tdim || t->nd1 != 0)
-    return fail(MPCX_ERR_UNSUPPORTED, "the row-gather kernel covers P1 simplex elasticity with bs == gdim over cells");
+    return fail(MPCX_ERR_UNSUPPORTED, "the row-gather kernels cover P1 simplex / P2 tetrahedron elasticity with bs == gdim over cells");
   if (dofmap->nd != nd || dofmap->bs != bs || P->nd != nd || P->bs != bs || P->nrows_b * bs != A->num_rows
       || P->nnz_block * bs * bs != A->nnz)
     return fail(MPCX_ERR_ARG, "row plan was built for a different space or matrix");
@@ -2181,7 +2183,12 @@ int mpcx_assemble_matrix_rowgather_f64(const mpcx_integral* integral, const mpcx
     if (nb < 1) nb = 1;
     KernelTimer kt(s);  // dominant kernel of the call
     MPCX_COUNT_LAUNCH();
-    if (t->tdim == 3) k_rowgather_elast_p1<3><<<(unsigned)nb, 256, 0, s>>>(Pd, in, md, dofmap->map, bc, Ad);
+    if (p2tet)
+    {
+      const size_t smem = sizeof(double) * (10 * 10 * 9 + 8 * 32 * 11);
+      k_rowgather_elast_affine3d<10><<<(unsigned)nb, 256, smem, s>>>(Pd, make_tab(t), in, md, dofmap->map, bc, Ad);
+    }
+    else if (t->tdim == 3) k_rowgather_elast_p1<3><<<(unsigned)nb, 256, 0, s>>>(Pd, in, md, dofmap->map, bc, Ad);
     else k_rowgather_elast_p1<2><<<(unsigned)nb, 256, 0, s>>>(Pd, in, md, dofmap->map, bc, Ad);
   }
   if (in.nslave_cells > 0)  // cells holding slaves: elimination kernel, added on top of the stored rows

@@ -192,10 +192,12 @@ class Matrix:
 
     def row_plan(self, form, integral, s_integral, key_extra=(), keepalive=()):
         """Row plan (csrc/mpcx_rowgather.cuh) of one integral into this pattern, built on the device on first use;
-        None when the element has no row-gather kernel (P1 simplex elasticity with bs == gdim has)."""
+        None when the element has no row-gather kernel (elasticity with bs == gdim on P1 simplices and P2 tetrahedra has)."""
         V0, V1 = form.function_spaces
         tab = form.tables(integral)
-        if not (V0 is V1 and int(integral.kernel) == 2 and integral.integral_type == "cell" and V0.nd == tab.tdim + 1
+        p1 = V0.nd == tab.tdim + 1
+        p2tet = tab.tdim == 3 and V0.nd == 10
+        if not (V0 is V1 and int(integral.kernel) == 2 and integral.integral_type == "cell" and (p1 or p2tet)
                 and tab.ng == tab.tdim + 1 and V0.bs == tab.tdim):
             return None
         key = ("row", id(V0), id(integral)) + tuple(key_extra)
