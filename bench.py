@@ -295,7 +295,8 @@ def cpu_reference(cfg: int, n: int, steps: int, warmup: int, budget_s: float, la
     matrix / vector with no communication, as `mpirun -n R` does; time of a step = slowest rank."""
     from oracle import oracle as orc
 
-    orc.build(march="native")
+    # the CPU arm runs a -march=native build of the oracle (BASELINE.md section 3); the tests keep the portable one
+    orc.LIB_PATH = orc.build(march="native", out=os.path.join(os.path.dirname(orc.LIB_PATH), "libmpc_oracle_native.so"))
     cores = os.cpu_count() or 1
     per_step = budget_s / max(1, steps + warmup)
     probs, what, full = cpu_rank_problems(cfg, n, cores, CPU_RATE_GUESS[cfg] * cores * per_step)

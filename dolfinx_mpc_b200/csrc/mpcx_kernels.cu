@@ -2183,13 +2183,23 @@ int mpcx_assemble_matrix_rowgather_f64(const mpcx_integral* integral, const mpcx
     if (nb < 1) nb = 1;
     KernelTimer kt(s);  // dominant kernel of the call
     MPCX_COUNT_LAUNCH();
+    const Tab tb = make_tab(t);
     if (p2tet)
     {
-      const size_t smem = sizeof(double) * (10 * 10 * 9 + 8 * 32 * 11);
-      k_rowgather_elast_affine3d<10><<<(unsigned)nb, 256, smem, s>>>(Pd, make_tab(t), in, md, dofmap->map, bc, Ad);
+      using E = RgAffineTet<10>;
+      const size_t smem = sizeof(double) * (E::SMEM_TABLE + 8 * 32 * E::GS);
+      k_rowgather_elast<E, 2><<<(unsigned)nb, 256, smem, s>>>(Pd, tb, in, md, bc, Ad);
     }
-    else if (t->tdim == 3) k_rowgather_elast_p1<3><<<(unsigned)nb, 256, 0, s>>>(Pd, in, md, dofmap->map, bc, Ad);
-    else k_rowgather_elast_p1<2><<<(unsigned)nb, 256, 0, s>>>(Pd, in, md, dofmap->map, bc, Ad);
+    else if (t->tdim == 3)
+    {
+      using E = RgP1<3>;
+      k_rowgather_elast<E, 3><<<(unsigned)nb, 256, sizeof(double) * 8 * 32 * E::GS, s>>>(Pd, tb, in, md, bc, Ad);
+    }
+    else
+    {
+      using E = RgP1<2>;
+      k_rowgather_elast<E, 3><<<(unsigned)nb, 256, sizeof(double) * 8 * 32 * E::GS, s>>>(Pd, tb, in, md, bc, Ad);
+    }
   }
   if (in.nslave_cells > 0)  // cells holding slaves: elimination kernel, added on top of the stored rows
   {

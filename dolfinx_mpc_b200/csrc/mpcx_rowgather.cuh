@@ -214,37 +214,150 @@ struct RowPlanD
   long long nrows_b;
 };
 
-// One warp per block row.  TD = tdim = gdim = bs, P1 (nd = TD + 1).
-template <int TD>
-__global__ void __launch_bounds__(256)
-k_rowgather_elast_p1(RowPlanD P, IntD in, MeshD mesh, const int* __restrict__ dm, const int8_t* __restrict__ bc, CsrD A)
+// ---- element policies: what a cell lane stages, and how a (cell, i, j) contribution is formed from the staged data
+// P1 simplex (TD = tdim = gdim = bs): the gradients of the barycentric coordinates and the volume (13 doubles in 3-D);
+// block = vol (mu g_i[b] g_j[a] + lambda g_i[a] g_j[b] + delta_ab mu g_i.g_j)
+template <int TD_>
+struct RgP1
 {
-  constexpr int NV = TD + 1, BS = TD, GS = NV * TD + 1;  // doubles per staged cell: gradients + volume
-  __shared__ double geo_all[8][32 * GS];
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  double* geo = geo_all[warp];
+  static constexpr int TD = TD_, ND = TD_ + 1, BS = TD_, GS = ND * TD_ + 1, SMEM_TABLE = 0;
+  __device__ static void init(const Tab&, double*) {}
+  __device__ static void stage(const P1Geom<TD>& G, double* g)
+  {
+#pragma unroll
+    for (int v = 0; v < ND; ++v)
+#pragma unroll
+      for (int k = 0; k < TD; ++k) g[v * TD + k] = G.g[v][k];
+    g[ND * TD] = G.vol;
+  }
+  __device__ static void add(const double*, const double* g, int il, int j, double mu, double lmbda, double (*acc)[BS])
+  {
+    double gi[TD], gj[TD];
+#pragma unroll
+    for (int k = 0; k < TD; ++k) { gi[k] = g[il * TD + k]; gj[k] = g[j * TD + k]; }
+    const double vol = g[ND * TD];
+    double dot = 0.0;
+#pragma unroll
+    for (int k = 0; k < TD; ++k) dot += gi[k] * gj[k];
+#pragma unroll
+    for (int a = 0; a < BS; ++a)
+#pragma unroll
+      for (int b = 0; b < BS; ++b) acc[a][b] += vol * (mu * gi[b] * gj[a] + lmbda * gi[a] * gj[b] + (a == b ? mu * dot : 0.0));
+  }
+};
+
+// Any Lagrange element on AFFINE tetrahedra, bs == 3 (P2: ND = 10; BASELINE config 3).  With a constant Jacobian the
+// quadrature collapses into reference tables: for a node pair (i, j)
+//   G = sum_q w_q grad phi_i (x) grad phi_j = K^T M_ij K,   M_ij[al][be] = sum_q w_q d_al phi_i(q) d_be phi_j(q),
+// K = J^-1 (K[al][k] = d xi_al / d x_k), and the block is |det J| (mu G^T + lambda G + mu tr(G) I).  A cell lane stages
+// K and |det J|; the M_ij of the element (ND^2 x 9 doubles, 7.2 KB for P2) sit in shared memory for the whole block: a
+// contribution costs 54 + 15 FMAs instead of a quadrature loop.
+template <int ND_>
+struct RgAffineTet
+{
+  static constexpr int TD = 3, ND = ND_, BS = 3, GS = 11, SMEM_TABLE = ND_ * ND_ * 9;
+  __device__ static void init(const Tab& t, double* M)
+  {
+    for (int e = threadIdx.x; e < ND * ND * 9; e += blockDim.x)
+    {
+      const int ij = e / 9, ab = e - ij * 9, i = ij / ND, j = ij - i * ND, al = ab / 3, be = ab - al * 3;
+      double acc = 0.0;
+      for (int q = 0; q < t.nq; ++q)
+        acc += __ldg(t.w + q) * __ldg(t.dphi + (q * 3 + al) * ND + i) * __ldg(t.dphi + (q * 3 + be) * ND + j);
+      M[e] = acc;
+    }
+  }
+  __device__ static void stage(const P1Geom<3>& G, double* g)
+  {
+    // rows of J^-1 = gradients of the barycentric coordinates 1..3; |det J| = 6 vol
+#pragma unroll
+    for (int al = 0; al < 3; ++al)
+#pragma unroll
+      for (int k = 0; k < 3; ++k) g[al * 3 + k] = G.g[al + 1][k];
+    g[9] = 6.0 * G.vol;
+  }
+  __device__ static void add(const double* M, const double* g, int i, int j, double mu, double lmbda, double (*acc)[BS])
+  {
+    const double* m = M + (i * ND + j) * 9;
+    double T[3][3], Gm[3][3];
+#pragma unroll
+    for (int al = 0; al < 3; ++al)
+#pragma unroll
+      for (int l = 0; l < 3; ++l) T[al][l] = m[al * 3] * g[l] + m[al * 3 + 1] * g[3 + l] + m[al * 3 + 2] * g[6 + l];
+#pragma unroll
+    for (int k = 0; k < 3; ++k)
+#pragma unroll
+      for (int l = 0; l < 3; ++l) Gm[k][l] = g[k] * T[0][l] + g[3 + k] * T[1][l] + g[6 + k] * T[2][l];
+    const double dj = g[9], tr = mu * (Gm[0][0] + Gm[1][1] + Gm[2][2]);
+#pragma unroll
+    for (int a = 0; a < BS; ++a)
+#pragma unroll
+      for (int b = 0; b < BS; ++b) acc[a][b] += dj * (mu * Gm[b][a] + lmbda * Gm[a][b] + (a == b ? tr : 0.0));
+  }
+};
+
+// One warp per block row.  Global-load latency is what this kernel fights (three dependent levels: row header ->
+// incidence / contribution lists -> dofmap -> coordinates): the header of the warp's NEXT row is requested while the
+// current one is processed, the incidence word, the column's contribution words (8 at a time, in registers) and its
+// Dirichlet flags are requested at the top of the row, before the cell phase.
+template <typename E, int MINB>
+__global__ void __launch_bounds__(256, MINB)
+k_rowgather_elast(RowPlanD P, Tab t, IntD in, MeshD mesh, const int8_t* __restrict__ bc, CsrD A)
+{
+  constexpr int TD = E::TD, ND = E::ND, BS = E::BS, GS = E::GS, NG = TD + 1, CW = 8;
+  extern __shared__ double rg_smem[];
+  double* M = rg_smem;                              // element tables (affine policy)
+  double* geo = rg_smem + E::SMEM_TABLE + (threadIdx.x >> 5) * 32 * GS;  // [32 cells][GS] of this warp
+  E::init(t, M);
+  if (E::SMEM_TABLE) __syncthreads();
+  const int lane = threadIdx.x & 31;
   const double mu = in.c[0], lmbda = in.c[1];
   const long long wstride = (long long)gridDim.x * 8;
-  for (long long I = (long long)blockIdx.x * 8 + warp; I < P.nrows_b; I += wstride)
+  long long I = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (I >= P.nrows_b) return;
+  int i0 = __ldg(P.inc_off + I), i1 = __ldg(P.inc_off + I + 1), kd = __ldg(P.diag + I);
+  long long r0 = __ldg(A.rp + BS * I), r1 = __ldg(A.rp + BS * I + 1);
+  for (;;)
   {
-    const int i0 = __ldg(P.inc_off + I), ninc = __ldg(P.inc_off + I + 1) - i0;
-    const long long r0 = __ldg(A.rp + BS * I);
-    const int nb = (int)((__ldg(A.rp + BS * I + 1) - r0) / BS);
+    const long long In = I + wstride;
+    const bool more = In < P.nrows_b;
+    int n_i0 = 0, n_i1 = 0, n_kd = 0;
+    long long n_r0 = 0, n_r1 = 0;
+    if (more)
+    {
+      n_i0 = __ldg(P.inc_off + In); n_i1 = __ldg(P.inc_off + In + 1); n_kd = __ldg(P.diag + In);
+      n_r0 = __ldg(A.rp + BS * In); n_r1 = __ldg(A.rp + BS * In + 1);
+    }
+    const int ninc = i1 - i0, nb = (int)((r1 - r0) / BS);
     const long long blk0 = r0 / (BS * BS);
-    const int kd = __ldg(P.diag + I);
     bool bcr[BS];
 #pragma unroll
     for (int a = 0; a < BS; ++a) bcr[a] = bc ? bc[BS * I + a] != 0 : false;
-    for (int cc = 0; cc < nb; cc += 32)  // block columns of the row, 32 at a time (one pass for P1 meshes)
+    for (int cc = 0; cc < nb; cc += 32)  // block columns of the row, 32 at a time (one pass on P1 meshes)
     {
       const int kc = cc + lane;
+      const bool col_ok = kc < nb;
       double acc[BS][BS];
 #pragma unroll
       for (int a = 0; a < BS; ++a)
 #pragma unroll
         for (int b = 0; b < BS; ++b) acc[a][b] = 0.0;
+      // requests of this pass: contribution range, column node (for its Dirichlet flags), first incidence word
       unsigned c_lo = 0, c_hi = 0;
-      if (kc < nb) { c_lo = __ldg(P.con_off + blk0 + kc); c_hi = __ldg(P.con_off + blk0 + kc + 1); }
+      int J = 0;
+      if (col_ok)
+      {
+        c_lo = __ldg(P.con_off + blk0 + kc); c_hi = __ldg(P.con_off + blk0 + kc + 1);
+        J = __ldg(A.col + r0 + (long long)BS * kc) / BS;
+      }
+      unsigned w0 = lane < ninc ? __ldg(P.inc + i0 + lane) : 0u;
+      unsigned short cw[CW];
+#pragma unroll
+      for (int u = 0; u < CW; ++u) cw[u] = (col_ok && c_lo + u < c_hi) ? __ldg(P.con + c_lo + u) : (unsigned short)0xffffu;
+      bool bcc[BS];
+#pragma unroll
+      for (int b = 0; b < BS; ++b) bcc[b] = (bc && col_ok) ? bc[BS * J + b] != 0 : false;
+      const bool diag_here = kd >= cc && kd < cc + 32;
       for (int ch = 0; ch < ninc || ch == 0; ch += 32)  // the cells around the node, 32 at a time
       {
         // ---- lanes = cells: affine geometry -> shared memory; diagonal block reduced with shuffles
@@ -256,185 +369,20 @@ k_rowgather_elast_p1(RowPlanD P, IntD in, MeshD mesh, const int* __restrict__ dm
         __syncwarp();
         if (ch + lane < ninc)
         {
-          const unsigned w = __ldg(P.inc + i0 + ch + lane);
-          const long long idx = w / NV;
-          const int il = (int)(w - idx * NV);
+          const unsigned w = ch == 0 ? w0 : __ldg(P.inc + i0 + ch + lane);
+          const long long idx = w / ND;
+          const int il = (int)(w - idx * ND);
           const int cell = in.cells ? __ldg(in.cells + idx) : (int)idx;
-          int xd[NV];
+          int xd[NG];
 #pragma unroll
-          for (int v = 0; v < NV; ++v) xd[v] = __ldg(mesh.xd + (long long)cell * NV + v);
-          double X[NV][3];
+          for (int v = 0; v < NG; ++v) xd[v] = __ldg(mesh.xd + (long long)cell * NG + v);
+          double X[NG][3];
           load_vertices<TD>(mesh, xd, X);
           P1Geom<TD> G;
           p1_geometry<TD>(X, G);
           double* g = geo + lane * GS;
-#pragma unroll
-          for (int v = 0; v < NV; ++v)
-#pragma unroll
-            for (int k = 0; k < TD; ++k) g[v * TD + k] = G.g[v][k];
-          g[NV * TD] = G.vol;
-          double gi[TD];
-#pragma unroll
-          for (int v = 0; v < NV; ++v)
-            if (v == il)
-            {
-#pragma unroll
-              for (int k = 0; k < TD; ++k) gi[k] = G.g[v][k];
-            }
-          double dot = 0.0;
-#pragma unroll
-          for (int k = 0; k < TD; ++k) dot += gi[k] * gi[k];
-#pragma unroll
-          for (int a = 0; a < BS; ++a)
-#pragma unroll
-            for (int b = 0; b < BS; ++b) dg[a][b] = G.vol * ((mu + lmbda) * gi[a] * gi[b] + (a == b ? mu * dot : 0.0));
-        }
-#pragma unroll
-        for (int a = 0; a < BS; ++a)
-#pragma unroll
-          for (int b = 0; b < BS; ++b)
-          {
-            double v = dg[a][b];
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-            if (kc == kd) acc[a][b] += v;
-          }
-        __syncwarp();
-        // ---- lanes = block columns: the contributions of the column that come from this chunk of cells
-        if (kc < nb && kc != kd)
-          for (unsigned q = c_lo; q < c_hi; ++q)
-          {
-            const unsigned cw = __ldg(P.con + q);
-            const int kl = (int)(cw >> 8) - ch, il = (int)((cw >> 4) & 15u), j = (int)(cw & 15u);
-            if (kl < 0 || kl >= 32) continue;  // a cell of another chunk (rows with more than 32 cells only)
-            const double* g = geo + kl * GS;
-            double gi[TD], gj[TD];
-#pragma unroll
-            for (int k = 0; k < TD; ++k) { gi[k] = g[il * TD + k]; gj[k] = g[j * TD + k]; }
-            const double vol = g[NV * TD];
-            double dot = 0.0;
-#pragma unroll
-            for (int k = 0; k < TD; ++k) dot += gi[k] * gj[k];
-#pragma unroll
-            for (int a = 0; a < BS; ++a)
-#pragma unroll
-              for (int b = 0; b < BS; ++b)
-                acc[a][b] += vol * (mu * gi[b] * gj[a] + lmbda * gi[a] * gj[b] + (a == b ? mu * dot : 0.0));
-          }
-      }
-      // ---- the row is written once (Dirichlet rows / columns zeroed, cpp/assemble_matrix.cpp:513-533)
-      if (kc < nb)
-      {
-        const int J = __ldg(A.col + r0 + (long long)BS * kc) / BS;
-#pragma unroll
-        for (int a = 0; a < BS; ++a)
-        {
-          double* dst = A.val + __ldg(A.rp + BS * I + a) + (long long)BS * kc;
-#pragma unroll
-          for (int b = 0; b < BS; ++b)
-          {
-            const bool z = bcr[a] || (bc && bc[BS * J + b] != 0);
-            dst[b] = z ? 0.0 : acc[a][b];
-          }
-        }
-      }
-    }
-  }
-}
-// The same row-gather scheme for ANY Lagrange element on affine tetrahedra with bs == 3 (P2: ND = 10; BASELINE config 3).
-// With a constant Jacobian the quadrature collapses into reference tables: for a node pair (i, j)
-//   G = sum_q w_q grad phi_i (x) grad phi_j = K^T M_ij K,   M_ij[al][be] = sum_q w_q d_al phi_i(q) d_be phi_j(q),
-// K = J^-1 (K[al][k] = d xi_al / d x_k), and the 3 x 3 block is |det J| (mu G^T + lambda G + mu tr(G) I).  The cell lanes
-// stage K and |det J| (10 doubles per cell), the M_ij of the element (ND^2 x 9 doubles, 7.2 KB for P2) sit in shared
-// memory for the whole block; a contribution costs 54 + 15 FMAs instead of a quadrature loop.
-template <int ND>
-__global__ void __launch_bounds__(256)
-k_rowgather_elast_affine3d(RowPlanD P, Tab t, IntD in, MeshD mesh, const int* __restrict__ dm, const int8_t* __restrict__ bc, CsrD A)
-{
-  constexpr int BS = 3, GS = 11;  // doubles per staged cell: K (9) + |det J| (+ 1 of padding: odd stride)
-  extern __shared__ double rg_smem[];
-  double* M = rg_smem;                       // [ND][ND][3][3]
-  double* geo_all = rg_smem + ND * ND * 9;   // [8 warps][32 cells][GS]
-  for (int e = threadIdx.x; e < ND * ND * 9; e += blockDim.x)
-  {
-    const int ij = e / 9, ab = e - ij * 9, i = ij / ND, j = ij - i * ND, al = ab / 3, be = ab - al * 3;
-    double acc = 0.0;
-    for (int q = 0; q < t.nq; ++q)
-      acc += __ldg(t.w + q) * __ldg(t.dphi + (q * 3 + al) * ND + i) * __ldg(t.dphi + (q * 3 + be) * ND + j);
-    M[e] = acc;
-  }
-  __syncthreads();
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  double* geo = geo_all + warp * 32 * GS;
-  const double mu = in.c[0], lmbda = in.c[1];
-  // block (i, j) of one cell from its staged K, |det J|: acc += |det J| (mu G^T + lambda G + mu tr(G) I), G = K^T M_ij K
-  auto add_block = [&](const double* g, int i, int j, double (*acc)[BS]) {
-    const double* m = M + (i * ND + j) * 9;
-    double T[3][3], G[3][3];
-#pragma unroll
-    for (int al = 0; al < 3; ++al)
-#pragma unroll
-      for (int l = 0; l < 3; ++l) T[al][l] = m[al * 3] * g[l] + m[al * 3 + 1] * g[3 + l] + m[al * 3 + 2] * g[6 + l];
-#pragma unroll
-    for (int k = 0; k < 3; ++k)
-#pragma unroll
-      for (int l = 0; l < 3; ++l) G[k][l] = g[k] * T[0][l] + g[3 + k] * T[1][l] + g[6 + k] * T[2][l];
-    const double dj = g[9], tr = mu * (G[0][0] + G[1][1] + G[2][2]);
-#pragma unroll
-    for (int a = 0; a < BS; ++a)
-#pragma unroll
-      for (int b = 0; b < BS; ++b) acc[a][b] += dj * (mu * G[b][a] + lmbda * G[a][b] + (a == b ? tr : 0.0));
-  };
-  const long long wstride = (long long)gridDim.x * 8;
-  for (long long I = (long long)blockIdx.x * 8 + warp; I < P.nrows_b; I += wstride)
-  {
-    const int i0 = __ldg(P.inc_off + I), ninc = __ldg(P.inc_off + I + 1) - i0;
-    const long long r0 = __ldg(A.rp + BS * I);
-    const int nb = (int)((__ldg(A.rp + BS * I + 1) - r0) / BS);
-    const long long blk0 = r0 / (BS * BS);
-    const int kd = __ldg(P.diag + I);
-    bool bcr[BS];
-#pragma unroll
-    for (int a = 0; a < BS; ++a) bcr[a] = bc ? bc[BS * I + a] != 0 : false;
-    for (int cc = 0; cc < nb; cc += 32)
-    {
-      const int kc = cc + lane;
-      double acc[BS][BS];
-#pragma unroll
-      for (int a = 0; a < BS; ++a)
-#pragma unroll
-        for (int b = 0; b < BS; ++b) acc[a][b] = 0.0;
-      unsigned c_lo = 0, c_hi = 0;
-      if (kc < nb) { c_lo = __ldg(P.con_off + blk0 + kc); c_hi = __ldg(P.con_off + blk0 + kc + 1); }
-      const bool diag_here = kd >= cc && kd < cc + 32;
-      for (int ch = 0; ch < ninc || ch == 0; ch += 32)
-      {
-        double dg[BS][BS];
-#pragma unroll
-        for (int a = 0; a < BS; ++a)
-#pragma unroll
-          for (int b = 0; b < BS; ++b) dg[a][b] = 0.0;
-        __syncwarp();
-        if (ch + lane < ninc)
-        {
-          const unsigned w = __ldg(P.inc + i0 + ch + lane);
-          const long long idx = w / ND;
-          const int il = (int)(w - idx * ND);
-          const int cell = in.cells ? __ldg(in.cells + idx) : (int)idx;
-          int xd[4];
-#pragma unroll
-          for (int v = 0; v < 4; ++v) xd[v] = __ldg(mesh.xd + (long long)cell * 4 + v);
-          double X[4][3];
-          load_vertices<3>(mesh, xd, X);
-          P1Geom<3> Gm;
-          p1_geometry<3>(X, Gm);  // rows of J^-1 = gradients of the barycentric coordinates 1..3; |det J| = 6 vol
-          double* g = geo + lane * GS;
-#pragma unroll
-          for (int al = 0; al < 3; ++al)
-#pragma unroll
-            for (int k = 0; k < 3; ++k) g[al * 3 + k] = Gm.g[al + 1][k];
-          g[9] = 6.0 * Gm.vol;
-          if (diag_here) add_block(g, il, il, dg);  // reads back this lane's own stores
+          E::stage(G, g);
+          if (diag_here) E::add(M, g, il, il, mu, lmbda, dg);  // reads back this lane's own stores
         }
         if (diag_here)
         {
@@ -450,31 +398,39 @@ k_rowgather_elast_affine3d(RowPlanD P, Tab t, IntD in, MeshD mesh, const int* __
             }
         }
         __syncwarp();
-        if (kc < nb && kc != kd)
-          for (unsigned q = c_lo; q < c_hi; ++q)
-          {
-            const unsigned cw = __ldg(P.con + q);
-            const int kl = (int)(cw >> 8) - ch, il = (int)((cw >> 4) & 15u), j = (int)(cw & 15u);
-            if (kl < 0 || kl >= 32) continue;
-            add_block(geo + kl * GS, il, j, acc);
-          }
-      }
-      if (kc < nb)
-      {
-        const int J = __ldg(A.col + r0 + (long long)BS * kc) / BS;
-#pragma unroll
-        for (int a = 0; a < BS; ++a)
+        // ---- lanes = block columns: the contributions of the column that come from this chunk of cells
+        if (col_ok && kc != kd)
         {
-          double* dst = A.val + __ldg(A.rp + BS * I + a) + (long long)BS * kc;
 #pragma unroll
-          for (int b = 0; b < BS; ++b)
+          for (int u = 0; u < CW; ++u)
           {
-            const bool z = bcr[a] || (bc && bc[BS * J + b] != 0);
-            dst[b] = z ? 0.0 : acc[a][b];
+            const unsigned c = cw[u];
+            const int kl = (int)(c >> 8) - ch;
+            if (c != 0xffffu && kl >= 0 && kl < 32) E::add(M, geo + kl * GS, (int)((c >> 4) & 15u), (int)(c & 15u), mu, lmbda, acc);
+          }
+          for (unsigned q = c_lo + CW; q < c_hi; ++q)  // columns fed by more than CW cells (rare)
+          {
+            const unsigned c = __ldg(P.con + q);
+            const int kl = (int)(c >> 8) - ch;
+            if (kl >= 0 && kl < 32) E::add(M, geo + kl * GS, (int)((c >> 4) & 15u), (int)(c & 15u), mu, lmbda, acc);
           }
         }
       }
+      // ---- the row is written once (Dirichlet rows / columns zeroed, cpp/assemble_matrix.cpp:513-533); scalar row
+      // BS I + a starts at r0 + a BS nb
+      if (col_ok)
+      {
+#pragma unroll
+        for (int a = 0; a < BS; ++a)
+        {
+          double* dst = A.val + r0 + (long long)a * BS * nb + (long long)BS * kc;
+#pragma unroll
+          for (int b = 0; b < BS; ++b) dst[b] = (bcr[a] || bcc[b]) ? 0.0 : acc[a][b];
+        }
+      }
     }
+    if (!more) break;
+    I = In; i0 = n_i0; i1 = n_i1; kd = n_kd; r0 = n_r0; r1 = n_r1;
   }
 }
 }  // namespace
