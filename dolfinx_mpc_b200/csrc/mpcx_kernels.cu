@@ -2184,21 +2184,44 @@ int mpcx_assemble_matrix_rowgather_f64(const mpcx_integral* integral, const mpcx
     KernelTimer kt(s);  // dominant kernel of the call
     MPCX_COUNT_LAUNCH();
     const Tab tb = make_tab(t);
+    const char* v1 = getenv("MPCX_ROWGATHER_V1");  // tuning: the one-row-per-warp kernel
+    const bool two = !(v1 && v1[0] == '1');
+    if (two)
+    {
+      nb = (P->nrows_b + 15) / 16;
+      if (nb > 148LL * 64) nb = 148LL * 64;
+      if (nb < 1) nb = 1;
+    }
     if (p2tet)
     {
       using E = RgAffineTet<10>;
-      const size_t smem = sizeof(double) * (E::SMEM_TABLE + 8 * 32 * E::GS);
-      k_rowgather_elast<E, 2><<<(unsigned)nb, 256, smem, s>>>(Pd, tb, in, md, bc, Ad);
+      const size_t smem = sizeof(double) * (E::SMEM_TABLE + (two ? 16 : 8) * 32 * E::GS);
+      if (two)
+      {
+        rc = cuda_check(cudaFuncSetAttribute(k_rowgather_elast2<E, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "smem attr");
+        if (rc) return rc;
+        k_rowgather_elast2<E, 2><<<(unsigned)nb, 256, smem, s>>>(Pd, tb, in, md, bc, Ad);
+      }
+      else k_rowgather_elast<E, 2><<<(unsigned)nb, 256, smem, s>>>(Pd, tb, in, md, bc, Ad);
     }
     else if (t->tdim == 3)
     {
       using E = RgP1<3>;
-      k_rowgather_elast<E, 3><<<(unsigned)nb, 256, sizeof(double) * 8 * 32 * E::GS, s>>>(Pd, tb, in, md, bc, Ad);
+      const size_t smem = sizeof(double) * (two ? 16 : 8) * 32 * E::GS;
+      if (two)
+      {
+        rc = cuda_check(cudaFuncSetAttribute(k_rowgather_elast2<E, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "smem attr");
+        if (rc) return rc;
+        k_rowgather_elast2<E, 3><<<(unsigned)nb, 256, smem, s>>>(Pd, tb, in, md, bc, Ad);
+      }
+      else k_rowgather_elast<E, 3><<<(unsigned)nb, 256, smem, s>>>(Pd, tb, in, md, bc, Ad);
     }
     else
     {
       using E = RgP1<2>;
-      k_rowgather_elast<E, 3><<<(unsigned)nb, 256, sizeof(double) * 8 * 32 * E::GS, s>>>(Pd, tb, in, md, bc, Ad);
+      const size_t smem = sizeof(double) * (two ? 16 : 8) * 32 * E::GS;
+      if (two) k_rowgather_elast2<E, 3><<<(unsigned)nb, 256, smem, s>>>(Pd, tb, in, md, bc, Ad);
+      else k_rowgather_elast<E, 3><<<(unsigned)nb, 256, smem, s>>>(Pd, tb, in, md, bc, Ad);
     }
   }
   if (in.nslave_cells > 0)  // cells holding slaves: elimination kernel, added on top of the stored rows

@@ -433,4 +433,163 @@ k_rowgather_elast(RowPlanD P, Tab t, IntD in, MeshD mesh, const int8_t* __restri
     I = In; i0 = n_i0; i1 = n_i1; kd = n_kd; r0 = n_r0; r1 = n_r1;
   }
 }
+// Two block rows per warp (16 lanes each): P1 rows have ~15 block columns and ~24 cells, so a whole warp per row left
+// half of the lanes idle in the contribution loop and one row's chain of dependent global loads in flight per warp.
+// All cells of a row (up to 32 per pass) are staged first, 16 at a time, then the columns are walked 16 at a time
+// without re-staging.  Rows with more than 32 cells take further passes that add onto the stored row (same lanes own
+// the same entries: plain read-modify-write, no atomics).
+template <typename E, int MINB>
+__global__ void __launch_bounds__(256, MINB)
+k_rowgather_elast2(RowPlanD P, Tab t, IntD in, MeshD mesh, const int8_t* __restrict__ bc, CsrD A)
+{
+  constexpr int TD = E::TD, ND = E::ND, BS = E::BS, GS = E::GS, NG = TD + 1, CW = 8;
+  extern __shared__ double rg_smem[];
+  double* M = rg_smem;
+  const int lane = threadIdx.x & 31, sub = lane >> 4, sl = lane & 15;
+  double* geo = rg_smem + E::SMEM_TABLE + ((threadIdx.x >> 5) * 2 + sub) * 32 * GS;  // [32 cells][GS] of this half-warp
+  E::init(t, M);
+  if (E::SMEM_TABLE) __syncthreads();
+  const double mu = in.c[0], lmbda = in.c[1];
+  const long long wstride = (long long)gridDim.x * 16;  // rows per sweep of the grid (8 warps x 2 rows per block)
+  long long I = ((long long)blockIdx.x * 8 + (threadIdx.x >> 5)) * 2 + sub;
+  if (I - sub >= P.nrows_b) return;  // both rows of the warp are past the end
+  auto hdr = [&](long long row, int& i0, int& i1, int& kd, long long& r0, long long& r1) {
+    i0 = i1 = kd = 0; r0 = r1 = 0;
+    if (row < P.nrows_b)
+    {
+      i0 = __ldg(P.inc_off + row); i1 = __ldg(P.inc_off + row + 1); kd = __ldg(P.diag + row);
+      r0 = __ldg(A.rp + BS * row); r1 = __ldg(A.rp + BS * row + 1);
+    }
+  };
+  int i0, i1, kd;
+  long long r0, r1;
+  hdr(I, i0, i1, kd, r0, r1);
+  for (;;)
+  {
+    const long long In = I + wstride;
+    const bool more = In - sub < P.nrows_b;  // warp-uniform
+    int n_i0, n_i1, n_kd;
+    long long n_r0, n_r1;
+    hdr(In, n_i0, n_i1, n_kd, n_r0, n_r1);
+    const int ninc = i1 - i0, nb = (int)((r1 - r0) / BS);
+    const long long blk0 = r0 / (BS * BS);
+    const int ninc_w = max(__shfl_sync(0xffffffffu, ninc, 0), __shfl_sync(0xffffffffu, ninc, 16));
+    const int nb_w = max(__shfl_sync(0xffffffffu, nb, 0), __shfl_sync(0xffffffffu, nb, 16));
+    bool bcr[BS];
+#pragma unroll
+    for (int a = 0; a < BS; ++a) bcr[a] = (bc && nb > 0) ? bc[BS * I + a] != 0 : false;
+    // requests for the first 16 columns, issued before the cell phase
+    unsigned c_lo = 0, c_hi = 0;
+    int J = 0;
+    if (sl < nb)
+    {
+      c_lo = __ldg(P.con_off + blk0 + sl); c_hi = __ldg(P.con_off + blk0 + sl + 1);
+      J = __ldg(A.col + r0 + (long long)BS * sl) / BS;
+    }
+    for (int sc = 0; sc < ninc_w || sc == 0; sc += 32)
+    {
+      // ---- lanes = cells (two steps of 16): affine geometry -> shared memory; diagonal block reduced over the half-warp
+      double dg[BS][BS];
+#pragma unroll
+      for (int a = 0; a < BS; ++a)
+#pragma unroll
+        for (int b = 0; b < BS; ++b) dg[a][b] = 0.0;
+      __syncwarp();
+#pragma unroll
+      for (int ss = 0; ss < 32; ss += 16)
+      {
+        const int k = sc + ss + sl;
+        if (k < ninc)
+        {
+          const unsigned w = __ldg(P.inc + i0 + k);
+          const long long idx = w / ND;
+          const int il = (int)(w - idx * ND);
+          const int cell = in.cells ? __ldg(in.cells + idx) : (int)idx;
+          int xd[NG];
+#pragma unroll
+          for (int v = 0; v < NG; ++v) xd[v] = __ldg(mesh.xd + (long long)cell * NG + v);
+          double X[NG][3];
+          load_vertices<TD>(mesh, xd, X);
+          P1Geom<TD> G;
+          p1_geometry<TD>(X, G);
+          double* g = geo + (ss + sl) * GS;
+          E::stage(G, g);
+          E::add(M, g, il, il, mu, lmbda, dg);  // reads back this lane's own stores
+        }
+      }
+#pragma unroll
+      for (int a = 0; a < BS; ++a)
+#pragma unroll
+        for (int b = 0; b < BS; ++b)
+        {
+          double v = dg[a][b];
+#pragma unroll
+          for (int o = 8; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+          dg[a][b] = v;
+        }
+      __syncwarp();
+      // ---- lanes = block columns, 16 at a time
+      for (int cc = 0; cc < nb_w; cc += 16)
+      {
+        const int kc = cc + sl;
+        const bool col_ok = kc < nb;
+        if (cc > 0 || sc > 0)
+        {
+          c_lo = c_hi = 0; J = 0;
+          if (col_ok)
+          {
+            c_lo = __ldg(P.con_off + blk0 + kc); c_hi = __ldg(P.con_off + blk0 + kc + 1);
+            J = __ldg(A.col + r0 + (long long)BS * kc) / BS;
+          }
+        }
+        unsigned short cw[CW];
+#pragma unroll
+        for (int u = 0; u < CW; ++u) cw[u] = (col_ok && c_lo + u < c_hi) ? __ldg(P.con + c_lo + u) : (unsigned short)0xffffu;
+        bool bcc[BS];
+#pragma unroll
+        for (int b = 0; b < BS; ++b) bcc[b] = (bc && col_ok) ? bc[BS * J + b] != 0 : false;
+        double acc[BS][BS];
+        const bool is_diag = col_ok && kc == kd;
+#pragma unroll
+        for (int a = 0; a < BS; ++a)
+#pragma unroll
+          for (int b = 0; b < BS; ++b) acc[a][b] = is_diag ? dg[a][b] : 0.0;
+        if (col_ok && !is_diag)
+        {
+#pragma unroll
+          for (int u = 0; u < CW; ++u)
+          {
+            const unsigned c = cw[u];
+            const int kl = (int)(c >> 8) - sc;
+            if (c != 0xffffu && kl >= 0 && kl < 32) E::add(M, geo + kl * GS, (int)((c >> 4) & 15u), (int)(c & 15u), mu, lmbda, acc);
+          }
+          for (unsigned q = c_lo + CW; q < c_hi; ++q)  // columns fed by more than CW cells (rare)
+          {
+            const unsigned c = __ldg(P.con + q);
+            const int kl = (int)(c >> 8) - sc;
+            if (kl >= 0 && kl < 32) E::add(M, geo + kl * GS, (int)((c >> 4) & 15u), (int)(c & 15u), mu, lmbda, acc);
+          }
+        }
+        // ---- the row is written once (Dirichlet rows / columns zeroed, cpp/assemble_matrix.cpp:513-533); scalar row
+        // BS I + a starts at r0 + a BS nb.  Passes after the first (rows with more than 32 cells) add onto it.
+        if (col_ok)
+        {
+#pragma unroll
+          for (int a = 0; a < BS; ++a)
+          {
+            double* dst = A.val + r0 + (long long)a * BS * nb + (long long)BS * kc;
+#pragma unroll
+            for (int b = 0; b < BS; ++b)
+            {
+              const double v = (bcr[a] || bcc[b]) ? 0.0 : acc[a][b];
+              if (sc == 0) dst[b] = v; else dst[b] += v;
+            }
+          }
+        }
+      }
+    }
+    if (!more) break;
+    I = In; i0 = n_i0; i1 = n_i1; kd = n_kd; r0 = n_r0; r1 = n_r1;
+  }
+}
 }  // namespace
