@@ -430,6 +430,8 @@ def run_ours(args):
 
     A.async_zero = bool(args.async_zero) and not args.unfused  # zero-fill of A overlapped with the previous assembly
 
+    A.deferred_errors = True  # cached, validated plans: the per-step error flag travels asynchronously (la.Matrix)
+
     def step():
         if args.unfused:
             mpcx.assemble_matrix(a, mpc, bcs=bcs, A=A)
@@ -461,6 +463,7 @@ def run_ours(args):
     ev1.record()
     barrier()
     t_wall1 = time.time()
+    A.synchronize()  # raises if any step of the loop reported a device error
     clk = clocks.stop(t_wall0, t_wall1) if rank == 0 else None  # samples inside the timed window, 20 ms apart
     ms_total = ev0.elapsed_time(ev1)
     launches = lib.mpcx_launch_count() - launches0

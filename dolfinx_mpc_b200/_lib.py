@@ -64,7 +64,7 @@ class MpcHostS(C.Structure):
 
 # every symbol include/mpcx.h declares (tests check the library exports all of them)
 SYMBOLS = (
-    "mpcx_last_error", "mpcx_abi_version", "mpcx_device_error", "mpcx_assemble_matrix_f64",
+    "mpcx_last_error", "mpcx_abi_version", "mpcx_device_error", "mpcx_device_error_async", "mpcx_assemble_matrix_f64",
     "mpcx_add_diagonal_f64", "mpcx_build_plan", "mpcx_assemble_vector_f64", "mpcx_apply_lifting_f64",
     "mpcx_backsubstitution_f64", "mpcx_homogenize_f64", "mpcx_gather_f64", "mpcx_scatter_add_f64",
     "mpcx_create_pattern_host", "mpcx_free_host", "mpcx_profile_enable", "mpcx_launch_count", "mpcx_profile_read",
@@ -98,6 +98,7 @@ def load():
     vp, i32, i64, f64 = C.c_void_p, C.c_int32, C.c_int64, C.c_double
     P = C.POINTER
     lib.mpcx_device_error.argtypes = [vp]
+    lib.mpcx_device_error_async.argtypes = [vp, vp]
     lib.mpcx_assemble_matrix_f64.argtypes = [P(IntegralS), P(MeshS), P(DofmapS), P(DofmapS), vp, vp, P(MpcS),
                                              P(MpcS), P(CsrS), P(PlanS), vp]
     lib.mpcx_add_diagonal_f64.argtypes = [P(CsrS), vp, i64, f64, vp]

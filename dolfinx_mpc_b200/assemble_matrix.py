@@ -202,7 +202,7 @@ def assemble_matrix(form: Form, constraint: Union[MultiPointConstraint, Sequence
                                                 _dev.ptr(bc0_d), _dev.ptr(bc1_d), C.byref(m0), C.byref(m1),
                                                 C.byref(As), None if plan is None else C.byref(plan), st))
     _add_diagonals(A, As, form, mpc0, mpc1, bcs, diagval, st)
-    _lib.check(lib.mpcx_device_error(st))
+    A.check_device_errors(st)
     A.assemble()
     return A
 

@@ -1439,6 +1439,13 @@ int mpcx_device_error(void* stream)
   return MPCX_OK;
 }
 
+int mpcx_device_error_async(int32_t* pinned_host_flag, void* stream)
+{
+  if (!pinned_host_flag) return fail(MPCX_ERR_ARG, "null argument");
+  return cuda_check(cudaMemcpyFromSymbolAsync(pinned_host_flag, g_dev_err, sizeof(int), 0, cudaMemcpyDeviceToHost, (cudaStream_t)stream),
+                    "device_error_async");
+}
+
 int mpcx_assemble_matrix_f64(const mpcx_integral* integral, const mpcx_mesh* mesh,
                              const mpcx_dofmap* dofmap0, const mpcx_dofmap* dofmap1,
                              const int8_t* bc0, const int8_t* bc1, const mpcx_mpc* mpc0,

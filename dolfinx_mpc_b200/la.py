@@ -55,6 +55,8 @@ class Matrix:
         # zero-fill overlapped with the previous assembly on a side stream (second value buffer); off by default
         self.async_zero = os.environ.get("MPCX_ASYNC_ZERO", "0") == "1"
         self._spare = None
+        self.deferred_errors = False
+        self._err_flag = None
 
     @property
     def row_ptr_host(self) -> np.ndarray:
@@ -70,6 +72,29 @@ class Matrix:
 
     def struct(self) -> _lib.CsrS:
         return _lib.CsrS(_dev.ptr(self.row_ptr), _dev.ptr(self.col), _dev.ptr(self.val), self.shape[0], self.nnz)
+
+    def check_device_errors(self, stream_ptr: int):
+        """Raise if a kernel reported an insertion outside the pattern.  Default: read the device flag now (one stream
+        synchronisation per assembly, as immediate as the reference's exception).  With ``deferred_errors`` the flag is
+        copied to pinned host memory in stream order and examined at the NEXT assembly into this matrix (and by
+        ``synchronize()``): a time loop then never drains the device queue -- the mode for steady-state loops over
+        cached plans, where every position was validated when the plans were built."""
+        lib = _lib.load()
+        if not self.deferred_errors:
+            _lib.check(lib.mpcx_device_error(stream_ptr))
+            return
+        if self._err_flag is None:
+            self._err_flag = torch.zeros(1, dtype=torch.int32).pin_memory()
+        elif int(self._err_flag[0]) != 0:
+            self.synchronize()
+        _lib.check(lib.mpcx_device_error_async(self._err_flag.data_ptr(), stream_ptr))
+
+    def synchronize(self):
+        """Wait for the assembly stream and raise any deferred device error."""
+        torch.cuda.current_stream(self.val.device).synchronize()
+        if self._err_flag is not None and int(self._err_flag[0]) != 0:
+            self._err_flag[0] = 0
+            _lib.check(_lib.load().mpcx_device_error(_dev.stream_ptr()))  # reads and clears the flag, raises with the message
 
     def zeroEntries(self):
         if self.async_zero:

@@ -61,7 +61,7 @@ def assemble_system(a: Form, L: Form, constraint: MultiPointConstraint, bcs: Opt
                 raise
         if A.last_system_fused:
             _add_diagonals(A, As, a, constraint, constraint, bcs, diagval, st)
-            _lib.check(lib.mpcx_device_error(st))
+            A.check_device_errors(st)
             A.assemble()
         else:  # refused before anything was launched (e.g. a coefficient layout without a tile kernel)
             assemble_matrix(a, constraint, bcs=bcs, diagval=diagval, A=A)

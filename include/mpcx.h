@@ -174,6 +174,10 @@ int mpcx_profile_read(double* ms_sum, long long* n_timed);
 /* Reads and clears the device-side error flag (syncs `stream`). 0 = none,
  * MPCX_ERR_PATTERN = an insertion missed the pattern. */
 int mpcx_device_error(void* stream);
+/* The same flag copied to pinned host memory in stream order, WITHOUT synchronising: the caller examines
+ * *pinned_host_flag later (after an event / at its next call), so that a time loop keeps the device queue filled.  The
+ * flag is not cleared. */
+int mpcx_device_error_async(int32_t* pinned_host_flag, void* stream);
 
 /* A += integral, with BC row/column zeroing and MPC elimination K^T A_e K.
  * Replaces assemble_cells_impl + modify_mpc_cell (cpp/assemble_matrix.cpp:417-548,

@@ -544,3 +544,29 @@ def test_async_zero_double_buffer(oracle):
         torch.cuda.synchronize()
         assert_csr_close(*A.getValuesCSR(), *ref)
     assert len(ptrs) == 2
+
+
+def test_deferred_error_is_still_loud():
+    """Matrix.deferred_errors: the device error flag travels asynchronously, but an insertion outside the pattern
+    still raises -- at synchronize() or at the next assembly into the matrix, whichever comes first."""
+    import dolfinx_mpc_b200 as mpcx
+    from dolfinx_mpc_b200 import _lib
+
+    c = problems.case_periodic_2d(6, 1, False)
+    mpc = _mpc(c)
+    empty = mpcx.MultiPointConstraint(c.V)
+    empty.finalize()
+    A = mpcx.create_matrix(c.a, empty)  # pattern without the master columns
+    A.deferred_errors = True
+    try:
+        mpcx.assemble_matrix(c.a, mpc, A=A)  # may or may not raise here (plan construction checks eagerly)
+        with pytest.raises(_lib.MpcxError):
+            A.synchronize()
+    except _lib.MpcxError:
+        pass
+    # and a clean matrix stays clean
+    B = mpcx.create_matrix(c.a, mpc)
+    B.deferred_errors = True
+    for _ in range(3):
+        mpcx.assemble_matrix(c.a, mpc, A=B)
+    B.synchronize()
