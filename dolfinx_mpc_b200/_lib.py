@@ -30,7 +30,8 @@ class MeshS(C.Structure):
 
 
 class DofmapS(C.Structure):
-    _fields_ = [("map", C.c_void_p), ("nd", C.c_int32), ("bs", C.c_int32), ("num_dofs", C.c_int64)]
+    _fields_ = [("map", C.c_void_p), ("nd", C.c_int32), ("bs", C.c_int32), ("num_dofs", C.c_int64),
+                ("num_owned_dofs", C.c_int64)]
 
 
 class MpcS(C.Structure):
@@ -70,9 +71,10 @@ SYMBOLS = (
     "mpcx_create_pattern_host", "mpcx_free_host", "mpcx_profile_enable", "mpcx_launch_count", "mpcx_profile_read",
     "mpcx_flag_cells", "mpcx_tile_plan_create", "mpcx_tile_plan_destroy", "mpcx_tile_plan_info",
     "mpcx_assemble_matrix_tiled_f64", "mpcx_vector_tile_plan_create", "mpcx_assemble_vector_tiled_f64",
-    "mpcx_pattern_create", "mpcx_pattern_export", "mpcx_pattern_destroy", "mpcx_assemble_system_tiled_f64", "mpcx_nccl_load", "mpcx_comm_unique_id", "mpcx_comm_create",
+    "mpcx_pattern_create", "mpcx_pattern_export", "mpcx_pattern_destroy", "mpcx_assemble_system_tiled_f64", "mpcx_assemble_system_tiled_part_f64", "mpcx_nccl_load", "mpcx_comm_unique_id", "mpcx_comm_create",
     "mpcx_comm_destroy", "mpcx_ghost_reduce_f64", "mpcx_tile_plan_add_slave_cells", "mpcx_row_plan_create", "mpcx_row_plan_destroy",
-    "mpcx_assemble_matrix_rowgather_f64",
+    "mpcx_assemble_matrix_rowgather_f64", "mpcx_slave_plan_create", "mpcx_slave_plan_destroy",
+    "mpcx_assemble_slave_cells_f64",
 )
 
 _lib = None
@@ -120,13 +122,19 @@ def load():
     lib.mpcx_row_plan_create.argtypes = [P(DofmapS), vp, i64, vp, P(CsrS), vp, P(vp)]
     lib.mpcx_row_plan_destroy.argtypes = [vp]
     lib.mpcx_row_plan_destroy.restype = None
-    lib.mpcx_assemble_matrix_rowgather_f64.argtypes = [P(IntegralS), P(MeshS), P(DofmapS), vp, P(MpcS), P(CsrS), vp, vp]
+    lib.mpcx_assemble_matrix_rowgather_f64.argtypes = [P(IntegralS), P(MeshS), P(DofmapS), vp, P(MpcS), P(CsrS), vp, vp, vp]
+    lib.mpcx_slave_plan_create.argtypes = [P(IntegralS), P(DofmapS), P(DofmapS), vp, vp, P(MpcS), P(MpcS), P(CsrS), vp, P(vp)]
+    lib.mpcx_slave_plan_destroy.argtypes = [vp]
+    lib.mpcx_slave_plan_destroy.restype = None
+    lib.mpcx_assemble_slave_cells_f64.argtypes = [P(IntegralS), P(MeshS), P(MpcS), P(MpcS), P(CsrS), vp, vp]
     lib.mpcx_nccl_load.argtypes = [C.c_char_p]
     lib.mpcx_comm_unique_id.argtypes = [vp]
     lib.mpcx_comm_create.argtypes = [vp, i32, i32, P(vp)]
     lib.mpcx_comm_destroy.argtypes = [vp]
     lib.mpcx_comm_destroy.restype = None
     lib.mpcx_ghost_reduce_f64.argtypes = [vp, vp, vp, i64, P(i64), vp, P(i64), vp, vp, vp]
+    lib.mpcx_assemble_system_tiled_part_f64.argtypes = [P(IntegralS), P(IntegralS), P(MeshS), P(DofmapS), vp, P(MpcS),
+                                                        P(CsrS), vp, vp, vp, i32, vp]
     lib.mpcx_flag_cells.argtypes = [P(DofmapS), vp, i64, vp, vp, vp]
     lib.mpcx_backsubstitution_f64.argtypes = [P(MpcS), vp, vp]
     lib.mpcx_homogenize_f64.argtypes = [P(MpcS), vp, vp]

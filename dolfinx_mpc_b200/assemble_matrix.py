@@ -180,8 +180,10 @@ def assemble_matrix(form: Form, constraint: Union[MultiPointConstraint, Sequence
             raise RuntimeError(f"{it.integral_type} integrals have no device kernel yet")
         s = _dev.integral_struct(form, it, (mpc0, mpc1), keep)
         if n_it == 0 and row_plan is not None:
+            sp = (A.slave_plan(form, it, s, bc0_d, bc1_d, mpc0, mpc1)
+                  if s.num_slave_cells > 0 and os.environ.get("MPCX_SLAVE_PLAN", "1") != "0" else None)
             _lib.check(lib.mpcx_assemble_matrix_rowgather_f64(C.byref(s), C.byref(mesh_s), C.byref(d0), _dev.ptr(bc0_d),
-                                                              C.byref(m0), C.byref(As), row_plan[0], st))
+                                                              C.byref(m0), C.byref(As), row_plan[0], sp, st))
             continue
         facet = it.integral_type == "exterior_facet"  # surface-sized: generic kernel, row search per entry
         tile = (A.tile_plan(form, it, s, bc0_d, bc1_d, (id(mpc0), id(mpc1)), keepalive=(mpc0, mpc1))

@@ -99,12 +99,12 @@ def _vector_tile_plan(form: Form, it, s_integral, constraint, mesh_s, dm):
             it._dev[key] = None
             return None
         _lib.check(lib.mpcx_device_error(_dev.stream_ptr()))
-        info = (C.c_int64 * 14)()
-        lib.mpcx_tile_plan_info(handle, info, 14)
+        info = (C.c_int64 * 15)()
+        lib.mpcx_tile_plan_info(handle, info, 15)
         it._dev[("keepalive",) + key] = (V, constraint)  # their id() keys the plan: must not be reused while cached
         it._dev[key] = (handle, _PlanHandle(handle),
                         dict(zip(("tiles", "cells_per_tile", "bulk_cells", "max_nodes", "max_dests", "tile_nodes",
-                                  "dests", "bytes", "max_slots", "slots", "max_runs", "runs", "max_stage", "symmetric"), [int(v) for v in info])))
+                                  "dests", "bytes", "max_slots", "slots", "max_runs", "runs", "max_stage", "symmetric", "interface_tiles"), [int(v) for v in info])))
     return it._dev[key]
 
 

@@ -1225,6 +1225,112 @@ k_matrix_p1_mpc_planned(IntD in, MeshD mesh, const double* __restrict__ coeffs0,
   }
 }
 
+// ---- slave-cell scatter plan for ANY element (generic elimination): per slave cell the (element entry, CSR position,
+// row-coefficient index, column-coefficient index) of every insertion of modify_mpc_cell
+// (cpp/assemble_matrix.cpp:214-267).  One warp per cell; pass 0 counts, pass 1 writes (lanes deal the element entries,
+// a warp scan places their insertions).  The assembly kernel then tabulates A_e and walks the list -- no constraint
+// lookups, no serial prefix over the cell's dofs, no row searches (the per-cell prefix ran on ONE lane with dependent
+// global loads and was what made the generic elimination kernel 4.5 ms for the 0.3 M slave cells of config 5).
+struct SlavePlanD
+{
+  const long long* off;
+  const unsigned short* ent;
+  const long long* pos;
+  const int *ca, *cb;
+};
+
+__global__ void __launch_bounds__(128)
+k_slave_plan_generic(int pass, IntD in, const int* __restrict__ dm0, const int* __restrict__ dm1, int nd0, int nd1, int bs0,
+                     int bs1, const int8_t* __restrict__ bc0, const int8_t* __restrict__ bc1, MpcD m0, MpcD m1, CsrD A,
+                     int* __restrict__ cnt, const long long* __restrict__ off, unsigned short* __restrict__ ent,
+                     long long* __restrict__ pos, int* __restrict__ ca, int* __restrict__ cb)
+{
+  const int lane = threadIdx.x & 31;
+  const long long it = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (it >= in.nslave_cells) return;
+  const long long index = __ldg(in.slave_cells + it);
+  const int cell = in.cells ? __ldg(in.cells + index) : (int)index;
+  const int n0 = nd0 * bs0, n1 = nd1 * bs1;
+  long long w = pass ? off[it] : 0;
+  int total = 0;
+  for (int e0 = 0; e0 < n0 * n1; e0 += 32)
+  {
+    const int e = e0 + lane;
+    int nr = 0, nc = 0, r = 0, c = 0, ra = 0, cb0 = 0;
+    bool sr = false, sc = false;
+    if (e < n0 * n1)
+    {
+      const int p = e / n1, q = e - p * n1;
+      r = dm0[(long long)cell * nd0 + p / bs0] * bs0 + p % bs0;
+      c = dm1[(long long)cell * nd1 + q / bs1] * bs1 + q % bs1;
+      if (!((bc0 && bc0[r]) || (bc1 && bc1[c])))
+      {
+        sr = m0.is_slave[r]; sc = m1.is_slave[c];
+        ra = sr ? m0.offsets[r] : 0; cb0 = sc ? m1.offsets[c] : 0;
+        nr = sr ? m0.offsets[r + 1] - ra : 1;
+        nc = sc ? m1.offsets[c + 1] - cb0 : 1;
+      }
+    }
+    const int mine = nr * nc;
+    int scan = mine;  // inclusive warp scan
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1)
+    {
+      const int v = __shfl_up_sync(0xffffffffu, scan, o);
+      if (lane >= o) scan += v;
+    }
+    const int tot = __shfl_sync(0xffffffffu, scan, 31);
+    if (pass)
+    {
+      long long k = w + scan - mine;
+      for (int a = 0; a < nr; ++a)
+        for (int b = 0; b < nc; ++b, ++k)
+        {
+          const long long f = csr_find(A, sr ? m0.masters[ra + a] : r, sc ? m1.masters[cb0 + b] : c);
+          if (f < 0) g_dev_err = MPCX_ERR_PATTERN;
+          ent[k] = (unsigned short)e;
+          pos[k] = f < 0 ? 0 : f;
+          ca[k] = sr ? ra + a : -1;
+          cb[k] = sc ? cb0 + b : -1;
+        }
+    }
+    w += tot;
+    total += tot;
+  }
+  if (!pass && lane == 0) cnt[it] = total;
+}
+
+// Warp per slave cell, any element: tabulated element matrix in shared memory, insertions through the scatter plan.
+__global__ void __launch_bounds__(128)
+k_matrix_generic_planned(Tab t, IntD in, MeshD mesh, int n0, int n1, const double* __restrict__ coeffs0,
+                         const double* __restrict__ coeffs1, SlavePlanD sp, double* __restrict__ val, int smem_per_warp)
+{
+  extern __shared__ double smem[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  double* base = smem + (size_t)warp * smem_per_warp;
+  double* X = base;
+  double* Ae = X + 3 * mesh.ng;
+  double* g = Ae + n0 * n1;
+  double* w = g + 3 * (t.nd > t.nd1 ? t.nd : t.nd1);
+  const long long wstride = (long long)gridDim.x * (blockDim.x >> 5);
+  for (long long it = (long long)blockIdx.x * (blockDim.x >> 5) + warp; it < in.nslave_cells; it += wstride)
+  {
+    const long long index = __ldg(in.slave_cells + it);
+    const int cell = in.cells ? __ldg(in.cells + index) : (int)index;
+    const long long k0 = __ldg(sp.off + it), k1 = __ldg(sp.off + it + 1);
+    __syncwarp();
+    load_cell(mesh, in, index, cell, X, w, lane);
+    __syncwarp();
+    tabulate_warp(entity_view(t, in, index), in.kernel, in.c, X, w, Ae, g, lane);
+    for (long long k = k0 + lane; k < k1; k += 32)
+    {
+      const int a = __ldg(sp.ca + k), b = __ldg(sp.cb + k);
+      const double wgt = (a >= 0 ? __ldg(coeffs0 + a) : 1.0) * (b >= 0 ? __ldg(coeffs1 + b) : 1.0);
+      atomicAdd(val + __ldg(sp.pos + k), wgt * Ae[__ldg(sp.ent + k)]);
+    }
+  }
+}
+
 // Thread per listed cell (cells with a Dirichlet column), scalar P1: b -= scale K^T A_e (g - x0)
 // (cpp/lifting.h:77-133,250-301).  A cell of the list without a bc column is skipped (:93-109).
 template <int TD>
@@ -1773,9 +1879,10 @@ int mpcx_tile_plan_info(const mpcx_tile_plan* plan, int64_t* out, int32_t n)
 {
   if (!plan || !out) return fail(MPCX_ERR_ARG, "null argument");
   const TilePlan* P = reinterpret_cast<const TilePlan*>(plan);
-  const int64_t v[14] = {P->nt, P->C, P->n_bulk, P->max_nodes, P->max_dests, P->total_nodes, P->total_dests, P->bytes,
-                         P->max_slots, P->total_slots, P->max_runs, P->total_runs, P->max_stage, P->sym};
-  for (int i = 0; i < n && i < 14; ++i) out[i] = v[i];
+  const int64_t v[15] = {P->nt, P->C, P->n_bulk, P->max_nodes, P->max_dests, P->total_nodes, P->total_dests, P->bytes,
+                         P->max_slots, P->total_slots, P->max_runs, P->total_runs, P->max_stage, P->sym,
+                         (P->n_iface + P->C - 1) / P->C};
+  for (int i = 0; i < n && i < 15; ++i) out[i] = v[i];
   return MPCX_OK;
 }
 
@@ -1951,6 +2058,14 @@ int mpcx_assemble_system_tiled_f64(const mpcx_integral* a_integral, const mpcx_i
                                    double* b, const mpcx_tile_plan* matrix_plan, const mpcx_tile_plan* vector_plan,
                                    void* stream)
 {
+  return mpcx_assemble_system_tiled_part_f64(a_integral, L_integral, mesh, dofmap, bc, mpc, A, b, matrix_plan, vector_plan, 0, stream);
+}
+
+int mpcx_assemble_system_tiled_part_f64(const mpcx_integral* a_integral, const mpcx_integral* L_integral, const mpcx_mesh* mesh,
+                                        const mpcx_dofmap* dofmap, const int8_t* bc, const mpcx_mpc* mpc, const mpcx_csr* A,
+                                        double* b, const mpcx_tile_plan* matrix_plan, const mpcx_tile_plan* vector_plan,
+                                        int32_t part, void* stream)
+{
   int rc = check_integral(a_integral, true);
   if (rc) return rc;
   rc = check_integral(L_integral, false);
@@ -1986,7 +2101,10 @@ int mpcx_assemble_system_tiled_f64(const mpcx_integral* a_integral, const mpcx_i
   const MeshD md{mesh->x, mesh->x_dofmap, mesh->ng, mesh->x_stride};
   const CsrD Ad{(const long long*)A->row_ptr, A->col, A->val};
   const MpcD m = make_mpc(mpc);
-  if (P->nt > 0)
+  if (part < 0 || part > 2) return fail(MPCX_ERR_ARG, "part must be 0, 1 or 2");
+  const int nt_iface = (int)((P->n_iface + P->C - 1) / P->C);
+  const int t_begin = part == 2 ? nt_iface : 0, t_end = part == 1 ? nt_iface : P->nt;
+  if (t_end > t_begin)
   {
     const TilePlanD Pd = tile_plan_view(P), Qd = tile_plan_view(Q);
     const size_t smem = fused_smem_bytes(Pd, Qd, t->tdim + 1, P->ns, P->sym != 0);
@@ -1994,13 +2112,13 @@ int mpcx_assemble_system_tiled_f64(const mpcx_integral* a_integral, const mpcx_i
     auto kern = t->tdim == 3 ? (P->sym ? k_ptile_system_p1<3, true> : k_ptile_system_p1<3, false>)
                              : (P->sym ? k_ptile_system_p1<2, true> : k_ptile_system_p1<2, false>);
     int grid = 0;
-    rc = persistent_grid((const void*)kern, smem, P->nt, &grid);
+    rc = persistent_grid((const void*)kern, smem, t_end - t_begin, &grid);
     if (rc) return rc;
     KernelTimer kt(s);  // dominant kernel of the call
     MPCX_COUNT_LAUNCH();
-    kern<<<grid, MPCX_TILE_THREADS, smem, s>>>(Pd, Qd, P->nt, ina, inL, md, Ad, b);
+    kern<<<grid, MPCX_TILE_THREADS, smem, s>>>(Pd, Qd, t_begin, t_end, ina, inL, md, Ad, b);
   }
-  if (ina.nslave_cells > 0)
+  if (ina.nslave_cells > 0 && part != 2)
   {
     const unsigned nbv = (unsigned)((ina.nslave_cells + 255) / 256);
     launch_p1_slave_cells(P, t->tdim, ina, md, dofmap, dofmap, bc, bc, mpc, mpc, Ad, s);
@@ -2146,6 +2264,95 @@ int mpcx_debug_set_trace(long long* buf)
 }
 #endif
 
+struct mpcx_slave_plan
+{
+  long long ncells = 0, total = 0;
+  int n0 = 0, n1 = 0;
+  long long *off = nullptr, *pos = nullptr;
+  unsigned short* ent = nullptr;
+  int *ca = nullptr, *cb = nullptr;
+};
+
+void mpcx_slave_plan_destroy(mpcx_slave_plan* P)
+{
+  if (!P) return;
+  cudaFree(P->off); cudaFree(P->pos); cudaFree(P->ent); cudaFree(P->ca); cudaFree(P->cb);
+  delete P;
+}
+
+int mpcx_slave_plan_create(const mpcx_integral* integral, const mpcx_dofmap* dofmap0, const mpcx_dofmap* dofmap1,
+                           const int8_t* bc0, const int8_t* bc1, const mpcx_mpc* mpc0, const mpcx_mpc* mpc1,
+                           const mpcx_csr* A, void* stream, mpcx_slave_plan** plan_out)
+{
+  if (!integral || !dofmap0 || !dofmap1 || !mpc0 || !mpc1 || !A || !plan_out) return fail(MPCX_ERR_ARG, "null argument");
+  *plan_out = nullptr;
+  const long long ns = integral->num_slave_cells;
+  const int n0 = dofmap0->nd * dofmap0->bs, n1 = dofmap1->nd * dofmap1->bs;
+  if (n0 * n1 > 65535) return fail(MPCX_ERR_UNSUPPORTED, "slave plan: element matrix with more than 65535 entries");
+  mpcx_slave_plan* P = new mpcx_slave_plan();
+  P->ncells = ns; P->n0 = n0; P->n1 = n1;
+  *plan_out = P;
+  if (ns <= 0 || !integral->slave_cells) return MPCX_OK;
+  cudaStream_t s = (cudaStream_t)stream;
+  const IntD in = make_int(integral);
+  const MpcD m0 = make_mpc(mpc0), m1 = make_mpc(mpc1);
+  const CsrD Ad{(const long long*)A->row_ptr, A->col, A->val};
+  int rc = MPCX_OK;
+  int* cnt = nullptr;
+  void* tmp = nullptr;
+  size_t tb = 0;
+  const unsigned nb = (unsigned)((ns * 32 + 127) / 128);
+  TP_CK(tp_alloc(&cnt, ns + 1));
+  TP_CK(cudaMemsetAsync(cnt, 0, sizeof(int) * (size_t)(ns + 1), s));
+  TP_CK(tp_alloc(&P->off, ns + 1));
+  MPCX_COUNT_LAUNCH();
+  k_slave_plan_generic<<<nb, 128, 0, s>>>(0, in, dofmap0->map, dofmap1->map, dofmap0->nd, dofmap1->nd, dofmap0->bs, dofmap1->bs, bc0,
+                                          bc1, m0, m1, Ad, cnt, nullptr, nullptr, nullptr, nullptr, nullptr);
+  TP_CK(cub::DeviceScan::ExclusiveSum(nullptr, tb, cnt, P->off, (int)(ns + 1), s));
+  TP_CK(cudaMalloc(&tmp, tb));
+  TP_CK(cub::DeviceScan::ExclusiveSum(tmp, tb, cnt, P->off, (int)(ns + 1), s));
+  TP_CK(cudaMemcpyAsync(&P->total, P->off + ns, sizeof(long long), cudaMemcpyDeviceToHost, s));
+  TP_CK(cudaStreamSynchronize(s));
+  TP_CK(tp_alloc(&P->ent, P->total)); TP_CK(tp_alloc(&P->pos, P->total)); TP_CK(tp_alloc(&P->ca, P->total)); TP_CK(tp_alloc(&P->cb, P->total));
+  MPCX_COUNT_LAUNCH();
+  k_slave_plan_generic<<<nb, 128, 0, s>>>(1, in, dofmap0->map, dofmap1->map, dofmap0->nd, dofmap1->nd, dofmap0->bs, dofmap1->bs, bc0,
+                                          bc1, m0, m1, Ad, cnt, P->off, P->ent, P->pos, P->ca, P->cb);
+  TP_CK(cudaStreamSynchronize(s));
+done:
+  cudaFree(cnt); cudaFree(tmp);
+  if (rc != MPCX_OK) { mpcx_slave_plan_destroy(P); *plan_out = nullptr; }
+  return rc;
+}
+
+int mpcx_assemble_slave_cells_f64(const mpcx_integral* integral, const mpcx_mesh* mesh, const mpcx_mpc* mpc0,
+                                  const mpcx_mpc* mpc1, const mpcx_csr* A, const mpcx_slave_plan* plan, void* stream)
+{
+  int rc = check_integral(integral, true);
+  if (rc) return rc;
+  if (!mesh || !mpc0 || !mpc1 || !A || !plan) return fail(MPCX_ERR_ARG, "null argument");
+  const mpcx_tables* t = integral->tables;
+  const int nd1 = t->nd1 ? t->nd1 : t->nd, bs1 = t->nd1 ? t->bs1 : t->bs;
+  const int n0 = t->nd * t->bs, n1 = nd1 * bs1;
+  if (plan->n0 != n0 || plan->n1 != n1 || plan->ncells != integral->num_slave_cells)
+    return fail(MPCX_ERR_ARG, "slave plan was built for a different element or cell list");
+  if (plan->ncells <= 0) return MPCX_OK;
+  const IntD in = make_int(integral);
+  const MeshD md{mesh->x, mesh->x_dofmap, mesh->ng, mesh->x_stride};
+  const int wcount = in.cstride > 0 ? in.cstride : 1;
+  const int spw = 3 * mesh->ng + n0 * n1 + 3 * std::max(t->nd, nd1) + wcount + 1;
+  const size_t smem = (size_t)spw * 4 * sizeof(double);
+  if (smem > 48 * 1024)
+  {
+    rc = cuda_check(cudaFuncSetAttribute(k_matrix_generic_planned, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "smem attr");
+    if (rc) return rc;
+  }
+  const SlavePlanD sp{plan->off, plan->ent, plan->pos, plan->ca, plan->cb};
+  MPCX_COUNT_LAUNCH();
+  k_matrix_generic_planned<<<grid_for_warps(plan->ncells, 4), 128, smem, (cudaStream_t)stream>>>(make_tab(t), in, md, n0, n1, mpc0->coeffs,
+                                                                                                 mpc1->coeffs, sp, A->val, spw);
+  return cuda_check(cudaGetLastError(), "assemble_slave_cells launch");
+}
+
 int mpcx_row_plan_create(const mpcx_dofmap* dofmap, const int32_t* cells, int64_t num_cells, const int8_t* skip,
                          const mpcx_csr* A, void* stream, mpcx_row_plan** plan_out)
 {
@@ -2162,7 +2369,7 @@ void mpcx_row_plan_destroy(mpcx_row_plan* plan) { row_plan_free(reinterpret_cast
 
 int mpcx_assemble_matrix_rowgather_f64(const mpcx_integral* integral, const mpcx_mesh* mesh, const mpcx_dofmap* dofmap,
                                        const int8_t* bc, const mpcx_mpc* mpc, const mpcx_csr* A, const mpcx_row_plan* plan,
-                                       void* stream)
+                                       const mpcx_slave_plan* slave_plan, void* stream)
 {
   int rc = check_integral(integral, true);
   if (rc) return rc;
@@ -2231,7 +2438,9 @@ int mpcx_assemble_matrix_rowgather_f64(const mpcx_integral* integral, const mpcx
       else k_rowgather_elast<E, 3><<<(unsigned)nb, 256, smem, s>>>(Pd, tb, in, md, bc, Ad);
     }
   }
-  if (in.nslave_cells > 0)  // cells holding slaves: elimination kernel, added on top of the stored rows
+  if (in.nslave_cells > 0 && slave_plan)  // cells holding slaves, through their scatter plan, on top of the stored rows
+    return mpcx_assemble_slave_cells_f64(integral, mesh, mpc, mpc, A, slave_plan, stream);
+  if (in.nslave_cells > 0)  // cells holding slaves: searching elimination kernel, added on top of the stored rows
   {
     const Tab tab = make_tab(t);
     const MpcD m = make_mpc(mpc);

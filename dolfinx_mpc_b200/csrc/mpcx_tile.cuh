@@ -74,6 +74,7 @@ struct TilePlan
 {
   int nt = 0, C = 0, ne = 0, ng = 0, nd0 = 0, nd1 = 0;
   int max_nodes = 0, max_dests = 0, max_slots = 0, max_runs = 0, max_stage = 0;
+  long long n_iface = 0;  // bulk cells touching a ghost row: they fill the first ceil(n_iface / C) tiles
   long long nrows = 0, nvals = 0, n_bulk = 0, total_nodes = 0, total_dests = 0, total_slots = 0, total_runs = 0, bytes = 0;
   int *cell_pos = nullptr, *tile_node_off = nullptr, *node_ids = nullptr, *dest_k = nullptr, *tile_nd = nullptr,
       *tile_slots = nullptr, *tile_nr = nullptr, *tile_stage = nullptr;
@@ -156,15 +157,20 @@ struct BBox
 };
 
 // Morton code of the cell centroid; skipped cells sort last
+// cells that touch a ghost row (a block >= first_ghost_block of dm) sort before all others: bit 61 clear / set
+#define MPCX_TP_INTERIOR_BIT (1ull << 61)
 __global__ void k_tp_cell_codes(MeshD mesh, BBox bb, const int* __restrict__ cells, long long nc,
-                                const int8_t* __restrict__ skip, unsigned long long* __restrict__ code,
-                                int* __restrict__ iota)
+                                const int8_t* __restrict__ skip, const int* __restrict__ dm, int nd, long long first_ghost_block,
+                                unsigned long long* __restrict__ code, int* __restrict__ iota)
 {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= nc) return;
   iota[i] = (int)i;
   if (skip && skip[i]) { code[i] = ~0ull; return; }
   const int cell = cells ? cells[i] : (int)i;
+  bool iface = false;
+  if (first_ghost_block > 0)
+    for (int k = 0; k < nd; ++k) iface |= dm[(long long)cell * nd + k] >= first_ghost_block;
   double c[3] = {0, 0, 0};
   for (int g = 0; g < mesh.ng; ++g)
   {
@@ -176,9 +182,23 @@ __global__ void k_tp_cell_codes(MeshD mesh, BBox bb, const int* __restrict__ cel
   {
     double u = (c[k] / mesh.ng - bb.lo[k]) * bb.inv[k];
     u = u < 0.0 ? 0.0 : (u > 1.0 ? 1.0 : u);
-    m |= spread21((unsigned long long)(u * 2097151.0)) << k;
+    m |= spread21((unsigned long long)(u * 1048575.0)) << k;  // 20 bits per axis: bits 60.. stay free
   }
-  code[i] = m;
+  code[i] = m | (iface ? 0ull : MPCX_TP_INTERIOR_BIT);
+}
+
+// first index whose code is >= bound (codes sorted ascending)
+__global__ void k_tp_count_below(const unsigned long long* __restrict__ sorted_code, long long nc, unsigned long long bound,
+                                 long long* __restrict__ out)
+{
+  if (blockIdx.x || threadIdx.x) return;
+  long long lo = 0, hi = nc;
+  while (lo < hi)
+  {
+    const long long mid = (lo + hi) >> 1;
+    if (sorted_code[mid] < bound) lo = mid + 1; else hi = mid;
+  }
+  *out = lo;
 }
 
 __global__ void k_tp_count_bulk(const unsigned long long* __restrict__ sorted_code, long long nc, long long* __restrict__ n_bulk)
@@ -1251,12 +1271,17 @@ int tile_plan_build(const mpcx_mesh* mesh, const mpcx_dofmap* dm0, const mpcx_do
   // 2. cells along the Morton curve (skipped cells last), tiles of C consecutive cells
   TP_CK(tp_alloc(&code, nc)); TP_CK(tp_alloc(&code2, nc)); TP_CK(tp_alloc(&iota, nc)); TP_CK(tp_alloc(&order, nc));
   TP_CK(tp_alloc(&nb_dev, 1));
-  k_tp_cell_codes<<<tp_grid(nc), 256, 0, s>>>(md, bb, cells, nc, skip, code, iota);
+  k_tp_cell_codes<<<tp_grid(nc), 256, 0, s>>>(md, bb, cells, nc, skip, dm0->map, dm0->nd,
+                                              dm0->num_owned_dofs > 0 && dm0->num_owned_dofs < dm0->num_dofs ? dm0->num_owned_dofs / dm0->bs : 0,
+                                              code, iota);
   TP_CK(cub::DeviceRadixSort::SortPairs(nullptr, tb, code, code2, iota, order, (int)nc, 0, 64, s));
   TP_CK(need_tmp(tb));
   TP_CK(cub::DeviceRadixSort::SortPairs(tmp, tb, code, code2, iota, order, (int)nc, 0, 64, s));
   k_tp_count_bulk<<<1, 32, 0, s>>>(code2, nc, nb_dev);
   TP_CK(cudaMemcpyAsync(&P->n_bulk, nb_dev, sizeof(long long), cudaMemcpyDeviceToHost, s));
+  TP_CK(cudaStreamSynchronize(s));
+  k_tp_count_below<<<1, 32, 0, s>>>(code2, nc, MPCX_TP_INTERIOR_BIT, nb_dev);
+  TP_CK(cudaMemcpyAsync(&P->n_iface, nb_dev, sizeof(long long), cudaMemcpyDeviceToHost, s));
   TP_CK(cudaStreamSynchronize(s));
   cudaFree(code); code = nullptr; cudaFree(code2); code2 = nullptr; cudaFree(iota); iota = nullptr;
   P->nt = (int)((P->n_bulk + C - 1) / C);

@@ -142,7 +142,7 @@ __device__ __forceinline__ void fused_tma_mrecords(const FusedSmem& S, const Til
 //   sync 2   warp 0: TMA bulk reduce-add of the runs, then TMA R(t+1)
 template <int TD, bool SYM>
 __global__ void __launch_bounds__(MPCX_TILE_THREADS, 2)
-k_ptile_system_p1(TilePlanD P, TilePlanD Q, int nt, IntD ina, IntD inL, MeshD mesh, CsrD A, double* __restrict__ b)
+k_ptile_system_p1(TilePlanD P, TilePlanD Q, int t_begin, int nt, IntD ina, IntD inL, MeshD mesh, CsrD A, double* __restrict__ b)
 {
   constexpr int NV = TD + 1, NS = SYM ? NV * (NV + 1) / 2 : NV * NV, NT = MPCX_TILE_THREADS;
   extern __shared__ __align__(16) unsigned char tile_smem[];
@@ -150,7 +150,7 @@ k_ptile_system_p1(TilePlanD P, TilePlanD Q, int nt, IntD ina, IntD inL, MeshD me
   const int tid = threadIdx.x;
   const bool issuer = tid < 32;
   const int G = gridDim.x;
-  int t = blockIdx.x;
+  int t = t_begin + blockIdx.x;  // tiles [t_begin, nt)
   if (t >= nt) return;
   // header loader threads: word w of the matrix (w < 12) or vector (w >= 12) header
   const int hw_i = tid - 32;

@@ -58,7 +58,8 @@ def space_dev(V: FunctionSpace) -> dict:
 
 
 def dofmap_struct(V: FunctionSpace, num_dofs: int) -> _lib.DofmapS:
-    return _lib.DofmapS(ptr(space_dev(V)["dofmap"]), V.nd, V.bs, num_dofs)
+    n_owned = V.index_map.size_local * V.bs
+    return _lib.DofmapS(ptr(space_dev(V)["dofmap"]), V.nd, V.bs, num_dofs, n_owned if V.index_map.num_ghosts else 0)
 
 
 def mpc_dev(mpc) -> dict:

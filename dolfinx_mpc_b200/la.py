@@ -47,6 +47,7 @@ class Matrix:
         self._plans = {}
         self._tile_plans = {}
         self._row_plans = []
+        self._slave_plans = {}
         self._keepalive = {}  # objects whose id() keys a cached plan: kept alive so that the id cannot be reused
         # "tile": entries combined per 512-cell tile in shared memory, one reduction per (tile, entry), where a
         # tile kernel exists; "atomic": one red.global.add per element entry
@@ -208,10 +209,10 @@ class Matrix:
                                                               _dev.ptr(bc0_d), _dev.ptr(bc1_d), C.byref(m0), C.byref(m1),
                                                               C.byref(A), _dev.stream_ptr()))
                 _lib.check(lib.mpcx_device_error(_dev.stream_ptr()))
-            info = (C.c_int64 * 14)()
-            lib.mpcx_tile_plan_info(handle, info, 14)
+            info = (C.c_int64 * 15)()
+            lib.mpcx_tile_plan_info(handle, info, 15)
             self._tile_plans[key] = (handle, dict(zip(("tiles", "cells_per_tile", "bulk_cells", "max_nodes",
-                                                       "max_dests", "tile_nodes", "dests", "bytes", "max_slots", "slots", "max_runs", "runs", "max_stage", "symmetric"),
+                                                       "max_dests", "tile_nodes", "dests", "bytes", "max_slots", "slots", "max_runs", "runs", "max_stage", "symmetric", "interface_tiles"),
                                                       [int(v) for v in info])))
         return self._tile_plans[key]
 
@@ -253,9 +254,31 @@ class Matrix:
             self._tile_plans[key] = (handle, {"row_plan": 1})
         return self._tile_plans[key]
 
+    def slave_plan(self, form, integral, s_integral, bc0_d, bc1_d, mpc0, mpc1):
+        """Scatter plan of the cells of ``integral`` that hold slaves (any element), built on the device on first use."""
+        key = ("slave", id(integral), id(mpc0), id(mpc1), _dev.ptr(bc0_d), _dev.ptr(bc1_d))
+        if key not in self._slave_plans:
+            self._keepalive[key] = (integral, mpc0, mpc1, bc0_d, bc1_d)
+            lib = _lib.load()
+            V0, V1 = form.function_spaces
+            d0 = _dev.dofmap_struct(V0, self.shape[0])
+            d1 = _dev.dofmap_struct(V1, self.shape[1])
+            m0 = _dev.mpc_dev(mpc0)["struct"]
+            m1 = _dev.mpc_dev(mpc1)["struct"]
+            A = self.struct()
+            handle = C.c_void_p()
+            _lib.check(lib.mpcx_slave_plan_create(C.byref(s_integral), C.byref(d0), C.byref(d1), _dev.ptr(bc0_d),
+                                                  _dev.ptr(bc1_d), C.byref(m0), C.byref(m1), C.byref(A),
+                                                  _dev.stream_ptr(), C.byref(handle)))
+            _lib.check(lib.mpcx_device_error(_dev.stream_ptr()))
+            self._slave_plans[key] = handle
+        return self._slave_plans[key]
+
     def __del__(self):
         try:
             lib = _lib.load()
+            for h in self._slave_plans.values():
+                lib.mpcx_slave_plan_destroy(h)
             rows = set(h.value for h in self._row_plans)
             for entry in self._tile_plans.values():
                 if entry is not None and entry[0].value not in rows:

@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define MPCX_ABI_VERSION 3
+#define MPCX_ABI_VERSION 4
 #define MPCX_MAX_CONSTANTS 8
 
 typedef enum mpcx_status
@@ -96,6 +96,10 @@ typedef struct mpcx_dofmap
   const int32_t* map; /* [num_cells][nd], blocked */
   int32_t nd, bs;
   int64_t num_dofs; /* unrolled, owned + ghost */
+  /* unrolled dofs owned by this process (owned first, ghosts after: cpp/MultiPointConstraint.h:112-115); 0 = all.  The
+   * tile plans order the cells that touch a ghost row first, so that the rows to be sent to their owners are complete
+   * early (mpcx_assemble_system_tiled_part_f64). */
+  int64_t num_owned_dofs;
 } mpcx_dofmap;
 
 /* MultiPointConstraint data (cpp/MultiPointConstraint.h:201-223; tuple `mpc_data`
@@ -202,7 +206,8 @@ void mpcx_tile_plan_destroy(mpcx_tile_plan* plan);
 /* out[0..13] = tiles, cells per tile, bulk cells, max vertices / dest records per tile, total tile vertices,
  * total dest records, plan bytes read per assembly, max / total element-buffer slots, max / total runs
  * (= TMA bulk reductions per assembly), max staging positions per tile, 1 for a symmetric plan (same dofmap
- * and bc markers on both sides: upper-triangular records feed entry (r, c) and entry (c, r)) */
+ * and bc markers on both sides: upper-triangular records feed entry (r, c) and entry (c, r)); out[14] = number of
+ * leading tiles that hold every cell touching a ghost row (0 without ghosts) */
 int mpcx_tile_plan_info(const mpcx_tile_plan* plan, int64_t* out, int32_t n);
 
 /* Optional: scatter plan for the cells holding slaves (integral->slave_cells), stored inside a matrix tile plan of a
@@ -256,12 +261,34 @@ int mpcx_assemble_system_tiled_f64(const mpcx_integral* a_integral, const mpcx_i
  * (cells around every node, and for every block entry the (cell, i, j) contributions) is built once per pattern /
  * dofmap / active cells / skip flags on the device.  One constraint and one bc marker array on both sides. */
 typedef struct mpcx_row_plan mpcx_row_plan;
+typedef struct mpcx_slave_plan mpcx_slave_plan;
 int mpcx_row_plan_create(const mpcx_dofmap* dofmap, const int32_t* cells, int64_t num_cells, const int8_t* skip,
                          const mpcx_csr* A, void* stream, mpcx_row_plan** plan_out);
 void mpcx_row_plan_destroy(mpcx_row_plan* plan);
 int mpcx_assemble_matrix_rowgather_f64(const mpcx_integral* integral, const mpcx_mesh* mesh, const mpcx_dofmap* dofmap,
                                        const int8_t* bc, const mpcx_mpc* mpc, const mpcx_csr* A, const mpcx_row_plan* plan,
-                                       void* stream);
+                                       const mpcx_slave_plan* slave_plan /* optional */, void* stream);
+
+/* Scatter plan of the cells holding slaves for ANY element (the general form of mpcx_tile_plan_add_slave_cells): the
+ * (element entry, CSR position, coefficient indices) of every insertion modify_mpc_cell makes for them
+ * (cpp/assemble_matrix.cpp:214-267, explicit zeros of bc rows / columns left out), found once per pattern / constraint /
+ * bc set.  mpcx_assemble_slave_cells_f64 tabulates the element matrix of every such cell and walks its list:
+ * A += K^T A_e K for those cells only. */
+int mpcx_slave_plan_create(const mpcx_integral* integral, const mpcx_dofmap* dofmap0, const mpcx_dofmap* dofmap1,
+                           const int8_t* bc0, const int8_t* bc1, const mpcx_mpc* mpc0, const mpcx_mpc* mpc1,
+                           const mpcx_csr* A, void* stream, mpcx_slave_plan** plan_out);
+void mpcx_slave_plan_destroy(mpcx_slave_plan* plan);
+int mpcx_assemble_slave_cells_f64(const mpcx_integral* integral, const mpcx_mesh* mesh, const mpcx_mpc* mpc0,
+                                  const mpcx_mpc* mpc1, const mpcx_csr* A, const mpcx_slave_plan* plan, void* stream);
+
+/* The same in two parts, for overlapping the ghost-row exchange with the assembly of the interior: part 1 = the cells
+ * holding slaves and the tiles that touch ghost rows (tiles [0, interface_tiles) of the plans, see mpcx_tile_plan_info
+ * out[14]) -- after it every ghost row of A is complete and can travel (mpcx_ghost_reduce_f64 on another stream);
+ * part 2 = the remaining tiles; part 0 = everything (= mpcx_assemble_system_tiled_f64). */
+int mpcx_assemble_system_tiled_part_f64(const mpcx_integral* a_integral, const mpcx_integral* L_integral, const mpcx_mesh* mesh,
+                                        const mpcx_dofmap* dofmap, const int8_t* bc, const mpcx_mpc* mpc, const mpcx_csr* A,
+                                        double* b, const mpcx_tile_plan* matrix_plan, const mpcx_tile_plan* vector_plan,
+                                        int32_t part, void* stream);
 
 /* A[d, d] += diagval for the listed unrolled dofs.  Slave diagonal
  * (cpp/assemble_matrix.cpp:711-724) and Dirichlet diagonal

@@ -81,11 +81,20 @@ def _worker_cuda(rank, world, periodic_z, n, nzc, out_dir):
     A = D.create_matrix(P["a"], mpc)
     b = mpcx.create_vector(mpc)
     D.attach_ghost_exchange(A, b, P)
-    mpcx.assemble_matrix(P["a"], mpc, bcs=P["bcs"], A=A)
-    mpcx.assemble_vector(P["L"], mpc, b=b)
-    if P["bcs"]:
-        mpcx.apply_lifting(b, [P["a"]], [P["bcs"]], mpc)
-    b.ghostUpdate()
+    if os.environ.get("MPCX_TEST_FUSED") == "1":
+        # one call: fused matrix + vector kernel in two parts, the ghost rows travelling while the interior is assembled
+        for _ in range(2):  # twice into the same objects: cached plans, streams and events reused
+            mpcx.assemble_system(P["a"], P["L"], mpc, bcs=P["bcs"], A=A, b=b)
+        assert A.last_system_fused
+        info = [e[1] for e in A._tile_plans.values() if e is not None and "interface_tiles" in e[1]]
+        if V.index_map.num_ghosts:
+            assert info and 0 < info[0]["interface_tiles"] < info[0]["tiles"], info
+    else:
+        mpcx.assemble_matrix(P["a"], mpc, bcs=P["bcs"], A=A)
+        mpcx.assemble_vector(P["L"], mpc, b=b)
+        if P["bcs"]:
+            mpcx.apply_lifting(b, [P["a"]], [P["bcs"]], mpc)
+        b.ghostUpdate()
     torch.cuda.synchronize()
     rp, col, val = A.getValuesCSR()
     n_owned = V.index_map.size_local
@@ -98,13 +107,19 @@ def _worker_cuda(rank, world, periodic_z, n, nzc, out_dir):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("fused", [False, True])
 @pytest.mark.parametrize("periodic_z", [False, True])
-def test_two_gpu_assembly_matches_serial(oracle, tmp_path, periodic_z):
-    """The distributed path end to end on two real GPUs (CUDA kernels + NCCL ghost-row exchange) against the serial
-    oracle assembly of the global problem; skipped on a single-GPU box."""
+def test_two_gpu_assembly_matches_serial(oracle, tmp_path, periodic_z, fused):
+    """The distributed path end to end on two real GPUs (CUDA kernels + NCCL ghost-row exchange through
+    mpcx_ghost_reduce_f64) against the serial oracle assembly of the global problem; skipped on a single-GPU box.
+    ``fused``: through assemble_system, whose interface tiles go first so that the exchange overlaps the interior."""
     if torch.cuda.device_count() < 2:
         pytest.skip("needs two GPUs")
-    _run_and_compare(oracle, tmp_path, 2, periodic_z, cuda=True, n=7, nzc=4)
+    os.environ["MPCX_TEST_FUSED"] = "1" if fused else "0"
+    try:
+        _run_and_compare(oracle, tmp_path, 2, periodic_z, cuda=True, n=9 if fused else 7, nzc=5 if fused else 4)
+    finally:
+        del os.environ["MPCX_TEST_FUSED"]
 
 
 @pytest.mark.parametrize("world,periodic_z", [(2, False), (2, True), (3, False), (3, True)])
