@@ -14,6 +14,7 @@
 #include <stdio.h>
 #include <string.h>
 #include <stdlib.h>
+#include <limits.h>
 #include <dlfcn.h>
 
 #include <atomic>
@@ -2141,6 +2142,7 @@ struct NcclApi
   void* lib = nullptr;
   int (*GetUniqueId)(void*) = nullptr;
   int (*CommInitRank)(void**, int, mpcx_nccl_id /* by value, as ncclCommInitRank takes it */, int) = nullptr;
+  int (*CommInitRankConfig)(void**, int, mpcx_nccl_id, int, void*) = nullptr;  // optional (NCCL >= 2.14)
   int (*CommDestroy)(void*) = nullptr;
   int (*GroupStart)() = nullptr;
   int (*GroupEnd)() = nullptr;
@@ -2168,6 +2170,7 @@ int nccl_bind(const char* path)
   a.lib = h;
   a.GetUniqueId = (decltype(a.GetUniqueId))dlsym(h, "ncclGetUniqueId");
   a.CommInitRank = (decltype(a.CommInitRank))dlsym(h, "ncclCommInitRank");
+  a.CommInitRankConfig = (decltype(a.CommInitRankConfig))dlsym(h, "ncclCommInitRankConfig");
   a.CommDestroy = (decltype(a.CommDestroy))dlsym(h, "ncclCommDestroy");
   a.GroupStart = (decltype(a.GroupStart))dlsym(h, "ncclGroupStart");
   a.GroupEnd = (decltype(a.GroupEnd))dlsym(h, "ncclGroupEnd");
@@ -2205,8 +2208,27 @@ int mpcx_comm_create(const void* id128, int32_t rank, int32_t world, mpcx_comm**
   mpcx_nccl_id id;
   memcpy(&id, id128, sizeof(id));
   void* c = nullptr;
-  rc = nccl_check(g_nccl.CommInitRank(&c, world, id, rank), "ncclCommInitRank");
-  if (rc) return rc;
+  // MPCX_NCCL_MAX_CTAS > 0 caps the CTAs of the communicator's kernels (ncclConfig_t.maxCTAs): with the interface-first
+  // schedule (MPCX_OVERLAP=1) the send/recv kernel runs beside the interior tiles and every one of its CTAs holds a
+  // whole SM while it waits for the neighbour.  Default 0 = NCCL's own choice: with the exchange AFTER the assembly, a
+  // cap of 4 made the ~60 MB per neighbour of a 100 M cell slab 0.7 ms slower (profiles/README.md, r02_h).
+  // The struct is ncclConfig_t as of NCCL 2.18 (newer libraries accept older, shorter versions by their `version`).
+  struct { size_t size; unsigned magic, version; int blocking, cgaClusterSize, minCTAs, maxCTAs; const char* netName; int splitShare; } cfg
+      = {sizeof(cfg), 0xcafebeefu, 21800u, INT_MIN, INT_MIN, INT_MIN, INT_MIN, nullptr, INT_MIN};
+  int max_ctas = 0;
+  if (const char* e = getenv("MPCX_NCCL_MAX_CTAS")) max_ctas = atoi(e);
+  bool made = false;
+  if (g_nccl.CommInitRankConfig && max_ctas > 0)
+  {
+    cfg.minCTAs = 1;
+    cfg.maxCTAs = max_ctas;
+    made = g_nccl.CommInitRankConfig(&c, world, id, rank, &cfg) == 0 && c != nullptr;
+  }
+  if (!made)
+  {
+    rc = nccl_check(g_nccl.CommInitRank(&c, world, id, rank), "ncclCommInitRank");
+    if (rc) return rc;
+  }
   *comm_out = new mpcx_comm{c, rank, world};
   return MPCX_OK;
 }

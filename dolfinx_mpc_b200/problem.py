@@ -52,12 +52,15 @@ def assemble_system(a: Form, L: Form, constraint: MultiPointConstraint, bcs: Opt
         A.zeroEntries()
         As = A.struct()  # after zeroEntries: with async_zero the values live in the other buffer now
         b.set(0.0)
-        # With several ranks: the cells holding slaves and the tiles that touch ghost rows first (part 1); the ghost
-        # rows then travel to their owners on a second stream WHILE the interior tiles are assembled (part 2) -- the
-        # exchange, and the waiting for a neighbour that is a little behind, hide behind ~90 % of the kernel time.
+        # With several ranks and MPCX_OVERLAP=1: the cells holding slaves and the tiles that touch ghost rows first
+        # (part 1); the ghost rows then travel to their owners on a second stream WHILE the interior tiles are assembled
+        # (part 2).  Off by default -- measured on two B200s (profiles/README.md, r02_h): the exchange costs 0.26 ms of a
+        # 4.8 ms step, and the NCCL send/recv kernel, which holds whole SMs while it waits for its neighbour, delays the
+        # persistent CTAs of part 2 by more than that (6.5 ms; 5.0 ms with dynamically claimed tiles, which in turn cost
+        # the tile kernel 6 %).
         n_if, n_t = plans[-1]
         overlap = (A.ghost_exchange is not None and getattr(A.ghost_exchange, "mat", None) is not None and 0 < n_if < n_t
-                   and os.environ.get("MPCX_OVERLAP", "1") != "0")
+                   and os.environ.get("MPCX_OVERLAP", "0") == "1")
 
         def part(k):
             _lib.check(lib.mpcx_assemble_system_tiled_part_f64(C.byref(sa), C.byref(sL), C.byref(mesh_s), C.byref(dm),
