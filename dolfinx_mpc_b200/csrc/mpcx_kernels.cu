@@ -785,6 +785,76 @@ k_vector_affine_source(Tab t, IntD in, MeshD mesh, const int* __restrict__ dm, M
   }
 }
 
+// Thread per (cell, component) for the same term on an element of ND nodes (P2: 6 / 10): the ND row dofs, the ND
+// coefficient values and the ND results of the thread stay in registers, its loads are independent of one another
+// (the lane-per-entry kernel above keeps ONE cell in flight per warp behind a chain of four dependent loads: 7.5 ms for
+// the 12.3 M P2 tetrahedra of BASELINE config 3), the reference mass matrix is read from shared memory as a broadcast,
+// and the bs threads of a cell hit neighbouring addresses of f and b.
+template <int ND>
+__global__ void __launch_bounds__(256)
+k_vector_affine_source_comp(Tab t, IntD in, MeshD mesh, const int* __restrict__ dm, MpcD m, double* __restrict__ b)
+{
+  __shared__ double M[ND * ND];
+  for (int e = threadIdx.x; e < ND * ND; e += blockDim.x)
+  {
+    const int i = e / ND, j = e - i * ND;
+    double acc = 0.0;
+    for (int q = 0; q < t.nq; ++q) acc += __ldg(t.w + q) * __ldg(t.phi + q * ND + i) * __ldg(t.phi + q * ND + j);
+    M[e] = acc;
+  }
+  __syncthreads();
+  const int bs = t.bs;
+  const long long total = in.ncells * bs;
+  for (long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x; gid < total; gid += (long long)gridDim.x * blockDim.x)
+  {
+    const long long index = gid / bs;
+    const int a = (int)(gid - index * bs);
+    const int cell = in.cells ? __ldg(in.cells + index) : (int)index;
+    int r[ND];
+    double f[ND];
+#pragma unroll
+    for (int j = 0; j < ND; ++j)
+    {
+      r[j] = __ldg(dm + (long long)cell * ND + j) * bs + a;
+      f[j] = in.coeffs ? __ldg(in.coeffs + index * in.cstride + j * bs + a)
+                       : __ldg(in.wnodal + (long long)__ldg(in.wmap + (long long)cell * ND + j) * bs + a);
+    }
+    double X[4][3];
+#pragma unroll
+    for (int v = 0; v < 4; ++v)
+    {
+      const double* p = mesh.x + (long long)__ldg(mesh.xd + (long long)cell * mesh.ng + (v <= t.tdim ? v : 0)) * mesh.xs;
+      X[v][0] = __ldg(p); X[v][1] = __ldg(p + 1); X[v][2] = __ldg(p + 2);
+    }
+    double det;
+    if (t.tdim == 2)
+      det = (X[1][0] - X[0][0]) * (X[2][1] - X[0][1]) - (X[2][0] - X[0][0]) * (X[1][1] - X[0][1]);
+    else
+    {
+      const double a0 = X[1][0] - X[0][0], a1 = X[1][1] - X[0][1], a2 = X[1][2] - X[0][2];
+      const double b0 = X[2][0] - X[0][0], b1 = X[2][1] - X[0][1], b2 = X[2][2] - X[0][2];
+      const double c0 = X[3][0] - X[0][0], c1 = X[3][1] - X[0][1], c2 = X[3][2] - X[0][2];
+      det = a0 * (b1 * c2 - b2 * c1) - a1 * (b0 * c2 - b2 * c0) + a2 * (b0 * c1 - b1 * c0);
+    }
+    const double sc = in.c[0] * fabs(det);
+#pragma unroll
+    for (int i = 0; i < ND; ++i)
+    {
+      // same order of the sum as the lane-per-entry kernel (j ascending, then the scale)
+      double acc = 0.0;
+#pragma unroll
+      for (int j = 0; j < ND; ++j) acc += M[i * ND + j] * f[j];
+      const double v = sc * acc;
+      const int ri = r[i];
+      const int o0 = m.is_slave[ri] ? m.offsets[ri] : 0, o1 = m.is_slave[ri] ? m.offsets[ri + 1] : 0;
+      if (o1 > o0)
+        for (int k = o0; k < o1; ++k) atomicAdd(b + m.masters[k], m.coeffs[k] * v);
+      else
+        atomicAdd(b + ri, v);
+    }
+  }
+}
+
 // Thread per cell, P1 source vector of a BLOCKED space (bs = BS components, coefficient in the test space):
 // b_(i,a) = c0 vol / ((d+1)(d+2)) (f_(i,a) + sum_j f_(j,a)); elimination per entry as in modify_mpc_vec
 // (cpp/assemble_vector.h:52-68).  One RED per entry: 12 per tetrahedron for bs = 3.
@@ -1747,6 +1817,15 @@ int mpcx_assemble_vector_f64(const mpcx_integral* integral, const mpcx_mesh* mes
            && (in.coeffs ? in.cstride == n : (in.wnd == nd && in.wbs == bs)))
   {
     // affine simplex, coefficient in the test space: reference mass matrix times nodal values
+    if ((nd == 6 || nd == 10) && getenv("MPCX_VECTOR_LANES") == nullptr)
+    {
+      long long nbc = (in.ncells * bs + 255) / 256;
+      if (nbc > 148LL * 16) nbc = 148LL * 16;
+      MPCX_COUNT_LAUNCH();
+      if (nd == 10) k_vector_affine_source_comp<10><<<(unsigned)nbc, 256, 0, s>>>(tab, in, md, dofmap->map, m, b);
+      else k_vector_affine_source_comp<6><<<(unsigned)nbc, 256, 0, s>>>(tab, in, md, dofmap->map, m, b);
+      return cuda_check(cudaGetLastError(), "assemble_vector launch");
+    }
     const int lpc = n <= 16 ? 16 : 32, cpb = 256 / lpc;
     const size_t smem = sizeof(double) * ((size_t)nd * nd + (size_t)cpb * n);
     long long nb = (in.ncells + cpb - 1) / cpb;

@@ -286,14 +286,79 @@ k_ct_build(int pass, const int* __restrict__ order, long long n_bulk, const int*
     int hoff, total;
     Scan(scan).ExclusiveSum(h, hoff, total);
     __syncthreads();
+    // Tile-local vertex NUMBERS are free.  Phase 1 of the kernels gathers the coordinates of vertex v of 16 cells with
+    // one LDS.64 per half-warp and component: two different vertices whose numbers agree mod 16 cost an extra
+    // wavefront (12 such loads per cell: 41 M of the fused kernel's 238 M excess wavefronts at 256^3, profiles/r02_c).
+    // Greedy colouring, vertex by vertex in id order: the residue (mod 16) no other vertex of the same (half-warp,
+    // v) groups holds yet, classes filled evenly; the tile's vertex list is padded to a multiple of 16 (holes repeat the
+    // first vertex).
+    const int nnp = (total + 15) & ~15;
     if (pass == 0)
     {
-      if (cl == 0) tile_nn[t] = total;
+      if (cl == 0) tile_nn[t] = nnp;
     }
     else
     {
+      constexpr int NI = NT * NGc, NGRP = (NT / 16) * NGc;
+      unsigned char* vgrp = ct_smem + extra_off;                                              // [NI] group of sorted item s
+      unsigned short* vstart = reinterpret_cast<unsigned short*>(vgrp + ((NI + 15) & ~15));   // [NI + 8] first item of vertex li
+      unsigned short* vperm = vstart + NI + 8;                                                // [NI] number given to vertex li
+      unsigned short* vmask = vperm + NI;                                                     // [NGRP] residues taken per group
+      int* vsh = reinterpret_cast<int*>(vmask + NGRP + (NGRP & 1));                           // [16] class sizes, [16] first key
       const int noff = tile_node_off[t];
       int li = hoff - 1;  // run index of the item before this thread's first item
+#pragma unroll
+      for (int g = 0; g < NGc; ++g)
+      {
+        if (keys[g] == MPCX_CT_INVALID) continue;
+        const int sidx = cl * NGc + g;  // valid keys sort first
+        if (head[g]) vstart[++li] = (unsigned short)sidx;
+        vgrp[sidx] = (unsigned char)(((vals[g] / NGc) >> 4) * NGc + vals[g] % NGc);
+      }
+      if (cl == 0) { vstart[total] = (unsigned short)(nc_t * NGc); vsh[16] = (int)keys[0]; }
+      for (int i = cl; i < NGRP; i += NT) vmask[i] = 0;
+      if (cl < 16) vsh[cl] = 0;
+      __syncthreads();
+      if (cl == 0)
+      {
+        const int capmax = nnp >> 4;
+        for (int u = 0; u < total; ++u)
+        {
+          const int s0 = vstart[u], s1 = vstart[u + 1];
+          int best = -1;
+          if (MPCX_CT_BANKOPT != 0)
+          {
+            unsigned taken = 0u;
+            for (int q = s0; q < s1; ++q) taken |= vmask[vgrp[q]];
+            int bestc = 1 << 30;
+            for (int r = 0; r < 16; ++r)
+            {
+              if (vsh[r] >= capmax) continue;
+              int c = vsh[r];  // among conflict-free residues: the emptiest class
+              if ((taken >> r) & 1u)
+              {
+                c = 1 << 16;  // no free residue left in some group: the one fewest of the vertex's groups hold
+                for (int q = s0; q < s1; ++q) c += ((vmask[vgrp[q]] >> r) & 1u) << 8;
+                c += vsh[r];
+              }
+              if (c < bestc) { bestc = c; best = r; }
+            }
+          }
+          else
+            best = u & 15, best = vsh[best] < capmax ? best : -1;
+          if (best < 0)
+            for (int r = 0; r < 16 && best < 0; ++r)
+              if (vsh[r] < capmax) best = r;
+          vperm[u] = (unsigned short)(best + 16 * vsh[best]);
+          ++vsh[best];
+          for (int q = s0; q < s1; ++q) vmask[vgrp[q]] |= (unsigned short)(1u << best);
+        }
+      }
+      __syncthreads();
+      const int key0 = vsh[16];
+      for (int i = cl; i < nnp; i += NT) node_ids[noff + i] = key0;
+      __syncthreads();
+      li = hoff - 1;
 #pragma unroll
       for (int g = 0; g < NGc; ++g)
       {
@@ -301,9 +366,9 @@ k_ct_build(int pass, const int* __restrict__ order, long long n_bulk, const int*
         if (head[g])
         {
           ++li;
-          node_ids[noff + li] = (int)keys[g];
+          node_ids[noff + vperm[li]] = (int)keys[g];
         }
-        cell_nodes[first * NGc + vals[g]] = (uint16_t)li;
+        cell_nodes[first * NGc + vals[g]] = vperm[li];
       }
     }
   }
@@ -640,42 +705,61 @@ k_ct_build(int pass, const int* __restrict__ order, long long n_bulk, const int*
       }
     }
   }
-  // Vector plans: the fused kernel GATHERS through the inverse slot map -- the thread of row record (group g, lane l)
-  // reads, at step i, the 16-byte pair of the cell in its slot i; a quarter-warp is conflict-free when its 8 cells
-  // differ mod 8.  Latin pattern, record by record: step i of lane l prefers a cell with (cell mod 8) == (l + i) mod 8.
+  // Vector plans: the fused kernel GATHERS through the inverse slot map -- the thread of row record p reads, at step i,
+  // the 16-byte pair of the cell in its slot i with one LDS.128; the 8 records of a quarter-warp (p / 8) are served in
+  // one wavefront when their 8 cells differ mod 8.  Which cell of a row sits in which slot is free: one thread per
+  // quarter-warp walks the steps and gives every record, in turn, a remaining cell whose residue no other record of
+  // the quarter holds at that step (records past their count read the zero pair at cellv[C + (p & 7)] until their
+  // last group of four steps ends: residue p & 7).
   const bool optv = vec && ok && (MPCX_CT_BANKOPT != 0);
   if (optv)
   {
+    unsigned short* pinv = pcnt;  // [nrec] dest of record p (the counts were written out above)
 #pragma unroll
     for (int e = 0; e < NEc; ++e) srcv[cl * NEc + e] = vals[e];
-    __syncthreads();
     for (int d = cl; d < total; d += NT)
+      if (rcnt[d] > 0) pinv[npos[d]] = (unsigned short)d;
+    __syncthreads();
+    for (int q = cl; 8 * q < nrec; q += NT)
     {
-      const int s0 = dstart[d], cnt = (int)dstart[d + 1] - s0, l = npos[d] & 7;
-      if (cnt > 32)
+      int s0[8], cn[8];
+      unsigned used_src[8];
+      int maxc = 0;
+      for (int l = 0; l < 8; ++l)
       {
-        for (int k = 0; k < cnt; ++k) isrc[s0 + k] = (unsigned char)k;
-        continue;
+        const int p = 8 * q + l;
+        s0[l] = 0; cn[l] = 0; used_src[l] = 0u;
+        if (p >= nrec) continue;
+        const int d = pinv[p];
+        s0[l] = dstart[d]; cn[l] = (int)dstart[d + 1] - s0[l];
+        if (cn[l] > 32)  // (never on simplicial meshes) identity order, takes no part in the pattern
+        {
+          for (int k = 0; k < cn[l]; ++k) isrc[s0[l] + k] = (unsigned char)k;
+          cn[l] = 0;
+        }
+        maxc = cn[l] > maxc ? cn[l] : maxc;
       }
-      unsigned used_src = 0u, used_pos = 0u;
-      for (int i = 0; i < cnt; ++i)
+      for (int i = 0; i < maxc; ++i)
       {
-        const int want = (l + i) & 7;
-        for (int k = 0; k < cnt; ++k)
-          if (!((used_src >> k) & 1u) && ((srcv[s0 + k] / NEc) & 7) == want)
+        unsigned used_res = 0u;
+        for (int l = 0; l < 8; ++l)
+          if (cn[l] > 0 && cn[l] <= i && i < ((cn[l] + 3) & ~3)) used_res |= 1u << l;
+        for (int ll = 0; ll < 8; ++ll)
+        {
+          const int l = (ll + i) & 7;  // the first pick rotates
+          if (i >= cn[l]) continue;
+          int pick = -1, fallback = -1;
+          for (int k = 0; k < cn[l] && pick < 0; ++k)
           {
-            used_src |= 1u << k; used_pos |= 1u << i;
-            isrc[s0 + k] = (unsigned char)i;
-            break;
+            if ((used_src[l] >> k) & 1u) continue;
+            if (fallback < 0) fallback = k;
+            if (!((used_res >> ((srcv[s0[l] + k] / NEc) & 7)) & 1u)) pick = k;
           }
-      }
-      int i = 0;
-      for (int k = 0; k < cnt; ++k)
-      {
-        if ((used_src >> k) & 1u) continue;
-        while ((used_pos >> i) & 1u) ++i;
-        isrc[s0 + k] = (unsigned char)i;
-        used_pos |= 1u << i;
+          if (pick < 0) pick = fallback;
+          used_src[l] |= 1u << pick;
+          used_res |= 1u << ((srcv[s0[l] + pick] / NEc) & 7);
+          isrc[s0[l] + pick] = (unsigned char)i;
+        }
       }
     }
     __syncthreads();

@@ -51,7 +51,7 @@ __host__ __device__ inline size_t fused_smem_bytes(const TilePlanD& P, const Til
 {
   auto al = [](size_t b) { return (b + 15) & ~(size_t)15; };
   size_t b = al(24 * (size_t)P.max_nodes) + al(8 * (size_t)P.max_stage) + al(8 * (size_t)(P.max_slots + 1))
-             + al(8 * (size_t)Q.max_dests) + al(16 * (size_t)(P.C + 1));
+             + al(8 * (size_t)Q.max_dests) + al(16 * (size_t)(P.C + 8));
   b += al(8 * (size_t)P.max_runs) + al(4 * (size_t)(P.max_dests / 32)) + (sym ? 2 : 1) * al(2 * (size_t)P.max_dests)
        + al((size_t)P.max_dests);
   b += al(4 * (size_t)(Q.max_dests / 32)) + al(4 * (size_t)Q.max_dests) + al((size_t)Q.max_dests);
@@ -68,7 +68,7 @@ __device__ __forceinline__ FusedSmem fused_carve(unsigned char* sp, const TilePl
   S.stage = reinterpret_cast<double*>(sp); sp += al(8 * (size_t)P.max_stage);
   S.ebuf = reinterpret_cast<double*>(sp); sp += al(8 * (size_t)(P.max_slots + 1));
   S.fs = reinterpret_cast<double*>(sp); sp += al(8 * (size_t)Q.max_dests);
-  S.cellv = reinterpret_cast<double2*>(sp); sp += al(16 * (size_t)(P.C + 1));
+  S.cellv = reinterpret_cast<double2*>(sp); sp += al(16 * (size_t)(P.C + 8));
   S.R.runs = reinterpret_cast<int2*>(sp); sp += al(8 * (size_t)P.max_runs);
   S.R.gi = reinterpret_cast<unsigned*>(sp); sp += al(4 * (size_t)(P.max_dests / 32));
   S.R.dk = nullptr;
@@ -156,7 +156,8 @@ k_ptile_system_p1(TilePlanD P, TilePlanD Q, int t_begin, int nt, IntD ina, IntD 
   const int hw_i = tid - 32;
   const bool loader = hw_i >= 0 && hw_i < 24;
   const int* hsrc = loader ? reinterpret_cast<const int*>(hw_i < 12 ? P.hdr : Q.hdr) + (hw_i < 12 ? hw_i : hw_i - 12) : nullptr;
-  if (tid == 0) { mbar_init(S.barC, 1); mbar_init(S.barR, 2); S.cellv[NT] = make_double2(0.0, 0.0); }
+  if (tid == 0) { mbar_init(S.barC, 1); mbar_init(S.barR, 2); }
+  if (tid < 8) S.cellv[NT + tid] = make_double2(0.0, 0.0);  // zero pairs read by records past their count, one per bank group
   if (loader)
   {
     S.hb[hw_i] = __ldg(hsrc + 12 * (long long)t);
@@ -297,14 +298,14 @@ k_ptile_system_p1(TilePlanD P, TilePlanD Q, int t_begin, int nt, IntD ina, IntD 
       {
         const unsigned g = S.giv[k >> 5];
         const uint16_t* e = S.vinc + (g & 0xffffu) + (k & 31);
-        const int cnt = S.dcntv[k];
+        const int cnt = S.dcntv[k], zs = NT + (k & 7);
         double s1 = 0.0, s2 = 0.0;
 #pragma unroll 1
         for (int i = 0; i < cnt; i += 4, e += 4 * MPCX_CT_GSTRIDE)
         {
-          // four independent index -> pair loads in flight; lanes past their count read the zero pair at cellv[NT]
-          const int c0 = e[0], c1 = i + 1 < cnt ? (int)e[MPCX_CT_GSTRIDE] : NT, c2 = i + 2 < cnt ? (int)e[2 * MPCX_CT_GSTRIDE] : NT,
-                    c3 = i + 3 < cnt ? (int)e[3 * MPCX_CT_GSTRIDE] : NT;
+          // four independent index -> pair loads in flight; lanes past their count read the zero pair of their bank group
+          const int c0 = e[0], c1 = i + 1 < cnt ? (int)e[MPCX_CT_GSTRIDE] : zs, c2 = i + 2 < cnt ? (int)e[2 * MPCX_CT_GSTRIDE] : zs,
+                    c3 = i + 3 < cnt ? (int)e[3 * MPCX_CT_GSTRIDE] : zs;
           const double2 v0 = S.cellv[c0], v1 = S.cellv[c1], v2 = S.cellv[c2], v3 = S.cellv[c3];
           s1 += (v0.x + v1.x) + (v2.x + v3.x);
           s2 += (v0.y + v1.y) + (v2.y + v3.y);
