@@ -21,6 +21,7 @@
 #include <mutex>
 #include <algorithm>
 #include <vector>
+#include <type_traits>
 
 #include "mpcx.h"
 
@@ -2491,53 +2492,55 @@ int mpcx_assemble_matrix_rowgather_f64(const mpcx_integral* integral, const mpcx
   const IntD in = make_int(integral);
   const MeshD md{mesh->x, mesh->x_dofmap, mesh->ng, mesh->x_stride};
   const CsrD Ad{(const long long*)A->row_ptr, A->col, A->val};
-  const RowPlanD Pd{P->inc_off, P->inc, P->con_off, P->con, P->diag, P->nrows_b};
+  // geometry once per cell into the plan's scratch (MPCX_ROWGATHER_GEO=0: per incidence inside the row kernels)
+  const char* geo_env = getenv("MPCX_ROWGATHER_GEO");
+  const bool pre_geo = P->geo != nullptr && P->n_cells >= integral->num_cells && !(geo_env && geo_env[0] == '0');
+  const RowPlanD Pd{P->inc_off, P->inc, P->con_off, P->con, P->diag, P->nrows_b, P->ccol, P->row_con, P->rflag,
+                    pre_geo ? P->geo : nullptr};
   {
-    long long nb = (P->nrows_b + 7) / 8;
-    if (nb > 148LL * 64) nb = 148LL * 64;
-    if (nb < 1) nb = 1;
     KernelTimer kt(s);  // dominant kernel of the call
     MPCX_COUNT_LAUNCH();
     const Tab tb = make_tab(t);
-    const char* v1 = getenv("MPCX_ROWGATHER_V1");  // tuning: the one-row-per-warp kernel
-    const bool two = !(v1 && v1[0] == '1');
-    if (two)
-    {
-      nb = (P->nrows_b + 15) / 16;
-      if (nb > 148LL * 64) nb = 148LL * 64;
-      if (nb < 1) nb = 1;
-    }
-    if (p2tet)
-    {
-      using E = RgAffineTet<10>;
-      const size_t smem = sizeof(double) * (E::SMEM_TABLE + (two ? 16 : 8) * 32 * E::GS);
-      if (two)
+    // 3 (default): half-warp per row, flat walk of the row's contributions; 2: half-warp per row, lane per column;
+    // 1: warp per row (MPCX_ROWGATHER_V, tuning; 1 also through the older MPCX_ROWGATHER_V1=1)
+    int ver = 2;  // the flat walk (3) measured slower on both configs (profiles/README.md r02_k): kept for reference
+    if (const char* e = getenv("MPCX_ROWGATHER_V")) ver = atoi(e);
+    if (const char* v1 = getenv("MPCX_ROWGATHER_V1")) ver = v1[0] == '1' ? 1 : ver;
+    if (ver < 1 || ver > 3 || (ver == 3 && !P->flat_ok)) ver = 2;
+    long long nb = ver == 1 ? (P->nrows_b + 7) / 8 : (P->nrows_b + 15) / 16;
+    if (nb > 148LL * 64) nb = 148LL * 64;
+    if (nb < 1) nb = 1;
+    auto launch = [&](auto e_tag, auto minb_tag) -> int {
+      using E = decltype(e_tag);
+      constexpr int MINB = decltype(minb_tag)::value;
+      const size_t smem = sizeof(double) * (E::SMEM_TABLE + (ver == 1 ? 8 : 16) * 32 * E::GS) + (ver == 3 ? 16 * 256 : 0);
+      auto go = [&](auto kern) -> int {
+        if (smem > 48 * 1024)
+        {
+          const int r = cuda_check(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "smem attr");
+          if (r) return r;
+        }
+        kern<<<(unsigned)nb, 256, smem, s>>>(Pd, tb, in, md, bc, Ad);
+        return MPCX_OK;
+      };
+      if (pre_geo && in.ncells > 0)
       {
-        rc = cuda_check(cudaFuncSetAttribute(k_rowgather_elast2<E, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "smem attr");
-        if (rc) return rc;
-        k_rowgather_elast2<E, 2><<<(unsigned)nb, 256, smem, s>>>(Pd, tb, in, md, bc, Ad);
+        MPCX_COUNT_LAUNCH();
+        k_rg_geometry<E><<<(unsigned)((in.ncells + 255) / 256), 256, 0, s>>>(in, md, P->geo);
       }
-      else k_rowgather_elast<E, 2><<<(unsigned)nb, 256, smem, s>>>(Pd, tb, in, md, bc, Ad);
-    }
-    else if (t->tdim == 3)
-    {
-      using E = RgP1<3>;
-      const size_t smem = sizeof(double) * (two ? 16 : 8) * 32 * E::GS;
-      if (two)
-      {
-        rc = cuda_check(cudaFuncSetAttribute(k_rowgather_elast2<E, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "smem attr");
-        if (rc) return rc;
-        k_rowgather_elast2<E, 3><<<(unsigned)nb, 256, smem, s>>>(Pd, tb, in, md, bc, Ad);
-      }
-      else k_rowgather_elast<E, 3><<<(unsigned)nb, 256, smem, s>>>(Pd, tb, in, md, bc, Ad);
-    }
-    else
-    {
-      using E = RgP1<2>;
-      const size_t smem = sizeof(double) * (two ? 16 : 8) * 32 * E::GS;
-      if (two) k_rowgather_elast2<E, 3><<<(unsigned)nb, 256, smem, s>>>(Pd, tb, in, md, bc, Ad);
-      else k_rowgather_elast<E, 3><<<(unsigned)nb, 256, smem, s>>>(Pd, tb, in, md, bc, Ad);
-    }
+      int r = MPCX_OK;
+      if (ver == 3) r = pre_geo ? go(k_rowgather_elast3<E, MINB, true>) : go(k_rowgather_elast3<E, MINB, false>);
+      else if (ver == 2) r = pre_geo ? go(k_rowgather_elast2<E, MINB, true>) : go(k_rowgather_elast2<E, MINB, false>);
+      else r = go(k_rowgather_elast<E, MINB>);
+      if (r) return r;
+      return MPCX_OK;
+    };
+    if (p2tet && getenv("MPCX_ROWGATHER_MINB3")) rc = launch(RgAffineTet<10>{}, std::integral_constant<int, 3>{});
+    else if (p2tet) rc = launch(RgAffineTet<10>{}, std::integral_constant<int, 2>{});
+    else if (t->tdim == 3 && getenv("MPCX_ROWGATHER_MINB2")) rc = launch(RgP1<3>{}, std::integral_constant<int, 2>{});
+    else if (t->tdim == 3) rc = launch(RgP1<3>{}, std::integral_constant<int, 3>{});
+    else rc = launch(RgP1<2>{}, std::integral_constant<int, 3>{});
+    if (rc) return rc;
   }
   if (in.nslave_cells > 0 && slave_plan)  // cells holding slaves, through their scatter plan, on top of the stored rows
     return mpcx_assemble_slave_cells_f64(integral, mesh, mpc, mpc, A, slave_plan, stream);

@@ -31,12 +31,21 @@ struct RowPlan
   unsigned* con_off = nullptr;   // [nnz_block + 1] contributions of every block entry (block CSR order)
   unsigned short* con = nullptr; // [n_con] (incidence within the row) << 8 | local row index i << 4 | local column index j
   unsigned char* diag = nullptr; // [nrows_b] position of the diagonal block in its row
+  // flat walk (k_rowgather_elast3): contributions of a row as ONE list, dealt evenly to the lanes
+  unsigned char* ccol = nullptr; // [n_con] block column (position in its row) of every contribution
+  unsigned* row_con = nullptr;   // [nrows_b + 1] first contribution of every block row
+  unsigned char* rflag = nullptr;// [nrows_b] 1: the row has block entries without any contribution (stored as zeros)
+  int flat_ok = 0;               // 0: some row has more than 256 block columns (ccol would not fit)
+  double* geo = nullptr;         // [n_cells][14] scratch: staged geometry of every active cell (written by every assembly)
+  long long n_cells = 0;
 };
+__device__ int g_rp_wide;
 
 void row_plan_free(RowPlan* P)
 {
   if (!P) return;
   cudaFree(P->inc_off); cudaFree(P->inc); cudaFree(P->con_off); cudaFree(P->con); cudaFree(P->diag);
+  cudaFree(P->ccol); cudaFree(P->row_con); cudaFree(P->rflag); cudaFree(P->geo);
   delete P;
 }
 
@@ -88,7 +97,8 @@ __global__ void k_rp_low32(const unsigned long long* __restrict__ keys, long lon
   if (e < n) out[e] = (unsigned)(keys[e] & 0xffffffffull);
 }
 
-// one key per (incidence, local column j): (global block entry) << 16 | (incidence within the row) << 8 | i << 4 | j
+// one key per (incidence, local column j):
+// (global block entry) << 24 | (block column in its row) << 16 | (incidence within the row) << 8 | i << 4 | j
 __global__ void k_rp_contrib_keys(const unsigned long long* __restrict__ ikeys, long long n_inc, const int* __restrict__ inc_off,
                                   const int* __restrict__ dm, int nd, int bs, const int* __restrict__ cells, CsrD A,
                                   unsigned long long* __restrict__ ckeys, unsigned char* __restrict__ diag)
@@ -109,14 +119,32 @@ __global__ void k_rp_contrib_keys(const unsigned long long* __restrict__ ikeys, 
     const int k = blockcol_find(A, bs, I, J);
     if (k < 0) { g_dev_err = MPCX_ERR_PATTERN; ckeys[e * nd + j] = ~0ull; continue; }
     if (J == I) diag[I] = (unsigned char)k;
-    ckeys[e * nd + j] = ((unsigned long long)(blk0 + k) << 16) | ((unsigned long long)(klocal & 255) << 8) | ((unsigned)il << 4) | (unsigned)j;
+    if (k > 255) g_rp_wide = 1;  // the flat walk stores k in 8 bits
+    ckeys[e * nd + j] = ((unsigned long long)(blk0 + k) << 24) | ((unsigned long long)(k & 255) << 16)
+                        | ((unsigned long long)(klocal & 255) << 8) | ((unsigned)il << 4) | (unsigned)j;
   }
 }
 
-__global__ void k_rp_con(const unsigned long long* __restrict__ ckeys, long long n, unsigned short* __restrict__ con)
+__global__ void k_rp_con(const unsigned long long* __restrict__ ckeys, long long n, unsigned short* __restrict__ con,
+                         unsigned char* __restrict__ ccol)
 {
   const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (e < n) con[e] = (unsigned short)(ckeys[e] & 0xffffull);
+  if (e < n) { con[e] = (unsigned short)(ckeys[e] & 0xffffull); ccol[e] = (unsigned char)((ckeys[e] >> 16) & 0xffull); }
+}
+
+// per block row: its first contribution and whether one of its block entries has none
+__global__ void k_rp_rowmeta(CsrD A, int bs, long long nrows_b, const unsigned* __restrict__ con_off,
+                             unsigned* __restrict__ row_con, unsigned char* __restrict__ rflag)
+{
+  const long long I = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (I > nrows_b) return;
+  const long long b0 = A.rp[bs * I] / ((long long)bs * bs);
+  row_con[I] = con_off[b0];
+  if (I == nrows_b) return;
+  const long long b1 = A.rp[bs * (I + 1)] / ((long long)bs * bs);
+  unsigned char f = 0;
+  for (long long e = b0; e < b1; ++e) f |= con_off[e] == con_off[e + 1];
+  rflag[I] = f;
 }
 
 // rows without any bulk cell still need their diagonal position (they are written as zeros; the value is unused)
@@ -148,9 +176,18 @@ int row_plan_build(const mpcx_dofmap* dm, const int32_t* cells, long long nc, co
   long long n_valid = 0;
   int last = 0;
   P->nd = nd; P->bs = bs; P->nrows_b = dm->num_dofs / bs; P->nnz_block = Acsr->nnz / ((long long)bs * bs);
-  if (nd > 16 || bs < 1 || P->nrows_b >= (1ll << 31) || n0 * nd >= (1ll << 32) || P->nnz_block >= (1ll << 39))
+  if (nd > 16 || bs < 1 || P->nrows_b >= (1ll << 31) || n0 * nd >= (1ll << 32) || P->nnz_block >= (1ll << 39))  // key: 39 + 8 + 16 bits
   { rc = fail(MPCX_ERR_UNSUPPORTED, "row plan: sizes outside the plan format"); goto done; }
   RP_CK(cudaMalloc(&P->inc_off, sizeof(int) * (size_t)(P->nrows_b + 1)));
+  P->n_cells = nc;
+  // scratch for the geometry-once-per-cell variant (MPCX_ROWGATHER_GEO=1 when the plan is created; measured: config 3
+  // -1.4 %, config 5 +14 % because of the extra pass over the cells -- profiles/README.md r02_k -- so off by default)
+  if (const char* ge = getenv("MPCX_ROWGATHER_GEO"))
+    if (ge[0] == '1' && cudaMalloc(&P->geo, sizeof(double) * 14 * (size_t)(nc > 0 ? nc : 1)) != cudaSuccess)
+    {
+      (void)cudaGetLastError();  // no room for the scratch: the kernels evaluate the geometry per incidence instead
+      P->geo = nullptr;
+    }
   RP_CK(cudaMalloc(&P->diag, (size_t)P->nrows_b + 1));
   k_rp_diag_default<<<(unsigned)((P->nrows_b + 255) / 256), 256, 0, s>>>(A, bs, P->nrows_b, P->diag);
   if (n0 > 0)
@@ -173,6 +210,13 @@ int row_plan_build(const mpcx_dofmap* dm, const int32_t* cells, long long nc, co
   RP_CK(cudaMalloc(&P->inc, sizeof(unsigned) * (size_t)(n_valid > 0 ? n_valid : 1)));
   RP_CK(cudaMalloc(&P->con_off, sizeof(unsigned) * (size_t)(P->nnz_block + 1)));
   RP_CK(cudaMalloc(&P->con, sizeof(unsigned short) * (size_t)(P->n_con > 0 ? P->n_con : 1)));
+  RP_CK(cudaMalloc(&P->ccol, (size_t)(P->n_con > 0 ? P->n_con : 1)));
+  RP_CK(cudaMalloc(&P->row_con, sizeof(unsigned) * (size_t)(P->nrows_b + 1)));
+  RP_CK(cudaMalloc(&P->rflag, (size_t)P->nrows_b + 1));
+  {
+    const int zero = 0;
+    RP_CK(cudaMemcpyToSymbolAsync(g_rp_wide, &zero, sizeof(int), 0, cudaMemcpyHostToDevice, s));
+  }
   if (n_valid > 0)
   {
     unsigned long long *c1 = nullptr, *c2 = nullptr;
@@ -182,13 +226,13 @@ int row_plan_build(const mpcx_dofmap* dm, const int32_t* cells, long long nc, co
     if (e2 != cudaSuccess) { cudaFree(c1); rc = cuda_check(e2, "row plan alloc"); goto done; }
     k_rp_contrib_keys<<<(unsigned)((n_valid + 127) / 128), 128, 0, s>>>(k2, n_valid, P->inc_off, dm->map, nd, bs, cells, A, c1, P->diag);
     cudaFree(k1); k1 = nullptr;
-    e2 = cub::DeviceRadixSort::SortKeys(nullptr, tb, c1, c2, (int)P->n_con, 0, 56, s);
+    e2 = cub::DeviceRadixSort::SortKeys(nullptr, tb, c1, c2, (int)P->n_con, 0, 64, s);
     if (e2 == cudaSuccess) e2 = cudaMalloc(&tmp, tb);
-    if (e2 == cudaSuccess) e2 = cub::DeviceRadixSort::SortKeys(tmp, tb, c1, c2, (int)P->n_con, 0, 56, s);
+    if (e2 == cudaSuccess) e2 = cub::DeviceRadixSort::SortKeys(tmp, tb, c1, c2, (int)P->n_con, 0, 64, s);
     if (e2 == cudaSuccess)
     {
-      k_rp_lower<<<(unsigned)((P->nnz_block + 256) / 256), 256, 0, s>>>(c2, P->n_con, 16, P->nnz_block, nullptr, P->con_off);
-      k_rp_con<<<(unsigned)((P->n_con + 255) / 256), 256, 0, s>>>(c2, P->n_con, P->con);
+      k_rp_lower<<<(unsigned)((P->nnz_block + 256) / 256), 256, 0, s>>>(c2, P->n_con, 24, P->nnz_block, nullptr, P->con_off);
+      k_rp_con<<<(unsigned)((P->n_con + 255) / 256), 256, 0, s>>>(c2, P->n_con, P->con, P->ccol);
       e2 = cudaStreamSynchronize(s);
     }
     cudaFree(c1); cudaFree(c2);
@@ -196,7 +240,13 @@ int row_plan_build(const mpcx_dofmap* dm, const int32_t* cells, long long nc, co
   }
   else
     RP_CK(cudaMemsetAsync(P->con_off, 0, sizeof(unsigned) * (size_t)(P->nnz_block + 1), s));
-  RP_CK(cudaStreamSynchronize(s));
+  k_rp_rowmeta<<<(unsigned)((P->nrows_b + 256) / 256), 256, 0, s>>>(A, bs, P->nrows_b, P->con_off, P->row_con, P->rflag);
+  {
+    int wide = 0;
+    RP_CK(cudaMemcpyFromSymbolAsync(&wide, g_rp_wide, sizeof(int), 0, cudaMemcpyDeviceToHost, s));
+    RP_CK(cudaStreamSynchronize(s));
+    P->flat_ok = wide ? 0 : 1;
+  }
 done:
   cudaFree(k1); cudaFree(k2); cudaFree(tmp);
   if (rc != MPCX_OK) { row_plan_free(P); P = nullptr; }
@@ -212,7 +262,51 @@ struct RowPlanD
   const unsigned short* con;
   const unsigned char* diag;
   long long nrows_b;
+  const unsigned char* ccol;
+  const unsigned* row_con;
+  const unsigned char* rflag;
+  const double* geo;  // staged geometry per active cell (stride GSP), or nullptr: evaluate per incidence
 };
+
+// The geometry a cell lane stages, evaluated ONCE per cell instead of once per incident node (P2: 10 x): the row
+// kernels then copy GS doubles per incidence -- one dependent load level and ~100 FP64 instructions less in their cell
+// phase, which for P2 edge-node rows (5 cells on 16 lanes) was about as long as the contribution phase.
+template <typename E>
+__global__ void __launch_bounds__(256)
+k_rg_geometry(IntD in, MeshD mesh, double* __restrict__ geo)
+{
+  constexpr int TD = E::TD, NG = TD + 1, GS = E::GS, GSP = (GS + 1) & ~1;
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= in.ncells) return;
+  const int cell = in.cells ? __ldg(in.cells + idx) : (int)idx;
+  int xd[NG];
+#pragma unroll
+  for (int v = 0; v < NG; ++v) xd[v] = __ldg(mesh.xd + (long long)cell * NG + v);
+  double X[NG][3];
+  load_vertices<TD>(mesh, xd, X);
+  P1Geom<TD> G;
+  p1_geometry<TD>(X, G);
+  double g[GSP];
+  g[GSP - 1] = 0.0;
+  E::stage(G, g);
+  double2* dst = reinterpret_cast<double2*>(geo + idx * GSP);
+#pragma unroll
+  for (int k = 0; k < GSP / 2; ++k) dst[k] = make_double2(g[2 * k], g[2 * k + 1]);
+}
+
+template <typename E>
+__device__ __forceinline__ void rg_copy_geometry(const double* __restrict__ geo, long long idx, double* g)
+{
+  constexpr int GS = E::GS, GSP = (GS + 1) & ~1;
+  const double2* src = reinterpret_cast<const double2*>(geo + idx * GSP);
+#pragma unroll
+  for (int k = 0; k < GSP / 2; ++k)
+  {
+    const double2 v = __ldg(src + k);
+    g[2 * k] = v.x;
+    if (2 * k + 1 < GS) g[2 * k + 1] = v.y;
+  }
+}
 
 // ---- element policies: what a cell lane stages, and how a (cell, i, j) contribution is formed from the staged data
 // P1 simplex (TD = tdim = gdim = bs): the gradients of the barycentric coordinates and the volume (13 doubles in 3-D);
@@ -438,7 +532,7 @@ k_rowgather_elast(RowPlanD P, Tab t, IntD in, MeshD mesh, const int8_t* __restri
 // All cells of a row (up to 32 per pass) are staged first, 16 at a time, then the columns are walked 16 at a time
 // without re-staging.  Rows with more than 32 cells take further passes that add onto the stored row (same lanes own
 // the same entries: plain read-modify-write, no atomics).
-template <typename E, int MINB>
+template <typename E, int MINB, bool PRE>
 __global__ void __launch_bounds__(256, MINB)
 k_rowgather_elast2(RowPlanD P, Tab t, IntD in, MeshD mesh, const int8_t* __restrict__ bc, CsrD A)
 {
@@ -504,16 +598,20 @@ k_rowgather_elast2(RowPlanD P, Tab t, IntD in, MeshD mesh, const int8_t* __restr
           const unsigned w = __ldg(P.inc + i0 + k);
           const long long idx = w / ND;
           const int il = (int)(w - idx * ND);
-          const int cell = in.cells ? __ldg(in.cells + idx) : (int)idx;
-          int xd[NG];
-#pragma unroll
-          for (int v = 0; v < NG; ++v) xd[v] = __ldg(mesh.xd + (long long)cell * NG + v);
-          double X[NG][3];
-          load_vertices<TD>(mesh, xd, X);
-          P1Geom<TD> G;
-          p1_geometry<TD>(X, G);
           double* g = geo + (ss + sl) * GS;
-          E::stage(G, g);
+          if (PRE) rg_copy_geometry<E>(P.geo, idx, g);
+          else
+          {
+            const int cell = in.cells ? __ldg(in.cells + idx) : (int)idx;
+            int xd[NG];
+#pragma unroll
+            for (int v = 0; v < NG; ++v) xd[v] = __ldg(mesh.xd + (long long)cell * NG + v);
+            double X[NG][3];
+            load_vertices<TD>(mesh, xd, X);
+            P1Geom<TD> G;
+            p1_geometry<TD>(X, G);
+            E::stage(G, g);
+          }
           E::add(M, g, il, il, mu, lmbda, dg);  // reads back this lane's own stores
         }
       }
@@ -590,6 +688,224 @@ k_rowgather_elast2(RowPlanD P, Tab t, IntD in, MeshD mesh, const int8_t* __restr
     }
     if (!more) break;
     I = In; i0 = n_i0; i1 = n_i1; kd = n_kd; r0 = n_r0; r1 = n_r1;
+  }
+}
+
+// Flat walk: the contributions of a row are ONE list (sorted by block column); the 16 lanes of the row's half-warp take
+// equal contiguous shares of it instead of a column each.  With a lane per column the lanes of a pass ran as long as
+// the column with the most contributions (P2: 1 .. 24 per column) and 13 of 32 lanes were active in the FP64
+// instructions of the kernel (ncu, profiles/r02_i); here every lane forms the same number of 3 x 3 contributions
+// (+- 1).  A lane accumulates in registers while the column stays the same and stores a column when it leaves it; the
+// column a share STARTS in the middle of (head) goes to the lane that holds the column's beginning through a segmented
+// suffix sum over the half-warp (shuffles, 9 values, once per row), so every entry is still written exactly once,
+// without atomics.  The diagonal block is just another column.  Block entries without any contribution (pairs whose
+// cells all hold slaves) are stored as zeros by the rows flagged at plan time.
+template <typename E, int MINB, bool PRE>
+__global__ void __launch_bounds__(256, MINB)
+k_rowgather_elast3(RowPlanD P, Tab t, IntD in, MeshD mesh, const int8_t* __restrict__ bc, CsrD A)
+{
+  constexpr int TD = E::TD, ND = E::ND, BS = E::BS, GS = E::GS, NG = TD + 1;
+  extern __shared__ double rg_smem[];
+  double* M = rg_smem;
+  const int lane = threadIdx.x & 31, sub = lane >> 4, sl = lane & 15, hw = (threadIdx.x >> 5) * 2 + sub;
+  double* geo = rg_smem + E::SMEM_TABLE + hw * 32 * GS;  // [32 cells][GS] of this half-warp
+  unsigned char* cmask = reinterpret_cast<unsigned char*>(rg_smem + E::SMEM_TABLE + 16 * 32 * GS) + hw * 256;  // Dirichlet bits per column
+  E::init(t, M);
+  if (E::SMEM_TABLE) __syncthreads();
+  const double mu = in.c[0], lmbda = in.c[1];
+  const long long wstride = (long long)gridDim.x * 16;
+  long long I = ((long long)blockIdx.x * 8 + (threadIdx.x >> 5)) * 2 + sub;
+  if (I - sub >= P.nrows_b) return;
+  auto hdr = [&](long long row, int& i0, int& i1, unsigned& t0, unsigned& t1, long long& r0, long long& r1, int& fl) {
+    i0 = i1 = fl = 0; t0 = t1 = 0u; r0 = r1 = 0;
+    if (row < P.nrows_b)
+    {
+      i0 = __ldg(P.inc_off + row); i1 = __ldg(P.inc_off + row + 1); fl = __ldg(P.rflag + row);
+      t0 = __ldg(P.row_con + row); t1 = __ldg(P.row_con + row + 1);
+      r0 = __ldg(A.rp + BS * row); r1 = __ldg(A.rp + BS * row + 1);
+    }
+  };
+  int i0, i1, fl;
+  unsigned tb0, tb1;
+  long long r0, r1;
+  hdr(I, i0, i1, tb0, tb1, r0, r1, fl);
+  for (;;)
+  {
+    const long long In = I + wstride;
+    const bool more = In - sub < P.nrows_b;  // warp-uniform
+    int n_i0, n_i1, n_fl;
+    unsigned n_t0, n_t1;
+    long long n_r0, n_r1;
+    hdr(In, n_i0, n_i1, n_t0, n_t1, n_r0, n_r1, n_fl);
+    const int ninc = i1 - i0, nb = (int)((r1 - r0) / BS);
+    const int T = (int)(tb1 - tb0);
+    const int ninc_w = max(__shfl_sync(0xffffffffu, ninc, 0), __shfl_sync(0xffffffffu, ninc, 16));
+    const int T_w = max(__shfl_sync(0xffffffffu, T, 0), __shfl_sync(0xffffffffu, T, 16));
+    const int nb_w = max(__shfl_sync(0xffffffffu, nb, 0), __shfl_sync(0xffffffffu, nb, 16));
+    bool bcr[BS];
+#pragma unroll
+    for (int a = 0; a < BS; ++a) bcr[a] = (bc && nb > 0) ? bc[BS * I + a] != 0 : false;
+    // this lane's share of the list and its first words, requested before the cell phase
+    const unsigned ta = tb0 + (unsigned)(((long long)T * sl) >> 4), te = tb0 + (unsigned)(((long long)T * (sl + 1)) >> 4);
+    const int prevcol = ta > tb0 ? (int)__ldg(P.ccol + ta - 1) : -1;  // column of the contribution before the share
+    constexpr int CW = 8;
+    unsigned pw[CW];  // (column << 16 | contribution word) of the first CW contributions of the share
+#pragma unroll
+    for (int u = 0; u < CW; ++u)
+      pw[u] = ta + u < te ? ((unsigned)__ldg(P.ccol + ta + u) << 16) | (unsigned)__ldg(P.con + ta + u) : 0xffffffffu;
+    // Dirichlet bits of the columns -> shared memory (lanes = columns; two dependent loads, hidden behind the cell phase)
+    __syncwarp();
+    if (bc)
+      for (int kc = sl; kc < nb; kc += 16)
+      {
+        const int J = __ldg(A.col + r0 + (long long)BS * kc) / BS;
+        unsigned m = 0u;
+#pragma unroll
+        for (int b = 0; b < BS; ++b) m |= (bc[BS * J + b] != 0 ? 1u : 0u) << b;
+        cmask[kc] = (unsigned char)m;
+      }
+    auto store = [&](int col, const double (*acc)[BS], bool first_pass) {
+      const unsigned m = bc ? cmask[col] : 0u;
+#pragma unroll
+      for (int a = 0; a < BS; ++a)
+      {
+        double* dst = A.val + r0 + (long long)a * BS * nb + (long long)BS * col;
+#pragma unroll
+        for (int b = 0; b < BS; ++b)
+        {
+          const double v = (bcr[a] || ((m >> b) & 1u)) ? 0.0 : acc[a][b];
+          if (first_pass) dst[b] = v; else dst[b] += v;
+        }
+      }
+    };
+    for (int sc = 0; sc < ninc_w || sc == 0; sc += 32)
+    {
+      // ---- lanes = cells (two steps of 16): affine geometry -> shared memory
+      __syncwarp();
+#pragma unroll
+      for (int ss = 0; ss < 32; ss += 16)
+      {
+        const int k = sc + ss + sl;
+        if (k < ninc)
+        {
+          const unsigned w = __ldg(P.inc + i0 + k);
+          const long long idx = w / ND;
+          if (PRE) rg_copy_geometry<E>(P.geo, idx, geo + (ss + sl) * GS);
+          else
+          {
+            const int cell = in.cells ? __ldg(in.cells + idx) : (int)idx;
+            int xd[NG];
+#pragma unroll
+            for (int v = 0; v < NG; ++v) xd[v] = __ldg(mesh.xd + (long long)cell * NG + v);
+            double X[NG][3];
+            load_vertices<TD>(mesh, xd, X);
+            P1Geom<TD> G;
+            p1_geometry<TD>(X, G);
+            E::stage(G, geo + (ss + sl) * GS);
+          }
+        }
+      }
+      __syncwarp();
+      // ---- lanes = equal shares of the row's contributions
+      double acc[BS][BS], H[BS][BS];
+#pragma unroll
+      for (int a = 0; a < BS; ++a)
+#pragma unroll
+        for (int b = 0; b < BS; ++b) { acc[a][b] = 0.0; H[a][b] = 0.0; }
+      const bool nonempty = ta < te;
+      const int firstcol = nonempty ? (int)(pw[0] >> 16) : -2;
+      const bool headful = nonempty && prevcol == firstcol;  // the share starts inside the column of the lane before it
+      int cur = firstcol;
+      bool in_head = headful;
+      const int steps = (T_w + 15) >> 4;  // >= the longest share of the warp
+      auto step = [&](unsigned word) {
+        const unsigned c16 = word & 0xffffu;
+        const int col = (int)(word >> 16);
+        if (col != cur)
+        {
+          if (in_head)
+          {
+#pragma unroll
+            for (int a = 0; a < BS; ++a)
+#pragma unroll
+              for (int b = 0; b < BS; ++b) H[a][b] = acc[a][b];
+            in_head = false;
+          }
+          else store(cur, acc, sc == 0);
+          cur = col;
+#pragma unroll
+          for (int a = 0; a < BS; ++a)
+#pragma unroll
+            for (int b = 0; b < BS; ++b) acc[a][b] = 0.0;
+        }
+        const int kl = (int)(c16 >> 8) - sc;
+        if (kl >= 0 && kl < 32) E::add(M, geo + kl * GS, (int)((c16 >> 4) & 15u), (int)(c16 & 15u), mu, lmbda, acc);
+      };
+#pragma unroll
+      for (int u = 0; u < CW; ++u)
+        if (u < steps && pw[u] != 0xffffffffu) step(pw[u]);
+      for (int m = CW; m < steps; ++m)  // shares longer than CW (rows with more than 16 CW contributions)
+      {
+        const unsigned tt = ta + (unsigned)m;
+        if (tt < te) step(((unsigned)__ldg(P.ccol + tt) << 16) | (unsigned)__ldg(P.con + tt));
+      }
+      // What is left in acc: the LAST column of the share, whose beginning this lane holds (tail; the lanes after it may
+      // hold more of it as their heads) -- or, when the whole share lies inside the previous lane's column, a head.  An
+      // empty share carries a zero head of the column before it, which keeps that column's lanes consecutive.
+      const bool has_tail = nonempty && !in_head;
+      if (in_head)
+      {
+#pragma unroll
+        for (int a = 0; a < BS; ++a)
+#pragma unroll
+          for (int b = 0; b < BS; ++b) H[a][b] = acc[a][b];
+      }
+      const int hkey = headful ? firstcol : ((!nonempty && prevcol >= 0) ? prevcol : -1 - sl);
+      // segmented suffix sum of the heads over the half-warp (equal keys sit in consecutive lanes)
+#pragma unroll
+      for (int o = 1; o < 16; o <<= 1)
+      {
+        const int k2 = __shfl_down_sync(0xffffffffu, hkey, o, 16);
+        const bool take = sl + o < 16 && k2 == hkey;
+#pragma unroll
+        for (int a = 0; a < BS; ++a)
+#pragma unroll
+          for (int b = 0; b < BS; ++b)
+          {
+            const double v2 = __shfl_down_sync(0xffffffffu, H[a][b], o, 16);
+            if (take) H[a][b] += v2;
+          }
+      }
+      {
+        const int k2 = __shfl_down_sync(0xffffffffu, hkey, 1, 16);
+        const bool take = has_tail && sl + 1 < 16 && k2 == cur;
+#pragma unroll
+        for (int a = 0; a < BS; ++a)
+#pragma unroll
+          for (int b = 0; b < BS; ++b)
+          {
+            const double v2 = __shfl_down_sync(0xffffffffu, H[a][b], 1, 16);
+            if (take) acc[a][b] += v2;
+          }
+        if (has_tail) store(cur, acc, sc == 0);
+      }
+    }
+    // block entries without contributions (and rows without any bulk cell): zeros
+    if (fl || T == 0)
+    {
+      const long long blk0 = r0 / (BS * BS);
+      for (int kc = sl; kc < nb; kc += 16)
+        if (__ldg(P.con_off + blk0 + kc) == __ldg(P.con_off + blk0 + kc + 1))
+        {
+#pragma unroll
+          for (int a = 0; a < BS; ++a)
+#pragma unroll
+            for (int b = 0; b < BS; ++b) A.val[r0 + (long long)a * BS * nb + (long long)BS * kc + b] = 0.0;
+        }
+    }
+    (void)nb_w;
+    if (!more) break;
+    I = In; i0 = n_i0; i1 = n_i1; tb0 = n_t0; tb1 = n_t1; r0 = n_r0; r1 = n_r1; fl = n_fl;
   }
 }
 }  // namespace
