@@ -65,7 +65,7 @@ class MpcHostS(C.Structure):
 
 # every symbol include/mpcx.h declares (tests check the library exports all of them)
 SYMBOLS = (
-    "mpcx_last_error", "mpcx_abi_version", "mpcx_device_error", "mpcx_device_error_async", "mpcx_assemble_matrix_f64",
+    "mpcx_last_error", "mpcx_abi_version", "mpcx_device_error", "mpcx_device_error_async", "mpcx_zero_f64", "mpcx_assemble_matrix_f64",
     "mpcx_add_diagonal_f64", "mpcx_build_plan", "mpcx_assemble_vector_f64", "mpcx_apply_lifting_f64",
     "mpcx_backsubstitution_f64", "mpcx_homogenize_f64", "mpcx_gather_f64", "mpcx_scatter_add_f64",
     "mpcx_create_pattern_host", "mpcx_free_host", "mpcx_profile_enable", "mpcx_launch_count", "mpcx_profile_read",
@@ -101,6 +101,7 @@ def load():
     P = C.POINTER
     lib.mpcx_device_error.argtypes = [vp]
     lib.mpcx_device_error_async.argtypes = [vp, vp]
+    lib.mpcx_zero_f64.argtypes = [vp, C.c_int64, vp]
     lib.mpcx_assemble_matrix_f64.argtypes = [P(IntegralS), P(MeshS), P(DofmapS), P(DofmapS), vp, vp, P(MpcS),
                                              P(MpcS), P(CsrS), P(PlanS), vp]
     lib.mpcx_add_diagonal_f64.argtypes = [P(CsrS), vp, i64, f64, vp]

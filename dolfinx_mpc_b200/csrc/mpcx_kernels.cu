@@ -1624,6 +1624,13 @@ int mpcx_device_error_async(int32_t* pinned_host_flag, void* stream)
                     "device_error_async");
 }
 
+int mpcx_zero_f64(double* data, int64_t n, void* stream)
+{
+  if (n < 0 || (!data && n > 0)) return fail(MPCX_ERR_ARG, "bad buffer");
+  if (n == 0) return MPCX_OK;
+  return cuda_check(cudaMemsetAsync(data, 0, sizeof(double) * (size_t)n, (cudaStream_t)stream), "zero");
+}
+
 int mpcx_assemble_matrix_f64(const mpcx_integral* integral, const mpcx_mesh* mesh,
                              const mpcx_dofmap* dofmap0, const mpcx_dofmap* dofmap1,
                              const int8_t* bc0, const int8_t* bc1, const mpcx_mpc* mpc0,

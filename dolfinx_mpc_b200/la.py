@@ -100,8 +100,8 @@ class Matrix:
     def zeroEntries(self):
         if self.async_zero:
             self._swap_to_zeroed_buffer()
-        else:
-            self.val.zero_()
+        else:  # cudaMemsetAsync through the library on the assembly stream (no framework fill kernel on the hot path)
+            _lib.check(_lib.load().mpcx_zero_f64(_dev.ptr(self.val), self.val.numel(), _dev.stream_ptr()))
 
     def _swap_to_zeroed_buffer(self):
         """``async_zero``: two value buffers.  The assembly that starts now writes into the spare one, which was
@@ -355,7 +355,10 @@ class Vector:
         return self.data.data_ptr() % 16 == 0
 
     def set(self, v: float):
-        self.data.fill_(v)
+        if v == 0.0 and self.data.is_cuda:
+            _lib.check(_lib.load().mpcx_zero_f64(_dev.ptr(self.data), self.data.numel(), _dev.stream_ptr()))
+        else:
+            self.data.fill_(v)
 
     @property
     def array(self) -> np.ndarray:

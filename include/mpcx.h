@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define MPCX_ABI_VERSION 4
+#define MPCX_ABI_VERSION 5
 #define MPCX_MAX_CONSTANTS 8
 
 typedef enum mpcx_status
@@ -182,6 +182,11 @@ int mpcx_device_error(void* stream);
  * *pinned_host_flag later (after an event / at its next call), so that a time loop keeps the device queue filled.  The
  * flag is not cleared. */
 int mpcx_device_error_async(int32_t* pinned_host_flag, void* stream);
+
+/* data[0 .. n) <- 0 in stream order (cudaMemsetAsync): `A.zeroEntries()` before an assembly
+ * (python/src/dolfinx_mpc/assemble_matrix.py:51, problem.py:539) and `b_local.set(0.0)`
+ * (python/src/dolfinx_mpc/assemble_vector.py:100-101) in the reference's callers. */
+int mpcx_zero_f64(double* data, int64_t n, void* stream);
 
 /* A += integral, with BC row/column zeroing and MPC elimination K^T A_e K.
  * Replaces assemble_cells_impl + modify_mpc_cell (cpp/assemble_matrix.cpp:417-548,
