@@ -16,6 +16,7 @@ Everything in this module except ``GhostExchange.reduce_*`` is once-per-pattern 
 from __future__ import annotations
 
 import ctypes as C
+import os
 from typing import Callable, Optional
 
 import numpy as np
@@ -256,6 +257,155 @@ def extend_pattern(row_ptr: np.ndarray, col: np.ndarray, imap_rows: IndexMap, im
     return row_ptr, col, col_global, plan
 
 
+def _all_to_all_tensors(objs, group, dev):
+    """Tensor version of :func:`_all_to_all_objects`: ``objs[r]`` is None or a tuple of int64 tensors on ``dev``; the
+    received tuples are views of one receive buffer on ``dev``.  NCCL: two ``all_to_all_single`` calls (sizes, payload),
+    the payload never leaves the device; gloo (CPU tests): ``all_gather_object``."""
+    world = dist.get_world_size(group)
+    me = dist.get_rank(group)
+    if dist.get_backend(group) != "nccl":
+        gathered = [None] * world
+        dist.all_gather_object(gathered, [None if o is None else tuple(t.cpu() for t in o) for o in objs], group=group)
+        return [None if gathered[src][me] is None else tuple(t.to(dev) for t in gathered[src][me]) for src in range(world)]
+    narr = max([len(o) for o in objs if o is not None], default=0)
+    t = torch.tensor([narr], device=dev)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX, group=group)
+    narr = int(t.item())
+    sizes = np.full((world, max(1, narr)), -1, dtype=np.int64)
+    for r, o in enumerate(objs):
+        if o is not None:
+            sizes[r, : len(o)] = [a.numel() for a in o]
+    s_send = torch.from_numpy(sizes).to(dev)
+    s_recv = torch.empty_like(s_send)
+    dist.all_to_all_single(s_recv, s_send, group=group)
+    rsz = s_recv.cpu().numpy()
+    parts = [a.reshape(-1).to(torch.int64) for o in objs if o is not None for a in o]
+    send = torch.cat(parts) if parts else torch.zeros(0, dtype=torch.int64, device=dev)
+    out_splits = [0 if o is None else int(sum(a.numel() for a in o)) for o in objs]
+    in_splits = [int(np.clip(rsz[r], 0, None).sum()) for r in range(world)]
+    recv = torch.empty(sum(in_splits), dtype=torch.int64, device=dev)
+    dist.all_to_all_single(recv, send, in_splits, out_splits, group=group)
+    out, pos = [], 0
+    for r in range(world):
+        if rsz[r, 0] < 0:
+            out.append(None)
+            continue
+        arrs = []
+        for k in range(narr):
+            n = int(rsz[r, k])
+            if n < 0:
+                break
+            arrs.append(recv[pos:pos + n])
+            pos += n
+        out.append(tuple(arrs))
+    return out
+
+
+def extend_pattern_device(row_ptr: torch.Tensor, col: torch.Tensor, imap_rows: IndexMap, imap_cols: IndexMap, bs0: int,
+                          bs1: int, group=None):
+    """:func:`extend_pattern` on tensors that stay where they are (the device under NCCL): the ghost rows' (global row,
+    global column) pairs travel point to point, the owner maps the columns to local ones (new pattern ghosts for
+    unknown blocks), and the owned rows between the first and the last row that receive something are rebuilt in ONE
+    sort of (row, column) keys -- no per-row host loop, no host copy of the pattern.  Same return values as
+    :func:`extend_pattern`, as tensors (``col_global`` too)."""
+    dev = row_ptr.device
+    world = dist.get_world_size(group)
+    i64 = torch.int64
+    n_owned_r = imap_rows.size_local * bs0
+    n_rows = row_ptr.numel() - 1
+    nloc_blocks = imap_cols.size_local + imap_cols.num_ghosts
+    ncols_local = nloc_blocks * bs1
+    lo_c, hi_c = imap_cols.local_range
+    ghosts_c = torch.from_numpy(np.asarray(imap_cols.ghosts, dtype=np.int64)).to(dev)
+
+    def col_l2g(c):
+        blk = torch.div(c, bs1, rounding_mode="floor")
+        g = blk + lo_c
+        if ghosts_c.numel():
+            gi = (blk - imap_cols.size_local).clamp_(min=0)
+            g = torch.where(blk < imap_cols.size_local, g, ghosts_c[gi])
+        return g * bs1 + c % bs1
+
+    # ghost rows -> (global row, row lengths, global cols) per owner; the per-row bookkeeping (O(ghost rows)) on the host
+    ghost_rows = np.arange(n_owned_r, n_rows, dtype=np.int64)
+    g_owner = np.repeat(np.asarray(imap_rows.owners, dtype=np.int64), bs0)
+    g_glob = np.repeat(np.asarray(imap_rows.ghosts, dtype=np.int64), bs0) * bs0 + np.tile(np.arange(bs0), imap_rows.num_ghosts)
+    send, send_idx, send_counts = [], [], []
+    for dst in range(world):
+        rows = ghost_rows[g_owner == dst]
+        if len(rows) == 0:
+            send.append(None)
+            send_counts.append(0)
+            continue
+        rows_t = torch.from_numpy(rows).to(dev)
+        starts = row_ptr[rows_t]
+        lens = row_ptr[rows_t + 1] - starts
+        if np.all(np.diff(rows) == 1):  # ghosts of one owner are usually one contiguous block of rows
+            idx = torch.arange(int(starts[0]), int(row_ptr[int(rows[-1]) + 1]), device=dev, dtype=i64)
+        else:
+            excl = torch.cumsum(lens, 0) - lens
+            idx = torch.arange(int(lens.sum()), device=dev, dtype=i64) + torch.repeat_interleave(starts - excl, lens)
+        send.append((torch.from_numpy(g_glob[rows - n_owned_r]).to(dev), lens, col_l2g(col[idx].to(i64))))
+        send_idx.append(idx)
+        send_counts.append(int(idx.numel()))
+    recv = _all_to_all_tensors(send, group, dev)
+
+    lo_r = imap_rows.local_range[0] * bs0
+    col_global = col_l2g(torch.arange(ncols_local, device=dev, dtype=i64))
+    extra_r, extra_c = [], []
+    for src in range(world):
+        if recv[src] is None:
+            continue
+        grow, lens, gcols = recv[src]
+        extra_r.append(torch.repeat_interleave(grow - lo_r, lens))
+        extra_c.append(gcols)
+    recv_pos, recv_counts = torch.zeros(0, dtype=i64, device=dev), [0] * world
+    if extra_r:
+        er = torch.cat(extra_r)
+        ec_g = torch.cat(extra_c)
+        if er.numel():
+            assert int(er.min()) >= 0 and int(er.max()) < n_owned_r, "received a ghost row this rank does not own"
+        # global -> local column, allocating pattern ghosts for unknown blocks
+        blk = torch.div(ec_g, bs1, rounding_mode="floor")
+        own = (blk >= lo_c) & (blk < hi_c)
+        loc = torch.where(own, blk - lo_c, torch.full_like(blk, -1))
+        if ghosts_c.numel():
+            sg, order = torch.sort(ghosts_c, stable=True)
+            pos = torch.searchsorted(sg, blk).clamp_(max=sg.numel() - 1)
+            hit = (sg[pos] == blk) & ~own
+            loc = torch.where(hit, order[pos] + imap_cols.size_local, loc)
+        unknown = loc < 0
+        new_blocks = torch.unique(blk[unknown])
+        if new_blocks.numel():
+            loc = torch.where(unknown, torch.searchsorted(new_blocks, blk) + nloc_blocks, loc)
+            newg = (new_blocks[:, None] * bs1 + torch.arange(bs1, device=dev, dtype=i64)[None, :]).reshape(-1)
+            col_global = torch.cat([col_global, newg])
+        ec = loc * bs1 + ec_g % bs1
+        ncol_tot = int(col_global.numel())
+        new_keys = er * ncol_tot + ec
+        # rebuild the owned rows [r_lo, r_hi): old entries and received ones, unique, sorted by (row, column)
+        r_lo, r_hi = int(er.min()), int(er.max()) + 1
+        e_lo, e_hi = int(row_ptr[r_lo]), int(row_ptr[r_hi])
+        old_len = row_ptr[1:] - row_ptr[:-1]
+        row_of = torch.repeat_interleave(torch.arange(r_lo, r_hi, device=dev, dtype=i64), old_len[r_lo:r_hi])
+        keys = torch.unique(torch.cat([row_of * ncol_tot + col[e_lo:e_hi].to(i64), new_keys]))  # sorted
+        del row_of
+        k_rows = torch.div(keys, ncol_tot, rounding_mode="floor")
+        new_len = old_len.clone()
+        new_len[r_lo:r_hi] = torch.bincount(k_rows - r_lo, minlength=r_hi - r_lo)
+        new_row_ptr = torch.zeros(n_rows + 1, dtype=i64, device=dev)
+        torch.cumsum(new_len, 0, out=new_row_ptr[1:])
+        new_col = torch.cat([col[:e_lo], (keys - k_rows * ncol_tot).to(torch.int32), col[e_hi:]])
+        recv_pos = e_lo + torch.searchsorted(keys, new_keys)
+        recv_counts = [0 if recv[s_] is None else int(recv[s_][1].sum()) for s_ in range(world)]
+        shift = int(new_row_ptr[n_owned_r] - row_ptr[n_owned_r])  # ghost rows moved by the growth of the owned part
+        send_idx = [i + shift for i in send_idx]
+        row_ptr, col = new_row_ptr, new_col
+    plan = {"send_idx": torch.cat(send_idx) if send_idx else torch.zeros(0, dtype=i64, device=dev),
+            "send_counts": send_counts, "recv_pos": recv_pos, "recv_counts": recv_counts}
+    return row_ptr, col, col_global, plan
+
+
 def vector_plan(imap: IndexMap, bs: int, group=None):
     """Exchange plan of ``VecGhostUpdate(ADD, REVERSE)``: ghost entries grouped by owner, and on the owner
     the local positions they are added to."""
@@ -330,12 +480,14 @@ class GhostExchange:
         self.group = group
         self.send_counts = list(plan["send_counts"])
         self.recv_counts = list(plan["recv_counts"])
-        si = np.asarray(plan["send_idx"], dtype=np.int64)
-        self.n_send, self.n_recv = int(si.size), int(np.asarray(plan["recv_pos"]).size)
-        self.contiguous = self.n_send > 0 and bool(np.all(np.diff(si) == 1))
+        si, rp = plan["send_idx"], plan["recv_pos"]
+        si = si.to(torch.int64) if isinstance(si, torch.Tensor) else torch.from_numpy(np.asarray(si, dtype=np.int64))
+        rp = rp.to(torch.int64) if isinstance(rp, torch.Tensor) else torch.from_numpy(np.asarray(rp, dtype=np.int64))
+        self.n_send, self.n_recv = int(si.numel()), int(rp.numel())
+        self.contiguous = self.n_send > 0 and bool(torch.all(si[1:] - si[:-1] == 1))
         self.send_start = int(si[0]) if self.n_send else 0
-        self.send_idx = torch.from_numpy(si).to(device)
-        self.recv_pos = torch.from_numpy(np.asarray(plan["recv_pos"], dtype=np.int64)).to(device)
+        self.send_idx = si.to(device)
+        self.recv_pos = rp.to(device)
         self.send_buf = torch.empty(self.n_send, dtype=torch.float64, device=device)
         self.recv_buf = torch.empty(self.n_recv, dtype=torch.float64, device=device)
         self.comm = None
@@ -400,11 +552,20 @@ def create_matrix(a: fem.Form, mpc: MultiPointConstraint, group=None):
     from .assemble_matrix import create_sparsity_pattern
     from .la import Matrix
 
-    row_ptr, col = create_sparsity_pattern(a, mpc)
     V = mpc.function_space
-    row_ptr, col, col_global, plan = extend_pattern(row_ptr, col, V.index_map, V.index_map, V.bs, V.bs, group)
-    A = Matrix(row_ptr, col, (V.num_dofs, len(col_global)), (V.bs, V.bs))
-    A.col_global = col_global
+    if torch.cuda.is_available() and os.environ.get("MPCX_PATTERN", "device") != "host":
+        # pattern built, extended and kept on the device; col_global comes back for the callers
+        from .assemble_matrix import create_sparsity_pattern_device
+
+        row_ptr, col = create_sparsity_pattern_device(a, mpc)
+        row_ptr, col, col_global, plan = extend_pattern_device(row_ptr, col, V.index_map, V.index_map, V.bs, V.bs, group)
+        A = Matrix(row_ptr, col.contiguous(), (V.num_dofs, int(col_global.numel())), (V.bs, V.bs))
+        A.col_global = col_global.cpu().numpy()
+    else:
+        row_ptr, col = create_sparsity_pattern(a, mpc)
+        row_ptr, col, col_global, plan = extend_pattern(row_ptr, col, V.index_map, V.index_map, V.bs, V.bs, group)
+        A = Matrix(row_ptr, col, (V.num_dofs, len(col_global)), (V.bs, V.bs))
+        A.col_global = col_global
     A.ghost_exchange = MatVecExchange(plan, None, _dev.device(), group)
     return A
 

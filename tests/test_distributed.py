@@ -48,8 +48,15 @@ def _worker(rank, world, port, periodic_z, n, nzc, out_dir, cuda=False):
 
     P = D.build_slab_problem(n, rank, world, _f, periodic_z=periodic_z, nzc=nzc)
     mpc, V = P["mpc"], P["mpc"].function_space
-    rp, col = create_sparsity_pattern(P["a"], mpc, num_threads=2)
-    rp, col, col_global, plan = D.extend_pattern(rp, col, V.index_map, V.index_map, 1, 1)
+    rp0, col0 = create_sparsity_pattern(P["a"], mpc, num_threads=2)
+    rp, col, col_global, plan = D.extend_pattern(rp0, col0, V.index_map, V.index_map, 1, 1)
+    # the tensor version (what runs on the device under NCCL) gives the same pattern and the same exchange plan
+    rp_t, col_t, cg_t, plan_t = D.extend_pattern_device(torch.from_numpy(rp0), torch.from_numpy(col0), V.index_map,
+                                                        V.index_map, 1, 1)
+    assert np.array_equal(rp_t.numpy(), rp) and np.array_equal(col_t.numpy(), col)
+    assert np.array_equal(cg_t.numpy(), col_global)
+    assert np.array_equal(plan_t["send_idx"].numpy(), plan["send_idx"]) and np.array_equal(plan_t["recv_pos"].numpy(), plan["recv_pos"])
+    assert list(plan_t["send_counts"]) == list(plan["send_counts"]) and list(plan_t["recv_counts"]) == list(plan["recv_counts"])
     m = orc.WrappedMPC(V, mpc.is_slave, mpc.masters.array, mpc.coefficients()[0], mpc.masters.offsets,
                        mpc.cell_to_slaves.array, mpc.cell_to_slaves.offsets, mpc.slaves, mpc.num_local_slaves)
     _, _, val = orc.assemble_matrix(P["a"], m, bcs=P["bcs"], pattern=(rp, col))
