@@ -91,6 +91,30 @@ def test_matrix_vector_lifting_match_oracle(oracle, name):
     oracle.compare_mpc_rhs(b0, b.array, K, slaves)
 
 
+@pytest.mark.parametrize("variant", [{"MPCX_ROWGATHER_V": "1"}, {"MPCX_ROWGATHER_V": "3"}, {"MPCX_ROWGATHER_GEO": "1"},
+                                     {"MPCX_ROWGATHER_V": "3", "MPCX_ROWGATHER_GEO": "1"}, {"MPCX_ROWGATHER": "0"}],
+                         ids=["warp-per-row", "flat-walk", "geometry-once", "flat-walk+geometry-once", "atomic"])
+@pytest.mark.parametrize("name", ["contact3d", "slip3d-P2-2"])
+def test_row_gather_variants_match_oracle(oracle, monkeypatch, name, variant):
+    """The blocked-elasticity kernels kept behind switches (profiles/README.md r02_k) produce the same matrix as the
+    default one (half-warp per row, lane per column) and the oracle: warp per row, the flat walk over a row's
+    contributions, the geometry evaluated once per cell, and the atomic-scatter fallback."""
+    import dolfinx_mpc_b200 as mpcx
+
+    if name not in problems.ALL_CASES:
+        pytest.skip("case not in this build of the problem set")
+    for k, v in variant.items():
+        monkeypatch.setenv(k, v)
+    c = problems.ALL_CASES[name]()
+    mpc = _mpc(c)
+    m = oracle.mpc_from_arrays(c.V, c.data)
+    A = mpcx.assemble_matrix(c.a, mpc, bcs=c.bcs, diagval=1.0)
+    rp_o, col_o, val_o = oracle.assemble_matrix(c.a, m, bcs=c.bcs, diagval=1.0)
+    assert_csr_close(*A.getValuesCSR(), rp_o, col_o, val_o)
+    mpcx.assemble_matrix(c.a, mpc, bcs=c.bcs, diagval=1.0, A=A)  # cached plans
+    assert_csr_close(*A.getValuesCSR(), rp_o, col_o, val_o)
+
+
 @pytest.mark.parametrize("name", ["periodic2d-P1-8-bc1", "slip3d-P1-3", "contact3d"])
 def test_lifting_with_x0_and_scale(oracle, name):
     import dolfinx_mpc_b200 as mpcx
