@@ -34,6 +34,7 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
 FALLBACK_HBM_GBS = 6650.0  # /opt/skills/guides/B200_PROFILING.md fallback
+BULK_REDUCE_PEAK_GADDS = 270.0  # cp.reduce.async.bulk add.f64, whole B200, kernel-shaped operations (see main)
 TRAFFIC_FILE = os.path.join(ROOT, "profiles", "traffic.json")  # written by tools/ncu_summary.py from ncu --set full captures
 
 DEFAULT_N = {2: 256, 3: 127, 4: 512, 5: 114}
@@ -509,6 +510,16 @@ def run_ours(args):
                 "algorithmic_bytes_per_launch": alg, "bytes_per_cell": alg / nc, "kernel_ms": k_ms,
                 "kernel_share_of_step": kms.value / ms_total,
                 "step_algorithmic_frac": algorithmic_bytes(P, A.nnz, True) / (ms_total / args.steps * 1e-3) / 1e9 / peak}
+
+    # second bound of the tile kernels: the fp64 additions the copy engine performs at L2 (cp.reduce.async.bulk).  Its
+    # peak was measured in isolation with the kernel's operation shape (tools/micro/bulk_rate.cu,
+    # profiles/r02_n_bulk_rate.txt: 33 operations of 672 B per tile and CTA, two CTAs per SM -> 270 G fp64 adds/s)
+    slots = [e[1].get("stage_slots", 0) for e in getattr(A, "_tile_plans", {}).values() if e is not None and not e[1].get("vec")]
+    if fused and slots and slots[0] > 0:
+        roofline["reduce_engine"] = {"fp64_adds_per_launch": int(slots[0]), "achieved": slots[0] / (k_ms * 1e-3) / 1e9,
+                                     "peak": BULK_REDUCE_PEAK_GADDS, "unit": "G fp64 adds/s",
+                                     "frac": slots[0] / (k_ms * 1e-3) / 1e9 / BULK_REDUCE_PEAK_GADDS,
+                                     "peak_source": "measured in isolation, tools/micro/bulk_rate.cu (profiles/r02_n_bulk_rate.txt)"}
 
     # matrix-only / vector-only split of the step, timed separately after the main loop
     def timed(fn, reps=3):

@@ -1967,10 +1967,10 @@ int mpcx_tile_plan_info(const mpcx_tile_plan* plan, int64_t* out, int32_t n)
 {
   if (!plan || !out) return fail(MPCX_ERR_ARG, "null argument");
   const TilePlan* P = reinterpret_cast<const TilePlan*>(plan);
-  const int64_t v[15] = {P->nt, P->C, P->n_bulk, P->max_nodes, P->max_dests, P->total_nodes, P->total_dests, P->bytes,
+  const int64_t v[16] = {P->nt, P->C, P->n_bulk, P->max_nodes, P->max_dests, P->total_nodes, P->total_dests, P->bytes,
                          P->max_slots, P->total_slots, P->max_runs, P->total_runs, P->max_stage, P->sym,
-                         (P->n_iface + P->C - 1) / P->C};
-  for (int i = 0; i < n && i < 15; ++i) out[i] = v[i];
+                         (P->n_iface + P->C - 1) / P->C, P->total_stage};
+  for (int i = 0; i < n && i < 16; ++i) out[i] = v[i];
   return MPCX_OK;
 }
 

@@ -76,6 +76,7 @@ struct TilePlan
   int max_nodes = 0, max_dests = 0, max_slots = 0, max_runs = 0, max_stage = 0;
   long long n_iface = 0;  // bulk cells touching a ghost row: they fill the first ceil(n_iface / C) tiles
   long long nrows = 0, nvals = 0, n_bulk = 0, total_nodes = 0, total_dests = 0, total_slots = 0, total_runs = 0, bytes = 0;
+  long long total_stage = 0;  // staging positions over all tiles = fp64 adds the copy engine performs per assembly
   int *cell_pos = nullptr, *tile_node_off = nullptr, *node_ids = nullptr, *dest_k = nullptr, *tile_nd = nullptr,
       *tile_slots = nullptr, *tile_nr = nullptr, *tile_stage = nullptr;
   int2* runs = nullptr;
@@ -1394,6 +1395,7 @@ int tile_plan_build(const mpcx_mesh* mesh, const mpcx_dofmap* dm0, const mpcx_do
     P->total_runs += h_nr[t];
     P->max_runs = std::max(P->max_runs, h_nr[t]);
     P->max_stage = std::max(P->max_stage, h_st[t]);
+    P->total_stage += h_st[t];
     noff[t + 1] = noff[t] + h_nn[t];
     h_doff[t + 1] = h_doff[t] + ((h_nd[t] + 127) & ~127);  // 16-byte aligned dest / group records for the TMA bulk copies
     P->total_dests += h_nd[t];

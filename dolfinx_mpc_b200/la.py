@@ -209,10 +209,10 @@ class Matrix:
                                                               _dev.ptr(bc0_d), _dev.ptr(bc1_d), C.byref(m0), C.byref(m1),
                                                               C.byref(A), _dev.stream_ptr()))
                 _lib.check(lib.mpcx_device_error(_dev.stream_ptr()))
-            info = (C.c_int64 * 15)()
-            lib.mpcx_tile_plan_info(handle, info, 15)
+            info = (C.c_int64 * 16)()
+            lib.mpcx_tile_plan_info(handle, info, 16)
             self._tile_plans[key] = (handle, dict(zip(("tiles", "cells_per_tile", "bulk_cells", "max_nodes",
-                                                       "max_dests", "tile_nodes", "dests", "bytes", "max_slots", "slots", "max_runs", "runs", "max_stage", "symmetric", "interface_tiles"),
+                                                       "max_dests", "tile_nodes", "dests", "bytes", "max_slots", "slots", "max_runs", "runs", "max_stage", "symmetric", "interface_tiles", "stage_slots"),
                                                       [int(v) for v in info])))
         return self._tile_plans[key]
 

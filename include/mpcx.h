@@ -212,7 +212,8 @@ void mpcx_tile_plan_destroy(mpcx_tile_plan* plan);
  * total dest records, plan bytes read per assembly, max / total element-buffer slots, max / total runs
  * (= TMA bulk reductions per assembly), max staging positions per tile, 1 for a symmetric plan (same dofmap
  * and bc markers on both sides: upper-triangular records feed entry (r, c) and entry (c, r)); out[14] = number of
- * leading tiles that hold every cell touching a ghost row (0 without ghosts) */
+ * leading tiles that hold every cell touching a ghost row (0 without ghosts); out[15] = staging positions over all
+ * tiles = fp64 additions the copy engine performs per assembly (entries + the zero padding inside runs) */
 int mpcx_tile_plan_info(const mpcx_tile_plan* plan, int64_t* out, int32_t n);
 
 /* Optional: scatter plan for the cells holding slaves (integral->slave_cells), stored inside a matrix tile plan of a
