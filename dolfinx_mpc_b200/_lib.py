@@ -51,7 +51,8 @@ class IntegralS(C.Structure):
                 ("num_cells", C.c_int64), ("coeffs", C.c_void_p), ("cstride", C.c_int32),
                 ("coeff_nodal", C.c_void_p), ("coeff_dofmap", C.c_void_p), ("coeff_nd", C.c_int32),
                 ("coeff_bs", C.c_int32), ("num_constants", C.c_int32), ("constants", C.c_double * MAX_CONSTANTS),
-                ("slave_cells", C.c_void_p), ("num_slave_cells", C.c_int64), ("local_facets", C.c_void_p)]
+                ("slave_cells", C.c_void_p), ("num_slave_cells", C.c_int64), ("local_facets", C.c_void_p),
+                ("custom", C.c_void_p)]
 
 
 class PlanS(C.Structure):
@@ -65,7 +66,8 @@ class MpcHostS(C.Structure):
 
 # every symbol include/mpcx.h declares (tests check the library exports all of them)
 SYMBOLS = (
-    "mpcx_last_error", "mpcx_abi_version", "mpcx_device_error", "mpcx_device_error_async", "mpcx_zero_f64", "mpcx_assemble_matrix_f64",
+    "mpcx_last_error", "mpcx_abi_version", "mpcx_device_error", "mpcx_device_error_async", "mpcx_zero_f64", "mpcx_custom_kernel_create", "mpcx_custom_kernel_destroy",
+    "mpcx_assemble_matrix_f64",
     "mpcx_add_diagonal_f64", "mpcx_build_plan", "mpcx_assemble_vector_f64", "mpcx_apply_lifting_f64",
     "mpcx_backsubstitution_f64", "mpcx_homogenize_f64", "mpcx_gather_f64", "mpcx_scatter_add_f64",
     "mpcx_create_pattern_host", "mpcx_free_host", "mpcx_profile_enable", "mpcx_launch_count", "mpcx_profile_read",
@@ -102,6 +104,9 @@ def load():
     lib.mpcx_device_error.argtypes = [vp]
     lib.mpcx_device_error_async.argtypes = [vp, vp]
     lib.mpcx_zero_f64.argtypes = [vp, C.c_int64, vp]
+    lib.mpcx_custom_kernel_create.argtypes = [C.c_char_p, C.c_char_p, C.c_int32, C.c_int32, C.c_int32, C.POINTER(vp)]
+    lib.mpcx_custom_kernel_destroy.argtypes = [vp]
+    lib.mpcx_custom_kernel_destroy.restype = None
     lib.mpcx_assemble_matrix_f64.argtypes = [P(IntegralS), P(MeshS), P(DofmapS), P(DofmapS), vp, vp, P(MpcS),
                                              P(MpcS), P(CsrS), P(PlanS), vp]
     lib.mpcx_add_diagonal_f64.argtypes = [P(CsrS), vp, i64, f64, vp]

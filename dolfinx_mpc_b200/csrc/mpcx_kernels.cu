@@ -21,13 +21,14 @@
 #include <mutex>
 #include <algorithm>
 #include <vector>
+#include <string>
 #include <type_traits>
 
 #include "mpcx.h"
 
 namespace
 {
-thread_local char g_err[512] = "";
+thread_local char g_err[2048] = "";
 __device__ int g_dev_err = 0;
 
 // ---- instrumentation (bench.py): launch counter and CUDA-event bracket of the dominant kernel
@@ -124,6 +125,7 @@ struct IntD
   const int* slave_cells;
   long long nslave_cells;
   const int* lfacets;  // exterior-facet integral: local facet of every active entity
+  const double* pre;   // custom kernel: element tensors of all active entities, evaluated before the launch
 };
 
 // Tables of one entity: the cell itself, or local facet lfacets[index] of it (cpp/assemble_matrix.cpp:361-362)
@@ -336,6 +338,20 @@ __device__ void tabulate_warp(const Tab& t, int kernel, const double* c, const d
   __syncwarp();
 }
 
+// Element tensor of one entity into shared memory: a registry kernel evaluated by the warp, or the values a custom
+// kernel left in global memory (mpcx_custom_kernel, evaluated for all entities before this launch)
+__device__ __forceinline__ void element_tensor(const Tab& view, const IntD& in, long long index, const double* X,
+                                               const double* w, double* Ae, double* g, int ne, int lane)
+{
+  if (in.pre)
+  {
+    for (int e = lane; e < ne; e += 32) Ae[e] = __ldg(in.pre + index * ne + e);
+    __syncwarp();
+  }
+  else
+    tabulate_warp(view, in.kernel, in.c, X, w, Ae, g, lane);
+}
+
 // Loads geometry, dofs and coefficients of one cell into the warp's shared memory.
 __device__ __forceinline__ void load_cell(const MeshD& m, const IntD& in, long long index, int cell,
                                           double* X, double* w, int lane)
@@ -392,7 +408,7 @@ k_matrix_generic(Tab t, IntD in, MeshD mesh, const int* __restrict__ dm0, const 
     for (int e = lane; e < nd0; e += 32) d0[e] = __ldg(dm0 + (long long)cell * nd0 + e);
     for (int e = lane; e < nd1; e += 32) d1[e] = __ldg(dm1 + (long long)cell * nd1 + e);
     __syncwarp();
-    tabulate_warp(entity_view(t, in, index), in.kernel, in.c, X, w, Ae, g, lane);
+    element_tensor(entity_view(t, in, index), in, index, X, w, Ae, g, n0 * n1, lane);
     if (!has_slaves)
     {
       for (int e = lane; e < n0 * n1; e += 32)
@@ -471,7 +487,7 @@ k_vector_generic(Tab t, IntD in, MeshD mesh, const int* __restrict__ dm, int nd,
     __syncwarp();
     load_cell(mesh, in, index, cell, X, w, lane);
     __syncwarp();
-    tabulate_warp(entity_view(t, in, index), in.kernel, in.c, X, w, be, g, lane);
+    element_tensor(entity_view(t, in, index), in, index, X, w, be, g, n, lane);
     for (int e = lane; e < n; e += 32)
     {
       const int ib = e / bs, ia = e - ib * bs;
@@ -521,7 +537,7 @@ k_lifting_generic(Tab t, IntD in, MeshD mesh, const int* __restrict__ dm0, const
     if (!__any_sync(0xffffffffu, any)) continue;
     load_cell(mesh, in, index, cell, X, w, lane);
     __syncwarp();
-    tabulate_warp(entity_view(t, in, index), in.kernel, in.c, X, w, Ae, g, lane);  // un-zeroed A_e (cpp/lifting.h:266-299)
+    element_tensor(entity_view(t, in, index), in, index, X, w, Ae, g, n0 * n1, lane);  // un-zeroed A_e (cpp/lifting.h:266-299)
     for (int p = lane; p < n0; p += 32)
     {
       double v = 0.0;
@@ -1393,7 +1409,7 @@ k_matrix_generic_planned(Tab t, IntD in, MeshD mesh, int n0, int n1, const doubl
     __syncwarp();
     load_cell(mesh, in, index, cell, X, w, lane);
     __syncwarp();
-    tabulate_warp(entity_view(t, in, index), in.kernel, in.c, X, w, Ae, g, lane);
+    element_tensor(entity_view(t, in, index), in, index, X, w, Ae, g, n0 * n1, lane);
     for (long long k = k0 + lane; k < k1; k += 32)
     {
       const int a = __ldg(sp.ca + k), b = __ldg(sp.cb + k);
@@ -1501,6 +1517,7 @@ IntD make_int(const mpcx_integral* in)
   for (int i = 0; i < MPCX_MAX_CONSTANTS; ++i) d.c[i] = i < in->num_constants ? in->constants[i] : 0.0;
   d.slave_cells = in->slave_cells; d.nslave_cells = in->num_slave_cells;
   d.lfacets = in->local_facets;
+  d.pre = nullptr;
   return d;
 }
 
@@ -1512,7 +1529,16 @@ int check_integral(const mpcx_integral* in, bool bilinear)
   const bool is_div = k == MPCX_KERNEL_DIV_TEST || k == MPCX_KERNEL_DIV_TRIAL;
   const bool is_bilinear = k == MPCX_KERNEL_LAPLACE || k == MPCX_KERNEL_MASS || k == MPCX_KERNEL_ELASTICITY
                            || k == MPCX_KERNEL_LAPLACE_VARCOEF || is_div;
-  if (k < 0 || k > MPCX_KERNEL_DIV_TRIAL) return fail(MPCX_ERR_UNSUPPORTED, "unknown kernel id");
+  if (k < 0 || k > MPCX_KERNEL_CUSTOM) return fail(MPCX_ERR_UNSUPPORTED, "unknown kernel id");
+  if (k == MPCX_KERNEL_CUSTOM)  // rank = the routine it is passed to; sizes are checked against the handle there
+  {
+    if (!in->custom) return fail(MPCX_ERR_ARG, "MPCX_KERNEL_CUSTOM needs mpcx_integral.custom");
+    const mpcx_tables* tc = in->tables;
+    if (tc->tdim != tc->gdim || (tc->tdim != 2 && tc->tdim != 3))
+      return fail(MPCX_ERR_UNSUPPORTED, "only tdim == gdim in {2, 3} has device kernels");
+    if (in->local_facets && !in->cells) return fail(MPCX_ERR_ARG, "an exterior-facet integral needs the cells of its facets");
+    return MPCX_OK;
+  }
   if (bilinear != is_bilinear)
     return fail(MPCX_ERR_UNSUPPORTED, "kernel rank does not match the assembly routine");
   const mpcx_tables* t = in->tables;
@@ -1566,6 +1592,218 @@ int persistent_grid(const void* kern, size_t smem, int nt, int* grid)
 }  // namespace
 
 // ====================================================================== C ABI
+
+// ---------------------------------------------------------------------- custom element kernels (NVRTC)
+// NVRTC is bound at run time (dlopen), like NCCL: the library loads on machines without it.
+struct mpcx_custom_kernel
+{
+  std::vector<char> cubin;
+  std::string entry;
+  int ne = 0, ng = 0, nw = 0;
+  cudaLibrary_t lib = nullptr;
+  cudaKernel_t fn = nullptr;
+  double* scratch = nullptr;
+  size_t scratch_bytes = 0;
+};
+namespace
+{
+struct NvrtcApi
+{
+  void* lib = nullptr;
+  int (*CreateProgram)(void**, const char*, const char*, int, const char* const*, const char* const*) = nullptr;
+  int (*CompileProgram)(void*, int, const char* const*) = nullptr;
+  int (*GetCUBINSize)(void*, size_t*) = nullptr;
+  int (*GetCUBIN)(void*, char*) = nullptr;
+  int (*GetProgramLogSize)(void*, size_t*) = nullptr;
+  int (*GetProgramLog)(void*, char*) = nullptr;
+  int (*DestroyProgram)(void**) = nullptr;
+};
+NvrtcApi g_nvrtc;
+std::mutex g_nvrtc_mutex;
+
+int nvrtc_bind()
+{
+  std::lock_guard<std::mutex> lock(g_nvrtc_mutex);
+  if (g_nvrtc.lib) return MPCX_OK;
+  const char* names[] = {getenv("MPCX_NVRTC_LIB"), "libnvrtc.so.12", "libnvrtc.so", "/usr/local/cuda/lib64/libnvrtc.so.12",
+                         "/usr/local/cuda/lib64/libnvrtc.so"};
+  void* h = nullptr;
+  for (const char* n : names)
+    if (n && n[0] && (h = dlopen(n, RTLD_NOW | RTLD_GLOBAL))) break;
+  if (!h) return fail(MPCX_ERR_UNSUPPORTED, "custom kernels need NVRTC: libnvrtc.so not found (set MPCX_NVRTC_LIB)");
+  NvrtcApi a;
+  a.lib = h;
+  a.CreateProgram = (decltype(a.CreateProgram))dlsym(h, "nvrtcCreateProgram");
+  a.CompileProgram = (decltype(a.CompileProgram))dlsym(h, "nvrtcCompileProgram");
+  a.GetCUBINSize = (decltype(a.GetCUBINSize))dlsym(h, "nvrtcGetCUBINSize");
+  a.GetCUBIN = (decltype(a.GetCUBIN))dlsym(h, "nvrtcGetCUBIN");
+  a.GetProgramLogSize = (decltype(a.GetProgramLogSize))dlsym(h, "nvrtcGetProgramLogSize");
+  a.GetProgramLog = (decltype(a.GetProgramLog))dlsym(h, "nvrtcGetProgramLog");
+  a.DestroyProgram = (decltype(a.DestroyProgram))dlsym(h, "nvrtcDestroyProgram");
+  if (!a.CreateProgram || !a.CompileProgram || !a.GetCUBINSize || !a.GetCUBIN || !a.GetProgramLogSize || !a.GetProgramLog
+      || !a.DestroyProgram)
+    return fail(MPCX_ERR_UNSUPPORTED, "libnvrtc lacks a required entry point");
+  g_nvrtc = a;
+  return MPCX_OK;
+}
+
+// what is compiled: type names FFCx output uses, the user's source, and the thread-per-entity driver
+const char* k_custom_prelude = R"SRC(
+typedef unsigned char uint8_t; typedef signed char int8_t; typedef short int16_t; typedef unsigned short uint16_t;
+typedef int int32_t; typedef unsigned int uint32_t; typedef long long int64_t; typedef unsigned long long uint64_t;
+#define restrict __restrict__
+#ifndef M_PI
+#define M_PI 3.14159265358979323846
+#endif
+)SRC";
+const char* k_custom_driver = R"SRC(
+struct mpcx_consts { double c[8]; };
+extern "C" __global__ void mpcx_custom_tabulate(double* __restrict__ out, const double* __restrict__ coeffs, int cstride,
+                                                const double* __restrict__ wnodal, const int* __restrict__ wmap, int wnd,
+                                                int wbs, mpcx_consts consts, const double* __restrict__ x, int xs,
+                                                const int* __restrict__ xd, const int* __restrict__ cells,
+                                                const int* __restrict__ lfacets, long long n)
+{
+  const long long index = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (index >= n) return;
+  const int cell = cells ? cells[index] : (int)index;
+  double cd[3 * MPCX_NG];
+  for (int g = 0; g < MPCX_NG; ++g)
+  {
+    const double* p = x + (long long)xd[(long long)cell * MPCX_NG + g] * xs;
+    cd[3 * g] = p[0]; cd[3 * g + 1] = p[1]; cd[3 * g + 2] = p[2];
+  }
+  double w[MPCX_NW > 0 ? MPCX_NW : 1];
+  if (coeffs)
+    for (int e = 0; e < MPCX_NW && e < cstride; ++e) w[e] = coeffs[index * cstride + e];
+  else if (wnodal)
+    for (int e = 0; e < MPCX_NW && e < wnd * wbs; ++e) w[e] = wnodal[(long long)wmap[(long long)cell * wnd + e / wbs] * wbs + e % wbs];
+  double A[MPCX_NE];
+  for (int e = 0; e < MPCX_NE; ++e) A[e] = 0.0;
+  int lf = lfacets ? lfacets[index] : 0;
+  MPCX_ENTRY(A, w, consts.c, cd, &lf, (const uint8_t*)0);
+  for (int e = 0; e < MPCX_NE; ++e) out[index * MPCX_NE + e] = A[e];
+}
+)SRC";
+
+struct CustomConsts { double c[8]; };
+
+// Evaluates the custom kernel for all active entities of the integral into the handle's scratch array and points
+// in.pre at it.  expected_ne: n0 * n1 (matrix, lifting) or n (vector).
+int custom_prepare(const mpcx_integral* integral, const mpcx_mesh* mesh, int expected_ne, IntD& in, cudaStream_t s)
+{
+  if (integral->kernel != MPCX_KERNEL_CUSTOM) return MPCX_OK;
+  mpcx_custom_kernel* ck = const_cast<mpcx_custom_kernel*>(integral->custom);
+  if (!ck) return fail(MPCX_ERR_ARG, "MPCX_KERNEL_CUSTOM needs mpcx_integral.custom");
+  if (ck->ne != expected_ne || ck->ng != mesh->ng)
+    return fail(MPCX_ERR_ARG, "custom kernel was created for a different element tensor size / coordinate element");
+  const int nw = in.coeffs ? in.cstride : (in.wnodal ? in.wnd * in.wbs : 0);
+  if (nw > ck->nw) return fail(MPCX_ERR_ARG, "custom kernel was created for fewer coefficient values than the integral packs");
+  if (in.ncells <= 0) return MPCX_OK;
+  if (!ck->fn)
+  {
+    int rc = cuda_check(cudaLibraryLoadData(&ck->lib, ck->cubin.data(), nullptr, nullptr, 0, nullptr, nullptr, 0), "load custom kernel");
+    if (rc) return rc;
+    rc = cuda_check(cudaLibraryGetKernel(&ck->fn, ck->lib, "mpcx_custom_tabulate"), "custom kernel entry");
+    if (rc) return rc;
+  }
+  const size_t need = sizeof(double) * (size_t)in.ncells * (size_t)ck->ne;
+  if (need > ck->scratch_bytes)
+  {
+    if (ck->scratch) cudaFree(ck->scratch);
+    ck->scratch = nullptr; ck->scratch_bytes = 0;
+    if (cudaMalloc(&ck->scratch, need) != cudaSuccess)
+    {
+      (void)cudaGetLastError();
+      return fail(MPCX_ERR_ALLOC, "custom kernel: no room for the element tensors of all active entities (num_cells x num_entries doubles)");
+    }
+    ck->scratch_bytes = need;
+  }
+  CustomConsts cc;
+  for (int i = 0; i < 8; ++i) cc.c[i] = i < MPCX_MAX_CONSTANTS ? in.c[i] : 0.0;
+  double* out = ck->scratch;
+  const double* coeffs = in.coeffs;
+  int cstride = in.cstride;
+  const double* wnodal = in.coeffs ? nullptr : in.wnodal;
+  const int* wmap = in.wmap;
+  int wnd = in.wnd, wbs = in.wbs;
+  const double* x = mesh->x;
+  int xs = mesh->x_stride;
+  const int* xd = mesh->x_dofmap;
+  const int* cells = in.cells;
+  const int* lf = in.lfacets;
+  long long n = in.ncells;
+  void* args[] = {&out, &coeffs, &cstride, &wnodal, &wmap, &wnd, &wbs, &cc, &x, &xs, &xd, &cells, &lf, &n};
+  MPCX_COUNT_LAUNCH();
+  const int rc = cuda_check(cudaLaunchKernel((const void*)ck->fn, dim3((unsigned)((n + 127) / 128)), dim3(128), args, 0, s),
+                            "custom kernel launch");
+  if (rc) return rc;
+  in.pre = ck->scratch;
+  return MPCX_OK;
+}
+}  // namespace
+
+int mpcx_custom_kernel_create(const char* source, const char* entry, int32_t num_entries, int32_t num_coordinate_dofs,
+                              int32_t num_coefficient_values, mpcx_custom_kernel** kernel_out)
+{
+  if (!source || !entry || !kernel_out || num_entries < 1 || num_coordinate_dofs < 1 || num_coefficient_values < 0)
+    return fail(MPCX_ERR_ARG, "bad custom kernel arguments");
+  *kernel_out = nullptr;
+  int rc = nvrtc_bind();
+  if (rc) return rc;
+  std::string src = k_custom_prelude;
+  // the user's source without its #include lines (no system headers under NVRTC; the prelude has the fixed-width types)
+  for (const char* p = source; *p;)
+  {
+    const char* e = strchr(p, '\n');
+    const size_t len = e ? (size_t)(e - p) + 1 : strlen(p);
+    const char* q = p;
+    while (*q == ' ' || *q == '\t') ++q;
+    if (!(q[0] == '#' && strncmp(q + 1 + strspn(q + 1, " \t"), "include", 7) == 0)) src.append(p, len);
+    else src.append("\n");
+    p += len;
+  }
+  src += "\n";
+  src += k_custom_driver;
+  void* prog = nullptr;
+  if (g_nvrtc.CreateProgram(&prog, src.c_str(), "mpcx_custom.cu", 0, nullptr, nullptr) != 0)
+    return fail(MPCX_ERR_CUDA, "nvrtcCreateProgram failed");
+  const std::string d_ne = "-DMPCX_NE=" + std::to_string(num_entries), d_ng = "-DMPCX_NG=" + std::to_string(num_coordinate_dofs),
+                    d_nw = "-DMPCX_NW=" + std::to_string(num_coefficient_values), d_en = std::string("-DMPCX_ENTRY=") + entry;
+  const char* opts[] = {"--gpu-architecture=sm_100a", "-default-device", "-std=c++17", d_ne.c_str(), d_ng.c_str(), d_nw.c_str(),
+                        d_en.c_str()};
+  const int crc = g_nvrtc.CompileProgram(prog, 7, opts);
+  if (crc != 0)
+  {
+    size_t ls = 0;
+    g_nvrtc.GetProgramLogSize(prog, &ls);
+    std::string log(ls + 1, '\0');
+    if (ls) g_nvrtc.GetProgramLog(prog, &log[0]);
+    g_nvrtc.DestroyProgram(&prog);
+    snprintf(g_err, sizeof(g_err), "custom kernel does not compile: %.1900s", log.c_str());
+    return MPCX_ERR_ARG;
+  }
+  size_t cs = 0;
+  g_nvrtc.GetCUBINSize(prog, &cs);
+  mpcx_custom_kernel* ck = new mpcx_custom_kernel();
+  ck->cubin.resize(cs);
+  g_nvrtc.GetCUBIN(prog, ck->cubin.data());
+  g_nvrtc.DestroyProgram(&prog);
+  if (cs == 0) { delete ck; return fail(MPCX_ERR_CUDA, "NVRTC produced no code"); }
+  ck->entry = entry; ck->ne = num_entries; ck->ng = num_coordinate_dofs; ck->nw = num_coefficient_values;
+  *kernel_out = ck;
+  return MPCX_OK;
+}
+
+void mpcx_custom_kernel_destroy(mpcx_custom_kernel* kernel)
+{
+  if (!kernel) return;
+  if (kernel->scratch) cudaFree(kernel->scratch);
+  if (kernel->lib) cudaLibraryUnload(kernel->lib);
+  delete kernel;
+}
+
+
 extern "C" {
 
 const char* mpcx_last_error(void) { return g_err; }
@@ -1649,6 +1887,8 @@ int mpcx_assemble_matrix_f64(const mpcx_integral* integral, const mpcx_mesh* mes
   cudaStream_t s = (cudaStream_t)stream;
   const Tab tab = make_tab(t);
   IntD in = make_int(integral);
+  rc = custom_prepare(integral, mesh, t->nd * t->bs * nd1 * bs1, in, s);
+  if (rc) return rc;
   const MeshD md{mesh->x, mesh->x_dofmap, mesh->ng, mesh->x_stride};
   const MpcD m0 = make_mpc(mpc0), m1 = make_mpc(mpc1);
   const CsrD Ad{(const long long*)A->row_ptr, A->col, A->val};
@@ -1800,6 +2040,8 @@ int mpcx_assemble_vector_f64(const mpcx_integral* integral, const mpcx_mesh* mes
   cudaStream_t s = (cudaStream_t)stream;
   const Tab tab = make_tab(t);
   IntD in = make_int(integral);
+  rc = custom_prepare(integral, mesh, t->nd * t->bs, in, s);
+  if (rc) return rc;
   const MeshD md{mesh->x, mesh->x_dofmap, mesh->ng, mesh->x_stride};
   const MpcD m = make_mpc(mpc);
   const int nd = t->nd, bs = t->bs, n = nd * bs;
@@ -1868,6 +2110,8 @@ int mpcx_apply_lifting_f64(const mpcx_integral* integral, const mpcx_mesh* mesh,
   if (integral->num_cells == 0 || nlist <= 0) return MPCX_OK;
   const Tab tab = make_tab(t);
   IntD in = make_int(integral);
+  rc = custom_prepare(integral, mesh, t->nd * t->bs * nd1 * bs1, in, (cudaStream_t)stream);
+  if (rc) return rc;
   const MeshD md{mesh->x, mesh->x_dofmap, mesh->ng, mesh->x_stride};
   const int nd = t->nd, bs = t->bs, n = nd * bs;
   const int kid = integral->kernel;
@@ -2445,7 +2689,9 @@ int mpcx_assemble_slave_cells_f64(const mpcx_integral* integral, const mpcx_mesh
   if (plan->n0 != n0 || plan->n1 != n1 || plan->ncells != integral->num_slave_cells)
     return fail(MPCX_ERR_ARG, "slave plan was built for a different element or cell list");
   if (plan->ncells <= 0) return MPCX_OK;
-  const IntD in = make_int(integral);
+  IntD in = make_int(integral);
+  rc = custom_prepare(integral, mesh, n0 * n1, in, (cudaStream_t)stream);
+  if (rc) return rc;
   const MeshD md{mesh->x, mesh->x_dofmap, mesh->ng, mesh->x_stride};
   const int wcount = in.cstride > 0 ? in.cstride : 1;
   const int spw = 3 * mesh->ng + n0 * n1 + 3 * std::max(t->nd, nd1) + wcount + 1;

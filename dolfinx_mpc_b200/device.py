@@ -139,6 +139,11 @@ def integral_struct(form: Form, it: Integral, mpcs, keep: list) -> _lib.Integral
     s.num_constants = len(it.constants)
     for i, c in enumerate(it.constants):
         s.constants[i] = float(c)
+    if it.custom is not None:
+        n = 1
+        for Vk in form.function_spaces:
+            n *= Vk.nd * Vk.bs
+        s.custom = it.custom.handle(n, form.mesh.x_dofmap.shape[1], int(s.cstride))
     # active cells holding a slave of either constraint, as positions in the active list
     key = ("slave_cells",) + tuple(id(m) for m in mpcs)
     if key not in d:

@@ -35,6 +35,7 @@ class Kernel(enum.IntEnum):
     # rectangular blocks (test and trial spaces differ: python/tests/test_rectangular_assembly.py:83-86)
     DIV_TEST = 5  # c[0] * inner(p, div(v)) dx: test = vector space (bs == gdim), trial = scalar space
     DIV_TRIAL = 6  # c[0] * inner(div(u), q) dx: test = scalar space, trial = vector space (bs == gdim)
+    CUSTOM = 7  # Integral.custom: tabulate_tensor source compiled at run time (CustomKernel)
 
 
 @dataclasses.dataclass
@@ -232,12 +233,48 @@ def _qdegree(kernel: Kernel, cell_type: str, degree: int) -> int:
         return 2 * degree
     if kernel == Kernel.LAPLACE_VARCOEF:
         return 3 * degree - 2 if simplex else 3 * degree
+    if kernel == Kernel.CUSTOM:
+        return 1  # the tables only describe the element sizes to the library; the kernel has its own quadrature
     raise ValueError(kernel)
 
 
 def _qdegree_mixed(cell_type: str, degree0: int, degree1: int) -> int:
     """phi * d(phi'): sum of the degrees minus one on simplices (affine map), sum of the degrees on tensor cells."""
     return degree0 + degree1 - 1 if _el.is_simplex(cell_type) else degree0 + degree1
+
+
+class CustomKernel:
+    """An element kernel outside the registry: C / CUDA source defining
+    ``void <entry>(double* A, const double* w, const double* c, const double* coordinate_dofs, const int*
+    entity_local_index, const uint8_t* quadrature_permutation)`` -- the UFCx ``tabulate_tensor`` signature, i.e. what
+    ``a.kernel(IntegralType::cell, i, 0)`` hands the reference (``cpp/assemble_matrix.cpp:438-439, 620-636``); FFCx
+    output can be passed as generated.  Compiled on first use with NVRTC (``mpcx_custom_kernel_create``)."""
+
+    def __init__(self, source: str, entry: str):
+        self.source, self.entry = source, entry
+        self._handles = {}
+
+    def handle(self, num_entries: int, num_coordinate_dofs: int, num_coefficient_values: int):
+        from . import _lib
+
+        key = (num_entries, num_coordinate_dofs, num_coefficient_values)
+        if key not in self._handles:
+            import ctypes as C
+
+            h = C.c_void_p()
+            _lib.check(_lib.load().mpcx_custom_kernel_create(self.source.encode(), self.entry.encode(), num_entries,
+                                                            num_coordinate_dofs, num_coefficient_values, C.byref(h)))
+            self._handles[key] = h
+        return self._handles[key]
+
+    def __del__(self):
+        try:
+            from . import _lib
+
+            for h in self._handles.values():
+                _lib.load().mpcx_custom_kernel_destroy(h)
+        except Exception:
+            pass
 
 
 @dataclasses.dataclass
@@ -254,6 +291,7 @@ class Integral:
     integral_type: str = "cell"
     facets: Optional[np.ndarray] = None
     local_facets: Optional[np.ndarray] = None
+    custom: Optional[CustomKernel] = None  # kernel == Kernel.CUSTOM
 
     def __post_init__(self):
         self.constants = np.ascontiguousarray(self.constants, dtype=np.float64)
@@ -361,6 +399,16 @@ def source(V: FunctionSpace, f: Function, scale: float = 1.0, cells=None, facets
     or ``* ds`` over the given exterior facets (the traction term of ``python/tests/test_surface_integral.py:52-72``)."""
     assert f.function_space.bs == V.bs and f.function_space.nd == V.nd
     return Form(1, (V,), [Integral(Kernel.SOURCE, [scale], (f,), cells=cells, facets=facets)])
+
+
+def custom_form(spaces: Sequence[FunctionSpace], kernel: CustomKernel, constants=(), coefficients=(), cells=None,
+                facets=None) -> Form:
+    """A form whose element tensor comes from a :class:`CustomKernel` -- ``dolfinx.fem.form(any UFL expression)`` in
+    the reference: ``len(spaces)`` is the rank, ``coefficients`` are packed per cell in the order given (each
+    ``[nd][bs]``, as ``pack_coefficients`` does), ``constants`` fill ``c``."""
+    spaces = tuple(spaces)
+    return Form(len(spaces), spaces, [Integral(Kernel.CUSTOM, list(constants), tuple(coefficients), cells=cells, facets=facets,
+                                               custom=kernel)])
 
 
 def locate_exterior_facets(mesh: Mesh, marker=None) -> np.ndarray:

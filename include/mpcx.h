@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define MPCX_ABI_VERSION 5
+#define MPCX_ABI_VERSION 6
 #define MPCX_MAX_CONSTANTS 8
 
 typedef enum mpcx_status
@@ -53,8 +53,25 @@ typedef enum mpcx_kernel
   MPCX_KERNEL_SOURCE = 3,          /* c[0] * inner(f, v) dx (linear form); w = f at the cell dofs */
   MPCX_KERNEL_LAPLACE_VARCOEF = 4, /* c[0] * w * inner(grad u, grad v) dx; w scalar, same element */
   MPCX_KERNEL_DIV_TEST = 5,        /* c[0] * inner(p, div v) dx; test = vector element (bs == gdim), trial = scalar */
-  MPCX_KERNEL_DIV_TRIAL = 6        /* c[0] * inner(div u, q) dx; test = scalar element, trial = vector (bs1 == gdim) */
+  MPCX_KERNEL_DIV_TRIAL = 6,       /* c[0] * inner(div u, q) dx; test = scalar element, trial = vector (bs1 == gdim) */
+  MPCX_KERNEL_CUSTOM = 7           /* mpcx_integral.custom: a tabulate_tensor function compiled at run time (below) */
 } mpcx_kernel;
+
+/* The reference's opaque element kernel (`fn` of cpp/assemble_matrix.cpp:438-439, called at :505-506 and
+ * cpp/assemble_vector.cpp / cpp/lifting.h alike) for forms outside the registry above.  `source` is C / CUDA source
+ * that defines
+ *     void <entry>(double* A, const double* w, const double* c, const double* coordinate_dofs,
+ *                  const int* entity_local_index, const uint8_t* quadrature_permutation);
+ * -- the UFCx tabulate_tensor signature, so FFCx output can be passed as generated (its #include lines are dropped;
+ * functions without an execution space become device functions; `restrict` is accepted).  It is compiled once with
+ * NVRTC for sm_100a; an assembly first evaluates it for every active entity (thread per entity: coordinate_dofs
+ * [num_coordinate_dofs][3], w = the packed coefficients of the entity, A zeroed, num_entries values) into a scratch
+ * array owned by the handle, then the generic kernels eliminate and scatter as for a registry kernel.  The NVRTC log of
+ * a failed compilation is what mpcx_last_error() returns. */
+typedef struct mpcx_custom_kernel mpcx_custom_kernel;
+int mpcx_custom_kernel_create(const char* source, const char* entry, int32_t num_entries, int32_t num_coordinate_dofs,
+                              int32_t num_coefficient_values, mpcx_custom_kernel** kernel_out);
+void mpcx_custom_kernel_destroy(mpcx_custom_kernel* kernel);
 
 /* Tabulated element (what FFCx bakes into the generated kernel). */
 typedef struct mpcx_tables
@@ -152,6 +169,8 @@ typedef struct mpcx_integral
   /* exterior-facet integral: entity i is local facet local_facets[i] of cell cells[i] (the (cell, local facet)
    * pairs of cpp/assemble_matrix.cpp:343-348); NULL for a cell integral.  Needs tables->nfacets > 0. */
   const int32_t* local_facets;
+  /* kernel == MPCX_KERNEL_CUSTOM: the compiled element kernel (NULL otherwise) */
+  const mpcx_custom_kernel* custom;
 } mpcx_integral;
 
 /* Scatter plan: for every active cell and local entry (p, q) the offset of column

@@ -44,7 +44,8 @@ enum
   K_SOURCE = 3,
   K_LAPLACE_VARCOEF = 4,
   K_DIV_TEST = 5,  /* c0 * inner(p, div v) dx: test = vector element, trial = scalar element */
-  K_DIV_TRIAL = 6  /* c0 * inner(div u, q) dx: test = scalar element, trial = vector element */
+  K_DIV_TRIAL = 6, /* c0 * inner(div u, q) dx: test = scalar element, trial = vector element */
+  K_CUSTOM = 7     /* the function set with orc_set_custom_kernel: the reference's opaque `fn` itself */
 };
 
 /* Tabulated element: the tables an FFCx kernel has baked into its source. */
@@ -364,10 +365,24 @@ static void k_div_trial(double* A, const double* w, const double* c, const doubl
   div_coupling(A, c, X, (const orc_tables*)cd, 0);
 }
 
+/* A tabulate_tensor function handed in by the caller (UFCx signature without custom_data) -- what the reference
+ * receives from a.kernel(...) (cpp/assemble_matrix.cpp:438-439, 620-636).  Process-global: the tests set it before
+ * assembling a form of kind K_CUSTOM. */
+typedef void (*orc_custom_fn)(double* A, const double* w, const double* c, const double* coordinate_dofs,
+                              const int* entity_local_index, const uint8_t* quadrature_permutation);
+static orc_custom_fn g_custom_fn = NULL;
+void orc_set_custom_kernel(void* fn) { g_custom_fn = (orc_custom_fn)fn; }
+static void k_custom(double* A, const double* w, const double* c, const double* X, const int* e, const uint8_t* p, void* cd)
+{
+  (void)cd;
+  if (g_custom_fn) g_custom_fn(A, w, c, X, e, p);
+}
+
 static ufcx_kernel pick_kernel(int id)
 {
   switch (id)
   {
+  case K_CUSTOM: return k_custom;
   case K_LAPLACE: return k_laplace;
   case K_MASS: return k_mass;
   case K_ELASTICITY: return k_elasticity;
@@ -701,7 +716,7 @@ int orc_assemble_cells_vector(int kernel, const orc_tables* tab, const orc_mesh*
 {
   /* local_facets != NULL: exterior facets, cpp/assemble_vector.cpp:196-240 */
   ufcx_kernel fn = pick_kernel(kernel);
-  if (!fn || kernel != K_SOURCE) return ORC_ERR_KERNEL;
+  if (!fn || (kernel != K_SOURCE && kernel != K_CUSTOM)) return ORC_ERR_KERNEL;
   const int nd = dm->nd, bs = dm->bs, n = nd * bs, ng = mesh->ng;
   double* X = (double*)malloc(sizeof(double) * 3 * (size_t)ng);
   double* be = (double*)malloc(sizeof(double) * (size_t)n);

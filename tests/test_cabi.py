@@ -34,7 +34,7 @@ def test_library_exports_every_declared_symbol(lib):
     for name in declared:
         assert hasattr(lib, name), f"libmpcx.so does not export {name}"
     assert sorted(_lib.SYMBOLS) == declared, "ctypes binding and header disagree"
-    assert lib.mpcx_abi_version() == 5
+    assert lib.mpcx_abi_version() == 6
 
 
 def test_null_arguments_are_rejected_without_a_device(lib):

@@ -1,0 +1,185 @@
+"""Custom element kernels: the reference takes an opaque ``tabulate_tensor`` pointer from the form
+(``cpp/assemble_matrix.cpp:438-439, 505-506, 620-636``); here the same C source is compiled with NVRTC for the device
+(``mpcx_custom_kernel_create``) and with gcc for the oracle (``orc_set_custom_kernel``), and both sides must agree --
+on a form the registry also has (P1 Laplace on triangles) and on one it has not (a non-symmetric convection-diffusion-
+reaction operator with a vector-valued velocity coefficient, plus its load vector)."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+import problems
+from test_gpu_parity import _mpc, assert_csr_close, assert_vec_close
+
+# UFCx signature; closed forms (affine P1), so no tables are needed
+LAPLACE_P1_TRI = r"""
+#include <math.h>
+#include <stdint.h>
+void laplace_p1_tri(double* restrict A, const double* restrict w, const double* restrict c,
+                    const double* restrict x, const int* restrict entity_local_index,
+                    const uint8_t* restrict quadrature_permutation)
+{
+  const double J00 = x[3] - x[0], J01 = x[6] - x[0], J10 = x[4] - x[1], J11 = x[7] - x[1];
+  const double det = J00 * J11 - J01 * J10;
+  /* gradients of the barycentric coordinates */
+  const double g[3][2] = {{(J10 - J11) / det, (J01 - J00) / det}, {J11 / det, -J01 / det}, {-J10 / det, J00 / det}};
+  const double area = 0.5 * fabs(det);
+  for (int i = 0; i < 3; ++i)
+    for (int j = 0; j < 3; ++j) A[3 * i + j] += c[0] * area * (g[i][0] * g[j][0] + g[i][1] * g[j][1]);
+}
+"""
+
+# a(u, v) = kappa grad u . grad v + (beta . grad u) v + sigma u v on P1 tetrahedra, beta a P1 vector field (w[4][3]);
+# L(v) = s * f v with f a P1 scalar field (w[4])
+CDR_P1_TET = r"""
+#include <math.h>
+#include <stdint.h>
+static void tet_geometry(const double* x, double g[4][3], double* vol)
+{
+  double J[3][3];
+  for (int k = 0; k < 3; ++k)
+    for (int a = 0; a < 3; ++a) J[k][a] = x[3 * (a + 1) + k] - x[k];
+  const double det = J[0][0] * (J[1][1] * J[2][2] - J[1][2] * J[2][1]) - J[0][1] * (J[1][0] * J[2][2] - J[1][2] * J[2][0])
+                     + J[0][2] * (J[1][0] * J[2][1] - J[1][1] * J[2][0]);
+  /* rows of J^-1 = gradients of lambda_1..3 */
+  g[1][0] = (J[1][1] * J[2][2] - J[1][2] * J[2][1]) / det; g[1][1] = (J[0][2] * J[2][1] - J[0][1] * J[2][2]) / det;
+  g[1][2] = (J[0][1] * J[1][2] - J[0][2] * J[1][1]) / det;
+  g[2][0] = (J[1][2] * J[2][0] - J[1][0] * J[2][2]) / det; g[2][1] = (J[0][0] * J[2][2] - J[0][2] * J[2][0]) / det;
+  g[2][2] = (J[0][2] * J[1][0] - J[0][0] * J[1][2]) / det;
+  g[3][0] = (J[1][0] * J[2][1] - J[1][1] * J[2][0]) / det; g[3][1] = (J[0][1] * J[2][0] - J[0][0] * J[2][1]) / det;
+  g[3][2] = (J[0][0] * J[1][1] - J[0][1] * J[1][0]) / det;
+  for (int k = 0; k < 3; ++k) g[0][k] = -(g[1][k] + g[2][k] + g[3][k]);
+  *vol = fabs(det) / 6.0;
+}
+void cdr_p1_tet(double* restrict A, const double* restrict w, const double* restrict c, const double* restrict x,
+                const int* restrict entity_local_index, const uint8_t* restrict quadrature_permutation)
+{
+  double g[4][3], vol;
+  tet_geometry(x, g, &vol);
+  for (int i = 0; i < 4; ++i)
+    for (int j = 0; j < 4; ++j)
+    {
+      double v = c[0] * (g[i][0] * g[j][0] + g[i][1] * g[j][1] + g[i][2] * g[j][2]);
+      double conv = 0.0; /* sum_k (beta_k . grad phi_j) int phi_k phi_i / vol */
+      for (int k = 0; k < 4; ++k)
+        conv += (w[3 * k] * g[j][0] + w[3 * k + 1] * g[j][1] + w[3 * k + 2] * g[j][2]) * ((k == i ? 2.0 : 1.0) / 20.0);
+      v += conv + c[1] * ((i == j ? 2.0 : 1.0) / 20.0);
+      A[4 * i + j] += vol * v;
+    }
+}
+void load_p1_tet(double* restrict b, const double* restrict w, const double* restrict c, const double* restrict x,
+                 const int* restrict entity_local_index, const uint8_t* restrict quadrature_permutation)
+{
+  double g[4][3], vol;
+  tet_geometry(x, g, &vol);
+  for (int i = 0; i < 4; ++i)
+    for (int k = 0; k < 4; ++k) b[i] += c[0] * vol * w[k] * ((k == i ? 2.0 : 1.0) / 20.0);
+}
+"""
+
+
+def _host_fn(tmp_path, source: str, entry: str):
+    """The same source compiled for the host: the function pointer the reference would get from the form."""
+    src = tmp_path / f"{entry}.c"
+    src.write_text(source)
+    so = tmp_path / f"{entry}.so"
+    subprocess.run(["gcc", "-O2", "-std=c99", "-shared", "-fPIC", "-o", str(so), str(src), "-lm"], check=True)
+    lib = C.CDLL(str(so))
+    return lib, C.cast(getattr(lib, entry), C.c_void_p)
+
+
+def test_custom_kernel_compiles_and_reports_errors():
+    """NVRTC needs no GPU: the handle is created here; a source that does not compile raises with the compiler's log."""
+    from dolfinx_mpc_b200 import _lib
+
+    lib = _lib.load()
+    h = C.c_void_p()
+    _lib.check(lib.mpcx_custom_kernel_create(LAPLACE_P1_TRI.encode(), b"laplace_p1_tri", 9, 3, 0, C.byref(h)))
+    assert h.value
+    lib.mpcx_custom_kernel_destroy(h)
+    bad = LAPLACE_P1_TRI.replace("const double area", "const double area_ = undefined_symbol; const double area")
+    with pytest.raises(_lib.MpcxError) as e:
+        _lib.check(lib.mpcx_custom_kernel_create(bad.encode(), b"laplace_p1_tri", 9, 3, 0, C.byref(h)))
+    assert "undefined_symbol" in str(e.value)
+
+
+def test_oracle_custom_kernel_equals_registry(oracle, tmp_path):
+    """The oracle's K_CUSTOM path (the reference's opaque fn) reproduces its registry kernel for the same form."""
+    from dolfinx_mpc_b200 import fem
+
+    c = problems.ALL_CASES["periodic2d-P1-8-bc1"]()
+    m = oracle.mpc_from_arrays(c.V, c.data)
+    keep, fn = _host_fn(tmp_path, LAPLACE_P1_TRI, "laplace_p1_tri")
+    oracle.lib().orc_set_custom_kernel(fn)
+    a_c = fem.custom_form((c.V, c.V), fem.CustomKernel(LAPLACE_P1_TRI, "laplace_p1_tri"), constants=[1.0])
+    a_r = fem.laplace(c.V, 1.0)
+    rp, col, val = oracle.assemble_matrix(a_c, m, bcs=c.bcs)
+    rp_r, col_r, val_r = oracle.assemble_matrix(a_r, m, bcs=c.bcs)
+    assert_csr_close(rp, col, val, rp_r, col_r, val_r)
+    del keep
+
+
+@pytest.mark.gpu
+def test_custom_laplace_matches_registry_and_oracle(oracle, tmp_path):
+    import dolfinx_mpc_b200 as mpcx
+    from dolfinx_mpc_b200 import fem
+
+    c = problems.ALL_CASES["periodic2d-P1-8-bc1"]()
+    mpc = _mpc(c)
+    m = oracle.mpc_from_arrays(c.V, c.data)
+    a_c = fem.custom_form((c.V, c.V), fem.CustomKernel(LAPLACE_P1_TRI, "laplace_p1_tri"), constants=[1.0])
+    A = mpcx.assemble_matrix(a_c, mpc, bcs=c.bcs)
+    A_r = mpcx.assemble_matrix(fem.laplace(c.V, 1.0), mpc, bcs=c.bcs)
+    assert_csr_close(*A.getValuesCSR(), *A_r.getValuesCSR())
+    keep, fn = _host_fn(tmp_path, LAPLACE_P1_TRI, "laplace_p1_tri")
+    oracle.lib().orc_set_custom_kernel(fn)
+    assert_csr_close(*A.getValuesCSR(), *oracle.assemble_matrix(a_c, m, bcs=c.bcs))
+    mpcx.assemble_matrix(a_c, mpc, bcs=c.bcs, A=A)  # cached handle, plans and scratch
+    assert_csr_close(*A.getValuesCSR(), *A_r.getValuesCSR())
+    del keep
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", ["periodic3d-P1-bs1-4-ax2-bc1", "periodic3d-P1-bs1-3-ax3-bc0"])
+def test_custom_convection_diffusion_matches_oracle(oracle, tmp_path, name):
+    """A form the registry does not have: non-symmetric matrix with a vector coefficient, its lifting and a load vector
+    with a scalar coefficient, through MPC elimination and Dirichlet conditions, against the oracle running the SAME
+    source compiled for the host."""
+    import dolfinx_mpc_b200 as mpcx
+    from dolfinx_mpc_b200 import fem, generators as gen
+
+    c = problems.ALL_CASES[name]()
+    V = c.V
+    mpc = _mpc(c)
+    m = oracle.mpc_from_arrays(V, c.data)
+    W = gen.functionspace(V.mesh, 1, 3)
+    beta = fem.Function(W)
+    xb = np.asarray(V.mesh.x)[:, :3]
+    beta.array[:] = np.stack([1.0 + xb[:, 1], -0.5 + xb[:, 0] * xb[:, 2], 0.3 * np.cos(xb[:, 0])], axis=1).reshape(-1)[: len(beta.array)]
+    f = fem.Function(V)
+    f.array[:] = (np.sin(3 * xb[:, 0]) + xb[:, 1] * xb[:, 2])[: len(f.array)]
+    ka = fem.CustomKernel(CDR_P1_TET, "cdr_p1_tet")
+    kl = fem.CustomKernel(CDR_P1_TET, "load_p1_tet")
+    a = fem.custom_form((V, V), ka, constants=[0.7, 2.0], coefficients=[beta])
+    L = fem.custom_form((V,), kl, constants=[1.5], coefficients=[f])
+
+    keep_a, fn_a = _host_fn(tmp_path, CDR_P1_TET, "cdr_p1_tet")
+    A = mpcx.assemble_matrix(a, mpc, bcs=c.bcs)
+    oracle.lib().orc_set_custom_kernel(fn_a)
+    rp_o, col_o, val_o = oracle.assemble_matrix(a, m, bcs=c.bcs)
+    assert_csr_close(*A.getValuesCSR(), rp_o, col_o, val_o)
+    asym = A.to_scipy()
+    assert abs(asym - asym.T).max() > 1e-3  # the operator is not symmetric: nothing relied on symmetry
+
+    b = mpcx.assemble_vector(L, mpc)
+    keep_l = C.CDLL(keep_a._name)
+    oracle.lib().orc_set_custom_kernel(C.cast(keep_l.load_p1_tet, C.c_void_p))
+    b_o = oracle.assemble_vector(L, m)
+    assert_vec_close(b.array, b_o)
+    if c.bcs:
+        mpcx.apply_lifting(b, [a], [c.bcs], mpc)
+        oracle.lib().orc_set_custom_kernel(fn_a)
+        oracle.apply_lifting(b_o, [a], [c.bcs], m)
+        assert_vec_close(b.array, b_o)
