@@ -333,6 +333,11 @@ class Form:
             V1 = self.function_spaces[1]
             return _el.mixed_element_tables(self.mesh.cell_type, V.degree, V1.degree,
                                             _qdegree_mixed(self.mesh.cell_type, V.degree, V1.degree))
+        if (integral.kernel == Kernel.CUSTOM and self.rank == 2 and integral.integral_type == "cell"
+                and self.function_spaces[1].degree != V.degree):
+            # a custom kernel between different elements: the tables only carry the two elements' sizes
+            V1 = self.function_spaces[1]
+            return _el.mixed_element_tables(self.mesh.cell_type, V.degree, V1.degree, 1)
         make = _el.facet_tables if integral.integral_type == "exterior_facet" else _el.element_tables
         return make(self.mesh.cell_type, V.degree, _qdegree(integral.kernel, self.mesh.cell_type, V.degree))
 

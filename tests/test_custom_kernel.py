@@ -183,3 +183,79 @@ def test_custom_convection_diffusion_matches_oracle(oracle, tmp_path, name):
         oracle.lib().orc_set_custom_kernel(fn_a)
         oracle.apply_lifting(b_o, [a], [c.bcs], m)
         assert_vec_close(b.array, b_o)
+
+
+# Robin term int u v ds on a facet of a P1 tetrahedron (local facet f is opposite vertex f): the exterior-facet call
+# of cpp/assemble_matrix.cpp:361-362, entity_local_index = the local facet
+FACET_MASS_P1_TET = r"""
+#include <math.h>
+void facet_mass_p1_tet(double* restrict A, const double* restrict w, const double* restrict c, const double* restrict x,
+                       const int* restrict entity_local_index, const unsigned char* restrict quadrature_permutation)
+{
+  const int f = entity_local_index[0];
+  int v[3], n = 0;
+  for (int k = 0; k < 4; ++k)
+    if (k != f) v[n++] = k;
+  double e1[3], e2[3];
+  for (int k = 0; k < 3; ++k) { e1[k] = x[3 * v[1] + k] - x[3 * v[0] + k]; e2[k] = x[3 * v[2] + k] - x[3 * v[0] + k]; }
+  const double cx = e1[1] * e2[2] - e1[2] * e2[1], cy = e1[2] * e2[0] - e1[0] * e2[2], cz = e1[0] * e2[1] - e1[1] * e2[0];
+  const double area = 0.5 * sqrt(cx * cx + cy * cy + cz * cz);
+  for (int i = 0; i < 3; ++i)
+    for (int j = 0; j < 3; ++j) A[4 * v[i] + v[j]] += c[0] * area * ((i == j ? 2.0 : 1.0) / 12.0);
+}
+"""
+
+# plumbing check for a block between DIFFERENT elements (P2 vector test space x P1 scalar trial space): a kernel with
+# recognisable entries, the same on both sides
+PATTERN_RECT = r"""
+void pattern_rect(double* restrict A, const double* restrict w, const double* restrict c, const double* restrict x,
+                  const int* restrict entity_local_index, const unsigned char* restrict quadrature_permutation)
+{
+  const double s = x[3] - x[0] + 2.0 * (x[7] - x[1]);  /* depends on the cell */
+  for (int i = 0; i < 12; ++i)
+    for (int j = 0; j < 3; ++j) A[3 * i + j] += c[0] * (1.0 + i + 10.0 * j) * s;
+}
+"""
+
+
+@pytest.mark.gpu
+def test_custom_exterior_facet_kernel_matches_registry_and_oracle(oracle, tmp_path):
+    import dolfinx_mpc_b200 as mpcx
+    from dolfinx_mpc_b200 import fem
+
+    c = problems.ALL_CASES["surface-robin3d-P1"]()
+    V = c.V
+    mpc = _mpc(c)
+    m = oracle.mpc_from_arrays(V, c.data)
+    allf = fem.locate_exterior_facets(V.mesh)
+    k = fem.CustomKernel(FACET_MASS_P1_TET, "facet_mass_p1_tet")
+    a_c = fem.laplace(V) + fem.custom_form((V, V), k, constants=[1.5], facets=allf)
+    a_r = fem.laplace(V) + fem.mass(V, 1.5, facets=allf)
+    A = mpcx.assemble_matrix(a_c, mpc, bcs=c.bcs)
+    A_r = mpcx.assemble_matrix(a_r, mpc, bcs=c.bcs)
+    assert_csr_close(*A.getValuesCSR(), *A_r.getValuesCSR())
+    keep, fn = _host_fn(tmp_path, FACET_MASS_P1_TET, "facet_mass_p1_tet")
+    oracle.lib().orc_set_custom_kernel(fn)
+    assert_csr_close(*A.getValuesCSR(), *oracle.assemble_matrix(a_c, m, bcs=c.bcs))
+    del keep
+
+
+@pytest.mark.gpu
+def test_custom_kernel_between_different_elements(oracle, tmp_path):
+    import dolfinx_mpc_b200 as mpcx
+    from dolfinx_mpc_b200 import MultiPointConstraint, fem
+
+    sc = problems.case_stokes_2d()
+    mpc_v = MultiPointConstraint(sc.V)
+    mpc_v.add_constraint(sc.V, *sc.data_v)
+    mpc_v.finalize()
+    mpc_q = MultiPointConstraint(sc.Q)
+    mpc_q.finalize()
+    a01 = fem.custom_form((sc.V, sc.Q), fem.CustomKernel(PATTERN_RECT, "pattern_rect"), constants=[0.5])
+    A = mpcx.assemble_matrix(a01, [mpc_v, mpc_q], bcs=sc.bcs)
+    keep, fn = _host_fn(tmp_path, PATTERN_RECT, "pattern_rect")
+    oracle.lib().orc_set_custom_kernel(fn)
+    mv = oracle.mpc_from_arrays(sc.V, sc.data_v)
+    mq = oracle.OracleMPC.empty(sc.Q)
+    assert_csr_close(*A.getValuesCSR(), *oracle.assemble_matrix(a01, mv, mq, bcs=sc.bcs, same_space=False))
+    del keep
