@@ -259,3 +259,83 @@ def test_custom_kernel_between_different_elements(oracle, tmp_path):
     mq = oracle.OracleMPC.empty(sc.Q)
     assert_csr_close(*A.getValuesCSR(), *oracle.assemble_matrix(a01, mv, mq, bcs=sc.bcs, same_space=False))
     del keep
+
+
+# In the STYLE FFCx generates (function-scope static tables, quadrature loop, `restrict`, ufcx.h include): the mass
+# matrix of P1 on triangles with a 3-point degree-2 rule.  (FFCx itself is not installed here: hand-written after its
+# output format.)
+FFCX_STYLE_MASS_P1_TRI = r"""
+#include <math.h>
+#include <stdint.h>
+#include <ufcx.h>
+
+void tabulate_tensor_integral_mass_p1(double* restrict A,
+                                      const double* restrict w,
+                                      const double* restrict c,
+                                      const double* restrict coordinate_dofs,
+                                      const int* restrict entity_local_index,
+                                      const uint8_t* restrict quadrature_permutation)
+{
+// Quadrature rules
+static const double weights_e1b[3] = {0.1666666666666667, 0.1666666666666667, 0.1666666666666667};
+// Precomputed values of basis functions and precomputations
+// FE* dimensions: [permutation][entities][points][dofs]
+static const double FE0_C0_D10_Qe1b[1][1][1][3] = {{{{-1.0, 1.0, 0.0}}}};
+static const double FE0_C0_D01_Qe1b[1][1][1][3] = {{{{-1.0, 0.0, 1.0}}}};
+static const double FE1_C0_Qe1b[1][1][3][3] = {{{{0.6666666666666667, 0.1666666666666667, 0.1666666666666667},
+  {0.1666666666666667, 0.1666666666666667, 0.6666666666666667},
+  {0.1666666666666667, 0.6666666666666667, 0.1666666666666667}}}};
+// ------------------------
+// Section: Jacobian
+double J_c0 = 0.0;
+double J_c3 = 0.0;
+double J_c1 = 0.0;
+double J_c2 = 0.0;
+for (int ic = 0; ic < 3; ++ic)
+{
+  J_c0 += coordinate_dofs[(ic) * 3] * FE0_C0_D10_Qe1b[0][0][0][ic];
+  J_c3 += coordinate_dofs[(ic) * 3 + 1] * FE0_C0_D01_Qe1b[0][0][0][ic];
+  J_c1 += coordinate_dofs[(ic) * 3] * FE0_C0_D01_Qe1b[0][0][0][ic];
+  J_c2 += coordinate_dofs[(ic) * 3 + 1] * FE0_C0_D10_Qe1b[0][0][0][ic];
+}
+// ------------------------
+double sp_e1b_0 = J_c0 * J_c3;
+double sp_e1b_1 = J_c1 * J_c2;
+double sp_e1b_2 = -sp_e1b_1;
+double sp_e1b_3 = sp_e1b_0 + sp_e1b_2;
+double sp_e1b_4 = fabs(sp_e1b_3);
+double sp_e1b_5 = c[0] * sp_e1b_4;
+for (int iq = 0; iq < 3; ++iq)
+{
+  const double fw0 = sp_e1b_5 * weights_e1b[iq];
+  double t0[3];
+  for (int i = 0; i < 3; ++i)
+    t0[i] = fw0 * FE1_C0_Qe1b[0][0][iq][i];
+  for (int i = 0; i < 3; ++i)
+    for (int j = 0; j < 3; ++j)
+      A[3 * (i) + (j)] += FE1_C0_Qe1b[0][0][iq][j] * t0[i];
+}
+}
+"""
+
+
+def test_ffcx_style_source_compiles():
+    from dolfinx_mpc_b200 import _lib
+
+    h = C.c_void_p()
+    _lib.check(_lib.load().mpcx_custom_kernel_create(FFCX_STYLE_MASS_P1_TRI.encode(), b"tabulate_tensor_integral_mass_p1",
+                                                    9, 3, 0, C.byref(h)))
+    _lib.load().mpcx_custom_kernel_destroy(h)
+
+
+@pytest.mark.gpu
+def test_ffcx_style_mass_matches_registry(oracle):
+    import dolfinx_mpc_b200 as mpcx
+    from dolfinx_mpc_b200 import fem
+
+    c = problems.ALL_CASES["periodic2d-P1-8-bc1"]()
+    mpc = _mpc(c)
+    k = fem.CustomKernel(FFCX_STYLE_MASS_P1_TRI, "tabulate_tensor_integral_mass_p1")
+    A = mpcx.assemble_matrix(fem.custom_form((c.V, c.V), k, constants=[2.5]), mpc, bcs=c.bcs)
+    A_r = mpcx.assemble_matrix(fem.mass(c.V, 2.5), mpc, bcs=c.bcs)
+    assert_csr_close(*A.getValuesCSR(), *A_r.getValuesCSR())
