@@ -115,6 +115,36 @@ def test_row_gather_variants_match_oracle(oracle, monkeypatch, name, variant):
     assert_csr_close(*A.getValuesCSR(), rp_o, col_o, val_o)
 
 
+@pytest.mark.parametrize("cfg,n", [(3, 10), (5, 21)])
+def test_bench_configs_3_and_5_match_oracle(oracle, cfg, n):
+    """The problems `bench.py --config 3 / 5` builds (P2 elasticity with slip on the inclined face of the rotated cube;
+    two stacked boxes of P1 elasticity with a contact constraint), at a size the oracle finishes in seconds: matrix
+    (row-gather kernel + slave-cell plan), vector and lifting entry for entry, through the same three calls the bench
+    step makes."""
+    import bench
+    import dolfinx_mpc_b200 as mpcx
+
+    P = bench.build_config(cfg, n)
+    a, L, mpc, bcs = P["a"], P["L"], P["mpc"], P["bcs"]
+    V = mpc.function_space
+    m = oracle.WrappedMPC(V, mpc.is_slave, mpc.masters.array, mpc.coefficients()[0], mpc.masters.offsets,
+                          mpc.cell_to_slaves.array, mpc.cell_to_slaves.offsets, mpc.slaves, mpc.num_local_slaves)
+    A = mpcx.create_matrix(a, mpc)
+    b = mpcx.create_vector(mpc)
+    for _ in range(2):  # second pass through the cached plans
+        mpcx.assemble_matrix(a, mpc, bcs=bcs, A=A)
+        mpcx.assemble_vector(L, mpc, b=b)
+        if bcs:
+            mpcx.apply_lifting(b, [a], [bcs], mpc)
+    assert any(k[0] == "row" for k in A._tile_plans if isinstance(k, tuple)), "the row-gather path did not run"
+    rp_o, col_o, val_o = oracle.assemble_matrix(a, m, bcs=bcs)
+    assert_csr_close(*A.getValuesCSR(), rp_o, col_o, val_o)
+    b_o = oracle.assemble_vector(L, m)
+    if bcs:
+        oracle.apply_lifting(b_o, [a], [bcs], m)
+    assert_vec_close(b.array, b_o)
+
+
 @pytest.mark.parametrize("name", ["periodic2d-P1-8-bc1", "slip3d-P1-3", "contact3d"])
 def test_lifting_with_x0_and_scale(oracle, name):
     import dolfinx_mpc_b200 as mpcx
