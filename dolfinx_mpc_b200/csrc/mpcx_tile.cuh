@@ -157,6 +157,32 @@ struct BBox
   double lo[3], inv[3];
 };
 
+// sum over the (non-skipped) cells of the extents of their bounding boxes, per axis, and their number: the mean cell
+// size the Morton lattice is aligned with (tile_plan_build)
+__global__ void k_tp_cell_extent(MeshD mesh, const int* __restrict__ cells, long long nc, const int8_t* __restrict__ skip,
+                                 double* __restrict__ sum4)
+{
+  double a[4] = {0.0, 0.0, 0.0, 0.0};
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nc; i += (long long)gridDim.x * blockDim.x)
+  {
+    if (skip && skip[i]) continue;
+    const int cell = cells ? cells[i] : (int)i;
+    double lo[3] = {1e300, 1e300, 1e300}, hi[3] = {-1e300, -1e300, -1e300};
+    for (int g = 0; g < mesh.ng; ++g)
+    {
+      const double* p = mesh.x + (long long)mesh.xd[(long long)cell * mesh.ng + g] * mesh.xs;
+      for (int k = 0; k < 3; ++k) { lo[k] = p[k] < lo[k] ? p[k] : lo[k]; hi[k] = p[k] > hi[k] ? p[k] : hi[k]; }
+    }
+    for (int k = 0; k < 3; ++k) a[k] += hi[k] - lo[k];
+    a[3] += 1.0;
+  }
+  for (int k = 0; k < 4; ++k)
+  {
+    for (int o = 16; o > 0; o >>= 1) a[k] += __shfl_xor_sync(0xffffffffu, a[k], o);
+    if ((threadIdx.x & 31) == 0 && a[k] != 0.0) atomicAdd(sum4 + k, a[k]);
+  }
+}
+
 // Morton code of the cell centroid; skipped cells sort last
 // cells that touch a ghost row (a block >= first_ghost_block of dm) sort before all others: bit 61 clear / set
 #define MPCX_TP_INTERIOR_BIT (1ull << 61)
@@ -1343,6 +1369,44 @@ int tile_plan_build(const mpcx_mesh* mesh, const mpcx_dofmap* dm0, const mpcx_do
     {
       bb.lo[k] = dec_f64(h[k]);
       bb.inv[k] = ext > 0.0 ? 1.0 / ext : 0.0;
+    }
+    // Lattice ALIGNED with the cells: on a structured mesh (every Kuhn tetrahedron spans exactly one cube of the grid)
+    // the tiles should be unions of whole cubes, which they are when a cube is exactly 2^m Morton cells wide; with the
+    // plain bounding-box scale a 255-cube axis leaves every level of the curve cutting through cubes: 1.64 tiles per
+    // matrix entry and 0.44 tile vertices per cell instead of 1.46 and 0.37 (tools/complete_entries.py model; the
+    // same mesh with 256 cubes per axis is aligned by accident).  n_k = extent / (mean cell extent) cells along axis k,
+    // the same 2^m sub-cells per cell on every axis: isotropic in cell counts, hence in space for isotropic cells --
+    // the slab case of the comment above keeps its cubic tiles.  Unstructured meshes: harmless.  MPCX_TILE_ALIGN=0: off.
+    {
+      const char* al = getenv("MPCX_TILE_ALIGN");
+      double* sum4 = nullptr;
+      if (!(al && al[0] == '0') && nc > 0 && tp_alloc(&sum4, 4) == cudaSuccess)
+      {
+        double hs[4] = {0, 0, 0, 0};
+        cudaMemsetAsync(sum4, 0, sizeof(hs), s);
+        k_tp_cell_extent<<<148 * 4, 256, 0, s>>>(md, cells, nc, skip, sum4);
+        cudaMemcpyAsync(hs, sum4, sizeof(hs), cudaMemcpyDeviceToHost, s);
+        cudaStreamSynchronize(s);
+        cudaFree(sum4);
+        long long nk[3] = {1, 1, 1}, nmax = 1;
+        bool usable = hs[3] > 0.0;
+        for (int k = 0; k < 3 && usable; ++k)
+        {
+          const double ek = dec_f64(h[3 + k]) - dec_f64(h[k]), ck = hs[k] / hs[3];
+          if (ek > 0.0 && ck > 0.0) nk[k] = std::max(1ll, (long long)llround(ek / ck));
+          nmax = std::max(nmax, nk[k]);
+        }
+        if (usable && nmax <= (1ll << 19))
+        {
+          int m = 0;
+          while ((nmax << (m + 1)) <= (1ll << 20)) ++m;
+          for (int k = 0; k < 3; ++k)
+          {
+            const double ek = dec_f64(h[3 + k]) - dec_f64(h[k]);
+            bb.inv[k] = ek > 0.0 ? (double)(nk[k] << m) / (ek * 1048575.0) : 0.0;
+          }
+        }
+      }
     }
     // tuning: MPCX_TILE_STRETCH="fx,fy,fz" divides the Morton scale of an axis by f (tiles f times longer along it)
     if (const char* st = getenv("MPCX_TILE_STRETCH"))
