@@ -155,7 +155,28 @@ __device__ __forceinline__ unsigned long long spread21(unsigned long long v)
 struct BBox
 {
   double lo[3], inv[3];
+  int hilbert;  // 1: Hilbert curve instead of Morton order (MPCX_TILE_CURVE=hilbert)
 };
+
+// Skilling's transform: 20-bit coordinates -> "transposed" Hilbert index (interleave X[0], X[1], X[2], X[0] highest)
+__device__ __forceinline__ void hilbert_transpose(unsigned X[3])
+{
+  const unsigned M = 1u << 19;
+  for (unsigned Q = M; Q > 1; Q >>= 1)
+  {
+    const unsigned Pm = Q - 1;
+    for (int i = 0; i < 3; ++i)
+    {
+      if (X[i] & Q) X[0] ^= Pm;
+      else { const unsigned t = (X[0] ^ X[i]) & Pm; X[0] ^= t; X[i] ^= t; }
+    }
+  }
+  X[1] ^= X[0]; X[2] ^= X[1];
+  unsigned t = 0;
+  for (unsigned Q = M; Q > 1; Q >>= 1)
+    if (X[2] & Q) t ^= Q - 1;
+  X[0] ^= t; X[1] ^= t; X[2] ^= t;
+}
 
 // sum over the (non-skipped) cells of the extents of their bounding boxes, per axis, and their number: the mean cell
 // size the Morton lattice is aligned with (tile_plan_build)
@@ -205,12 +226,20 @@ __global__ void k_tp_cell_codes(MeshD mesh, BBox bb, const int* __restrict__ cel
     for (int k = 0; k < 3; ++k) c[k] += p[k];
   }
   unsigned long long m = 0;
+  unsigned q[3];
   for (int k = 0; k < 3; ++k)
   {
     double u = (c[k] / mesh.ng - bb.lo[k]) * bb.inv[k];
     u = u < 0.0 ? 0.0 : (u > 1.0 ? 1.0 : u);
-    m |= spread21((unsigned long long)(u * 1048575.0)) << k;  // 20 bits per axis: bits 60.. stay free
+    q[k] = (unsigned)(u * 1048575.0);  // 20 bits per axis: bits 60.. stay free
   }
+  if (bb.hilbert)
+  {
+    hilbert_transpose(q);
+    m = (spread21(q[0]) << 2) | (spread21(q[1]) << 1) | spread21(q[2]);
+  }
+  else
+    for (int k = 0; k < 3; ++k) m |= spread21(q[k]) << k;
   code[i] = m | (iface ? 0ull : MPCX_TP_INTERIOR_BIT);
 }
 
@@ -1330,6 +1359,10 @@ int tile_plan_build(const mpcx_mesh* mesh, const mpcx_dofmap* dm0, const mpcx_do
   bool fits = true;
   long long alloc_dests = 0;
   BBox bb;
+  {
+    const char* cv = getenv("MPCX_TILE_CURVE");
+    bb.hilbert = (cv && cv[0] == 'h') ? 1 : 0;
+  }
   int variant = 0;
   auto need_tmp = [&](size_t bytes) -> cudaError_t {
     if (bytes <= tmp_bytes) return cudaSuccess;
