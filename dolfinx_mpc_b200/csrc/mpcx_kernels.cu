@@ -125,7 +125,8 @@ struct IntD
   const int* slave_cells;
   long long nslave_cells;
   const int* lfacets;  // exterior-facet integral: local facet of every active entity
-  const double* pre;   // custom kernel: element tensors of all active entities, evaluated before the launch
+  const double* pre;   // custom kernel: element tensors of the active entities [pre_first, pre_first + pre_count),
+  long long pre_first, pre_count;  // evaluated before the launch; the generic kernels skip the entities outside
 };
 
 // Tables of one entity: the cell itself, or local facet lfacets[index] of it (cpp/assemble_matrix.cpp:361-362)
@@ -345,11 +346,17 @@ __device__ __forceinline__ void element_tensor(const Tab& view, const IntD& in, 
 {
   if (in.pre)
   {
-    for (int e = lane; e < ne; e += 32) Ae[e] = __ldg(in.pre + index * ne + e);
+    for (int e = lane; e < ne; e += 32) Ae[e] = __ldg(in.pre + (index - in.pre_first) * ne + e);
     __syncwarp();
   }
   else
     tabulate_warp(view, in.kernel, in.c, X, w, Ae, g, lane);
+}
+
+// custom kernel evaluated in chunks: is this entity outside the chunk whose tensors are in memory?
+__device__ __forceinline__ bool outside_chunk(const IntD& in, long long index)
+{
+  return in.pre && (index < in.pre_first || index >= in.pre_first + in.pre_count);
 }
 
 // Loads geometry, dofs and coefficients of one cell into the warp's shared memory.
@@ -399,6 +406,7 @@ k_matrix_generic(Tab t, IntD in, MeshD mesh, const int* __restrict__ dm0, const 
   for (long long it = (long long)blockIdx.x * (blockDim.x >> 5) + warp; it < nwork; it += wstride)
   {
     const long long index = mode == 1 ? (long long)__ldg(in.slave_cells + it) : it;
+    if (outside_chunk(in, index)) continue;
     const int cell = in.cells ? __ldg(in.cells + index) : (int)index;
     const bool has_slaves = (__ldg(m0.c2s_off + cell + 1) > __ldg(m0.c2s_off + cell))
                             || (__ldg(m1.c2s_off + cell + 1) > __ldg(m1.c2s_off + cell));
@@ -483,6 +491,7 @@ k_vector_generic(Tab t, IntD in, MeshD mesh, const int* __restrict__ dm, int nd,
   const long long wstride = (long long)gridDim.x * (blockDim.x >> 5);
   for (long long index = (long long)blockIdx.x * (blockDim.x >> 5) + warp; index < in.ncells; index += wstride)
   {
+    if (outside_chunk(in, index)) continue;
     const int cell = in.cells ? __ldg(in.cells + index) : (int)index;
     __syncwarp();
     load_cell(mesh, in, index, cell, X, w, lane);
@@ -523,6 +532,7 @@ k_lifting_generic(Tab t, IntD in, MeshD mesh, const int* __restrict__ dm0, const
   for (long long it = (long long)blockIdx.x * (blockDim.x >> 5) + warp; it < nlist; it += wstride)
   {
     const long long index = bc_cells ? (long long)__ldg(bc_cells + it) : it;
+    if (outside_chunk(in, index)) continue;
     const int cell = in.cells ? __ldg(in.cells + index) : (int)index;
     __syncwarp();
     bool any = false;  // cpp/lifting.h:93-109
@@ -1404,6 +1414,7 @@ k_matrix_generic_planned(Tab t, IntD in, MeshD mesh, int n0, int n1, const doubl
   for (long long it = (long long)blockIdx.x * (blockDim.x >> 5) + warp; it < in.nslave_cells; it += wstride)
   {
     const long long index = __ldg(in.slave_cells + it);
+    if (outside_chunk(in, index)) continue;
     const int cell = in.cells ? __ldg(in.cells + index) : (int)index;
     const long long k0 = __ldg(sp.off + it), k1 = __ldg(sp.off + it + 1);
     __syncwarp();
@@ -1517,7 +1528,7 @@ IntD make_int(const mpcx_integral* in)
   for (int i = 0; i < MPCX_MAX_CONSTANTS; ++i) d.c[i] = i < in->num_constants ? in->constants[i] : 0.0;
   d.slave_cells = in->slave_cells; d.nslave_cells = in->num_slave_cells;
   d.lfacets = in->local_facets;
-  d.pre = nullptr;
+  d.pre = nullptr; d.pre_first = 0; d.pre_count = 0;
   return d;
 }
 
@@ -1662,10 +1673,11 @@ extern "C" __global__ void mpcx_custom_tabulate(double* __restrict__ out, const 
                                                 const double* __restrict__ wnodal, const int* __restrict__ wmap, int wnd,
                                                 int wbs, mpcx_consts consts, const double* __restrict__ x, int xs,
                                                 const int* __restrict__ xd, const int* __restrict__ cells,
-                                                const int* __restrict__ lfacets, long long n)
+                                                const int* __restrict__ lfacets, long long first, long long n)
 {
-  const long long index = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (index >= n) return;
+  const long long slot = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (slot >= n) return;
+  const long long index = first + slot;
   const int cell = cells ? cells[index] : (int)index;
   double cd[3 * MPCX_NG];
   for (int g = 0; g < MPCX_NG; ++g)
@@ -1682,15 +1694,28 @@ extern "C" __global__ void mpcx_custom_tabulate(double* __restrict__ out, const 
   for (int e = 0; e < MPCX_NE; ++e) A[e] = 0.0;
   int lf = lfacets ? lfacets[index] : 0;
   MPCX_ENTRY(A, w, consts.c, cd, &lf, (const uint8_t*)0);
-  for (int e = 0; e < MPCX_NE; ++e) out[index * MPCX_NE + e] = A[e];
+  for (int e = 0; e < MPCX_NE; ++e) out[slot * MPCX_NE + e] = A[e];
 }
 )SRC";
 
 struct CustomConsts { double c[8]; };
 
-// Evaluates the custom kernel for all active entities of the integral into the handle's scratch array and points
-// in.pre at it.  expected_ne: n0 * n1 (matrix, lifting) or n (vector).
-int custom_prepare(const mpcx_integral* integral, const mpcx_mesh* mesh, int expected_ne, IntD& in, cudaStream_t s)
+// Entities per chunk of a custom-kernel assembly: the element tensors of a chunk live in the handle's scratch array
+// (MPCX_CUSTOM_SCRATCH_MB, default 4096 MB; MPCX_CUSTOM_CHUNK_CELLS overrides the count, used by the tests)
+long long custom_chunk(const mpcx_integral* integral, long long ncells)
+{
+  if (integral->kernel != MPCX_KERNEL_CUSTOM || !integral->custom || ncells <= 0) return ncells > 0 ? ncells : 1;
+  long long mb = 4096;
+  if (const char* e = getenv("MPCX_CUSTOM_SCRATCH_MB")) mb = atoll(e) > 0 ? atoll(e) : mb;
+  long long chunk = (mb << 20) / ((long long)sizeof(double) * integral->custom->ne);
+  if (const char* e = getenv("MPCX_CUSTOM_CHUNK_CELLS")) chunk = atoll(e) > 0 ? atoll(e) : chunk;
+  return std::max(1ll, std::min(chunk, ncells));
+}
+
+// Evaluates the custom kernel for the active entities [first, first + count) of the integral into the handle's scratch
+// array and points in.pre at it.  expected_ne: n0 * n1 (matrix, lifting) or n (vector).
+int custom_prepare(const mpcx_integral* integral, const mpcx_mesh* mesh, int expected_ne, IntD& in, cudaStream_t s,
+                   long long first, long long count)
 {
   if (integral->kernel != MPCX_KERNEL_CUSTOM) return MPCX_OK;
   mpcx_custom_kernel* ck = const_cast<mpcx_custom_kernel*>(integral->custom);
@@ -1699,7 +1724,7 @@ int custom_prepare(const mpcx_integral* integral, const mpcx_mesh* mesh, int exp
     return fail(MPCX_ERR_ARG, "custom kernel was created for a different element tensor size / coordinate element");
   const int nw = in.coeffs ? in.cstride : (in.wnodal ? in.wnd * in.wbs : 0);
   if (nw > ck->nw) return fail(MPCX_ERR_ARG, "custom kernel was created for fewer coefficient values than the integral packs");
-  if (in.ncells <= 0) return MPCX_OK;
+  if (count <= 0) return MPCX_OK;
   if (!ck->fn)
   {
     int rc = cuda_check(cudaLibraryLoadData(&ck->lib, ck->cubin.data(), nullptr, nullptr, 0, nullptr, nullptr, 0), "load custom kernel");
@@ -1707,7 +1732,7 @@ int custom_prepare(const mpcx_integral* integral, const mpcx_mesh* mesh, int exp
     rc = cuda_check(cudaLibraryGetKernel(&ck->fn, ck->lib, "mpcx_custom_tabulate"), "custom kernel entry");
     if (rc) return rc;
   }
-  const size_t need = sizeof(double) * (size_t)in.ncells * (size_t)ck->ne;
+  const size_t need = sizeof(double) * (size_t)count * (size_t)ck->ne;
   if (need > ck->scratch_bytes)
   {
     if (ck->scratch) cudaFree(ck->scratch);
@@ -1715,7 +1740,7 @@ int custom_prepare(const mpcx_integral* integral, const mpcx_mesh* mesh, int exp
     if (cudaMalloc(&ck->scratch, need) != cudaSuccess)
     {
       (void)cudaGetLastError();
-      return fail(MPCX_ERR_ALLOC, "custom kernel: no room for the element tensors of all active entities (num_cells x num_entries doubles)");
+      return fail(MPCX_ERR_ALLOC, "custom kernel: no room for the element tensors of one chunk (lower MPCX_CUSTOM_SCRATCH_MB)");
     }
     ck->scratch_bytes = need;
   }
@@ -1732,13 +1757,13 @@ int custom_prepare(const mpcx_integral* integral, const mpcx_mesh* mesh, int exp
   const int* xd = mesh->x_dofmap;
   const int* cells = in.cells;
   const int* lf = in.lfacets;
-  long long n = in.ncells;
-  void* args[] = {&out, &coeffs, &cstride, &wnodal, &wmap, &wnd, &wbs, &cc, &x, &xs, &xd, &cells, &lf, &n};
+  long long f0 = first, n = count;
+  void* args[] = {&out, &coeffs, &cstride, &wnodal, &wmap, &wnd, &wbs, &cc, &x, &xs, &xd, &cells, &lf, &f0, &n};
   MPCX_COUNT_LAUNCH();
   const int rc = cuda_check(cudaLaunchKernel((const void*)ck->fn, dim3((unsigned)((n + 127) / 128)), dim3(128), args, 0, s),
                             "custom kernel launch");
   if (rc) return rc;
-  in.pre = ck->scratch;
+  in.pre = ck->scratch; in.pre_first = first; in.pre_count = count;
   return MPCX_OK;
 }
 }  // namespace
@@ -1887,8 +1912,6 @@ int mpcx_assemble_matrix_f64(const mpcx_integral* integral, const mpcx_mesh* mes
   cudaStream_t s = (cudaStream_t)stream;
   const Tab tab = make_tab(t);
   IntD in = make_int(integral);
-  rc = custom_prepare(integral, mesh, t->nd * t->bs * nd1 * bs1, in, s);
-  if (rc) return rc;
   const MeshD md{mesh->x, mesh->x_dofmap, mesh->ng, mesh->x_stride};
   const MpcD m0 = make_mpc(mpc0), m1 = make_mpc(mpc1);
   const CsrD Ad{(const long long*)A->row_ptr, A->col, A->val};
@@ -1926,6 +1949,20 @@ int mpcx_assemble_matrix_f64(const mpcx_integral* integral, const mpcx_mesh* mes
       MPCX_COUNT_LAUNCH(), k_matrix_generic<uint8_t><<<grid, 128, smem, s>>>(tab, in, md, dofmap0->map, dofmap1->map, nd, nd1, bs, bs1, bc0, bc1,
                                                         m0, m1, Ad, (const uint8_t*)lpos, mode, spw);
   };
+  if (kid == MPCX_KERNEL_CUSTOM)
+  {
+    // a custom kernel: its element tensors are evaluated chunk by chunk into the handle's scratch array, each chunk
+    // followed by the generic kernels, which skip the entities outside it
+    const long long chunk = custom_chunk(integral, in.ncells);
+    for (long long first = 0; first < in.ncells; first += chunk)
+    {
+      rc = custom_prepare(integral, mesh, n * n1, in, s, first, std::min(chunk, in.ncells - first));
+      if (rc) return rc;
+      if (have_split && lpos) { launch_generic(2, in.ncells); launch_generic(1, in.nslave_cells); }
+      else launch_generic(0, in.ncells);
+    }
+    return cuda_check(cudaGetLastError(), "assemble_matrix launch");
+  }
   const bool fast_elasticity = lpos && have_split && kid == MPCX_KERNEL_ELASTICITY && p1_simplex && bs == t->tdim
                                && !integral->local_facets;
   const bool fast_p2_elasticity = lpos && have_split && kid == MPCX_KERNEL_ELASTICITY && t->tdim == 3 && bs == 3 && t->ng == 4
@@ -2040,8 +2077,6 @@ int mpcx_assemble_vector_f64(const mpcx_integral* integral, const mpcx_mesh* mes
   cudaStream_t s = (cudaStream_t)stream;
   const Tab tab = make_tab(t);
   IntD in = make_int(integral);
-  rc = custom_prepare(integral, mesh, t->nd * t->bs, in, s);
-  if (rc) return rc;
   const MeshD md{mesh->x, mesh->x_dofmap, mesh->ng, mesh->x_stride};
   const MpcD m = make_mpc(mpc);
   const int nd = t->nd, bs = t->bs, n = nd * bs;
@@ -2089,7 +2124,13 @@ int mpcx_assemble_vector_f64(const mpcx_integral* integral, const mpcx_mesh* mes
     const int wcount = in.cstride > 0 ? in.cstride : 1;
     const int spw = 3 * mesh->ng + n + 3 * nd + wcount + 1;
     const size_t smem = (size_t)spw * 4 * sizeof(double);
-    MPCX_COUNT_LAUNCH(), k_vector_generic<<<grid_for_warps(in.ncells, 4), 128, smem, s>>>(tab, in, md, dofmap->map, nd, bs, m, b, spw);
+    const long long chunk = custom_chunk(integral, in.ncells);
+    for (long long first = 0; first < in.ncells; first += chunk)
+    {
+      rc = custom_prepare(integral, mesh, n, in, s, first, std::min(chunk, in.ncells - first));
+      if (rc) return rc;
+      MPCX_COUNT_LAUNCH(), k_vector_generic<<<grid_for_warps(in.ncells, 4), 128, smem, s>>>(tab, in, md, dofmap->map, nd, bs, m, b, spw);
+    }
   }
   return cuda_check(cudaGetLastError(), "assemble_vector launch");
 }
@@ -2110,8 +2151,6 @@ int mpcx_apply_lifting_f64(const mpcx_integral* integral, const mpcx_mesh* mesh,
   if (integral->num_cells == 0 || nlist <= 0) return MPCX_OK;
   const Tab tab = make_tab(t);
   IntD in = make_int(integral);
-  rc = custom_prepare(integral, mesh, t->nd * t->bs * nd1 * bs1, in, (cudaStream_t)stream);
-  if (rc) return rc;
   const MeshD md{mesh->x, mesh->x_dofmap, mesh->ng, mesh->x_stride};
   const int nd = t->nd, bs = t->bs, n = nd * bs;
   const int kid = integral->kernel;
@@ -2140,9 +2179,15 @@ int mpcx_apply_lifting_f64(const mpcx_integral* integral, const mpcx_mesh* mesh,
     rc = cuda_check(cudaFuncSetAttribute(k_lifting_generic, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "smem attr");
     if (rc) return rc;
   }
-  MPCX_COUNT_LAUNCH(), k_lifting_generic<<<grid_for_warps(nlist, 4), 128, smem, (cudaStream_t)stream>>>(
-      tab, in, md, dofmap0->map, dofmap1->map, nd, nd1, bs, bs1, bc_markers1, bc_values1, x0, scale, make_mpc(mpc0),
-      bc_cells, nlist, b, spw);
+  const long long chunk = custom_chunk(integral, in.ncells);
+  for (long long first = 0; first < in.ncells; first += chunk)
+  {
+    rc = custom_prepare(integral, mesh, n * n1, in, (cudaStream_t)stream, first, std::min(chunk, in.ncells - first));
+    if (rc) return rc;
+    MPCX_COUNT_LAUNCH(), k_lifting_generic<<<grid_for_warps(nlist, 4), 128, smem, (cudaStream_t)stream>>>(
+        tab, in, md, dofmap0->map, dofmap1->map, nd, nd1, bs, bs1, bc_markers1, bc_values1, x0, scale, make_mpc(mpc0),
+        bc_cells, nlist, b, spw);
+  }
   return cuda_check(cudaGetLastError(), "apply_lifting launch");
 }
 
@@ -2690,8 +2735,6 @@ int mpcx_assemble_slave_cells_f64(const mpcx_integral* integral, const mpcx_mesh
     return fail(MPCX_ERR_ARG, "slave plan was built for a different element or cell list");
   if (plan->ncells <= 0) return MPCX_OK;
   IntD in = make_int(integral);
-  rc = custom_prepare(integral, mesh, n0 * n1, in, (cudaStream_t)stream);
-  if (rc) return rc;
   const MeshD md{mesh->x, mesh->x_dofmap, mesh->ng, mesh->x_stride};
   const int wcount = in.cstride > 0 ? in.cstride : 1;
   const int spw = 3 * mesh->ng + n0 * n1 + 3 * std::max(t->nd, nd1) + wcount + 1;
@@ -2702,9 +2745,15 @@ int mpcx_assemble_slave_cells_f64(const mpcx_integral* integral, const mpcx_mesh
     if (rc) return rc;
   }
   const SlavePlanD sp{plan->off, plan->ent, plan->pos, plan->ca, plan->cb};
-  MPCX_COUNT_LAUNCH();
-  k_matrix_generic_planned<<<grid_for_warps(plan->ncells, 4), 128, smem, (cudaStream_t)stream>>>(make_tab(t), in, md, n0, n1, mpc0->coeffs,
-                                                                                                 mpc1->coeffs, sp, A->val, spw);
+  const long long chunk = custom_chunk(integral, in.ncells);
+  for (long long first = 0; first < in.ncells; first += chunk)
+  {
+    rc = custom_prepare(integral, mesh, n0 * n1, in, (cudaStream_t)stream, first, std::min(chunk, in.ncells - first));
+    if (rc) return rc;
+    MPCX_COUNT_LAUNCH();
+    k_matrix_generic_planned<<<grid_for_warps(plan->ncells, 4), 128, smem, (cudaStream_t)stream>>>(make_tab(t), in, md, n0, n1, mpc0->coeffs,
+                                                                                                   mpc1->coeffs, sp, A->val, spw);
+  }
   return cuda_check(cudaGetLastError(), "assemble_slave_cells launch");
 }
 

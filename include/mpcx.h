@@ -66,7 +66,8 @@ typedef enum mpcx_kernel
  * functions without an execution space become device functions; `restrict` is accepted).  It is compiled once with
  * NVRTC for sm_100a; an assembly first evaluates it for every active entity (thread per entity: coordinate_dofs
  * [num_coordinate_dofs][3], w = the packed coefficients of the entity, A zeroed, num_entries values) into a scratch
- * array owned by the handle, then the generic kernels eliminate and scatter as for a registry kernel.  The NVRTC log of
+ * array owned by the handle -- in chunks of entities bounded by MPCX_CUSTOM_SCRATCH_MB (default 4096) --, each chunk
+ * followed by the generic kernels, which eliminate and scatter as for a registry kernel.  The NVRTC log of
  * a failed compilation is what mpcx_last_error() returns. */
 typedef struct mpcx_custom_kernel mpcx_custom_kernel;
 int mpcx_custom_kernel_create(const char* source, const char* entry, int32_t num_entries, int32_t num_coordinate_dofs,

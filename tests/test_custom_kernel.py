@@ -142,14 +142,18 @@ def test_custom_laplace_matches_registry_and_oracle(oracle, tmp_path):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("chunk_cells", [None, "37"])
 @pytest.mark.parametrize("name", ["periodic3d-P1-bs1-4-ax2-bc1", "periodic3d-P1-bs1-3-ax3-bc0"])
-def test_custom_convection_diffusion_matches_oracle(oracle, tmp_path, name):
+def test_custom_convection_diffusion_matches_oracle(oracle, tmp_path, monkeypatch, name, chunk_cells):
     """A form the registry does not have: non-symmetric matrix with a vector coefficient, its lifting and a load vector
     with a scalar coefficient, through MPC elimination and Dirichlet conditions, against the oracle running the SAME
-    source compiled for the host."""
+    source compiled for the host.  ``chunk_cells``: the element tensors evaluated 37 cells at a time (the scratch array
+    of a custom kernel is bounded, MPCX_CUSTOM_SCRATCH_MB), every chunk followed by the elimination / scatter kernels."""
     import dolfinx_mpc_b200 as mpcx
     from dolfinx_mpc_b200 import fem, generators as gen
 
+    if chunk_cells:
+        monkeypatch.setenv("MPCX_CUSTOM_CHUNK_CELLS", chunk_cells)
     c = problems.ALL_CASES[name]()
     V = c.V
     mpc = _mpc(c)
