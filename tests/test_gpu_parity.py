@@ -507,6 +507,31 @@ def test_assemble_system_matches_oracle(oracle, name):
     assert_vec_close(b.array, b_o)
 
 
+@pytest.mark.parametrize("switch", [{"MPCX_TILE_CURVE": "hilbert"}, {"MPCX_TILE_ALIGN": "0"},
+                                    {"MPCX_TILE_CURVE": "hilbert", "MPCX_TILE_ALIGN": "0"}],
+                         ids=["hilbert", "bounding-box-scale", "hilbert+bounding-box-scale"])
+@pytest.mark.parametrize("name", ["periodic3d-P1-bs1-4-ax2-bc1", "periodic2d-P1-8-bc1"])
+def test_tile_order_switches_keep_parity(oracle, monkeypatch, name, switch):
+    """The order of the cells along the space-filling curve (Morton on the cell-aligned lattice by default; Hilbert, or the
+    plain bounding-box scale, behind switches: profiles/README.md r02_r) changes the tile plans, never the result."""
+    import dolfinx_mpc_b200 as mpcx
+
+    for k, v in switch.items():
+        monkeypatch.setenv(k, v)
+    c = problems.ALL_CASES[name]()
+    mpc = _mpc(c)
+    m = oracle.mpc_from_arrays(c.V, c.data)
+    a_lift = c.a_lift if c.a_lift is not None else c.a
+    bcs = c.bcs if c.a_lift is not None else []
+    A, b = mpcx.assemble_system(c.a, c.L, mpc, bcs=bcs)  # fused kernel, or the separate tile kernels: same plans
+    assert A._tile_plans, "no tile plan was built"
+    assert_csr_close(*A.getValuesCSR(), *oracle.assemble_matrix(c.a, m, bcs=bcs))
+    b_o = oracle.assemble_vector(c.L, m)
+    if bcs:
+        oracle.apply_lifting(b_o, [a_lift], [bcs], m)
+    assert_vec_close(b.array, b_o)
+
+
 def test_fused_system_general_plan_and_scrambled_mesh(oracle):
     """The fused kernel on a mesh with scrambled node / cell numbering, once with the symmetric matrix plan and once
     with the general one (MPCX_TILE_SYM=0), variable-coefficient Laplace + source sharing one coefficient."""
