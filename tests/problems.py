@@ -253,6 +253,40 @@ def case_stokes_2d(n=4, theta=np.pi / 4, cell="triangle"):
     return StokesCase(V, Q, a, L, data_v, bcs)
 
 
+def case_vector_poisson_cross_component(n=5):
+    """python/tests/test_vector_poisson.py:25-133: block size 2, the slave in sub-space 0 and its master in sub-space 1
+    (two such pairs, one with two masters), Dirichlet condition on one wall in both components + lifting."""
+    mesh = gen.create_unit_square(n, n)
+    V = gen.functionspace(mesh, 1, 2)
+    X = V.tabulate_dof_coordinates()
+    wall = np.flatnonzero(np.isclose(X[:, 0], 0.0))
+    bc_dofs = (wall[:, None] * 2 + np.arange(2)[None, :]).reshape(-1).astype(np.int32)
+    bcs = [fem.DirichletBC(V, bc_dofs, 0.1)]
+    h = 1.0 / n
+    data = gen.general_constraint(V, {(1.0, 0.0): {(1.0, 1.0): 0.1, (1.0 - h, 1.0): 0.3}, (1.0, 2 * h): {(1.0, 1.0 - h): 0.7}},
+                                  comp_slave=0, comp_master=1)
+    a = fem.laplace(V) + fem.mass(V, 0.5)
+    return Case("vector-poisson-cross-component", V, a, _source(V, _vec(_f2d, 2)), data, bcs, a_lift=a)
+
+
+def case_hex_elasticity(n=3):
+    """python/tests/test_cube_contact.py:163-302 in small: Q1 hexahedra, vector elasticity (bs 3), the top plane of the
+    cube tied component-wise to the bottom plane (periodic in z), Dirichlet on the wall x = 0."""
+    mesh = gen.create_unit_cube(n, n, n, "hexahedron")
+    V = gen.functionspace(mesh, 1, 3)
+    X = V.tabulate_dof_coordinates()
+    wall = np.flatnonzero(np.isclose(X[:, 0], 0.0))
+    bc_dofs = (wall[:, None] * 3 + np.arange(3)[None, :]).reshape(-1).astype(np.int32)
+    bcs = [fem.DirichletBC(V, bc_dofs, 0.0)]
+    data = gen.periodic_constraint(V, axes=(2,), exclude_dofs=bc_dofs)
+    a = fem.elasticity(V, 3.0, 1.5)
+    return Case("hex-elasticity-periodic", V, a, _source(V, _vec(_f3d, 3)), data, bcs, a_lift=a)
+
+
+# cases checked on the oracle only (tests/test_oracle.py): more of the reference's test configurations
+ORACLE_ONLY_CASES = {"vector-poisson-cross-component": case_vector_poisson_cross_component,
+                     "hex-elasticity-periodic": case_hex_elasticity}
+
 ALL_CASES: dict = {}
 for _c in (
     lambda: case_general_2d("triangle", 1), lambda: case_general_2d("triangle", 2),
