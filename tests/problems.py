@@ -283,10 +283,6 @@ def case_hex_elasticity(n=3):
     return Case("hex-elasticity-periodic", V, a, _source(V, _vec(_f3d, 3)), data, bcs, a_lift=a)
 
 
-# cases checked on the oracle only (tests/test_oracle.py): more of the reference's test configurations
-ORACLE_ONLY_CASES = {"vector-poisson-cross-component": case_vector_poisson_cross_component,
-                     "hex-elasticity-periodic": case_hex_elasticity}
-
 ALL_CASES: dict = {}
 for _c in (
     lambda: case_general_2d("triangle", 1), lambda: case_general_2d("triangle", 2),
@@ -299,6 +295,7 @@ for _c in (
     case_contact_3d, lambda: case_tie_2d(6, 2), lambda: case_tie_2d(5, 1), case_lifting_single_quad,
     case_varcoef_subdomains, case_empty, case_hex, case_surface_traction_2d,
     lambda: case_surface_robin_3d(3, 1), lambda: case_surface_robin_3d(2, 2),
+    case_vector_poisson_cross_component, case_hex_elasticity,
 ):
     _k = _c()
     ALL_CASES[_k.name] = _c

@@ -93,9 +93,9 @@ def test_mpc_build_matches_product_finalize(oracle):
         assert np.array_equal(mpc.cell_to_slaves.array, m.c2s)
 
 
-@pytest.mark.parametrize("name", list(problems.ALL_CASES) + list(problems.ORACLE_ONLY_CASES))
+@pytest.mark.parametrize("name", list(problems.ALL_CASES))
 def test_oracle_satisfies_reference_identities(oracle, name):
-    c = (problems.ALL_CASES.get(name) or problems.ORACLE_ONLY_CASES[name])()
+    c = problems.ALL_CASES[name]()
     n = c.V.num_dofs
     m = oracle.mpc_from_arrays(c.V, c.data)
     e = oracle.OracleMPC.empty(c.V)
